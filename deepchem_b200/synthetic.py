@@ -1,0 +1,188 @@
+"""Seeded synthetic molecule streams shaped like the datasets BASELINE.json names.
+
+No RDKit and no network exist on the build or GPU boxes, so every benchmark / parity input
+is generated here directly at the featurizer's *output* contract
+(``ConvMol(atom_features, adj_list)``, deepchem/feat/graph_features.py:698 ->
+deepchem/feat/mol_graphs.py:48) in the packed shard format the host layout builder
+consumes (see ``PackedMols``).
+
+Shapes:
+  zinc      atoms/mol ~ clip(Poisson(25), 6, 50), random spanning tree with valence cap 4
+            plus 0-3 ring closures (mean degree ~2.1-2.2), 75 0/1 features (~8 ones/row)
+  stress    as zinc but with a heavy-degree tail up to 10 and degree-0 singleton
+            molecules, so that all 11 degree buckets are populated
+  delaney   13.3 atoms/mol,  tox21  18.5 atoms/mol,  qm9  4-9 atoms/mol
+"""
+import numpy as np
+
+
+class PackedMols(object):
+    """A shard of molecules with no Python objects inside.
+
+    atom_ptr [B+1] int32   first atom of each molecule in the concatenated arrays
+    adj_ptr  [N+1] int32   CSR over atoms (concatenated, in each molecule's own order)
+    adj_idx  [E]   int32   neighbour ids, molecule-local, in adjacency-list order
+    features [N,F] float32
+    """
+
+    __slots__ = ("atom_ptr", "adj_ptr", "adj_idx", "features")
+
+    def __init__(self, atom_ptr, adj_ptr, adj_idx, features):
+        self.atom_ptr = np.ascontiguousarray(atom_ptr, dtype=np.int32)
+        self.adj_ptr = np.ascontiguousarray(adj_ptr, dtype=np.int32)
+        self.adj_idx = np.ascontiguousarray(adj_idx, dtype=np.int32)
+        self.features = np.ascontiguousarray(features, dtype=np.float32)
+
+    @property
+    def n_mols(self):
+        return self.atom_ptr.shape[0] - 1
+
+    @property
+    def n_atoms(self):
+        return int(self.atom_ptr[-1])
+
+    @property
+    def n_feat(self):
+        return self.features.shape[1]
+
+    def __len__(self):
+        return self.n_mols
+
+    def mol(self, i):
+        """(features [n,F], adj_list list-of-lists) of molecule i."""
+        a0, a1 = int(self.atom_ptr[i]), int(self.atom_ptr[i + 1])
+        adj = [self.adj_idx[self.adj_ptr[a]:self.adj_ptr[a + 1]].tolist() for a in range(a0, a1)]
+        return self.features[a0:a1], adj
+
+    def to_list(self):
+        return [self.mol(i) for i in range(self.n_mols)]
+
+    def slice(self, lo, hi):
+        """Molecules [lo, hi) as a new PackedMols (copies)."""
+        a0, a1 = int(self.atom_ptr[lo]), int(self.atom_ptr[hi])
+        e0, e1 = int(self.adj_ptr[a0]), int(self.adj_ptr[a1])
+        return PackedMols(self.atom_ptr[lo:hi + 1] - a0, self.adj_ptr[a0:a1 + 1] - e0,
+                          self.adj_idx[e0:e1], self.features[a0:a1])
+
+    def take(self, idx):
+        """Molecules idx[0], idx[1], ... (repeats allowed) as a new PackedMols."""
+        idx = np.asarray(idx, dtype=np.int64)
+        n_per = (self.atom_ptr[idx + 1] - self.atom_ptr[idx]).astype(np.int64)
+        atom_ptr = np.concatenate([[0], np.cumsum(n_per)])
+        rows = np.concatenate([np.arange(self.atom_ptr[i], self.atom_ptr[i + 1]) for i in idx]) \
+            if idx.size else np.zeros(0, np.int64)
+        deg = (self.adj_ptr[rows + 1] - self.adj_ptr[rows]).astype(np.int64)
+        adj_ptr = np.concatenate([[0], np.cumsum(deg)])
+        adj = np.concatenate([self.adj_idx[self.adj_ptr[r]:self.adj_ptr[r + 1]] for r in rows]) \
+            if rows.size else np.zeros(0, np.int32)
+        return PackedMols(atom_ptr, adj_ptr, adj, self.features[rows])
+
+    @staticmethod
+    def from_list(mols, n_feat=None):
+        """mols: iterable of (features [n,F], adj_list)."""
+        atom_ptr, adj_ptr, adj_idx, feats = [0], [0], [], []
+        for f, adj in mols:
+            f = np.asarray(f, dtype=np.float32)
+            feats.append(f.reshape(len(adj), -1) if f.size else f.reshape(0, n_feat or 0))
+            atom_ptr.append(atom_ptr[-1] + len(adj))
+            for nb in adj:
+                adj_idx.extend(int(k) for k in nb)
+                adj_ptr.append(len(adj_idx))
+        if feats:
+            features = np.concatenate(feats, 0)
+        else:
+            features = np.zeros((0, n_feat or 0), np.float32)
+        return PackedMols(atom_ptr, adj_ptr, np.asarray(adj_idx, dtype=np.int32), features)
+
+
+def _random_mol_adj(rng, n, cap, ring_max):
+    """Random spanning tree with degree cap + ring closures -> adjacency lists."""
+    adj = [[] for _ in range(n)]
+    for i in range(1, n):
+        p = int(rng.integers(0, i))
+        if len(adj[p]) >= cap:
+            # any earlier atom with free valence (exists: a tree with cap >= 2 has a leaf)
+            free = [q for q in range(i) if len(adj[q]) < cap]
+            p = free[int(rng.integers(0, len(free)))]
+        adj[p].append(i)
+        adj[i].append(p)
+    n_rings = int(rng.integers(0, ring_max + 1)) if n >= 5 else 0
+    for _ in range(n_rings):
+        for _try in range(8):
+            a, b = (int(v) for v in rng.integers(0, n, size=2))
+            if a != b and b not in adj[a] and len(adj[a]) < cap and len(adj[b]) < cap:
+                adj[a].append(b)
+                adj[b].append(a)
+                break
+    return adj
+
+
+def _random_features(rng, n, n_feat, ones_per_row=8):
+    f = np.zeros((n, n_feat), dtype=np.float32)
+    if n:
+        cols = rng.integers(0, n_feat, size=(n, ones_per_row))
+        f[np.arange(n)[:, None], cols] = 1.0
+    return f
+
+
+_SHAPES = {
+    # name: (mean atoms, min, max, degree cap, max ring closures)
+    "zinc": (25.0, 6, 50, 4, 3),
+    "pcba": (25.0, 6, 50, 4, 3),
+    "tox21": (18.5, 2, 60, 4, 3),
+    "delaney": (13.3, 1, 40, 4, 2),
+    "qm9": (8.8, 4, 9, 4, 1),
+}
+
+
+def make_molecules(n_mols, seed=0, shape="zinc", n_feat=75, dense_features=False):
+    """Return a PackedMols of ``n_mols`` synthetic molecules.
+
+    ``shape='stress'``: zinc-like sizes, degree cap 10, ~5 % single-atom molecules
+    (degree-0 bucket) and hub atoms so that degrees 5..10 occur.
+    ``dense_features``: N(0,1) features instead of 0/1 (numerics tests).
+    """
+    rng = np.random.default_rng(seed)
+    stress = shape == "stress"
+    mean, lo, hi, cap, rings = _SHAPES["zinc" if stress else shape]
+    if shape == "qm9":
+        sizes = rng.integers(lo, hi + 1, size=n_mols)
+    else:
+        sizes = np.clip(rng.poisson(mean, size=n_mols), lo, hi)
+    mols = []
+    for i in range(n_mols):
+        n = int(sizes[i])
+        if stress and rng.random() < 0.05:
+            n = 1
+        if n == 1:
+            adj = [[]]
+        elif stress and rng.random() < 0.3:
+            # hub molecule: atom 0 bonded to k others, rest is a capped tree
+            adj = _random_mol_adj(rng, n, 4, rings)
+            k = int(rng.integers(5, 11))
+            others = [j for j in range(1, n) if j not in adj[0]]
+            for j in others[:max(0, k - len(adj[0]))]:
+                if len(adj[j]) < 10:
+                    adj[0].append(j)
+                    adj[j].append(0)
+        else:
+            adj = _random_mol_adj(rng, n, cap, rings)
+        if dense_features:
+            f = rng.standard_normal((n, n_feat)).astype(np.float32)
+        else:
+            f = _random_features(rng, n, n_feat)
+        mols.append((f, adj))
+    return PackedMols.from_list(mols, n_feat)
+
+
+def make_labels(n_mols, n_tasks, mode="regression", seed=0, n_classes=2, missing=0.0):
+    """y [B,T] and w [B,T]; ``missing`` fraction of weights set to 0 (Tox21-like)."""
+    rng = np.random.default_rng(seed + 7919)
+    if mode == "classification":
+        y = rng.integers(0, n_classes, size=(n_mols, n_tasks)).astype(np.float32)
+    else:
+        y = rng.standard_normal((n_mols, n_tasks)).astype(np.float32)
+    w = np.ones((n_mols, n_tasks), dtype=np.float32)
+    if missing > 0:
+        w[rng.random((n_mols, n_tasks)) < missing] = 0.0
+    return y, w
