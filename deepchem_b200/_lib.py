@@ -1,0 +1,115 @@
+"""ctypes binding of libdcgc.so (include/dcgc.h).  No torch types cross this boundary: only
+raw pointers, sizes and a cudaStream_t.  There is no CPU fallback: if the library cannot be
+loaded (or built), importing the ops raises."""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_int32, c_int64, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdcgc.so")
+
+DCGC_OK = 0
+DCGC_ERR_INVALID = -1
+DCGC_ERR_DEGREE = -2
+DCGC_ERR_INDEX = -3
+DCGC_ERR_CUDA = -4
+DCGC_ERR_NOMEM = -5
+
+ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
+GEMM_FP32, GEMM_BF16, GEMM_TF32X3 = 0, 1, 2
+N_DEG = 11
+TILE_ROWS = 128
+
+
+class LayoutInfo(Structure):
+    """dcgc_layout_info"""
+    _fields_ = [
+        ("n_mols", c_int64), ("n_segments", c_int64), ("n_atoms", c_int64), ("n_edges", c_int64),
+        ("n_tiles", c_int64), ("tile_rows", c_int32), ("reserved", c_int32),
+        ("deg_count", c_int64 * N_DEG),
+        ("off_deg_slice", c_int64), ("off_membership", c_int64), ("off_perm", c_int64),
+        ("off_row_ptr", c_int64), ("off_col_idx", c_int64), ("off_t_row_ptr", c_int64),
+        ("off_t_src", c_int64), ("off_t_slot", c_int64), ("off_mol_ptr", c_int64),
+        ("off_mol_atoms", c_int64), ("off_tiles", c_int64), ("slab_bytes", c_int64),
+    ]
+
+
+_P = c_void_p
+_SIGNATURES = {
+    "dcgc_last_error": (c_char_p, []),
+    "dcgc_version": (c_int32, []),
+    "dcgc_device_ok": (c_int32, []),
+    "dcgc_layout_plan": (c_int32, [c_int64, _P, _P, c_int64, c_int32, POINTER(LayoutInfo)]),
+    "dcgc_layout_build": (c_int32, [c_int64, _P, _P, _P, POINTER(LayoutInfo), _P]),
+    "dcgc_layout_permute_features_host": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, c_int64, c_int32]),
+    "dcgc_layout_plan_from_deg": (c_int32, [_P, c_int64, c_int32, POINTER(LayoutInfo)]),
+    "dcgc_layout_build_from_deg": (c_int32, [_P, _P, _P, POINTER(LayoutInfo), _P]),
+    "dcgc_permute_rows": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, c_int64, _P]),
+    "dcgc_gather_sum": (c_int32, [_P, c_int64, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
+    "dcgc_pool_fwd": (c_int32, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
+    "dcgc_pool_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, c_int64, _P]),
+    "dcgc_gather_fwd": (c_int32, [_P, c_int64, _P, _P, c_int64, c_int32, c_int32, _P, c_int64, _P, _P]),
+    "dcgc_gather_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int32, c_int32, _P, c_int64, _P]),
+    "dcgc_group_gemm_fwd": (c_int32, [c_int32, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, c_int32,
+                                      _P, c_int64, c_int32, c_int64, c_int32, _P, c_int64, _P]),
+    "dcgc_group_gemm_dgrad": (c_int32, [c_int32, _P, c_int64, c_int32, _P, c_int32, c_int32, _P, c_int64,
+                                        c_int32, c_int64, _P, c_int64, _P, c_int64, _P]),
+    "dcgc_group_gemm_wgrad_workspace": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
+    "dcgc_group_gemm_wgrad": (c_int32, [c_int32, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, c_int64,
+                                        c_int32, _P, c_int32, _P, _P, _P, c_int64, _P]),
+}
+
+_lib = None
+
+
+class DcgcError(RuntimeError):
+    pass
+
+
+def exported_symbols():
+    """Names include/dcgc.h declares (kept in sync by tests/test_cabi.py)."""
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load (building first if the .so is missing and nvcc is present) and return the library."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:  # no nvcc, or compile error
+            raise DcgcError(
+                "libdcgc.so is not built (%s). Run `python -m deepchem_b200.build`; there is no "
+                "CPU or pure-PyTorch fallback for this path." % (e,))
+    try:
+        handle = ctypes.CDLL(LIB_PATH)
+    except OSError as e:
+        raise DcgcError("cannot load %s: %s (no fallback path exists)" % (LIB_PATH, e))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(handle, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return _lib
+
+
+def last_error():
+    return lib().dcgc_last_error().decode("utf-8", "replace")
+
+
+def check(status):
+    """Translate a C status into the exception the reference raises in the same situation."""
+    if status == DCGC_OK:
+        return
+    msg = last_error()
+    if status == DCGC_ERR_DEGREE:
+        # featurizer raises ValueError for degree > max_deg (feat/graph_features.py:34-36)
+        raise ValueError(msg)
+    if status in (DCGC_ERR_INVALID, DCGC_ERR_INDEX):
+        raise ValueError(msg)
+    if status == DCGC_ERR_NOMEM:
+        raise MemoryError(msg)
+    raise DcgcError("libdcgc error %d: %s" % (status, msg))

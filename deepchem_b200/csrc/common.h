@@ -1,0 +1,39 @@
+// Internal helpers shared by the libdcgc translation units (not part of the ABI).
+#pragma once
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "dcgc.h"
+
+void dcgc_set_error(const char* fmt, ...);
+
+#define DCGC_CHECK_ARG(cond, ...)   \
+  do {                              \
+    if (!(cond)) {                  \
+      dcgc_set_error(__VA_ARGS__);  \
+      return DCGC_ERR_INVALID;      \
+    }                               \
+  } while (0)
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define DCGC_CUDA_LAUNCH_CHECK(what)                                        \
+  do {                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                   \
+    if (e__ != cudaSuccess) {                                               \
+      dcgc_set_error("%s: %s", what, cudaGetErrorString(e__));              \
+      return DCGC_ERR_CUDA;                                                 \
+    }                                                                       \
+  } while (0)
+#define DCGC_CUDA_CALL(expr)                                                \
+  do {                                                                      \
+    cudaError_t e__ = (expr);                                               \
+    if (e__ != cudaSuccess) {                                               \
+      dcgc_set_error("%s: %s", #expr, cudaGetErrorString(e__));             \
+      return DCGC_ERR_CUDA;                                                 \
+    }                                                                       \
+  } while (0)
+#endif
+
+static inline int64_t dcgc_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }

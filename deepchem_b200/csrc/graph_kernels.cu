@@ -1,0 +1,415 @@
+// HBM-bound kernels of the GraphConv path for sm_100a: neighbour gather-sum (K1/K5/K8),
+// GraphPool max (+argslot) and its scatter-free backward (K3/K7), GraphGather segment sum/max
+// and its backward (K4/K7), row permutation.
+//
+// Common shape: one thread owns one 16-byte column group (float4) of one OUTPUT row, so every
+// output element is written exactly once by exactly one thread (no float atomics, fixed
+// summation order = index order), consecutive threads touch consecutive 16-byte groups of a
+// row (128-bit coalesced loads of whole feature rows) and consecutive rows of the output.
+// A scalar (VEC=1) instantiation handles widths / strides that are not 16-byte aligned
+// (the reference's raw [N,75] feature matrix).
+#include "common.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<4> {
+  using T = float4;
+  static __device__ __forceinline__ T load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ void store(float* p, T v) { *reinterpret_cast<float4*>(p) = v; }
+  static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+template <>
+struct Vec<1> {
+  using T = float;
+  static __device__ __forceinline__ T load(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void store(float* p, T v) { *p = v; }
+  static __device__ __forceinline__ T zero() { return 0.f; }
+};
+
+__device__ __forceinline__ void vadd(float4& a, const float4 b) {
+  a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+}
+__device__ __forceinline__ void vadd(float& a, const float b) { a += b; }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+inline unsigned grid_for(int64_t work) { return (unsigned)((work + kThreads - 1) / kThreads); }
+
+// ------------------------------------------------------------------------------------------
+// permute rows (+ zero the pad columns)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+permute_rows_kernel(const float* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ perm,
+                    int64_t n_rows, int n_feat, float* __restrict__ dst, int64_t ld_dst) {
+  const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t row = t / ld_dst;
+  const int c = (int)(t - row * ld_dst);
+  if (row >= n_rows) return;
+  dst[row * ld_dst + c] = c < n_feat ? __ldg(src + (int64_t)__ldg(perm + row) * ld_src + c) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1/K5/K8: CSR gather-sum
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+gather_sum_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restrict__ row_ptr,
+                  const int32_t* __restrict__ idx, int64_t n_rows, int groups, int width,
+                  const float* addend, int64_t ld_add, float* out, int64_t ld_out) {
+  using V = Vec<VEC>;
+  const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t row = t / groups;
+  const int c = (int)(t - row * groups) * VEC;
+  if (row >= n_rows || c >= width) return;
+  int e = __ldg(row_ptr + row);
+  const int e1 = __ldg(row_ptr + row + 1);
+  typename V::T acc = V::zero();
+  if (addend) acc = *reinterpret_cast<const typename V::T*>(addend + row * ld_add + c);  // may alias out
+  const float* xc = x + c;
+  // four independent row loads in flight per thread (degrees 1..4 carry almost all rows)
+  for (; e + 4 <= e1; e += 4) {
+    const int j0 = __ldg(idx + e), j1 = __ldg(idx + e + 1), j2 = __ldg(idx + e + 2), j3 = __ldg(idx + e + 3);
+    const typename V::T v0 = V::load(xc + (int64_t)j0 * ld_x);
+    const typename V::T v1 = V::load(xc + (int64_t)j1 * ld_x);
+    const typename V::T v2 = V::load(xc + (int64_t)j2 * ld_x);
+    const typename V::T v3 = V::load(xc + (int64_t)j3 * ld_x);
+    vadd(acc, v0); vadd(acc, v1); vadd(acc, v2); vadd(acc, v3);
+  }
+  if (e + 2 <= e1) {
+    const int j0 = __ldg(idx + e), j1 = __ldg(idx + e + 1);
+    const typename V::T v0 = V::load(xc + (int64_t)j0 * ld_x);
+    const typename V::T v1 = V::load(xc + (int64_t)j1 * ld_x);
+    vadd(acc, v0); vadd(acc, v1);
+    e += 2;
+  }
+  if (e < e1) vadd(acc, V::load(xc + (int64_t)__ldg(idx + e) * ld_x));
+  V::store(out + row * ld_out + c, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: GraphPool forward.  First slot attaining the max wins (strict > when scanning
+// self, nbr_0, nbr_1, ...), which is torch.max's tie rule on the reference's
+// concat([self, gathered]) (torch_models/layers.py:6358-6361).
+// ------------------------------------------------------------------------------------------
+template <int VEC, bool AFFINE, bool ARG>
+__global__ void __launch_bounds__(kThreads)
+pool_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ scale,
+                const float* __restrict__ shift, const int32_t* __restrict__ row_ptr,
+                const int32_t* __restrict__ col_idx, int64_t n_rows, int groups, int width,
+                float* __restrict__ out, int64_t ld_out, uint8_t* __restrict__ arg, int64_t ld_arg) {
+  const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t row = t / groups;
+  const int c = (int)(t - row * groups) * VEC;
+  if (row >= n_rows || c >= width) return;
+  float sc[VEC], sh[VEC], m[VEC];
+  uint8_t a[VEC];
+  if (AFFINE) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) { sc[v] = __ldg(scale + c + v); sh[v] = __ldg(shift + c + v); }
+  }
+  auto load = [&](int64_t r, float* dst) {
+    if (VEC == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(x + r * ld_x + c));
+      dst[0] = q.x; dst[1 % VEC] = q.y; dst[2 % VEC] = q.z; dst[3 % VEC] = q.w;
+    } else {
+      dst[0] = __ldg(x + r * ld_x + c);
+    }
+    if (AFFINE) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) dst[v] = fmaf(dst[v], sc[v], sh[v]);
+    }
+  };
+  load(row, m);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) a[v] = 0;
+  const int e0 = __ldg(row_ptr + row), e1 = __ldg(row_ptr + row + 1);
+  int e = e0;
+  for (; e + 2 <= e1; e += 2) {
+    float u0[VEC], u1[VEC];
+    const int j0 = __ldg(col_idx + e), j1 = __ldg(col_idx + e + 1);
+    load(j0, u0);
+    load(j1, u1);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      if (u0[v] > m[v]) { m[v] = u0[v]; a[v] = (uint8_t)(e - e0 + 1); }
+      if (u1[v] > m[v]) { m[v] = u1[v]; a[v] = (uint8_t)(e - e0 + 2); }
+    }
+  }
+  if (e < e1) {
+    float u0[VEC];
+    load(__ldg(col_idx + e), u0);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v)
+      if (u0[v] > m[v]) { m[v] = u0[v]; a[v] = (uint8_t)(e - e0 + 1); }
+  }
+  if (VEC == 4) {
+    *reinterpret_cast<float4*>(out + row * ld_out + c) = make_float4(m[0], m[1 % VEC], m[2 % VEC], m[3 % VEC]);
+    if (ARG) *reinterpret_cast<uchar4*>(arg + row * ld_arg + c) = make_uchar4(a[0], a[1 % VEC], a[2 % VEC], a[3 % VEC]);
+  } else {
+    out[row * ld_out + c] = m[0];
+    if (ARG) arg[row * ld_arg + c] = a[0];
+  }
+}
+
+// K7: GraphPool backward over the transposed CSR (each source row gathers from the rows that
+// selected it; nothing is scattered).
+template <int VEC, bool AFFINE>
+__global__ void __launch_bounds__(kThreads)
+pool_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy, const uint8_t* __restrict__ arg,
+                int64_t ld_arg, const float* __restrict__ scale, const int32_t* __restrict__ t_row_ptr,
+                const int32_t* __restrict__ t_src, const int32_t* __restrict__ t_slot, int64_t n_rows,
+                int groups, int width, float* __restrict__ dx, int64_t ld_dx) {
+  const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t row = t / groups;
+  const int c = (int)(t - row * groups) * VEC;
+  if (row >= n_rows || c >= width) return;
+  float acc[VEC];
+  auto take = [&](int64_t r, int slot, bool first) {
+    float d[VEC];
+    uint8_t a[VEC];
+    if (VEC == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(dy + r * ld_dy + c));
+      const uchar4 b = __ldg(reinterpret_cast<const uchar4*>(arg + r * ld_arg + c));
+      d[0] = q.x; d[1 % VEC] = q.y; d[2 % VEC] = q.z; d[3 % VEC] = q.w;
+      a[0] = b.x; a[1 % VEC] = b.y; a[2 % VEC] = b.z; a[3 % VEC] = b.w;
+    } else {
+      d[0] = __ldg(dy + r * ld_dy + c);
+      a[0] = __ldg(arg + r * ld_arg + c);
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float g = (a[v] == slot) ? d[v] : 0.f;
+      acc[v] = first ? g : acc[v] + g;
+    }
+  };
+  take(row, 0, true);
+  const int e1 = __ldg(t_row_ptr + row + 1);
+  for (int e = __ldg(t_row_ptr + row); e < e1; ++e) take(__ldg(t_src + e), __ldg(t_slot + e) + 1, false);
+  if (AFFINE) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] *= __ldg(scale + c + v);
+  }
+  if (VEC == 4) {
+    *reinterpret_cast<float4*>(dx + row * ld_dx + c) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+  } else {
+    dx[row * ld_dx + c] = acc[0];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: GraphGather.  One thread owns one 16-byte column group of one molecule and walks the
+// molecule's rows in ascending order (the order CPU scatter_add accumulates in,
+// deepchem/utils/pytorch_utils.py:70-72).  Max ties keep the lowest row (strict >).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == DCGC_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == DCGC_ACT_TANH) return tanhf(v);
+  return v;
+}
+__device__ __forceinline__ float act_grad_from_out(float o, int act) {
+  if (act == DCGC_ACT_RELU) return o > 0.f ? 1.f : 0.f;
+  if (act == DCGC_ACT_TANH) return 1.f - o * o;
+  return 1.f;
+}
+
+template <int VEC, bool ARG>
+__global__ void __launch_bounds__(kThreads)
+gather_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restrict__ mol_ptr,
+                  const int32_t* __restrict__ mol_atoms, int64_t n_seg, int groups, int width, int act,
+                  float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argrow) {
+  const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t g = t / groups;
+  const int c = (int)(t - g * groups) * VEC;
+  if (g >= n_seg || c >= width) return;
+  float s[VEC], m[VEC];
+  int32_t a[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { s[v] = 0.f; m[v] = -INFINITY; a[v] = -1; }
+  const int e1 = __ldg(mol_ptr + g + 1);
+  for (int e = __ldg(mol_ptr + g); e < e1; ++e) {
+    const int32_t r = __ldg(mol_atoms + e);
+    float u[VEC];
+    if (VEC == 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(x + (int64_t)r * ld_x + c));
+      u[0] = q.x; u[1 % VEC] = q.y; u[2 % VEC] = q.z; u[3 % VEC] = q.w;
+    } else {
+      u[0] = __ldg(x + (int64_t)r * ld_x + c);
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      s[v] += u[v];
+      if (u[v] > m[v] || a[v] < 0) { m[v] = u[v]; a[v] = r; }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    out[g * ld_out + c + v] = apply_act(s[v], act);
+    out[g * ld_out + width + c + v] = apply_act(m[v], act);
+    if (ARG) argrow[g * (int64_t)width + c + v] = a[v];
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+gather_bwd_kernel(const float* __restrict__ dout, int64_t ld_dout, const float* __restrict__ out,
+                  int64_t ld_out, const int32_t* __restrict__ argrow, const int32_t* __restrict__ membership,
+                  int64_t n_rows, int groups, int width, int act, float* __restrict__ dx, int64_t ld_dx) {
+  const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t row = t / groups;
+  const int c = (int)(t - row * groups) * VEC;
+  if (row >= n_rows || c >= width) return;
+  const int64_t g = __ldg(membership + row);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    const int cc = c + v;
+    if (cc >= width) break;
+    float d = __ldg(dout + g * ld_dout + cc) * act_grad_from_out(__ldg(out + g * ld_out + cc), act);
+    if (__ldg(argrow + g * (int64_t)width + cc) == (int32_t)row)
+      d += __ldg(dout + g * ld_dout + width + cc) * act_grad_from_out(__ldg(out + g * ld_out + width + cc), act);
+    dx[row * ld_dx + cc] = d;
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+extern "C" int dcgc_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return 0;
+  }
+  int dev = 0, major = 0;
+  DCGC_CUDA_CALL(cudaGetDevice(&dev));
+  DCGC_CUDA_CALL(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  return major == 10 ? 1 : 0;
+}
+
+extern "C" int dcgc_permute_rows(const float* src, int64_t ld_src, const int32_t* perm, int64_t n_rows,
+                                 int32_t n_feat, float* dst, int64_t ld_dst, void* stream) {
+  DCGC_CHECK_ARG(n_rows >= 0 && n_feat >= 0 && ld_src >= n_feat && ld_dst >= n_feat,
+                 "dcgc_permute_rows: bad sizes");
+  if (n_rows == 0 || ld_dst == 0) return DCGC_OK;
+  DCGC_CHECK_ARG(src && perm && dst, "dcgc_permute_rows: null pointer");
+  permute_rows_kernel<<<grid_for(n_rows * ld_dst), kThreads, 0, (cudaStream_t)stream>>>(
+      src, ld_src, perm, n_rows, n_feat, dst, ld_dst);
+  DCGC_CUDA_LAUNCH_CHECK("dcgc_permute_rows");
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_gather_sum(const float* x, int64_t ld_x, const int32_t* row_ptr, const int32_t* idx,
+                               int64_t n_rows_out, int32_t width, const float* addend, int64_t ld_add,
+                               float* out, int64_t ld_out, void* stream) {
+  DCGC_CHECK_ARG(n_rows_out >= 0 && width >= 0 && ld_x >= width && ld_out >= width &&
+                     (addend == nullptr || ld_add >= width), "dcgc_gather_sum: bad sizes");
+  if (n_rows_out == 0 || width == 0) return DCGC_OK;
+  DCGC_CHECK_ARG(x && row_ptr && out, "dcgc_gather_sum: null pointer");
+  const bool v4 = width % 4 == 0 && ld_x % 4 == 0 && ld_out % 4 == 0 && aligned16(x) && aligned16(out) &&
+                  (addend == nullptr || (ld_add % 4 == 0 && aligned16(addend)));
+  if (v4) {
+    const int groups = width / 4;
+    gather_sum_kernel<4><<<grid_for(n_rows_out * groups), kThreads, 0, (cudaStream_t)stream>>>(
+        x, ld_x, row_ptr, idx, n_rows_out, groups, width, addend, ld_add, out, ld_out);
+  } else {
+    gather_sum_kernel<1><<<grid_for(n_rows_out * width), kThreads, 0, (cudaStream_t)stream>>>(
+        x, ld_x, row_ptr, idx, n_rows_out, width, width, addend, ld_add, out, ld_out);
+  }
+  DCGC_CUDA_LAUNCH_CHECK("dcgc_gather_sum");
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_pool_fwd(const float* x, int64_t ld_x, const float* scale, const float* shift,
+                             const int32_t* row_ptr, const int32_t* col_idx, int64_t n_rows,
+                             int32_t width, float* out, int64_t ld_out, uint8_t* arg, int64_t ld_arg,
+                             void* stream) {
+  DCGC_CHECK_ARG(n_rows >= 0 && width >= 0 && ld_x >= width && ld_out >= width, "dcgc_pool_fwd: bad sizes");
+  DCGC_CHECK_ARG((scale == nullptr) == (shift == nullptr), "dcgc_pool_fwd: scale and shift go together");
+  DCGC_CHECK_ARG(arg == nullptr || ld_arg >= width, "dcgc_pool_fwd: ld_arg smaller than width");
+  if (n_rows == 0 || width == 0) return DCGC_OK;
+  DCGC_CHECK_ARG(x && row_ptr && out, "dcgc_pool_fwd: null pointer");
+  const bool v4 = width % 4 == 0 && ld_x % 4 == 0 && ld_out % 4 == 0 && aligned16(x) && aligned16(out) &&
+                  (arg == nullptr || (ld_arg % 4 == 0 && (reinterpret_cast<uintptr_t>(arg) & 3) == 0));
+  const int groups = v4 ? width / 4 : width;
+  const unsigned grid = grid_for(n_rows * groups);
+  cudaStream_t st = (cudaStream_t)stream;
+#define DCGC_POOL_LAUNCH(V, A, R)                                                              \
+  pool_fwd_kernel<V, A, R><<<grid, kThreads, 0, st>>>(x, ld_x, scale, shift, row_ptr, col_idx, \
+                                                      n_rows, groups, width, out, ld_out, arg, ld_arg)
+  if (v4) {
+    if (scale) { if (arg) DCGC_POOL_LAUNCH(4, true, true); else DCGC_POOL_LAUNCH(4, true, false); }
+    else { if (arg) DCGC_POOL_LAUNCH(4, false, true); else DCGC_POOL_LAUNCH(4, false, false); }
+  } else {
+    if (scale) { if (arg) DCGC_POOL_LAUNCH(1, true, true); else DCGC_POOL_LAUNCH(1, true, false); }
+    else { if (arg) DCGC_POOL_LAUNCH(1, false, true); else DCGC_POOL_LAUNCH(1, false, false); }
+  }
+#undef DCGC_POOL_LAUNCH
+  DCGC_CUDA_LAUNCH_CHECK("dcgc_pool_fwd");
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_pool_bwd(const float* dy, int64_t ld_dy, const uint8_t* arg, int64_t ld_arg,
+                             const float* scale, const int32_t* t_row_ptr, const int32_t* t_src,
+                             const int32_t* t_slot, int64_t n_rows, int32_t width, float* dx,
+                             int64_t ld_dx, void* stream) {
+  DCGC_CHECK_ARG(n_rows >= 0 && width >= 0 && ld_dy >= width && ld_dx >= width && ld_arg >= width,
+                 "dcgc_pool_bwd: bad sizes");
+  if (n_rows == 0 || width == 0) return DCGC_OK;
+  DCGC_CHECK_ARG(dy && arg && t_row_ptr && dx, "dcgc_pool_bwd: null pointer");
+  const bool v4 = width % 4 == 0 && ld_dy % 4 == 0 && ld_dx % 4 == 0 && ld_arg % 4 == 0 && aligned16(dy) &&
+                  aligned16(dx) && (reinterpret_cast<uintptr_t>(arg) & 3) == 0;
+  const int groups = v4 ? width / 4 : width;
+  const unsigned grid = grid_for(n_rows * groups);
+  cudaStream_t st = (cudaStream_t)stream;
+#define DCGC_POOLB_LAUNCH(V, A)                                                                   \
+  pool_bwd_kernel<V, A><<<grid, kThreads, 0, st>>>(dy, ld_dy, arg, ld_arg, scale, t_row_ptr, t_src, \
+                                                   t_slot, n_rows, groups, width, dx, ld_dx)
+  if (v4) { if (scale) DCGC_POOLB_LAUNCH(4, true); else DCGC_POOLB_LAUNCH(4, false); }
+  else { if (scale) DCGC_POOLB_LAUNCH(1, true); else DCGC_POOLB_LAUNCH(1, false); }
+#undef DCGC_POOLB_LAUNCH
+  DCGC_CUDA_LAUNCH_CHECK("dcgc_pool_bwd");
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_gather_fwd(const float* x, int64_t ld_x, const int32_t* mol_ptr, const int32_t* mol_atoms,
+                               int64_t n_segments, int32_t width, int32_t act, float* out, int64_t ld_out,
+                               int32_t* argrow, void* stream) {
+  DCGC_CHECK_ARG(n_segments >= 0 && width >= 0 && ld_x >= width && ld_out >= 2 * (int64_t)width,
+                 "dcgc_gather_fwd: bad sizes");
+  DCGC_CHECK_ARG(act >= DCGC_ACT_NONE && act <= DCGC_ACT_TANH, "dcgc_gather_fwd: unknown activation %d", act);
+  if (n_segments == 0 || width == 0) return DCGC_OK;
+  DCGC_CHECK_ARG(x && mol_ptr && out, "dcgc_gather_fwd: null pointer");
+  const bool v4 = width % 4 == 0 && ld_x % 4 == 0 && aligned16(x);
+  const int groups = v4 ? width / 4 : width;
+  const unsigned grid = grid_for(n_segments * groups);
+  cudaStream_t st = (cudaStream_t)stream;
+#define DCGC_GATHER_LAUNCH(V, R)                                                                    \
+  gather_fwd_kernel<V, R><<<grid, kThreads, 0, st>>>(x, ld_x, mol_ptr, mol_atoms, n_segments, groups, \
+                                                     width, act, out, ld_out, argrow)
+  if (v4) { if (argrow) DCGC_GATHER_LAUNCH(4, true); else DCGC_GATHER_LAUNCH(4, false); }
+  else { if (argrow) DCGC_GATHER_LAUNCH(1, true); else DCGC_GATHER_LAUNCH(1, false); }
+#undef DCGC_GATHER_LAUNCH
+  DCGC_CUDA_LAUNCH_CHECK("dcgc_gather_fwd");
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_gather_bwd(const float* dout, int64_t ld_dout, const float* out, int64_t ld_out,
+                               const int32_t* argrow, const int32_t* membership, int64_t n_rows,
+                               int32_t width, int32_t act, float* dx, int64_t ld_dx, void* stream) {
+  DCGC_CHECK_ARG(n_rows >= 0 && width >= 0 && ld_dout >= 2 * (int64_t)width && ld_out >= 2 * (int64_t)width &&
+                     ld_dx >= width, "dcgc_gather_bwd: bad sizes");
+  DCGC_CHECK_ARG(act >= DCGC_ACT_NONE && act <= DCGC_ACT_TANH, "dcgc_gather_bwd: unknown activation %d", act);
+  if (n_rows == 0 || width == 0) return DCGC_OK;
+  DCGC_CHECK_ARG(dout && out && argrow && membership && dx, "dcgc_gather_bwd: null pointer");
+  const int groups = (width + 3) / 4;
+  gather_bwd_kernel<4><<<grid_for(n_rows * groups), kThreads, 0, (cudaStream_t)stream>>>(
+      dout, ld_dout, out, ld_out, argrow, membership, n_rows, groups, width, act, dx, ld_dx);
+  DCGC_CUDA_LAUNCH_CHECK("dcgc_gather_bwd");
+  return DCGC_OK;
+}

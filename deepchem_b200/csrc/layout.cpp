@@ -1,0 +1,285 @@
+// Host layout builder: packed molecule shard -> degree-major batch slab.
+//
+// Replaces ConvMol._deg_sort + ConvMol.agglomerate_mols
+// (deepchem/feat/mol_graphs.py:113-185, 256-349).  The reference sorts every molecule's atoms
+// stably by degree, then sorts the concatenation stably by degree again; the composite is one
+// stable counting sort of all atoms keyed by degree, i.e. the batch order is
+// (degree, molecule, position inside the molecule).  Everything here is integer work and must
+// match the reference bit for bit (tests/test_layout.py).
+#include <string.h>
+
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+#include "common.h"
+
+static thread_local char g_err[512] = "";
+
+void dcgc_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* dcgc_last_error(void) { return g_err; }
+extern "C" int dcgc_version(void) { return 100; }
+
+static void plan_offsets(dcgc_layout_info* info) {
+  const int64_t N = info->n_atoms, E = info->n_edges, S = info->n_segments;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) {
+    int64_t o = off;
+    off = dcgc_align_up(off + bytes, 256);
+    return o;
+  };
+  info->off_deg_slice = take(DCGC_N_DEG * 2 * 8);
+  info->off_membership = take(N * 4);
+  info->off_perm = take(N * 4);
+  info->off_row_ptr = take((N + 1) * 4);
+  info->off_col_idx = take(E * 4);
+  info->off_t_row_ptr = take((N + 1) * 4);
+  info->off_t_src = take(E * 4);
+  info->off_t_slot = take(E * 4);
+  info->off_mol_ptr = take((S + 1) * 4);
+  info->off_mol_atoms = take(N * 4);
+  info->off_tiles = take(info->n_tiles * 16);
+  info->slab_bytes = off;
+}
+
+static int finish_plan(dcgc_layout_info* info, int64_t n_segments, int32_t tile_rows) {
+  int64_t N = 0, E = 0, T = 0;
+  for (int d = 0; d < DCGC_N_DEG; ++d) {
+    N += info->deg_count[d];
+    E += (int64_t)d * info->deg_count[d];
+    T += (info->deg_count[d] + tile_rows - 1) / tile_rows;
+  }
+  if (N >= (int64_t)1 << 31 || E >= (int64_t)1 << 31) {
+    dcgc_set_error("batch too large for int32 indices (N=%lld, E=%lld)", (long long)N, (long long)E);
+    return DCGC_ERR_INVALID;
+  }
+  info->n_atoms = N;
+  info->n_edges = E;
+  info->n_tiles = T;
+  info->tile_rows = tile_rows;
+  info->reserved = 0;
+  info->n_segments = n_segments;
+  plan_offsets(info);
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_layout_plan(int64_t n_mols, const int32_t* atom_ptr, const int32_t* adj_ptr,
+                                int64_t n_segments, int32_t tile_rows, dcgc_layout_info* info) {
+  DCGC_CHECK_ARG(n_mols >= 0 && atom_ptr && adj_ptr && info, "dcgc_layout_plan: null argument");
+  DCGC_CHECK_ARG(tile_rows > 0, "dcgc_layout_plan: tile_rows must be positive");
+  DCGC_CHECK_ARG(n_segments >= n_mols, "dcgc_layout_plan: n_segments (%lld) < n_mols (%lld)",
+                 (long long)n_segments, (long long)n_mols);
+  memset(info, 0, sizeof(*info));
+  info->n_mols = n_mols;
+  const int64_t N = atom_ptr[n_mols];
+  DCGC_CHECK_ARG(atom_ptr[0] == 0 && N >= 0, "dcgc_layout_plan: atom_ptr must start at 0");
+  for (int64_t a = 0; a < N; ++a) {
+    const int64_t d = (int64_t)adj_ptr[a + 1] - adj_ptr[a];
+    if (d < 0 || d > DCGC_MAX_DEG) {
+      dcgc_set_error("atom %lld has degree %lld; the layout supports degrees 0..%d", (long long)a,
+                     (long long)d, DCGC_MAX_DEG);
+      return DCGC_ERR_DEGREE;
+    }
+    info->deg_count[d]++;
+  }
+  return finish_plan(info, n_segments, tile_rows);
+}
+
+// Shared tail: everything derivable from (deg_count, membership, col_idx).
+static void build_derived(const dcgc_layout_info* info, char* slab) {
+  const int64_t N = info->n_atoms, E = info->n_edges, S = info->n_segments;
+  int64_t* deg_slice = (int64_t*)(slab + info->off_deg_slice);
+  const int32_t* membership = (const int32_t*)(slab + info->off_membership);
+  int32_t* row_ptr = (int32_t*)(slab + info->off_row_ptr);
+  const int32_t* col_idx = (const int32_t*)(slab + info->off_col_idx);
+  int32_t* t_row_ptr = (int32_t*)(slab + info->off_t_row_ptr);
+  int32_t* t_src = (int32_t*)(slab + info->off_t_src);
+  int32_t* t_slot = (int32_t*)(slab + info->off_t_slot);
+  int32_t* mol_ptr = (int32_t*)(slab + info->off_mol_ptr);
+  int32_t* mol_atoms = (int32_t*)(slab + info->off_mol_atoms);
+  int32_t* tiles = (int32_t*)(slab + info->off_tiles);
+
+  // deg_slice: running starts, not zeroed for empty buckets (mol_graphs.py:295-305)
+  int64_t start = 0, t = 0, e = 0;
+  for (int d = 0; d < DCGC_N_DEG; ++d) {
+    const int64_t cnt = info->deg_count[d];
+    deg_slice[2 * d] = start;
+    deg_slice[2 * d + 1] = cnt;
+    for (int64_t r = 0; r < cnt; ++r) {
+      row_ptr[start + r] = (int32_t)e;
+      e += d;
+    }
+    for (int64_t r = 0; r < cnt; r += info->tile_rows) {
+      tiles[4 * t + 0] = (int32_t)(start + r);
+      tiles[4 * t + 1] = (int32_t)std::min<int64_t>(info->tile_rows, cnt - r);
+      tiles[4 * t + 2] = d;
+      tiles[4 * t + 3] = 0;
+      ++t;
+    }
+    start += cnt;
+  }
+  row_ptr[N] = (int32_t)e;
+
+  // transposed CSR by counting sort on the column id; entries of one column end up ordered by
+  // (row, slot) because rows and slots are visited in ascending order.
+  memset(t_row_ptr, 0, (size_t)(N + 1) * 4);
+  for (int64_t k = 0; k < E; ++k) t_row_ptr[col_idx[k] + 1]++;
+  for (int64_t j = 0; j < N; ++j) t_row_ptr[j + 1] += t_row_ptr[j];
+  {
+    std::vector<int32_t> cur(t_row_ptr, t_row_ptr + N);
+    for (int64_t i = 0; i < N; ++i) {
+      for (int32_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k) {
+        const int32_t p = cur[col_idx[k]]++;
+        t_src[p] = (int32_t)i;
+        t_slot[p] = k - row_ptr[i];
+      }
+    }
+  }
+  // molecule -> rows CSR (membership is not globally sorted)
+  memset(mol_ptr, 0, (size_t)(S + 1) * 4);
+  for (int64_t i = 0; i < N; ++i) mol_ptr[membership[i] + 1]++;
+  for (int64_t g = 0; g < S; ++g) mol_ptr[g + 1] += mol_ptr[g];
+  {
+    std::vector<int32_t> cur(mol_ptr, mol_ptr + S);
+    for (int64_t i = 0; i < N; ++i) mol_atoms[cur[membership[i]]++] = (int32_t)i;
+  }
+}
+
+extern "C" int dcgc_layout_build(int64_t n_mols, const int32_t* atom_ptr, const int32_t* adj_ptr,
+                                 const int32_t* adj_idx, const dcgc_layout_info* info, void* slab_v) {
+  DCGC_CHECK_ARG(atom_ptr && adj_ptr && info && slab_v, "dcgc_layout_build: null argument");
+  DCGC_CHECK_ARG(n_mols == info->n_mols && atom_ptr[n_mols] == info->n_atoms,
+                 "dcgc_layout_build: info does not match the inputs");
+  DCGC_CHECK_ARG(adj_idx || info->n_edges == 0, "dcgc_layout_build: null adj_idx");
+  char* slab = (char*)slab_v;
+  const int64_t N = info->n_atoms;
+  int32_t* membership = (int32_t*)(slab + info->off_membership);
+  int32_t* perm = (int32_t*)(slab + info->off_perm);
+  int32_t* col_idx = (int32_t*)(slab + info->off_col_idx);
+
+  // stable counting sort by degree
+  int64_t bucket_start[DCGC_N_DEG], edge_start[DCGC_N_DEG], cursor[DCGC_N_DEG];
+  int64_t s = 0, es = 0;
+  for (int d = 0; d < DCGC_N_DEG; ++d) {
+    bucket_start[d] = cursor[d] = s;
+    edge_start[d] = es;
+    s += info->deg_count[d];
+    es += (int64_t)d * info->deg_count[d];
+  }
+  std::vector<int32_t> new_of_old((size_t)N);
+  for (int64_t m = 0; m < n_mols; ++m) {
+    for (int64_t a = atom_ptr[m]; a < atom_ptr[m + 1]; ++a) {
+      const int d = adj_ptr[a + 1] - adj_ptr[a];
+      if (d < 0 || d > DCGC_MAX_DEG) {
+        dcgc_set_error("atom %lld has degree %d; the layout supports degrees 0..%d", (long long)a, d,
+                       DCGC_MAX_DEG);
+        return DCGC_ERR_DEGREE;
+      }
+      const int64_t r = cursor[d]++;
+      new_of_old[a] = (int32_t)r;
+      perm[r] = (int32_t)a;
+      membership[r] = (int32_t)m;
+    }
+  }
+  for (int d = 0; d < DCGC_N_DEG; ++d) {
+    if (cursor[d] != bucket_start[d] + info->deg_count[d]) {
+      dcgc_set_error("dcgc_layout_build: degree histogram changed since dcgc_layout_plan");
+      return DCGC_ERR_INVALID;
+    }
+  }
+  // neighbour lists: renumber to batch rows, keep list order (mol_graphs.py:139-141, 327-336)
+  for (int64_t m = 0; m < n_mols; ++m) {
+    const int64_t base = atom_ptr[m], n_local = atom_ptr[m + 1] - base;
+    for (int64_t a = base; a < base + n_local; ++a) {
+      const int d = adj_ptr[a + 1] - adj_ptr[a];
+      const int64_t r = new_of_old[a];
+      int32_t* dst = col_idx + edge_start[d] + (r - bucket_start[d]) * d;
+      const int32_t* src = adj_idx + adj_ptr[a];
+      for (int k = 0; k < d; ++k) {
+        const int64_t nb = src[k];
+        if (nb < 0 || nb >= n_local) {
+          dcgc_set_error("molecule %lld atom %lld: neighbour index %lld outside [0,%lld)", (long long)m,
+                         (long long)(a - base), (long long)nb, (long long)n_local);
+          return DCGC_ERR_INDEX;
+        }
+        dst[k] = new_of_old[base + nb];
+      }
+    }
+  }
+  build_derived(info, slab);
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_layout_plan_from_deg(const int64_t* deg_slice, int64_t n_segments,
+                                         int32_t tile_rows, dcgc_layout_info* info) {
+  DCGC_CHECK_ARG(deg_slice && info, "dcgc_layout_plan_from_deg: null argument");
+  DCGC_CHECK_ARG(tile_rows > 0 && n_segments >= 0, "dcgc_layout_plan_from_deg: bad sizes");
+  memset(info, 0, sizeof(*info));
+  for (int d = 0; d < DCGC_N_DEG; ++d) {
+    DCGC_CHECK_ARG(deg_slice[2 * d + 1] >= 0, "dcgc_layout_plan_from_deg: negative bucket size");
+    info->deg_count[d] = deg_slice[2 * d + 1];
+  }
+  info->n_mols = n_segments;
+  return finish_plan(info, n_segments, tile_rows);
+}
+
+extern "C" int dcgc_layout_build_from_deg(const int64_t* deg_slice, const int32_t* membership,
+                                          const int32_t* col_idx, const dcgc_layout_info* info,
+                                          void* slab_v) {
+  DCGC_CHECK_ARG(deg_slice && info && slab_v, "dcgc_layout_build_from_deg: null argument");
+  DCGC_CHECK_ARG((membership || info->n_atoms == 0) && (col_idx || info->n_edges == 0),
+                 "dcgc_layout_build_from_deg: null index array");
+  char* slab = (char*)slab_v;
+  const int64_t N = info->n_atoms, E = info->n_edges, S = info->n_segments;
+  for (int64_t i = 0; i < N; ++i) {
+    if (membership[i] < 0 || membership[i] >= S) {
+      dcgc_set_error("membership[%lld] = %d outside [0,%lld)", (long long)i, membership[i], (long long)S);
+      return DCGC_ERR_INDEX;
+    }
+  }
+  for (int64_t k = 0; k < E; ++k) {
+    if (col_idx[k] < 0 || col_idx[k] >= N) {
+      dcgc_set_error("adjacency entry %lld = %d outside [0,%lld)", (long long)k, col_idx[k], (long long)N);
+      return DCGC_ERR_INDEX;
+    }
+  }
+  memcpy(slab + info->off_membership, membership, (size_t)N * 4);
+  memcpy(slab + info->off_col_idx, col_idx, (size_t)E * 4);
+  int32_t* perm = (int32_t*)(slab + info->off_perm);
+  for (int64_t i = 0; i < N; ++i) perm[i] = (int32_t)i;
+  build_derived(info, slab);
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_layout_permute_features_host(const float* src, int64_t ld_src, const int32_t* perm,
+                                                 int64_t n_atoms, int32_t n_feat, float* dst,
+                                                 int64_t ld_dst, int32_t n_threads) {
+  DCGC_CHECK_ARG((src && perm && dst) || n_atoms == 0, "dcgc_layout_permute_features_host: null argument");
+  DCGC_CHECK_ARG(n_feat >= 0 && ld_src >= n_feat && ld_dst >= n_feat,
+                 "dcgc_layout_permute_features_host: leading dimension smaller than n_feat");
+  auto work = [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
+      float* d = dst + i * ld_dst;
+      memcpy(d, src + (int64_t)perm[i] * ld_src, (size_t)n_feat * 4);
+      for (int64_t c = n_feat; c < ld_dst; ++c) d[c] = 0.f;
+    }
+  };
+  if (n_threads <= 1 || n_atoms < 4096) {
+    work(0, n_atoms);
+    return DCGC_OK;
+  }
+  std::vector<std::thread> pool;
+  const int64_t chunk = (n_atoms + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; ++t) {
+    const int64_t lo = t * chunk, hi = std::min(n_atoms, lo + chunk);
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  for (auto& th : pool) th.join();
+  return DCGC_OK;
+}

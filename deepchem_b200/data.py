@@ -1,0 +1,108 @@
+"""Minimal dataset objects with the iteration contract GraphConvModel relies on.
+
+The model accepts any object with DeepChem's ``iterbatches(batch_size, epochs, deterministic,
+pad_batches)`` (deepchem/data/datasets.py:843-898) yielding ``(X, y, w, ids)`` where X is an
+object array of ConvMol-like molecules — a real ``dc.data.NumpyDataset`` / ``DiskDataset`` works
+unchanged.  ``PackedDataset`` is the fast native form: molecules live in a PackedMols shard
+(flat arrays, no Python objects) and batches are slices of it.
+"""
+import math
+
+import numpy as np
+
+from .synthetic import PackedMols
+
+
+def pad_batch(batch_size, X_b, y_b, w_b, ids_b):
+    """Pad by tiling the samples; only the first copy keeps its weights
+    (deepchem/data/datasets.py:142-218)."""
+    n = len(X_b)
+    if n == batch_size:
+        return X_b, y_b, w_b, ids_b
+    reps = np.arange(batch_size) % n
+    X_out = X_b.take(reps) if isinstance(X_b, PackedMols) else X_b[reps]
+    y_out = None if y_b is None else y_b[reps]
+    ids_out = ids_b[reps]
+    if w_b is None:
+        w_out = None
+    else:
+        w_out = np.zeros((batch_size,) + w_b.shape[1:], dtype=w_b.dtype)
+        w_out[:n] = w_b
+    return X_out, y_out, w_out, ids_out
+
+
+class _ArrayDataset(object):
+    def _init_arrays(self, n, y, w, ids, n_tasks):
+        if y is None:
+            y = np.zeros((n, n_tasks or 1), dtype=np.float32)
+            w = np.zeros((n, n_tasks or 1), dtype=np.float32) if w is None else w
+        y = np.asarray(y)
+        if y.ndim == 1:
+            y = y.reshape(-1, 1)
+        if w is None:
+            w = np.ones((n, y.shape[1]) if y.ndim > 1 else (n,), dtype=np.float32)
+        w = np.asarray(w)
+        if w.ndim == 1:
+            w = w.reshape(-1, 1)
+        if ids is None:
+            ids = np.arange(n)
+        self._y, self._w, self._ids = y, w, np.asarray(ids)
+
+    y = property(lambda self: self._y)
+    w = property(lambda self: self._w)
+    ids = property(lambda self: self._ids)
+
+    def __len__(self):
+        return len(self._y)
+
+    def get_shape(self):
+        return (len(self),), self._y.shape, self._w.shape, self._ids.shape
+
+    def _take_X(self, idx, contiguous):
+        raise NotImplementedError
+
+    def iterbatches(self, batch_size=None, epochs=1, deterministic=False, pad_batches=False):
+        n = len(self)
+        if batch_size is None:
+            batch_size = n
+        for _ in range(epochs):
+            perm = np.arange(n) if deterministic else np.random.permutation(n)
+            for b in range(math.ceil(n / batch_size) if n else 0):
+                idx = perm[b * batch_size:min(n, (b + 1) * batch_size)]
+                batch = (self._take_X(idx, deterministic), self._y[idx], self._w[idx], self._ids[idx])
+                if pad_batches:
+                    batch = pad_batch(batch_size, *batch)
+                yield batch
+
+
+class NumpyDataset(_ArrayDataset):
+    """X is an object array (or list) of ConvMol-like molecules."""
+
+    def __init__(self, X, y=None, w=None, ids=None, n_tasks=1):
+        if not isinstance(X, np.ndarray):
+            arr = np.empty(len(X), dtype=object)
+            for i, m in enumerate(X):
+                arr[i] = m
+            X = arr
+        self._X = X
+        self._init_arrays(len(X), y, w, ids, n_tasks)
+
+    X = property(lambda self: self._X)
+
+    def _take_X(self, idx, contiguous):
+        return self._X[idx]
+
+
+class PackedDataset(_ArrayDataset):
+    """Molecules stored as one PackedMols shard; batches are PackedMols slices."""
+
+    def __init__(self, packed, y=None, w=None, ids=None, n_tasks=1):
+        self.packed = packed
+        self._init_arrays(packed.n_mols, y, w, ids, n_tasks)
+
+    X = property(lambda self: self.packed)
+
+    def _take_X(self, idx, contiguous):
+        if contiguous and len(idx):
+            return self.packed.slice(int(idx[0]), int(idx[-1]) + 1)
+        return self.packed.take(idx)

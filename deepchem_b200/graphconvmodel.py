@@ -1,0 +1,462 @@
+"""GraphConvModel: the drop-in model class for the B200 path.
+
+Mirrors deepchem/models/torch_models/graphconvmodel.py (``TrimGraphOutput`` :21,
+``_GraphConvTorchModel`` :36, ``GraphConvModel`` :252) and the parts of ``TorchModel``
+(deepchem/models/torch_models/torch_model.py) the path goes through: ``fit`` / ``fit_generator``
+(:289-496), ``fit_on_batch``, ``predict`` / ``predict_on_batch`` / ``predict_embedding``
+(:547-761), ``evaluate``, ``save_checkpoint`` / ``restore`` (:996-1090).
+
+Differences from the reference torch port, each one deliberate:
+  * gradients flow through GraphConv / GraphPool (the reference detaches them);
+  * layer widths are generic (the reference hard-codes 64 in BatchNorm1d and the dense input);
+  * ``GraphConvModel(n_tasks, graph_conv_layers, dense_layer_size, mode)`` (the Keras call
+    shape, deepchem/models/graph_models.py:922-933) is accepted as well as the torch one.
+Kept as in the torch port: BatchNorm1d(eps=1e-3, momentum=0.99), dropout gated by the
+``training`` argument, untrimmed fingerprint output, -1/0 rows for absent molecules, state_dict
+keys.
+"""
+import logging
+import os
+import time
+from collections.abc import Sequence as SequenceCollection
+from typing import List
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from ._lib import ACT_NONE, ACT_RELU
+from .data import NumpyDataset, PackedDataset  # noqa: F401  (re-exported)
+from .layers import GraphConv, GraphGather, GraphPool, gemm_mode_code
+from .mol_graphs import BatchLayout, pack_convmols
+from .synthetic import PackedMols
+
+logger = logging.getLogger(__name__)
+
+
+class TrimGraphOutput(nn.Module):
+    """Trim to the number of real samples (graphconvmodel.py:21-33).  n_samples stays on the
+    host, so no device sync happens here."""
+
+    def forward(self, inputs):
+        n_samples = int(inputs[1])
+        return inputs[0][0:n_samples]
+
+
+class _GraphConvTorchModel(nn.Module):
+    """GraphConv -> BN -> (dropout) -> GraphPool per layer, Dense+ReLU -> BN -> GraphGather(tanh)
+    -> head (graphconvmodel.py:77-249; generic widths as in graph_models.py:835-902)."""
+
+    def __init__(self, n_tasks: int, number_input_features: List[int] = None,
+                 graph_conv_layers: List[int] = [64, 64], dense_layer_size: int = 128, dropout=0.0,
+                 mode: str = "classification", number_atom_features: int = 75, n_classes: int = 2,
+                 batch_normalize: bool = True, uncertainty: bool = False, batch_size: int = 100,
+                 gemm_mode: str = "fp32"):
+        super(_GraphConvTorchModel, self).__init__()
+        if mode not in ['classification', 'regression']:
+            raise ValueError("mode must be either 'classification' or 'regression'")
+        graph_conv_layers = list(graph_conv_layers)
+        if number_input_features is None:
+            number_input_features = [number_atom_features] + graph_conv_layers[:-1]
+        self.n_tasks, self.n_classes, self.mode = n_tasks, n_classes, mode
+        self.uncertainty = uncertainty
+        self.gemm_mode = gemm_mode_code(gemm_mode)
+        if not isinstance(dropout, SequenceCollection):
+            dropout = [dropout] * (len(graph_conv_layers) + 1)
+        if len(dropout) != len(graph_conv_layers) + 1:
+            raise ValueError('Wrong number of dropout probabilities provided')
+        if uncertainty:
+            if mode != "regression":
+                raise ValueError("Uncertainty is only supported in regression mode")
+            if any(d == 0.0 for d in dropout):
+                raise ValueError('Dropout must be included in every layer to predict uncertainty')
+
+        self.graph_convs = nn.ModuleList([
+            GraphConv(layer_size, input_size, activation_fn=F.relu, gemm_mode=gemm_mode)
+            for layer_size, input_size in zip(graph_conv_layers, number_input_features)])
+
+        def bn(width):
+            return nn.BatchNorm1d(num_features=width, eps=1e-3, momentum=0.99, affine=True,
+                                  track_running_stats=True) if batch_normalize else nn.Identity()
+        self.batch_norms = nn.ModuleList([bn(c) for c in graph_conv_layers] + [bn(dense_layer_size)])
+        self.dropouts = nn.ModuleList([nn.Dropout(rate) if rate > 0.0 else nn.Identity() for rate in dropout])
+        self.graph_pools = nn.ModuleList([GraphPool() for _ in graph_conv_layers])
+        self.dense = nn.Linear(graph_conv_layers[-1], dense_layer_size)
+        self.dense_act = F.relu
+        self.graph_gather = GraphGather(batch_size=batch_size, activation_fn=torch.tanh)
+        self.trim = TrimGraphOutput()
+        if self.mode == 'classification':
+            self.reshape_dense = nn.Linear(dense_layer_size * 2, n_tasks * n_classes)
+        else:
+            self.regression_dense = nn.Linear(dense_layer_size * 2, n_tasks)
+            if self.uncertainty:
+                self.uncertainty_dense = nn.Linear(dense_layer_size * 2, n_tasks)
+                self.uncertainty_trim = TrimGraphOutput()
+
+    def forward(self, inputs, training=False):
+        atom_features = inputs[0]
+        degree_slice = inputs[1]
+        membership = inputs[2]
+        n_samples = inputs[3]
+        deg_adjs = list(inputs[4:])
+
+        in_layer = atom_features
+        for i in range(len(self.graph_convs)):
+            gc1 = self.graph_convs[i]([in_layer, degree_slice, membership] + deg_adjs)
+            gc1 = self.batch_norms[i](gc1)
+            if training:
+                gc1 = self.dropouts[i](gc1)
+            in_layer = self.graph_pools[i]([gc1, degree_slice, membership] + deg_adjs)
+        # atom-level Dense + ReLU through the same grouped-GEMM kernel (single group)
+        denseact = ops.GroupLinearFn.apply(in_layer, self.dense.weight.t().contiguous(), self.dense.bias,
+                                           ACT_RELU, self.gemm_mode)
+        denseact = self.batch_norms[-1](denseact)
+        if training:
+            denseact = self.dropouts[-1](denseact)
+        neural_fingerprint = self.graph_gather([denseact, degree_slice, membership] + deg_adjs)
+        if self.mode == 'classification':
+            logits = torch.reshape(self.reshape_dense(neural_fingerprint), (-1, self.n_tasks, self.n_classes))
+            logits = self.trim([logits, n_samples])
+            output = F.softmax(logits, dim=2)
+            return [output, logits, neural_fingerprint]
+        output = self.trim([self.regression_dense(neural_fingerprint), n_samples])
+        if self.uncertainty:
+            log_var = self.uncertainty_trim([self.uncertainty_dense(neural_fingerprint), n_samples])
+            return [output, torch.exp(log_var), output, log_var, neural_fingerprint]
+        return [output, neural_fingerprint]
+
+
+def _standard_loss(mode, uncertainty):
+    """(loss * w).mean() over all elements, as _StandardLoss (torch_model.py:1275-1294) with
+    L2Loss (losses.py:76-94) / SoftmaxCrossEntropy (losses.py:236-259) / the uncertainty loss
+    (graphconvmodel.py:360-372)."""
+    def loss(outputs, labels, weights):
+        y, w = labels[0], weights[0]
+        if mode == "classification":
+            per = -torch.sum(y * F.log_softmax(outputs[0], dim=-1), dim=-1)
+        elif uncertainty:
+            out, log_var = outputs[0], outputs[1]
+            per = torch.square(out - y.reshape(out.shape)) / torch.exp(log_var) + log_var
+        else:
+            per = F.mse_loss(outputs[0], y.reshape(outputs[0].shape), reduction='none')
+        if w.dim() < per.dim():
+            w = w.reshape(tuple(w.shape) + (1,) * (per.dim() - w.dim()))
+        return (per * w).mean()
+    return loss
+
+
+def to_one_hot(y, n_classes=2):
+    """deepchem.metrics.to_one_hot"""
+    y = np.asarray(y).astype(np.int64).reshape(-1)
+    out = np.zeros((y.shape[0], n_classes), dtype=np.float32)
+    out[np.arange(y.shape[0]), y] = 1
+    return out
+
+
+class BatchInputs(list):
+    """The list default_generator yields ([features, deg_slice, membership, n_samples,
+    deg_adj_1..10], numpy views of the layout slab) carrying the BatchLayout itself so that
+    _prepare_batch can move everything with one H2D copy."""
+    layout = None
+    packed_features = None
+
+
+class GraphConvModel(object):
+    """Graph convolutional model on the B200 path.
+
+    ``GraphConvModel(n_tasks, number_input_features=[75, 64], graph_conv_layers=[64, 64], ...)``
+    (torch reference, graphconvmodel.py:284-296) and ``GraphConvModel(n_tasks, graph_conv_layers,
+    dense_layer_size, ...)`` (Keras reference, graph_models.py:922-933) are both accepted; a single
+    positional list is read as ``number_input_features`` only if it starts with
+    ``number_atom_features``.
+    """
+
+    def __init__(self, n_tasks, *args, graph_conv_layers=None, number_input_features=None,
+                 dense_layer_size=128, dropout=0.0, mode="classification", number_atom_features=75,
+                 n_classes=2, batch_size=100, batch_normalize=True, uncertainty=False,
+                 learning_rate=0.001, model_dir=None, device=None, gemm_mode="fp32", log_frequency=100,
+                 **kwargs):
+        args = list(args)
+        if args and isinstance(args[0], (list, tuple)):
+            first = list(args.pop(0))
+            if args and isinstance(args[0], (list, tuple)):      # torch: (n_tasks, in_widths, conv_widths)
+                number_input_features, graph_conv_layers = first, list(args.pop(0))
+            elif graph_conv_layers is not None or (first and first[0] == number_atom_features):
+                number_input_features = first                    # torch: (n_tasks, in_widths)
+            else:
+                graph_conv_layers = first                        # Keras: (n_tasks, conv_widths, dense, ...)
+        if args:
+            dense_layer_size = args.pop(0)
+        if args:
+            dropout = args.pop(0)
+        if args:
+            mode = args.pop(0)
+        if args:
+            raise TypeError("too many positional arguments")
+        if graph_conv_layers is None:
+            graph_conv_layers = [64, 64]
+        self.mode, self.n_tasks, self.n_classes = mode, n_tasks, n_classes
+        self.batch_size, self.uncertainty = batch_size, uncertainty
+        if device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("deepchem_b200.GraphConvModel needs a CUDA device (B200); "
+                                   "there is no CPU path")
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.model = _GraphConvTorchModel(
+            n_tasks, graph_conv_layers=graph_conv_layers, number_input_features=number_input_features,
+            dense_layer_size=dense_layer_size, dropout=dropout, mode=mode,
+            number_atom_features=number_atom_features, n_classes=n_classes,
+            batch_normalize=batch_normalize, uncertainty=uncertainty, batch_size=batch_size,
+            gemm_mode=gemm_mode).to(self.device)
+        if mode == "classification":
+            self.output_types = ['prediction', 'loss', 'embedding']
+        elif uncertainty:
+            self.output_types = ['prediction', 'variance', 'loss', 'loss', 'embedding']
+        else:
+            self.output_types = ['prediction', 'embedding']
+        self._prediction_outputs = [i for i, t in enumerate(self.output_types) if t == 'prediction']
+        self._loss_outputs = [i for i, t in enumerate(self.output_types) if t == 'loss'] or self._prediction_outputs
+        self._variance_outputs = [i for i, t in enumerate(self.output_types) if t == 'variance']
+        self._embedding_outputs = [i for i, t in enumerate(self.output_types) if t == 'embedding']
+        self._loss_fn = _standard_loss(mode, uncertainty)
+        self.learning_rate = learning_rate
+        self._pytorch_optimizer = torch.optim.Adam(self.model.parameters(), lr=learning_rate,
+                                                   betas=(0.9, 0.999), eps=1e-8)
+        self._global_step = 0
+        self._grad_slab = None
+        self.log_frequency = log_frequency
+        self.model_dir = model_dir
+        self.number_atom_features = number_atom_features
+
+    # ------------------------------------------------------------------ batching
+    def default_generator(self, dataset, epochs=1, mode='fit', deterministic=True, pad_batches=True):
+        """Dataset -> (inputs, [y], [w]) per batch (graphconvmodel.py:382-422).  The layout comes
+        from the C++ builder instead of ConvMol.agglomerate_mols."""
+        for (X_b, y_b, w_b, ids_b) in dataset.iterbatches(batch_size=self.batch_size, epochs=epochs,
+                                                          deterministic=deterministic,
+                                                          pad_batches=pad_batches):
+            if y_b is not None and self.mode == 'classification' and not (mode == 'predict'):
+                y_b = to_one_hot(np.asarray(y_b).flatten(), self.n_classes).reshape(
+                    -1, self.n_tasks, self.n_classes)
+            yield (self.batch_inputs(X_b), [y_b], [w_b])
+
+    def batch_inputs(self, X_b, pinned=True):
+        packed = X_b if isinstance(X_b, PackedMols) else pack_convmols(X_b)
+        n_seg = max(self.batch_size, packed.n_mols)
+        layout = BatchLayout.build(packed, n_segments=n_seg, pinned=pinned)
+        inputs = BatchInputs([None, layout.deg_slice, layout.membership, np.array(packed.n_mols)]
+                             + layout.deg_adjacency_lists()[1:])
+        inputs.layout = layout
+        inputs.packed_features = packed.features
+        return inputs
+
+    def _prepare_batch(self, batch):
+        """Host -> device boundary (torch_model.py:923-952): one copy for the integer slab, one
+        for the (unpermuted) features, then a device-side row permutation into degree-major
+        order with rows padded to a 16-byte multiple."""
+        inputs, labels, weights = batch
+        if getattr(inputs, "layout", None) is None:
+            raise TypeError("inputs must come from GraphConvModel.default_generator / batch_inputs")
+        topo = inputs.layout.to_device(self.device)
+        feats = torch.from_numpy(np.ascontiguousarray(inputs.packed_features, dtype=np.float32))
+        feats = feats.to(self.device, non_blocking=True)
+        x = ops.permute_rows(feats, topo.perm)
+        x._dcgc_zero_padded = True
+        dev_inputs = topo.model_inputs(x, n_samples=int(inputs[3]))
+
+        def conv(arrs):
+            out = []
+            for a in arrs or []:
+                if a is None:
+                    out.append(None)
+                else:
+                    a = np.asarray(a)
+                    if a.dtype == np.float64:
+                        a = a.astype(np.float32)
+                    out.append(torch.as_tensor(a, device=self.device))
+            return out
+        return dev_inputs, conv(labels), conv(weights)
+
+    # ------------------------------------------------------------------ training
+    def fit(self, dataset, nb_epoch=10, max_checkpoints_to_keep=5, checkpoint_interval=1000,
+            deterministic=False, restore=False, callbacks=[], all_losses=None):
+        return self.fit_generator(
+            self.default_generator(dataset, epochs=nb_epoch, deterministic=deterministic),
+            max_checkpoints_to_keep, checkpoint_interval, restore, callbacks=callbacks,
+            all_losses=all_losses)
+
+    def fit_generator(self, generator, max_checkpoints_to_keep=5, checkpoint_interval=1000, restore=False,
+                      callbacks=[], all_losses=None):
+        if not isinstance(callbacks, SequenceCollection):
+            callbacks = [callbacks]
+        self.model.train()
+        avg_loss = torch.zeros((), device=self.device)
+        last_avg_loss, averaged_batches = 0.0, 0
+        t0 = time.time()
+        for batch in generator:
+            if restore:
+                self.restore()
+                restore = False
+            batch_loss = self._train_step(*self._prepare_batch(batch))
+            self._global_step += 1
+            step = self._global_step
+            avg_loss = avg_loss + batch_loss.detach()
+            averaged_batches += 1
+            if step % self.log_frequency == 0:
+                last_avg_loss = float(avg_loss) / averaged_batches
+                logger.info('Ending global_step %d: Average loss %g' % (step, last_avg_loss))
+                if all_losses is not None:
+                    all_losses.append(last_avg_loss)
+                avg_loss = torch.zeros((), device=self.device)
+                averaged_batches = 0
+            if self.model_dir and checkpoint_interval > 0 and step % checkpoint_interval == checkpoint_interval - 1:
+                self.save_checkpoint(max_checkpoints_to_keep)
+            for c in callbacks:
+                try:
+                    c(self, step, iteration_loss=batch_loss)
+                except TypeError:
+                    c(self, step)
+        if averaged_batches > 0:
+            last_avg_loss = float(avg_loss) / averaged_batches
+            if all_losses is not None:
+                all_losses.append(last_avg_loss)
+        if self.model_dir and checkpoint_interval > 0:
+            self.save_checkpoint(max_checkpoints_to_keep)
+        logger.info("TIMING: model fitting took %0.3f s" % (time.time() - t0))
+        return last_avg_loss
+
+    def _train_step(self, inputs, labels, weights):
+        """zero_grad, forward, loss, backward, Adam step (torch_model.py:435-443).  The reference
+        never passes training=True here, so dropout stays off during fit."""
+        slab = self._grad_slab
+        if slab is None:
+            self._pytorch_optimizer.zero_grad(set_to_none=True)
+        else:
+            slab.zero()
+            slab.attach()
+        outputs = self.model(inputs)
+        outputs = [outputs[i] for i in self._loss_outputs]
+        loss = self._loss_fn(outputs, labels, weights)
+        loss.backward()
+        if slab is not None:
+            # data parallel: one all-reduce of the flat gradient slab, then identical Adam steps
+            slab.collect()
+            slab.all_reduce_mean()
+        self._pytorch_optimizer.step()
+        return loss
+
+    def enable_data_parallel(self):
+        """Average gradients over the default process group every step (equal per-rank batches
+        and a mean loss make the averaged gradient exact).  Parameters are broadcast
+        from rank 0 first so that every replica starts identical."""
+        import torch.distributed as dist
+        from .parallel import GradSlab, world_size
+        if world_size() > 1:
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, src=0)
+        self._grad_slab = GradSlab(self.model.parameters())
+        return self
+
+    def fit_on_batch(self, X, y, w):
+        """One training step on one batch of ConvMol-like molecules (or a PackedMols)."""
+        self.model.train()
+        n = len(X)
+        ds = PackedDataset(X, y, w) if isinstance(X, PackedMols) else NumpyDataset(X, y, w)
+        bs, self.batch_size = self.batch_size, max(self.batch_size, n)
+        try:
+            batch = next(self.default_generator(ds, deterministic=True, pad_batches=False))
+        finally:
+            self.batch_size = bs
+        loss = self._train_step(*self._prepare_batch(batch))
+        self._global_step += 1
+        return float(loss)
+
+    # ------------------------------------------------------------------ inference
+    def _predict(self, generator, output_idx):
+        self.model.eval()
+        results = None
+        with torch.no_grad():
+            for batch in generator:
+                inputs, _, _ = self._prepare_batch(batch)
+                outs = self.model(inputs)
+                vals = [outs[i].detach().cpu().numpy() for i in output_idx]
+                if results is None:
+                    results = [[] for _ in vals]
+                for r, v in zip(results, vals):
+                    r.append(v)
+        if results is None:
+            return []
+        final = [np.concatenate(r, axis=0) for r in results]
+        return final[0] if len(final) == 1 else final
+
+    def predict(self, dataset, transformers=[]):
+        gen = self.default_generator(dataset, mode='predict', deterministic=True, pad_batches=False)
+        return self._predict(gen, self._prediction_outputs)
+
+    def predict_on_batch(self, X):
+        ds = PackedDataset(X) if isinstance(X, PackedMols) else NumpyDataset(X)
+        return self.predict(ds)
+
+    def predict_embedding(self, dataset):
+        """Untrimmed fingerprints, batch_size rows per batch, as the reference returns them."""
+        gen = self.default_generator(dataset, mode='predict', deterministic=True, pad_batches=False)
+        return self._predict(gen, self._embedding_outputs)
+
+    def evaluate(self, dataset, metrics, transformers=[], per_task_metrics=False):
+        """{name: score} for metric callables f(y_true, y_pred[, w]) or dc.metrics.Metric-like
+        objects exposing ``compute_metric(y, y_pred, w)``."""
+        y_pred = self.predict(dataset)
+        if not isinstance(metrics, (list, tuple)):
+            metrics = [metrics]
+        out = {}
+        for m in metrics:
+            if hasattr(m, "compute_metric"):
+                out[getattr(m, "name", m.__class__.__name__)] = m.compute_metric(dataset.y, y_pred, dataset.w)
+            else:
+                out[getattr(m, "__name__", "metric")] = m(dataset.y, y_pred)
+        return out
+
+    # ------------------------------------------------------------------ checkpoints
+    def get_checkpoints(self, model_dir=None):
+        model_dir = model_dir or self.model_dir
+        if not model_dir or not os.path.isdir(model_dir):
+            return []
+        files = [f for f in os.listdir(model_dir) if f.startswith("checkpoint") and f.endswith(".pt")]
+        files.sort(key=lambda f: int(f[len("checkpoint"):-3]))
+        return [os.path.join(model_dir, f) for f in files]
+
+    def save_checkpoint(self, max_checkpoints_to_keep=5, model_dir=None):
+        """checkpoint1.pt is the newest; older ones are shifted up (torch_model.py:996-1042)."""
+        model_dir = model_dir or self.model_dir
+        if model_dir is None:
+            raise ValueError("model_dir is not set")
+        os.makedirs(model_dir, exist_ok=True)
+        data = {'model_state_dict': self.model.state_dict(),
+                'optimizer_state_dict': self._pytorch_optimizer.state_dict(),
+                'global_step': self._global_step}
+        tmp = os.path.join(model_dir, 'temp_checkpoint.pt')
+        torch.save(data, tmp)
+        paths = [os.path.join(model_dir, 'checkpoint%d.pt' % (i + 1)) for i in range(max_checkpoints_to_keep)]
+        if os.path.exists(paths[-1]):
+            os.remove(paths[-1])
+        for i in reversed(range(max_checkpoints_to_keep - 1)):
+            if os.path.exists(paths[i]):
+                os.rename(paths[i], paths[i + 1])
+        os.rename(tmp, paths[0])
+
+    def restore(self, checkpoint=None, model_dir=None):
+        if checkpoint is None:
+            cps = self.get_checkpoints(model_dir)
+            if not cps:
+                raise ValueError('No checkpoint found')
+            checkpoint = cps[0]
+        data = torch.load(checkpoint, map_location=self.device)
+        self.model.load_state_dict(data['model_state_dict'])
+        self._pytorch_optimizer.load_state_dict(data['optimizer_state_dict'])
+        self._global_step = data['global_step']
+
+    def get_global_step(self):
+        return self._global_step

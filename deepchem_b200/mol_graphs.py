@@ -1,0 +1,366 @@
+"""ConvMol batch layout, host side.
+
+Mirrors the reference interface of deepchem/feat/mol_graphs.py (``ConvMol`` :41,
+``ConvMol.agglomerate_mols`` :256, ``MultiConvMol`` :352) while the work is done by the C++
+layout builder behind the C ABI (include/dcgc.h, csrc/layout.cpp):
+
+    packed shard (PackedMols)  --dcgc_layout_plan/build-->  one pinned slab
+        deg_slice | membership | perm | CSR | CSR^T | molecule CSR | GEMM row tiles
+    slab  --one H2D copy-->  DeviceTopology (int32 views of one device buffer)
+
+``MultiConvMol`` exposes the reference's numpy view of the same slab (bit-exact with
+``agglomerate_mols``); ``DeviceTopology`` is what the CUDA ops consume.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .synthetic import PackedMols
+
+MAX_DEG = 10
+MIN_DEG = 0
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class ConvMol(object):
+    """One molecule: atom features + adjacency lists, atoms stably sorted by degree.
+
+    Same constructor and accessors as the reference class (mol_graphs.py:48-233); the
+    per-molecule degree sort (mol_graphs.py:113-185) is done with numpy here because it runs
+    once per molecule at featurisation time, outside the hot path.
+    """
+
+    def __init__(self, atom_features, adj_list, max_deg=MAX_DEG, min_deg=MIN_DEG):
+        atom_features = np.asarray(atom_features)
+        n = len(adj_list)
+        if atom_features.ndim != 2 or atom_features.shape[0] != n:
+            raise ValueError("atom_features must be [n_atoms, n_feat] with one row per adjacency list")
+        self.n_atoms, self.n_feat = atom_features.shape
+        self.max_deg, self.min_deg = max_deg, min_deg
+        deg = np.fromiter((len(a) for a in adj_list), dtype=np.int32, count=n)
+        if n and (deg.max() > max_deg or deg.min() < min_deg):
+            raise ValueError("atom degree outside [%d, %d]" % (min_deg, max_deg))
+        order = np.argsort(deg, kind="stable")
+        rank = np.empty(n, dtype=np.int64)
+        rank[order] = np.arange(n)
+        sdeg = deg[order]
+        self.atom_features = atom_features[order, :]
+        self.deg_list = sdeg.tolist()
+        self.degree_list = self.deg_list
+        self.membership = n * [0]
+        self.canon_adj_list = [rank[np.asarray(adj_list[i], dtype=np.int64)].tolist() if len(adj_list[i])
+                               else [] for i in order]
+        nb = max_deg + 1 - min_deg
+        counts = np.bincount(sdeg - min_deg, minlength=nb).astype(np.int32) if n else np.zeros(nb, np.int32)
+        starts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        self.deg_adj_lists = []
+        for d in range(min_deg, max_deg + 1):
+            lo, hi = starts[d - min_deg], starts[d - min_deg + 1]
+            if hi > lo and d > 0:
+                block = np.asarray(self.canon_adj_list[lo:hi], dtype=np.int32).reshape(hi - lo, d)
+            else:
+                block = np.zeros((hi - lo if d == 0 else 0, d), dtype=np.int32)
+            self.deg_adj_lists.append(block)
+        ds = np.zeros((nb, 2), dtype=np.int32)
+        ds[:, 1] = counts
+        ds[:, 0] = starts[:-1] * (counts != 0)      # starts of empty buckets are zeroed (:184)
+        self.deg_slice = ds
+        self.deg_start = starts.tolist()
+        self.deg_id_list = sdeg - min_deg
+        self.deg_block_indices = (np.arange(n) - starts[sdeg - min_deg]).astype(np.int32) if n \
+            else np.zeros(0, np.int32)
+
+    def get_atoms_with_deg(self, deg):
+        s, c = self.deg_slice[deg - self.min_deg]
+        return self.atom_features[s:s + c, :]
+
+    def get_num_atoms_with_deg(self, deg):
+        return self.deg_slice[deg - self.min_deg, 1]
+
+    def get_num_atoms(self):
+        return self.n_atoms
+
+    def get_atom_features(self):
+        return self.atom_features
+
+    def get_adjacency_list(self):
+        return self.canon_adj_list
+
+    def get_deg_adjacency_lists(self):
+        return self.deg_adj_lists
+
+    def get_deg_slice(self):
+        return self.deg_slice
+
+    @staticmethod
+    def get_null_mol(n_feat, max_deg=MAX_DEG, min_deg=MIN_DEG):
+        """One atom of every degree, each bonded to itself (mol_graphs.py:236-254)."""
+        feats = np.random.uniform(0, 1, [max_deg + 1 - min_deg, n_feat])
+        adj = [deg * [deg - min_deg] for deg in range(min_deg, max_deg + 1)]
+        return ConvMol(feats, adj)
+
+    @staticmethod
+    def agglomerate_mols(mols, max_deg=MAX_DEG, min_deg=MIN_DEG):
+        """Drop-in for the reference static method (mol_graphs.py:256-349)."""
+        if max_deg != MAX_DEG or min_deg != MIN_DEG:
+            raise ValueError("the B200 layout is built for degrees 0..10")
+        packed = pack_convmols(mols)
+        layout = BatchLayout.build(packed, n_segments=len(mols))
+        feats = np.concatenate([np.asarray(m.atom_features) for m in mols]) if len(mols) else \
+            np.zeros((0, 0))
+        return layout.multi_conv_mol(feats)
+
+
+def pack_convmols(mols):
+    """ConvMol-like objects (ours or the reference's: ``atom_features`` + ``canon_adj_list``)
+    -> PackedMols.  Python loop over molecules; datasets that care keep PackedMols shards."""
+    if isinstance(mols, PackedMols):
+        return mols
+    atom_ptr = np.zeros(len(mols) + 1, dtype=np.int64)
+    degs, adj = [], []
+    feats = []
+    for i, m in enumerate(mols):
+        a = m.canon_adj_list if hasattr(m, "canon_adj_list") else m.get_adjacency_list()
+        atom_ptr[i + 1] = atom_ptr[i] + len(a)
+        for nb in a:
+            degs.append(len(nb))
+            adj.extend(nb)
+        feats.append(np.asarray(m.atom_features, dtype=np.float32))
+    adj_ptr = np.concatenate([[0], np.cumsum(np.asarray(degs, dtype=np.int64))]) if degs else np.zeros(1, np.int64)
+    features = np.concatenate(feats) if feats else np.zeros((0, 0), np.float32)
+    return PackedMols(atom_ptr, adj_ptr, np.asarray(adj, dtype=np.int32), features)
+
+
+class MultiConvMol(object):
+    """numpy view of a batch, API of mol_graphs.py:352-375."""
+
+    def __init__(self, nodes, deg_adj_lists, deg_slice, membership, num_mols):
+        self.nodes = nodes
+        self.deg_adj_lists = deg_adj_lists
+        self.deg_slice = deg_slice
+        self.membership = membership
+        self.num_mols = num_mols
+        self.num_atoms = nodes.shape[0]
+
+    def get_deg_adjacency_lists(self):
+        return self.deg_adj_lists
+
+    def get_atom_features(self):
+        return self.nodes
+
+    def get_num_atoms(self):
+        return self.num_atoms
+
+    def get_num_molecules(self):
+        return self.num_mols
+
+
+_SLAB_FIELDS = (
+    # name, offset attribute, dtype, length expression
+    ("deg_slice", "off_deg_slice", np.int64, lambda i: 22),
+    ("membership", "off_membership", np.int32, lambda i: i.n_atoms),
+    ("perm", "off_perm", np.int32, lambda i: i.n_atoms),
+    ("row_ptr", "off_row_ptr", np.int32, lambda i: i.n_atoms + 1),
+    ("col_idx", "off_col_idx", np.int32, lambda i: i.n_edges),
+    ("t_row_ptr", "off_t_row_ptr", np.int32, lambda i: i.n_atoms + 1),
+    ("t_src", "off_t_src", np.int32, lambda i: i.n_edges),
+    ("t_slot", "off_t_slot", np.int32, lambda i: i.n_edges),
+    ("mol_ptr", "off_mol_ptr", np.int32, lambda i: i.n_segments + 1),
+    ("mol_atoms", "off_mol_atoms", np.int32, lambda i: i.n_atoms),
+    ("tiles", "off_tiles", np.int32, lambda i: 4 * i.n_tiles),
+)
+
+
+class BatchLayout(object):
+    """Host slab produced by the C++ builder + typed numpy views into it."""
+
+    def __init__(self, info, slab, slab_tensor=None):
+        self.info = info
+        self.slab = slab                  # np.uint8 [slab_bytes]
+        self.slab_tensor = slab_tensor    # pinned torch tensor sharing the memory (or None)
+        for name, off_attr, dt, length in _SLAB_FIELDS:
+            off = getattr(info, off_attr)
+            n = int(length(info))
+            setattr(self, name, slab[off:off + n * np.dtype(dt).itemsize].view(dt))
+        self.deg_slice = self.deg_slice.reshape(11, 2)
+        self.tiles = self.tiles.reshape(-1, 4)
+        self.deg_count = [int(c) for c in info.deg_count]
+
+    n_atoms = property(lambda self: int(self.info.n_atoms))
+    n_edges = property(lambda self: int(self.info.n_edges))
+    n_mols = property(lambda self: int(self.info.n_mols))
+    n_segments = property(lambda self: int(self.info.n_segments))
+    n_tiles = property(lambda self: int(self.info.n_tiles))
+
+    @staticmethod
+    def _alloc(nbytes, pinned):
+        if pinned:
+            import torch
+            t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+            return t.numpy()[:nbytes], t
+        return np.empty(nbytes, dtype=np.uint8), None
+
+    @staticmethod
+    def build(packed, n_segments=None, pinned=False):
+        """Run the C++ builder on a PackedMols shard (replaces agglomerate_mols)."""
+        L = _lib.lib()
+        n_mols = packed.n_mols
+        if n_segments is None:
+            n_segments = n_mols
+        info = _lib.LayoutInfo()
+        _lib.check(L.dcgc_layout_plan(n_mols, _ptr(packed.atom_ptr), _ptr(packed.adj_ptr), n_segments,
+                                      _lib.TILE_ROWS, ctypes.byref(info)))
+        slab, t = BatchLayout._alloc(int(info.slab_bytes), pinned)
+        _lib.check(L.dcgc_layout_build(n_mols, _ptr(packed.atom_ptr), _ptr(packed.adj_ptr),
+                                       _ptr(packed.adj_idx), ctypes.byref(info), _ptr(slab)))
+        return BatchLayout(info, slab, t)
+
+    @staticmethod
+    def from_reference_arrays(deg_slice, membership, deg_adj_lists, n_segments, pinned=False):
+        """Build from an already-agglomerated layout (the reference's arrays): used when a
+        caller hands the layers plain tensors.  deg_adj_lists: degree 1..10 (or 0..10)."""
+        L = _lib.lib()
+        deg_slice = np.ascontiguousarray(deg_slice, dtype=np.int64)
+        if deg_slice.shape != (11, 2):
+            raise ValueError("deg_slice must be [11, 2]")
+        lists = list(deg_adj_lists)
+        if len(lists) == 11:
+            lists = lists[1:]
+        if len(lists) != 10:
+            raise ValueError("expected the 10 adjacency tables of degree 1..10")
+        flat = []
+        for d, a in enumerate(lists, start=1):
+            a = np.asarray(a)
+            if a.size and (a.ndim != 2 or a.shape[1] != d):
+                raise ValueError("deg_adj_lists[%d] must be [N_%d, %d]" % (d, d, d))
+            if a.shape[0] != deg_slice[d, 1]:
+                raise ValueError("deg_adj_lists[%d] has %d rows, deg_slice says %d"
+                                 % (d, a.shape[0], deg_slice[d, 1]))
+            flat.append(a.reshape(-1).astype(np.int32))
+        col_idx = np.ascontiguousarray(np.concatenate(flat) if flat else np.zeros(0, np.int32))
+        membership = np.ascontiguousarray(membership, dtype=np.int32)
+        if membership.shape[0] != deg_slice[:, 1].sum():
+            raise ValueError("membership length does not match deg_slice")
+        info = _lib.LayoutInfo()
+        _lib.check(L.dcgc_layout_plan_from_deg(_ptr(deg_slice), n_segments, _lib.TILE_ROWS, ctypes.byref(info)))
+        slab, t = BatchLayout._alloc(int(info.slab_bytes), pinned)
+        _lib.check(L.dcgc_layout_build_from_deg(_ptr(deg_slice), _ptr(membership), _ptr(col_idx),
+                                                ctypes.byref(info), _ptr(slab)))
+        return BatchLayout(info, slab, t)
+
+    def deg_adjacency_lists(self):
+        """deg_adj_lists[0..10] as int32 [N_d, d] views of col_idx."""
+        out, off = [], 0
+        for d in range(11):
+            n = self.deg_count[d]
+            out.append(self.col_idx[off:off + n * d].reshape(n, d))
+            off += n * d
+        return out
+
+    def permute_features(self, features, ld_out=None, n_threads=4, out=None):
+        """Degree-major copy of a [N,F] float32 feature matrix (host)."""
+        features = np.ascontiguousarray(features, dtype=np.float32)
+        n, f = features.shape if features.ndim == 2 else (0, 0)
+        if n != self.n_atoms:
+            raise ValueError("features has %d rows, batch has %d atoms" % (n, self.n_atoms))
+        ld_out = ld_out or f
+        if out is None:
+            out = np.empty((n, ld_out), dtype=np.float32)
+        _lib.check(_lib.lib().dcgc_layout_permute_features_host(
+            _ptr(features), f, _ptr(self.perm), n, f, _ptr(out), ld_out, n_threads))
+        return out
+
+    def multi_conv_mol(self, features):
+        """Reference-shaped numpy object (features keep their dtype, as in the reference)."""
+        features = np.asarray(features)
+        nodes = features[self.perm] if features.size else features.reshape(self.n_atoms, -1)
+        return MultiConvMol(nodes, self.deg_adjacency_lists(), self.deg_slice.copy(),
+                            self.membership.copy(), self.n_mols)
+
+    def model_inputs(self, features, n_samples=None):
+        """The list GraphConvModel.default_generator yields (graphconvmodel.py:414-421)."""
+        mm = self.multi_conv_mol(features)
+        return [mm.get_atom_features(), mm.deg_slice, np.array(mm.membership),
+                np.array(self.n_mols if n_samples is None else n_samples)] + mm.deg_adj_lists[1:]
+
+    def to_device(self, device, non_blocking=True):
+        return DeviceTopology(self, device, non_blocking)
+
+
+class DeviceTopology(object):
+    """Device-resident integer layout: one buffer, int32 views.  Everything the kernels need
+    about the batch graph; features are NOT in here."""
+
+    def __init__(self, layout, device, non_blocking=True):
+        import torch
+        self.layout = layout
+        self.device = torch.device(device)
+        src = layout.slab_tensor if layout.slab_tensor is not None else torch.from_numpy(layout.slab)
+        nbytes = int(layout.info.slab_bytes)
+        self.buffer = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+        if nbytes:
+            self.buffer[:nbytes].copy_(src[:nbytes], non_blocking=non_blocking)
+        info = layout.info
+        for name, off_attr, dt, length in _SLAB_FIELDS:
+            off = getattr(info, off_attr)
+            n = int(length(info))
+            tdt = torch.int64 if dt is np.int64 else torch.int32
+            view = self.buffer[off:off + n * np.dtype(dt).itemsize].view(tdt)
+            setattr(self, name, view)
+        self.deg_slice = self.deg_slice.view(11, 2)
+        self.tiles = self.tiles.view(-1, 4)
+        self.n_atoms, self.n_edges = layout.n_atoms, layout.n_edges
+        self.n_mols, self.n_segments, self.n_tiles = layout.n_mols, layout.n_segments, layout.n_tiles
+        self.deg_count = layout.deg_count
+        self._deg_count_c = (ctypes.c_int64 * 11)(*self.deg_count)
+
+    def deg_adjacency_lists(self):
+        out, off = [], 0
+        for d in range(11):
+            n = self.deg_count[d]
+            out.append(self.col_idx[off:off + n * d].view(n, d))
+            off += n * d
+        return out
+
+    def model_inputs(self, features, n_samples=None):
+        """[features, deg_slice, membership, n_samples, deg_adj_1..10] as device tensors, with
+        this topology attached to the deg_slice tensor so that the layers find it."""
+        import torch
+        deg_slice = self.deg_slice
+        attach(deg_slice, self)
+        ns = torch.tensor(self.n_mols if n_samples is None else n_samples)
+        return [features, deg_slice, self.membership, ns] + self.deg_adjacency_lists()[1:]
+
+
+def attach(tensor, topo):
+    tensor._dcgc_topology = topo
+    return tensor
+
+
+def topology_of(inputs, n_segments=None):
+    """Find (or derive) the DeviceTopology for a layer input list
+    ``[features, deg_slice, membership, (deg_adj_1..10)]``.
+
+    Fast path: the generator attached it to ``deg_slice``.  Slow path (plain tensors, as in the
+    reference's layer tests): copy the small integer arrays to the host, run the C++ builder and
+    upload — a synchronising fallback for hand-built inputs, cached on the tensor."""
+    deg_slice = inputs[1]
+    topo = getattr(deg_slice, "_dcgc_topology", None)
+    if topo is not None and (n_segments is None or topo.n_segments >= n_segments):
+        return topo
+    membership = inputs[2]
+    adjs = [t for t in inputs[3:] if getattr(t, "dim", lambda: 0)() == 2]
+    ds = deg_slice.detach().cpu().numpy()
+    mem = membership.detach().cpu().numpy().astype(np.int32)
+    lists = [a.detach().cpu().numpy() for a in adjs]
+    nseg = int(mem.max()) + 1 if mem.size else 0
+    if n_segments is not None:
+        nseg = max(nseg, int(n_segments))
+    layout = BatchLayout.from_reference_arrays(ds, mem, lists, nseg)
+    topo = layout.to_device(inputs[0].device)
+    attach(deg_slice, topo)
+    return topo

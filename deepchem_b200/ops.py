@@ -1,0 +1,404 @@
+"""PyTorch custom ops (autograd Functions) over the C ABI of libdcgc.
+
+PyTorch owns device memory and the stream; every compute call goes through ctypes into
+hand-written sm_100a kernels (include/dcgc.h).  There is no fallback: tensors must be CUDA
+float32 tensors and the library must load.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ACT_TANH, GEMM_FP32, check
+
+_ACT_CODES = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "tanh": ACT_TANH}
+
+
+def act_code(act):
+    """Map an activation spec (None / 'relu' / 'tanh' / torch function) to a fused epilogue code;
+    returns None if the activation cannot be fused (caller applies it with torch)."""
+    if act in _ACT_CODES:
+        return _ACT_CODES[act]
+    if act in (torch.relu, torch.nn.functional.relu):
+        return ACT_RELU
+    if act in (torch.tanh, torch.nn.functional.tanh):
+        return ACT_TANH
+    if isinstance(act, torch.nn.ReLU):
+        return ACT_RELU
+    if isinstance(act, torch.nn.Tanh):
+        return ACT_TANH
+    return None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check_dev(t, name):
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: the deepchem_b200 ops have no CPU path" % name)
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32, got %s" % (name, t.dtype))
+
+
+def _rowmajor(t):
+    """Return a tensor whose rows are contiguous (stride(1) == 1); views with a padded leading
+    dimension are used as they are."""
+    if t.dim() != 2:
+        raise ValueError("expected a 2-D tensor")
+    if t.shape[1] > 1 and t.stride(1) != 1:
+        return t.contiguous()
+    if t.shape[1] <= 1 and t.shape[0] > 1 and t.stride(0) < 1:
+        return t.contiguous()
+    return t
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def padded_empty(n_rows, width, device, dtype=torch.float32):
+    """[n_rows, width] view of a buffer whose leading dimension is a multiple of 4 floats, so
+    that every row starts 16-byte aligned (pad columns are zero)."""
+    ld = (width + 3) // 4 * 4
+    if ld == width:
+        return torch.empty(n_rows, width, device=device, dtype=dtype)
+    buf = torch.zeros(n_rows, ld, device=device, dtype=dtype)
+    return buf[:, :width]
+
+
+# ------------------------------------------------------------------------------------------
+# launch accounting (bench.py: gpu_launches, per-kernel CUDA-event timing for the roofline)
+# ------------------------------------------------------------------------------------------
+_launches = 0
+_prof = None
+
+
+def launch_count():
+    """Number of libdcgc kernels launched by this process so far."""
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def profile_begin(name):
+    """Bracket every launch of the entry point `name` with CUDA events on the launching stream."""
+    global _prof
+    _prof = {"name": name, "events": []}
+
+
+def profile_end():
+    """-> {'launches', 'ms' (sum of event durations), 'bytes' (sum of algorithmic bytes)}"""
+    global _prof
+    prof, _prof = _prof, None
+    if prof is None:
+        return None
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b, _ in prof["events"])
+    return {"name": prof["name"], "launches": len(prof["events"]), "ms": ms,
+            "bytes": sum(nb for _, _, nb in prof["events"])}
+
+
+class _Timed(object):
+    def __init__(self, name, nbytes):
+        self.on = _prof is not None and _prof["name"] == name
+        self.nbytes = nbytes
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.e1.record()
+            _prof["events"].append((self.e0, self.e1, self.nbytes))
+
+
+# ------------------------------------------------------------------------------------------
+# raw launchers (no autograd)
+# ------------------------------------------------------------------------------------------
+def gather_sum(x, row_ptr, idx, n_rows_out, addend=None, out=None):
+    x = _rowmajor(x)
+    width = x.shape[1]
+    if out is None:
+        out = addend if addend is not None else padded_empty(n_rows_out, width, x.device)
+    # algorithmic bytes: read x once, write out once, read the index list
+    # (+ the addend when the self-path gradient is fused in)
+    nbytes = (2 + (addend is not None)) * n_rows_out * width * 4 + idx.numel() * 4
+    with _Timed("dcgc_gather_sum", nbytes):
+        check(_lib.lib().dcgc_gather_sum(_p(x), _ld(x), _p(row_ptr), _p(idx), n_rows_out, width,
+                                         _p(addend), _ld(addend) if addend is not None else 0,
+                                         _p(out), _ld(out), _stream()))
+    _count()
+    return out
+
+
+def permute_rows(src, perm, n_feat=None, ld_out=None):
+    src = _rowmajor(src)
+    n_feat = src.shape[1] if n_feat is None else n_feat
+    n = perm.shape[0]
+    ld_out = ld_out or (n_feat + 3) // 4 * 4
+    out = torch.empty(n, ld_out, device=src.device, dtype=torch.float32)
+    check(_lib.lib().dcgc_permute_rows(_p(src), _ld(src), _p(perm), n, n_feat, _p(out), ld_out, _stream()))
+    _count()
+    return out[:, :n_feat]
+
+
+def group_gemm_fwd(a1, a2, w, bias, topo, act, mode=GEMM_FP32):
+    """y = act([a1|a2] . w[g] + bias[g]); topo=None means a single group over all rows."""
+    n_rows, k1 = a1.shape
+    k2 = a2.shape[1] if a2 is not None else 0
+    n = w.shape[-1]
+    y = padded_empty(n_rows, n, a1.device)
+    tiles = topo.tiles if topo is not None else None
+    check(_lib.lib().dcgc_group_gemm_fwd(
+        mode, _p(a1), _ld(a1), k1, _p(a2), _ld(a2) if a2 is not None else 0, k2, _p(w), _p(bias), n,
+        _p(tiles), topo.n_tiles if topo is not None else 0, _lib.TILE_ROWS, n_rows, act, _p(y), _ld(y),
+        _stream()))
+    _count()
+    return y
+
+
+def group_gemm_dgrad(g, w, k1, k2, topo, want1=True, want2=True, mode=GEMM_FP32):
+    n_rows, n = g.shape
+    d1 = padded_empty(n_rows, k1, g.device) if want1 else None
+    d2 = padded_empty(n_rows, k2, g.device) if (want2 and k2) else None
+    tiles = topo.tiles if topo is not None else None
+    check(_lib.lib().dcgc_group_gemm_dgrad(
+        mode, _p(g), _ld(g), n, _p(w), k1, k2, _p(tiles), topo.n_tiles if topo is not None else 0,
+        _lib.TILE_ROWS, n_rows, _p(d1), _ld(d1) if d1 is not None else 0, _p(d2),
+        _ld(d2) if d2 is not None else 0, _stream()))
+    _count()
+    return d1, d2
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.type, device.index)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def group_gemm_wgrad(a1, a2, g, topo, n_groups, mode=GEMM_FP32):
+    """dW [n_groups, k1+k2, n], dbias [n_groups, n]; deterministic."""
+    n_rows, k1 = a1.shape
+    k2 = a2.shape[1] if a2 is not None else 0
+    n = g.shape[1]
+    L = _lib.lib()
+    dw = torch.empty(n_groups, k1 + k2, n, device=g.device, dtype=torch.float32)
+    db = torch.empty(n_groups, n, device=g.device, dtype=torch.float32)
+    nbytes = int(L.dcgc_group_gemm_wgrad_workspace(k1, k2, n, n_groups))
+    ws = _workspace(nbytes, g.device)
+    if topo is not None:
+        counts = topo._deg_count_c
+    else:
+        counts = (ctypes.c_int64 * 1)(n_rows)
+    check(L.dcgc_group_gemm_wgrad(mode, _p(a1), _ld(a1), k1, _p(a2), _ld(a2) if a2 is not None else 0, k2,
+                                  _p(g), _ld(g), n, counts, n_groups, _p(dw), _p(db), _p(ws), nbytes,
+                                  _stream()))
+    _count(2)
+    return dw, db
+
+
+# ------------------------------------------------------------------------------------------
+# autograd Functions
+# ------------------------------------------------------------------------------------------
+class NeighborSum(torch.autograd.Function):
+    """S[i] = sum_{j in N(i)} X[j]  (K1) with the transposed gather as backward (K5)."""
+
+    @staticmethod
+    def forward(ctx, x, topo):
+        _check_dev(x, "atom_features")
+        ctx.topo = topo
+        return gather_sum(x, topo.row_ptr, topo.col_idx, topo.n_atoms)
+
+    @staticmethod
+    def backward(ctx, ds):
+        topo = ctx.topo
+        return gather_sum(_rowmajor(ds), topo.t_row_ptr, topo.t_src, topo.n_atoms), None
+
+
+class GraphConvFn(torch.autograd.Function):
+    """Fused GraphConv (K1 + K2 forward, K5 + K6 backward).
+
+    w: [11, 2*Fp, C] packed weights (rows 0:Fp self, Fp:2Fp neighbour; Fp = padded input width),
+    bias: [11, C].  x may be a [N, F] view of a zero-padded [N, Fp] buffer."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, topo, act, mode):
+        _check_dev(x, "atom_features")
+        x = _rowmajor(x)
+        fp = w.shape[1] // 2
+        xk = _widen(x, fp)
+        s = gather_sum(xk, topo.row_ptr, topo.col_idx, topo.n_atoms)
+        y = group_gemm_fwd(xk, s, w, bias, topo, act, mode)
+        ctx.topo, ctx.act, ctx.mode, ctx.f = topo, act, mode, x.shape[1]
+        ctx.save_for_backward(xk, s, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xk, s, w, y = ctx.saved_tensors
+        topo, mode = ctx.topo, ctx.mode
+        fp = w.shape[1] // 2
+        g = _rowmajor(dy)
+        if ctx.act == ACT_RELU:
+            g = g * (y > 0)
+        elif ctx.act == ACT_TANH:
+            g = g * (1 - y * y)
+        dw = db = dx = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw, db = group_gemm_wgrad(xk, s, g, topo, 11, mode)
+        if ctx.needs_input_grad[0]:
+            d1, d2 = group_gemm_dgrad(g, w, fp, fp, topo, True, True, mode)
+            dx = gather_sum(d2, topo.t_row_ptr, topo.t_src, topo.n_atoms, addend=d1)
+            dx = dx[:, :ctx.f]
+        return dx, dw, db, None, None, None
+
+
+def _widen(x, fp):
+    """[N,F] -> [N,fp] sharing storage when x is a view of a zero-padded buffer with ld >= fp."""
+    n, f = x.shape
+    if f == fp:
+        return x
+    if n > 0 and x.stride(0) >= fp and x.stride(1) == 1 and getattr(x, "_dcgc_zero_padded", False):
+        return torch.as_strided(x, (n, fp), (x.stride(0), 1))
+    out = torch.zeros(n, fp, device=x.device, dtype=x.dtype)
+    out[:, :f] = x
+    return out
+
+
+class GroupLinearFn(torch.autograd.Function):
+    """y = act(x . w + b) with w [K, n] (single group): the atom-level Dense layer."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, act, mode):
+        _check_dev(x, "input")
+        x = _rowmajor(x)
+        y = group_gemm_fwd(x, None, w, bias, None, act, mode)
+        ctx.act, ctx.mode = act, mode
+        ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, y = ctx.saved_tensors
+        g = _rowmajor(dy)
+        if ctx.act == ACT_RELU:
+            g = g * (y > 0)
+        elif ctx.act == ACT_TANH:
+            g = g * (1 - y * y)
+        dw = db = dx = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dw, db = group_gemm_wgrad(x, None, g, None, 1, ctx.mode)
+            dw, db = dw[0], db[0]
+        if ctx.needs_input_grad[0]:
+            dx, _ = group_gemm_dgrad(g, w, x.shape[1], 0, None, True, False, ctx.mode)
+        return dx, dw, db, None, None
+
+
+class GraphPoolFn(torch.autograd.Function):
+    """P[i] = max(X[i], max_{j in N(i)} X[j]) (K3); backward gathers over CSR^T (K7).
+    (The C entry point can also fold a per-channel affine; the fused model engine uses that.)"""
+
+    @staticmethod
+    def forward(ctx, x, topo):
+        _check_dev(x, "atom_features")
+        x = _rowmajor(x)
+        n, c = x.shape
+        out = padded_empty(n, c, x.device)
+        ld_arg = (c + 3) // 4 * 4
+        arg = torch.empty(n, ld_arg, dtype=torch.uint8, device=x.device) if x.requires_grad else None
+        check(_lib.lib().dcgc_pool_fwd(_p(x), _ld(x), None, None, _p(topo.row_ptr), _p(topo.col_idx),
+                                       n, c, _p(out), _ld(out), _p(arg), ld_arg, _stream()))
+        _count()
+        ctx.topo = topo
+        ctx.save_for_backward(arg)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (arg,) = ctx.saved_tensors
+        topo = ctx.topo
+        dy = _rowmajor(dy)
+        n, c = dy.shape
+        dx = padded_empty(n, c, dy.device)
+        check(_lib.lib().dcgc_pool_bwd(_p(dy), _ld(dy), _p(arg), arg.stride(0), None, _p(topo.t_row_ptr),
+                                       _p(topo.t_src), _p(topo.t_slot), n, c, _p(dx), _ld(dx), _stream()))
+        _count()
+        return dx, None
+
+
+class GraphGatherFn(torch.autograd.Function):
+    """Z[g] = act([sum_{i in g} X[i] | max_{i in g} X[i]]) (K4) and its backward (K7)."""
+
+    @staticmethod
+    def forward(ctx, x, topo, n_segments, act):
+        _check_dev(x, "atom_features")
+        x = _rowmajor(x)
+        n, d = x.shape
+        if n_segments > topo.n_segments:
+            raise ValueError("layout was built for %d segments, GraphGather asks for %d"
+                             % (topo.n_segments, n_segments))
+        out = torch.empty(n_segments, 2 * d, device=x.device, dtype=torch.float32)
+        argrow = torch.empty(n_segments, d, device=x.device, dtype=torch.int32) if x.requires_grad else None
+        check(_lib.lib().dcgc_gather_fwd(_p(x), _ld(x), _p(topo.mol_ptr), _p(topo.mol_atoms), n_segments, d,
+                                         act, _p(out), 2 * d, _p(argrow), _stream()))
+        _count()
+        ctx.topo, ctx.act, ctx.shape = topo, act, (n, d)
+        ctx.save_for_backward(out, argrow)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        out, argrow = ctx.saved_tensors
+        n, d = ctx.shape
+        dout = _rowmajor(dout)
+        dx = padded_empty(n, d, dout.device)
+        check(_lib.lib().dcgc_gather_bwd(_p(dout), _ld(dout), _p(out), 2 * d, _p(argrow),
+                                         _p(ctx.topo.membership), n, d, ctx.act, _p(dx), _ld(dx), _stream()))
+        _count()
+        return dx, None, None, None
+
+
+def pack_graphconv_weights(W_list, b_list, fp):
+    """21 reference parameters -> packed [11, 2*fp, C] / [11, C] (differentiable).
+
+    Reference order (torch_models/layers.py:6189-6226): W[2(d-1)] neighbour weight of degree d,
+    W[2(d-1)+1] self weight of degree d, W[20] degree-0 self weight.  Packed group d holds
+    [self ; neighbour]; group 0's neighbour half is zero."""
+    f, c = W_list[0].shape
+    dev = W_list[0].device
+    wst = torch.stack(list(W_list) + [torch.zeros(f, c, device=dev, dtype=W_list[0].dtype)])   # [22,F,C]
+    if fp != f:
+        wst = torch.nn.functional.pad(wst, (0, 0, 0, fp - f))
+    idx = _pack_index(dev)
+    w = wst[idx].reshape(11, 2 * fp, c)
+    bst = torch.stack(list(b_list) + [torch.zeros(c, device=dev, dtype=b_list[0].dtype)])      # [22,C]
+    bias = bst[idx].sum(1)
+    return w.contiguous(), bias.contiguous()
+
+
+_pack_idx_cache = {}
+
+
+def _pack_index(device):
+    key = str(device)
+    if key not in _pack_idx_cache:
+        rows = [[20, 21]] + [[2 * (d - 1) + 1, 2 * (d - 1)] for d in range(1, 11)]
+        _pack_idx_cache[key] = torch.tensor(rows, dtype=torch.long, device=device)
+    return _pack_idx_cache[key]

@@ -1,0 +1,185 @@
+/*
+ * dcgc.h — C ABI of libdcgc: the B200 (sm_100a) GraphConv / GraphPool / GraphGather /
+ * DMPNN message-passing path for DeepChem.
+ *
+ * The reference (pandegroup/deepchem) has no native code and therefore no FFI to mirror;
+ * each entry point below replaces the Python/libtorch code cited next to it and is what a
+ * maintainer would bind (ctypes stub in INTEGRATION.md).  Conventions:
+ *   - every function returns an int status (DCGC_OK == 0, negative on error) and never
+ *     throws or aborts; dcgc_last_error() returns a thread-local message.
+ *   - "dev" pointers are device pointers owned by the caller (PyTorch caching allocator on
+ *     the Python side); kernels only write caller-provided outputs / workspaces.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All device
+ *     functions are asynchronous on that stream and re-entrant across streams.
+ *   - matrices are row-major with an explicit leading dimension `ld*` (in elements).
+ *   - integer layout arrays are int32 unless stated; deg_slice is int64 as in the reference.
+ */
+#ifndef DCGC_H_
+#define DCGC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCGC_OK 0
+#define DCGC_ERR_INVALID (-1) /* bad argument (null pointer, negative size, unsupported width) */
+#define DCGC_ERR_DEGREE (-2)  /* an atom has more than max_deg neighbours (feat/graph_features.py:34-36) */
+#define DCGC_ERR_INDEX (-3)   /* neighbour index outside its molecule */
+#define DCGC_ERR_CUDA (-4)    /* CUDA runtime error; message has the cudaError string */
+#define DCGC_ERR_NOMEM (-5)   /* workspace too small */
+
+#define DCGC_MAX_DEG 10
+#define DCGC_N_DEG 11
+
+/* activation codes for fused epilogues */
+#define DCGC_ACT_NONE 0
+#define DCGC_ACT_RELU 1
+#define DCGC_ACT_TANH 2
+
+/* GEMM arithmetic modes */
+#define DCGC_GEMM_FP32 0 /* SIMT FFMA, fp32 in / fp32 accumulate: the 1e-5 parity mode        */
+#define DCGC_GEMM_BF16 1 /* tcgen05 kind::f16, bf16 operands / fp32 accumulate: the 2e-2 mode  */
+#define DCGC_GEMM_TF32X3 2 /* tcgen05 kind::tf32 with 3-term split: fp32-grade accuracy       */
+
+const char* dcgc_last_error(void);
+int dcgc_version(void);
+/* 1 if a CUDA device with compute capability 10.x is visible, 0 if not, <0 on error */
+int dcgc_device_ok(void);
+
+/* --------------------------------------------------------------------------------------------
+ * Host layout builder.  Replaces ConvMol.agglomerate_mols (deepchem/feat/mol_graphs.py:256-349)
+ * and the per-molecule degree sort of ConvMol.__init__ (mol_graphs.py:113-185): the composite of
+ * the two stable sorts is one stable counting sort of all atoms by degree.
+ *
+ * Input: a packed shard (no Python objects): atom_ptr[n_mols+1], adj_ptr[n_atoms+1],
+ * adj_idx[n_edges] (molecule-local neighbour ids in adjacency-list order).
+ * Output: one host slab (caller-allocated, ideally pinned) holding every array the device path
+ * needs, at the byte offsets reported in dcgc_layout_info; a single H2D copy moves it.
+ * Bit-exact with the reference for deg_slice (int64 [11,2], running starts), membership and
+ * deg_adj_1..10 (col_idx is their concatenation, flattened row-major).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dcgc_layout_info {
+  int64_t n_mols;     /* molecules in this batch                                    */
+  int64_t n_segments; /* GraphGather segments (batch_size >= n_mols; extras are empty) */
+  int64_t n_atoms;    /* N                                                          */
+  int64_t n_edges;    /* E = sum_d d*N_d directed neighbour entries                 */
+  int64_t n_tiles;    /* row tiles of at most tile_rows rows that never straddle a degree bucket */
+  int32_t tile_rows;
+  int32_t reserved;
+  int64_t deg_count[DCGC_N_DEG]; /* N_d (host copy of deg_slice[:,1]) */
+  /* byte offsets into the slab (each 256-byte aligned) */
+  int64_t off_deg_slice;  /* int64 [11,2]                                              */
+  int64_t off_membership; /* int32 [N]                                                 */
+  int64_t off_perm;       /* int32 [N]   row i of the batch = atom perm[i] of the packed shard */
+  int64_t off_row_ptr;    /* int32 [N+1]                                               */
+  int64_t off_col_idx;    /* int32 [E]   == concat(deg_adj_1.flatten(), ..., deg_adj_10.flatten()) */
+  int64_t off_t_row_ptr;  /* int32 [N+1] transposed CSR                                */
+  int64_t off_t_src;      /* int32 [E]   row i referencing this row, ordered by (i, slot) */
+  int64_t off_t_slot;     /* int32 [E]   slot k of that reference in row i's list       */
+  int64_t off_mol_ptr;    /* int32 [n_segments+1]                                      */
+  int64_t off_mol_atoms;  /* int32 [N]   rows of each molecule, ascending              */
+  int64_t off_tiles;      /* int32 [n_tiles,4] = (row0, n_rows, degree, 0)             */
+  int64_t slab_bytes;
+} dcgc_layout_info;
+
+/* Pass 1: validate degrees, count, and compute sizes / offsets.  O(N). */
+int dcgc_layout_plan(int64_t n_mols, const int32_t* atom_ptr, const int32_t* adj_ptr,
+                     int64_t n_segments, int32_t tile_rows, dcgc_layout_info* info);
+/* Pass 2: fill the slab.  `info` must come from dcgc_layout_plan on the same inputs. */
+int dcgc_layout_build(int64_t n_mols, const int32_t* atom_ptr, const int32_t* adj_ptr,
+                      const int32_t* adj_idx, const dcgc_layout_info* info, void* slab);
+/* Host feature permutation into degree-major order (the numpy-facing MultiConvMol path):
+ * dst[i, 0:n_feat] = src[perm[i], 0:n_feat]; columns n_feat..ld_dst-1 are zeroed. */
+int dcgc_layout_permute_features_host(const float* src, int64_t ld_src, const int32_t* perm,
+                                      int64_t n_atoms, int32_t n_feat, float* dst, int64_t ld_dst,
+                                      int32_t n_threads);
+/* Derive the same slab from an already-agglomerated reference layout (deg_slice, membership,
+ * col_idx = concatenated deg_adj lists): used when a caller hands the layers plain tensors. */
+int dcgc_layout_plan_from_deg(const int64_t* deg_slice, int64_t n_segments, int32_t tile_rows,
+                              dcgc_layout_info* info);
+int dcgc_layout_build_from_deg(const int64_t* deg_slice, const int32_t* membership,
+                               const int32_t* col_idx, const dcgc_layout_info* info, void* slab);
+
+/* --------------------------------------------------------------------------------------------
+ * Device kernels.  fp32 activations, row-major, leading dimensions in floats.
+ * ------------------------------------------------------------------------------------------ */
+
+/* dst[i, 0:n_feat] = src[perm[i], 0:n_feat], pad columns zeroed (device-side feature permute,
+ * replaces `atoms_by_deg[order]`, mol_graphs.py:277). */
+int dcgc_permute_rows(const float* src_dev, int64_t ld_src, const int32_t* perm_dev, int64_t n_rows,
+                      int32_t n_feat, float* dst_dev, int64_t ld_dst, void* stream);
+
+/* K1 / K5 / K8 — CSR gather-sum: out[i,:] = sum_{e in [row_ptr[i], row_ptr[i+1])} x[idx[e], :].
+ * Forward of GraphConv.sum_neigh (torch_models/layers.py:6236-6246) with (row_ptr, col_idx);
+ * its backward (the transposed scatter) with (t_row_ptr, t_src); DMPNN `message[mapping].sum(1)`
+ * (layers.py:1629) with an ELL table turned into CSR.  Rows with no entries are written as zeros.
+ * If addend_dev is non-null, out[i,:] = addend[i,:] + sum (out may alias addend): this fuses the
+ * `self-path + neighbour-path` add of the GraphConv input gradient.
+ * No atomics: one thread owns one 16-byte group of one output row; summation order = index order. */
+int dcgc_gather_sum(const float* x_dev, int64_t ld_x, const int32_t* row_ptr_dev,
+                    const int32_t* idx_dev, int64_t n_rows_out, int32_t width,
+                    const float* addend_dev, int64_t ld_add, float* out_dev, int64_t ld_out,
+                    void* stream);
+
+/* K3 — GraphPool forward (layers.py:6342-6367): out[i,c] = max(x[i,c], max_k x[col[row_ptr[i]+k],c]).
+ * If scale/shift are non-null the per-channel affine y = x*scale[c] + shift[c] (a folded
+ * BatchNorm) is applied to every loaded element first.  arg_dev (uint8 [N, ld_arg], may be null
+ * for inference) receives the FIRST slot attaining the max: 0 = self, k+1 = neighbour k. */
+int dcgc_pool_fwd(const float* x_dev, int64_t ld_x, const float* scale_dev, const float* shift_dev,
+                  const int32_t* row_ptr_dev, const int32_t* col_idx_dev, int64_t n_rows,
+                  int32_t width, float* out_dev, int64_t ld_out, uint8_t* arg_dev, int64_t ld_arg,
+                  void* stream);
+/* K7 — GraphPool backward without scatter: dx[j,c] = [arg[j,c]==0]*dy[j,c]
+ *      + sum_{e in T(j)} [arg[t_src[e],c] == t_slot[e]+1] * dy[t_src[e],c].
+ * If scale is non-null the result is multiplied by scale[c] (chain rule of the folded affine). */
+int dcgc_pool_bwd(const float* dy_dev, int64_t ld_dy, const uint8_t* arg_dev, int64_t ld_arg,
+                  const float* scale_dev, const int32_t* t_row_ptr_dev, const int32_t* t_src_dev,
+                  const int32_t* t_slot_dev, int64_t n_rows, int32_t width, float* dx_dev,
+                  int64_t ld_dx, void* stream);
+
+/* K4 — GraphGather forward (layers.py:6464-6479; pytorch_utils.py:20-74, 473-528):
+ * out[g, 0:D] = act(sum_{i in mol g} x[i,:]), out[g, D:2D] = act(max_{i in mol g} x[i,:]),
+ * empty segment -> sum 0, max -inf (tanh -> -1).  argrow_dev (int32 [n_seg, D], may be null)
+ * receives the lowest row index attaining the max (-1 for empty segments). */
+int dcgc_gather_fwd(const float* x_dev, int64_t ld_x, const int32_t* mol_ptr_dev,
+                    const int32_t* mol_atoms_dev, int64_t n_segments, int32_t width, int32_t act,
+                    float* out_dev, int64_t ld_out, int32_t* argrow_dev, void* stream);
+/* K7 — GraphGather backward: dx[i,c] = dsum[m,c] + [argrow[m,c]==i]*dmax[m,c] with m =
+ * membership[i] and d* = dout * act'(out) (act' from the saved output). */
+int dcgc_gather_bwd(const float* dout_dev, int64_t ld_dout, const float* out_dev, int64_t ld_out,
+                    const int32_t* argrow_dev, const int32_t* membership_dev, int64_t n_rows,
+                    int32_t width, int32_t act, float* dx_dev, int64_t ld_dx, void* stream);
+
+/* K2 — degree-grouped affine map (GraphConv.forward, layers.py:6202-6229; also the atom-level
+ * Dense and the DMPNN Linear layers with a single group):
+ *   y[r,:] = act( a1[r,0:k1] . W[g][0:k1,:] + a2[r,0:k2] . W[g][k1:k1+k2,:] + bias[g,:] )
+ * for every row r of every tile, g = tile degree (tiles from the layout slab; g = 0 for all rows
+ * when tiles_dev is null and the whole [0,n_rows) range is one group).  W is [n_groups, k1+k2, n]
+ * row-major; a2 may be null (k2 = 0).  bias may be null. */
+int dcgc_group_gemm_fwd(int32_t mode, const float* a1_dev, int64_t ld_a1, int32_t k1,
+                        const float* a2_dev, int64_t ld_a2, int32_t k2, const float* w_dev,
+                        const float* bias_dev, int32_t n, const int32_t* tiles_dev, int64_t n_tiles,
+                        int32_t tile_rows, int64_t n_rows, int32_t act, float* y_dev, int64_t ld_y,
+                        void* stream);
+/* K6 (dgrad): [d1 | d2][r,:] = g[r,0:n] . W[g]^T, columns 0:k1 to d1 and k1:k1+k2 to d2 (either
+ * may be null to skip).  Takes the same W as the forward (reads it transposed). */
+int dcgc_group_gemm_dgrad(int32_t mode, const float* g_dev, int64_t ld_g, int32_t n,
+                          const float* w_dev, int32_t k1, int32_t k2, const int32_t* tiles_dev,
+                          int64_t n_tiles, int32_t tile_rows, int64_t n_rows, float* d1_dev,
+                          int64_t ld_d1, float* d2_dev, int64_t ld_d2, void* stream);
+/* K6 (wgrad): dW[g] = [a1 | a2]_g^T . grad_g  ([k1+k2, n]) and dbias[g] = column sums of grad_g,
+ * per group, deterministic (fixed split of the rows, partials reduced in a fixed order).
+ * workspace: dcgc_group_gemm_wgrad_workspace() bytes.  Groups with no rows get zeros. */
+int64_t dcgc_group_gemm_wgrad_workspace(int32_t k1, int32_t k2, int32_t n, int32_t n_groups);
+int dcgc_group_gemm_wgrad(int32_t mode, const float* a1_dev, int64_t ld_a1, int32_t k1,
+                          const float* a2_dev, int64_t ld_a2, int32_t k2, const float* g_dev,
+                          int64_t ld_g, int32_t n, const int64_t* deg_count_host, int32_t n_groups,
+                          float* dw_dev, float* dbias_dev, void* workspace_dev,
+                          int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCGC_H_ */

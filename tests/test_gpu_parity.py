@@ -1,0 +1,413 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): integer work bit-exact; fp32 outputs and gradients
+within 1e-5 relative (measured as max|a-b| / max|b| per tensor, `helpers.rel_err`); bf16-GEMM
+mode within 2e-2.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import load_golden, oracle_batch, rel_err, torch_args, unpack_mols
+from oracle import graphconv_torch as O
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda", 0)
+
+
+def _setup(pm, n_segments=None, padded=True):
+    """-> (oracle MultiConvMol, device inputs list [x, deg_slice, membership, adj...], topo)"""
+    from deepchem_b200 import mol_graphs as MG, ops
+    dev = _cuda()
+    _, mm = oracle_batch(pm.to_list())
+    lay = MG.BatchLayout.build(pm, n_segments=n_segments or pm.n_mols)
+    topo = lay.to_device(dev)
+    feats = torch.from_numpy(pm.features).to(dev)
+    if padded:
+        x = ops.permute_rows(feats, topo.perm)
+        x._dcgc_zero_padded = True
+    else:
+        x = feats[topo.perm.long()].contiguous()
+    ins = topo.model_inputs(x)
+    return mm, [ins[0], ins[1], ins[2]] + ins[4:], topo
+
+
+def _mols(n, seed, shape="stress", dense=True, n_feat=75):
+    from deepchem_b200.synthetic import make_molecules
+    return make_molecules(n, seed=seed, shape=shape, n_feat=n_feat, dense_features=dense)
+
+
+# ---------------------------------------------------------------------------- layout on device
+def test_device_topology_matches_host_layout():
+    pm = _mols(200, 1)
+    mm, ins, topo = _setup(pm)
+    assert np.array_equal(ins[1].cpu().numpy(), mm.deg_slice)
+    assert np.array_equal(ins[2].cpu().numpy(), mm.membership)
+    for a, r in zip(ins[3:], mm.get_deg_adjacency_lists()[1:]):
+        assert np.array_equal(a.cpu().numpy(), r)
+    assert np.array_equal(ins[0].cpu().numpy(), np.asarray(mm.get_atom_features(), np.float32))
+
+
+# ---------------------------------------------------------------------------- K1 / K5
+@pytest.mark.parametrize("padded", [True, False])
+def test_neighbor_sum_forward_backward(padded):
+    from deepchem_b200 import ops
+    pm = _mols(150, 2)
+    mm, ins, topo = _setup(pm, padded=padded)
+    x = ins[0].detach().clone().requires_grad_(True)
+    s = ops.NeighborSum.apply(x, topo)
+    xo = torch.from_numpy(np.asarray(mm.get_atom_features(), np.float32)).requires_grad_(True)
+    adjs = [torch.from_numpy(a).long() for a in mm.get_deg_adjacency_lists()]
+    so = torch.cat([xo[a].sum(1) for a in adjs], 0)
+    assert rel_err(s.detach().cpu().numpy(), so.detach().numpy()) < FP32_TOL
+    g = torch.randn(so.shape, generator=torch.Generator().manual_seed(0))
+    so.backward(g)
+    s.backward(g.to(x.device))
+    assert rel_err(x.grad.cpu().numpy(), xo.grad.numpy()) < FP32_TOL
+
+
+# ---------------------------------------------------------------------------- GraphConv layer
+def _oracle_conv(mm, W, b, act, gout):
+    args = torch_args(mm)
+    x = args[0].clone().requires_grad_(True)
+    Wl = [w.clone().requires_grad_(True) for w in W]
+    bl = [v.clone().requires_grad_(True) for v in b]
+    y = O.graph_conv(x, args[1], args[3:], Wl, bl, act)
+    y.backward(gout)
+    return y.detach(), x.grad, [w.grad for w in Wl], [v.grad for v in bl]
+
+
+@pytest.mark.parametrize("n_feat,c,padded", [(75, 64, True), (75, 64, False), (128, 128, True), (64, 2, True),
+                                             (75, 130, True)])
+def test_graph_conv_layer_forward_backward(n_feat, c, padded):
+    from deepchem_b200.layers import GraphConv
+    dev = _cuda()
+    pm = _mols(120, 3, n_feat=n_feat)
+    mm, ins, topo = _setup(pm, padded=padded)
+    torch.manual_seed(1)
+    layer = GraphConv(c, n_feat, activation_fn=F.relu).to(dev)
+    with torch.no_grad():
+        for p in layer.b_list:
+            p.normal_(0, 0.5)
+    W = [p.detach().cpu() for p in layer.W_list]
+    b = [p.detach().cpu() for p in layer.b_list]
+    x = ins[0].detach()
+    if padded:
+        x._dcgc_zero_padded = True
+        xin = x.requires_grad_(True)
+    else:
+        xin = x.clone().requires_grad_(True)
+    y = layer([xin] + ins[1:])
+    gout = torch.randn(y.shape, generator=torch.Generator().manual_seed(2))
+    y.backward(gout.to(dev))
+    yo, dxo, dWo, dbo = _oracle_conv(mm, W, b, torch.relu, gout)
+    assert rel_err(y.detach().cpu().numpy(), yo.numpy()) < FP32_TOL
+    assert rel_err(xin.grad.cpu().numpy(), dxo.numpy()) < FP32_TOL
+    scale_w = max(float(g.abs().max()) for g in dWo)
+    scale_b = max(float(g.abs().max()) for g in dbo)
+    for k in range(21):
+        assert float((layer.W_list[k].grad.cpu() - dWo[k]).abs().max()) < FP32_TOL * scale_w * 4, k
+        assert float((layer.b_list[k].grad.cpu() - dbo[k]).abs().max()) < FP32_TOL * scale_b * 4, k
+
+
+def test_graph_conv_kat_golden():
+    """Reference known-answer vector (models/tests/test_layers.py:1458-1493) through the CUDA layer
+    fed with plain tensors exactly like the reference test does."""
+    from deepchem_b200.layers import GraphConv
+    dev = _cuda()
+    d = load_golden("kat_ccc_c.npz")
+    _, mm = oracle_batch(unpack_mols(d))
+    args = [a.to(dev) for a in torch_args(mm)]
+    layer = GraphConv(2, number_input_features=75).to(dev)
+    layer.W_list = torch.nn.ParameterList([torch.nn.Parameter(torch.tensor(k).to(dev)) for k in d["asset_graphconvlayer_weights"]])
+    layer.b_list = torch.nn.ParameterList([torch.nn.Parameter(torch.tensor(k).to(dev)) for k in d["asset_graphconvlayer_biases"]])
+    result = layer(args)
+    assert result.shape == (4, 2)
+    assert np.allclose(result.detach().cpu().numpy(), d["asset_graphconvlayer_result"], atol=1e-6)
+    assert len(list(layer.parameters())) == 42
+
+
+# ---------------------------------------------------------------------------- GraphPool
+@pytest.mark.parametrize("c,ties", [(64, False), (128, True), (75, True), (3, False)])
+def test_graph_pool_forward_backward(c, ties):
+    from deepchem_b200.layers import GraphPool
+    dev = _cuda()
+    pm = _mols(130, 4, n_feat=c, dense=not ties)      # 0/1 features -> constant ties
+    mm, ins, topo = _setup(pm, padded=False)
+    x = ins[0].detach().clone().requires_grad_(True)
+    p = GraphPool()([x] + ins[1:])
+    args = torch_args(mm)
+    xo = args[0].clone().requires_grad_(True)
+    po = O.graph_pool(xo, args[1], args[3:])
+    assert np.array_equal(p.detach().cpu().numpy(), po.detach().numpy())     # max is exact
+    g = torch.randn(po.shape, generator=torch.Generator().manual_seed(3))
+    po.backward(g)
+    p.backward(g.to(dev))
+    assert rel_err(x.grad.cpu().numpy(), xo.grad.numpy()) < FP32_TOL
+
+
+def test_graph_pool_gather_kat_golden():
+    from deepchem_b200.layers import GraphGather, GraphPool
+    dev = _cuda()
+    d = load_golden("kat_ccc_c.npz")
+    _, mm = oracle_batch(unpack_mols(d))
+    args = [a.to(dev) for a in torch_args(mm)]
+    assert np.array_equal(GraphPool()(args).cpu().numpy(), d["asset_graphpoollayer_result"])
+    res = GraphGather(2)(args)
+    assert res.shape == (2, 150)
+    assert np.allclose(res.cpu().numpy(), d["asset_graphgatherlayer_result"], atol=1e-6)
+
+
+# ---------------------------------------------------------------------------- GraphGather
+@pytest.mark.parametrize("d_width,act", [(128, "tanh"), (75, None), (128, None)])
+def test_graph_gather_forward_backward(d_width, act):
+    from deepchem_b200.layers import GraphGather
+    dev = _cuda()
+    pm = _mols(90, 5, n_feat=d_width)
+    bsz = pm.n_mols + 4                      # four empty segments
+    mm, ins, topo = _setup(pm, n_segments=bsz, padded=False)
+    fn = torch.tanh if act == "tanh" else None
+    x = ins[0].detach().clone().requires_grad_(True)
+    z = GraphGather(bsz, activation_fn=fn)([x] + ins[1:])
+    args = torch_args(mm)
+    xo = args[0].clone().requires_grad_(True)
+    zo = O.graph_gather(xo, args[2], bsz, fn)
+    assert z.shape == (bsz, 2 * d_width)
+    assert rel_err(z.detach().cpu().numpy(), zo.detach().numpy()) < FP32_TOL
+    zc = z.detach().cpu().numpy()
+    assert np.all(zc[-4:, :d_width] == 0)
+    assert np.all(zc[-4:, d_width:] == (-1 if act == "tanh" else -np.inf))
+    g = torch.randn(zo.shape, generator=torch.Generator().manual_seed(4))
+    if act is None:
+        g[-4:] = 0                          # -inf * 0 would be NaN in both implementations
+    zo.backward(g)
+    z.backward(g.to(dev))
+    assert rel_err(x.grad.cpu().numpy(), xo.grad.numpy()) < FP32_TOL
+
+
+def test_graph_gather_asserts_like_reference():
+    from deepchem_b200.layers import GraphGather
+    dev = _cuda()
+    with pytest.raises(AssertionError, match="larger than 1"):
+        GraphGather(1)([torch.zeros(2, 4, device=dev), None, torch.zeros(2, dtype=torch.int32, device=dev)])
+
+
+# ---------------------------------------------------------------------------- whole model
+def _device_model_from_oracle(om, mode, bsz, layers, dense, n_tasks, **kw):
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    m = GraphConvModel(n_tasks, graph_conv_layers=layers, dense_layer_size=dense, mode=mode, batch_size=bsz, **kw)
+    assert set(m.model.state_dict()) == set(om.state_dict())
+    m.model.load_state_dict(om.state_dict())
+    return m
+
+
+@pytest.mark.parametrize("mode,layers", [("classification", [64, 64]), ("regression", [128, 128, 128])])
+def test_model_forward_loss_and_gradients(mode, layers):
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.synthetic import make_labels
+    _cuda()
+    n_tasks, dense = 3, 128
+    pm = _mols(60, 6, dense=False)
+    bsz = 64
+    torch.manual_seed(5)
+    om = O.OracleGraphConvModel(n_tasks, layers, dense, mode=mode, batch_size=bsz)
+    with torch.no_grad():
+        for p in om.parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.1)
+    m = _device_model_from_oracle(om, mode, bsz, layers, dense, n_tasks)
+    y, w = make_labels(pm.n_mols, n_tasks, mode, seed=1, missing=0.2)
+    ds = PackedDataset(pm, y, w)
+    batch = next(m.default_generator(ds, deterministic=True, pad_batches=False))
+    inputs, labels, weights = m._prepare_batch(batch)
+    m.model.train()
+    outs = m.model(inputs)
+    loss = m._loss_fn([outs[i] for i in m._loss_outputs], labels, weights)
+    loss.backward()
+
+    _, mm = oracle_batch(pm.to_list())
+    om.train()
+    oo = om(torch_args(mm, pm.n_mols))
+    yl = torch.from_numpy(batch[1][0])
+    lo = O.standard_loss(mode, oo, yl, torch.from_numpy(w))
+    lo.backward()
+    for a, b in zip(outs, oo):
+        assert rel_err(a.detach().cpu().numpy(), b.detach().numpy()) < 2e-5
+    assert abs(float(loss) - float(lo)) < 1e-5 * max(1.0, abs(float(lo)))
+    og = dict(om.named_parameters())
+    for name, p in m.model.named_parameters():
+        ref = og[name].grad
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(ref)
+        ref = ref if ref is not None else torch.zeros_like(got)
+        scale = max(float(ref.abs().max()), 1e-6)
+        assert float((got - ref).abs().max()) < 5e-5 * scale + 1e-9, name
+    # running statistics follow torch's momentum convention (new = 0.01*old + 0.99*batch)
+    for (k, v), (_, vo) in zip(m.model.state_dict().items(), om.state_dict().items()):
+        if "running" in k:
+            assert rel_err(v.cpu().numpy(), vo.numpy()) < 2e-5, k
+
+
+def test_model_kat_golden_and_state_dict():
+    """models/tests/test_graphconv_torchmodel.py:15-95 on the CUDA model."""
+    from deepchem_b200.graphconvmodel import _GraphConvTorchModel
+    dev = _cuda()
+    d = load_golden("kat_ccc_c.npz")
+    _, mm = oracle_batch(unpack_mols(d))
+    args = [a.to(dev) if a.dim() else a for a in torch_args(mm, 2)]
+    m = _GraphConvTorchModel(2, graph_conv_layers=[64, 64], number_input_features=[75, 64], dense_layer_size=128,
+                             dropout=0.0, mode="classification", number_atom_features=75, n_classes=2,
+                             batch_normalize=False, uncertainty=False, batch_size=10).to(dev)
+    with torch.no_grad():
+        for i in (0, 1):
+            for k in range(21):
+                m.graph_convs[i].W_list[k].copy_(torch.from_numpy(d["asset_graphconvlayer%d_weights" % i][k]))
+                m.graph_convs[i].b_list[k].copy_(torch.from_numpy(d["asset_graphconvlayer%d_biases" % i][k]))
+        m.dense.weight.copy_(torch.from_numpy(d["asset_dense_weights"].T))
+        m.dense.bias.copy_(torch.from_numpy(d["asset_dense_biases"]))
+        m.reshape_dense.weight.copy_(torch.from_numpy(d["asset_reshapedense_weights"].T))
+        m.reshape_dense.bias.copy_(torch.from_numpy(d["asset_reshapedense_biases"]))
+    out = m(args)
+    assert len(out) == 3
+    assert np.allclose(out[0].detach().cpu().numpy(), d["asset_graphconvmodel_output_classification"], atol=1e-5)
+    assert np.allclose(out[1].detach().cpu().numpy(), d["asset_graphconvmodel_logits_classification"], atol=1e-5)
+    assert np.allclose(out[2].detach().cpu().numpy(), d["asset_graphconvmodel_neural_classification"], atol=1e-5)
+
+
+def test_model_reference_golden_train_and_eval():
+    """Reference _GraphConvTorchModel outputs (generated in the build container)."""
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.synthetic import PackedMols
+    _cuda()
+    for mode in ("classification", "regression"):
+        d = load_golden("ref_model_%s.npz" % mode)
+        pm = PackedMols(d["atom_ptr"], d["adj_ptr"], d["adj_idx"], d["features"])
+        m = GraphConvModel(3, [64, 64], 128, mode=mode, batch_size=int(d["batch_size"]))
+        m.model.load_state_dict({k[3:]: torch.from_numpy(v) for k, v in d.items() if k.startswith("sd:")})
+        batch = next(m.default_generator(PackedDataset(pm, n_tasks=3), mode="predict", deterministic=True,
+                                         pad_batches=False))
+        inputs, _, _ = m._prepare_batch(batch)
+        m.model.train()
+        for i, r in enumerate(m.model(inputs)):
+            assert rel_err(r.detach().cpu().numpy(), d["ref_train_out%d" % i]) < 2e-5, (mode, i)
+        m.model.eval()
+        for i, r in enumerate(m.model(inputs)):
+            assert rel_err(r.detach().cpu().numpy(), d["ref_eval_out%d" % i]) < 2e-5, (mode, i)
+
+
+def test_fit_predict_checkpoint_roundtrip(tmp_path):
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    from deepchem_b200.synthetic import make_labels, make_molecules
+    _cuda()
+    pm = make_molecules(50, seed=8, shape="delaney")
+    y, w = make_labels(50, 1, "regression", seed=2)
+    ds = PackedDataset(pm, y, w)
+    torch.manual_seed(0)
+    m = GraphConvModel(1, [32, 32], 64, mode="regression", batch_size=20, model_dir=str(tmp_path),
+                       batch_normalize=False, learning_rate=0.003)
+    losses = []
+    m.fit(ds, nb_epoch=1, deterministic=True)
+    first = float(np.mean((m.predict(ds) - y) ** 2))
+    m.fit(ds, nb_epoch=60, deterministic=True, all_losses=losses)
+    pred = m.predict(ds)
+    assert pred.shape == (50, 1)
+    assert float(np.mean((pred - y) ** 2)) < 0.5 * first      # it learns (GraphConv weights get gradients)
+    assert all(p.grad is not None for p in m.model.graph_convs[0].W_list[:8:2])
+    emb = m.predict_embedding(ds)
+    assert emb.shape == (60, 128)                              # untrimmed: 3 batches x batch_size rows
+    m2 = GraphConvModel(1, [32, 32], 64, mode="regression", batch_size=20, model_dir=str(tmp_path),
+                        batch_normalize=False)
+    m2.restore()
+    assert np.array_equal(m2.predict(ds), pred) and m2.get_global_step() == m.get_global_step()
+
+
+# ---------------------------------------------------------------------------- full-size properties
+def test_full_size_batch_properties():
+    """B=4096 ZINC-shaped batch (BASELINE config 3): size-independent invariants."""
+    from deepchem_b200 import ops
+    from deepchem_b200.layers import GraphGather, GraphPool
+    from deepchem_b200.synthetic import make_molecules
+    dev = _cuda()
+    pm = make_molecules(4096, seed=0)
+    from deepchem_b200 import mol_graphs as MG
+    lay = MG.BatchLayout.build(pm, n_segments=4096)
+    topo = lay.to_device(dev)
+    n = lay.n_atoms
+    deg = torch.from_numpy(np.diff(lay.row_ptr)).to(dev)
+    ones = torch.ones(n, 128, device=dev)
+    # gather-sum of ones is the degree; of a linear combination is the linear combination
+    s1 = ops.gather_sum(ones, topo.row_ptr, topo.col_idx, n)
+    assert torch.equal(s1, deg[:, None].float().expand(n, 128))
+    g = torch.Generator(device=dev).manual_seed(0)
+    a = torch.randn(n, 128, device=dev, generator=g)
+    b = torch.randn(n, 128, device=dev, generator=g)
+    sa, sb = ops.gather_sum(a, topo.row_ptr, topo.col_idx, n), ops.gather_sum(b, topo.row_ptr, topo.col_idx, n)
+    sab = ops.gather_sum(2 * a - 3 * b, topo.row_ptr, topo.col_idx, n)
+    assert float((sab - (2 * sa - 3 * sb)).abs().max()) < 1e-4
+    # transposed gather is the adjoint: <S(a), b> == <a, S^T(b)>
+    stb = ops.gather_sum(b, topo.t_row_ptr, topo.t_src, n)
+    lhs, rhs = float((sa.double() * b.double()).sum()), float((a.double() * stb.double()).sum())
+    assert abs(lhs - rhs) < 1e-6 * abs(lhs) + 1e-3
+    # against torch ops on the same device
+    ref = torch.zeros_like(a).index_add_(0, torch.repeat_interleave(torch.arange(n, device=dev), deg.long()),
+                                         a[topo.col_idx.long()])
+    assert float((sa - ref).abs().max()) < 1e-4
+    # pool: >= self, idempotent on constants, equals the reference formulation
+    ins = topo.model_inputs(a)
+    ins = [ins[0], ins[1], ins[2]] + ins[4:]
+    p = GraphPool()(ins)
+    assert bool((p >= a).all())
+    nb_max = torch.full_like(a, -float("inf")).index_reduce_(
+        0, torch.repeat_interleave(torch.arange(n, device=dev), deg.long()), a[topo.col_idx.long()], "amax")
+    assert torch.equal(p, torch.maximum(a, nb_max))
+    # gather: sum half adds up to the column sums, atom counts per molecule
+    z = GraphGather(4096)([ones] + ins[1:])
+    counts = torch.from_numpy(np.diff(lay.mol_ptr)).to(dev).float()
+    assert torch.equal(z[:, 0], counts) and torch.equal(z[:, 128:], torch.ones(4096, 128, device=dev))
+    za = GraphGather(4096)(ins)
+    assert float((za[:, :128].double().sum(0) - a.double().sum(0)).abs().max()) < 1e-2
+    ref_max = torch.full((4096, 128), -float("inf"), device=dev).index_reduce_(0, topo.membership.long(), a, "amax")
+    assert torch.equal(za[:, 128:], ref_max)
+
+
+def test_full_size_model_step_against_oracle():
+    """Config 3 at full size against the oracle on the host cores (a few seconds of CPU)."""
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.synthetic import make_labels, make_molecules
+    _cuda()
+    pm = make_molecules(4096, seed=1)
+    y, w = make_labels(4096, 1, "regression", seed=3)
+    torch.manual_seed(7)
+    layers = [128, 128, 128]
+    om = O.OracleGraphConvModel(1, layers, 128, mode="regression", batch_size=4096)
+    m = _device_model_from_oracle(om, "regression", 4096, layers, 128, 1)
+    batch = next(m.default_generator(PackedDataset(pm, y, w), deterministic=True))
+    inputs, labels, weights = m._prepare_batch(batch)
+    m.model.train()
+    outs = m.model(inputs)
+    loss = m._loss_fn([outs[0]], labels, weights)
+    loss.backward()
+    _, mm = oracle_batch(pm.to_list())
+    om.train()
+    oo = om(torch_args(mm, 4096))
+    lo = O.standard_loss("regression", oo, torch.from_numpy(y), torch.from_numpy(w))
+    lo.backward()
+    assert rel_err(outs[0].detach().cpu().numpy(), oo[0].detach().numpy()) < 5e-5
+    assert abs(float(loss) - float(lo)) < 1e-5 * abs(float(lo))
+    og = dict(om.named_parameters())
+    worst = 0.0
+    for name, p in m.model.named_parameters():
+        ref = og[name].grad
+        if ref is None or p.grad is None:
+            continue
+        worst = max(worst, float((p.grad.cpu() - ref).abs().max()) / max(float(ref.abs().max()), 1e-8))
+    assert worst < 2e-4, worst

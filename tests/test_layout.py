@@ -1,0 +1,121 @@
+"""Host layout builder (C++ behind the C ABI) against the reference goldens and the oracle:
+integer outputs must match bit for bit (dtype included)."""
+import numpy as np
+import pytest
+
+from helpers import load_golden, oracle_batch, unpack_mols
+from deepchem_b200 import mol_graphs as MG
+from deepchem_b200.synthetic import PackedMols, make_molecules
+from oracle.convmol_layout import derived_topology
+
+
+def _packed(d):
+    return PackedMols(d["atom_ptr"], d["adj_ptr"], d["adj_idx"], d["features"].astype(np.float32))
+
+
+@pytest.mark.parametrize("name", ["kat_ccc_c.npz", "ref_layout_stress.npz", "ref_layout_zinc.npz",
+                                  "ref_layout_delaney.npz"])
+def test_builder_matches_reference_golden(name):
+    d = load_golden(name)
+    lay = MG.BatchLayout.build(_packed(d))
+    assert lay.deg_slice.dtype == np.int64 and np.array_equal(lay.deg_slice, d["ref_deg_slice"])
+    assert lay.membership.dtype == np.int32 and np.array_equal(lay.membership, d["ref_membership"])
+    for k, a in enumerate(lay.deg_adjacency_lists()):
+        r = d["ref_deg_adj_%d" % k]
+        assert a.dtype == np.int32 and a.shape == r.shape and np.array_equal(a, r), k
+    feats = lay.permute_features(d["features"].astype(np.float32))
+    assert np.array_equal(feats, d["ref_nodes"].astype(np.float32))
+    padded = lay.permute_features(d["features"].astype(np.float32), ld_out=76)
+    assert np.array_equal(padded[:, :75], feats) and np.all(padded[:, 75] == 0)
+
+
+@pytest.mark.parametrize("name", ["kat_ccc_c.npz", "ref_layout_stress.npz"])
+def test_convmol_class_matches_reference_golden(name):
+    """ConvMol.__init__ outputs (a1) and the agglomerate_mols drop-in (a2)."""
+    d = load_golden(name)
+    cms = [MG.ConvMol(f, adj) for f, adj in unpack_mols(d)]
+    ds = np.stack([c.deg_slice for c in cms])
+    assert ds.dtype == d["ref_mol_deg_slice"].dtype and np.array_equal(ds, d["ref_mol_deg_slice"])
+    assert np.array_equal(np.concatenate([c.deg_block_indices for c in cms]), d["ref_mol_deg_block_indices"])
+    assert np.array_equal(np.concatenate([np.asarray(c.degree_list, np.int32) for c in cms]), d["ref_mol_degree_list"])
+    flat = np.asarray([k for c in cms for nb in c.get_adjacency_list() for k in nb], np.int32)
+    assert np.array_equal(flat, d["ref_mol_canon_adj_flat"])
+    assert np.array_equal(np.concatenate([c.get_atom_features() for c in cms]), d["ref_mol_features_sorted"])
+    mm = MG.ConvMol.agglomerate_mols(cms)
+    assert np.array_equal(mm.deg_slice, d["ref_deg_slice"]) and mm.deg_slice.dtype == np.int64
+    assert np.array_equal(mm.membership, d["ref_membership"])
+    assert np.array_equal(mm.get_atom_features(), d["ref_nodes"])
+    assert mm.get_atom_features().dtype == d["ref_nodes"].dtype
+    for k, a in enumerate(mm.get_deg_adjacency_lists()):
+        assert np.array_equal(a, d["ref_deg_adj_%d" % k])
+    assert mm.get_num_atoms() == d["ref_nodes"].shape[0] and mm.get_num_molecules() == len(cms)
+
+
+def test_null_mol_self_loops():
+    d = load_golden("ref_layout_nullmol.npz")
+    adj = [deg * [deg] for deg in range(11)]
+    nm = MG.ConvMol(d["features"], adj)
+    mm = MG.ConvMol.agglomerate_mols([nm, nm])
+    assert np.array_equal(mm.deg_slice, d["deg_slice"]) and np.array_equal(mm.membership, d["membership"])
+    for k, a in enumerate(mm.get_deg_adjacency_lists()):
+        assert np.array_equal(a, d["deg_adj_%d" % k])
+
+
+@pytest.mark.parametrize("shape,n,seed", [("stress", 300, 1), ("zinc", 257, 2), ("qm9", 100, 3)])
+def test_builder_matches_oracle_on_random_batches(shape, n, seed):
+    pm = make_molecules(n, seed=seed, shape=shape)
+    _, mm = oracle_batch(pm.to_list())
+    nseg = n + 5
+    lay = MG.BatchLayout.build(pm, n_segments=nseg)
+    assert np.array_equal(lay.deg_slice, mm.deg_slice) and np.array_equal(lay.membership, mm.membership)
+    for a, r in zip(lay.deg_adjacency_lists(), mm.get_deg_adjacency_lists()):
+        assert np.array_equal(a, r)
+    t = derived_topology(mm.deg_slice, mm.membership, mm.get_deg_adjacency_lists(), nseg)
+    for k in ("row_ptr", "col_idx", "t_row_ptr", "t_src", "t_slot", "mol_ptr", "mol_atoms"):
+        assert np.array_equal(getattr(lay, k), t[k]), k
+    # perm: row i of the batch is atom perm[i] of the shard
+    assert np.array_equal(pm.features[lay.perm], np.asarray(mm.get_atom_features(), np.float32))
+    # tiles: cover every row exactly once, never straddle a degree bucket
+    rows = np.concatenate([np.arange(r0, r0 + nr) for r0, nr, _, _ in lay.tiles])
+    assert np.array_equal(rows, np.arange(lay.n_atoms))
+    deg_of_row = np.repeat(np.arange(11), lay.deg_slice[:, 1])
+    for r0, nr, dg, _ in lay.tiles:
+        assert 0 < nr <= 128 and np.all(deg_of_row[r0:r0 + nr] == dg)
+    # the same slab derived from the reference arrays alone
+    lay2 = MG.BatchLayout.from_reference_arrays(mm.deg_slice, mm.membership, mm.get_deg_adjacency_lists(), nseg)
+    for k in ("row_ptr", "col_idx", "t_row_ptr", "t_src", "t_slot", "mol_ptr", "mol_atoms", "tiles", "deg_slice"):
+        assert np.array_equal(getattr(lay, k), getattr(lay2, k)), k
+
+
+def test_empty_and_degenerate_batches():
+    empty = PackedMols([0], [0], [], np.zeros((0, 75), np.float32))
+    lay = MG.BatchLayout.build(empty, n_segments=4)
+    assert lay.n_atoms == 0 and lay.n_tiles == 0 and lay.mol_ptr.tolist() == [0] * 5
+    assert lay.deg_slice.tolist() == [[0, 0]] * 11
+    single = PackedMols.from_list([(np.ones((1, 75), np.float32), [[]])])
+    lay = MG.BatchLayout.build(single)
+    assert lay.deg_slice[0].tolist() == [0, 1] and lay.membership.tolist() == [0]
+    assert [a.shape for a in lay.deg_adjacency_lists()][:2] == [(1, 0), (0, 1)]
+
+
+def test_builder_errors():
+    f = np.zeros((12, 75), np.float32)
+    too_many = [list(range(1, 12))] + [[0]] * 11          # atom 0 has degree 11
+    with pytest.raises(ValueError, match="degree"):
+        MG.BatchLayout.build(PackedMols.from_list([(f, too_many)]))
+    bad_index = PackedMols.from_list([(np.zeros((2, 75), np.float32), [[5], [0]])])
+    with pytest.raises(ValueError, match="neighbour index"):
+        MG.BatchLayout.build(bad_index)
+    with pytest.raises(ValueError):
+        MG.BatchLayout.build(PackedMols.from_list([(np.zeros((1, 75), np.float32), [[]])]), n_segments=0)
+
+
+def test_asymmetric_adjacency_master_atom():
+    """A fake atom appended to every real atom's list but with no list of its own
+    (feat/graph_features.py:906-909): CSR^T must still be the exact transpose."""
+    adj = [[1, 3], [0, 2, 3], [1, 3], []]
+    lay = MG.BatchLayout.build(PackedMols.from_list([(np.zeros((4, 75), np.float32), adj)]))
+    for j in range(lay.n_atoms):
+        for e in range(lay.t_row_ptr[j], lay.t_row_ptr[j + 1]):
+            assert lay.col_idx[lay.row_ptr[lay.t_src[e]] + lay.t_slot[e]] == j
+    assert lay.t_row_ptr[-1] == lay.n_edges == 7
