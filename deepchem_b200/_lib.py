@@ -3,7 +3,7 @@ raw pointers, sizes and a cudaStream_t.  There is no CPU fallback: if the librar
 loaded (or built), importing the ops raises."""
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdcgc.so")
@@ -34,6 +34,29 @@ class LayoutInfo(Structure):
     ]
 
 
+MODEL_MAX_LAYERS = 8
+
+
+class Topology(Structure):
+    """dcgc_topology"""
+    _fields_ = [
+        ("n_atoms", c_int64), ("n_edges", c_int64), ("n_segments", c_int64), ("n_tiles", c_int64),
+        ("deg_count", c_int64 * N_DEG),
+        ("row_ptr", c_void_p), ("col_idx", c_void_p), ("t_row_ptr", c_void_p), ("t_src", c_void_p),
+        ("t_slot", c_void_p), ("mol_ptr", c_void_p), ("mol_atoms", c_void_p), ("membership", c_void_p),
+        ("tiles", c_void_p),
+    ]
+
+
+class GcModelConfig(Structure):
+    """dcgc_gcmodel_config"""
+    _fields_ = [
+        ("n_layers", c_int32), ("n_feat", c_int32), ("widths", c_int32 * MODEL_MAX_LAYERS),
+        ("dense", c_int32), ("n_out", c_int32), ("n_classes", c_int32), ("mode", c_int32),
+        ("batch_norm", c_int32), ("gemm_mode", c_int32), ("bn_eps", c_float), ("bn_momentum", c_float),
+    ]
+
+
 _P = c_void_p
 _SIGNATURES = {
     "dcgc_last_error": (c_char_p, []),
@@ -48,7 +71,7 @@ _SIGNATURES = {
     "dcgc_gather_sum": (c_int32, [_P, c_int64, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
     "dcgc_pool_fwd": (c_int32, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
     "dcgc_pool_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, c_int64, _P]),
-    "dcgc_gather_fwd": (c_int32, [_P, c_int64, _P, _P, c_int64, c_int32, c_int32, _P, c_int64, _P, _P]),
+    "dcgc_gather_fwd": (c_int32, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int64, _P, _P]),
     "dcgc_gather_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int32, c_int32, _P, c_int64, _P]),
     "dcgc_group_gemm_fwd": (c_int32, [c_int32, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, c_int32,
                                       _P, c_int64, c_int32, c_int64, c_int32, _P, c_int64, _P]),
@@ -57,6 +80,18 @@ _SIGNATURES = {
     "dcgc_group_gemm_wgrad_workspace": (c_int64, [c_int32, c_int32, c_int32, c_int32]),
     "dcgc_group_gemm_wgrad": (c_int32, [c_int32, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, c_int64,
                                         c_int32, _P, c_int32, _P, _P, _P, c_int64, _P]),
+    "dcgc_linear_fwd": (c_int32, [c_int32, _P, c_int64, c_int32, _P, _P, c_int32, c_int64, c_int32, _P, c_int64, _P]),
+    "dcgc_linear_dgrad": (c_int32, [c_int32, _P, c_int64, c_int32, _P, c_int32, c_int64, _P, c_int64, _P]),
+    "dcgc_linear_wgrad_workspace": (c_int64, [c_int32, c_int32]),
+    "dcgc_linear_wgrad": (c_int32, [c_int32, _P, c_int64, c_int32, _P, c_int64, c_int32, c_int64, _P, _P, _P,
+                                    c_int64, _P]),
+    "dcgc_gcmodel_layout": (c_int32, [POINTER(GcModelConfig), _P, _P, POINTER(c_int64), POINTER(c_int64)]),
+    "dcgc_gcmodel_workspace_bytes": (c_int64, [POINTER(GcModelConfig), c_int64, c_int64]),
+    "dcgc_gcmodel_forward": (c_int32, [POINTER(GcModelConfig), POINTER(Topology), _P, c_int64, c_int64, _P, _P,
+                                       c_int32, _P, c_int64, _P, _P, _P, _P]),
+    "dcgc_gcmodel_train_step": (c_int32, [POINTER(GcModelConfig), POINTER(Topology), _P, c_int64, _P, _P, c_int64,
+                                          _P, _P, _P, _P, c_int64, _P, _P, _P]),
+    "dcgc_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, c_float, _P]),
 }
 
 _lib = None

@@ -336,6 +336,7 @@ struct ReduceArgs {
   float* dw; float* dbias;
   int64_t kn;  // (k1+k2)*n
   int n, n_groups;
+  int transpose;  // write dw[g][j][k] instead of dw[g][k][j] (nn.Linear weight layout)
   int chunk_prefix[DCGC_N_DEG + 1];
 };
 
@@ -347,7 +348,12 @@ __global__ void __launch_bounds__(NT) wgrad_reduce_kernel(const ReduceArgs p) {
   float s = 0.f;
   if (idx < p.kn) {
     for (int c = c0; c < c1; ++c) s += __ldg(p.ws + (int64_t)c * p.kn + idx);
-    p.dw[(int64_t)g * p.kn + idx] = s;
+    int64_t o = idx;
+    if (p.transpose) {
+      const int64_t k = idx / p.n, j = idx - k * p.n;
+      o = j * (p.kn / p.n) + k;
+    }
+    p.dw[(int64_t)g * p.kn + o] = s;
   } else if (p.dbias) {
     const int64_t j = idx - p.kn;
     for (int c = c0; c < c1; ++c) s += __ldg(p.wsb + (int64_t)c * p.n + j);
@@ -444,10 +450,10 @@ extern "C" int64_t dcgc_group_gemm_wgrad_workspace(int32_t k1, int32_t k2, int32
   return chunks * ((int64_t)(k1 + k2) * n + n) * 4 + 256;
 }
 
-extern "C" int dcgc_group_gemm_wgrad(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2,
-                                     int64_t ld_a2, int32_t k2, const float* g, int64_t ld_g, int32_t n,
-                                     const int64_t* deg_count, int32_t n_groups, float* dw, float* dbias,
-                                     void* workspace, int64_t workspace_bytes, void* stream) {
+static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2,
+                      int64_t ld_a2, int32_t k2, const float* g, int64_t ld_g, int32_t n,
+                      const int64_t* deg_count, int32_t n_groups, float* dw, float* dbias,
+                      void* workspace, int64_t workspace_bytes, int transpose, void* stream) {
   DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32, "dcgc_group_gemm_wgrad: GEMM mode %d is not available in this build", mode);
   DCGC_CHECK_ARG(k1 >= 0 && k2 >= 0 && n >= 0 && ld_a1 >= k1 && ld_g >= n, "dcgc_group_gemm_wgrad: bad sizes");
   DCGC_CHECK_ARG(n_groups >= 1 && n_groups <= DCGC_N_DEG && deg_count, "dcgc_group_gemm_wgrad: bad groups");
@@ -511,8 +517,72 @@ extern "C" int dcgc_group_gemm_wgrad(int32_t mode, const float* a1, int64_t ld_a
     DCGC_CUDA_LAUNCH_CHECK("dcgc_group_gemm_wgrad (stage 1)");
   }
   q.ws = p.ws; q.wsb = p.wsb; q.dw = dw; q.dbias = dbias; q.kn = kn; q.n = n; q.n_groups = n_groups;
+  q.transpose = transpose;
   dim3 rgrid((unsigned)((kn + n + NT - 1) / NT), (unsigned)n_groups);
   wgrad_reduce_kernel<<<rgrid, NT, 0, st>>>(q);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_group_gemm_wgrad (stage 2)");
   return DCGC_OK;
+}
+
+extern "C" int dcgc_group_gemm_wgrad(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2,
+                                     int64_t ld_a2, int32_t k2, const float* g, int64_t ld_g, int32_t n,
+                                     const int64_t* deg_count, int32_t n_groups, float* dw, float* dbias,
+                                     void* workspace, int64_t workspace_bytes, void* stream) {
+  return wgrad_impl(mode, a1, ld_a1, k1, a2, ld_a2, k2, g, ld_g, n, deg_count, n_groups, dw, dbias, workspace,
+                    workspace_bytes, 0, stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// nn.Linear-layout helpers (weight stored [n_out, k_in] as torch does): the atom-level Dense
+// layer (graphconvmodel.py:172,222) and the DMPNN W_i / W_h / W_o (layers.py:1510-1517).
+// ------------------------------------------------------------------------------------------
+extern "C" int dcgc_linear_fwd(int32_t mode, const float* x, int64_t ld_x, int32_t k, const float* w,
+                               const float* bias, int32_t n, int64_t n_rows, int32_t act, float* y, int64_t ld_y,
+                               void* stream) {
+  DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32, "dcgc_linear_fwd: GEMM mode %d is not available in this build", mode);
+  DCGC_CHECK_ARG(k >= 0 && n >= 0 && n_rows >= 0 && ld_x >= k && ld_y >= n, "dcgc_linear_fwd: bad sizes");
+  DCGC_CHECK_ARG(act >= DCGC_ACT_NONE && act <= DCGC_ACT_TANH, "dcgc_linear_fwd: unknown activation %d", act);
+  if (n_rows == 0 || n == 0) return DCGC_OK;
+  DCGC_CHECK_ARG(x && w && y, "dcgc_linear_fwd: null pointer");
+  GemmArgs p{};
+  p.a1 = x; p.ld_a1 = ld_x; p.k1 = k;
+  p.w = w; p.w_group_stride = 0; p.ld_w = k;
+  p.bias = bias; p.bias_group_stride = 0;
+  p.n1 = n; p.n2 = 0;
+  p.c1 = y; p.ld_c1 = ld_y;
+  p.tiles = nullptr; p.n_rows = n_rows; p.act = act;
+  p.a1_vec = ld_x % 4 == 0 && aligned16(x);
+  p.w_vec = k % 4 == 0 && aligned16(w);
+  p.c1_vec = ld_y % 4 == 0 && aligned16(y);
+  const int64_t row_tiles = (n_rows + BM - 1) / BM;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n > 64) {
+    dim3 grid((unsigned)row_tiles, (unsigned)((n + 127) / 128));
+    gemm_kernel<128, true><<<grid, NT, 0, st>>>(p);
+  } else {
+    dim3 grid((unsigned)row_tiles, 1);
+    gemm_kernel<64, true><<<grid, NT, 0, st>>>(p);
+  }
+  DCGC_CUDA_LAUNCH_CHECK("dcgc_linear_fwd");
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_linear_dgrad(int32_t mode, const float* g, int64_t ld_g, int32_t n, const float* w, int32_t k,
+                                 int64_t n_rows, float* dx, int64_t ld_dx, void* stream) {
+  // dx = g . w with w [n, k]: a plain (non-transposed) product with K = n, N = k
+  return dcgc_group_gemm_fwd(mode, g, ld_g, n, nullptr, 0, 0, w, nullptr, k, nullptr, 0, BM, n_rows, DCGC_ACT_NONE,
+                             dx, ld_dx, stream);
+}
+
+extern "C" int64_t dcgc_linear_wgrad_workspace(int32_t k, int32_t n) {
+  return dcgc_group_gemm_wgrad_workspace(k, 0, n, 1);
+}
+
+extern "C" int dcgc_linear_wgrad(int32_t mode, const float* x, int64_t ld_x, int32_t k, const float* g, int64_t ld_g,
+                                 int32_t n, int64_t n_rows, float* dw, float* dbias, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+  // dw [n, k] = g^T . x ; dbias [n] = column sums of g
+  const int64_t counts[1] = {n_rows};
+  return wgrad_impl(mode, x, ld_x, k, nullptr, 0, 0, g, ld_g, n, counts, 1, dw, dbias, workspace, workspace_bytes, 1,
+                    stream);
 }

@@ -219,17 +219,22 @@ __device__ __forceinline__ float act_grad_from_out(float o, int act) {
 
 template <int VEC, bool ARG>
 __global__ void __launch_bounds__(kThreads)
-gather_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restrict__ mol_ptr,
+gather_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const int32_t* __restrict__ mol_ptr,
                   const int32_t* __restrict__ mol_atoms, int64_t n_seg, int groups, int width, int act,
                   float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argrow) {
   const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t g = t / groups;
   const int c = (int)(t - g * groups) * VEC;
   if (g >= n_seg || c >= width) return;
-  float s[VEC], m[VEC];
+  float s[VEC], m[VEC], sc[VEC], sh[VEC];
   int32_t a[VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) { s[v] = 0.f; m[v] = -INFINITY; a[v] = -1; }
+  for (int v = 0; v < VEC; ++v) {
+    s[v] = 0.f; m[v] = -INFINITY; a[v] = -1;
+    sc[v] = scale ? __ldg(scale + c + v) : 1.f;
+    sh[v] = scale ? __ldg(shift + c + v) : 0.f;
+  }
   const int e1 = __ldg(mol_ptr + g + 1);
   for (int e = __ldg(mol_ptr + g); e < e1; ++e) {
     const int32_t r = __ldg(mol_atoms + e);
@@ -239,6 +244,10 @@ gather_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __re
       u[0] = q.x; u[1 % VEC] = q.y; u[2 % VEC] = q.z; u[3 % VEC] = q.w;
     } else {
       u[0] = __ldg(x + (int64_t)r * ld_x + c);
+    }
+    if (scale) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) u[v] = fmaf(u[v], sc[v], sh[v]);
     }
 #pragma unroll
     for (int v = 0; v < VEC; ++v) {
@@ -377,9 +386,11 @@ extern "C" int dcgc_pool_bwd(const float* dy, int64_t ld_dy, const uint8_t* arg,
   return DCGC_OK;
 }
 
-extern "C" int dcgc_gather_fwd(const float* x, int64_t ld_x, const int32_t* mol_ptr, const int32_t* mol_atoms,
-                               int64_t n_segments, int32_t width, int32_t act, float* out, int64_t ld_out,
-                               int32_t* argrow, void* stream) {
+extern "C" int dcgc_gather_fwd(const float* x, int64_t ld_x, const float* scale, const float* shift,
+                               const int32_t* mol_ptr, const int32_t* mol_atoms, int64_t n_segments,
+                               int32_t width, int32_t act, float* out, int64_t ld_out, int32_t* argrow,
+                               void* stream) {
+  DCGC_CHECK_ARG((scale == nullptr) == (shift == nullptr), "dcgc_gather_fwd: scale and shift go together");
   DCGC_CHECK_ARG(n_segments >= 0 && width >= 0 && ld_x >= width && ld_out >= 2 * (int64_t)width,
                  "dcgc_gather_fwd: bad sizes");
   DCGC_CHECK_ARG(act >= DCGC_ACT_NONE && act <= DCGC_ACT_TANH, "dcgc_gather_fwd: unknown activation %d", act);
@@ -390,8 +401,8 @@ extern "C" int dcgc_gather_fwd(const float* x, int64_t ld_x, const int32_t* mol_
   const unsigned grid = grid_for(n_segments * groups);
   cudaStream_t st = (cudaStream_t)stream;
 #define DCGC_GATHER_LAUNCH(V, R)                                                                    \
-  gather_fwd_kernel<V, R><<<grid, kThreads, 0, st>>>(x, ld_x, mol_ptr, mol_atoms, n_segments, groups, \
-                                                     width, act, out, ld_out, argrow)
+  gather_fwd_kernel<V, R><<<grid, kThreads, 0, st>>>(x, ld_x, scale, shift, mol_ptr, mol_atoms,      \
+                                                     n_segments, groups, width, act, out, ld_out, argrow)
   if (v4) { if (argrow) DCGC_GATHER_LAUNCH(4, true); else DCGC_GATHER_LAUNCH(4, false); }
   else { if (argrow) DCGC_GATHER_LAUNCH(1, true); else DCGC_GATHER_LAUNCH(1, false); }
 #undef DCGC_GATHER_LAUNCH

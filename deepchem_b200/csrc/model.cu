@@ -1,0 +1,748 @@
+// Whole-model engine for GraphConvModel: one C call runs the forward, the loss and the full
+// backward of
+//   [GraphConv -> ReLU -> BatchNorm -> GraphPool] x L -> Dense -> ReLU -> BatchNorm ->
+//   GraphGather(tanh) -> Linear head -> (softmax) -> weighted mean loss
+// (deepchem/models/torch_models/graphconvmodel.py:188-249, torch_model.py:435-443,1275-1294)
+// over a flat fp32 parameter slab, writing every gradient into a flat gradient slab of the same
+// layout (one NCCL all-reduce per step in data parallel, one fused Adam launch).
+//
+// Fusions relative to the layer-by-layer graph:
+//   * BatchNorm's normalise+affine is folded into the loads of the consumer (GraphPool max /
+//     GraphGather) as a per-channel scale/shift: the normalised tensor is never materialised;
+//   * BatchNorm backward + ReLU backward are one elementwise pass producing the GEMM gradient;
+//   * per-channel statistics (forward: sum y, sum y^2; backward: sum dA, sum dA*y) are two-stage
+//     deterministic column reductions with float64 accumulation (no float atomics);
+//   * the self-path and neighbour-path input gradients are added inside the transposed gather.
+#include <math.h>
+
+#include "common.h"
+
+namespace {
+
+constexpr int kT = 256;
+
+inline unsigned blocks_for(int64_t n, int t = kT) { return (unsigned)((n + t - 1) / t); }
+
+// ------------------------------------------------------------------------------------------
+// column moments: out_a[c] = sum_r a[r,c], out_ab[c] = sum_r a[r,c]*b[r,c]   (float64, 2 stages)
+// ------------------------------------------------------------------------------------------
+constexpr int kMomRows = 512;  // rows per stage-1 block
+
+__global__ void __launch_bounds__(256)
+col_moments_partial(const float* __restrict__ a, int64_t ld_a, const float* __restrict__ b, int64_t ld_b,
+                    int64_t n_rows, int width, double* __restrict__ part) {
+  // block: 128 column lanes x 2 row lanes; grid: (row chunks, column tiles of 128)
+  const int cx = threadIdx.x & 127, ry = threadIdx.x >> 7;
+  const int c = blockIdx.y * 128 + cx;
+  const int64_t r0 = (int64_t)blockIdx.x * kMomRows;
+  const int64_t r1 = min(n_rows, r0 + kMomRows);
+  float sa = 0.f, sab = 0.f;
+  double da = 0.0, dab = 0.0;
+  if (c < width) {
+    int cnt = 0;
+    for (int64_t r = r0 + ry; r < r1; r += 2) {
+      const float va = __ldg(a + r * ld_a + c);
+      const float vb = __ldg(b + r * ld_b + c);
+      sa += va;
+      sab = fmaf(va, vb, sab);
+      if (++cnt == 32) {  // flush the fp32 running sums into float64 every 32 rows
+        da += sa; dab += sab; sa = 0.f; sab = 0.f; cnt = 0;
+      }
+    }
+    da += sa; dab += sab;
+  }
+  __shared__ double sh[2][2][128];
+  sh[0][ry][cx] = da;
+  sh[1][ry][cx] = dab;
+  __syncthreads();
+  if (ry == 0 && c < width) {
+    const int64_t o = ((int64_t)blockIdx.x * 2) * width + c;
+    part[o] = sh[0][0][cx] + sh[0][1][cx];
+    part[o + width] = sh[1][0][cx] + sh[1][1][cx];
+  }
+}
+
+// BatchNorm forward finalize: batch statistics -> folded scale/shift, running-stat update.
+// torch semantics (graphconvmodel.py:150-158: eps=1e-3, momentum=0.99 meaning new-stat weight):
+//   normalise with the biased batch variance; running_var uses the unbiased one.
+__global__ void bn_fwd_finalize(const double* __restrict__ part, int n_chunks, int width, int64_t n_rows,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < n_chunks; ++k) {
+    s += part[((int64_t)k * 2) * width + c];
+    ss += part[((int64_t)k * 2 + 1) * width + c];
+  }
+  const double n = (double)n_rows;
+  const double mean = n > 0 ? s / n : 0.0;
+  double var = n > 0 ? ss / n - mean * mean : 0.0;
+  if (var < 0) var = 0;
+  const double invstd = 1.0 / sqrt(var + (double)eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float sc = (float)(g * invstd);
+  mean_out[c] = (float)mean;
+  invstd_out[c] = (float)invstd;
+  scale_out[c] = sc;
+  shift_out[c] = (float)(b - mean * (double)sc);
+  if (running_mean) {
+    const double unbiased = n > 1 ? var * n / (n - 1.0) : var;
+    running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+    running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+  }
+}
+
+// eval mode: scale/shift from the running statistics
+__global__ void bn_eval_fold(const float* __restrict__ gamma, const float* __restrict__ beta,
+                             const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                             float eps, int width, float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  const float invstd = 1.f / sqrtf(running_var[c] + eps);
+  const float sc = gamma[c] * invstd;
+  scale_out[c] = sc;
+  shift_out[c] = beta[c] - running_mean[c] * sc;
+}
+
+// BatchNorm backward finalize: dgamma, dbeta and the three per-channel coefficients of
+//   dY = c1 * (dA - mean_dA - xhat * mean_dAx),  xhat = (Y - mean) * invstd
+__global__ void bn_bwd_finalize(const double* __restrict__ part, int n_chunks, int width, int64_t n_rows,
+                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                const float* __restrict__ scale, float* __restrict__ dgamma,
+                                float* __restrict__ dbeta, float* __restrict__ coef /* [3, width] */) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  double sda = 0.0, sday = 0.0;
+  for (int k = 0; k < n_chunks; ++k) {
+    sda += part[((int64_t)k * 2) * width + c];
+    sday += part[((int64_t)k * 2 + 1) * width + c];
+  }
+  const double n = (double)n_rows;
+  const double dg = (double)invstd[c] * (sday - (double)mean[c] * sda);  // sum dA * xhat
+  if (dgamma) dgamma[c] = (float)dg;
+  if (dbeta) dbeta[c] = (float)sda;
+  coef[c] = scale[c];
+  coef[width + c] = n > 0 ? (float)(sda / n) : 0.f;
+  coef[2 * width + c] = n > 0 ? (float)(dg / n) : 0.f;
+}
+
+// g = relu'(y) * bn_backward(dA)   (in place on dA allowed)
+__global__ void __launch_bounds__(kT)
+bn_relu_bwd_apply(const float* da, int64_t ld_da, const float* __restrict__ y, int64_t ld_y,
+                  const float* __restrict__ mean, const float* __restrict__ invstd,
+                  const float* __restrict__ coef, int64_t n_rows, int width, int relu, float* g, int64_t ld_g) {
+  const int64_t t = (int64_t)blockIdx.x * kT + threadIdx.x;
+  const int groups = width >> 2;
+  const int64_t row = t / groups;
+  const int c = (int)(t - row * groups) << 2;
+  if (row >= n_rows) return;
+  const float4 d = *reinterpret_cast<const float4*>(da + row * ld_da + c);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(y + row * ld_y + c));
+  const float4 m = __ldg(reinterpret_cast<const float4*>(mean + c));
+  const float4 is = __ldg(reinterpret_cast<const float4*>(invstd + c));
+  const float4 c1 = __ldg(reinterpret_cast<const float4*>(coef + c));
+  const float4 c2 = __ldg(reinterpret_cast<const float4*>(coef + width + c));
+  const float4 c3 = __ldg(reinterpret_cast<const float4*>(coef + 2 * width + c));
+  float4 o;
+  o.x = c1.x * (d.x - c2.x - (v.x - m.x) * is.x * c3.x);
+  o.y = c1.y * (d.y - c2.y - (v.y - m.y) * is.y * c3.y);
+  o.z = c1.z * (d.z - c2.z - (v.z - m.z) * is.z * c3.z);
+  o.w = c1.w * (d.w - c2.w - (v.w - m.w) * is.w * c3.w);
+  if (relu) {
+    o.x = v.x > 0.f ? o.x : 0.f; o.y = v.y > 0.f ? o.y : 0.f;
+    o.z = v.z > 0.f ? o.z : 0.f; o.w = v.w > 0.f ? o.w : 0.f;
+  }
+  *reinterpret_cast<float4*>(g + row * ld_g + c) = o;
+}
+
+// no BatchNorm: g = relu'(y) * dA
+__global__ void __launch_bounds__(kT)
+relu_bwd_apply(const float* da, int64_t ld_da, const float* __restrict__ y, int64_t ld_y, int64_t n_rows,
+               int width, float* g, int64_t ld_g) {
+  const int64_t t = (int64_t)blockIdx.x * kT + threadIdx.x;
+  const int groups = width >> 2;
+  const int64_t row = t / groups;
+  const int c = (int)(t - row * groups) << 2;
+  if (row >= n_rows) return;
+  float4 d = *reinterpret_cast<const float4*>(da + row * ld_da + c);
+  const float4 v = __ldg(reinterpret_cast<const float4*>(y + row * ld_y + c));
+  d.x = v.x > 0.f ? d.x : 0.f; d.y = v.y > 0.f ? d.y : 0.f;
+  d.z = v.z > 0.f ? d.z : 0.f; d.w = v.w > 0.f ? d.w : 0.f;
+  *reinterpret_cast<float4*>(g + row * ld_g + c) = d;
+}
+
+// ------------------------------------------------------------------------------------------
+// GraphConv bias packing: reference order b[0..20] (layers.py:6189-6226) <-> per-degree sums
+// ------------------------------------------------------------------------------------------
+__global__ void conv_bias_pack(const float* __restrict__ b21, int c_out, float* __restrict__ b11) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= DCGC_N_DEG * c_out) return;
+  const int d = i / c_out, c = i - d * c_out;
+  b11[i] = d == 0 ? b21[20 * c_out + c]
+                  : b21[(2 * (d - 1)) * c_out + c] + b21[(2 * (d - 1) + 1) * c_out + c];
+}
+__global__ void conv_bias_unpack(const float* __restrict__ db11, int c_out, float* __restrict__ db21) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 21 * c_out) return;
+  const int k = i / c_out, c = i - k * c_out;
+  const int d = k == 20 ? 0 : k / 2 + 1;
+  db21[i] = db11[d * c_out + c];
+}
+
+// ------------------------------------------------------------------------------------------
+// head: out[b,t] = fp[b,:] . Wh[t,:] + bh[t]   (one warp per output element)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kT)
+head_fwd(const float* __restrict__ fp, int64_t ld_fp, const float* __restrict__ wh, const float* __restrict__ bh,
+         int64_t n_rows, int k, int n_out, float* __restrict__ out) {
+  const int64_t warp = ((int64_t)blockIdx.x * kT + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= n_rows * n_out) return;
+  const int64_t b = warp / n_out;
+  const int t = (int)(warp - b * n_out);
+  float s = 0.f;
+  for (int j = lane; j < k; j += 32) s = fmaf(__ldg(fp + b * ld_fp + j), __ldg(wh + (int64_t)t * k + j), s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[b * n_out + t] = s + (bh ? bh[t] : 0.f);
+}
+
+// per-(sample, task) loss and d(out); mean over all n_samples*n_tasks elements
+// (torch_model.py:1275-1294).  mode 0: w*(out-y)^2 (losses.py:76-94); mode 1: -w*sum_c y_c
+// log_softmax(logits)_c (losses.py:236-259).
+__global__ void __launch_bounds__(kT)
+loss_fwd_bwd(const float* __restrict__ out, const float* __restrict__ y, const float* __restrict__ w,
+             int64_t n_elems, int n_classes, int mode, float* __restrict__ per_elem, float* __restrict__ dout) {
+  const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
+  if (i >= n_elems) return;
+  const float wi = w ? w[i] : 1.f;
+  const float inv = 1.f / (float)n_elems;
+  if (mode == 0) {
+    const float d = out[i] - y[i];
+    per_elem[i] = wi * d * d;
+    dout[i] = 2.f * wi * d * inv;
+  } else {
+    const float* lg = out + i * n_classes;
+    const float* yy = y + i * n_classes;
+    float mx = -INFINITY;
+    for (int c = 0; c < n_classes; ++c) mx = fmaxf(mx, lg[c]);
+    float se = 0.f, sy = 0.f;
+    for (int c = 0; c < n_classes; ++c) { se += expf(lg[c] - mx); sy += yy[c]; }
+    const float lse = mx + logf(se);
+    float l = 0.f;
+    for (int c = 0; c < n_classes; ++c) {
+      const float logp = lg[c] - lse;
+      l -= yy[c] * logp;
+      dout[i * n_classes + c] = wi * inv * (expf(logp) * sy - yy[c]);
+    }
+    per_elem[i] = wi * l;
+  }
+}
+
+__global__ void __launch_bounds__(1024) loss_reduce(const float* __restrict__ per_elem, int64_t n_elems,
+                                                    float* __restrict__ loss) {
+  __shared__ double sh[1024];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n_elems; i += 1024) s += per_elem[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = n_elems > 0 ? (float)(sh[0] / (double)n_elems) : 0.f;
+}
+
+__global__ void softmax_rows(const float* __restrict__ logits, int64_t n_rows, int n_classes,
+                             float* __restrict__ probs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows) return;
+  const float* lg = logits + i * n_classes;
+  float mx = -INFINITY;
+  for (int c = 0; c < n_classes; ++c) mx = fmaxf(mx, lg[c]);
+  float se = 0.f;
+  for (int c = 0; c < n_classes; ++c) se += expf(lg[c] - mx);
+  for (int c = 0; c < n_classes; ++c) probs[i * n_classes + c] = expf(lg[c] - mx) / se;
+}
+
+// head backward, stage 1: partial dWh[t,j] / dbh[t] over a chunk of samples
+constexpr int kHeadChunk = 128;
+__global__ void __launch_bounds__(kT)
+head_bwd_partial(const float* __restrict__ dout, const float* __restrict__ fp, int64_t ld_fp, int64_t n_rows,
+                 int k, int n_out, float* __restrict__ part /* [chunks, n_out, k+1] */) {
+  const int t = blockIdx.y;
+  const int64_t b0 = (int64_t)blockIdx.x * kHeadChunk, b1 = min(n_rows, b0 + kHeadChunk);
+  for (int j = threadIdx.x; j <= k; j += kT) {
+    float s = 0.f;
+    if (j < k) {
+      for (int64_t b = b0; b < b1; ++b) s = fmaf(__ldg(dout + b * n_out + t), __ldg(fp + b * ld_fp + j), s);
+    } else {
+      for (int64_t b = b0; b < b1; ++b) s += __ldg(dout + b * n_out + t);
+    }
+    part[((int64_t)blockIdx.x * n_out + t) * (k + 1) + j] = s;
+  }
+}
+__global__ void head_bwd_final(const float* __restrict__ part, int n_chunks, int k, int n_out,
+                               float* __restrict__ dwh, float* __restrict__ dbh) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)n_out * (k + 1)) return;
+  const int t = (int)(i / (k + 1)), j = (int)(i - (int64_t)t * (k + 1));
+  float s = 0.f;
+  for (int c = 0; c < n_chunks; ++c) s += part[((int64_t)c * n_out + t) * (k + 1) + j];
+  if (j < k) dwh[(int64_t)t * k + j] = s;
+  else if (dbh) dbh[t] = s;
+}
+// dfp[b,j] = sum_t dout[b,t] * Wh[t,j] for b < n_rows, 0 for the padded segments
+__global__ void __launch_bounds__(kT)
+head_bwd_input(const float* __restrict__ dout, const float* __restrict__ wh, int64_t n_rows, int64_t n_seg, int k,
+               int n_out, float* __restrict__ dfp) {
+  const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
+  if (i >= n_seg * k) return;
+  const int64_t b = i / k;
+  const int j = (int)(i - b * k);
+  float s = 0.f;
+  if (b < n_rows)
+    for (int t = 0; t < n_out; ++t) s = fmaf(__ldg(dout + b * n_out + t), __ldg(wh + (int64_t)t * k + j), s);
+  dfp[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Adam on the flat slab (torch.optim.Adam semantics, models/optimizers.py:190-241)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kT)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            int64_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+  const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i] * grad_scale;
+  const float mi = b1 * m[i] + (1.f - b1) * gi;
+  const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  p[i] -= (lr / bc1) * (mi / denom);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct Arena {
+  char* base;
+  int64_t off, cap;
+  bool ok = true;
+  template <typename T>
+  T* take(int64_t n) {
+    const int64_t bytes = dcgc_align_up(n * (int64_t)sizeof(T), 256);
+    if (off + bytes > cap) { ok = false; off += bytes; return nullptr; }
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+
+struct Layout {
+  int L;
+  int f[DCGC_MODEL_MAX_LAYERS + 1];   // input width of conv l (f[0] = n_feat), f[L] = last conv width
+  int fp[DCGC_MODEL_MAX_LAYERS + 1];  // padded to a multiple of 4
+  int64_t conv_w[DCGC_MODEL_MAX_LAYERS], conv_b[DCGC_MODEL_MAX_LAYERS];
+  int64_t bn_g[DCGC_MODEL_MAX_LAYERS + 1], bn_b[DCGC_MODEL_MAX_LAYERS + 1];
+  int64_t dense_w, dense_b, head_w, head_b, n_params;
+  int64_t bn_mean[DCGC_MODEL_MAX_LAYERS + 1], bn_var[DCGC_MODEL_MAX_LAYERS + 1], n_bn;
+};
+
+int make_layout(const dcgc_gcmodel_config* cfg, Layout* lo) {
+  DCGC_CHECK_ARG(cfg, "dcgc_gcmodel: null config");
+  DCGC_CHECK_ARG(cfg->n_layers >= 1 && cfg->n_layers <= DCGC_MODEL_MAX_LAYERS, "dcgc_gcmodel: 1..%d conv layers",
+                 DCGC_MODEL_MAX_LAYERS);
+  DCGC_CHECK_ARG(cfg->n_feat > 0 && cfg->dense > 0 && cfg->n_out > 0, "dcgc_gcmodel: bad widths");
+  DCGC_CHECK_ARG(cfg->dense % 4 == 0, "dcgc_gcmodel: dense width must be a multiple of 4");
+  DCGC_CHECK_ARG(cfg->mode == 0 || (cfg->mode == 1 && cfg->n_classes >= 2 && cfg->n_out % cfg->n_classes == 0),
+                 "dcgc_gcmodel: bad mode / n_classes");
+  const int L = cfg->n_layers;
+  lo->L = L;
+  lo->f[0] = cfg->n_feat;
+  for (int l = 0; l < L; ++l) {
+    DCGC_CHECK_ARG(cfg->widths[l] > 0 && cfg->widths[l] % 4 == 0,
+                   "dcgc_gcmodel: conv widths must be positive multiples of 4");
+    lo->f[l + 1] = cfg->widths[l];
+  }
+  for (int l = 0; l <= L; ++l) lo->fp[l] = (lo->f[l] + 3) / 4 * 4;
+  int64_t off = 0, boff = 0;
+  auto take = [&](int64_t n) { int64_t o = off; off += (n + 3) / 4 * 4; return o; };  // 16-byte aligned tensors
+  for (int l = 0; l < L; ++l) {
+    const int c = cfg->widths[l];
+    lo->conv_w[l] = take((int64_t)DCGC_N_DEG * 2 * lo->fp[l] * c);
+    lo->conv_b[l] = take((int64_t)21 * c);
+    if (cfg->batch_norm) {
+      lo->bn_g[l] = take(c); lo->bn_b[l] = take(c);
+      lo->bn_mean[l] = boff; boff += c; lo->bn_var[l] = boff; boff += c;
+    } else {
+      lo->bn_g[l] = lo->bn_b[l] = lo->bn_mean[l] = lo->bn_var[l] = -1;
+    }
+  }
+  lo->dense_w = take((int64_t)cfg->dense * lo->f[L]);
+  lo->dense_b = take(cfg->dense);
+  if (cfg->batch_norm) {
+    lo->bn_g[L] = take(cfg->dense); lo->bn_b[L] = take(cfg->dense);
+    lo->bn_mean[L] = boff; boff += cfg->dense; lo->bn_var[L] = boff; boff += cfg->dense;
+  } else {
+    lo->bn_g[L] = lo->bn_b[L] = lo->bn_mean[L] = lo->bn_var[L] = -1;
+  }
+  lo->head_w = take((int64_t)cfg->n_out * 2 * cfg->dense);
+  lo->head_b = take(cfg->n_out);
+  lo->n_params = off;
+  lo->n_bn = boff;
+  return DCGC_OK;
+}
+
+struct Saved {
+  const float* h[DCGC_MODEL_MAX_LAYERS + 1];  // conv inputs (h[0] = x), h[L] = last pool output
+  int64_t ld_h[DCGC_MODEL_MAX_LAYERS + 1];
+  float* s[DCGC_MODEL_MAX_LAYERS];
+  float* y[DCGC_MODEL_MAX_LAYERS];
+  uint8_t* arg[DCGC_MODEL_MAX_LAYERS];
+  float* z;        // dense pre-BN (post-ReLU)
+  float* stats;    // per BN: mean, invstd, scale, shift (4 * width each)
+  int64_t stats_off[DCGC_MODEL_MAX_LAYERS + 1];
+  float* fp;       // fingerprint [n_seg, 2D]
+  int32_t* argrow;
+  float* out;      // [n_samples, n_out]
+  float* b11[DCGC_MODEL_MAX_LAYERS];
+  double* part;    // column-moment partials
+  int n_chunks;
+};
+
+int check_topo(const dcgc_topology* t) {
+  DCGC_CHECK_ARG(t, "dcgc_gcmodel: null topology");
+  DCGC_CHECK_ARG(t->n_atoms >= 0 && t->n_edges >= 0 && t->n_segments >= 0 && t->n_tiles >= 0,
+                 "dcgc_gcmodel: negative topology size");
+  if (t->n_atoms > 0)
+    DCGC_CHECK_ARG(t->row_ptr && t->t_row_ptr && t->mol_ptr && t->mol_atoms && t->membership && t->tiles,
+                   "dcgc_gcmodel: null topology array");
+  if (t->n_edges > 0) DCGC_CHECK_ARG(t->col_idx && t->t_src && t->t_slot, "dcgc_gcmodel: null adjacency array");
+  return DCGC_OK;
+}
+
+#define RET_IF(expr)                \
+  do {                              \
+    int st__ = (expr);              \
+    if (st__ != DCGC_OK) return st__; \
+  } while (0)
+
+int bn_forward(const dcgc_gcmodel_config* cfg, const Layout& lo, int idx, const float* y, int64_t ld_y, int64_t n,
+               int width, const float* params, float* bn_running, int training, Saved& sv, cudaStream_t st) {
+  float* stats = sv.stats + sv.stats_off[idx];
+  float *mean = stats, *invstd = stats + width, *scale = stats + 2 * width, *shift = stats + 3 * width;
+  const float* gamma = params + lo.bn_g[idx];
+  const float* beta = params + lo.bn_b[idx];
+  float* rm = bn_running ? bn_running + lo.bn_mean[idx] : nullptr;
+  float* rv = bn_running ? bn_running + lo.bn_var[idx] : nullptr;
+  if (training) {
+    if (n > 0) {
+      dim3 grid((unsigned)sv.n_chunks, (unsigned)((width + 127) / 128));
+      col_moments_partial<<<grid, 256, 0, st>>>(y, ld_y, y, ld_y, n, width, sv.part);
+      DCGC_CUDA_LAUNCH_CHECK("col_moments_partial");
+    }
+    bn_fwd_finalize<<<(width + 127) / 128, 128, 0, st>>>(sv.part, n > 0 ? sv.n_chunks : 0, width, n, gamma, beta,
+                                                         cfg->bn_eps, cfg->bn_momentum, rm, rv, mean, invstd, scale,
+                                                         shift);
+    DCGC_CUDA_LAUNCH_CHECK("bn_fwd_finalize");
+  } else {
+    DCGC_CHECK_ARG(rm && rv, "dcgc_gcmodel: eval-mode BatchNorm needs the running statistics");
+    bn_eval_fold<<<(width + 127) / 128, 128, 0, st>>>(gamma, beta, rm, rv, cfg->bn_eps, width, scale, shift);
+    DCGC_CUDA_LAUNCH_CHECK("bn_eval_fold");
+  }
+  return DCGC_OK;
+}
+
+int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_topology* t, const float* x,
+                 int64_t ld_x, int64_t n_samples, const float* params, float* bn_running, int training,
+                 int keep_arg, Arena& ws, Saved& sv, cudaStream_t st) {
+  const int L = lo.L, D = cfg->dense;
+  const int64_t N = t->n_atoms, S = t->n_segments;
+  DCGC_CHECK_ARG(ld_x >= lo.fp[0] || N == 0, "dcgc_gcmodel: x must be zero-padded to a leading dimension >= %d",
+                 lo.fp[0]);
+  DCGC_CHECK_ARG(n_samples >= 0 && n_samples <= S, "dcgc_gcmodel: n_samples outside [0, n_segments]");
+  // ---- carve the workspace
+  sv.n_chunks = (int)((N + kMomRows - 1) / kMomRows);
+  int wmax = D;
+  for (int l = 0; l < L; ++l) wmax = wmax > cfg->widths[l] ? wmax : cfg->widths[l];
+  sv.part = ws.take<double>((int64_t)(sv.n_chunks > 0 ? sv.n_chunks : 1) * 2 * wmax);
+  int64_t so = 0;
+  for (int l = 0; l <= L; ++l) { sv.stats_off[l] = so; so += 4 * (int64_t)(l < L ? cfg->widths[l] : D); }
+  sv.stats = ws.take<float>(so);
+  sv.h[0] = x; sv.ld_h[0] = ld_x;
+  for (int l = 0; l < L; ++l) {
+    const int c = cfg->widths[l];
+    sv.s[l] = ws.take<float>(N * lo.fp[l]);
+    sv.y[l] = ws.take<float>(N * c);
+    sv.arg[l] = keep_arg ? ws.take<uint8_t>(N * c) : nullptr;
+    sv.h[l + 1] = ws.take<float>(N * c); sv.ld_h[l + 1] = c;
+    sv.b11[l] = ws.take<float>(DCGC_N_DEG * c);
+  }
+  sv.z = ws.take<float>(N * D);
+  sv.fp = ws.take<float>(S * 2 * D);
+  sv.argrow = keep_arg ? ws.take<int32_t>(S * D) : nullptr;
+  sv.out = ws.take<float>((n_samples > 0 ? n_samples : 1) * cfg->n_out);
+  if (!ws.ok) {
+    dcgc_set_error("dcgc_gcmodel: workspace too small (%lld bytes needed so far, %lld given)", (long long)ws.off,
+                   (long long)ws.cap);
+    return DCGC_ERR_NOMEM;
+  }
+  // ---- conv stack
+  for (int l = 0; l < L; ++l) {
+    const int c = cfg->widths[l], fp = lo.fp[l];
+    const float* h = sv.h[l];
+    const int64_t ld = sv.ld_h[l];
+    conv_bias_pack<<<blocks_for(DCGC_N_DEG * c), kT, 0, st>>>(params + lo.conv_b[l], c, sv.b11[l]);
+    DCGC_CUDA_LAUNCH_CHECK("conv_bias_pack");
+    RET_IF(dcgc_gather_sum(h, ld, t->row_ptr, t->col_idx, N, fp, nullptr, 0, sv.s[l], fp, st));
+    RET_IF(dcgc_group_gemm_fwd(cfg->gemm_mode, h, ld, fp, sv.s[l], fp, fp, params + lo.conv_w[l], sv.b11[l], c,
+                               t->tiles, t->n_tiles, 128, N, DCGC_ACT_RELU, sv.y[l], c, st));
+    const float *scale = nullptr, *shift = nullptr;
+    if (cfg->batch_norm) {
+      RET_IF(bn_forward(cfg, lo, l, sv.y[l], c, N, c, params, bn_running, training, sv, st));
+      scale = sv.stats + sv.stats_off[l] + 2 * c;
+      shift = scale + c;
+    }
+    RET_IF(dcgc_pool_fwd(sv.y[l], c, scale, shift, t->row_ptr, t->col_idx, N, c, const_cast<float*>(sv.h[l + 1]), c,
+                         sv.arg[l], c, st));
+  }
+  // ---- atom-level dense + ReLU (+BN folded into the gather), GraphGather(tanh), head
+  RET_IF(dcgc_linear_fwd(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], params + lo.dense_w, params + lo.dense_b, D, N,
+                         DCGC_ACT_RELU, sv.z, D, st));
+  const float *scale = nullptr, *shift = nullptr;
+  if (cfg->batch_norm) {
+    RET_IF(bn_forward(cfg, lo, L, sv.z, D, N, D, params, bn_running, training, sv, st));
+    scale = sv.stats + sv.stats_off[L] + 2 * D;
+    shift = scale + D;
+  }
+  RET_IF(dcgc_gather_fwd(sv.z, D, scale, shift, t->mol_ptr, t->mol_atoms, S, D, DCGC_ACT_TANH, sv.fp, 2 * D,
+                         sv.argrow, st));
+  if (n_samples > 0) {
+    head_fwd<<<blocks_for(n_samples * cfg->n_out * 32), kT, 0, st>>>(sv.fp, 2 * D, params + lo.head_w,
+                                                                    params + lo.head_b, n_samples, 2 * D, cfg->n_out,
+                                                                    sv.out);
+    DCGC_CUDA_LAUNCH_CHECK("head_fwd");
+  }
+  return DCGC_OK;
+}
+
+}  // namespace
+
+extern "C" int dcgc_gcmodel_layout(const dcgc_gcmodel_config* cfg, int64_t* param_offsets, int64_t* bn_offsets,
+                                   int64_t* n_params, int64_t* n_bn) {
+  Layout lo;
+  RET_IF(make_layout(cfg, &lo));
+  if (param_offsets) {
+    int k = 0;
+    for (int l = 0; l < lo.L; ++l) {
+      param_offsets[k++] = lo.conv_w[l]; param_offsets[k++] = lo.conv_b[l];
+      param_offsets[k++] = lo.bn_g[l]; param_offsets[k++] = lo.bn_b[l];
+    }
+    param_offsets[k++] = lo.dense_w; param_offsets[k++] = lo.dense_b;
+    param_offsets[k++] = lo.bn_g[lo.L]; param_offsets[k++] = lo.bn_b[lo.L];
+    param_offsets[k++] = lo.head_w; param_offsets[k++] = lo.head_b;
+  }
+  if (bn_offsets) {
+    int k = 0;
+    for (int l = 0; l <= lo.L; ++l) { bn_offsets[k++] = lo.bn_mean[l]; bn_offsets[k++] = lo.bn_var[l]; }
+  }
+  if (n_params) *n_params = lo.n_params;
+  if (n_bn) *n_bn = lo.n_bn;
+  return DCGC_OK;
+}
+
+extern "C" int64_t dcgc_gcmodel_workspace_bytes(const dcgc_gcmodel_config* cfg, int64_t n_atoms, int64_t n_segments) {
+  Layout lo;
+  if (make_layout(cfg, &lo) != DCGC_OK || n_atoms < 0 || n_segments < 0) return -1;
+  const int L = lo.L, D = cfg->dense;
+  int wmax = D;
+  int64_t per_atom = 0;  // floats per atom
+  for (int l = 0; l < L; ++l) {
+    const int c = cfg->widths[l];
+    wmax = wmax > c ? wmax : c;
+    per_atom += lo.fp[l] + 2 * c + (c + 3) / 4;  // S, Y, P, arg (bytes/4)
+  }
+  per_atom += D;                 // Z
+  int fmax = 0;
+  for (int l = 0; l <= L; ++l) fmax = fmax > lo.fp[l] ? fmax : lo.fp[l];
+  per_atom += 2 * (int64_t)wmax + 2 * (int64_t)fmax;  // backward scratch: dA, dP, d1, d2
+  int64_t bytes = n_atoms * per_atom * 4;
+  bytes += n_segments * (int64_t)(2 * D * 2 + D) * 4;            // fp, dfp, argrow
+  bytes += n_segments * (int64_t)cfg->n_out * 4 * 3;              // out, dout, per-element loss
+  bytes += ((n_atoms + kMomRows - 1) / kMomRows + 1) * 2 * (int64_t)wmax * 8;
+  bytes += ((n_segments + kHeadChunk - 1) / kHeadChunk + 1) * (int64_t)cfg->n_out * (2 * D + 1) * 4;
+  int64_t wg = 0;
+  for (int l = 0; l < L; ++l) {
+    const int64_t b = dcgc_group_gemm_wgrad_workspace(lo.fp[l], lo.fp[l], cfg->widths[l], DCGC_N_DEG);
+    wg = wg > b ? wg : b;
+  }
+  const int64_t bd = dcgc_linear_wgrad_workspace(lo.f[L], D);
+  wg = wg > bd ? wg : bd;
+  bytes += wg;
+  bytes += (int64_t)(L + 1) * 16 * wmax * 4 + (int64_t)L * DCGC_N_DEG * wmax * 8 + 3 * (int64_t)wmax * 4;
+  return bytes + 256 * 64;  // alignment slack for every carve
+}
+
+extern "C" int dcgc_gcmodel_forward(const dcgc_gcmodel_config* cfg, const dcgc_topology* topo, const float* x,
+                                    int64_t ld_x, int64_t n_samples, const float* params, float* bn_running,
+                                    int32_t training, void* workspace, int64_t workspace_bytes, float* out,
+                                    float* probs, float* fingerprint, void* stream) {
+  Layout lo;
+  RET_IF(make_layout(cfg, &lo));
+  RET_IF(check_topo(topo));
+  DCGC_CHECK_ARG(params && (workspace || workspace_bytes == 0), "dcgc_gcmodel_forward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ws{(char*)workspace, 0, workspace_bytes};
+  Saved sv{};
+  RET_IF(forward_impl(cfg, lo, topo, x, ld_x, n_samples, params, bn_running, training, 0, ws, sv, st));
+  const int64_t S = topo->n_segments;
+  if (fingerprint && S > 0)
+    DCGC_CUDA_CALL(cudaMemcpyAsync(fingerprint, sv.fp, (size_t)S * 2 * cfg->dense * 4, cudaMemcpyDeviceToDevice, st));
+  if (out && n_samples > 0)
+    DCGC_CUDA_CALL(cudaMemcpyAsync(out, sv.out, (size_t)n_samples * cfg->n_out * 4, cudaMemcpyDeviceToDevice, st));
+  if (probs && n_samples > 0 && cfg->mode == 1) {
+    const int64_t rows = n_samples * (cfg->n_out / cfg->n_classes);
+    softmax_rows<<<blocks_for(rows), kT, 0, st>>>(sv.out, rows, cfg->n_classes, probs);
+    DCGC_CUDA_LAUNCH_CHECK("softmax_rows");
+  }
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcgc_topology* topo, const float* x,
+                                       int64_t ld_x, const float* y, const float* w, int64_t n_samples,
+                                       const float* params, float* grads, float* bn_running, void* workspace,
+                                       int64_t workspace_bytes, float* loss_dev, float* out, void* stream) {
+  Layout lo;
+  RET_IF(make_layout(cfg, &lo));
+  RET_IF(check_topo(topo));
+  DCGC_CHECK_ARG(params && grads && y && loss_dev && workspace, "dcgc_gcmodel_train_step: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const dcgc_topology* t = topo;
+  const int L = lo.L, D = cfg->dense, T = cfg->n_out;
+  const int64_t N = t->n_atoms, S = t->n_segments;
+  Arena ws{(char*)workspace, 0, workspace_bytes};
+  Saved sv{};
+  RET_IF(forward_impl(cfg, lo, t, x, ld_x, n_samples, params, bn_running, 1, 1, ws, sv, st));
+
+  // ---- backward scratch
+  int wmax = D, fmax = 0;
+  for (int l = 0; l < L; ++l) wmax = wmax > cfg->widths[l] ? wmax : cfg->widths[l];
+  for (int l = 0; l <= L; ++l) fmax = fmax > lo.fp[l] ? fmax : lo.fp[l];
+  float* dA = ws.take<float>(N * wmax);   // grad wrt BN output / then GEMM gradient G (in place)
+  float* dP = ws.take<float>(N * wmax);   // grad wrt pool output of the layer below
+  float* d2 = ws.take<float>(N * fmax);   // neighbour-path input gradient before the transposed gather
+  float* dfp = ws.take<float>(S * 2 * D);
+  float* dout = ws.take<float>((n_samples > 0 ? n_samples : 1) * T);
+  const int n_loss_elems_per_row = cfg->mode == 1 ? T / cfg->n_classes : T;
+  float* per_elem = ws.take<float>((n_samples > 0 ? n_samples : 1) * n_loss_elems_per_row);
+  const int head_chunks = (int)((n_samples + kHeadChunk - 1) / kHeadChunk);
+  float* head_part = ws.take<float>((int64_t)(head_chunks > 0 ? head_chunks : 1) * T * (2 * D + 1));
+  float* coef = ws.take<float>(3 * (int64_t)wmax);
+  float* db11 = ws.take<float>(DCGC_N_DEG * (int64_t)wmax);
+  int64_t wg_bytes = dcgc_linear_wgrad_workspace(lo.f[L], D);
+  for (int l = 0; l < L; ++l) {
+    const int64_t b = dcgc_group_gemm_wgrad_workspace(lo.fp[l], lo.fp[l], cfg->widths[l], DCGC_N_DEG);
+    wg_bytes = wg_bytes > b ? wg_bytes : b;
+  }
+  char* wg = ws.take<char>(wg_bytes);
+  if (!ws.ok) {
+    dcgc_set_error("dcgc_gcmodel_train_step: workspace too small (%lld bytes needed, %lld given)", (long long)ws.off,
+                   (long long)ws.cap);
+    return DCGC_ERR_NOMEM;
+  }
+
+  // ---- loss and head
+  const int64_t n_elems = n_samples * n_loss_elems_per_row;
+  if (n_elems > 0) {
+    loss_fwd_bwd<<<blocks_for(n_elems), kT, 0, st>>>(sv.out, y, w, n_elems, cfg->mode == 1 ? cfg->n_classes : 1,
+                                                     cfg->mode, per_elem, dout);
+    DCGC_CUDA_LAUNCH_CHECK("loss_fwd_bwd");
+  }
+  loss_reduce<<<1, 1024, 0, st>>>(per_elem, n_elems, loss_dev);
+  DCGC_CUDA_LAUNCH_CHECK("loss_reduce");
+  if (out && n_samples > 0)
+    DCGC_CUDA_CALL(cudaMemcpyAsync(out, sv.out, (size_t)n_samples * T * 4, cudaMemcpyDeviceToDevice, st));
+  if (head_chunks > 0) {
+    dim3 grid((unsigned)head_chunks, (unsigned)T);
+    head_bwd_partial<<<grid, kT, 0, st>>>(dout, sv.fp, 2 * D, n_samples, 2 * D, T, head_part);
+    DCGC_CUDA_LAUNCH_CHECK("head_bwd_partial");
+  }
+  head_bwd_final<<<blocks_for((int64_t)T * (2 * D + 1)), kT, 0, st>>>(head_part, head_chunks, 2 * D, T,
+                                                                      grads + lo.head_w, grads + lo.head_b);
+  DCGC_CUDA_LAUNCH_CHECK("head_bwd_final");
+  if (S > 0) {
+    head_bwd_input<<<blocks_for(S * 2 * D), kT, 0, st>>>(dout, params + lo.head_w, n_samples, S, 2 * D, T, dfp);
+    DCGC_CUDA_LAUNCH_CHECK("head_bwd_input");
+  }
+  // ---- GraphGather backward -> dA (grad wrt the BN output of the dense layer)
+  RET_IF(dcgc_gather_bwd(dfp, 2 * D, sv.fp, 2 * D, sv.argrow, t->membership, N, D, DCGC_ACT_TANH, dA, D, st));
+
+  auto bn_backward = [&](int idx, const float* yv, int width) -> int {
+    // dA (ld = width) -> G in place; dgamma / dbeta into the gradient slab
+    if (cfg->batch_norm) {
+      const float* stats = sv.stats + sv.stats_off[idx];
+      if (N > 0) {
+        dim3 grid((unsigned)sv.n_chunks, (unsigned)((width + 127) / 128));
+        col_moments_partial<<<grid, 256, 0, st>>>(dA, width, yv, width, N, width, sv.part);
+        DCGC_CUDA_LAUNCH_CHECK("col_moments_partial (bwd)");
+      }
+      bn_bwd_finalize<<<(width + 127) / 128, 128, 0, st>>>(sv.part, N > 0 ? sv.n_chunks : 0, width, N, stats,
+                                                           stats + width, stats + 2 * width, grads + lo.bn_g[idx],
+                                                           grads + lo.bn_b[idx], coef);
+      DCGC_CUDA_LAUNCH_CHECK("bn_bwd_finalize");
+      if (N > 0) {
+        bn_relu_bwd_apply<<<blocks_for(N * (width / 4)), kT, 0, st>>>(dA, width, yv, width, stats, stats + width, coef,
+                                                                      N, width, 1, dA, width);
+        DCGC_CUDA_LAUNCH_CHECK("bn_relu_bwd_apply");
+      }
+    } else if (N > 0) {
+      relu_bwd_apply<<<blocks_for(N * (width / 4)), kT, 0, st>>>(dA, width, yv, width, N, width, dA, width);
+      DCGC_CUDA_LAUNCH_CHECK("relu_bwd_apply");
+    }
+    return DCGC_OK;
+  };
+
+  // ---- dense layer backward
+  RET_IF(bn_backward(L, sv.z, D));
+  RET_IF(dcgc_linear_wgrad(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], dA, D, D, N, grads + lo.dense_w,
+                           grads + lo.dense_b, wg, wg_bytes, st));
+  RET_IF(dcgc_linear_dgrad(cfg->gemm_mode, dA, D, D, params + lo.dense_w, lo.f[L], N, dP, lo.f[L], st));
+
+  // ---- conv stack backward
+  for (int l = L - 1; l >= 0; --l) {
+    const int c = cfg->widths[l], fp = lo.fp[l];
+    // GraphPool backward over CSR^T: dP (ld c) -> dA (ld c)
+    RET_IF(dcgc_pool_bwd(dP, c, sv.arg[l], c, nullptr, t->t_row_ptr, t->t_src, t->t_slot, N, c, dA, c, st));
+    RET_IF(bn_backward(l, sv.y[l], c));
+    RET_IF(dcgc_group_gemm_wgrad(cfg->gemm_mode, sv.h[l], sv.ld_h[l], fp, sv.s[l], fp, fp, dA, c, c, t->deg_count,
+                                 DCGC_N_DEG, grads + lo.conv_w[l], db11, wg, wg_bytes, st));
+    conv_bias_unpack<<<blocks_for(21 * c), kT, 0, st>>>(db11, c, grads + lo.conv_b[l]);
+    DCGC_CUDA_LAUNCH_CHECK("conv_bias_unpack");
+    if (l > 0) {
+      // [dP | d2] = G . W^T, then dP += transposed gather of d2
+      RET_IF(dcgc_group_gemm_dgrad(cfg->gemm_mode, dA, c, c, params + lo.conv_w[l], fp, fp, t->tiles, t->n_tiles, 128,
+                                   N, dP, fp, d2, fp, st));
+      RET_IF(dcgc_gather_sum(d2, fp, t->t_row_ptr, t->t_src, N, fp, dP, fp, dP, fp, st));
+    }
+  }
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              float lr, float beta1, float beta2, float eps, int64_t step, float grad_scale,
+                              void* stream) {
+  DCGC_CHECK_ARG(n >= 0 && step >= 1, "dcgc_adam_step: bad sizes (step counts from 1)");
+  if (n == 0) return DCGC_OK;
+  DCGC_CHECK_ARG(params && grads && exp_avg && exp_avg_sq, "dcgc_adam_step: null pointer");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<blocks_for(n), kT, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                              eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  DCGC_CUDA_LAUNCH_CHECK("dcgc_adam_step");
+  return DCGC_OK;
+}

@@ -1,0 +1,232 @@
+"""Flat-slab training engine binding (dcgc_gcmodel_* in include/dcgc.h).
+
+All parameters of a ``_GraphConvTorchModel`` are re-homed into ONE contiguous fp32 buffer whose
+layout is the one the C++ engine computes; every ``nn.Parameter`` (and BatchNorm running buffer)
+becomes a view into it, so ``state_dict()`` keeps the reference's keys and shapes
+(``graph_convs.{i}.W_list.{k}``, ``batch_norms.{i}.*``, ``dense.*``, ...) while one C call
+runs forward + loss + backward and writes every gradient into a parallel flat gradient slab
+(``p.grad`` are views of it).  Data parallel = one all-reduce of that slab; the optimizer is one
+fused Adam launch.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+_workspaces = {}
+
+
+def _ws(nbytes, device):
+    key = (device.type, device.index)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.1) + 1024, dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def topology_struct(topo):
+    """dcgc_topology for a DeviceTopology (cached on the object)."""
+    st = getattr(topo, "_c_struct", None)
+    if st is not None:
+        return st
+    st = _lib.Topology()
+    st.n_atoms, st.n_edges, st.n_segments, st.n_tiles = topo.n_atoms, topo.n_edges, topo.n_segments, topo.n_tiles
+    for d in range(11):
+        st.deg_count[d] = topo.deg_count[d]
+    for name in ("row_ptr", "col_idx", "t_row_ptr", "t_src", "t_slot", "mol_ptr", "mol_atoms", "membership", "tiles"):
+        setattr(st, name, getattr(topo, name).data_ptr())
+    topo._c_struct = st
+    return st
+
+
+class FlatEngine(object):
+    """Owns the parameter / gradient / optimizer slabs of one model."""
+
+    def __init__(self, model, device, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.model = model
+        self.device = torch.device(device)
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.step_count = 0
+        L = len(model.graph_convs)
+        cfg = _lib.GcModelConfig()
+        cfg.n_layers = L
+        cfg.n_feat = model.graph_convs[0].number_input_features
+        for l, conv in enumerate(model.graph_convs):
+            cfg.widths[l] = conv.out_channel
+        cfg.dense = model.dense.out_features
+        head = model.reshape_dense if model.mode == "classification" else model.regression_dense
+        cfg.n_out = head.out_features
+        cfg.n_classes = model.n_classes if model.mode == "classification" else 1
+        cfg.mode = 1 if model.mode == "classification" else 0
+        cfg.batch_norm = 1 if isinstance(model.batch_norms[0], torch.nn.BatchNorm1d) else 0
+        cfg.gemm_mode = model.gemm_mode
+        cfg.bn_eps, cfg.bn_momentum = 1e-3, 0.99
+        self.cfg = cfg
+        self.head = head
+        n_off = 4 * L + 6
+        offs = (ctypes.c_int64 * n_off)()
+        boffs = (ctypes.c_int64 * (2 * (L + 1)))()
+        n_params, n_bn = ctypes.c_int64(), ctypes.c_int64()
+        check(_lib.lib().dcgc_gcmodel_layout(ctypes.byref(cfg), offs, boffs, ctypes.byref(n_params),
+                                             ctypes.byref(n_bn)))
+        self.offsets, self.bn_offsets = list(offs), list(boffs)
+        self.n_params, self.n_bn = n_params.value, n_bn.value
+        dev = self.device
+        self.params = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+        self.grads = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(self.n_params, dtype=torch.float32, device=dev)
+        self.bn_running = torch.zeros(max(self.n_bn, 1), dtype=torch.float32, device=dev)
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self._slots = []      # (parameter, param view, grad view)
+        self._bn_slots = []   # (module, name, view)
+        self._build_slots()
+        self.adopt()
+
+    @staticmethod
+    def eligible(model):
+        """The engine covers the standard fit path: classification / regression without the
+        uncertainty head, widths that are multiples of 4.  Anything else uses the autograd layers."""
+        if getattr(model, "uncertainty", False):
+            return False
+        if len(model.graph_convs) > _lib.MODEL_MAX_LAYERS:
+            return False
+        widths = [c.out_channel for c in model.graph_convs] + [model.dense.out_features]
+        if any(w % 4 for w in widths):
+            return False
+        ins = [c.number_input_features for c in model.graph_convs]
+        if ins[1:] != widths[:len(ins) - 1] or model.dense.in_features != widths[len(ins) - 1]:
+            return False
+        bn = [isinstance(b, torch.nn.BatchNorm1d) for b in model.batch_norms]
+        return all(bn) or not any(bn)
+
+    # ------------------------------------------------------------------ slab <-> module views
+    def _view(self, slab, off, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        return slab[off:off + n].view(*shape)
+
+    def _build_slots(self):
+        m, cfg = self.model, self.cfg
+        L = cfg.n_layers
+        for l, conv in enumerate(m.graph_convs):
+            f, c = conv.number_input_features, conv.out_channel
+            fp = (f + 3) // 4 * 4
+            w_off, b_off, g_off, be_off = self.offsets[4 * l:4 * l + 4]
+            wp = self._view(self.params, w_off, (11, 2 * fp, c))
+            gp = self._view(self.grads, w_off, (11, 2 * fp, c))
+            for k in range(21):
+                if k == 20:
+                    d, r0 = 0, 0
+                elif k % 2 == 0:
+                    d, r0 = k // 2 + 1, fp      # neighbour weight of degree d
+                else:
+                    d, r0 = (k - 1) // 2 + 1, 0  # self weight of degree d
+                self._slots.append((conv.W_list[k], wp[d, r0:r0 + f, :], gp[d, r0:r0 + f, :]))
+            bp = self._view(self.params, b_off, (21, c))
+            bg = self._view(self.grads, b_off, (21, c))
+            for k in range(21):
+                self._slots.append((conv.b_list[k], bp[k], bg[k]))
+            if cfg.batch_norm:
+                self._add_bn(m.batch_norms[l], g_off, be_off, self.bn_offsets[2 * l], self.bn_offsets[2 * l + 1], c)
+        w_off, b_off, g_off, be_off = self.offsets[4 * L:4 * L + 4]
+        d_out, d_in = m.dense.out_features, m.dense.in_features
+        self._slots.append((m.dense.weight, self._view(self.params, w_off, (d_out, d_in)),
+                            self._view(self.grads, w_off, (d_out, d_in))))
+        self._slots.append((m.dense.bias, self._view(self.params, b_off, (d_out,)),
+                            self._view(self.grads, b_off, (d_out,))))
+        if cfg.batch_norm:
+            self._add_bn(m.batch_norms[L], g_off, be_off, self.bn_offsets[2 * L], self.bn_offsets[2 * L + 1], d_out)
+        hw, hb = self.offsets[4 * L + 4], self.offsets[4 * L + 5]
+        n_out = self.head.out_features
+        self._slots.append((self.head.weight, self._view(self.params, hw, (n_out, 2 * d_out)),
+                            self._view(self.grads, hw, (n_out, 2 * d_out))))
+        self._slots.append((self.head.bias, self._view(self.params, hb, (n_out,)),
+                            self._view(self.grads, hb, (n_out,))))
+
+    def _add_bn(self, bn, g_off, b_off, m_off, v_off, c):
+        self._slots.append((bn.weight, self._view(self.params, g_off, (c,)), self._view(self.grads, g_off, (c,))))
+        self._slots.append((bn.bias, self._view(self.params, b_off, (c,)), self._view(self.grads, b_off, (c,))))
+        self._bn_slots.append((bn, "running_mean", self._view(self.bn_running, m_off, (c,))))
+        self._bn_slots.append((bn, "running_var", self._view(self.bn_running, v_off, (c,))))
+
+    def adopt(self):
+        """Copy current parameter values into the slab (where they are not already views of it) and
+        re-point ``p.data`` / ``p.grad`` / BN buffers at the slab."""
+        with torch.no_grad():
+            for p, view, gview in self._slots:
+                if p.data_ptr() != view.data_ptr() or p.data.stride() != view.stride():
+                    view.copy_(p.data.to(view.device))
+                    p.data = view
+                p.grad = gview
+            for bn, name, view in self._bn_slots:
+                buf = getattr(bn, name)
+                if buf.data_ptr() != view.data_ptr():
+                    view.copy_(buf.to(view.device))
+                    setattr(bn, name, view)
+
+    def aliased(self):
+        return all(p.data_ptr() == v.data_ptr() for p, v, _ in self._slots) and \
+            all(getattr(bn, name).data_ptr() == v.data_ptr() for bn, name, v in self._bn_slots)
+
+    # ------------------------------------------------------------------ compute
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def train_step(self, topo, x, y, w, n_samples, out=None):
+        """forward + loss + backward; gradients land in self.grads.  Returns the device loss scalar."""
+        if not self.aliased():
+            self.adopt()
+        L = _lib.lib()
+        nbytes = int(L.dcgc_gcmodel_workspace_bytes(ctypes.byref(self.cfg), topo.n_atoms, topo.n_segments))
+        ws = _ws(nbytes, self.device)
+        check(L.dcgc_gcmodel_train_step(
+            ctypes.byref(self.cfg), ctypes.byref(topology_struct(topo)), x.data_ptr(), x.stride(0),
+            y.data_ptr(), w.data_ptr() if w is not None else None, n_samples, self.params.data_ptr(),
+            self.grads.data_ptr(), self.bn_running.data_ptr() if self.n_bn else None, ws.data_ptr(), ws.numel(),
+            self.loss.data_ptr(), out.data_ptr() if out is not None else None, self._stream()))
+        return self.loss
+
+    def forward(self, topo, x, n_samples, training=False, want_probs=True):
+        """-> (out [n_samples, n_out], probs or None, fingerprint [n_segments, 2D])"""
+        if not self.aliased():
+            self.adopt()
+        L = _lib.lib()
+        cfg = self.cfg
+        nbytes = int(L.dcgc_gcmodel_workspace_bytes(ctypes.byref(cfg), topo.n_atoms, topo.n_segments))
+        ws = _ws(nbytes, self.device)
+        out = torch.empty(n_samples, cfg.n_out, dtype=torch.float32, device=self.device)
+        probs = torch.empty_like(out) if (want_probs and cfg.mode == 1) else None
+        fp = torch.empty(topo.n_segments, 2 * cfg.dense, dtype=torch.float32, device=self.device)
+        check(L.dcgc_gcmodel_forward(
+            ctypes.byref(cfg), ctypes.byref(topology_struct(topo)), x.data_ptr(), x.stride(0), n_samples,
+            self.params.data_ptr(), self.bn_running.data_ptr() if self.n_bn else None, 1 if training else 0,
+            ws.data_ptr(), ws.numel(), out.data_ptr(), probs.data_ptr() if probs is not None else None,
+            fp.data_ptr(), self._stream()))
+        return out, probs, fp
+
+    def adam_step(self, grad_scale=1.0):
+        self.step_count += 1
+        check(_lib.lib().dcgc_adam_step(self.params.data_ptr(), self.grads.data_ptr(), self.exp_avg.data_ptr(),
+                                        self.exp_avg_sq.data_ptr(), self.n_params, self.lr, self.betas[0],
+                                        self.betas[1], self.eps, self.step_count, grad_scale, self._stream()))
+
+    # kernel launches of one train step (bench.py gpu_launches bookkeeping)
+    def launches_per_step(self):
+        L = self.cfg.n_layers
+        bn = 3 if self.cfg.batch_norm else 1
+        fwd = L * (4 + (2 if self.cfg.batch_norm else 0)) + 1 + (2 if self.cfg.batch_norm else 0) + 2
+        bwd = 5 + 1 + (bn + 3) + L * (1 + bn + 3) + (L - 1) * 2
+        return fwd + bwd + 1
+
+    def state_dict(self):
+        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count}
+
+    def load_state_dict(self, sd):
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_count = int(sd["step"])

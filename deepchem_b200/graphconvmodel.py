@@ -29,6 +29,7 @@ import torch.nn.functional as F
 from . import ops
 from ._lib import ACT_NONE, ACT_RELU
 from .data import NumpyDataset, PackedDataset  # noqa: F401  (re-exported)
+from .engine import FlatEngine
 from .layers import GraphConv, GraphGather, GraphPool, gemm_mode_code
 from .mol_graphs import BatchLayout, pack_convmols
 from .synthetic import PackedMols
@@ -177,7 +178,7 @@ class GraphConvModel(object):
                  dense_layer_size=128, dropout=0.0, mode="classification", number_atom_features=75,
                  n_classes=2, batch_size=100, batch_normalize=True, uncertainty=False,
                  learning_rate=0.001, model_dir=None, device=None, gemm_mode="fp32", log_frequency=100,
-                 **kwargs):
+                 use_engine=True, **kwargs):
         args = list(args)
         if args and isinstance(args[0], (list, tuple)):
             first = list(args.pop(0))
@@ -227,6 +228,12 @@ class GraphConvModel(object):
                                                    betas=(0.9, 0.999), eps=1e-8)
         self._global_step = 0
         self._grad_slab = None
+        self._dp = False
+        # fused whole-model engine (flat parameter slab, one C call per step) when the model shape
+        # allows it; otherwise the per-layer autograd ops are used.
+        self._engine = None
+        if use_engine and FlatEngine.eligible(self.model):
+            self._engine = FlatEngine(self.model, self.device, lr=learning_rate)
         self.log_frequency = log_frequency
         self.model_dir = model_dir
         self.number_atom_features = number_atom_features
@@ -331,6 +338,8 @@ class GraphConvModel(object):
     def _train_step(self, inputs, labels, weights):
         """zero_grad, forward, loss, backward, Adam step (torch_model.py:435-443).  The reference
         never passes training=True here, so dropout stays off during fit."""
+        if self._engine is not None:
+            return self._engine_step(inputs, labels, weights)
         slab = self._grad_slab
         if slab is None:
             self._pytorch_optimizer.zero_grad(set_to_none=True)
@@ -348,12 +357,38 @@ class GraphConvModel(object):
         self._pytorch_optimizer.step()
         return loss
 
+    def _engine_step(self, inputs, labels, weights):
+        """One C call for forward + loss + backward over the flat slabs, one all-reduce of the
+        gradient slab in data parallel, one fused Adam launch."""
+        eng = self._engine
+        topo = inputs[1]._dcgc_topology
+        w = weights[0] if weights and weights[0] is not None else None
+        loss = eng.train_step(topo, inputs[0], labels[0].contiguous(), w.contiguous() if w is not None else None,
+                              int(inputs[3]))
+        scale = 1.0
+        if self._dp:
+            import torch.distributed as dist
+            from .parallel import world_size
+            if world_size() > 1:
+                dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM)
+                scale = 1.0 / world_size()
+        eng.adam_step(scale)
+        if eng.cfg.batch_norm:
+            torch._foreach_add_([bn.num_batches_tracked for bn in self.model.batch_norms], 1)
+        return loss
+
     def enable_data_parallel(self):
         """Average gradients over the default process group every step (equal per-rank batches
         and a mean loss make the averaged gradient exact).  Parameters are broadcast
         from rank 0 first so that every replica starts identical."""
         import torch.distributed as dist
         from .parallel import GradSlab, world_size
+        self._dp = True
+        if self._engine is not None:
+            if world_size() > 1:
+                dist.broadcast(self._engine.params, src=0)
+                dist.broadcast(self._engine.bn_running, src=0)
+            return self
         if world_size() > 1:
             for t in list(self.model.parameters()) + list(self.model.buffers()):
                 dist.broadcast(t.data, src=0)
@@ -434,8 +469,8 @@ class GraphConvModel(object):
         if model_dir is None:
             raise ValueError("model_dir is not set")
         os.makedirs(model_dir, exist_ok=True)
-        data = {'model_state_dict': self.model.state_dict(),
-                'optimizer_state_dict': self._pytorch_optimizer.state_dict(),
+        opt = self._engine.state_dict() if self._engine is not None else self._pytorch_optimizer.state_dict()
+        data = {'model_state_dict': self.model.state_dict(), 'optimizer_state_dict': opt,
                 'global_step': self._global_step}
         tmp = os.path.join(model_dir, 'temp_checkpoint.pt')
         torch.save(data, tmp)
@@ -455,7 +490,10 @@ class GraphConvModel(object):
             checkpoint = cps[0]
         data = torch.load(checkpoint, map_location=self.device)
         self.model.load_state_dict(data['model_state_dict'])
-        self._pytorch_optimizer.load_state_dict(data['optimizer_state_dict'])
+        if self._engine is not None and 'exp_avg' in data['optimizer_state_dict']:
+            self._engine.load_state_dict(data['optimizer_state_dict'])
+        elif self._engine is None:
+            self._pytorch_optimizer.load_state_dict(data['optimizer_state_dict'])
         self._global_step = data['global_step']
 
     def get_global_step(self):

@@ -356,8 +356,8 @@ class GraphGatherFn(torch.autograd.Function):
                              % (topo.n_segments, n_segments))
         out = torch.empty(n_segments, 2 * d, device=x.device, dtype=torch.float32)
         argrow = torch.empty(n_segments, d, device=x.device, dtype=torch.int32) if x.requires_grad else None
-        check(_lib.lib().dcgc_gather_fwd(_p(x), _ld(x), _p(topo.mol_ptr), _p(topo.mol_atoms), n_segments, d,
-                                         act, _p(out), 2 * d, _p(argrow), _stream()))
+        check(_lib.lib().dcgc_gather_fwd(_p(x), _ld(x), None, None, _p(topo.mol_ptr), _p(topo.mol_atoms),
+                                         n_segments, d, act, _p(out), 2 * d, _p(argrow), _stream()))
         _count()
         ctx.topo, ctx.act, ctx.shape = topo, act, (n, d)
         ctx.save_for_backward(out, argrow)

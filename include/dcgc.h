@@ -142,10 +142,12 @@ int dcgc_pool_bwd(const float* dy_dev, int64_t ld_dy, const uint8_t* arg_dev, in
 /* K4 — GraphGather forward (layers.py:6464-6479; pytorch_utils.py:20-74, 473-528):
  * out[g, 0:D] = act(sum_{i in mol g} x[i,:]), out[g, D:2D] = act(max_{i in mol g} x[i,:]),
  * empty segment -> sum 0, max -inf (tanh -> -1).  argrow_dev (int32 [n_seg, D], may be null)
- * receives the lowest row index attaining the max (-1 for empty segments). */
-int dcgc_gather_fwd(const float* x_dev, int64_t ld_x, const int32_t* mol_ptr_dev,
-                    const int32_t* mol_atoms_dev, int64_t n_segments, int32_t width, int32_t act,
-                    float* out_dev, int64_t ld_out, int32_t* argrow_dev, void* stream);
+ * receives the lowest row index attaining the max (-1 for empty segments).  A non-null
+ * scale/shift applies the per-channel affine x*scale[c] + shift[c] (folded BatchNorm) on load. */
+int dcgc_gather_fwd(const float* x_dev, int64_t ld_x, const float* scale_dev, const float* shift_dev,
+                    const int32_t* mol_ptr_dev, const int32_t* mol_atoms_dev, int64_t n_segments,
+                    int32_t width, int32_t act, float* out_dev, int64_t ld_out, int32_t* argrow_dev,
+                    void* stream);
 /* K7 — GraphGather backward: dx[i,c] = dsum[m,c] + [argrow[m,c]==i]*dmax[m,c] with m =
  * membership[i] and d* = dout * act'(out) (act' from the saved output). */
 int dcgc_gather_bwd(const float* dout_dev, int64_t ld_dout, const float* out_dev, int64_t ld_out,
@@ -178,6 +180,94 @@ int dcgc_group_gemm_wgrad(int32_t mode, const float* a1_dev, int64_t ld_a1, int3
                           int64_t ld_g, int32_t n, const int64_t* deg_count_host, int32_t n_groups,
                           float* dw_dev, float* dbias_dev, void* workspace_dev,
                           int64_t workspace_bytes, void* stream);
+
+/* nn.Linear-layout variants (weight [n_out, k_in] as torch stores it): the atom-level Dense of the
+ * model (graphconvmodel.py:172,222) and the DMPNN W_i / W_h / W_o (layers.py:1510-1517).
+ *   fwd   y = act(x . w^T + bias)          dgrad  dx = g . w
+ *   wgrad dw[n,k] = g^T . x, dbias[n] = column sums of g   (deterministic, same workspace rule) */
+int dcgc_linear_fwd(int32_t mode, const float* x_dev, int64_t ld_x, int32_t k, const float* w_dev,
+                    const float* bias_dev, int32_t n, int64_t n_rows, int32_t act, float* y_dev,
+                    int64_t ld_y, void* stream);
+int dcgc_linear_dgrad(int32_t mode, const float* g_dev, int64_t ld_g, int32_t n, const float* w_dev,
+                      int32_t k, int64_t n_rows, float* dx_dev, int64_t ld_dx, void* stream);
+int64_t dcgc_linear_wgrad_workspace(int32_t k, int32_t n);
+int dcgc_linear_wgrad(int32_t mode, const float* x_dev, int64_t ld_x, int32_t k, const float* g_dev,
+                      int64_t ld_g, int32_t n, int64_t n_rows, float* dw_dev, float* dbias_dev,
+                      void* workspace_dev, int64_t workspace_bytes, void* stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Whole-model engine: GraphConvModel forward / loss / backward in one call over flat slabs.
+ * Replaces the per-step Python of TorchModel.fit_generator (torch_model.py:428-443) +
+ * _GraphConvTorchModel.forward (graphconvmodel.py:188-249) + autograd.  Layer widths and the
+ * dense width must be multiples of 4; x must be zero-padded to a leading dimension that is a
+ * multiple of 4.
+ *
+ * Parameter slab (fp32, offsets from dcgc_gcmodel_layout, every tensor 16-byte aligned):
+ *   per conv layer l: W [11, 2*Fp_l, C_l]  (group d: rows 0:F self weight W_list[2(d-1)+1], rows
+ *                       Fp:Fp+F neighbour weight W_list[2(d-1)]; group 0: W_list[20]; pad rows 0),
+ *                     b [21, C_l] (reference order), BN gamma [C_l], beta [C_l]
+ *   dense: W [D, C_L] (nn.Linear layout), b [D], BN gamma [D], beta [D]
+ *   head:  W [n_out, 2D], b [n_out]
+ * The gradient slab has the same layout.  bn_running holds (running_mean, running_var) per BN.
+ * ------------------------------------------------------------------------------------------ */
+#define DCGC_MODEL_MAX_LAYERS 8
+
+typedef struct dcgc_topology {
+  int64_t n_atoms, n_edges, n_segments, n_tiles;
+  int64_t deg_count[DCGC_N_DEG]; /* host copy of N_d */
+  const int32_t* row_ptr;
+  const int32_t* col_idx;
+  const int32_t* t_row_ptr;
+  const int32_t* t_src;
+  const int32_t* t_slot;
+  const int32_t* mol_ptr;
+  const int32_t* mol_atoms;
+  const int32_t* membership;
+  const int32_t* tiles; /* device pointers into the uploaded layout slab */
+} dcgc_topology;
+
+typedef struct dcgc_gcmodel_config {
+  int32_t n_layers;
+  int32_t n_feat;                        /* atom feature width (75) */
+  int32_t widths[DCGC_MODEL_MAX_LAYERS]; /* graph_conv_layers */
+  int32_t dense;                         /* dense_layer_size */
+  int32_t n_out;                         /* n_tasks (regression) or n_tasks * n_classes */
+  int32_t n_classes;
+  int32_t mode;                          /* 0 regression (L2), 1 classification (softmax CE) */
+  int32_t batch_norm;
+  int32_t gemm_mode;                     /* DCGC_GEMM_* */
+  float bn_eps;                          /* 1e-3 */
+  float bn_momentum;                     /* 0.99: weight of the NEW statistic (torch convention) */
+} dcgc_gcmodel_config;
+
+/* param_offsets: 4 per conv layer (W, b, gamma, beta), then dense (W, b, gamma, beta), then head
+ * (W, b); -1 where batch_norm is off.  bn_offsets: (mean, var) per BN, conv layers then dense. */
+int dcgc_gcmodel_layout(const dcgc_gcmodel_config* cfg, int64_t* param_offsets, int64_t* bn_offsets,
+                        int64_t* n_params, int64_t* n_bn);
+int64_t dcgc_gcmodel_workspace_bytes(const dcgc_gcmodel_config* cfg, int64_t n_atoms,
+                                     int64_t n_segments);
+/* Inference / plain forward.  training != 0: batch statistics (running stats updated if
+ * bn_running != NULL); training == 0: running statistics.  out [n_samples, n_out] (logits in
+ * classification mode), probs (optional, classification), fingerprint [n_segments, 2D] (optional,
+ * untrimmed as in the reference). */
+int dcgc_gcmodel_forward(const dcgc_gcmodel_config* cfg, const dcgc_topology* topo, const float* x_dev,
+                         int64_t ld_x, int64_t n_samples, const float* params_dev, float* bn_running_dev,
+                         int32_t training, void* workspace_dev, int64_t workspace_bytes, float* out_dev,
+                         float* probs_dev, float* fingerprint_dev, void* stream);
+/* One training forward + loss + backward.  y: [n_samples, n_tasks] (regression) or one-hot
+ * [n_samples, n_tasks, n_classes]; w: [n_samples, n_tasks] (may be NULL = ones).  loss_dev receives
+ * the scalar loss (mean over n_samples * n_tasks elements); every gradient is written (not
+ * accumulated) into grads_dev. */
+int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcgc_topology* topo, const float* x_dev,
+                            int64_t ld_x, const float* y_dev, const float* w_dev, int64_t n_samples,
+                            const float* params_dev, float* grads_dev, float* bn_running_dev,
+                            void* workspace_dev, int64_t workspace_bytes, float* loss_dev,
+                            float* out_dev, void* stream);
+/* Fused Adam over a flat slab, torch.optim.Adam semantics (models/optimizers.py:190-241);
+ * grads are multiplied by grad_scale first (1/world_size after a summing all-reduce). */
+int dcgc_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                   int64_t n, float lr, float beta1, float beta2, float eps, int64_t step,
+                   float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

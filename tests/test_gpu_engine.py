@@ -1,0 +1,163 @@
+"""The fused whole-model engine (dcgc_gcmodel_*) against the CPU oracle: loss, every gradient,
+BatchNorm running statistics, Adam trajectory, eval-mode forward."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import oracle_batch, rel_err, torch_args
+from oracle import graphconv_torch as O
+
+pytestmark = pytest.mark.gpu
+MODEL_TOL = 1e-4     # composite tolerance, see tests/test_gpu_parity.py
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def _pair(mode, layers, dense, n_tasks, bsz, bn=True, seed=5):
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    torch.manual_seed(seed)
+    om = O.OracleGraphConvModel(n_tasks, layers, dense, mode=mode, batch_size=bsz, batch_normalize=bn)
+    with torch.no_grad():
+        for p in om.parameters():
+            if p.dim() == 1:
+                p.add_(torch.randn_like(p) * 0.1)
+    m = GraphConvModel(n_tasks, graph_conv_layers=layers, dense_layer_size=dense, mode=mode, batch_size=bsz,
+                       batch_normalize=bn)
+    assert m._engine is not None
+    m.model.load_state_dict(om.state_dict())
+    assert m._engine.aliased()
+    return om, m
+
+
+def _oracle_step(om, mode, pm, y_onehot_or_y, w, n):
+    _, mm = oracle_batch(pm.to_list())
+    om.train()
+    oo = om(torch_args(mm, n))
+    lo = O.standard_loss(mode, oo, torch.from_numpy(y_onehot_or_y), torch.from_numpy(w))
+    return oo, lo
+
+
+@pytest.mark.parametrize("mode,layers,bn,shape", [("regression", [64, 64], True, "stress"),
+                                                  ("classification", [128, 128, 128], True, "zinc"),
+                                                  ("regression", [32, 64], False, "stress"),
+                                                  ("classification", [64], True, "delaney")])
+def test_engine_train_step_matches_oracle(mode, layers, bn, shape):
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.synthetic import make_labels, make_molecules
+    _cuda()
+    n_tasks, dense, bsz = 3, 128, 72
+    pm = make_molecules(70, seed=11, shape=shape)
+    y, w = make_labels(pm.n_mols, n_tasks, mode, seed=2, missing=0.25)
+    om, m = _pair(mode, layers, dense, n_tasks, bsz, bn)
+    batch = next(m.default_generator(PackedDataset(pm, y, w), deterministic=True, pad_batches=False))
+    inputs, labels, weights = m._prepare_batch(batch)
+    eng = m._engine
+    out = torch.empty(pm.n_mols, eng.cfg.n_out, device=m.device)
+    loss = eng.train_step(inputs[1]._dcgc_topology, inputs[0], labels[0], weights[0], pm.n_mols, out=out)
+    oo, lo = _oracle_step(om, mode, pm, batch[1][0], w, pm.n_mols)
+    lo.backward()
+    ref_out = oo[1] if mode == "classification" else oo[0]
+    assert rel_err(out.cpu().numpy().reshape(ref_out.shape), ref_out.detach().numpy()) < MODEL_TOL
+    assert abs(float(loss) - float(lo.detach())) < 1e-5 * max(1.0, abs(float(lo.detach())))
+    og = dict(om.named_parameters())
+    for name, p in m.model.named_parameters():
+        ref = og[name].grad
+        ref = torch.zeros_like(og[name]) if ref is None else ref
+        scale = max(float(ref.abs().max()), 1e-6)
+        assert float((p.grad.cpu() - ref).abs().max()) < 2 * MODEL_TOL * scale + 1e-9, name
+    for (k, v), (_, vo) in zip(m.model.state_dict().items(), om.state_dict().items()):
+        if "running" in k:
+            assert rel_err(v.cpu().numpy(), vo.numpy()) < MODEL_TOL, k
+
+
+def test_engine_gradients_equal_autograd_path():
+    """Two CUDA evaluations of the same math (fused engine vs per-layer autograd ops)."""
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.synthetic import make_labels, make_molecules
+    _cuda()
+    pm = make_molecules(200, seed=12, shape="zinc")
+    y, w = make_labels(200, 2, "regression", seed=3)
+    om, m = _pair("regression", [64, 128], 128, 2, 200)
+    batch = next(m.default_generator(PackedDataset(pm, y, w), deterministic=True))
+    inputs, labels, weights = m._prepare_batch(batch)
+    sd = {k: v.clone() for k, v in m.model.state_dict().items()}
+    loss_e = float(m._engine.train_step(inputs[1]._dcgc_topology, inputs[0], labels[0], weights[0], 200))
+    g_engine = {n: p.grad.clone() for n, p in m.model.named_parameters()}
+    m.model.load_state_dict(sd)                       # undo the running-stat update
+    m._engine.grads.zero_()
+    m.model.train()
+    outs = m.model(inputs)
+    loss_a = m._loss_fn([outs[0]], labels, weights)
+    loss_a.backward()
+    assert abs(loss_e - float(loss_a)) < 1e-6 * max(1.0, abs(loss_e))
+    for n, p in m.model.named_parameters():
+        scale = max(float(g_engine[n].abs().max()), 1e-6)
+        assert float((p.grad - g_engine[n]).abs().max()) < 5e-5 * scale + 1e-9, n
+
+
+def test_engine_adam_trajectory_matches_torch_adam():
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.synthetic import make_labels, make_molecules
+    _cuda()
+    pm = make_molecules(64, seed=13, shape="delaney")
+    y, w = make_labels(64, 1, "regression", seed=4)
+    om, m = _pair("regression", [32, 32], 64, 1, 64, bn=False)
+    opt = torch.optim.Adam(om.parameters(), lr=1e-3, betas=(0.9, 0.999), eps=1e-8)
+    ds = PackedDataset(pm, y, w)
+    for step in range(5):
+        loss = m.fit_on_batch(pm, y, w)
+        opt.zero_grad()
+        oo, lo = _oracle_step(om, "regression", pm, y, w, 64)
+        lo.backward()
+        opt.step()
+        assert abs(loss - float(lo.detach())) < 2e-5 * max(1.0, abs(float(lo.detach()))), step
+    osd = om.state_dict()
+    for k, v in m.model.state_dict().items():
+        assert rel_err(v.cpu().numpy(), osd[k].numpy()) < 2e-4, k
+    assert m.get_global_step() == 5 and m._engine.step_count == 5
+    del ds
+
+
+def test_engine_eval_forward_and_predict():
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.synthetic import make_molecules
+    _cuda()
+    pm = make_molecules(50, seed=14, shape="stress")
+    om, m = _pair("classification", [64, 64], 128, 4, 64)
+    with torch.no_grad():                                  # non-trivial running statistics
+        for bn in om.batch_norms:
+            bn.running_mean.normal_(0, 0.2)
+            bn.running_var.uniform_(0.5, 1.5)
+    m.model.load_state_dict(om.state_dict())
+    batch = next(m.default_generator(PackedDataset(pm, n_tasks=4), mode="predict", deterministic=True,
+                                     pad_batches=False))
+    inputs, _, _ = m._prepare_batch(batch)
+    out, probs, fp = m._engine.forward(inputs[1]._dcgc_topology, inputs[0], 50, training=False)
+    _, mm = oracle_batch(pm.to_list())
+    om.eval()
+    oo = om(torch_args(mm, 50))
+    assert rel_err(probs.cpu().numpy().reshape(50, 4, 2), oo[0].detach().numpy()) < MODEL_TOL
+    assert rel_err(out.cpu().numpy().reshape(50, 4, 2), oo[1].detach().numpy()) < MODEL_TOL
+    assert rel_err(fp.cpu().numpy(), oo[2].detach().numpy()) < MODEL_TOL
+    assert np.all(fp.cpu().numpy()[50:, :128] == 0) and np.all(fp.cpu().numpy()[50:, 128:] == -1)
+
+
+def test_state_dict_survives_flat_slab():
+    """Parameters are views of one slab; checkpoints keep the reference keys and reload exactly."""
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    _cuda()
+    m = GraphConvModel(12, [64, 64], 128, mode="classification", batch_size=50)
+    sd = m.model.state_dict()
+    assert sum(1 for _ in sd) == 103                        # 103 tensors for the default model
+    assert sum(v.numel() for k, v in sd.items() if "running" not in k and "num_batches" not in k) == 204504
+    assert sd["graph_convs.0.W_list.3"].shape == (75, 64) and sd["dense.weight"].shape == (128, 64)
+    m2 = GraphConvModel(12, [64, 64], 128, mode="classification", batch_size=50)
+    m2.model.load_state_dict(sd)
+    assert m2._engine.aliased()
+    assert torch.equal(m2._engine.params, m._engine.params)
+    m2.model.to("cuda:0")
+    m2._engine.adopt()
+    assert m2._engine.aliased()
