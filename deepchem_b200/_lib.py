@@ -62,6 +62,9 @@ _SIGNATURES = {
     "dcgc_last_error": (c_char_p, []),
     "dcgc_version": (c_int32, []),
     "dcgc_device_ok": (c_int32, []),
+    "dcgc_launch_count": (c_int64, []),
+    "dcgc_profile_begin": (c_int32, [c_char_p]),
+    "dcgc_profile_end": (c_int32, [POINTER(ctypes.c_double), POINTER(c_int64)]),
     "dcgc_layout_plan": (c_int32, [c_int64, _P, _P, c_int64, c_int32, POINTER(LayoutInfo)]),
     "dcgc_layout_build": (c_int32, [c_int64, _P, _P, _P, POINTER(LayoutInfo), _P]),
     "dcgc_layout_permute_features_host": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, c_int64, c_int32]),

@@ -18,8 +18,19 @@ void dcgc_set_error(const char* fmt, ...);
 
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
+
+#include <atomic>
+extern std::atomic<long long> g_dcgc_launches;
+// RAII: if profiling of entry point `name` is on, brackets the enclosed launches with CUDA events
+struct DcgcProfScope {
+  DcgcProfScope(const char* name, cudaStream_t st);
+  ~DcgcProfScope();
+  cudaEvent_t e1_;
+  cudaStream_t st_;
+};
 #define DCGC_CUDA_LAUNCH_CHECK(what)                                        \
   do {                                                                      \
+    g_dcgc_launches.fetch_add(1, std::memory_order_relaxed);                \
     cudaError_t e__ = cudaGetLastError();                                   \
     if (e__ != cudaSuccess) {                                               \
       dcgc_set_error("%s: %s", what, cudaGetErrorString(e__));              \

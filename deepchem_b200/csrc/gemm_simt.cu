@@ -378,6 +378,7 @@ extern "C" int dcgc_group_gemm_fwd(int32_t mode, const float* a1, int64_t ld_a1,
   DCGC_CHECK_ARG(tiles == nullptr || tile_rows == BM, "dcgc_group_gemm_fwd: tile_rows must be %d", BM);
   if (n_rows == 0 || n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(a1 && w && y, "dcgc_group_gemm_fwd: null pointer");
+  DcgcProfScope prof_scope("dcgc_group_gemm_fwd", (cudaStream_t)stream);
   GemmArgs p{};
   p.a1 = a1; p.ld_a1 = ld_a1; p.k1 = k1;
   p.a2 = a2; p.ld_a2 = ld_a2; p.k2 = a2 ? k2 : 0;
@@ -416,6 +417,7 @@ extern "C" int dcgc_group_gemm_dgrad(int32_t mode, const float* g, int64_t ld_g,
   DCGC_CHECK_ARG(tiles == nullptr || tile_rows == BM, "dcgc_group_gemm_dgrad: tile_rows must be %d", BM);
   if (n_rows == 0 || k1 + k2 == 0 || (!d1 && !d2)) return DCGC_OK;
   DCGC_CHECK_ARG(g && w, "dcgc_group_gemm_dgrad: null pointer");
+  DcgcProfScope prof_scope("dcgc_group_gemm_dgrad", (cudaStream_t)stream);
   GemmArgs p{};
   p.a1 = g; p.ld_a1 = ld_g; p.k1 = n;
   p.a2 = nullptr; p.ld_a2 = 0; p.k2 = 0;
@@ -502,6 +504,7 @@ static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, 
   p.a1_vec = ld_a1 % 4 == 0 && aligned16(a1);
   p.a2_vec = a2 && ld_a2 % 4 == 0 && aligned16(a2);
   p.g_vec = ld_g % 4 == 0 && aligned16(g);
+  DcgcProfScope prof_scope("dcgc_group_gemm_wgrad", (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   if (chunks > 0) {
     const int tiles_m = (Kt + BM - 1) / BM;

@@ -320,6 +320,7 @@ extern "C" int dcgc_gather_sum(const float* x, int64_t ld_x, const int32_t* row_
                      (addend == nullptr || ld_add >= width), "dcgc_gather_sum: bad sizes");
   if (n_rows_out == 0 || width == 0) return DCGC_OK;
   DCGC_CHECK_ARG(x && row_ptr && out, "dcgc_gather_sum: null pointer");
+  DcgcProfScope prof_scope("dcgc_gather_sum", (cudaStream_t)stream);
   const bool v4 = width % 4 == 0 && ld_x % 4 == 0 && ld_out % 4 == 0 && aligned16(x) && aligned16(out) &&
                   (addend == nullptr || (ld_add % 4 == 0 && aligned16(addend)));
   if (v4) {
@@ -343,6 +344,7 @@ extern "C" int dcgc_pool_fwd(const float* x, int64_t ld_x, const float* scale, c
   DCGC_CHECK_ARG(arg == nullptr || ld_arg >= width, "dcgc_pool_fwd: ld_arg smaller than width");
   if (n_rows == 0 || width == 0) return DCGC_OK;
   DCGC_CHECK_ARG(x && row_ptr && out, "dcgc_pool_fwd: null pointer");
+  DcgcProfScope prof_scope("dcgc_pool_fwd", (cudaStream_t)stream);
   const bool v4 = width % 4 == 0 && ld_x % 4 == 0 && ld_out % 4 == 0 && aligned16(x) && aligned16(out) &&
                   (arg == nullptr || (ld_arg % 4 == 0 && (reinterpret_cast<uintptr_t>(arg) & 3) == 0));
   const int groups = v4 ? width / 4 : width;
@@ -371,6 +373,7 @@ extern "C" int dcgc_pool_bwd(const float* dy, int64_t ld_dy, const uint8_t* arg,
                  "dcgc_pool_bwd: bad sizes");
   if (n_rows == 0 || width == 0) return DCGC_OK;
   DCGC_CHECK_ARG(dy && arg && t_row_ptr && dx, "dcgc_pool_bwd: null pointer");
+  DcgcProfScope prof_scope("dcgc_pool_bwd", (cudaStream_t)stream);
   const bool v4 = width % 4 == 0 && ld_dy % 4 == 0 && ld_dx % 4 == 0 && ld_arg % 4 == 0 && aligned16(dy) &&
                   aligned16(dx) && (reinterpret_cast<uintptr_t>(arg) & 3) == 0;
   const int groups = v4 ? width / 4 : width;
@@ -396,6 +399,7 @@ extern "C" int dcgc_gather_fwd(const float* x, int64_t ld_x, const float* scale,
   DCGC_CHECK_ARG(act >= DCGC_ACT_NONE && act <= DCGC_ACT_TANH, "dcgc_gather_fwd: unknown activation %d", act);
   if (n_segments == 0 || width == 0) return DCGC_OK;
   DCGC_CHECK_ARG(x && mol_ptr && out, "dcgc_gather_fwd: null pointer");
+  DcgcProfScope prof_scope("dcgc_gather_fwd", (cudaStream_t)stream);
   const bool v4 = width % 4 == 0 && ld_x % 4 == 0 && aligned16(x);
   const int groups = v4 ? width / 4 : width;
   const unsigned grid = grid_for(n_segments * groups);
@@ -418,6 +422,7 @@ extern "C" int dcgc_gather_bwd(const float* dout, int64_t ld_dout, const float* 
   DCGC_CHECK_ARG(act >= DCGC_ACT_NONE && act <= DCGC_ACT_TANH, "dcgc_gather_bwd: unknown activation %d", act);
   if (n_rows == 0 || width == 0) return DCGC_OK;
   DCGC_CHECK_ARG(dout && out && argrow && membership && dx, "dcgc_gather_bwd: null pointer");
+  DcgcProfScope prof_scope("dcgc_gather_bwd", (cudaStream_t)stream);
   const int groups = (width + 3) / 4;
   gather_bwd_kernel<4><<<grid_for(n_rows * groups), kThreads, 0, (cudaStream_t)stream>>>(
       dout, ld_dout, out, ld_out, argrow, membership, n_rows, groups, width, act, dx, ld_dx);

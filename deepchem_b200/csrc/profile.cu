@@ -1,0 +1,62 @@
+// Launch accounting and per-entry-point CUDA-event timing (bench.py: gpu_launches and the live
+// roofline measurement).  Events are recorded on the stream the kernel is launched on.
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+#include "common.h"
+
+std::atomic<long long> g_dcgc_launches{0};
+
+namespace {
+std::mutex g_mu;
+char g_name[64] = "";
+std::atomic<int> g_on{0};
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+}  // namespace
+
+DcgcProfScope::DcgcProfScope(const char* name, cudaStream_t st) : e1_(nullptr), st_(st) {
+  if (!g_on.load(std::memory_order_relaxed)) return;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (strcmp(name, g_name) != 0) return;
+  cudaEvent_t e0;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1_) != cudaSuccess) { e1_ = nullptr; return; }
+  cudaEventRecord(e0, st);
+  g_events.emplace_back(e0, e1_);
+}
+
+DcgcProfScope::~DcgcProfScope() {
+  if (e1_) cudaEventRecord(e1_, st_);
+}
+
+extern "C" long long dcgc_launch_count(void) { return g_dcgc_launches.load(); }
+
+extern "C" int dcgc_profile_begin(const char* entry_name) {
+  DCGC_CHECK_ARG(entry_name && strlen(entry_name) < sizeof(g_name), "dcgc_profile_begin: bad name");
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& ev : g_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  g_events.clear();
+  strcpy(g_name, entry_name);
+  g_on.store(1);
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_profile_end(double* total_ms, long long* launches) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_on.store(0);
+  double ms = 0.0;
+  for (auto& ev : g_events) {
+    float t = 0.f;
+    DCGC_CUDA_CALL(cudaEventSynchronize(ev.second));
+    DCGC_CUDA_CALL(cudaEventElapsedTime(&t, ev.first, ev.second));
+    ms += t;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = (long long)g_events.size();
+  for (auto& ev : g_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  g_events.clear();
+  g_name[0] = 0;
+  return DCGC_OK;
+}

@@ -164,6 +164,64 @@ class BatchInputs(list):
     packed_features = None
 
 
+class _Prefetcher(object):
+    """Runs ``model._prepare_batch`` for upcoming batches on a helper thread and a side CUDA stream;
+    the consumer's stream waits on an event before touching a prepared batch."""
+
+    def __init__(self, model, generator, depth=2):
+        import queue
+        import threading
+        self.model, self.generator = model, generator
+        self.q = queue.Queue(maxsize=max(1, depth))
+        self.stream = torch.cuda.Stream(device=model.device)
+        self.error = None
+        self.stop = False
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        try:
+            torch.cuda.set_device(self.model.device)
+            for batch in self.generator:
+                if self.stop:
+                    break
+                with torch.cuda.stream(self.stream):
+                    prepared = self.model._prepare_batch(batch)
+                    ev = torch.cuda.Event()
+                    ev.record(self.stream)
+                self.q.put((prepared, ev))
+        except BaseException as e:      # surfaced in the consumer
+            self.error = e
+        finally:
+            self.q.put(None)
+
+    def __iter__(self):
+        try:
+            while True:
+                item = self.q.get()
+                if item is None:
+                    break
+                prepared, ev = item
+                main = torch.cuda.current_stream()
+                main.wait_event(ev)
+                inputs, labels, weights = prepared
+                topo = inputs[1]._dcgc_topology
+                for t in [topo.buffer, inputs[0]._base if inputs[0]._base is not None else inputs[0]] + \
+                        [t for t in list(labels) + list(weights) if t is not None]:
+                    t.record_stream(main)
+                yield prepared
+            if self.error is not None:
+                raise self.error
+        finally:
+            self.stop = True
+            while self.thread.is_alive():       # unblock a producer stuck on a full queue
+                try:
+                    self.q.get_nowait()
+                except Exception:
+                    pass
+                self.thread.join(timeout=0.05)
+
+
 class GraphConvModel(object):
     """Graph convolutional model on the B200 path.
 
@@ -296,18 +354,24 @@ class GraphConvModel(object):
             all_losses=all_losses)
 
     def fit_generator(self, generator, max_checkpoints_to_keep=5, checkpoint_interval=1000, restore=False,
-                      callbacks=[], all_losses=None):
+                      callbacks=[], all_losses=None, prefetch=2):
+        """Train on (inputs, labels, weights) batches (torch_model.py:345-496).  With ``prefetch`` > 0
+        the host side of the next batches (C++ layout build, H2D copies on a side stream, device
+        permutation) runs in a helper thread while the GPU works on the current one — the role the
+        reference gives to DiskDataset's shard-prefetch thread (data/datasets.py:1670-1693)."""
         if not isinstance(callbacks, SequenceCollection):
             callbacks = [callbacks]
         self.model.train()
         avg_loss = torch.zeros((), device=self.device)
         last_avg_loss, averaged_batches = 0.0, 0
         t0 = time.time()
-        for batch in generator:
+        prepared_iter = _Prefetcher(self, generator, prefetch) if prefetch else \
+            (self._prepare_batch(b) for b in generator)
+        for prepared in prepared_iter:
             if restore:
                 self.restore()
                 restore = False
-            batch_loss = self._train_step(*self._prepare_batch(batch))
+            batch_loss = self._train_step(*prepared)
             self._global_step += 1
             step = self._global_step
             avg_loss = avg_loss + batch_loss.detach()

@@ -205,8 +205,9 @@ class BatchLayout(object):
         return np.empty(nbytes, dtype=np.uint8), None
 
     @staticmethod
-    def build(packed, n_segments=None, pinned=False):
-        """Run the C++ builder on a PackedMols shard (replaces agglomerate_mols)."""
+    def build(packed, n_segments=None, pinned=False, staging=None):
+        """Run the C++ builder on a PackedMols shard (replaces agglomerate_mols).  ``staging``: an
+        optional reusable pinned torch uint8 tensor to build into (grown by the caller)."""
         L = _lib.lib()
         n_mols = packed.n_mols
         if n_segments is None:
@@ -214,7 +215,10 @@ class BatchLayout(object):
         info = _lib.LayoutInfo()
         _lib.check(L.dcgc_layout_plan(n_mols, _ptr(packed.atom_ptr), _ptr(packed.adj_ptr), n_segments,
                                       _lib.TILE_ROWS, ctypes.byref(info)))
-        slab, t = BatchLayout._alloc(int(info.slab_bytes), pinned)
+        if staging is not None and staging.numel() >= int(info.slab_bytes):
+            slab, t = staging.numpy()[:int(info.slab_bytes)], staging
+        else:
+            slab, t = BatchLayout._alloc(int(info.slab_bytes), pinned)
         _lib.check(L.dcgc_layout_build(n_mols, _ptr(packed.atom_ptr), _ptr(packed.adj_ptr),
                                        _ptr(packed.adj_idx), ctypes.byref(info), _ptr(slab)))
         return BatchLayout(info, slab, t)

@@ -72,55 +72,28 @@ def padded_empty(n_rows, width, device, dtype=torch.float32):
 
 
 # ------------------------------------------------------------------------------------------
-# launch accounting (bench.py: gpu_launches, per-kernel CUDA-event timing for the roofline)
+# launch accounting (bench.py: gpu_launches, per-entry-point CUDA-event timing for the roofline);
+# both live inside the library so that launches made by the fused engine are seen too.
 # ------------------------------------------------------------------------------------------
-_launches = 0
-_prof = None
-
-
 def launch_count():
     """Number of libdcgc kernels launched by this process so far."""
-    return _launches
-
-
-def _count(n=1):
-    global _launches
-    _launches += n
+    return int(_lib.lib().dcgc_launch_count())
 
 
 def profile_begin(name):
-    """Bracket every launch of the entry point `name` with CUDA events on the launching stream."""
-    global _prof
-    _prof = {"name": name, "events": []}
+    """Bracket every call of the C entry point `name` with CUDA events on its launching stream."""
+    check(_lib.lib().dcgc_profile_begin(name.encode()))
 
 
 def profile_end():
-    """-> {'launches', 'ms' (sum of event durations), 'bytes' (sum of algorithmic bytes)}"""
-    global _prof
-    prof, _prof = _prof, None
-    if prof is None:
-        return None
-    torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b, _ in prof["events"])
-    return {"name": prof["name"], "launches": len(prof["events"]), "ms": ms,
-            "bytes": sum(nb for _, _, nb in prof["events"])}
+    """-> {'ms': summed event durations, 'launches': bracketed calls}"""
+    ms, n = ctypes.c_double(), ctypes.c_int64()
+    check(_lib.lib().dcgc_profile_end(ctypes.byref(ms), ctypes.byref(n)))
+    return {"ms": ms.value, "launches": n.value}
 
 
-class _Timed(object):
-    def __init__(self, name, nbytes):
-        self.on = _prof is not None and _prof["name"] == name
-        self.nbytes = nbytes
-
-    def __enter__(self):
-        if self.on:
-            self.e0 = torch.cuda.Event(enable_timing=True)
-            self.e1 = torch.cuda.Event(enable_timing=True)
-            self.e0.record()
-
-    def __exit__(self, *exc):
-        if self.on:
-            self.e1.record()
-            _prof["events"].append((self.e0, self.e1, self.nbytes))
+def _count(n=1):
+    pass
 
 
 # ------------------------------------------------------------------------------------------
@@ -131,14 +104,9 @@ def gather_sum(x, row_ptr, idx, n_rows_out, addend=None, out=None):
     width = x.shape[1]
     if out is None:
         out = addend if addend is not None else padded_empty(n_rows_out, width, x.device)
-    # algorithmic bytes: read x once, write out once, read the index list
-    # (+ the addend when the self-path gradient is fused in)
-    nbytes = (2 + (addend is not None)) * n_rows_out * width * 4 + idx.numel() * 4
-    with _Timed("dcgc_gather_sum", nbytes):
-        check(_lib.lib().dcgc_gather_sum(_p(x), _ld(x), _p(row_ptr), _p(idx), n_rows_out, width,
-                                         _p(addend), _ld(addend) if addend is not None else 0,
-                                         _p(out), _ld(out), _stream()))
-    _count()
+    check(_lib.lib().dcgc_gather_sum(_p(x), _ld(x), _p(row_ptr), _p(idx), n_rows_out, width,
+                                     _p(addend), _ld(addend) if addend is not None else 0,
+                                     _p(out), _ld(out), _stream()))
     return out
 
 

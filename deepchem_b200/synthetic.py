@@ -25,13 +25,14 @@ class PackedMols(object):
     features [N,F] float32
     """
 
-    __slots__ = ("atom_ptr", "adj_ptr", "adj_idx", "features")
+    __slots__ = ("atom_ptr", "adj_ptr", "adj_idx", "features", "_pin")
 
     def __init__(self, atom_ptr, adj_ptr, adj_idx, features):
         self.atom_ptr = np.ascontiguousarray(atom_ptr, dtype=np.int32)
         self.adj_ptr = np.ascontiguousarray(adj_ptr, dtype=np.int32)
         self.adj_idx = np.ascontiguousarray(adj_idx, dtype=np.int32)
         self.features = np.ascontiguousarray(features, dtype=np.float32)
+        self._pin = None
 
     @property
     def n_mols(self):
@@ -58,11 +59,32 @@ class PackedMols(object):
         return [self.mol(i) for i in range(self.n_mols)]
 
     def slice(self, lo, hi):
-        """Molecules [lo, hi) as a new PackedMols (copies)."""
+        """Molecules [lo, hi) as a new PackedMols.  The feature rows and neighbour ids are VIEWS
+        of this shard (a contiguous molecule range is a contiguous row range), so a pinned shard
+        yields pinned batches with no host copy; only the two small offset arrays are rebased."""
+        if lo == 0 and hi == self.n_mols:
+            return self
         a0, a1 = int(self.atom_ptr[lo]), int(self.atom_ptr[hi])
         e0, e1 = int(self.adj_ptr[a0]), int(self.adj_ptr[a1])
-        return PackedMols(self.atom_ptr[lo:hi + 1] - a0, self.adj_ptr[a0:a1 + 1] - e0,
-                          self.adj_idx[e0:e1], self.features[a0:a1])
+        out = PackedMols.__new__(PackedMols)
+        out.atom_ptr = self.atom_ptr[lo:hi + 1] - np.int32(a0)
+        out.adj_ptr = self.adj_ptr[a0:a1 + 1] - np.int32(e0)
+        out.adj_idx = self.adj_idx[e0:e1]
+        out.features = self.features[a0:a1]
+        out._pin = getattr(self, "_pin", None)
+        return out
+
+    def pin_memory(self):
+        """Move the feature matrix into page-locked host memory (needs torch + CUDA) so that H2D
+        copies of batches are asynchronous DMA with no staging copy."""
+        import torch
+        if getattr(self, "_pin", None) is not None:
+            return self
+        t = torch.empty(self.features.shape, dtype=torch.float32, pin_memory=True)
+        t.numpy()[...] = self.features
+        self.features = t.numpy()
+        self._pin = t
+        return self
 
     def take(self, idx):
         """Molecules idx[0], idx[1], ... (repeats allowed) as a new PackedMols."""
@@ -76,6 +98,20 @@ class PackedMols(object):
         adj = np.concatenate([self.adj_idx[self.adj_ptr[r]:self.adj_ptr[r + 1]] for r in rows]) \
             if rows.size else np.zeros(0, np.int32)
         return PackedMols(atom_ptr, adj_ptr, adj, self.features[rows])
+
+    @staticmethod
+    def concat(shards):
+        """Concatenate shards into one."""
+        atom_ptr, adj_ptr = [np.zeros(1, np.int64)], [np.zeros(1, np.int64)]
+        a_off = e_off = 0
+        for s in shards:
+            atom_ptr.append(s.atom_ptr[1:].astype(np.int64) + a_off)
+            adj_ptr.append(s.adj_ptr[1:].astype(np.int64) + e_off)
+            a_off += s.n_atoms
+            e_off += int(s.adj_ptr[-1])
+        return PackedMols(np.concatenate(atom_ptr), np.concatenate(adj_ptr),
+                          np.concatenate([s.adj_idx for s in shards]),
+                          np.concatenate([s.features for s in shards]))
 
     @staticmethod
     def from_list(mols, n_feat=None):

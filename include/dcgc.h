@@ -48,6 +48,15 @@ int dcgc_version(void);
 /* 1 if a CUDA device with compute capability 10.x is visible, 0 if not, <0 on error */
 int dcgc_device_ok(void);
 
+/* Launch accounting and live per-entry-point timing (used by bench.py): dcgc_launch_count()
+ * returns the number of kernels this library has launched in the process; between
+ * dcgc_profile_begin("dcgc_gather_sum") and dcgc_profile_end() every launch made by that entry
+ * point is bracketed by CUDA events on its own stream; _end synchronises them and returns the
+ * summed duration and the number of bracketed calls. */
+long long dcgc_launch_count(void);
+int dcgc_profile_begin(const char* entry_name);
+int dcgc_profile_end(double* total_ms, long long* launches);
+
 /* --------------------------------------------------------------------------------------------
  * Host layout builder.  Replaces ConvMol.agglomerate_mols (deepchem/feat/mol_graphs.py:256-349)
  * and the per-molecule degree sort of ConvMol.__init__ (mol_graphs.py:113-185): the composite of
