@@ -267,7 +267,7 @@ def run_ours(args):
         ds = PackedDataset(big, np.concatenate([y for _, y, _ in pool]), np.concatenate([w for _, _, w in pool]))
         model.log_frequency = 1                                # loss read back to the host every step
         losses = []
-        warm = itertools.islice(model.default_generator(ds, epochs=1000, deterministic=True), 3)
+        warm = itertools.islice(model.default_generator(ds, epochs=1000, deterministic=True), 12)
         model.fit_generator(warm, checkpoint_interval=0, all_losses=losses)
         barrier()
         gen = itertools.islice(model.default_generator(ds, epochs=1000, deterministic=True), K)
@@ -276,7 +276,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         ms2 = max_over_ranks((time.perf_counter() - t0) * 1e3)
         barrier()
-        assert len(losses) == K + 3
+        assert len(losses) == K + 12
         e2e = {"value": world * B * K / (ms2 * 1e-3), "unit": "molecules/s", "ms_per_step": ms2 / K,
                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                "api": "GraphConvModel.fit_generator(default_generator(PackedDataset)) with log_frequency=1: "

@@ -173,7 +173,11 @@ class _Prefetcher(object):
         import threading
         self.model, self.generator = model, generator
         self.q = queue.Queue(maxsize=max(1, depth))
-        self.stream = torch.cuda.Stream(device=model.device)
+        # one side stream per model: the caching allocator pools blocks per stream, so a fresh
+        # stream per fit() call would pay cudaMalloc again for every staging tensor
+        if model._prefetch_stream is None:
+            model._prefetch_stream = torch.cuda.Stream(device=model.device)
+        self.stream = model._prefetch_stream
         self.error = None
         self.stop = False
         self.thread = threading.Thread(target=self._run, daemon=True)
@@ -287,6 +291,9 @@ class GraphConvModel(object):
         self._global_step = 0
         self._grad_slab = None
         self._dp = False
+        self._prefetch_stream = None
+        self._staging = []          # ring of reusable pinned slabs: [tensor, event]
+        self._staging_next = 0
         # fused whole-model engine (flat parameter slab, one C call per step) when the model shape
         # allows it; otherwise the per-layer autograd ops are used.
         self._engine = None
@@ -308,10 +315,35 @@ class GraphConvModel(object):
                     -1, self.n_tasks, self.n_classes)
             yield (self.batch_inputs(X_b), [y_b], [w_b])
 
+    def _staging_slab(self, nbytes):
+        """Next pinned staging buffer of the ring (page-locked allocations are expensive, so they are
+        made once and reused; a slot is reused only after the H2D copy that read it has finished)."""
+        ring = 6
+        if len(self._staging) < ring:
+            self._staging.append([torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True), None])
+            slot = self._staging[-1]
+        else:
+            slot = self._staging[self._staging_next % ring]
+            self._staging_next += 1
+            if slot[1] is not None:
+                slot[1].synchronize()
+            if slot[0].numel() < nbytes:
+                slot[0] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+        return slot
+
     def batch_inputs(self, X_b, pinned=True):
         packed = X_b if isinstance(X_b, PackedMols) else pack_convmols(X_b)
         n_seg = max(self.batch_size, packed.n_mols)
-        layout = BatchLayout.build(packed, n_segments=n_seg, pinned=pinned)
+        slot = None
+        if pinned and torch.cuda.is_available():
+            # upper bound of the slab size without running the planner: 11 int32 arrays over atoms /
+            # edges / segments plus alignment
+            need = 4 * (5 * (packed.n_atoms + 2) + 3 * int(packed.adj_ptr[-1]) + (n_seg + 2)
+                        + 4 * (packed.n_atoms // 128 + 12)) + 256 * 16
+            slot = self._staging_slab(need)
+        layout = BatchLayout.build(packed, n_segments=n_seg, pinned=pinned,
+                                   staging=slot[0] if slot is not None else None)
+        layout._staging_slot = slot
         inputs = BatchInputs([None, layout.deg_slice, layout.membership, np.array(packed.n_mols)]
                              + layout.deg_adjacency_lists()[1:])
         inputs.layout = layout
@@ -326,6 +358,10 @@ class GraphConvModel(object):
         if getattr(inputs, "layout", None) is None:
             raise TypeError("inputs must come from GraphConvModel.default_generator / batch_inputs")
         topo = inputs.layout.to_device(self.device)
+        slot = getattr(inputs.layout, "_staging_slot", None)
+        if slot is not None:
+            slot[1] = torch.cuda.Event()
+            slot[1].record(torch.cuda.current_stream())
         feats = torch.from_numpy(np.ascontiguousarray(inputs.packed_features, dtype=np.float32))
         feats = feats.to(self.device, non_blocking=True)
         x = ops.permute_rows(feats, topo.perm)
