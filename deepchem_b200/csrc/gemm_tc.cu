@@ -1,0 +1,402 @@
+// tcgen05 (5th-gen tensor core) degree-grouped GEMMs with TMEM accumulators for sm_100a.
+//
+// Arithmetic: DCGC_GEMM_TF32X3 — every fp32 operand is split into tf32 hi + lo parts and three
+// kind::tf32 MMAs (hi*hi + hi*lo + lo*hi) are accumulated in fp32 in TMEM: ~2^-21 relative error per
+// product, i.e. fp32-grade results (the 1e-5 parity mode on tensor cores).  DCGC_GEMM_BF16 (not built
+// yet) is the same pipeline with one kind::f16 MMA.
+//
+// Pipeline of one CTA (one 128-row tile of one degree bucket x one 128-column tile):
+//   * 8 producer warps in two groups that take alternate K chunks: LDG.128 of the fp32 operands
+//     ([X | S] concatenated along K for the forward, G for dgrad; weights pre-split and pre-transposed
+//     by tc_prep_weights), hi/lo split in registers, STS.128 into the canonical K-major SWIZZLE_128B
+//     layout, fence.proxy.async, mbarrier arrive;
+//   * 1 MMA warp: one lane waits on the "full" mbarrier of a stage, issues 4 K-steps x 3 tcgen05.mma
+//     (M=128, N=128, K=8) and tcgen05.commit's the stage's "empty" mbarrier; after the last chunk it
+//     commits the "accumulator ready" mbarrier;
+//   * epilogue (producer warps 0-3, which own TMEM lanes 32w..32w+31): tcgen05.ld 32 columns at a
+//     time, bias + activation, transpose through shared memory, 512-byte coalesced row stores.
+// 3 stages x (A hi, A lo, B hi, B lo) x 16 KB = 192 KB of shared memory, 128 TMEM columns.
+#include "common.h"
+
+namespace {
+
+constexpr int TC_BM = 128;        // rows per tile (UMMA M)
+constexpr int TC_BN = 128;        // columns per tile (UMMA N)
+constexpr int TC_BK = 32;         // fp32 elements per K chunk = one 128-byte swizzle row
+constexpr int TC_UK = 8;          // tf32 UMMA K
+constexpr int TC_STAGES = 3;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KB
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;         // A hi, A lo, B hi, B lo
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_GROUP_THREADS = 128;                     // one producer group
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1) * 32;  // + MMA warp
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 + 256;
+constexpr int TC_EPI_LD = TC_BN + 4;                      // padded row of the epilogue staging tile
+
+struct TcArgs {
+  const float* a1; int64_t ld_a1; int k1;
+  const float* a2; int64_t ld_a2; int k2;
+  const float* bhi; const float* blo;   // [G][n_pad][k_pad], K contiguous, zero padded
+  int64_t b_group_stride; int k_pad;
+  const float* bias; int64_t bias_group_stride;
+  int n1, n2;
+  float* c1; int64_t ld_c1;
+  float* c2; int64_t ld_c2;
+  const int32_t* tiles; int64_t n_rows;
+  int act;
+  int a1_vec, a2_vec, c1_vec, c2_vec;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  // bounded spin: a protocol bug traps instead of hanging the GPU
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t tmem, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(cols));
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::tf32, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                                ((uint32_t)(TC_BM >> 4) << 24);
+
+__device__ __forceinline__ float tf32_hi(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+  hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+}
+// byte offset of 16-byte chunk `c` (0..7) of row `r` (0..127) inside a [128 x 32 fp32] swizzled tile
+__device__ __forceinline__ uint32_t swz(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ float4 ld4_masked(const float* p, int valid, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid >= 4 && vec) return __ldg(reinterpret_cast<const float4*>(p));
+  if (valid > 0) v.x = __ldg(p);
+  if (valid > 1) v.y = __ldg(p + 1);
+  if (valid > 2) v.z = __ldg(p + 2);
+  if (valid > 3) v.w = __ldg(p + 3);
+  return v;
+}
+__device__ __forceinline__ float tc_act(float v, int act) {
+  if (act == DCGC_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == DCGC_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// weight preparation: dst_hi/lo[g][n][k] (k contiguous, zero padded) from
+//   TRANS=1: src[g][k][n]   (forward: W[g] is [K, N])      K split as [k1 | pad | k2 | pad]
+//   TRANS=0: src[g][n][k]   (dgrad: rows of W[g] are the outputs, its columns the contraction)
+// ------------------------------------------------------------------------------------------
+struct PrepArgs {
+  const float* src; int64_t src_group_stride;
+  float* hi; float* lo; int64_t dst_group_stride;
+  int n, n_pad, k1, k2, k1_pad, k_pad, trans, src_ld;
+  int n1, n1_pad;  // TRANS=0: destination row j maps to source row (j < n1_pad ? j : n1 + j - n1_pad)
+};
+__global__ void __launch_bounds__(256) tc_prep_weights(const PrepArgs p) {
+  const int g = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (int64_t)p.n_pad * p.k_pad) return;
+  const int nn = (int)(i / p.k_pad), kk = (int)(i - (int64_t)nn * p.k_pad);
+  float v = 0.f;
+  if (p.trans) {
+    int ks = -1;
+    if (kk < p.k1_pad) { if (kk < p.k1) ks = kk; }
+    else if (kk - p.k1_pad < p.k2) ks = p.k1 + (kk - p.k1_pad);
+    if (nn < p.n && ks >= 0) v = __ldg(p.src + g * p.src_group_stride + (int64_t)ks * p.src_ld + nn);
+  } else {
+    int js = -1;
+    if (nn < p.n1_pad) { if (nn < p.n1) js = nn; }
+    else if (p.n1 + (nn - p.n1_pad) < p.n) js = p.n1 + (nn - p.n1_pad);
+    if (js >= 0 && kk < p.k1) v = __ldg(p.src + g * p.src_group_stride + (int64_t)js * p.src_ld + kk);
+  }
+  const float h = tf32_hi(v);
+  p.hi[g * p.dst_group_stride + i] = h;
+  p.lo[g * p.dst_group_stride + i] = v - h;
+}
+
+// ------------------------------------------------------------------------------------------
+// the GEMM kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // stage tiles need 1024-byte alignment
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_base = base + TC_STAGES * TC_STAGE_BYTES;
+  // barriers: full[s] at +8*s, empty[s] at +8*(3+s), accumulator-ready at +48, tmem pointer at +64
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TC_STAGES * TC_STAGE_BYTES + 64);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int row0, rows, g;
+  if (p.tiles) {
+    const int4 t = __ldg(reinterpret_cast<const int4*>(p.tiles) + blockIdx.x);
+    row0 = t.x; rows = t.y; g = t.z;
+  } else {
+    row0 = blockIdx.x * TC_BM;
+    rows = (int)min((int64_t)TC_BM, p.n_rows - row0);
+    g = 0;
+  }
+  const int n0 = blockIdx.y * TC_BN;
+  const int N = p.n1 + p.n2;
+  const int chunks1 = (p.k1 + TC_BK - 1) / TC_BK, chunks2 = (p.k2 + TC_BK - 1) / TC_BK;
+  const int total = chunks1 + chunks2;
+
+  if (tid == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(bar_base + 8 * s, TC_GROUP_THREADS);
+      mbar_init(bar_base + 8 * (TC_STAGES + s), 1);
+    }
+    mbar_init(bar_base + 48, 1);
+    fence_barrier_init();
+  }
+  if (warp == TC_PRODUCER_WARPS) tmem_alloc(bar_base + 64, TC_BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < TC_PRODUCER_WARPS) {
+    // ===== producers: group = warp / 4 takes chunks ch = group, group + 2, ... =====
+    const int group = warp >> 2, gt = tid & (TC_GROUP_THREADS - 1);
+    const float* bhi = p.bhi + (int64_t)g * p.b_group_stride + (int64_t)n0 * p.k_pad;
+    const float* blo = p.blo + (int64_t)g * p.b_group_stride + (int64_t)n0 * p.k_pad;
+    for (int ch = group; ch < total; ch += 2) {
+      const int s = ch % TC_STAGES, use = ch / TC_STAGES;
+      const float* src; int64_t ld; int ksrc, kbase; bool vec;
+      if (ch < chunks1) { src = p.a1; ld = p.ld_a1; ksrc = p.k1; kbase = ch * TC_BK; vec = p.a1_vec; }
+      else { src = p.a2; ld = p.ld_a2; ksrc = p.k2; kbase = (ch - chunks1) * TC_BK; vec = p.a2_vec; }
+      // issue every global load of this chunk first (8 A + 16 B float4 per thread in flight)
+      float4 ra[8], rh[8], rl[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int f = gt + it * TC_GROUP_THREADS, r = f >> 3, k = kbase + 4 * (f & 7);
+        ra[it] = r < rows ? ld4_masked(src + (int64_t)(row0 + r) * ld + k, ksrc - k, vec)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int f = gt + it * TC_GROUP_THREADS, r = f >> 3, c = f & 7;
+        const int64_t o = (int64_t)r * p.k_pad + (int64_t)ch * TC_BK + 4 * c;
+        rh[it] = __ldg(reinterpret_cast<const float4*>(bhi + o));
+        rl[it] = __ldg(reinterpret_cast<const float4*>(blo + o));
+      }
+      mbar_wait(bar_base + 8 * (TC_STAGES + s), (use & 1) ^ 1);   // stage free?
+      uint8_t* st = sm + s * TC_STAGE_BYTES;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int f = gt + it * TC_GROUP_THREADS;
+        const uint32_t o = swz(f >> 3, f & 7);
+        float4 hi, lo;
+        split4(ra[it], hi, lo);
+        *reinterpret_cast<float4*>(st + o) = hi;
+        *reinterpret_cast<float4*>(st + TC_TILE_BYTES + o) = lo;
+        *reinterpret_cast<float4*>(st + 2 * TC_TILE_BYTES + o) = rh[it];
+        *reinterpret_cast<float4*>(st + 3 * TC_TILE_BYTES + o) = rl[it];
+      }
+      fence_proxy_async();               // generic-proxy writes -> visible to the tensor core
+      mbar_arrive(bar_base + 8 * s);
+    }
+  } else if (lane == 0) {
+    // ===== MMA issuer (one thread) =====
+    for (int ch = 0; ch < total; ++ch) {
+      const int s = ch % TC_STAGES, use = ch / TC_STAGES;
+      mbar_wait(bar_base + 8 * s, use & 1);
+      tc_fence_after();
+      const uint32_t sa = base + s * TC_STAGE_BYTES;
+#pragma unroll
+      for (int k = 0; k < TC_BK / TC_UK; ++k) {
+        const uint32_t ko = k * TC_UK * 4;
+        const uint64_t ahi = make_desc(sa + ko), alo = make_desc(sa + TC_TILE_BYTES + ko);
+        const uint64_t bhi = make_desc(sa + 2 * TC_TILE_BYTES + ko), blo = make_desc(sa + 3 * TC_TILE_BYTES + ko);
+        umma_tf32(tmem, alo, bhi, kIdescTf32, (ch | k) != 0);
+        umma_tf32(tmem, ahi, blo, kIdescTf32, 1);
+        umma_tf32(tmem, ahi, bhi, kIdescTf32, 1);
+      }
+      umma_commit(bar_base + 8 * (TC_STAGES + s));   // frees the stage when these MMAs retire
+    }
+    umma_commit(bar_base + 48);                       // accumulator complete
+  }
+
+  // ===== epilogue: warps 0-3 own TMEM lanes [32*warp, 32*warp+32) =====
+  if (warp < 4) {
+    if (total > 0) {
+      mbar_wait(bar_base + 48, 0);
+      tc_fence_after();
+    }
+    float* stage = reinterpret_cast<float*>(sm) + warp * 32 * TC_EPI_LD;   // reuses the pipeline stages
+    const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_group_stride : nullptr;
+#pragma unroll 1
+    for (int cb = 0; cb < TC_BN; cb += 32) {
+      uint32_t v[32];
+      if (total > 0) {
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        float o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = n0 + cb + i + e;
+          float t = __uint_as_float(v[i + e]);
+          if (bias && c < N) t += __ldg(bias + c);
+          o[e] = tc_act(t, p.act);
+        }
+        *reinterpret_cast<float4*>(stage + lane * TC_EPI_LD + cb + i) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    __syncwarp();
+    // coalesced stores: one row (128 columns = 32 lanes x float4) per iteration
+    const int c = n0 + 4 * lane;
+    for (int r = 0; r < 32; ++r) {
+      const int row = warp * 32 + r;
+      if (row >= rows) break;
+      const int64_t grow = row0 + row;
+      const float4 o = *reinterpret_cast<const float4*>(stage + r * TC_EPI_LD + 4 * lane);
+      if (c + 3 < p.n1 && p.c1_vec) {
+        *reinterpret_cast<float4*>(p.c1 + grow * p.ld_c1 + c) = o;
+      } else if (c >= p.n1 && c + 3 < N && p.c2_vec && ((c - p.n1) & 3) == 0) {
+        *reinterpret_cast<float4*>(p.c2 + grow * p.ld_c2 + (c - p.n1)) = o;
+      } else {
+        const float e[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cc = c + q;
+          if (cc < p.n1) { if (p.c1) p.c1[grow * p.ld_c1 + cc] = e[q]; }
+          else if (cc < N) { if (p.c2) p.c2[grow * p.ld_c2 + (cc - p.n1)] = e[q]; }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_PRODUCER_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TC_BN);
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int ensure_smem_attr() {
+  static bool done = false;   // per process; the attribute is per function per device context
+  if (!done) {
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    done = true;
+  }
+  return DCGC_OK;
+}
+
+}  // namespace
+
+// Called by dcgc_group_gemm_fwd / _dgrad / dcgc_linear_* when mode == DCGC_GEMM_TF32X3.
+//   trans_w = 1: w is [G][k1+k2][n] (forward);  trans_w = 0: w is [G][n1+n2][k1] (dgrad / nn.Linear forward)
+int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_t ld_a2, int k2, const float* w,
+                 int n_groups, int trans_w, const float* bias, int n1, int n2, const int32_t* tiles, int64_t n_tiles,
+                 int64_t n_rows, int act, float* c1, int64_t ld_c1, float* c2, int64_t ld_c2, cudaStream_t st) {
+  const int N = n1 + n2;
+  const int64_t row_tiles = tiles ? n_tiles : (n_rows + TC_BM - 1) / TC_BM;
+  if (row_tiles == 0 || N == 0) return DCGC_OK;
+  int st_ = ensure_smem_attr();
+  if (st_ != DCGC_OK) return st_;
+  const int k1_pad = (k1 + TC_BK - 1) / TC_BK * TC_BK, k2_pad = (k2 + TC_BK - 1) / TC_BK * TC_BK;
+  const int k_pad = k1_pad + k2_pad;
+  // output column space: [0, n1) -> c1, [n1, n1+n2) -> c2 (contiguous: the kernel's epilogue maps them)
+  const int n_pad = (N + TC_BN - 1) / TC_BN * TC_BN;
+  const int64_t gstride = (int64_t)n_pad * k_pad;
+  float* prep = nullptr;
+  DCGC_CUDA_CALL(cudaMallocAsync((void**)&prep, (size_t)2 * n_groups * gstride * sizeof(float), st));
+  PrepArgs q{};
+  q.src = w; q.hi = prep; q.lo = prep + (int64_t)n_groups * gstride; q.dst_group_stride = gstride;
+  q.n = N; q.n_pad = n_pad; q.k1 = k1; q.k2 = k2; q.k1_pad = k1_pad; q.k_pad = k_pad; q.trans = trans_w;
+  if (trans_w) { q.src_ld = N; q.src_group_stride = (int64_t)(k1 + k2) * N; q.n1 = N; q.n1_pad = n_pad; }
+  else { q.src_ld = k1; q.src_group_stride = (int64_t)N * k1; q.n1 = N; q.n1_pad = n_pad; }
+  {
+    dim3 grid((unsigned)((gstride + 255) / 256), (unsigned)n_groups);
+    tc_prep_weights<<<grid, 256, 0, st>>>(q);
+    DCGC_CUDA_LAUNCH_CHECK("tc_prep_weights");
+  }
+  TcArgs p{};
+  p.a1 = a1; p.ld_a1 = ld_a1; p.k1 = k1;
+  p.a2 = a2; p.ld_a2 = ld_a2; p.k2 = a2 ? k2 : 0;
+  p.bhi = q.hi; p.blo = q.lo; p.b_group_stride = gstride; p.k_pad = k_pad;
+  p.bias = bias; p.bias_group_stride = N;
+  p.n1 = n1; p.n2 = n2; p.c1 = c1; p.ld_c1 = ld_c1; p.c2 = c2; p.ld_c2 = ld_c2;
+  p.tiles = tiles; p.n_rows = n_rows; p.act = act;
+  p.a1_vec = ld_a1 % 4 == 0 && aligned16(a1);
+  p.a2_vec = a2 && ld_a2 % 4 == 0 && aligned16(a2);
+  p.c1_vec = c1 && ld_c1 % 4 == 0 && aligned16(c1);
+  p.c2_vec = c2 && ld_c2 % 4 == 0 && aligned16(c2);
+  dim3 grid((unsigned)row_tiles, (unsigned)(n_pad / TC_BN));
+  tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
+  DCGC_CUDA_LAUNCH_CHECK("tc_gemm_kernel");
+  DCGC_CUDA_CALL(cudaFreeAsync(prep, st));
+  return DCGC_OK;
+}

@@ -1,0 +1,104 @@
+"""tcgen05 (TF32x3) GEMM path against the fp32 SIMT path and a float64 reference: the tensor-core
+mode must stay within the fp32 parity tolerance (1e-5 of the tensor scale)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda", 0)
+
+
+def _topo(n_mols=300, seed=3, shape="stress"):
+    from deepchem_b200 import mol_graphs as MG
+    from deepchem_b200.synthetic import make_molecules
+    pm = make_molecules(n_mols, seed=seed, shape=shape)
+    return MG.BatchLayout.build(pm).to_device(_cuda())
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+
+@pytest.mark.parametrize("k,c,act", [(128, 128, 1), (76, 128, 0), (64, 64, 1), (128, 256, 0), (75, 100, 2)])
+def test_tc_group_gemm_forward(k, c, act):
+    from deepchem_b200 import ops, _lib
+    dev = _cuda()
+    topo = _topo()
+    n = topo.n_atoms
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(n, k, device=dev, generator=g)
+    s = torch.randn(n, k, device=dev, generator=g)
+    w = torch.randn(11, 2 * k, c, device=dev, generator=g) / np.sqrt(2 * k)
+    b = torch.randn(11, c, device=dev, generator=g)
+    y_tc = ops.group_gemm_fwd(x, s, w, b, topo, act, _lib.GEMM_TF32X3)
+    y_32 = ops.group_gemm_fwd(x, s, w, b, topo, act, _lib.GEMM_FP32)
+    deg = torch.repeat_interleave(torch.arange(11, device=dev), torch.tensor(topo.deg_count, device=dev))
+    a = torch.cat([x, s], 1).double()
+    ref = torch.bmm(a.unsqueeze(1), w.double()[deg]).squeeze(1) + b.double()[deg]
+    ref = torch.relu(ref) if act == 1 else (torch.tanh(ref) if act == 2 else ref)
+    assert _rel(y_32, ref) < TOL
+    assert _rel(y_tc, ref) < TOL, _rel(y_tc, ref)
+
+
+@pytest.mark.parametrize("k,c", [(128, 128), (64, 128), (128, 64)])
+def test_tc_group_gemm_dgrad(k, c):
+    from deepchem_b200 import ops, _lib
+    dev = _cuda()
+    topo = _topo(seed=4)
+    n = topo.n_atoms
+    g = torch.Generator(device=dev).manual_seed(2)
+    go = torch.randn(n, c, device=dev, generator=g)
+    w = torch.randn(11, 2 * k, c, device=dev, generator=g) / np.sqrt(c)
+    d1, d2 = ops.group_gemm_dgrad(go, w, k, k, topo, True, True, _lib.GEMM_TF32X3)
+    deg = torch.repeat_interleave(torch.arange(11, device=dev), torch.tensor(topo.deg_count, device=dev))
+    ref = torch.bmm(go.double().unsqueeze(1), w.double()[deg].transpose(1, 2)).squeeze(1)
+    assert _rel(d1, ref[:, :k]) < TOL and _rel(d2, ref[:, k:]) < TOL
+    only2 = ops.group_gemm_dgrad(go, w, k, k, topo, False, True, _lib.GEMM_TF32X3)
+    assert only2[0] is None and torch.equal(only2[1], d2)
+
+
+def test_tc_linear_forward_ragged_rows():
+    from deepchem_b200 import _lib, ops
+    import ctypes
+    dev = _cuda()
+    g = torch.Generator(device=dev).manual_seed(3)
+    for n_rows in (1, 127, 128, 1000):
+        x = torch.randn(n_rows, 128, device=dev, generator=g)
+        w = torch.randn(96, 128, device=dev, generator=g) / 11.0
+        b = torch.randn(96, device=dev, generator=g)
+        y = torch.empty(n_rows, 96, device=dev)
+        _lib.check(_lib.lib().dcgc_linear_fwd(_lib.GEMM_TF32X3, x.data_ptr(), 128, 128, w.data_ptr(), b.data_ptr(), 96,
+                                              n_rows, 1, y.data_ptr(), 96,
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ref = torch.relu(x.double() @ w.double().t() + b.double())
+        assert _rel(y, ref) < TOL, n_rows
+
+
+def test_tc_model_engine_matches_fp32_engine():
+    """Whole train step with gemm_mode='tf32x3' against gemm_mode='fp32' (same parameters)."""
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    from deepchem_b200.synthetic import make_labels, make_molecules
+    _cuda()
+    pm = make_molecules(500, seed=5, shape="zinc")
+    y, w = make_labels(500, 2, "regression", seed=1)
+    torch.manual_seed(0)
+    m32 = GraphConvModel(2, [128, 128], 128, mode="regression", batch_size=500, gemm_mode="fp32")
+    mtc = GraphConvModel(2, [128, 128], 128, mode="regression", batch_size=500, gemm_mode="tf32x3")
+    mtc.model.load_state_dict(m32.model.state_dict())
+    res = []
+    for m in (m32, mtc):
+        batch = next(m.default_generator(PackedDataset(pm, y, w), deterministic=True))
+        inputs, labels, weights = m._prepare_batch(batch)
+        loss = float(m._engine.train_step(inputs[1]._dcgc_topology, inputs[0], labels[0], weights[0], 500))
+        res.append((loss, m._engine.grads.clone()))
+    assert abs(res[0][0] - res[1][0]) < 1e-5 * abs(res[0][0])
+    for (name, p32), (_, ptc) in zip(m32.model.named_parameters(), mtc.model.named_parameters()):
+        scale = max(float(p32.grad.abs().max()), 1e-8)
+        assert float((p32.grad - ptc.grad).abs().max()) < 1e-4 * scale, name
