@@ -26,40 +26,74 @@ inline unsigned blocks_for(int64_t n, int t = kT) { return (unsigned)((n + t - 1
 // ------------------------------------------------------------------------------------------
 // column moments: out_a[c] = sum_r a[r,c], out_ab[c] = sum_r a[r,c]*b[r,c]   (float64, 2 stages)
 // ------------------------------------------------------------------------------------------
-constexpr int kMomRows = 512;  // rows per stage-1 block
+constexpr int kMomRows = 256;   // rows per stage-1 block
+constexpr int kMomLanes = 16;   // row lanes per block (x 32 float4 column lanes = 512 threads)
 
-__global__ void __launch_bounds__(256)
+// block: 32 column lanes (float4 -> 128 columns) x 16 row lanes; every thread owns 16 rows of its
+// chunk, 8 independent 128-bit loads in flight; fp32 partials over <= 16 rows, float64 from there on.
+__global__ void __launch_bounds__(32 * kMomLanes)
 col_moments_partial(const float* __restrict__ a, int64_t ld_a, const float* __restrict__ b, int64_t ld_b,
                     int64_t n_rows, int width, double* __restrict__ part) {
-  // block: 128 column lanes x 2 row lanes; grid: (row chunks, column tiles of 128)
-  const int cx = threadIdx.x & 127, ry = threadIdx.x >> 7;
-  const int c = blockIdx.y * 128 + cx;
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.y * 128 + 4 * cx;
   const int64_t r0 = (int64_t)blockIdx.x * kMomRows;
   const int64_t r1 = min(n_rows, r0 + kMomRows);
-  float sa = 0.f, sab = 0.f;
-  double da = 0.0, dab = 0.0;
+  double da[4] = {0, 0, 0, 0}, dab[4] = {0, 0, 0, 0};
   if (c < width) {
-    int cnt = 0;
-    for (int64_t r = r0 + ry; r < r1; r += 2) {
-      const float va = __ldg(a + r * ld_a + c);
-      const float vb = __ldg(b + r * ld_b + c);
-      sa += va;
-      sab = fmaf(va, vb, sab);
-      if (++cnt == 32) {  // flush the fp32 running sums into float64 every 32 rows
-        da += sa; dab += sab; sa = 0.f; sab = 0.f; cnt = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float4 va[8], vb[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t r = r0 + ry + (int64_t)(half * 8 + u) * kMomLanes;
+        if (r < r1) {
+          va[u] = __ldg(reinterpret_cast<const float4*>(a + r * ld_a + c));
+          vb[u] = (b == a) ? va[u] : __ldg(reinterpret_cast<const float4*>(b + r * ld_b + c));
+        } else {
+          va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          vb[u] = va[u];
+        }
       }
+      float sa[4] = {0, 0, 0, 0}, sab[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        sa[0] += va[u].x; sa[1] += va[u].y; sa[2] += va[u].z; sa[3] += va[u].w;
+        sab[0] = fmaf(va[u].x, vb[u].x, sab[0]); sab[1] = fmaf(va[u].y, vb[u].y, sab[1]);
+        sab[2] = fmaf(va[u].z, vb[u].z, sab[2]); sab[3] = fmaf(va[u].w, vb[u].w, sab[3]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { da[e] += sa[e]; dab[e] += sab[e]; }
     }
-    da += sa; dab += sab;
   }
-  __shared__ double sh[2][2][128];
-  sh[0][ry][cx] = da;
-  sh[1][ry][cx] = dab;
+  __shared__ double sh[2][kMomLanes][128];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { sh[0][ry][4 * cx + e] = da[e]; sh[1][ry][4 * cx + e] = dab[e]; }
   __syncthreads();
-  if (ry == 0 && c < width) {
-    const int64_t o = ((int64_t)blockIdx.x * 2) * width + c;
-    part[o] = sh[0][0][cx] + sh[0][1][cx];
-    part[o + width] = sh[1][0][cx] + sh[1][1][cx];
+  // fixed-order reduction over the row lanes: threads 0..255 -> (quantity, column)
+  if (threadIdx.x < 256) {
+    const int q = threadIdx.x >> 7, col = threadIdx.x & 127;
+    double s = 0.0;
+#pragma unroll
+    for (int l = 0; l < kMomLanes; ++l) s += sh[q][l][col];
+    const int cc = blockIdx.y * 128 + col;
+    if (cc < width) part[((int64_t)blockIdx.x * 2 + q) * width + cc] = s;
   }
+}
+
+// sum of the stage-1 partials of one column, split over 8 lanes and combined in lane order
+__device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int n_chunks, int width, int c,
+                                                int lane8, double (*sh)[2][32], int cl, double& s, double& ss) {
+  double a = 0.0, b = 0.0;
+  for (int k = lane8; k < n_chunks; k += 8) {
+    a += part[((int64_t)k * 2) * width + c];
+    b += part[((int64_t)k * 2 + 1) * width + c];
+  }
+  sh[lane8][0][cl] = a;
+  sh[lane8][1][cl] = b;
+  __syncthreads();
+  s = 0.0; ss = 0.0;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) { s += sh[l][0][cl]; ss += sh[l][1][cl]; }
 }
 
 // BatchNorm forward finalize: batch statistics -> folded scale/shift, running-stat update.
@@ -70,13 +104,12 @@ __global__ void bn_fwd_finalize(const double* __restrict__ part, int n_chunks, i
                                 float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                 float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                 float* __restrict__ scale_out, float* __restrict__ shift_out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= width) return;
-  double s = 0.0, ss = 0.0;
-  for (int k = 0; k < n_chunks; ++k) {
-    s += part[((int64_t)k * 2) * width + c];
-    ss += part[((int64_t)k * 2 + 1) * width + c];
-  }
+  __shared__ double sh[8][2][32];
+  const int cl = threadIdx.x & 31, lane8 = threadIdx.x >> 5;
+  const int c = min(blockIdx.x * 32 + cl, width - 1);
+  double s, ss;
+  reduce_partials(part, n_chunks, width, c, lane8, sh, cl, s, ss);
+  if (lane8 != 0 || blockIdx.x * 32 + cl >= width) return;
   const double n = (double)n_rows;
   const double mean = n > 0 ? s / n : 0.0;
   double var = n > 0 ? ss / n - mean * mean : 0.0;
@@ -113,13 +146,12 @@ __global__ void bn_bwd_finalize(const double* __restrict__ part, int n_chunks, i
                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                 const float* __restrict__ scale, float* __restrict__ dgamma,
                                 float* __restrict__ dbeta, float* __restrict__ coef /* [3, width] */) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= width) return;
-  double sda = 0.0, sday = 0.0;
-  for (int k = 0; k < n_chunks; ++k) {
-    sda += part[((int64_t)k * 2) * width + c];
-    sday += part[((int64_t)k * 2 + 1) * width + c];
-  }
+  __shared__ double sh[8][2][32];
+  const int cl = threadIdx.x & 31, lane8 = threadIdx.x >> 5;
+  const int c = min(blockIdx.x * 32 + cl, width - 1);
+  double sda, sday;
+  reduce_partials(part, n_chunks, width, c, lane8, sh, cl, sda, sday);
+  if (lane8 != 0 || blockIdx.x * 32 + cl >= width) return;
   const double n = (double)n_rows;
   const double dg = (double)invstd[c] * (sday - (double)mean[c] * sda);  // sum dA * xhat
   if (dgamma) dgamma[c] = (float)dg;
@@ -443,10 +475,10 @@ int bn_forward(const dcgc_gcmodel_config* cfg, const Layout& lo, int idx, const 
   if (training) {
     if (n > 0) {
       dim3 grid((unsigned)sv.n_chunks, (unsigned)((width + 127) / 128));
-      col_moments_partial<<<grid, 256, 0, st>>>(y, ld_y, y, ld_y, n, width, sv.part);
+      col_moments_partial<<<grid, 32 * kMomLanes, 0, st>>>(y, ld_y, y, ld_y, n, width, sv.part);
       DCGC_CUDA_LAUNCH_CHECK("col_moments_partial");
     }
-    bn_fwd_finalize<<<(width + 127) / 128, 128, 0, st>>>(sv.part, n > 0 ? sv.n_chunks : 0, width, n, gamma, beta,
+    bn_fwd_finalize<<<(width + 31) / 32, 256, 0, st>>>(sv.part, n > 0 ? sv.n_chunks : 0, width, n, gamma, beta,
                                                          cfg->bn_eps, cfg->bn_momentum, rm, rv, mean, invstd, scale,
                                                          shift);
     DCGC_CUDA_LAUNCH_CHECK("bn_fwd_finalize");
@@ -688,10 +720,10 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
       const float* stats = sv.stats + sv.stats_off[idx];
       if (N > 0) {
         dim3 grid((unsigned)sv.n_chunks, (unsigned)((width + 127) / 128));
-        col_moments_partial<<<grid, 256, 0, st>>>(dA, width, yv, width, N, width, sv.part);
+        col_moments_partial<<<grid, 32 * kMomLanes, 0, st>>>(dA, width, yv, width, N, width, sv.part);
         DCGC_CUDA_LAUNCH_CHECK("col_moments_partial (bwd)");
       }
-      bn_bwd_finalize<<<(width + 127) / 128, 128, 0, st>>>(sv.part, N > 0 ? sv.n_chunks : 0, width, N, stats,
+      bn_bwd_finalize<<<(width + 31) / 32, 256, 0, st>>>(sv.part, N > 0 ? sv.n_chunks : 0, width, N, stats,
                                                            stats + width, stats + 2 * width, grads + lo.bn_g[idx],
                                                            grads + lo.bn_b[idx], coef);
       DCGC_CUDA_LAUNCH_CHECK("bn_bwd_finalize");
