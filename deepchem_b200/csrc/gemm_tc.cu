@@ -343,12 +343,235 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// v2: persistent, weight-resident kernel.  One CTA per SM keeps the (hi, lo) weight slice of its
+// column range resident in shared memory (reloaded only when the degree bucket of its tiles changes:
+// tiles are degree-sorted), streams A chunks through a small ring, double-buffers the accumulator
+// in TMEM so that the epilogue of tile i overlaps the MMAs of tile i+1, and stores straight from
+// registers (each thread owns one output row: 32 columns = one full 128-byte line per tcgen05.ld).
+//   warps 0-3  epilogue (TMEM lane quadrant = warp)      warps 4-11 producers (two groups)
+//   warp 12    MMA issuer + TMEM allocation
+// ------------------------------------------------------------------------------------------
+constexpr int V2_THREADS = 13 * 32;
+constexpr int V2_MAX_STAGES = 4;
+constexpr int V2_A_STAGE_BYTES = 2 * TC_TILE_BYTES;   // A hi + A lo
+
+struct TcArgs2 {
+  TcArgs a;
+  int n_row_tiles;   // number of 128-row tiles
+  int n_stages;      // A ring depth
+  int b_bytes;       // resident weight bytes (hi + lo) per CTA
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void tile_of(const TcArgs& p, int t, int& row0, int& rows, int& g) {
+  if (p.tiles) {
+    const int4 q = __ldg(reinterpret_cast<const int4*>(p.tiles) + t);
+    row0 = q.x; rows = q.y; g = q.z;
+  } else {
+    row0 = t * TC_BM;
+    rows = (int)min((int64_t)TC_BM, p.n_rows - row0);
+    g = 0;
+  }
+}
+
+template <int NCTA>
+__global__ void __launch_bounds__(V2_THREADS, 1) tc_gemm_kernel_v2(const TcArgs2 q) {
+  const TcArgs& p = q.a;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const int S = q.n_stages;
+  const uint32_t b_half = (uint32_t)q.b_bytes / 2;                 // hi region, then lo region
+  const uint32_t a_base = base + q.b_bytes;                        // A ring
+  const uint32_t bar_base = a_base + S * V2_A_STAGE_BYTES;
+  // barriers: full[s] +8s, empty[s] +32+8s, tmem_full[a] +64+8a, tmem_empty[a] +80+8a, tmem slot +96
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + q.b_bytes + S * V2_A_STAGE_BYTES + 96);
+  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCTA >> 3) << 17) |
+                              ((uint32_t)(TC_BM >> 4) << 24);
+  constexpr uint32_t kBChunk = NCTA * 128;                          // bytes of one [NCTA x 32] weight chunk
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int P = gridDim.x, pid = blockIdx.x;
+  const int n0 = blockIdx.y * NCTA;
+  const int N = p.n1 + p.n2;
+  const int chunks1 = (p.k1 + TC_BK - 1) / TC_BK, chunks2 = (p.k2 + TC_BK - 1) / TC_BK;
+  const int total = chunks1 + chunks2;
+  const int my_tiles = pid < q.n_row_tiles ? (q.n_row_tiles - pid + P - 1) / P : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < V2_MAX_STAGES; ++s) {
+      mbar_init(bar_base + 8 * s, TC_GROUP_THREADS);
+      mbar_init(bar_base + 32 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_base + 64 + 8 * a, 1);
+      mbar_init(bar_base + 80 + 8 * a, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 12) tmem_alloc(bar_base + 96, 2 * NCTA);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= 4 && warp < 12) {
+    // ===================== producers =====================
+    const int ptid = tid - 128, group = ptid >> 7, gt = ptid & 127;
+    int cur_g = -1, cc = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      int row0, rows, g;
+      tile_of(p, pid + it * P, row0, rows, g);
+      if (g != cur_g) {
+        // every chunk issued so far must have been consumed before the resident weights change
+        if (cc > 0) {
+          int lastc = ((cc - 1) & 1) == group ? cc - 1 : cc - 2;
+          if (lastc >= 0) mbar_wait(bar_base + 32 + 8 * (lastc % S), (lastc / S) & 1);
+        }
+        named_bar_sync(1, 256);
+        const float* bh = p.bhi + (int64_t)g * p.b_group_stride + (int64_t)n0 * p.k_pad;
+        const float* bl = p.blo + (int64_t)g * p.b_group_stride + (int64_t)n0 * p.k_pad;
+        const int per_chunk = NCTA * 8;                       // float4 per chunk
+        for (int f = ptid; f < total * per_chunk; f += 256) {
+          const int ch = f / per_chunk, w = f - ch * per_chunk, r = w >> 3, c = w & 7;
+          const int64_t o = (int64_t)r * p.k_pad + ch * TC_BK + 4 * c;
+          const uint32_t so = ch * kBChunk + swz(r, c);
+          *reinterpret_cast<float4*>(sm + so) = __ldg(reinterpret_cast<const float4*>(bh + o));
+          *reinterpret_cast<float4*>(sm + b_half + so) = __ldg(reinterpret_cast<const float4*>(bl + o));
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 256);
+        cur_g = g;
+      }
+      for (int ch = 0; ch < total; ++ch, ++cc) {
+        if ((cc & 1) != group) continue;
+        const int s = cc % S, use = cc / S;
+        const float* src; int64_t ld; int ksrc, kbase; bool vec;
+        if (ch < chunks1) { src = p.a1; ld = p.ld_a1; ksrc = p.k1; kbase = ch * TC_BK; vec = p.a1_vec; }
+        else { src = p.a2; ld = p.ld_a2; ksrc = p.k2; kbase = (ch - chunks1) * TC_BK; vec = p.a2_vec; }
+        float4 ra[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int f = gt + u * TC_GROUP_THREADS, r = f >> 3, k = kbase + 4 * (f & 7);
+          ra[u] = r < rows ? ld4_masked(src + (int64_t)(row0 + r) * ld + k, ksrc - k, vec)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        mbar_wait(bar_base + 32 + 8 * s, (use & 1) ^ 1);
+        uint8_t* st = sm + q.b_bytes + s * V2_A_STAGE_BYTES;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int f = gt + u * TC_GROUP_THREADS;
+          const uint32_t o = swz(f >> 3, f & 7);
+          float4 hi, lo;
+          split4(ra[u], hi, lo);
+          *reinterpret_cast<float4*>(st + o) = hi;
+          *reinterpret_cast<float4*>(st + TC_TILE_BYTES + o) = lo;
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_base + 8 * s);
+      }
+    }
+  } else if (warp == 12) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int cc = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int acc = it & 1;
+        mbar_wait(bar_base + 80 + 8 * acc, ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem + acc * NCTA;
+        for (int ch = 0; ch < total; ++ch, ++cc) {
+          const int s = cc % S;
+          mbar_wait(bar_base + 8 * s, (cc / S) & 1);
+          tc_fence_after();
+          const uint32_t sa = a_base + s * V2_A_STAGE_BYTES, sb = base + ch * kBChunk;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UK; ++k) {
+            const uint32_t ko = k * TC_UK * 4;
+            const uint64_t ahi = make_desc(sa + ko), alo = make_desc(sa + TC_TILE_BYTES + ko);
+            const uint64_t bhi = make_desc(sb + ko), blo = make_desc(sb + b_half + ko);
+            umma_tf32(d, alo, bhi, kIdesc, (ch | k) != 0);
+            umma_tf32(d, ahi, blo, kIdesc, 1);
+            umma_tf32(d, ahi, bhi, kIdesc, 1);
+          }
+          umma_commit(bar_base + 32 + 8 * s);
+        }
+        umma_commit(bar_base + 64 + 8 * acc);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 0-3) =====================
+    for (int it = 0; it < my_tiles; ++it) {
+      int row0, rows, g;
+      tile_of(p, pid + it * P, row0, rows, g);
+      const int acc = it & 1;
+      mbar_wait(bar_base + 64 + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+      const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_group_stride : nullptr;
+      const int row = warp * 32 + lane;
+      const int64_t grow = row0 + row;
+#pragma unroll 1
+      for (int cb = 0; cb < NCTA; cb += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + acc * NCTA + cb, v);
+        if (row < rows) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const int c = n0 + cb + i;
+            if (c >= N) break;
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float t = __uint_as_float(v[i + e]);
+              if (bias && c + e < N) t += __ldg(bias + c + e);
+              o[e] = tc_act(t, p.act);
+            }
+            if (c + 3 < p.n1 && p.c1_vec) {
+              *reinterpret_cast<float4*>(p.c1 + grow * p.ld_c1 + c) = make_float4(o[0], o[1], o[2], o[3]);
+            } else if (c >= p.n1 && c + 3 < N && p.c2_vec && ((c - p.n1) & 3) == 0) {
+              *reinterpret_cast<float4*>(p.c2 + grow * p.ld_c2 + (c - p.n1)) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int cc2 = c + e;
+                if (cc2 < p.n1) { if (p.c1) p.c1[grow * p.ld_c1 + cc2] = o[e]; }
+                else if (cc2 < N) { if (p.c2) p.c2[grow * p.ld_c2 + (cc2 - p.n1)] = o[e]; }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_base + 80 + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 2 * NCTA);
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+constexpr int V2_SMEM_BUDGET = 227 * 1024 - 1024 - 256;   // after alignment slack and barriers
+
+int g_num_sms = 0;
 
 int ensure_smem_attr() {
   static bool done = false;   // per process; the attribute is per function per device context
   if (!done) {
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        227 * 1024));
+    int dev = 0;
+    DCGC_CUDA_CALL(cudaGetDevice(&dev));
+    DCGC_CUDA_CALL(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     done = true;
   }
   return DCGC_OK;
@@ -394,9 +617,32 @@ int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_
   p.a2_vec = a2 && ld_a2 % 4 == 0 && aligned16(a2);
   p.c1_vec = c1 && ld_c1 % 4 == 0 && aligned16(c1);
   p.c2_vec = c2 && ld_c2 % 4 == 0 && aligned16(c2);
-  dim3 grid((unsigned)row_tiles, (unsigned)(n_pad / TC_BN));
-  tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
-  DCGC_CUDA_LAUNCH_CHECK("tc_gemm_kernel");
+  // persistent weight-resident kernel when the (hi, lo) weight slice of a 128- or 64-column range fits
+  // next to at least two A stages; otherwise the one-tile-per-CTA kernel
+  int ncta = 0;
+  if ((int64_t)128 * k_pad * 8 + 2 * V2_A_STAGE_BYTES <= V2_SMEM_BUDGET) ncta = 128;
+  else if ((int64_t)64 * k_pad * 8 + 2 * V2_A_STAGE_BYTES <= V2_SMEM_BUDGET) ncta = 64;
+  if (ncta && row_tiles < (1 << 30)) {
+    TcArgs2 q2{};
+    q2.a = p;
+    q2.n_row_tiles = (int)row_tiles;
+    q2.b_bytes = ncta * k_pad * 8;
+    int stages = (V2_SMEM_BUDGET - q2.b_bytes) / V2_A_STAGE_BYTES;
+    q2.n_stages = stages > V2_MAX_STAGES ? V2_MAX_STAGES : stages;
+    const int slices = (N + ncta - 1) / ncta;
+    int ctas = g_num_sms / slices;
+    if (ctas < 1) ctas = 1;
+    if (ctas > row_tiles) ctas = (int)row_tiles;
+    const int smem = q2.b_bytes + q2.n_stages * V2_A_STAGE_BYTES + 1024 + 256;
+    dim3 grid((unsigned)ctas, (unsigned)slices);
+    if (ncta == 128) tc_gemm_kernel_v2<128><<<grid, V2_THREADS, smem, st>>>(q2);
+    else tc_gemm_kernel_v2<64><<<grid, V2_THREADS, smem, st>>>(q2);
+    DCGC_CUDA_LAUNCH_CHECK("tc_gemm_kernel_v2");
+  } else {
+    dim3 grid((unsigned)row_tiles, (unsigned)(n_pad / TC_BN));
+    tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
+    DCGC_CUDA_LAUNCH_CHECK("tc_gemm_kernel");
+  }
   DCGC_CUDA_CALL(cudaFreeAsync(prep, st));
   return DCGC_OK;
 }
