@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches rotated through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", default=None, help="write an in-situ per-scope CUDA-event breakdown "
+                    "(5 extra steps, outside the timed region) to this file")
     return ap.parse_args()
 
 
@@ -256,6 +258,22 @@ def run_ours(args):
         n_at, n_ed = topo.n_atoms, topo.n_edges
         gs_bytes += sum(2 * n_at * w_ * 4 + n_ed * 4 for w_ in widths_in)
         gs_bytes += sum(3 * n_at * w_ * 4 + n_ed * 4 for w_ in widths_in[1:])
+
+    if args.breakdown and rank == 0:
+        ops.profile_begin("*")
+        nb = 5
+        for i in range(nb):
+            step_resident(i)
+        torch.cuda.synchronize()
+        rep = ops.profile_report()
+        tot = sum(v[0] for v in rep.values())
+        with open(args.breakdown, "w") as fh:
+            fh.write("# in-situ CUDA-event breakdown, %d steps, %s, ms_per_step(timed)=%.4f\n" % (nb, args.gemm_mode, ms / K))
+            fh.write("| scope | us/step | share | calls/step | us/call |\n|---|---:|---:|---:|---:|\n")
+            for name, (t, n) in sorted(rep.items(), key=lambda kv: -kv[1][0]):
+                fh.write("| %s | %.1f | %.1f%% | %.1f | %.1f |\n" % (name, t * 1e3 / nb, 100 * t / tot, n / nb, t * 1e3 / n))
+            fh.write("| total | %.1f | | | |\n" % (tot * 1e3 / nb))
+    barrier()
 
     # ---- timed region 2: end to end through the public API with host buffers
     e2e = None

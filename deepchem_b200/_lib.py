@@ -65,6 +65,7 @@ _SIGNATURES = {
     "dcgc_launch_count": (c_int64, []),
     "dcgc_profile_begin": (c_int32, [c_char_p]),
     "dcgc_profile_end": (c_int32, [POINTER(ctypes.c_double), POINTER(c_int64)]),
+    "dcgc_profile_report": (c_int32, [c_char_p, c_int64]),
     "dcgc_layout_plan": (c_int32, [c_int64, _P, _P, c_int64, c_int32, POINTER(LayoutInfo)]),
     "dcgc_layout_build": (c_int32, [c_int64, _P, _P, _P, POINTER(LayoutInfo), _P]),
     "dcgc_layout_permute_features_host": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, c_int64, c_int32]),

@@ -48,6 +48,22 @@ struct DcgcProfScope {
 #endif
 
 #ifdef __CUDACC__
+// stage-1 arguments of the weight-gradient contraction (shared by the SIMT and tcgen05 kernels):
+// chunk c of group g covers rows [group_row0[g] + (c - chunk_prefix[g]) * chunk_rows, ...) and writes
+// the partial dW to ws[c][k1+k2][n] and the partial column sums of grad to wsb[c][n]
+struct DcgcWgradArgs {
+  const float* a1; int64_t ld_a1; int k1;
+  const float* a2; int64_t ld_a2; int k2;
+  const float* g; int64_t ld_g; int n;
+  float* ws; float* wsb;
+  int chunk_rows, n_groups, tiles_n;
+  int64_t group_row0[DCGC_N_DEG + 1];
+  int chunk_prefix[DCGC_N_DEG + 1];
+  int a1_vec, a2_vec, g_vec;
+};
+int dcgc_tc_wgrad_stage1(const DcgcWgradArgs& p, int chunks, cudaStream_t st);
+int dcgc_tc_wgrad_grid_y(int k_total, int n);
+int dcgc_tc_num_sms();
 // tcgen05 path (gemm_tc.cu); see the comment there for the argument convention
 int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_t ld_a2, int k2, const float* w,
                  int n_groups, int trans_w, const float* bias, int n1, int n2, const int32_t* tiles, int64_t n_tiles,

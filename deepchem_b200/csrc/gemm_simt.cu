@@ -201,16 +201,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const GemmArgs p) {
 // wgrad: stage 1 — every CTA reduces one chunk of rows of one group into a 128 x BN partial of
 // dW (and of dbias); stage 2 — partials of a group are summed in chunk order.
 // ------------------------------------------------------------------------------------------
-struct WgradArgs {
-  const float* a1; int64_t ld_a1; int k1;
-  const float* a2; int64_t ld_a2; int k2;
-  const float* g; int64_t ld_g; int n;
-  float* ws; float* wsb;
-  int chunk_rows, n_groups, tiles_n;
-  int64_t group_row0[DCGC_N_DEG + 1];
-  int chunk_prefix[DCGC_N_DEG + 1];
-  int a1_vec, a2_vec, g_vec;
-};
+using WgradArgs = DcgcWgradArgs;
 
 template <int BN>
 __global__ void __launch_bounds__(NT, 2) wgrad_kernel(const WgradArgs p) {
@@ -464,7 +455,6 @@ static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, 
                       int64_t ld_a2, int32_t k2, const float* g, int64_t ld_g, int32_t n,
                       const int64_t* deg_count, int32_t n_groups, float* dw, float* dbias,
                       void* workspace, int64_t workspace_bytes, int transpose, void* stream) {
-  // the weight-gradient contraction runs on the fp32 SIMT path in every mode for now
   DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || mode == DCGC_GEMM_TF32X3,
                  "dcgc_group_gemm_wgrad: GEMM mode %d is not available in this build", mode);
   DCGC_CHECK_ARG(k1 >= 0 && k2 >= 0 && n >= 0 && ld_a1 >= k1 && ld_g >= n, "dcgc_group_gemm_wgrad: bad sizes");
@@ -483,8 +473,20 @@ static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, 
   p.a1 = a1; p.ld_a1 = ld_a1; p.k1 = k1;
   p.a2 = a2; p.ld_a2 = ld_a2; p.k2 = a2 ? k2 : 0;
   p.g = g; p.ld_g = ld_g; p.n = n;
-  int64_t chunk_rows = (total_rows + kTargetChunks - 1) / kTargetChunks;
-  chunk_rows = (chunk_rows + BK - 1) / BK * BK;
+  const bool tc = mode == DCGC_GEMM_TF32X3;
+  int64_t target = kTargetChunks;
+  if (tc) {
+    // one CTA per SM (the kernel takes the whole shared memory): keep the grid within one wave;
+    // every non-empty group adds at most one ragged chunk
+    int nonempty = 0;
+    for (int i = 0; i < n_groups; ++i) nonempty += deg_count[i] > 0;
+    target = dcgc_tc_num_sms() / dcgc_tc_wgrad_grid_y(Kt, n) - nonempty;
+    if (target > kTargetChunks) target = kTargetChunks;
+    if (target < 1) target = 1;
+  }
+  int64_t chunk_rows = (total_rows + target - 1) / target;
+  const int64_t gran = tc ? 32 : BK;
+  chunk_rows = (chunk_rows + gran - 1) / gran * gran;
   if (chunk_rows < 4 * BK) chunk_rows = 4 * BK;
   p.chunk_rows = (int)chunk_rows;
   p.n_groups = n_groups;
@@ -516,7 +518,10 @@ static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, 
   p.g_vec = ld_g % 4 == 0 && aligned16(g);
   DcgcProfScope prof_scope("dcgc_group_gemm_wgrad", (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
-  if (chunks > 0) {
+  if (chunks > 0 && tc) {
+    int st_ = dcgc_tc_wgrad_stage1(p, chunks, st);
+    if (st_ != DCGC_OK) return st_;
+  } else if (chunks > 0) {
     const int tiles_m = (Kt + BM - 1) / BM;
     if (n > 64) {
       p.tiles_n = (n + 127) / 128;
@@ -558,6 +563,7 @@ extern "C" int dcgc_linear_fwd(int32_t mode, const float* x, int64_t ld_x, int32
   DCGC_CHECK_ARG(act >= DCGC_ACT_NONE && act <= DCGC_ACT_TANH, "dcgc_linear_fwd: unknown activation %d", act);
   if (n_rows == 0 || n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(x && w && y, "dcgc_linear_fwd: null pointer");
+  DcgcProfScope prof_scope("dcgc_linear_fwd", (cudaStream_t)stream);
   if (mode == DCGC_GEMM_TF32X3)
     return dcgc_tc_gemm(x, ld_x, k, nullptr, 0, 0, w, 1, 0, bias, n, 0, nullptr, 0, n_rows, act, y, ld_y, nullptr, 0,
                         (cudaStream_t)stream);

@@ -16,6 +16,12 @@
 //   * epilogue (producer warps 0-3, which own TMEM lanes 32w..32w+31): tcgen05.ld 32 columns at a
 //     time, bias + activation, transpose through shared memory, 512-byte coalesced row stores.
 // 3 stages x (A hi, A lo, B hi, B lo) x 16 KB = 192 KB of shared memory, 128 TMEM columns.
+#include <stdlib.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.h"
 
 namespace {
@@ -555,11 +561,503 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tc_gemm_kernel_v2(const TcArgs2
   }
 }
 
+
+
+// ------------------------------------------------------------------------------------------
+// v3: persistent kernel, weights STREAMED per K chunk by the TMA engine.
+//   * tc_prep_image writes the split weights as ready-made shared-memory images: for every
+//     (group, column tile, K chunk) one 32 KB block = [B hi | B lo], each a K-major SWIZZLE_128B
+//     [128 x 32] tile, so a chunk of B is ONE 1-D bulk copy (cp.async.bulk, UBLKCP) issued by a
+//     dedicated warp with mbarrier complete_tx — no tensor map, no register staging, and the full
+//     128-column tile at any K (the resident-weight v2 kernel had to halve N for K = 256 and read
+//     A twice);
+//   * A producers (two groups of 4 warps taking alternate chunks) keep TWO chunks of 128-bit loads
+//     in flight per group (two register sets) across tile boundaries;
+//   * double-buffered TMEM accumulators: the epilogue of tile i overlaps the MMAs of tile i+1.
+//   warps 0-3 epilogue | 4-11 A producers | 12 MMA issuer + TMEM | 13 B loader (TMA)
+// ------------------------------------------------------------------------------------------
+constexpr int V3_THREADS = 14 * 32;
+constexpr int V3_STAGES = 3;
+constexpr int V3_STAGE_BYTES = 4 * TC_TILE_BYTES;   // A hi, A lo, B hi, B lo
+constexpr int V3_SMEM_BYTES = V3_STAGES * V3_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+struct ImgArgs {
+  const float* src; int64_t src_group_stride;
+  float* img;                 // [G][n_tiles][chunks][2][128 x 32 swizzled]
+  int n, k1, k2, k1_pad, trans, src_ld, n_tiles, chunks;
+};
+__global__ void __launch_bounds__(256) tc_prep_image(const ImgArgs p) {
+  const int g = blockIdx.z, nt = blockIdx.y, ch = blockIdx.x;
+  float* blk = p.img + (((int64_t)g * p.n_tiles + nt) * p.chunks + ch) * (2 * TC_BM * TC_BK);
+  for (int i = threadIdx.x; i < TC_BN * TC_BK; i += 256) {
+    int r, kl;
+    if (p.trans) { r = i & (TC_BN - 1); kl = i >> 7; }     // source is n-contiguous
+    else { kl = i & (TC_BK - 1); r = i >> 5; }             // source is k-contiguous
+    const int nn = nt * TC_BN + r, kk = ch * TC_BK + kl;
+    float v = 0.f;
+    if (nn < p.n) {
+      if (p.trans) {
+        int ks = -1;
+        if (kk < p.k1_pad) { if (kk < p.k1) ks = kk; }
+        else if (kk - p.k1_pad < p.k2) ks = p.k1 + (kk - p.k1_pad);
+        if (ks >= 0) v = __ldg(p.src + g * p.src_group_stride + (int64_t)ks * p.src_ld + nn);
+      } else if (kk < p.k1) {
+        v = __ldg(p.src + g * p.src_group_stride + (int64_t)nn * p.src_ld + kk);
+      }
+    }
+    const float h = tf32_hi(v);
+    const uint32_t o = (swz(r, kl >> 2) >> 2) + (kl & 3);   // float index inside the 16 KB tile
+    blk[o] = h;
+    blk[TC_BM * TC_BK + o] = v - h;
+  }
+}
+
+struct TcArgs3 {
+  TcArgs a;
+  const float* img;
+  int n_row_tiles, n_tiles_n;
+};
+
+__global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3 q) {
+  const TcArgs& p = q.a;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  constexpr int S = V3_STAGES;
+  const uint32_t bar_base = base + S * V3_STAGE_BYTES;
+  // barriers: full[s] +8s, empty[s] +32+8s, tmem_full[a] +64+8a, tmem_empty[a] +80+8a, tmem slot +96
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + S * V3_STAGE_BYTES + 96);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int P = gridDim.x, pid = blockIdx.x;
+  const int n0 = blockIdx.y * TC_BN;
+  const int N = p.n1 + p.n2;
+  const int chunks1 = (p.k1 + TC_BK - 1) / TC_BK, chunks2 = (p.k2 + TC_BK - 1) / TC_BK;
+  const int total = chunks1 + chunks2;
+  const int my_tiles = pid < q.n_row_tiles ? (q.n_row_tiles - pid + P - 1) / P : 0;
+  const int n_cc = my_tiles * total;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_base + 8 * s, 4 + 1);        // 4 producer warps of one group + the B loader
+      mbar_init(bar_base + 32 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_base + 64 + 8 * a, 1);
+      mbar_init(bar_base + 80 + 8 * a, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 12) tmem_alloc(bar_base + 96, 2 * TC_BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= 4 && warp < 12) {
+    // ===================== A producers =====================
+    const int ptid = tid - 128, group = ptid >> 7, gt = ptid & 127;
+    int c_it = -1, row0 = 0, rows = 0, gg = 0;
+    auto issue = [&](float4 (&r)[8], int cc) {
+      if (cc >= n_cc) return;
+      const int it = cc / total, ch = cc - it * total;
+      if (it != c_it) { tile_of(p, pid + it * P, row0, rows, gg); c_it = it; }
+      const float* src; int64_t ld; int ksrc, kbase; bool vec;
+      if (ch < chunks1) { src = p.a1; ld = p.ld_a1; ksrc = p.k1; kbase = ch * TC_BK; vec = p.a1_vec; }
+      else { src = p.a2; ld = p.ld_a2; ksrc = p.k2; kbase = (ch - chunks1) * TC_BK; vec = p.a2_vec; }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int f = gt + u * TC_GROUP_THREADS, r_ = f >> 3, k = kbase + 4 * (f & 7);
+        r[u] = r_ < rows ? ld4_masked(src + (int64_t)(row0 + r_) * ld + k, ksrc - k, vec)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto commit = [&](const float4 (&r)[8], int cc) {
+      const int s = cc % S, use = cc / S;
+      mbar_wait(bar_base + 32 + 8 * s, (use & 1) ^ 1);
+      uint8_t* st = sm + s * V3_STAGE_BYTES;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int f = gt + u * TC_GROUP_THREADS;
+        const uint32_t o = swz(f >> 3, f & 7);
+        float4 hi, lo;
+        split4(r[u], hi, lo);
+        *reinterpret_cast<float4*>(st + o) = hi;
+        *reinterpret_cast<float4*>(st + TC_TILE_BYTES + o) = lo;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_base + 8 * s);
+    };
+    float4 ra[8], rb[8];
+    issue(ra, group);
+    for (int cc = group; cc < n_cc; cc += 4) {
+      issue(rb, cc + 2);
+      commit(ra, cc);
+      issue(ra, cc + 4);
+      if (cc + 2 < n_cc) commit(rb, cc + 2);
+    }
+  } else if (warp == 13) {
+    // ===================== B loader: one bulk copy per chunk =====================
+    if (lane == 0) {
+      int cc = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        int row0, rows, g;
+        tile_of(p, pid + it * P, row0, rows, g);
+        const float* src = q.img + ((int64_t)g * q.n_tiles_n + blockIdx.y) * total * (2 * TC_BM * TC_BK);
+        for (int ch = 0; ch < total; ++ch, ++cc) {
+          const int s = cc % S, use = cc / S;
+          mbar_wait(bar_base + 32 + 8 * s, (use & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_base + 8 * s, 2 * TC_TILE_BYTES);
+          bulk_g2s(base + s * V3_STAGE_BYTES + 2 * TC_TILE_BYTES, src + (int64_t)ch * (2 * TC_BM * TC_BK),
+                   2 * TC_TILE_BYTES, bar_base + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 12) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int cc = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int acc = it & 1;
+        mbar_wait(bar_base + 80 + 8 * acc, ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem + acc * TC_BN;
+        for (int ch = 0; ch < total; ++ch, ++cc) {
+          const int s = cc % S;
+          mbar_wait(bar_base + 8 * s, (cc / S) & 1);
+          tc_fence_after();
+          const uint32_t sa = base + s * V3_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UK; ++k) {
+            const uint32_t ko = k * TC_UK * 4;
+            const uint64_t ahi = make_desc(sa + ko), alo = make_desc(sa + TC_TILE_BYTES + ko);
+            const uint64_t bhi = make_desc(sa + 2 * TC_TILE_BYTES + ko), blo = make_desc(sa + 3 * TC_TILE_BYTES + ko);
+            umma_tf32(d, alo, bhi, kIdescTf32, (ch | k) != 0);
+            umma_tf32(d, ahi, blo, kIdescTf32, 1);
+            umma_tf32(d, ahi, bhi, kIdescTf32, 1);
+          }
+          umma_commit(bar_base + 32 + 8 * s);
+        }
+        umma_commit(bar_base + 64 + 8 * acc);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 0-3) =====================
+    for (int it = 0; it < my_tiles; ++it) {
+      int row0, rows, g;
+      tile_of(p, pid + it * P, row0, rows, g);
+      const int acc = it & 1;
+      if (total > 0) {
+        mbar_wait(bar_base + 64 + 8 * acc, (it >> 1) & 1);
+        tc_fence_after();
+      }
+      const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_group_stride : nullptr;
+      const int row = warp * 32 + lane;
+      const int64_t grow = row0 + row;
+#pragma unroll 1
+      for (int cb = 0; cb < TC_BN; cb += 32) {
+        uint32_t v[32];
+        if (total > 0) {
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + acc * TC_BN + cb, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        if (row < rows) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const int c = n0 + cb + i;
+            if (c >= N) break;
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float t = __uint_as_float(v[i + e]);
+              if (bias && c + e < N) t += __ldg(bias + c + e);
+              o[e] = tc_act(t, p.act);
+            }
+            if (c + 3 < p.n1 && p.c1_vec) {
+              *reinterpret_cast<float4*>(p.c1 + grow * p.ld_c1 + c) = make_float4(o[0], o[1], o[2], o[3]);
+            } else if (c >= p.n1 && c + 3 < N && p.c2_vec && ((c - p.n1) & 3) == 0) {
+              *reinterpret_cast<float4*>(p.c2 + grow * p.ld_c2 + (c - p.n1)) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int cc2 = c + e;
+                if (cc2 < p.n1) { if (p.c1) p.c1[grow * p.ld_c1 + cc2] = o[e]; }
+                else if (cc2 < N) { if (p.c2) p.c2[grow * p.ld_c2 + (cc2 - p.n1)] = o[e]; }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bar_base + 80 + 8 * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 2 * TC_BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad on tensor cores: dW[g] = [a1|a2]_g^T . grad_g, a contraction over the ROWS (atoms) of one
+// degree bucket.  One CTA owns one chunk of rows of one group (fixed split => deterministic) and
+// MT 128-row tiles of dW x one 128-column tile:
+//   * 8 producer warps: lane = atom row of a 32-row K chunk, warp w = 16 consecutive feature
+//     columns; LDG.128 of [a1|a2] and grad (two register sets: the loads of chunk c+1 are in flight
+//     while chunk c is split into tf32 hi/lo and TRANSPOSED into the K-major SWIZZLE_128B tiles
+//     with conflict-free 4-byte stores (all lanes of a store hit one 128-byte smem row);
+//   * warp 8: one lane issues MT x 4 K-steps x 3 tcgen05.mma (lo*hi + hi*lo + hi*hi) per chunk;
+//   * epilogue (warps 0-3): tcgen05.ld the fp32 accumulators, store the partial dW to the
+//     workspace; the column sums of grad (dbias) are accumulated by the producers in registers and
+//     combined with a fixed-order warp shuffle reduction.
+// The partials are summed in chunk order by wgrad_reduce_kernel (gemm_simt.cu).
+// ------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 9 * 32;
+constexpr int WG_STAGES = 2;
+
+template <int MT>
+__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgradArgs p) {
+  constexpr int NL = 4 * (MT + 1);                              // float4 loads per thread per chunk
+  constexpr int STAGE_BYTES = (2 * MT + 2) * TC_TILE_BYTES;     // (A hi, A lo) x MT, G hi, G lo
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_base = base + WG_STAGES * STAGE_BYTES;
+  // barriers: full[s] +8s, empty[s] +16+8s, accumulator-ready +32, tmem slot +40
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + WG_STAGES * STAGE_BYTES + 40);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x;
+  int g = 0;
+  while (g + 1 < p.n_groups && chunk >= p.chunk_prefix[g + 1]) ++g;
+  const int64_t r_begin = p.group_row0[g] + (int64_t)(chunk - p.chunk_prefix[g]) * p.chunk_rows;
+  const int64_t r_end = min(p.group_row0[g + 1], r_begin + p.chunk_rows);
+  const int mp = blockIdx.y / p.tiles_n, nt = blockIdx.y - mp * p.tiles_n;
+  const int m0 = mp * MT * TC_BM, n0 = nt * TC_BN;
+  const int Kt = p.k1 + p.k2;
+  const int steps = (int)((r_end - r_begin + TC_BK - 1) / TC_BK);
+
+  if (tid == 0) {
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(bar_base + 8 * s, TC_PRODUCER_WARPS);
+      mbar_init(bar_base + 16 + 8 * s, 1);
+    }
+    mbar_init(bar_base + 32, 1);
+    fence_barrier_init();
+  }
+  if (warp == TC_PRODUCER_WARPS) tmem_alloc(bar_base + 40, MT * TC_BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < TC_PRODUCER_WARPS) {
+    float bsum[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bsum[i] = 0.f;
+    const int col = 16 * warp;   // first column of this warp inside every 128-wide tile
+
+    auto gload = [&](float4 (&r)[NL], int c) {
+      const int64_t row = r_begin + (int64_t)c * TC_BK + lane;
+      const bool live = row < r_end;
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int m = m0 + t * TC_BM + col + 4 * j;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live && m < Kt) {
+            if (m + 3 < p.k1) {
+              v = ld4_masked(p.a1 + row * p.ld_a1 + m, 4, p.a1_vec);
+            } else if (m >= p.k1) {
+              const int f2 = m - p.k1;
+              v = ld4_masked(p.a2 + row * p.ld_a2 + f2, p.k2 - f2, p.a2_vec && (f2 & 3) == 0);
+            } else {   // the float4 straddles the a1 | a2 boundary
+              float e[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int fe = m + q;
+                e[q] = fe < p.k1 ? __ldg(p.a1 + row * p.ld_a1 + fe)
+                                 : (fe < Kt ? __ldg(p.a2 + row * p.ld_a2 + (fe - p.k1)) : 0.f);
+              }
+              v = make_float4(e[0], e[1], e[2], e[3]);
+            }
+          }
+          r[4 * t + j] = v;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + col + 4 * j;
+        r[4 * MT + j] = live ? ld4_masked(p.g + row * p.ld_g + n, p.n - n, p.g_vec)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    auto sstore = [&](const float4 (&r)[NL], int c) {
+      const int s = c & 1, use = c >> 1;
+      mbar_wait(bar_base + 16 + 8 * s, (use & 1) ^ 1);           // the MMAs that read this stage retired
+      uint8_t* st = sm + s * STAGE_BYTES;
+      const uint32_t kofs = (uint32_t)(lane & 3) * 4;
+      const int kc = lane >> 2;
+#pragma unroll
+      for (int t = 0; t <= MT; ++t) {
+        uint8_t* hi_t = st + 2 * t * TC_TILE_BYTES;
+        uint8_t* lo_t = hi_t + TC_TILE_BYTES;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 hi, lo;
+          split4(r[4 * t + j], hi, lo);
+          const float h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int rr = col + 4 * j + e;                       // row of the K-major tile
+            const uint32_t o = (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128 + ((kc ^ (rr & 7)) << 4)) + kofs;
+            *reinterpret_cast<float*>(hi_t + o) = h[e];
+            *reinterpret_cast<float*>(lo_t + o) = l[e];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        bsum[4 * j + 0] += r[4 * MT + j].x; bsum[4 * j + 1] += r[4 * MT + j].y;
+        bsum[4 * j + 2] += r[4 * MT + j].z; bsum[4 * j + 3] += r[4 * MT + j].w;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_base + 8 * s);
+    };
+
+    float4 ra[NL], rb[NL];
+    if (steps > 0) gload(ra, 0);
+    for (int c = 0; c < steps; c += 2) {
+      if (c + 1 < steps) gload(rb, c + 1);
+      sstore(ra, c);
+      if (c + 2 < steps) gload(ra, c + 2);
+      if (c + 1 < steps) sstore(rb, c + 1);
+    }
+    // dbias partial: fixed-order butterfly over the 32 atom lanes
+    if (mp == 0) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float v = bsum[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int n = n0 + col + i;
+        if (lane == 0 && n < p.n) p.wsb[(int64_t)chunk * p.n + n] = v;
+      }
+    }
+  } else if (lane == 0) {
+    for (int c = 0; c < steps; ++c) {
+      const int s = c & 1;
+      mbar_wait(bar_base + 8 * s, (c >> 1) & 1);
+      tc_fence_after();
+      const uint32_t sa = base + s * STAGE_BYTES;
+      const uint32_t sg_hi = sa + 2 * MT * TC_TILE_BYTES, sg_lo = sg_hi + TC_TILE_BYTES;
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+        const uint32_t a_hi = sa + 2 * t * TC_TILE_BYTES, a_lo = a_hi + TC_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / TC_UK; ++k) {
+          const uint32_t ko = k * TC_UK * 4;
+          const uint64_t ahi = make_desc(a_hi + ko), alo = make_desc(a_lo + ko);
+          const uint64_t ghi = make_desc(sg_hi + ko), glo = make_desc(sg_lo + ko);
+          umma_tf32(tmem + t * TC_BN, alo, ghi, kIdescTf32, (c | k) != 0);
+          umma_tf32(tmem + t * TC_BN, ahi, glo, kIdescTf32, 1);
+          umma_tf32(tmem + t * TC_BN, ahi, ghi, kIdescTf32, 1);
+        }
+      }
+      umma_commit(bar_base + 16 + 8 * s);
+    }
+    umma_commit(bar_base + 32);
+  }
+
+  if (warp < 4) {
+    if (steps > 0) {
+      mbar_wait(bar_base + 32, 0);
+      tc_fence_after();
+    }
+    const bool n_vec = (p.n & 3) == 0 && (reinterpret_cast<uintptr_t>(p.ws) & 15) == 0;
+#pragma unroll 1
+    for (int t = 0; t < MT; ++t) {
+      const int m = m0 + t * TC_BM + warp * 32 + lane;
+      float* dst = p.ws + ((int64_t)chunk * Kt + m) * p.n;
+#pragma unroll 1
+      for (int cb = 0; cb < TC_BN; cb += 32) {
+        uint32_t v[32];
+        if (steps > 0) {
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + t * TC_BN + cb, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0u;
+        }
+        if (m < Kt) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const int c = n0 + cb + i;
+            if (c + 3 < p.n && n_vec) {
+              *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                                                                __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (c + e < p.n) dst[c + e] = __uint_as_float(v[i + e]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TC_PRODUCER_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem, MT * TC_BN);
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 constexpr int V2_SMEM_BUDGET = 227 * 1024 - 1024 - 256;   // after alignment slack and barriers
 
 int g_num_sms = 0;
+
+// Split-weight scratch (hi | lo), one grow-only buffer per (device, stream): launches on one stream are
+// ordered, so the prep -> GEMM -> next prep sequence never races; no allocation on the steady-state path.
+struct PrepBuf { float* p; size_t bytes; };
+std::mutex g_prep_mu;
+std::map<std::pair<int, cudaStream_t>, PrepBuf> g_prep;
+
+int prep_scratch(cudaStream_t st, size_t bytes, float** out) {
+  int dev = 0;
+  DCGC_CUDA_CALL(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_prep_mu);
+  PrepBuf& b = g_prep[std::make_pair(dev, st)];
+  if (b.bytes < bytes) {
+    if (b.p) {
+      DCGC_CUDA_CALL(cudaStreamSynchronize(st));
+      DCGC_CUDA_CALL(cudaFree(b.p));
+      b.p = nullptr; b.bytes = 0;
+    }
+    const size_t want = bytes + bytes / 2;
+    DCGC_CUDA_CALL(cudaMalloc((void**)&b.p, want));
+    b.bytes = want;
+  }
+  *out = b.p;
+  return DCGC_OK;
+}
 
 int ensure_smem_attr() {
   static bool done = false;   // per process; the attribute is per function per device context
@@ -569,6 +1067,9 @@ int ensure_smem_attr() {
                                         227 * 1024));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int dev = 0;
     DCGC_CUDA_CALL(cudaGetDevice(&dev));
     DCGC_CUDA_CALL(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -591,11 +1092,48 @@ int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_
   if (st_ != DCGC_OK) return st_;
   const int k1_pad = (k1 + TC_BK - 1) / TC_BK * TC_BK, k2_pad = (k2 + TC_BK - 1) / TC_BK * TC_BK;
   const int k_pad = k1_pad + k2_pad;
+  static const int variant = [] { const char* e = getenv("DCGC_TC_VARIANT"); return e ? atoi(e) : 3; }();
+  if (variant == 3 && row_tiles < (1 << 30)) {
+    const int n_tiles_n = (N + TC_BN - 1) / TC_BN, chunks = k_pad / TC_BK;
+    float* img = nullptr;
+    st_ = prep_scratch(st, (size_t)n_groups * n_tiles_n * (chunks > 0 ? chunks : 1) * 2 * TC_TILE_BYTES, &img);
+    if (st_ != DCGC_OK) return st_;
+    if (chunks > 0) {
+      ImgArgs ia{};
+      ia.src = w; ia.img = img; ia.n = N; ia.k1 = k1; ia.k2 = a2 ? k2 : 0; ia.k1_pad = k1_pad; ia.trans = trans_w;
+      ia.n_tiles = n_tiles_n; ia.chunks = chunks;
+      if (trans_w) { ia.src_ld = N; ia.src_group_stride = (int64_t)(k1 + k2) * N; }
+      else { ia.src_ld = k1; ia.src_group_stride = (int64_t)N * k1; }
+      dim3 pgrid((unsigned)chunks, (unsigned)n_tiles_n, (unsigned)n_groups);
+      tc_prep_image<<<pgrid, 256, 0, st>>>(ia);
+      DCGC_CUDA_LAUNCH_CHECK("tc_prep_image");
+    }
+    TcArgs3 q3{};
+    TcArgs& p3 = q3.a;
+    p3.a1 = a1; p3.ld_a1 = ld_a1; p3.k1 = k1;
+    p3.a2 = a2; p3.ld_a2 = ld_a2; p3.k2 = a2 ? k2 : 0;
+    p3.bias = bias; p3.bias_group_stride = N;
+    p3.n1 = n1; p3.n2 = n2; p3.c1 = c1; p3.ld_c1 = ld_c1; p3.c2 = c2; p3.ld_c2 = ld_c2;
+    p3.tiles = tiles; p3.n_rows = n_rows; p3.act = act;
+    p3.a1_vec = ld_a1 % 4 == 0 && aligned16(a1);
+    p3.a2_vec = a2 && ld_a2 % 4 == 0 && aligned16(a2);
+    p3.c1_vec = c1 && ld_c1 % 4 == 0 && aligned16(c1);
+    p3.c2_vec = c2 && ld_c2 % 4 == 0 && aligned16(c2);
+    q3.img = img; q3.n_row_tiles = (int)row_tiles; q3.n_tiles_n = n_tiles_n;
+    int ctas = g_num_sms / n_tiles_n;
+    if (ctas < 1) ctas = 1;
+    if (ctas > row_tiles) ctas = (int)row_tiles;
+    dim3 grid((unsigned)ctas, (unsigned)n_tiles_n);
+    tc_gemm_kernel_v3<<<grid, V3_THREADS, V3_SMEM_BYTES, st>>>(q3);
+    DCGC_CUDA_LAUNCH_CHECK("tc_gemm_kernel_v3");
+    return DCGC_OK;
+  }
   // output column space: [0, n1) -> c1, [n1, n1+n2) -> c2 (contiguous: the kernel's epilogue maps them)
   const int n_pad = (N + TC_BN - 1) / TC_BN * TC_BN;
   const int64_t gstride = (int64_t)n_pad * k_pad;
   float* prep = nullptr;
-  DCGC_CUDA_CALL(cudaMallocAsync((void**)&prep, (size_t)2 * n_groups * gstride * sizeof(float), st));
+  st_ = prep_scratch(st, (size_t)2 * n_groups * gstride * sizeof(float), &prep);
+  if (st_ != DCGC_OK) return st_;
   PrepArgs q{};
   q.src = w; q.hi = prep; q.lo = prep + (int64_t)n_groups * gstride; q.dst_group_stride = gstride;
   q.n = N; q.n_pad = n_pad; q.k1 = k1; q.k2 = k2; q.k1_pad = k1_pad; q.k_pad = k_pad; q.trans = trans_w;
@@ -643,6 +1181,32 @@ int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_
     tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
     DCGC_CUDA_LAUNCH_CHECK("tc_gemm_kernel");
   }
-  DCGC_CUDA_CALL(cudaFreeAsync(prep, st));
+  return DCGC_OK;
+}
+
+// Stage 1 of dcgc_group_gemm_wgrad / dcgc_linear_wgrad in DCGC_GEMM_TF32X3 mode (stage 2 is the shared
+// fixed-order reduction of the per-chunk partials).
+int dcgc_tc_wgrad_grid_y(int k_total, int n) {
+  const int mt = k_total > TC_BM ? 2 : 1;
+  return ((k_total + mt * TC_BM - 1) / (mt * TC_BM)) * ((n + TC_BN - 1) / TC_BN);
+}
+int dcgc_tc_num_sms() {
+  if (ensure_smem_attr() != DCGC_OK) return 148;
+  return g_num_sms > 0 ? g_num_sms : 148;
+}
+int dcgc_tc_wgrad_stage1(const DcgcWgradArgs& p_in, int chunks, cudaStream_t st) {
+  if (chunks <= 0) return DCGC_OK;
+  int st_ = ensure_smem_attr();
+  if (st_ != DCGC_OK) return st_;
+  DcgcWgradArgs p = p_in;
+  const int Kt = p.k1 + p.k2;
+  const int mt = Kt > TC_BM ? 2 : 1;
+  p.tiles_n = (p.n + TC_BN - 1) / TC_BN;
+  const int m_pairs = (Kt + mt * TC_BM - 1) / (mt * TC_BM);
+  dim3 grid((unsigned)chunks, (unsigned)(m_pairs * p.tiles_n));
+  const int smem = WG_STAGES * (2 * mt + 2) * TC_TILE_BYTES + 1024 + 256;
+  if (mt == 2) tc_wgrad_kernel<2><<<grid, WG_THREADS, smem, st>>>(p);
+  else tc_wgrad_kernel<1><<<grid, WG_THREADS, smem, st>>>(p);
+  DCGC_CUDA_LAUNCH_CHECK("tc_wgrad_kernel");
   return DCGC_OK;
 }

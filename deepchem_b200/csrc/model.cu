@@ -26,26 +26,35 @@ inline unsigned blocks_for(int64_t n, int t = kT) { return (unsigned)((n + t - 1
 // ------------------------------------------------------------------------------------------
 // column moments: out_a[c] = sum_r a[r,c], out_ab[c] = sum_r a[r,c]*b[r,c]   (float64, 2 stages)
 // ------------------------------------------------------------------------------------------
-constexpr int kMomRows = 256;   // rows per stage-1 block
-constexpr int kMomLanes = 16;   // row lanes per block (x 32 float4 column lanes = 512 threads)
+constexpr int kMomLanes = 16;       // row lanes per block (x 32 float4 column lanes = 512 threads)
+constexpr int kMomMaxChunks = 296;  // stage-1 blocks: two per SM, each walks a contiguous row range
 
-// block: 32 column lanes (float4 -> 128 columns) x 16 row lanes; every thread owns 16 rows of its
-// chunk, 8 independent 128-bit loads in flight; fp32 partials over <= 16 rows, float64 from there on.
-__global__ void __launch_bounds__(32 * kMomLanes)
+inline int mom_chunks(int64_t n) {
+  const int64_t c = (n + 127) / 128;
+  return (int)(c < 1 ? 1 : (c > kMomMaxChunks ? kMomMaxChunks : c));
+}
+inline int64_t mom_rows(int64_t n, int chunks) {
+  const int64_t r = (n + chunks - 1) / chunks;
+  return (r + kMomLanes - 1) / kMomLanes * kMomLanes;
+}
+
+// block: 32 column lanes (float4 -> 128 columns) x 16 row lanes walking rows r0+ry, r0+ry+16, ...;
+// 4 independent 128-bit loads per tensor in flight per thread; fp32 partials over 4 rows, float64 from
+// there on (fixed order => deterministic).
+__global__ void __launch_bounds__(32 * kMomLanes, 2)
 col_moments_partial(const float* __restrict__ a, int64_t ld_a, const float* __restrict__ b, int64_t ld_b,
-                    int64_t n_rows, int width, double* __restrict__ part) {
+                    int64_t n_rows, int width, int64_t rows_per_chunk, double* __restrict__ part) {
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.y * 128 + 4 * cx;
-  const int64_t r0 = (int64_t)blockIdx.x * kMomRows;
-  const int64_t r1 = min(n_rows, r0 + kMomRows);
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
+  const int64_t r1 = min(n_rows, r0 + rows_per_chunk);
   double da[4] = {0, 0, 0, 0}, dab[4] = {0, 0, 0, 0};
   if (c < width) {
+    for (int64_t rb = r0 + ry; rb < r1; rb += 4 * kMomLanes) {
+      float4 va[4], vb[4];
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      float4 va[8], vb[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int64_t r = r0 + ry + (int64_t)(half * 8 + u) * kMomLanes;
+      for (int u = 0; u < 4; ++u) {
+        const int64_t r = rb + (int64_t)u * kMomLanes;
         if (r < r1) {
           va[u] = __ldg(reinterpret_cast<const float4*>(a + r * ld_a + c));
           vb[u] = (b == a) ? va[u] : __ldg(reinterpret_cast<const float4*>(b + r * ld_b + c));
@@ -56,7 +65,7 @@ col_moments_partial(const float* __restrict__ a, int64_t ld_a, const float* __re
       }
       float sa[4] = {0, 0, 0, 0}, sab[4] = {0, 0, 0, 0};
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
         sa[0] += va[u].x; sa[1] += va[u].y; sa[2] += va[u].z; sa[3] += va[u].w;
         sab[0] = fmaf(va[u].x, vb[u].x, sab[0]); sab[1] = fmaf(va[u].y, vb[u].y, sab[1]);
         sab[2] = fmaf(va[u].z, vb[u].z, sab[2]); sab[3] = fmaf(va[u].w, vb[u].w, sab[3]);
@@ -80,20 +89,21 @@ col_moments_partial(const float* __restrict__ a, int64_t ld_a, const float* __re
   }
 }
 
-// sum of the stage-1 partials of one column, split over 8 lanes and combined in lane order
+// sum of the stage-1 partials of one column by one warp: lane-strided loads, fixed-order butterfly
 __device__ __forceinline__ void reduce_partials(const double* __restrict__ part, int n_chunks, int width, int c,
-                                                int lane8, double (*sh)[2][32], int cl, double& s, double& ss) {
+                                                int lane, double& s, double& ss) {
   double a = 0.0, b = 0.0;
-  for (int k = lane8; k < n_chunks; k += 8) {
+  for (int k = lane; k < n_chunks; k += 32) {
     a += part[((int64_t)k * 2) * width + c];
     b += part[((int64_t)k * 2 + 1) * width + c];
   }
-  sh[lane8][0][cl] = a;
-  sh[lane8][1][cl] = b;
-  __syncthreads();
-  s = 0.0; ss = 0.0;
 #pragma unroll
-  for (int l = 0; l < 8; ++l) { s += sh[l][0][cl]; ss += sh[l][1][cl]; }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  s = a;
+  ss = b;
 }
 
 // BatchNorm forward finalize: batch statistics -> folded scale/shift, running-stat update.
@@ -104,12 +114,12 @@ __global__ void bn_fwd_finalize(const double* __restrict__ part, int n_chunks, i
                                 float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                 float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                 float* __restrict__ scale_out, float* __restrict__ shift_out) {
-  __shared__ double sh[8][2][32];
-  const int cl = threadIdx.x & 31, lane8 = threadIdx.x >> 5;
-  const int c = min(blockIdx.x * 32 + cl, width - 1);
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= width) return;   // warp-uniform
   double s, ss;
-  reduce_partials(part, n_chunks, width, c, lane8, sh, cl, s, ss);
-  if (lane8 != 0 || blockIdx.x * 32 + cl >= width) return;
+  reduce_partials(part, n_chunks, width, c, lane, s, ss);
+  if (lane != 0) return;
   const double n = (double)n_rows;
   const double mean = n > 0 ? s / n : 0.0;
   double var = n > 0 ? ss / n - mean * mean : 0.0;
@@ -146,12 +156,12 @@ __global__ void bn_bwd_finalize(const double* __restrict__ part, int n_chunks, i
                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                 const float* __restrict__ scale, float* __restrict__ dgamma,
                                 float* __restrict__ dbeta, float* __restrict__ coef /* [3, width] */) {
-  __shared__ double sh[8][2][32];
-  const int cl = threadIdx.x & 31, lane8 = threadIdx.x >> 5;
-  const int c = min(blockIdx.x * 32 + cl, width - 1);
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= width) return;   // warp-uniform
   double sda, sday;
-  reduce_partials(part, n_chunks, width, c, lane8, sh, cl, sda, sday);
-  if (lane8 != 0 || blockIdx.x * 32 + cl >= width) return;
+  reduce_partials(part, n_chunks, width, c, lane, sda, sday);
+  if (lane != 0) return;
   const double n = (double)n_rows;
   const double dg = (double)invstd[c] * (sday - (double)mean[c] * sda);  // sum dA * xhat
   if (dgamma) dgamma[c] = (float)dg;
@@ -472,13 +482,15 @@ int bn_forward(const dcgc_gcmodel_config* cfg, const Layout& lo, int idx, const 
   const float* beta = params + lo.bn_b[idx];
   float* rm = bn_running ? bn_running + lo.bn_mean[idx] : nullptr;
   float* rv = bn_running ? bn_running + lo.bn_var[idx] : nullptr;
+  DcgcProfScope prof_scope("bn_stats_fwd", st);
   if (training) {
     if (n > 0) {
       dim3 grid((unsigned)sv.n_chunks, (unsigned)((width + 127) / 128));
-      col_moments_partial<<<grid, 32 * kMomLanes, 0, st>>>(y, ld_y, y, ld_y, n, width, sv.part);
+      col_moments_partial<<<grid, 32 * kMomLanes, 0, st>>>(y, ld_y, y, ld_y, n, width, mom_rows(n, sv.n_chunks),
+                                                           sv.part);
       DCGC_CUDA_LAUNCH_CHECK("col_moments_partial");
     }
-    bn_fwd_finalize<<<(width + 31) / 32, 256, 0, st>>>(sv.part, n > 0 ? sv.n_chunks : 0, width, n, gamma, beta,
+    bn_fwd_finalize<<<(width + 7) / 8, 256, 0, st>>>(sv.part, n > 0 ? sv.n_chunks : 0, width, n, gamma, beta,
                                                          cfg->bn_eps, cfg->bn_momentum, rm, rv, mean, invstd, scale,
                                                          shift);
     DCGC_CUDA_LAUNCH_CHECK("bn_fwd_finalize");
@@ -499,7 +511,7 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
                  lo.fp[0]);
   DCGC_CHECK_ARG(n_samples >= 0 && n_samples <= S, "dcgc_gcmodel: n_samples outside [0, n_segments]");
   // ---- carve the workspace
-  sv.n_chunks = (int)((N + kMomRows - 1) / kMomRows);
+  sv.n_chunks = mom_chunks(N);
   int wmax = D;
   for (int l = 0; l < L; ++l) wmax = wmax > cfg->widths[l] ? wmax : cfg->widths[l];
   sv.part = ws.take<double>((int64_t)(sv.n_chunks > 0 ? sv.n_chunks : 1) * 2 * wmax);
@@ -606,7 +618,7 @@ extern "C" int64_t dcgc_gcmodel_workspace_bytes(const dcgc_gcmodel_config* cfg, 
   int64_t bytes = n_atoms * per_atom * 4;
   bytes += n_segments * (int64_t)(2 * D * 2 + D) * 4;            // fp, dfp, argrow
   bytes += n_segments * (int64_t)cfg->n_out * 4 * 3;              // out, dout, per-element loss
-  bytes += ((n_atoms + kMomRows - 1) / kMomRows + 1) * 2 * (int64_t)wmax * 8;
+  bytes += (int64_t)(mom_chunks(n_atoms) + 1) * 2 * (int64_t)wmax * 8;
   bytes += ((n_segments + kHeadChunk - 1) / kHeadChunk + 1) * (int64_t)cfg->n_out * (2 * D + 1) * 4;
   int64_t wg = 0;
   for (int l = 0; l < L; ++l) {
@@ -690,6 +702,8 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
 
   // ---- loss and head
   const int64_t n_elems = n_samples * n_loss_elems_per_row;
+  {
+  DcgcProfScope prof_scope("head_loss_bwd", st);
   if (n_elems > 0) {
     loss_fwd_bwd<<<blocks_for(n_elems), kT, 0, st>>>(sv.out, y, w, n_elems, cfg->mode == 1 ? cfg->n_classes : 1,
                                                      cfg->mode, per_elem, dout);
@@ -711,6 +725,7 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
     head_bwd_input<<<blocks_for(S * 2 * D), kT, 0, st>>>(dout, params + lo.head_w, n_samples, S, 2 * D, T, dfp);
     DCGC_CUDA_LAUNCH_CHECK("head_bwd_input");
   }
+  }
   // ---- GraphGather backward -> dA (grad wrt the BN output of the dense layer)
   RET_IF(dcgc_gather_bwd(dfp, 2 * D, sv.fp, 2 * D, sv.argrow, t->membership, N, D, DCGC_ACT_TANH, dA, D, st));
 
@@ -718,15 +733,20 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
     // dA (ld = width) -> G in place; dgamma / dbeta into the gradient slab
     if (cfg->batch_norm) {
       const float* stats = sv.stats + sv.stats_off[idx];
+      {
+      DcgcProfScope prof_scope("bn_stats_bwd", st);
       if (N > 0) {
         dim3 grid((unsigned)sv.n_chunks, (unsigned)((width + 127) / 128));
-        col_moments_partial<<<grid, 32 * kMomLanes, 0, st>>>(dA, width, yv, width, N, width, sv.part);
+        col_moments_partial<<<grid, 32 * kMomLanes, 0, st>>>(dA, width, yv, width, N, width,
+                                                             mom_rows(N, sv.n_chunks), sv.part);
         DCGC_CUDA_LAUNCH_CHECK("col_moments_partial (bwd)");
       }
-      bn_bwd_finalize<<<(width + 31) / 32, 256, 0, st>>>(sv.part, N > 0 ? sv.n_chunks : 0, width, N, stats,
+      bn_bwd_finalize<<<(width + 7) / 8, 256, 0, st>>>(sv.part, N > 0 ? sv.n_chunks : 0, width, N, stats,
                                                            stats + width, stats + 2 * width, grads + lo.bn_g[idx],
                                                            grads + lo.bn_b[idx], coef);
       DCGC_CUDA_LAUNCH_CHECK("bn_bwd_finalize");
+      }
+      DcgcProfScope prof_scope("bn_relu_bwd_apply", st);
       if (N > 0) {
         bn_relu_bwd_apply<<<blocks_for(N * (width / 4)), kT, 0, st>>>(dA, width, yv, width, stats, stats + width, coef,
                                                                       N, width, 1, dA, width);
@@ -771,6 +791,7 @@ extern "C" int dcgc_adam_step(float* params, const float* grads, float* exp_avg,
   DCGC_CHECK_ARG(n >= 0 && step >= 1, "dcgc_adam_step: bad sizes (step counts from 1)");
   if (n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(params && grads && exp_avg && exp_avg_sq, "dcgc_adam_step: null pointer");
+  DcgcProfScope prof_scope("dcgc_adam_step", (cudaStream_t)stream);
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<blocks_for(n), kT, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,

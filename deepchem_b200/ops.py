@@ -92,6 +92,17 @@ def profile_end():
     return {"ms": ms.value, "launches": n.value}
 
 
+def profile_report():
+    """Ends a profile_begin("*") session -> {scope: (total_ms, calls)}."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(_lib.lib().dcgc_profile_report(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, ms, n = line.rsplit(" ", 2)
+        out[name] = (float(ms), int(n))
+    return out
+
+
 def _count(n=1):
     pass
 

@@ -56,6 +56,9 @@ int dcgc_device_ok(void);
 long long dcgc_launch_count(void);
 int dcgc_profile_begin(const char* entry_name);
 int dcgc_profile_end(double* total_ms, long long* launches);
+/* dcgc_profile_begin("*") brackets every entry point and every internal stage of the model engine;
+ * dcgc_profile_report ends such a session and writes one line "scope total_ms calls" per scope. */
+int dcgc_profile_report(char* out, int64_t cap);
 
 /* --------------------------------------------------------------------------------------------
  * Host layout builder.  Replaces ConvMol.agglomerate_mols (deepchem/feat/mol_graphs.py:256-349)

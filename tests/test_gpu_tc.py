@@ -104,3 +104,55 @@ def test_tc_model_engine_matches_fp32_engine():
         # two fp32-grade evaluations of an ill-conditioned sum over ~12k atoms through 3 BatchNorms
         # (see test_full_size_model_step_against_oracle): a few 1e-4 of the gradient scale apart
         assert float((p32.grad - ptc.grad).abs().max()) < 1e-2 * scale, name
+
+
+@pytest.mark.parametrize("k,c,shape", [(128, 128, "zinc"), (76, 128, "stress"), (64, 64, "stress"), (128, 256, "zinc"),
+                                       (192, 100, "stress")])
+def test_tc_group_gemm_wgrad(k, c, shape):
+    """tcgen05 weight gradient (contraction over the atoms of each degree bucket, operands
+    transposed into K-major tiles by the producers) against float64 and the SIMT path."""
+    from deepchem_b200 import ops, _lib
+    dev = _cuda()
+    topo = _topo(n_mols=700, seed=6, shape=shape)
+    n = topo.n_atoms
+    g = torch.Generator(device=dev).manual_seed(4)
+    x = torch.randn(n, k, device=dev, generator=g)
+    s = torch.randn(n, k, device=dev, generator=g)
+    go = torch.randn(n, c, device=dev, generator=g)
+    dw_tc, db_tc = ops.group_gemm_wgrad(x, s, go, topo, 11, _lib.GEMM_TF32X3)
+    dw_32, db_32 = ops.group_gemm_wgrad(x, s, go, topo, 11, _lib.GEMM_FP32)
+    a = torch.cat([x, s], 1).double()
+    start = 0
+    for d in range(11):
+        cnt = topo.deg_count[d]
+        ref = a[start:start + cnt].t() @ go[start:start + cnt].double()
+        refb = go[start:start + cnt].double().sum(0)
+        scale = max(float(ref.abs().max()), 1.0)
+        assert float((dw_32[d].double() - ref).abs().max()) < TOL * scale * 4
+        assert float((dw_tc[d].double() - ref).abs().max()) < TOL * scale * 4, (d, cnt)
+        assert float((db_tc[d].double() - refb).abs().max()) < TOL * max(float(refb.abs().max()), 1.0) * 4
+        start += cnt
+    # deterministic: a second call gives identical bits
+    dw2, db2 = ops.group_gemm_wgrad(x, s, go, topo, 11, _lib.GEMM_TF32X3)
+    assert torch.equal(dw2, dw_tc) and torch.equal(db2, db_tc)
+
+
+def test_tc_linear_wgrad_large():
+    from deepchem_b200 import _lib
+    import ctypes
+    dev = _cuda()
+    g = torch.Generator(device=dev).manual_seed(5)
+    n_rows, k, n = 50000, 128, 128
+    x = torch.randn(n_rows, k, device=dev, generator=g)
+    go = torch.randn(n_rows, n, device=dev, generator=g)
+    L = _lib.lib()
+    nbytes = int(L.dcgc_linear_wgrad_workspace(k, n))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dw = torch.empty(n, k, device=dev)
+    db = torch.empty(n, device=dev)
+    _lib.check(L.dcgc_linear_wgrad(_lib.GEMM_TF32X3, x.data_ptr(), k, k, go.data_ptr(), n, n, n_rows, dw.data_ptr(),
+                                   db.data_ptr(), ws.data_ptr(), nbytes,
+                                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    ref = go.double().t() @ x.double()
+    assert _rel(dw, ref) < TOL
+    assert _rel(db, go.double().sum(0)) < TOL
