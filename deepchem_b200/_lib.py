@@ -79,6 +79,12 @@ _SIGNATURES = {
     "dcgc_gather_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int32, c_int32, _P, c_int64, _P]),
     "dcgc_group_gemm_fwd": (c_int32, [c_int32, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, c_int32,
                                       _P, c_int64, c_int32, c_int64, c_int32, _P, c_int64, _P]),
+    "dcgc_group_gemm_fwd_stats": (c_int32, [c_int32, _P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, c_int32,
+                                            _P, c_int64, c_int32, c_int64, c_int32, _P, c_int64, _P,
+                                            POINTER(c_int32), _P]),
+    "dcgc_gemm_stats_max_chunks": (c_int32, []),
+    "dcgc_linear_fwd_stats": (c_int32, [c_int32, _P, c_int64, c_int32, _P, _P, c_int32, c_int64, c_int32, _P, c_int64,
+                                        _P, POINTER(c_int32), _P]),
     "dcgc_group_gemm_dgrad": (c_int32, [c_int32, _P, c_int64, c_int32, _P, c_int32, c_int32, _P, c_int64,
                                         c_int32, c_int64, _P, c_int64, _P, c_int64, _P]),
     "dcgc_group_gemm_wgrad_workspace": (c_int64, [c_int32, c_int32, c_int32, c_int32]),

@@ -356,10 +356,14 @@ constexpr int kTargetChunks = 148;
 
 }  // namespace
 
-extern "C" int dcgc_group_gemm_fwd(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2,
-                                   int64_t ld_a2, int32_t k2, const float* w, const float* bias, int32_t n,
-                                   const int32_t* tiles, int64_t n_tiles, int32_t tile_rows, int64_t n_rows,
-                                   int32_t act, float* y, int64_t ld_y, void* stream) {
+static int group_gemm_fwd_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2,
+                               int64_t ld_a2, int32_t k2, const float* w, const float* bias, int32_t n,
+                               const int32_t* tiles, int64_t n_tiles, int32_t tile_rows, int64_t n_rows,
+                               int32_t act, float* y, int64_t ld_y, double* stats, int32_t* stats_chunks,
+                               void* stream) {
+  if (stats_chunks) *stats_chunks = 0;
+  DCGC_CHECK_ARG(stats == nullptr || mode == DCGC_GEMM_TF32X3,
+                 "dcgc_group_gemm_fwd_stats: fused column statistics exist in DCGC_GEMM_TF32X3 mode only");
   DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || mode == DCGC_GEMM_TF32X3,
                  "dcgc_group_gemm_fwd: GEMM mode %d is not available in this build", mode);
   DCGC_CHECK_ARG(k1 >= 0 && k2 >= 0 && n >= 0 && n_rows >= 0 && ld_a1 >= k1 && ld_y >= n,
@@ -373,7 +377,7 @@ extern "C" int dcgc_group_gemm_fwd(int32_t mode, const float* a1, int64_t ld_a1,
   DcgcProfScope prof_scope("dcgc_group_gemm_fwd", (cudaStream_t)stream);
   if (mode == DCGC_GEMM_TF32X3)
     return dcgc_tc_gemm(a1, ld_a1, k1, a2, ld_a2, a2 ? k2 : 0, w, tiles ? DCGC_N_DEG : 1, 1, bias, n, 0, tiles, n_tiles,
-                        n_rows, act, y, ld_y, nullptr, 0, (cudaStream_t)stream);
+                        n_rows, act, y, ld_y, nullptr, 0, (cudaStream_t)stream, stats, stats_chunks);
   GemmArgs p{};
   p.a1 = a1; p.ld_a1 = ld_a1; p.k1 = k1;
   p.a2 = a2; p.ld_a2 = ld_a2; p.k2 = a2 ? k2 : 0;
@@ -400,6 +404,26 @@ extern "C" int dcgc_group_gemm_fwd(int32_t mode, const float* a1, int64_t ld_a1,
   DCGC_CUDA_LAUNCH_CHECK("dcgc_group_gemm_fwd");
   return DCGC_OK;
 }
+
+extern "C" int dcgc_group_gemm_fwd(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2,
+                                   int64_t ld_a2, int32_t k2, const float* w, const float* bias, int32_t n,
+                                   const int32_t* tiles, int64_t n_tiles, int32_t tile_rows, int64_t n_rows,
+                                   int32_t act, float* y, int64_t ld_y, void* stream) {
+  return group_gemm_fwd_impl(mode, a1, ld_a1, k1, a2, ld_a2, k2, w, bias, n, tiles, n_tiles, tile_rows, n_rows, act, y,
+                             ld_y, nullptr, nullptr, stream);
+}
+
+extern "C" int dcgc_group_gemm_fwd_stats(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2,
+                                         int64_t ld_a2, int32_t k2, const float* w, const float* bias, int32_t n,
+                                         const int32_t* tiles, int64_t n_tiles, int32_t tile_rows, int64_t n_rows,
+                                         int32_t act, float* y, int64_t ld_y, double* stats_part,
+                                         int32_t* n_chunks_out, void* stream) {
+  DCGC_CHECK_ARG(stats_part && n_chunks_out, "dcgc_group_gemm_fwd_stats: null statistics buffer");
+  return group_gemm_fwd_impl(mode, a1, ld_a1, k1, a2, ld_a2, k2, w, bias, n, tiles, n_tiles, tile_rows, n_rows, act, y,
+                             ld_y, stats_part, n_chunks_out, stream);
+}
+
+extern "C" int32_t dcgc_gemm_stats_max_chunks(void) { return dcgc_tc_num_sms(); }
 
 extern "C" int dcgc_group_gemm_dgrad(int32_t mode, const float* g, int64_t ld_g, int32_t n, const float* w,
                                      int32_t k1, int32_t k2, const int32_t* tiles, int64_t n_tiles,
@@ -554,9 +578,12 @@ extern "C" int dcgc_group_gemm_wgrad(int32_t mode, const float* a1, int64_t ld_a
 // nn.Linear-layout helpers (weight stored [n_out, k_in] as torch does): the atom-level Dense
 // layer (graphconvmodel.py:172,222) and the DMPNN W_i / W_h / W_o (layers.py:1510-1517).
 // ------------------------------------------------------------------------------------------
-extern "C" int dcgc_linear_fwd(int32_t mode, const float* x, int64_t ld_x, int32_t k, const float* w,
-                               const float* bias, int32_t n, int64_t n_rows, int32_t act, float* y, int64_t ld_y,
-                               void* stream) {
+static int linear_fwd_impl(int32_t mode, const float* x, int64_t ld_x, int32_t k, const float* w, const float* bias,
+                           int32_t n, int64_t n_rows, int32_t act, float* y, int64_t ld_y, double* stats,
+                           int32_t* stats_chunks, void* stream) {
+  if (stats_chunks) *stats_chunks = 0;
+  DCGC_CHECK_ARG(stats == nullptr || mode == DCGC_GEMM_TF32X3,
+                 "dcgc_linear_fwd_stats: fused column statistics exist in DCGC_GEMM_TF32X3 mode only");
   DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || mode == DCGC_GEMM_TF32X3,
                  "dcgc_linear_fwd: GEMM mode %d is not available in this build", mode);
   DCGC_CHECK_ARG(k >= 0 && n >= 0 && n_rows >= 0 && ld_x >= k && ld_y >= n, "dcgc_linear_fwd: bad sizes");
@@ -566,7 +593,7 @@ extern "C" int dcgc_linear_fwd(int32_t mode, const float* x, int64_t ld_x, int32
   DcgcProfScope prof_scope("dcgc_linear_fwd", (cudaStream_t)stream);
   if (mode == DCGC_GEMM_TF32X3)
     return dcgc_tc_gemm(x, ld_x, k, nullptr, 0, 0, w, 1, 0, bias, n, 0, nullptr, 0, n_rows, act, y, ld_y, nullptr, 0,
-                        (cudaStream_t)stream);
+                        (cudaStream_t)stream, stats, stats_chunks);
   GemmArgs p{};
   p.a1 = x; p.ld_a1 = ld_x; p.k1 = k;
   p.w = w; p.w_group_stride = 0; p.ld_w = k;
@@ -588,6 +615,19 @@ extern "C" int dcgc_linear_fwd(int32_t mode, const float* x, int64_t ld_x, int32
   }
   DCGC_CUDA_LAUNCH_CHECK("dcgc_linear_fwd");
   return DCGC_OK;
+}
+
+extern "C" int dcgc_linear_fwd(int32_t mode, const float* x, int64_t ld_x, int32_t k, const float* w,
+                               const float* bias, int32_t n, int64_t n_rows, int32_t act, float* y, int64_t ld_y,
+                               void* stream) {
+  return linear_fwd_impl(mode, x, ld_x, k, w, bias, n, n_rows, act, y, ld_y, nullptr, nullptr, stream);
+}
+
+extern "C" int dcgc_linear_fwd_stats(int32_t mode, const float* x, int64_t ld_x, int32_t k, const float* w,
+                                     const float* bias, int32_t n, int64_t n_rows, int32_t act, float* y,
+                                     int64_t ld_y, double* stats_part, int32_t* n_chunks_out, void* stream) {
+  DCGC_CHECK_ARG(stats_part && n_chunks_out, "dcgc_linear_fwd_stats: null statistics buffer");
+  return linear_fwd_impl(mode, x, ld_x, k, w, bias, n, n_rows, act, y, ld_y, stats_part, n_chunks_out, stream);
 }
 
 extern "C" int dcgc_linear_dgrad(int32_t mode, const float* g, int64_t ld_g, int32_t n, const float* w, int32_t k,

@@ -51,6 +51,7 @@ struct TcArgs {
   const int32_t* tiles; int64_t n_rows;
   int act;
   int a1_vec, a2_vec, c1_vec, c2_vec;
+  double* stats;   // optional [ctas][2][n1+n2]: per-CTA column sums of the stored values and of their squares
 };
 
 // ------------------------------------------------------------------------------------------
@@ -576,10 +577,33 @@ __global__ void __launch_bounds__(V2_THREADS, 1) tc_gemm_kernel_v2(const TcArgs2
 //   * double-buffered TMEM accumulators: the epilogue of tile i overlaps the MMAs of tile i+1.
 //   warps 0-3 epilogue | 4-11 A producers | 12 MMA issuer + TMEM | 13 B loader (TMA)
 // ------------------------------------------------------------------------------------------
+
+// A [32 rows x 32 cols] accumulator block arrives from TMEM as (lane = row, v[0..31] = columns).  Storing it
+// directly makes every STG.128 touch 32 different 128-byte lines with 16 bytes each (ncu: 32 half-filled
+// sectors per request, 53 us of a 124 us GEMM).  Transposing through a padded per-warp staging tile gives
+// stores where 8 consecutive lanes cover one full 128-byte line.
+constexpr int EPI_LD = 36;                              // floats per staged row (conflict-free for 128-bit access)
+constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
+constexpr int EPI_BYTES = 4 * EPI_WARP_FLOATS * 4;      // four epilogue warps
+template <typename F>
+__device__ __forceinline__ void warp_transpose_store(float* stg, int lane, const uint32_t (&v)[32], F&& f) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4)
+    *reinterpret_cast<float4*>(stg + lane * EPI_LD + i) =
+        make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+  __syncwarp();
+#pragma unroll
+  for (int i2 = 0; i2 < 8; ++i2) {
+    const int rr = i2 * 4 + (lane >> 3), cc = 4 * (lane & 7);
+    f(rr, cc, *reinterpret_cast<const float4*>(stg + rr * EPI_LD + cc));
+  }
+  __syncwarp();
+}
+
 constexpr int V3_THREADS = 14 * 32;
 constexpr int V3_STAGES = 3;
 constexpr int V3_STAGE_BYTES = 4 * TC_TILE_BYTES;   // A hi, A lo, B hi, B lo
-constexpr int V3_SMEM_BYTES = V3_STAGES * V3_STAGE_BYTES + 1024 + 256;
+constexpr int V3_SMEM_BYTES = V3_STAGES * V3_STAGE_BYTES + 1024 + 256 + EPI_BYTES;
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -595,28 +619,35 @@ struct ImgArgs {
   int n, k1, k2, k1_pad, trans, src_ld, n_tiles, chunks;
 };
 __global__ void __launch_bounds__(256) tc_prep_image(const ImgArgs p) {
-  const int g = blockIdx.z, nt = blockIdx.y, ch = blockIdx.x;
+  // one block = a quarter (1024 elements) of one [128 x 32] tile; 4 independent loads per thread
+  const int g = blockIdx.z, nt = blockIdx.y, ch = blockIdx.x >> 2, quarter = blockIdx.x & 3;
   float* blk = p.img + (((int64_t)g * p.n_tiles + nt) * p.chunks + ch) * (2 * TC_BM * TC_BK);
-  for (int i = threadIdx.x; i < TC_BN * TC_BK; i += 256) {
-    int r, kl;
-    if (p.trans) { r = i & (TC_BN - 1); kl = i >> 7; }     // source is n-contiguous
-    else { kl = i & (TC_BK - 1); r = i >> 5; }             // source is k-contiguous
-    const int nn = nt * TC_BN + r, kk = ch * TC_BK + kl;
-    float v = 0.f;
+  float v[4];
+  int r[4], kl[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = quarter * 1024 + u * 256 + threadIdx.x;
+    if (p.trans) { r[u] = i & (TC_BN - 1); kl[u] = i >> 7; }     // source is n-contiguous
+    else { kl[u] = i & (TC_BK - 1); r[u] = i >> 5; }             // source is k-contiguous
+    const int nn = nt * TC_BN + r[u], kk = ch * TC_BK + kl[u];
+    v[u] = 0.f;
     if (nn < p.n) {
       if (p.trans) {
         int ks = -1;
         if (kk < p.k1_pad) { if (kk < p.k1) ks = kk; }
         else if (kk - p.k1_pad < p.k2) ks = p.k1 + (kk - p.k1_pad);
-        if (ks >= 0) v = __ldg(p.src + g * p.src_group_stride + (int64_t)ks * p.src_ld + nn);
+        if (ks >= 0) v[u] = __ldg(p.src + g * p.src_group_stride + (int64_t)ks * p.src_ld + nn);
       } else if (kk < p.k1) {
-        v = __ldg(p.src + g * p.src_group_stride + (int64_t)nn * p.src_ld + kk);
+        v[u] = __ldg(p.src + g * p.src_group_stride + (int64_t)nn * p.src_ld + kk);
       }
     }
-    const float h = tf32_hi(v);
-    const uint32_t o = (swz(r, kl >> 2) >> 2) + (kl & 3);   // float index inside the 16 KB tile
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float h = tf32_hi(v[u]);
+    const uint32_t o = (swz(r[u], kl[u] >> 2) >> 2) + (kl[u] & 3);   // float index inside the 16 KB tile
     blk[o] = h;
-    blk[TC_BM * TC_BK + o] = v - h;
+    blk[TC_BM * TC_BK + o] = v[u] - h;
   }
 }
 
@@ -624,6 +655,9 @@ struct TcArgs3 {
   TcArgs a;
   const float* img;
   int n_row_tiles, n_tiles_n;
+  int knockout;   // debugging aid (env DCGC_TC_KNOCKOUT): 1 no output stores, 2 no MMAs, 4 no A loads,
+                  // 8 no weight copies, 16 no A shared-memory stores, 32 no TMEM loads, 64 no proxy fence,
+                  // 128 no weight-image kernel — results are wrong, timing only
 };
 
 __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3 q) {
@@ -676,24 +710,26 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int f = gt + u * TC_GROUP_THREADS, r_ = f >> 3, k = kbase + 4 * (f & 7);
-        r[u] = r_ < rows ? ld4_masked(src + (int64_t)(row0 + r_) * ld + k, ksrc - k, vec)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        r[u] = (r_ < rows && !(q.knockout & 4)) ? ld4_masked(src + (int64_t)(row0 + r_) * ld + k, ksrc - k, vec)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     auto commit = [&](const float4 (&r)[8], int cc) {
       const int s = cc % S, use = cc / S;
       mbar_wait(bar_base + 32 + 8 * s, (use & 1) ^ 1);
       uint8_t* st = sm + s * V3_STAGE_BYTES;
+      if (!(q.knockout & 16)) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int f = gt + u * TC_GROUP_THREADS;
-        const uint32_t o = swz(f >> 3, f & 7);
-        float4 hi, lo;
-        split4(r[u], hi, lo);
-        *reinterpret_cast<float4*>(st + o) = hi;
-        *reinterpret_cast<float4*>(st + TC_TILE_BYTES + o) = lo;
+        for (int u = 0; u < 8; ++u) {
+          const int f = gt + u * TC_GROUP_THREADS;
+          const uint32_t o = swz(f >> 3, f & 7);
+          float4 hi, lo;
+          split4(r[u], hi, lo);
+          *reinterpret_cast<float4*>(st + o) = hi;
+          *reinterpret_cast<float4*>(st + TC_TILE_BYTES + o) = lo;
+        }
       }
-      fence_proxy_async();
+      if (!(q.knockout & 64)) fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_base + 8 * s);
     };
@@ -716,6 +752,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
         for (int ch = 0; ch < total; ++ch, ++cc) {
           const int s = cc % S, use = cc / S;
           mbar_wait(bar_base + 32 + 8 * s, (use & 1) ^ 1);
+          if (q.knockout & 8) { mbar_arrive(bar_base + 8 * s); continue; }
           mbar_arrive_expect_tx(bar_base + 8 * s, 2 * TC_TILE_BYTES);
           bulk_g2s(base + s * V3_STAGE_BYTES + 2 * TC_TILE_BYTES, src + (int64_t)ch * (2 * TC_BM * TC_BK),
                    2 * TC_TILE_BYTES, bar_base + 8 * s);
@@ -736,14 +773,16 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
           mbar_wait(bar_base + 8 * s, (cc / S) & 1);
           tc_fence_after();
           const uint32_t sa = base + s * V3_STAGE_BYTES;
+          if (!(q.knockout & 2)) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / TC_UK; ++k) {
-            const uint32_t ko = k * TC_UK * 4;
-            const uint64_t ahi = make_desc(sa + ko), alo = make_desc(sa + TC_TILE_BYTES + ko);
-            const uint64_t bhi = make_desc(sa + 2 * TC_TILE_BYTES + ko), blo = make_desc(sa + 3 * TC_TILE_BYTES + ko);
-            umma_tf32(d, alo, bhi, kIdescTf32, (ch | k) != 0);
-            umma_tf32(d, ahi, blo, kIdescTf32, 1);
-            umma_tf32(d, ahi, bhi, kIdescTf32, 1);
+            for (int k = 0; k < TC_BK / TC_UK; ++k) {
+              const uint32_t ko = k * TC_UK * 4;
+              const uint64_t ahi = make_desc(sa + ko), alo = make_desc(sa + TC_TILE_BYTES + ko);
+              const uint64_t bhi = make_desc(sa + 2 * TC_TILE_BYTES + ko), blo = make_desc(sa + 3 * TC_TILE_BYTES + ko);
+              umma_tf32(d, alo, bhi, kIdescTf32, (ch | k) != 0);
+              umma_tf32(d, ahi, blo, kIdescTf32, 1);
+              umma_tf32(d, ahi, bhi, kIdescTf32, 1);
+            }
           }
           umma_commit(bar_base + 32 + 8 * s);
         }
@@ -752,55 +791,109 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
     }
   } else {
     // ===================== epilogue (warps 0-3) =====================
+    float* stg = reinterpret_cast<float*>(sm + S * V3_STAGE_BYTES + 256) + warp * EPI_WARP_FLOATS;
+    // fused BatchNorm statistics: this lane's column sums over the rows it stores (16 columns: 4 per 32-column
+    // block), fp32 over at most a few dozen rows, float64 from the cross-lane reduction on
+    // (four separate register sets, selected by a branch: one array indexed by the run-time block number
+    // was demoted to local memory by the compiler)
+    float su0[4] = {0.f, 0.f, 0.f, 0.f}, su1[4] = {0.f, 0.f, 0.f, 0.f}, su2[4] = {0.f, 0.f, 0.f, 0.f},
+          su3[4] = {0.f, 0.f, 0.f, 0.f};
+    float sq0[4] = {0.f, 0.f, 0.f, 0.f}, sq1[4] = {0.f, 0.f, 0.f, 0.f}, sq2[4] = {0.f, 0.f, 0.f, 0.f},
+          sq3[4] = {0.f, 0.f, 0.f, 0.f};
     for (int it = 0; it < my_tiles; ++it) {
       int row0, rows, g;
       tile_of(p, pid + it * P, row0, rows, g);
+      if (q.knockout & 1) rows = 0;
       const int acc = it & 1;
       if (total > 0) {
         mbar_wait(bar_base + 64 + 8 * acc, (it >> 1) & 1);
         tc_fence_after();
       }
       const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_group_stride : nullptr;
-      const int row = warp * 32 + lane;
-      const int64_t grow = row0 + row;
-#pragma unroll 1
+#pragma unroll 1   // (fully unrolled, the 32 copies of the store body overflowed the instruction cache: 2x slower)
       for (int cb = 0; cb < TC_BN; cb += 32) {
         uint32_t v[32];
-        if (total > 0) {
+        float ts[4] = {0.f, 0.f, 0.f, 0.f}, tq[4] = {0.f, 0.f, 0.f, 0.f};
+        if (total > 0 && !(q.knockout & 32)) {
           tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + acc * TC_BN + cb, v);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
-        if (row < rows) {
+        const int c = n0 + cb + 4 * (lane & 7);       // the 4 columns this lane stores
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (bias) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const int c = n0 + cb + i;
-            if (c >= N) break;
-            float o[4];
+          for (int e = 0; e < 4; ++e)
+            if (c + e < N) bv[e] = __ldg(bias + c + e);
+        }
+        warp_transpose_store(stg, lane, v, [&](int rr, int, float4 t) {
+          const int row = warp * 32 + rr;
+          if (row >= rows || c >= N) return;
+          const int64_t grow = row0 + row;
+          const float o[4] = {tc_act(t.x + bv[0], p.act), tc_act(t.y + bv[1], p.act), tc_act(t.z + bv[2], p.act),
+                              tc_act(t.w + bv[3], p.act)};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { ts[e] += o[e]; tq[e] = fmaf(o[e], o[e], tq[e]); }
+          if (c + 3 < p.n1 && p.c1_vec) {
+            *reinterpret_cast<float4*>(p.c1 + grow * p.ld_c1 + c) = make_float4(o[0], o[1], o[2], o[3]);
+          } else if (c >= p.n1 && c + 3 < N && p.c2_vec && ((c - p.n1) & 3) == 0) {
+            *reinterpret_cast<float4*>(p.c2 + grow * p.ld_c2 + (c - p.n1)) = make_float4(o[0], o[1], o[2], o[3]);
+          } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float t = __uint_as_float(v[i + e]);
-              if (bias && c + e < N) t += __ldg(bias + c + e);
-              o[e] = tc_act(t, p.act);
-            }
-            if (c + 3 < p.n1 && p.c1_vec) {
-              *reinterpret_cast<float4*>(p.c1 + grow * p.ld_c1 + c) = make_float4(o[0], o[1], o[2], o[3]);
-            } else if (c >= p.n1 && c + 3 < N && p.c2_vec && ((c - p.n1) & 3) == 0) {
-              *reinterpret_cast<float4*>(p.c2 + grow * p.ld_c2 + (c - p.n1)) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int cc2 = c + e;
-                if (cc2 < p.n1) { if (p.c1) p.c1[grow * p.ld_c1 + cc2] = o[e]; }
-                else if (cc2 < N) { if (p.c2) p.c2[grow * p.ld_c2 + (cc2 - p.n1)] = o[e]; }
-              }
+              const int cc2 = c + e;
+              if (cc2 < p.n1) { if (p.c1) p.c1[grow * p.ld_c1 + cc2] = o[e]; }
+              else if (cc2 < N) { if (p.c2) p.c2[grow * p.ld_c2 + (cc2 - p.n1)] = o[e]; }
             }
           }
-        }
+        });
+        // fold this block's sums into the statically indexed accumulators (cb is a run-time value here)
+#define DCGC_FOLD(SU, SQ)                                  \
+  {                                                        \
+    _Pragma("unroll") for (int e = 0; e < 4; ++e) {        \
+      SU[e] += ts[e];                                      \
+      SQ[e] += tq[e];                                      \
+    }                                                      \
+  }
+        if (cb == 0) DCGC_FOLD(su0, sq0)
+        else if (cb == 32) DCGC_FOLD(su1, sq1)
+        else if (cb == 64) DCGC_FOLD(su2, sq2)
+        else DCGC_FOLD(su3, sq3)
+#undef DCGC_FOLD
       }
       tc_fence_before();
       mbar_arrive(bar_base + 80 + 8 * acc);
+    }
+    if (p.stats) {
+      // lanes l, l+8, l+16, l+24 hold the same columns (different rows): fixed-order butterfly, then the four
+      // epilogue warps are combined in warp order through shared memory (deterministic)
+      double* shd = reinterpret_cast<double*>(sm + S * V3_STAGE_BYTES + 256);   // [4 warps][2][128]
+      named_bar_sync(2, 128);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float* su = (i >> 2) == 0 ? su0 : ((i >> 2) == 1 ? su1 : ((i >> 2) == 2 ? su2 : su3));
+        const float* sq = (i >> 2) == 0 ? sq0 : ((i >> 2) == 1 ? sq1 : ((i >> 2) == 2 ? sq2 : sq3));
+        double a = (double)su[i & 3], b = (double)sq[i & 3];
+        a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
+        a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
+        if (lane < 8) {
+          const int col = (i >> 2) * 32 + 4 * lane + (i & 3);
+          shd[(warp * 2 + 0) * TC_BN + col] = a;
+          shd[(warp * 2 + 1) * TC_BN + col] = b;
+        }
+      }
+      named_bar_sync(2, 128);
+      const int col = warp * 32 + lane;
+      if (n0 + col < N) {
+#pragma unroll
+        for (int qn = 0; qn < 2; ++qn) {
+          double t = 0.0;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) t += shd[(w * 2 + qn) * TC_BN + col];
+          p.stats[((int64_t)pid * 2 + qn) * N + n0 + col] = t;
+        }
+      }
     }
   }
   tc_fence_before();
@@ -990,10 +1083,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
       tc_fence_after();
     }
     const bool n_vec = (p.n & 3) == 0 && (reinterpret_cast<uintptr_t>(p.ws) & 15) == 0;
+    float* stg = reinterpret_cast<float*>(sm + WG_STAGES * STAGE_BYTES + 256) + warp * EPI_WARP_FLOATS;
 #pragma unroll 1
     for (int t = 0; t < MT; ++t) {
-      const int m = m0 + t * TC_BM + warp * 32 + lane;
-      float* dst = p.ws + ((int64_t)chunk * Kt + m) * p.n;
+      const int mbase = m0 + t * TC_BM + warp * 32;
 #pragma unroll 1
       for (int cb = 0; cb < TC_BN; cb += 32) {
         uint32_t v[32];
@@ -1003,20 +1096,20 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
-        if (m < Kt) {
+        const int c = n0 + cb + 4 * (lane & 7);
+        warp_transpose_store(stg, lane, v, [&](int rr, int, float4 o) {
+          const int m = mbase + rr;
+          if (m >= Kt || c >= p.n) return;
+          float* dst = p.ws + ((int64_t)chunk * Kt + m) * p.n + c;
+          if (c + 3 < p.n && n_vec) {
+            *reinterpret_cast<float4*>(dst) = o;
+          } else {
+            const float e[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const int c = n0 + cb + i;
-            if (c + 3 < p.n && n_vec) {
-              *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                                                                __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (c + e < p.n) dst[c + e] = __uint_as_float(v[i + e]);
-            }
+            for (int q = 0; q < 4; ++q)
+              if (c + q < p.n) dst[q] = e[q];
           }
-        }
+        });
       }
     }
   }
@@ -1084,10 +1177,12 @@ int ensure_smem_attr() {
 //   trans_w = 1: w is [G][k1+k2][n] (forward);  trans_w = 0: w is [G][n1+n2][k1] (dgrad / nn.Linear forward)
 int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_t ld_a2, int k2, const float* w,
                  int n_groups, int trans_w, const float* bias, int n1, int n2, const int32_t* tiles, int64_t n_tiles,
-                 int64_t n_rows, int act, float* c1, int64_t ld_c1, float* c2, int64_t ld_c2, cudaStream_t st) {
+                 int64_t n_rows, int act, float* c1, int64_t ld_c1, float* c2, int64_t ld_c2, cudaStream_t st,
+                 double* stats, int* stats_chunks) {
   const int N = n1 + n2;
+  if (stats_chunks) *stats_chunks = 0;
   const int64_t row_tiles = tiles ? n_tiles : (n_rows + TC_BM - 1) / TC_BM;
-  if (row_tiles == 0 || N == 0) return DCGC_OK;
+  if (row_tiles == 0 || N == 0) return DCGC_OK;   // *stats_chunks == 0: the caller's finalize sees no partials
   int st_ = ensure_smem_attr();
   if (st_ != DCGC_OK) return st_;
   const int k1_pad = (k1 + TC_BK - 1) / TC_BK * TC_BK, k2_pad = (k2 + TC_BK - 1) / TC_BK * TC_BK;
@@ -1098,13 +1193,14 @@ int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_
     float* img = nullptr;
     st_ = prep_scratch(st, (size_t)n_groups * n_tiles_n * (chunks > 0 ? chunks : 1) * 2 * TC_TILE_BYTES, &img);
     if (st_ != DCGC_OK) return st_;
-    if (chunks > 0) {
+    static const int knockout = [] { const char* e = getenv("DCGC_TC_KNOCKOUT"); return e ? atoi(e) : 0; }();
+    if (chunks > 0 && !(knockout & 128)) {
       ImgArgs ia{};
       ia.src = w; ia.img = img; ia.n = N; ia.k1 = k1; ia.k2 = a2 ? k2 : 0; ia.k1_pad = k1_pad; ia.trans = trans_w;
       ia.n_tiles = n_tiles_n; ia.chunks = chunks;
       if (trans_w) { ia.src_ld = N; ia.src_group_stride = (int64_t)(k1 + k2) * N; }
       else { ia.src_ld = k1; ia.src_group_stride = (int64_t)N * k1; }
-      dim3 pgrid((unsigned)chunks, (unsigned)n_tiles_n, (unsigned)n_groups);
+      dim3 pgrid((unsigned)chunks * 4, (unsigned)n_tiles_n, (unsigned)n_groups);
       tc_prep_image<<<pgrid, 256, 0, st>>>(ia);
       DCGC_CUDA_LAUNCH_CHECK("tc_prep_image");
     }
@@ -1120,9 +1216,12 @@ int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_
     p3.c1_vec = c1 && ld_c1 % 4 == 0 && aligned16(c1);
     p3.c2_vec = c2 && ld_c2 % 4 == 0 && aligned16(c2);
     q3.img = img; q3.n_row_tiles = (int)row_tiles; q3.n_tiles_n = n_tiles_n;
+    q3.knockout = knockout;
     int ctas = g_num_sms / n_tiles_n;
     if (ctas < 1) ctas = 1;
     if (ctas > row_tiles) ctas = (int)row_tiles;
+    p3.stats = stats;
+    if (stats_chunks) *stats_chunks = ctas;
     dim3 grid((unsigned)ctas, (unsigned)n_tiles_n);
     tc_gemm_kernel_v3<<<grid, V3_THREADS, V3_SMEM_BYTES, st>>>(q3);
     DCGC_CUDA_LAUNCH_CHECK("tc_gemm_kernel_v3");
@@ -1143,6 +1242,10 @@ int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_
     dim3 grid((unsigned)((gstride + 255) / 256), (unsigned)n_groups);
     tc_prep_weights<<<grid, 256, 0, st>>>(q);
     DCGC_CUDA_LAUNCH_CHECK("tc_prep_weights");
+  }
+  if (stats) {
+    dcgc_set_error("dcgc_tc_gemm: fused column statistics need kernel variant 3");
+    return DCGC_ERR_INVALID;
   }
   TcArgs p{};
   p.a1 = a1; p.ld_a1 = ld_a1; p.k1 = k1;
@@ -1204,7 +1307,7 @@ int dcgc_tc_wgrad_stage1(const DcgcWgradArgs& p_in, int chunks, cudaStream_t st)
   p.tiles_n = (p.n + TC_BN - 1) / TC_BN;
   const int m_pairs = (Kt + mt * TC_BM - 1) / (mt * TC_BM);
   dim3 grid((unsigned)chunks, (unsigned)(m_pairs * p.tiles_n));
-  const int smem = WG_STAGES * (2 * mt + 2) * TC_TILE_BYTES + 1024 + 256;
+  const int smem = WG_STAGES * (2 * mt + 2) * TC_TILE_BYTES + 1024 + 256 + EPI_BYTES;
   if (mt == 2) tc_wgrad_kernel<2><<<grid, WG_THREADS, smem, st>>>(p);
   else tc_wgrad_kernel<1><<<grid, WG_THREADS, smem, st>>>(p);
   DCGC_CUDA_LAUNCH_CHECK("tc_wgrad_kernel");

@@ -201,6 +201,9 @@ pool_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy, const uint8_t* __re
   }
 }
 
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
 // ------------------------------------------------------------------------------------------
 // K4: GraphGather.  One thread owns one 16-byte column group of one molecule and walks the
 // molecule's rows in ascending order (the order CPU scatter_add accumulates in,
@@ -282,6 +285,30 @@ gather_bwd_kernel(const float* __restrict__ dout, int64_t ld_dout, const float* 
       d += __ldg(dout + g * ld_dout + width + cc) * act_grad_from_out(__ldg(out + g * ld_out + width + cc), act);
     dx[row * ld_dx + cc] = d;
   }
+}
+
+
+// vectorised GraphGather backward: one thread = 4 columns of one atom row; the per-molecule
+// operands (dout, out, argrow: shared by the ~25 atoms of a molecule) come as 128-bit loads
+__global__ void __launch_bounds__(kThreads)
+gather_bwd_vec_kernel(const float* __restrict__ dout, int64_t ld_dout, const float* __restrict__ out,
+                      int64_t ld_out, const int32_t* __restrict__ argrow, const int32_t* __restrict__ membership,
+                      int64_t n_rows, int groups, int width, int act, float* __restrict__ dx, int64_t ld_dx) {
+  const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t row = t / groups;
+  const int c = (int)(t - row * groups) * 4;
+  if (row >= n_rows) return;
+  const int64_t g = __ldg(membership + row);
+  const float4 ds = ldg4(dout + g * ld_dout + c), os = ldg4(out + g * ld_out + c);
+  const float4 dm = ldg4(dout + g * ld_dout + width + c), om = ldg4(out + g * ld_out + width + c);
+  const int4 ar = __ldg(reinterpret_cast<const int4*>(argrow + g * (int64_t)width + c));
+  const int r32 = (int)row;
+  float4 o;
+  o.x = ds.x * act_grad_from_out(os.x, act) + (ar.x == r32 ? dm.x * act_grad_from_out(om.x, act) : 0.f);
+  o.y = ds.y * act_grad_from_out(os.y, act) + (ar.y == r32 ? dm.y * act_grad_from_out(om.y, act) : 0.f);
+  o.z = ds.z * act_grad_from_out(os.z, act) + (ar.z == r32 ? dm.z * act_grad_from_out(om.z, act) : 0.f);
+  o.w = ds.w * act_grad_from_out(os.w, act) + (ar.w == r32 ? dm.w * act_grad_from_out(om.w, act) : 0.f);
+  *reinterpret_cast<float4*>(dx + row * ld_dx + c) = o;
 }
 
 }  // namespace
@@ -424,8 +451,14 @@ extern "C" int dcgc_gather_bwd(const float* dout, int64_t ld_dout, const float* 
   DCGC_CHECK_ARG(dout && out && argrow && membership && dx, "dcgc_gather_bwd: null pointer");
   DcgcProfScope prof_scope("dcgc_gather_bwd", (cudaStream_t)stream);
   const int groups = (width + 3) / 4;
-  gather_bwd_kernel<4><<<grid_for(n_rows * groups), kThreads, 0, (cudaStream_t)stream>>>(
-      dout, ld_dout, out, ld_out, argrow, membership, n_rows, groups, width, act, dx, ld_dx);
+  const bool v4 = width % 4 == 0 && ld_dout % 4 == 0 && ld_out % 4 == 0 && ld_dx % 4 == 0 && aligned16(dout) &&
+                  aligned16(out) && aligned16(dx) && aligned16(argrow);
+  if (v4)
+    gather_bwd_vec_kernel<<<grid_for(n_rows * groups), kThreads, 0, (cudaStream_t)stream>>>(
+        dout, ld_dout, out, ld_out, argrow, membership, n_rows, groups, width, act, dx, ld_dx);
+  else
+    gather_bwd_kernel<4><<<grid_for(n_rows * groups), kThreads, 0, (cudaStream_t)stream>>>(
+        dout, ld_dout, out, ld_out, argrow, membership, n_rows, groups, width, act, dx, ld_dx);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_gather_bwd");
   return DCGC_OK;
 }

@@ -38,6 +38,12 @@ inline int64_t mom_rows(int64_t n, int chunks) {
   return (r + kMomLanes - 1) / kMomLanes * kMomLanes;
 }
 
+// rows of the statistics workspace: enough for our own stage 1 and for the GEMM-epilogue partials
+inline int part_chunks(int64_t n) {
+  const int a = mom_chunks(n), b = dcgc_gemm_stats_max_chunks();
+  return a > b ? a : b;
+}
+
 // block: 32 column lanes (float4 -> 128 columns) x 16 row lanes walking rows r0+ry, r0+ry+16, ...;
 // 4 independent 128-bit loads per tensor in flight per thread; fp32 partials over 4 rows, float64 from
 // there on (fixed order => deterministic).
@@ -474,8 +480,10 @@ int check_topo(const dcgc_topology* t) {
     if (st__ != DCGC_OK) return st__; \
   } while (0)
 
+// fused_chunks >= 0: the stage-1 partials were already written by the GEMM epilogue (dcgc_*_fwd_stats)
 int bn_forward(const dcgc_gcmodel_config* cfg, const Layout& lo, int idx, const float* y, int64_t ld_y, int64_t n,
-               int width, const float* params, float* bn_running, int training, Saved& sv, cudaStream_t st) {
+               int width, const float* params, float* bn_running, int training, Saved& sv, cudaStream_t st,
+               int fused_chunks = -1) {
   float* stats = sv.stats + sv.stats_off[idx];
   float *mean = stats, *invstd = stats + width, *scale = stats + 2 * width, *shift = stats + 3 * width;
   const float* gamma = params + lo.bn_g[idx];
@@ -484,15 +492,18 @@ int bn_forward(const dcgc_gcmodel_config* cfg, const Layout& lo, int idx, const 
   float* rv = bn_running ? bn_running + lo.bn_var[idx] : nullptr;
   DcgcProfScope prof_scope("bn_stats_fwd", st);
   if (training) {
-    if (n > 0) {
-      dim3 grid((unsigned)sv.n_chunks, (unsigned)((width + 127) / 128));
-      col_moments_partial<<<grid, 32 * kMomLanes, 0, st>>>(y, ld_y, y, ld_y, n, width, mom_rows(n, sv.n_chunks),
-                                                           sv.part);
-      DCGC_CUDA_LAUNCH_CHECK("col_moments_partial");
+    int chunks = fused_chunks;
+    if (chunks < 0) {
+      chunks = n > 0 ? sv.n_chunks : 0;
+      if (n > 0) {
+        dim3 grid((unsigned)sv.n_chunks, (unsigned)((width + 127) / 128));
+        col_moments_partial<<<grid, 32 * kMomLanes, 0, st>>>(y, ld_y, y, ld_y, n, width, mom_rows(n, sv.n_chunks),
+                                                             sv.part);
+        DCGC_CUDA_LAUNCH_CHECK("col_moments_partial");
+      }
     }
-    bn_fwd_finalize<<<(width + 7) / 8, 256, 0, st>>>(sv.part, n > 0 ? sv.n_chunks : 0, width, n, gamma, beta,
-                                                         cfg->bn_eps, cfg->bn_momentum, rm, rv, mean, invstd, scale,
-                                                         shift);
+    bn_fwd_finalize<<<(width + 7) / 8, 256, 0, st>>>(sv.part, chunks, width, n, gamma, beta, cfg->bn_eps,
+                                                       cfg->bn_momentum, rm, rv, mean, invstd, scale, shift);
     DCGC_CUDA_LAUNCH_CHECK("bn_fwd_finalize");
   } else {
     DCGC_CHECK_ARG(rm && rv, "dcgc_gcmodel: eval-mode BatchNorm needs the running statistics");
@@ -514,7 +525,7 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
   sv.n_chunks = mom_chunks(N);
   int wmax = D;
   for (int l = 0; l < L; ++l) wmax = wmax > cfg->widths[l] ? wmax : cfg->widths[l];
-  sv.part = ws.take<double>((int64_t)(sv.n_chunks > 0 ? sv.n_chunks : 1) * 2 * wmax);
+  sv.part = ws.take<double>((int64_t)part_chunks(N) * 2 * wmax);
   int64_t so = 0;
   for (int l = 0; l <= L; ++l) { sv.stats_off[l] = so; so += 4 * (int64_t)(l < L ? cfg->widths[l] : D); }
   sv.stats = ws.take<float>(so);
@@ -544,11 +555,17 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
     conv_bias_pack<<<blocks_for(DCGC_N_DEG * c), kT, 0, st>>>(params + lo.conv_b[l], c, sv.b11[l]);
     DCGC_CUDA_LAUNCH_CHECK("conv_bias_pack");
     RET_IF(dcgc_gather_sum(h, ld, t->row_ptr, t->col_idx, N, fp, nullptr, 0, sv.s[l], fp, st));
-    RET_IF(dcgc_group_gemm_fwd(cfg->gemm_mode, h, ld, fp, sv.s[l], fp, fp, params + lo.conv_w[l], sv.b11[l], c,
-                               t->tiles, t->n_tiles, 128, N, DCGC_ACT_RELU, sv.y[l], c, st));
+    const bool fuse_stats = cfg->batch_norm && training && cfg->gemm_mode == DCGC_GEMM_TF32X3;
+    int32_t fused = -1;
+    if (fuse_stats)
+      RET_IF(dcgc_group_gemm_fwd_stats(cfg->gemm_mode, h, ld, fp, sv.s[l], fp, fp, params + lo.conv_w[l], sv.b11[l], c,
+                                       t->tiles, t->n_tiles, 128, N, DCGC_ACT_RELU, sv.y[l], c, sv.part, &fused, st));
+    else
+      RET_IF(dcgc_group_gemm_fwd(cfg->gemm_mode, h, ld, fp, sv.s[l], fp, fp, params + lo.conv_w[l], sv.b11[l], c,
+                                 t->tiles, t->n_tiles, 128, N, DCGC_ACT_RELU, sv.y[l], c, st));
     const float *scale = nullptr, *shift = nullptr;
     if (cfg->batch_norm) {
-      RET_IF(bn_forward(cfg, lo, l, sv.y[l], c, N, c, params, bn_running, training, sv, st));
+      RET_IF(bn_forward(cfg, lo, l, sv.y[l], c, N, c, params, bn_running, training, sv, st, fused));
       scale = sv.stats + sv.stats_off[l] + 2 * c;
       shift = scale + c;
     }
@@ -556,11 +573,16 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
                          sv.arg[l], c, st));
   }
   // ---- atom-level dense + ReLU (+BN folded into the gather), GraphGather(tanh), head
-  RET_IF(dcgc_linear_fwd(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], params + lo.dense_w, params + lo.dense_b, D, N,
-                         DCGC_ACT_RELU, sv.z, D, st));
+  int32_t fused_d = -1;
+  if (cfg->batch_norm && training && cfg->gemm_mode == DCGC_GEMM_TF32X3)
+    RET_IF(dcgc_linear_fwd_stats(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], params + lo.dense_w,
+                                 params + lo.dense_b, D, N, DCGC_ACT_RELU, sv.z, D, sv.part, &fused_d, st));
+  else
+    RET_IF(dcgc_linear_fwd(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], params + lo.dense_w, params + lo.dense_b, D,
+                           N, DCGC_ACT_RELU, sv.z, D, st));
   const float *scale = nullptr, *shift = nullptr;
   if (cfg->batch_norm) {
-    RET_IF(bn_forward(cfg, lo, L, sv.z, D, N, D, params, bn_running, training, sv, st));
+    RET_IF(bn_forward(cfg, lo, L, sv.z, D, N, D, params, bn_running, training, sv, st, fused_d));
     scale = sv.stats + sv.stats_off[L] + 2 * D;
     shift = scale + D;
   }
@@ -618,7 +640,7 @@ extern "C" int64_t dcgc_gcmodel_workspace_bytes(const dcgc_gcmodel_config* cfg, 
   int64_t bytes = n_atoms * per_atom * 4;
   bytes += n_segments * (int64_t)(2 * D * 2 + D) * 4;            // fp, dfp, argrow
   bytes += n_segments * (int64_t)cfg->n_out * 4 * 3;              // out, dout, per-element loss
-  bytes += (int64_t)(mom_chunks(n_atoms) + 1) * 2 * (int64_t)wmax * 8;
+  bytes += (int64_t)(part_chunks(n_atoms) + 1) * 2 * (int64_t)wmax * 8;
   bytes += ((n_segments + kHeadChunk - 1) / kHeadChunk + 1) * (int64_t)cfg->n_out * (2 * D + 1) * 4;
   int64_t wg = 0;
   for (int l = 0; l < L; ++l) {

@@ -294,6 +294,10 @@ class GraphConvModel(object):
         self._prefetch_stream = None
         self._staging = []          # ring of reusable pinned slabs: [tensor, event]
         self._staging_next = 0
+        import threading
+        self._staging_lock = threading.Lock()
+        # host threads building batch layouts ahead of the GPU (default_generator)
+        self.host_workers = int(os.environ.get("DCGC_HOST_WORKERS", max(1, min(4, (os.cpu_count() or 2) // 2))))
         # fused whole-model engine (flat parameter slab, one C call per step) when the model shape
         # allows it; otherwise the per-layer autograd ops are used.
         self._engine = None
@@ -304,38 +308,66 @@ class GraphConvModel(object):
         self.number_atom_features = number_atom_features
 
     # ------------------------------------------------------------------ batching
-    def default_generator(self, dataset, epochs=1, mode='fit', deterministic=True, pad_batches=True):
+    def default_generator(self, dataset, epochs=1, mode='fit', deterministic=True, pad_batches=True,
+                          workers=None):
         """Dataset -> (inputs, [y], [w]) per batch (graphconvmodel.py:382-422).  The layout comes
-        from the C++ builder instead of ConvMol.agglomerate_mols."""
-        for (X_b, y_b, w_b, ids_b) in dataset.iterbatches(batch_size=self.batch_size, epochs=epochs,
-                                                          deterministic=deterministic,
-                                                          pad_batches=pad_batches):
-            if y_b is not None and self.mode == 'classification' and not (mode == 'predict'):
-                y_b = to_one_hot(np.asarray(y_b).flatten(), self.n_classes).reshape(
-                    -1, self.n_tasks, self.n_classes)
-            yield (self.batch_inputs(X_b), [y_b], [w_b])
+        from the C++ builder instead of ConvMol.agglomerate_mols.  ``workers`` > 1 builds the layouts
+        of upcoming batches concurrently on a thread pool (the C builder releases the GIL); batches
+        are still yielded in dataset order."""
+        if workers is None:
+            workers = self.host_workers
+
+        def batches():
+            for (X_b, y_b, w_b, ids_b) in dataset.iterbatches(batch_size=self.batch_size, epochs=epochs,
+                                                              deterministic=deterministic,
+                                                              pad_batches=pad_batches):
+                if y_b is not None and self.mode == 'classification' and not (mode == 'predict'):
+                    y_b = to_one_hot(np.asarray(y_b).flatten(), self.n_classes).reshape(
+                        -1, self.n_tasks, self.n_classes)
+                yield X_b, y_b, w_b
+
+        if workers <= 1:
+            for X_b, y_b, w_b in batches():
+                yield (self.batch_inputs(X_b), [y_b], [w_b])
+            return
+        import collections
+        from concurrent.futures import ThreadPoolExecutor
+        pending = collections.deque()
+        with ThreadPoolExecutor(max_workers=workers, thread_name_prefix="dcgc-layout") as pool:
+            for X_b, y_b, w_b in batches():
+                pending.append((pool.submit(self.batch_inputs, X_b), y_b, w_b))
+                if len(pending) > workers:
+                    fut, y0, w0 = pending.popleft()
+                    yield (fut.result(), [y0], [w0])
+            while pending:
+                fut, y0, w0 = pending.popleft()
+                yield (fut.result(), [y0], [w0])
 
     def _staging_slab(self, nbytes):
         """Next pinned staging buffer of the ring (page-locked allocations are expensive, so they are
-        made once and reused; a slot is reused only after the H2D copy that read it has finished)."""
-        ring = 6
-        if len(self._staging) < ring:
-            self._staging.append([torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True), None])
-            slot = self._staging[-1]
-        else:
+        made once and reused; a slot is reused only after the H2D copy that read it has finished).
+        The ring is longer than the deepest host pipeline (layout workers + prefetch queue), so a
+        slot is never handed out again before its previous batch has been uploaded."""
+        ring = 2 * max(1, self.host_workers) + 8
+        with self._staging_lock:
+            if len(self._staging) < ring:
+                self._staging.append([torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True), None])
+                return self._staging[-1]
             slot = self._staging[self._staging_next % ring]
             self._staging_next += 1
-            if slot[1] is not None:
-                slot[1].synchronize()
-            if slot[0].numel() < nbytes:
-                slot[0] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+        if slot[1] is not None:
+            slot[1].synchronize()
+            slot[1] = None
+        if slot[0].numel() < nbytes:
+            slot[0] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
         return slot
 
     def batch_inputs(self, X_b, pinned=True):
         packed = X_b if isinstance(X_b, PackedMols) else pack_convmols(X_b)
         n_seg = max(self.batch_size, packed.n_mols)
         slot = None
-        if pinned and torch.cuda.is_available():
+        pinned = pinned and torch.cuda.is_available()     # host-only callers (tests) get plain memory
+        if pinned:
             # upper bound of the slab size without running the planner: 11 int32 arrays over atoms /
             # edges / segments plus alignment
             need = 4 * (5 * (packed.n_atoms + 2) + 3 * int(packed.adj_ptr[-1]) + (n_seg + 2)

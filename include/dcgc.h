@@ -177,6 +177,17 @@ int dcgc_group_gemm_fwd(int32_t mode, const float* a1_dev, int64_t ld_a1, int32_
                         const float* bias_dev, int32_t n, const int32_t* tiles_dev, int64_t n_tiles,
                         int32_t tile_rows, int64_t n_rows, int32_t act, float* y_dev, int64_t ld_y,
                         void* stream);
+/* Same, plus fused per-column statistics of the stored output for the BatchNorm that follows
+ * (graphconvmodel.py:213-216): stats_part_dev [n_chunks][2][n] float64 receives, per chunk of rows, the
+ * column sums of y and of y*y; *n_chunks_out (host) is the number of chunks written, at most
+ * dcgc_gemm_stats_max_chunks().  Partials are combined in a fixed order (deterministic).
+ * DCGC_GEMM_TF32X3 only (the statistics are accumulated in the tcgen05 kernel's epilogue). */
+int dcgc_group_gemm_fwd_stats(int32_t mode, const float* a1_dev, int64_t ld_a1, int32_t k1,
+                              const float* a2_dev, int64_t ld_a2, int32_t k2, const float* w_dev,
+                              const float* bias_dev, int32_t n, const int32_t* tiles_dev, int64_t n_tiles,
+                              int32_t tile_rows, int64_t n_rows, int32_t act, float* y_dev, int64_t ld_y,
+                              double* stats_part_dev, int32_t* n_chunks_out, void* stream);
+int32_t dcgc_gemm_stats_max_chunks(void);
 /* K6 (dgrad): [d1 | d2][r,:] = g[r,0:n] . W[g]^T, columns 0:k1 to d1 and k1:k1+k2 to d2 (either
  * may be null to skip).  Takes the same W as the forward (reads it transposed). */
 int dcgc_group_gemm_dgrad(int32_t mode, const float* g_dev, int64_t ld_g, int32_t n,
@@ -200,6 +211,9 @@ int dcgc_group_gemm_wgrad(int32_t mode, const float* a1_dev, int64_t ld_a1, int3
 int dcgc_linear_fwd(int32_t mode, const float* x_dev, int64_t ld_x, int32_t k, const float* w_dev,
                     const float* bias_dev, int32_t n, int64_t n_rows, int32_t act, float* y_dev,
                     int64_t ld_y, void* stream);
+int dcgc_linear_fwd_stats(int32_t mode, const float* x_dev, int64_t ld_x, int32_t k, const float* w_dev,
+                          const float* bias_dev, int32_t n, int64_t n_rows, int32_t act, float* y_dev,
+                          int64_t ld_y, double* stats_part_dev, int32_t* n_chunks_out, void* stream);
 int dcgc_linear_dgrad(int32_t mode, const float* g_dev, int64_t ld_g, int32_t n, const float* w_dev,
                       int32_t k, int64_t n_rows, float* dx_dev, int64_t ld_dx, void* stream);
 int64_t dcgc_linear_wgrad_workspace(int32_t k, int32_t n);

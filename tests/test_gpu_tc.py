@@ -156,3 +156,37 @@ def test_tc_linear_wgrad_large():
     ref = go.double().t() @ x.double()
     assert _rel(dw, ref) < TOL
     assert _rel(db, go.double().sum(0)) < TOL
+
+
+@pytest.mark.parametrize("k,c", [(128, 128), (76, 64), (64, 200)])
+def test_tc_group_gemm_fwd_fused_column_statistics(k, c):
+    """dcgc_group_gemm_fwd_stats: same output as the plain call, and per-chunk float64 column sums of y and
+    y*y (the BatchNorm statistics of graphconvmodel.py:213-216) that add up to the torch sums."""
+    import ctypes
+    from deepchem_b200 import _lib, ops
+    dev = _cuda()
+    topo = _topo(n_mols=900, seed=8, shape="zinc")
+    n = topo.n_atoms
+    g = torch.Generator(device=dev).manual_seed(7)
+    x = torch.randn(n, k, device=dev, generator=g)
+    s = torch.randn(n, k, device=dev, generator=g)
+    w = torch.randn(11, 2 * k, c, device=dev, generator=g) / np.sqrt(2 * k)
+    b = torch.randn(11, c, device=dev, generator=g)
+    L = _lib.lib()
+    y_ref = ops.group_gemm_fwd(x, s, w, b, topo, 1, _lib.GEMM_TF32X3)
+    y = torch.empty(n, c, device=dev)
+    max_chunks = int(L.dcgc_gemm_stats_max_chunks())
+    part = torch.full((max_chunks, 2, c), float("nan"), device=dev, dtype=torch.float64)
+    n_chunks = ctypes.c_int32(0)
+    _lib.check(L.dcgc_group_gemm_fwd_stats(_lib.GEMM_TF32X3, x.data_ptr(), k, k, s.data_ptr(), k, k, w.data_ptr(),
+                                           b.data_ptr(), c, topo.tiles.data_ptr(), topo.n_tiles, 128, n, 1,
+                                           y.data_ptr(), c, part.data_ptr(), ctypes.byref(n_chunks),
+                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    assert torch.equal(y, y_ref)
+    nc = n_chunks.value
+    assert 0 < nc <= max_chunks
+    tot = part[:nc].sum(0)
+    assert not torch.isnan(tot).any()
+    yd = y.double()
+    assert _rel(tot[0], yd.sum(0)) < 1e-6
+    assert _rel(tot[1], (yd * yd).sum(0)) < 1e-6

@@ -1,0 +1,52 @@
+"""Host side of the batch pipeline (no GPU): multi-worker layout building keeps dataset order and
+produces the same layouts as the single-threaded generator (graphconvmodel.py:382-422 contract)."""
+import threading
+
+import numpy as np
+
+from deepchem_b200 import graphconvmodel as G
+from deepchem_b200.data import PackedDataset
+from deepchem_b200.synthetic import make_molecules
+
+FIELDS = ("deg_slice", "membership", "perm", "row_ptr", "col_idx", "t_row_ptr", "t_src", "t_slot", "mol_ptr",
+          "mol_atoms", "tiles")
+
+
+def _host_model(batch_size, workers):
+    m = G.GraphConvModel.__new__(G.GraphConvModel)      # host-only: no CUDA objects are created
+    m.batch_size, m.mode, m.n_tasks, m.n_classes = batch_size, 'regression', 1, 2
+    m.host_workers = workers
+    m._staging, m._staging_next, m._staging_lock = [], 0, threading.Lock()
+    return m
+
+
+def test_parallel_generator_matches_serial_and_keeps_order():
+    pm = make_molecules(1000, seed=2, shape="stress")
+    ds = PackedDataset(pm, np.arange(1000, dtype=np.float32).reshape(-1, 1), np.ones((1000, 1), np.float32))
+    m = _host_model(128, 3)
+    serial = list(m.default_generator(ds, epochs=2, workers=1))
+    par = list(m.default_generator(ds, epochs=2, workers=3))
+    assert len(serial) == len(par) == 16
+    for (ia, ya, wa), (ib, yb, wb) in zip(serial, par):
+        assert np.array_equal(ya[0], yb[0]) and np.array_equal(wa[0], wb[0])
+        assert int(ia[3]) == int(ib[3])
+        for f in FIELDS:
+            assert np.array_equal(getattr(ia.layout, f), getattr(ib.layout, f)), f
+    # last batch of each epoch is padded to batch_size with zero weights (datasets.py:142-218)
+    assert serial[7][1][0].shape[0] == 128 and float(serial[7][2][0][1000 - 7 * 128:].sum()) == 0.0
+
+
+def test_parallel_generator_propagates_errors():
+    class Bad(object):
+        def iterbatches(self, **kw):
+            pm = make_molecules(8, seed=1)
+            pm.adj_idx = pm.adj_idx.copy()
+            pm.adj_idx[0] = 10 ** 6                      # neighbour outside its molecule
+            yield pm, np.zeros((8, 1), np.float32), np.ones((8, 1), np.float32), np.arange(8)
+    m = _host_model(8, 2)
+    try:
+        list(m.default_generator(Bad(), workers=2))
+    except Exception as e:
+        assert "neighbour" in str(e) or "index" in str(e).lower()
+    else:
+        raise AssertionError("expected the layout builder's index error")
