@@ -57,8 +57,23 @@ class GcModelConfig(Structure):
     ]
 
 
+class DmpnnInfo(ctypes.Structure):
+    _fields_ = [(n, c_int64) for n in ("n_mols", "n_atoms", "n_bonds", "n_rows", "k", "n_a2b_entries",
+                                       "n_map_entries")] + \
+        [("keep_pads", c_int32), ("reserved", c_int32)] + \
+        [(n, c_int64) for n in ("off_row_of_mol", "off_mol_ptr", "off_bond_src", "off_bond_edge", "off_a2b_ell",
+                                "off_map_ell", "off_a2b_ptr", "off_a2b_idx", "off_a2b_t_ptr", "off_a2b_t_idx",
+                                "off_map_ptr", "off_map_idx", "off_map_t_ptr", "off_map_t_idx", "slab_bytes")]
+
+
 _P = c_void_p
 _SIGNATURES = {
+    "dcgc_dmpnn_plan": (c_int32, [c_int64, _P, _P, _P, _P, c_int32, POINTER(DmpnnInfo)]),
+    "dcgc_dmpnn_build": (c_int32, [c_int64, _P, _P, _P, _P, POINTER(DmpnnInfo), _P]),
+    "dcgc_dmpnn_concat_rows": (c_int32, [_P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, c_int64, _P, c_int64, _P]),
+    "dcgc_segment_readout_fwd": (c_int32, [_P, c_int64, _P, c_int64, c_int32, c_int32, c_float, _P, c_int64, _P]),
+    "dcgc_segment_readout_bwd": (c_int32, [_P, c_int64, _P, c_int64, c_int64, c_int32, c_int32, c_float, _P, c_int64,
+                                           _P]),
     "dcgc_last_error": (c_char_p, []),
     "dcgc_version": (c_int32, []),
     "dcgc_device_ok": (c_int32, []),

@@ -109,8 +109,15 @@ pool_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restri
   float sc[VEC], sh[VEC], m[VEC];
   uint8_t a[VEC];
   if (AFFINE) {
+    if (VEC == 4) {   // c is a multiple of 4 and the statistics buffers are 16-byte aligned
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(scale + c));
+      const float4 h4 = __ldg(reinterpret_cast<const float4*>(shift + c));
+      sc[0] = s4.x; sc[1 % VEC] = s4.y; sc[2 % VEC] = s4.z; sc[3 % VEC] = s4.w;
+      sh[0] = h4.x; sh[1 % VEC] = h4.y; sh[2 % VEC] = h4.z; sh[3 % VEC] = h4.w;
+    } else {
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) { sc[v] = __ldg(scale + c + v); sh[v] = __ldg(shift + c + v); }
+      for (int v = 0; v < VEC; ++v) { sc[v] = __ldg(scale + c + v); sh[v] = __ldg(shift + c + v); }
+    }
   }
   auto load = [&](int64_t r, float* dst) {
     if (VEC == 4) {
@@ -373,7 +380,8 @@ extern "C" int dcgc_pool_fwd(const float* x, int64_t ld_x, const float* scale, c
   DCGC_CHECK_ARG(x && row_ptr && out, "dcgc_pool_fwd: null pointer");
   DcgcProfScope prof_scope("dcgc_pool_fwd", (cudaStream_t)stream);
   const bool v4 = width % 4 == 0 && ld_x % 4 == 0 && ld_out % 4 == 0 && aligned16(x) && aligned16(out) &&
-                  (arg == nullptr || (ld_arg % 4 == 0 && (reinterpret_cast<uintptr_t>(arg) & 3) == 0));
+                  (arg == nullptr || (ld_arg % 4 == 0 && (reinterpret_cast<uintptr_t>(arg) & 3) == 0)) &&
+                  (scale == nullptr || (aligned16(scale) && aligned16(shift)));
   const int groups = v4 ? width / 4 : width;
   const unsigned grid = grid_for(n_rows * groups);
   cudaStream_t st = (cudaStream_t)stream;

@@ -381,3 +381,109 @@ def _pack_index(device):
         rows = [[20, 21]] + [[2 * (d - 1) + 1, 2 * (d - 1)] for d in range(1, 11)]
         _pack_idx_cache[key] = torch.tensor(rows, dtype=torch.long, device=device)
     return _pack_idx_cache[key]
+
+
+# ------------------------------------------------------------------------------------------
+# D-MPNN path: generic CSR gather-sum, two-operand linear, per-molecule readout
+# ------------------------------------------------------------------------------------------
+class CsrPair(object):
+    """A gather pattern and its transpose: out[i] = sum_{e in [row_ptr[i], row_ptr[i+1])} x[idx[e]]
+    (n_out rows from n_in rows); (t_row_ptr, t_idx) lists, for every input row, the output rows reading it."""
+
+    def __init__(self, row_ptr, idx, t_row_ptr, t_idx, n_out, n_in):
+        self.row_ptr, self.idx, self.t_row_ptr, self.t_idx = row_ptr, idx, t_row_ptr, t_idx
+        self.n_out, self.n_in = int(n_out), int(n_in)
+
+
+class CsrGatherSumFn(torch.autograd.Function):
+    """K8: ``message[mapping].sum(1)`` / ``h_message[atom_to_incoming_bonds].sum(1)``
+    (torch_models/layers.py:1629, 1539); backward = gather over the transposed pattern (no atomics)."""
+
+    @staticmethod
+    def forward(ctx, x, csr):
+        _check_dev(x, "message")
+        ctx.csr = csr
+        return gather_sum(_rowmajor(x), csr.row_ptr, csr.idx, csr.n_out)
+
+    @staticmethod
+    def backward(ctx, dy):
+        csr = ctx.csr
+        return gather_sum(_rowmajor(dy), csr.t_row_ptr, csr.t_idx, csr.n_in), None
+
+
+class GroupLinear2Fn(torch.autograd.Function):
+    """y = act([a1 | a2] . w + b) with w [k1+k2, n] (one group).  K9: W_i / W_h (a2 = None) and
+    W_o(cat(atom_features, messages)) (layers.py:1541) without materialising the concatenation."""
+
+    @staticmethod
+    def forward(ctx, a1, a2, w, bias, act, mode):
+        _check_dev(a1, "input")
+        a1 = _rowmajor(a1)
+        a2 = _rowmajor(a2) if a2 is not None else None
+        w = w.contiguous()
+        y = group_gemm_fwd(a1, a2, w, bias, None, act, mode)
+        ctx.act, ctx.mode = act, mode
+        ctx.has2 = a2 is not None
+        ctx.save_for_backward(a1, a2, w, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a1, a2, w, y = ctx.saved_tensors
+        g = _rowmajor(dy)
+        if ctx.act == ACT_RELU:
+            g = g * (y > 0)
+        elif ctx.act == ACT_TANH:
+            g = g * (1 - y * y)
+        k1 = a1.shape[1]
+        k2 = a2.shape[1] if ctx.has2 else 0
+        dw = db = d1 = d2 = None
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            dw, db = group_gemm_wgrad(a1, a2, g, None, 1, ctx.mode)
+            dw, db = dw[0], db[0]
+        need1, need2 = ctx.needs_input_grad[0], ctx.has2 and ctx.needs_input_grad[1]
+        if need1 or need2:
+            d1, d2 = group_gemm_dgrad(g, w, k1, k2, None, need1, need2, ctx.mode)
+        return d1, d2, dw, (db if ctx.needs_input_grad[3] else None), None, None
+
+
+_READOUT_MODES = {"mean": 0, "sum": 1, "norm": 2}
+
+
+class SegmentReadoutFn(torch.autograd.Function):
+    """Per-molecule mean / sum / sum-over-norm of contiguous atom rows (layers.py:1550-1583)."""
+
+    @staticmethod
+    def forward(ctx, x, mol_ptr, n_mols, mode, norm):
+        _check_dev(x, "atoms_hidden_states")
+        x = _rowmajor(x)
+        if mode not in _READOUT_MODES:
+            raise Exception("Invalid aggregation")
+        out = torch.empty(n_mols, x.shape[1], device=x.device, dtype=torch.float32)
+        check(_lib.lib().dcgc_segment_readout_fwd(_p(x), _ld(x), _p(mol_ptr), n_mols, x.shape[1],
+                                                  _READOUT_MODES[mode], float(norm), _p(out), _ld(out), _stream()))
+        ctx.args = (mol_ptr, n_mols, x.shape[0], mode, float(norm))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        mol_ptr, n_mols, n_atoms, mode, norm = ctx.args
+        dout = _rowmajor(dout)
+        dx = torch.empty(n_atoms, dout.shape[1], device=dout.device, dtype=torch.float32)
+        check(_lib.lib().dcgc_segment_readout_bwd(_p(dout), _ld(dout), _p(mol_ptr), n_mols, n_atoms, dout.shape[1],
+                                                  _READOUT_MODES[mode], norm, _p(dx), _ld(dx), _stream()))
+        return dx, None, None, None, None
+
+
+def dmpnn_concat_rows(atom_feat, bond_feat, bond_src, bond_edge, n_rows, ld_out=None):
+    """f_ini_atoms_bonds on the device (dmpnn.py:183-188), zero rows on the pad rows; returns a [n_rows, fa+fb]
+    view of a buffer whose rows are padded to a 16-byte multiple."""
+    atom_feat, bond_feat = _rowmajor(atom_feat), _rowmajor(bond_feat)
+    fa, fb = atom_feat.shape[1], bond_feat.shape[1]
+    ld_out = ld_out or (fa + fb + 3) // 4 * 4
+    out = torch.empty(n_rows, ld_out, device=atom_feat.device, dtype=torch.float32)
+    check(_lib.lib().dcgc_dmpnn_concat_rows(_p(atom_feat), _ld(atom_feat), fa, _p(bond_feat), _ld(bond_feat), fb,
+                                            _p(bond_src), _p(bond_edge), n_rows, _p(out), ld_out, _stream()))
+    v = out[:, :fa + fb]
+    v._dcgc_zero_padded = True
+    return v

@@ -222,6 +222,57 @@ int dcgc_linear_wgrad(int32_t mode, const float* x_dev, int64_t ld_x, int32_t k,
                       void* workspace_dev, int64_t workspace_bytes, void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * D-MPNN host table builder.  Replaces _MapperDMPNN (deepchem/models/torch_models/dmpnn.py:123-243),
+ * the batch-wide -1 padding of DMPNNModel.default_generator (dmpnn.py:741-753) and the PyG collation
+ * with _ModData.__inc__ (dmpnn.py:17-35).
+ *
+ * Input: packed graphs — node_ptr[n_mols+1], edge_ptr[n_mols+1], edge_src / edge_dst[n_bonds]
+ * (molecule-local atom ids; directed bonds in (i->j, j->i) pairs at positions (2k, 2k+1) as
+ * DMPNNFeaturizer emits them).  Row space of the bond tensors: molecule k owns rows
+ * [row_of_mol[k], row_of_mol[k] + E_k] = its E_k bonds + one zero pad row.
+ * Output slab (int32 arrays at the byte offsets below, 256-byte aligned):
+ *   a2b_ell [n_atoms, k], map_ell [n_rows, k]   == the reference's batched atom_to_incoming_bonds /
+ *       mapping tensors (every entry shifted by the molecule's row offset, pads included; int64 there)
+ *   bond_src [n_rows]   global atom row feeding f_ini (-1 on pad rows), bond_edge [n_rows] global bond id
+ *   (a2b_ptr, a2b_idx) CSR atom <- bond rows, (map_ptr, map_idx) CSR bond row <- bond rows, and their
+ *   transposes for the backward gathers.  keep_pads == 0 drops the pad entries (exact while the pad rows
+ *   are zero, i.e. bias == False); keep_pads == 1 keeps them, resolved to the row torch would read.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct dcgc_dmpnn_info {
+  int64_t n_mols, n_atoms, n_bonds, n_rows; /* n_rows = n_bonds + n_mols */
+  int64_t k;                                /* batch-wide max in-degree, at least 1 */
+  int64_t n_a2b_entries, n_map_entries;     /* CSR entry counts */
+  int32_t keep_pads, reserved;
+  int64_t off_row_of_mol; /* int32 [n_mols+1] */
+  int64_t off_mol_ptr;    /* int32 [n_mols+1] first atom of each molecule */
+  int64_t off_bond_src, off_bond_edge;
+  int64_t off_a2b_ell, off_map_ell;
+  int64_t off_a2b_ptr, off_a2b_idx, off_a2b_t_ptr, off_a2b_t_idx;
+  int64_t off_map_ptr, off_map_idx, off_map_t_ptr, off_map_t_idx;
+  int64_t slab_bytes;
+} dcgc_dmpnn_info;
+
+int dcgc_dmpnn_plan(int64_t n_mols, const int32_t* node_ptr, const int32_t* edge_ptr, const int32_t* edge_src,
+                    const int32_t* edge_dst, int32_t keep_pads, dcgc_dmpnn_info* info);
+int dcgc_dmpnn_build(int64_t n_mols, const int32_t* node_ptr, const int32_t* edge_ptr, const int32_t* edge_src,
+                     const int32_t* edge_dst, const dcgc_dmpnn_info* info, void* slab);
+
+/* f_ini_atoms_bonds on the device (dmpnn.py:183-188): out[r, 0:fa] = atom_feat[bond_src[r], :],
+ * out[r, fa:fa+fb] = bond_feat[bond_edge[r], :], zero rows where bond_src[r] < 0; columns
+ * fa+fb..ld_out-1 are zeroed. */
+int dcgc_dmpnn_concat_rows(const float* atom_feat_dev, int64_t ld_a, int32_t fa, const float* bond_feat_dev,
+                           int64_t ld_b, int32_t fb, const int32_t* bond_src_dev, const int32_t* bond_edge_dev,
+                           int64_t n_rows, float* out_dev, int64_t ld_out, void* stream);
+/* Readout (torch_models/layers.py:1550-1583): out[m, :] = scale_m * sum_{a in [mol_ptr[m], mol_ptr[m+1])} x[a, :]
+ * with scale_m = 1/n_atoms(m) (mode 0, 'mean'), 1 (mode 1, 'sum') or 1/norm (mode 2, 'norm'); rows summed in
+ * ascending order.  The backward broadcasts: dx[a, :] = scale_m * dout[m(a), :]. */
+int dcgc_segment_readout_fwd(const float* x_dev, int64_t ld_x, const int32_t* mol_ptr_dev, int64_t n_mols,
+                             int32_t width, int32_t mode, float norm, float* out_dev, int64_t ld_out, void* stream);
+int dcgc_segment_readout_bwd(const float* dout_dev, int64_t ld_dout, const int32_t* mol_ptr_dev, int64_t n_mols,
+                             int64_t n_atoms, int32_t width, int32_t mode, float norm, float* dx_dev, int64_t ld_dx,
+                             void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * Whole-model engine: GraphConvModel forward / loss / backward in one call over flat slabs.
  * Replaces the per-step Python of TorchModel.fit_generator (torch_model.py:428-443) +
  * _GraphConvTorchModel.forward (graphconvmodel.py:188-249) + autograd.  Layer widths and the
