@@ -31,6 +31,12 @@ if ROOT not in sys.path:
 WORKLOAD = "zinc-synthetic B=4096/GPU, 25 atoms avg, F=75, GraphConv[128,128,128]+dense128+BN, regression T=1"
 LAYERS = [128, 128, 128]
 DENSE = 128
+# dram__bytes_read.sum + dram__bytes_write.sum per gather_sum launch, mean over the 5 launches of one step
+# (1 layer-0 forward 33.3 MB, 2 forward 78.9 MB, 2 backward 134.5 MB), from the ncu --set full capture
+# summarised in profiles/r1c_ncu_gather_sum.md (kernel unchanged since): BELOW the algorithmic bytes
+# because the 52 MB activation tensors are still L2-resident when the gather reads them.
+NCU_GATHER_SUM_TRAFFIC = 92.0e6
+NCU_TRAFFIC_SOURCE = "profiles/r1c_ncu_gather_sum.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
 
 
 def parse():
@@ -40,7 +46,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
-    ap.add_argument("--gemm-mode", default=os.environ.get("DCGC_GEMM_MODE", "fp32"))
+    ap.add_argument("--gemm-mode", default=os.environ.get("DCGC_GEMM_MODE", "tf32x3"),
+                    help="tf32x3 (default): tcgen05 tensor cores, 3-term TF32 split with fp32 accumulation, fp32-grade "
+                         "results (same 1e-5 parity tests as fp32); fp32: SIMT FFMA")
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches rotated through")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -298,8 +306,9 @@ def run_ours(args):
         e2e = {"value": world * B * K / (ms2 * 1e-3), "unit": "molecules/s", "ms_per_step": ms2 / K,
                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                "api": "GraphConvModel.fit_generator(default_generator(PackedDataset)) with log_frequency=1: "
-                      "C++ layout build + H2D from pinned host memory + fwd/bwd/Adam + loss readback every "
-                      "step (host work of the next batch overlaps the GPU on a prefetch thread)"}
+                      "C++ layout build (worker threads) + H2D from pinned host memory + fwd/bwd/Adam + a 4-byte "
+                      "loss readback for every step (asynchronous, consumed one step late); host work of the "
+                      "next batches overlaps the GPU on a prefetch thread"}
 
     if rank != 0:
         return
@@ -316,7 +325,8 @@ def run_ours(args):
         achieved = prof["bytes"] / (prof["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "gather_sum_kernel<4> (K1 neighbour gather-sum fwd + K5 transposed bwd)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "peak_source": peak_src, "traffic": None, "launches": prof["launches"],
+                "peak_source": peak_src, "traffic": NCU_GATHER_SUM_TRAFFIC, "traffic_source": NCU_TRAFFIC_SOURCE,
+                "launches": prof["launches"],
                 "avg_launch_us": prof["ms"] * 1e3 / prof["launches"],
                 "algorithmic_bytes_per_launch": prof["bytes"] / prof["launches"],
                 "share_of_step": prof["ms"] / ms}
@@ -329,9 +339,13 @@ def run_ours(args):
     line = {
         "metric": "GraphConv fwd+bwd molecules/sec", "value": value, "unit": "molecules/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32" if args.gemm_mode == "fp32" else args.gemm_mode, "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": world * B, "atoms_per_batch": n_atoms,
-                   "parallelism": "dp%d" % world, "gemm_mode": args.gemm_mode, "optimizer": "Adam (in step)",
+                   "parallelism": "dp%d" % world, "gemm_mode": args.gemm_mode,
+                   "arithmetic": "fp32 storage and accumulation everywhere; tf32x3 = every GEMM product as three tcgen05 "
+                                 "kind::tf32 MMAs (hi*hi + hi*lo + lo*hi), error ~2^-21, inside the 1e-5 parity bar "
+                                 "(tests/test_gpu_tc.py); fp32 = SIMT FFMA",
+                   "optimizer": "Adam (in step)", "host_workers": model.host_workers,
                    "l2": "no explicit flush: %d distinct batches rotated, >1 GB touched per step (> 126 MB L2)"
                          % len(pool)},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,

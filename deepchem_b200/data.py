@@ -92,6 +92,9 @@ class NumpyDataset(_ArrayDataset):
     def _take_X(self, idx, contiguous):
         return self._X[idx]
 
+    def select_range(self, lo, hi):
+        return NumpyDataset(self._X[lo:hi], self._y[lo:hi], self._w[lo:hi], self._ids[lo:hi])
+
 
 class PackedDataset(_ArrayDataset):
     """Molecules stored as one PackedMols shard; batches are PackedMols slices."""
@@ -106,3 +109,7 @@ class PackedDataset(_ArrayDataset):
         if contiguous and len(idx):
             return self.packed.slice(int(idx[0]), int(idx[-1]) + 1)
         return self.packed.take(idx)
+
+    def select_range(self, lo, hi):
+        """Molecules [lo, hi) as a dataset sharing this one's memory (inference sharding)."""
+        return PackedDataset(self.packed.slice(lo, hi), self._y[lo:hi], self._w[lo:hi], self._ids[lo:hi])

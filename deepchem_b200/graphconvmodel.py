@@ -15,6 +15,7 @@ Kept as in the torch port: BatchNorm1d(eps=1e-3, momentum=0.99), dropout gated b
 ``training`` argument, untrimmed fingerprint output, -1/0 rows for absent molecules, state_dict
 keys.
 """
+import collections
 import logging
 import os
 import time
@@ -35,6 +36,27 @@ from .mol_graphs import BatchLayout, pack_convmols
 from .synthetic import PackedMols
 
 logger = logging.getLogger(__name__)
+
+
+def _default_host_workers():
+    """Layout-builder threads per process: the cores this process may use, shared between the ranks of the
+    node (LOCAL_WORLD_SIZE under torchrun), minus the training and prefetch threads; between 1 and 4."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 2
+    ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+    return max(1, min(4, cores // ranks - 2))
+
+
+class _DoneEvent(object):
+    """Stand-in for a CUDA event when the loss already lives on the host."""
+
+    def query(self):
+        return True
+
+    def synchronize(self):
+        pass
 
 
 class TrimGraphOutput(nn.Module):
@@ -162,6 +184,29 @@ class BatchInputs(list):
     _prepare_batch can move everything with one H2D copy."""
     layout = None
     packed_features = None
+    packed_features_pinned = None
+
+
+class _DeviceSlot(object):
+    """Reusable device + pinned-host buffers of one in-flight batch (grow-only).  The steady-state step then
+    makes no cudaMalloc / cudaHostAlloc call: with per-batch tensors of slightly different sizes the caching
+    allocators occasionally had to go to the driver, which synchronises the device (seen as multi-millisecond
+    stalls of the end-to-end step, worst with several ranks on one host)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+        self.free_event = None      # recorded on the consumer's stream when it is done with this slot
+        self.copied_event = None    # recorded on the producer's stream after the H2D copies of this slot
+
+    def get(self, name, numel, dtype, pinned=False):
+        t = self.bufs.get(name)
+        if t is None or t.numel() < numel:
+            cap = int(numel * 1.15) + 1024
+            t = torch.empty(cap, dtype=dtype, pin_memory=True) if pinned else \
+                torch.empty(cap, dtype=dtype, device=self.device)
+            self.bufs[name] = t
+        return t
 
 
 class _Prefetcher(object):
@@ -178,6 +223,10 @@ class _Prefetcher(object):
         if model._prefetch_stream is None:
             model._prefetch_stream = torch.cuda.Stream(device=model.device)
         self.stream = model._prefetch_stream
+        n_slots = max(1, depth) + 2          # queued + being consumed + being prepared
+        while len(model._device_slots) < n_slots:
+            model._device_slots.append(_DeviceSlot(model.device))
+        self.slots = model._device_slots[:n_slots]
         self.error = None
         self.stop = False
         self.thread = threading.Thread(target=self._run, daemon=True)
@@ -186,14 +235,22 @@ class _Prefetcher(object):
     def _run(self):
         try:
             torch.cuda.set_device(self.model.device)
+            k = 0
             for batch in self.generator:
                 if self.stop:
                     break
+                slot = self.slots[k % len(self.slots)]
+                k += 1
                 with torch.cuda.stream(self.stream):
-                    prepared = self.model._prepare_batch(batch)
+                    if slot.free_event is not None:
+                        self.stream.wait_event(slot.free_event)      # the consumer finished with these buffers
+                    if slot.copied_event is not None:
+                        slot.copied_event.synchronize()              # pinned staging may be rewritten
+                    prepared = self.model._prepare_batch(batch, slot)
                     ev = torch.cuda.Event()
                     ev.record(self.stream)
-                self.q.put((prepared, ev))
+                    slot.copied_event = ev
+                self.q.put((prepared, ev, slot))
         except BaseException as e:      # surfaced in the consumer
             self.error = e
         finally:
@@ -201,18 +258,22 @@ class _Prefetcher(object):
 
     def __iter__(self):
         try:
+            prev = None
             while True:
                 item = self.q.get()
+                if prev is not None:
+                    # the consumer has issued all its work on the previous batch: its slot may be refilled once
+                    # that work has run
+                    fe = torch.cuda.Event()
+                    fe.record(torch.cuda.current_stream())
+                    prev.free_event = fe
+                    prev = None
                 if item is None:
                     break
-                prepared, ev = item
+                prepared, ev, slot = item
                 main = torch.cuda.current_stream()
                 main.wait_event(ev)
-                inputs, labels, weights = prepared
-                topo = inputs[1]._dcgc_topology
-                for t in [topo.buffer, inputs[0]._base if inputs[0]._base is not None else inputs[0]] + \
-                        [t for t in list(labels) + list(weights) if t is not None]:
-                    t.record_stream(main)
+                prev = slot
                 yield prepared
             if self.error is not None:
                 raise self.error
@@ -292,12 +353,15 @@ class GraphConvModel(object):
         self._grad_slab = None
         self._dp = False
         self._prefetch_stream = None
+        self._loss_ring = [torch.zeros((), dtype=torch.float32).pin_memory() if self.device.type == "cuda"
+                           else torch.zeros(()) for _ in range(4)]
+        self._device_slots = []     # reusable per-batch device buffers of the prefetch pipeline
         self._staging = []          # ring of reusable pinned slabs: [tensor, event]
         self._staging_next = 0
         import threading
         self._staging_lock = threading.Lock()
         # host threads building batch layouts ahead of the GPU (default_generator)
-        self.host_workers = int(os.environ.get("DCGC_HOST_WORKERS", max(1, min(4, (os.cpu_count() or 2) // 2))))
+        self.host_workers = int(os.environ.get("DCGC_HOST_WORKERS", _default_host_workers()))
         # fused whole-model engine (flat parameter slab, one C call per step) when the model shape
         # allows it; otherwise the per-layer autograd ops are used.
         self._engine = None
@@ -380,38 +444,65 @@ class GraphConvModel(object):
                              + layout.deg_adjacency_lists()[1:])
         inputs.layout = layout
         inputs.packed_features = packed.features
+        # page-locked torch view of the same rows when the shard was pinned: the H2D copy is then a true
+        # asynchronous DMA.  (A numpy view of pinned memory goes through torch's pageable path: a blocking
+        # cudaMemcpy that holds the driver's context lock and stalls the training thread's kernel launches —
+        # measured: the 0.8 ms copy serialised with the 1.7 ms step instead of overlapping it.)
+        pin = getattr(packed, "_pin", None)
+        inputs.packed_features_pinned = pin if (pin is not None and tuple(pin.shape) == packed.features.shape) else None
         return inputs
 
-    def _prepare_batch(self, batch):
+    def _prepare_batch(self, batch, slot=None):
         """Host -> device boundary (torch_model.py:923-952): one copy for the integer slab, one
         for the (unpermuted) features, then a device-side row permutation into degree-major
-        order with rows padded to a 16-byte multiple."""
+        order with rows padded to a 16-byte multiple.  ``slot`` (prefetch pipeline): reusable device /
+        pinned buffers to build into instead of fresh allocations."""
         inputs, labels, weights = batch
         if getattr(inputs, "layout", None) is None:
             raise TypeError("inputs must come from GraphConvModel.default_generator / batch_inputs")
-        topo = inputs.layout.to_device(self.device)
-        slot = getattr(inputs.layout, "_staging_slot", None)
+        layout = inputs.layout
+        buf = slot.get("slab", int(layout.info.slab_bytes), torch.uint8) if slot is not None else None
+        topo = layout.to_device(self.device, buffer=buf)
+        sslot = getattr(layout, "_staging_slot", None)
+        if sslot is not None:
+            sslot[1] = torch.cuda.Event()
+            sslot[1].record(torch.cuda.current_stream())
+        feats = getattr(inputs, "packed_features_pinned", None)
+        if feats is None:
+            feats = torch.from_numpy(np.ascontiguousarray(inputs.packed_features, dtype=np.float32))
+        n, f = feats.shape
         if slot is not None:
-            slot[1] = torch.cuda.Event()
-            slot[1].record(torch.cuda.current_stream())
-        feats = torch.from_numpy(np.ascontiguousarray(inputs.packed_features, dtype=np.float32))
-        feats = feats.to(self.device, non_blocking=True)
-        x = ops.permute_rows(feats, topo.perm)
+            fdev = slot.get("feats", n * f, torch.float32)[:n * f].view(n, f)
+            fdev.copy_(feats, non_blocking=True)
+            x = ops.permute_rows(fdev, topo.perm, out=slot.get("x", n * ((f + 3) // 4 * 4), torch.float32))
+        else:
+            x = ops.permute_rows(feats.to(self.device, non_blocking=True), topo.perm)
         x._dcgc_zero_padded = True
         dev_inputs = topo.model_inputs(x, n_samples=int(inputs[3]))
 
-        def conv(arrs):
+        def conv(arrs, tag):
             out = []
-            for a in arrs or []:
+            for i, a in enumerate(arrs or []):
                 if a is None:
                     out.append(None)
+                    continue
+                a = np.asarray(a)
+                if a.dtype == np.float64:
+                    a = a.astype(np.float32)
+                a = np.ascontiguousarray(a)
+                t = torch.from_numpy(a)
+                if slot is not None and self.device.type == "cuda":
+                    host = slot.get("h%s%d" % (tag, i), t.numel(), t.dtype, pinned=True)[:t.numel()].view(t.shape)
+                    host.copy_(t)
+                    dev = slot.get("d%s%d" % (tag, i), t.numel(), t.dtype)[:t.numel()].view(t.shape)
+                    dev.copy_(host, non_blocking=True)
+                    out.append(dev)
                 else:
-                    a = np.asarray(a)
-                    if a.dtype == np.float64:
-                        a = a.astype(np.float32)
-                    out.append(torch.as_tensor(a, device=self.device))
+                    if self.device.type == "cuda":
+                        t = t.pin_memory()
+                    out.append(t.to(self.device, non_blocking=True))
             return out
-        return dev_inputs, conv(labels), conv(weights)
+        return dev_inputs, conv(labels, "y"), conv(weights, "w")
 
     # ------------------------------------------------------------------ training
     def fit(self, dataset, nb_epoch=10, max_checkpoints_to_keep=5, checkpoint_interval=1000,
@@ -430,9 +521,27 @@ class GraphConvModel(object):
         if not isinstance(callbacks, SequenceCollection):
             callbacks = [callbacks]
         self.model.train()
-        avg_loss = torch.zeros((), device=self.device)
-        last_avg_loss, averaged_batches = 0.0, 0
         t0 = time.time()
+        # Every step's loss is read back to the host (4 bytes, pinned, asynchronous) but consumed one step late:
+        # the device never waits for the Python loop between steps (a blocking float(loss) per step cost 0.3 ms
+        # of a 2 ms step).  Logging / all_losses follow the reference's cadence (torch_model.py:453-463).
+        pending = collections.deque()           # (step, pinned scalar, event)
+        state = {"sum": 0.0, "n": 0, "last": 0.0}
+
+        def consume(limit):
+            # take the losses whose copies have landed; block only while more than `limit` are outstanding
+            while pending and (len(pending) > limit or pending[0][2].query()):
+                step_i, host, ev = pending.popleft()
+                ev.synchronize()
+                state["sum"] += float(host)
+                state["n"] += 1
+                if step_i % self.log_frequency == 0:
+                    state["last"] = state["sum"] / state["n"]
+                    logger.info('Ending global_step %d: Average loss %g' % (step_i, state["last"]))
+                    if all_losses is not None:
+                        all_losses.append(state["last"])
+                    state["sum"], state["n"] = 0.0, 0
+
         prepared_iter = _Prefetcher(self, generator, prefetch) if prefetch else \
             (self._prepare_batch(b) for b in generator)
         for prepared in prepared_iter:
@@ -442,15 +551,15 @@ class GraphConvModel(object):
             batch_loss = self._train_step(*prepared)
             self._global_step += 1
             step = self._global_step
-            avg_loss = avg_loss + batch_loss.detach()
-            averaged_batches += 1
-            if step % self.log_frequency == 0:
-                last_avg_loss = float(avg_loss) / averaged_batches
-                logger.info('Ending global_step %d: Average loss %g' % (step, last_avg_loss))
-                if all_losses is not None:
-                    all_losses.append(last_avg_loss)
-                avg_loss = torch.zeros((), device=self.device)
-                averaged_batches = 0
+            if batch_loss.is_cuda:
+                host = self._loss_ring[step % len(self._loss_ring)]
+                host.copy_(batch_loss.detach(), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+            else:
+                host, ev = batch_loss.detach().clone(), _DoneEvent()
+            pending.append((step, host, ev))
+            consume(len(self._loss_ring) - 2)
             if self.model_dir and checkpoint_interval > 0 and step % checkpoint_interval == checkpoint_interval - 1:
                 self.save_checkpoint(max_checkpoints_to_keep)
             for c in callbacks:
@@ -458,14 +567,17 @@ class GraphConvModel(object):
                     c(self, step, iteration_loss=batch_loss)
                 except TypeError:
                     c(self, step)
-        if averaged_batches > 0:
-            last_avg_loss = float(avg_loss) / averaged_batches
+        consume(0)
+        while pending:
+            consume(-1)
+        if state["n"] > 0:
+            state["last"] = state["sum"] / state["n"]
             if all_losses is not None:
-                all_losses.append(last_avg_loss)
+                all_losses.append(state["last"])
         if self.model_dir and checkpoint_interval > 0:
             self.save_checkpoint(max_checkpoints_to_keep)
         logger.info("TIMING: model fitting took %0.3f s" % (time.time() - t0))
-        return last_avg_loss
+        return state["last"]
 
     def _train_step(self, inputs, labels, weights):
         """zero_grad, forward, loss, backward, Adam step (torch_model.py:435-443).  The reference
@@ -543,9 +655,32 @@ class GraphConvModel(object):
 
     # ------------------------------------------------------------------ inference
     def _predict(self, generator, output_idx):
+        """Forward-only pass over the batches (torch_model.py:547-652).  With the fused engine the batches are
+        prepared ahead on the prefetch thread, every batch is one C call, outputs stay on the device and come
+        back in ONE device-to-host copy at the end (the reference copies every output of every batch,
+        torch_model.py:606)."""
         self.model.eval()
         results = None
         with torch.no_grad():
+            if self._engine is not None:
+                cls = self.mode == "classification"
+                chunks = None
+                for inputs, _, _ in _Prefetcher(self, generator, 2):
+                    topo, n = inputs[1]._dcgc_topology, int(inputs[3])
+                    out, probs, fp = self._engine.forward(topo, inputs[0], n, training=False, want_probs=cls)
+                    if cls:
+                        outs = [probs.view(n, self.n_tasks, self.n_classes), out.view(n, self.n_tasks, self.n_classes), fp]
+                    else:
+                        outs = [out, fp]
+                    vals = [outs[i] for i in output_idx]
+                    if chunks is None:
+                        chunks = [[] for _ in vals]
+                    for c, v in zip(chunks, vals):
+                        c.append(v)
+                if chunks is None:
+                    return []
+                final = [torch.cat(c, dim=0).cpu().numpy() for c in chunks]
+                return final[0] if len(final) == 1 else final
             for batch in generator:
                 inputs, _, _ = self._prepare_batch(batch)
                 outs = self.model(inputs)
@@ -559,7 +694,14 @@ class GraphConvModel(object):
         final = [np.concatenate(r, axis=0) for r in results]
         return final[0] if len(final) == 1 else final
 
-    def predict(self, dataset, transformers=[]):
+    def predict(self, dataset, transformers=[], shard=None):
+        """Predictions for the dataset (torch_model.py:731-761).  ``shard=(rank, world)`` restricts the pass to
+        this rank's contiguous range of molecules (parallel.shard_range): sharded inference needs no
+        communication, the caller concatenates the per-rank results in rank order."""
+        if shard is not None:
+            from .parallel import shard_range
+            lo, hi = shard_range(len(dataset), int(shard[0]), int(shard[1]))
+            dataset = dataset.select_range(lo, hi)
         gen = self.default_generator(dataset, mode='predict', deterministic=True, pad_batches=False)
         return self._predict(gen, self._prediction_outputs)
 

@@ -291,21 +291,24 @@ class BatchLayout(object):
         return [mm.get_atom_features(), mm.deg_slice, np.array(mm.membership),
                 np.array(self.n_mols if n_samples is None else n_samples)] + mm.deg_adj_lists[1:]
 
-    def to_device(self, device, non_blocking=True):
-        return DeviceTopology(self, device, non_blocking)
+    def to_device(self, device, non_blocking=True, buffer=None):
+        return DeviceTopology(self, device, non_blocking, buffer)
 
 
 class DeviceTopology(object):
     """Device-resident integer layout: one buffer, int32 views.  Everything the kernels need
     about the batch graph; features are NOT in here."""
 
-    def __init__(self, layout, device, non_blocking=True):
+    def __init__(self, layout, device, non_blocking=True, buffer=None):
         import torch
         self.layout = layout
         self.device = torch.device(device)
         src = layout.slab_tensor if layout.slab_tensor is not None else torch.from_numpy(layout.slab)
         nbytes = int(layout.info.slab_bytes)
-        self.buffer = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+        if buffer is not None and buffer.numel() >= max(nbytes, 1):
+            self.buffer = buffer           # caller-owned, reused across batches (no allocator traffic)
+        else:
+            self.buffer = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
         if nbytes:
             self.buffer[:nbytes].copy_(src[:nbytes], non_blocking=non_blocking)
         info = layout.info

@@ -121,12 +121,15 @@ def gather_sum(x, row_ptr, idx, n_rows_out, addend=None, out=None):
     return out
 
 
-def permute_rows(src, perm, n_feat=None, ld_out=None):
+def permute_rows(src, perm, n_feat=None, ld_out=None, out=None):
     src = _rowmajor(src)
     n_feat = src.shape[1] if n_feat is None else n_feat
     n = perm.shape[0]
     ld_out = ld_out or (n_feat + 3) // 4 * 4
-    out = torch.empty(n, ld_out, device=src.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(n, ld_out, device=src.device, dtype=torch.float32)
+    else:
+        out = out[:n * ld_out].view(n, ld_out)
     check(_lib.lib().dcgc_permute_rows(_p(src), _ld(src), _p(perm), n, n_feat, _p(out), ld_out, _stream()))
     _count()
     return out[:, :n_feat]

@@ -71,7 +71,8 @@ class PackedMols(object):
         out.adj_ptr = self.adj_ptr[a0:a1 + 1] - np.int32(e0)
         out.adj_idx = self.adj_idx[e0:e1]
         out.features = self.features[a0:a1]
-        out._pin = getattr(self, "_pin", None)
+        pin = getattr(self, "_pin", None)
+        out._pin = pin[a0:a1] if pin is not None else None     # torch view of the same pinned rows
         return out
 
     def pin_memory(self):
