@@ -323,7 +323,7 @@ def run_ours(args):
     if prof and prof["launches"]:
         prof["bytes"] = gs_bytes
         achieved = prof["bytes"] / (prof["ms"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "gather_sum_kernel<4> (K1 neighbour gather-sum fwd + K5 transposed bwd)",
+        roof = {"bound": "hbm", "kernel": "gather_sum_kernel<4, bucketed> (K1 neighbour gather-sum fwd + K5 transposed bwd)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": peak_src, "traffic": NCU_GATHER_SUM_TRAFFIC, "traffic_source": NCU_TRAFFIC_SOURCE,
                 "launches": prof["launches"],

@@ -44,7 +44,7 @@ class Topology(Structure):
         ("deg_count", c_int64 * N_DEG),
         ("row_ptr", c_void_p), ("col_idx", c_void_p), ("t_row_ptr", c_void_p), ("t_src", c_void_p),
         ("t_slot", c_void_p), ("mol_ptr", c_void_p), ("mol_atoms", c_void_p), ("membership", c_void_p),
-        ("tiles", c_void_p),
+        ("tiles", c_void_p), ("symmetric", c_int32), ("reserved", c_int32),
     ]
 
 
@@ -88,6 +88,7 @@ _SIGNATURES = {
     "dcgc_layout_build_from_deg": (c_int32, [_P, _P, _P, POINTER(LayoutInfo), _P]),
     "dcgc_permute_rows": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, c_int64, _P]),
     "dcgc_gather_sum": (c_int32, [_P, c_int64, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
+    "dcgc_gather_sum_bucketed": (c_int32, [_P, c_int64, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
     "dcgc_pool_fwd": (c_int32, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
     "dcgc_pool_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, c_int64, _P]),
     "dcgc_gather_fwd": (c_int32, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int64, _P, _P]),

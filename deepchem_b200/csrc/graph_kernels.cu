@@ -56,18 +56,42 @@ permute_rows_kernel(const float* __restrict__ src, int64_t ld_src, const int32_t
 // ------------------------------------------------------------------------------------------
 // K1/K5/K8: CSR gather-sum
 // ------------------------------------------------------------------------------------------
-template <int VEC>
+// Degree-bucketed rows (the ConvMol layout): row i of bucket d has exactly d entries, so the CSR offsets are
+// arithmetic and the row_ptr load — one of the three dependent loads row_ptr -> idx -> row that bound this
+// kernel (profiles/r1c_ncu_gather_sum.md) — disappears.
+struct DegBuckets {
+  int row0[DCGC_N_DEG + 1];   // first row of bucket d; row0[11] = number of rows
+  int e0[DCGC_N_DEG];         // first entry of bucket d
+};
+
+template <int VEC, bool BUCKET>
 __global__ void __launch_bounds__(kThreads)
 gather_sum_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restrict__ row_ptr,
-                  const int32_t* __restrict__ idx, int64_t n_rows, int groups, int width,
+                  const DegBuckets bk, const int32_t* __restrict__ idx, int64_t n_rows, int groups, int width,
                   const float* addend, int64_t ld_add, float* out, int64_t ld_out) {
   using V = Vec<VEC>;
   const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t row = t / groups;
   const int c = (int)(t - row * groups) * VEC;
   if (row >= n_rows || c >= width) return;
-  int e = __ldg(row_ptr + row);
-  const int e1 = __ldg(row_ptr + row + 1);
+  int e, e1;
+  if (BUCKET) {
+    // static indices only: a run-time index into the by-value parameter struct makes the compiler copy it to
+    // local memory (measured: 52 us instead of 32 us per launch)
+    int d = 0, r0 = bk.row0[0], eb = bk.e0[0];
+#pragma unroll
+    for (int k = 1; k < DCGC_N_DEG; ++k) {
+      const bool ge = (int)row >= bk.row0[k];
+      d = ge ? k : d;
+      r0 = ge ? bk.row0[k] : r0;
+      eb = ge ? bk.e0[k] : eb;
+    }
+    e = eb + ((int)row - r0) * d;
+    e1 = e + d;
+  } else {
+    e = __ldg(row_ptr + row);
+    e1 = __ldg(row_ptr + row + 1);
+  }
   typename V::T acc = V::zero();
   if (addend) acc = *reinterpret_cast<const typename V::T*>(addend + row * ld_add + c);  // may alias out
   const float* xc = x + c;
@@ -80,14 +104,23 @@ gather_sum_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __re
     const typename V::T v3 = V::load(xc + (int64_t)j3 * ld_x);
     vadd(acc, v0); vadd(acc, v1); vadd(acc, v2); vadd(acc, v3);
   }
-  if (e + 2 <= e1) {
+  // remainder of 1..3 rows: all of them in flight at once (degree-3 atoms, ~27 % of a molecule, used to pay two
+  // dependent round trips: a pair, then the single)
+  const int rem = e1 - e;
+  if (rem == 3) {
+    const int j0 = __ldg(idx + e), j1 = __ldg(idx + e + 1), j2 = __ldg(idx + e + 2);
+    const typename V::T v0 = V::load(xc + (int64_t)j0 * ld_x);
+    const typename V::T v1 = V::load(xc + (int64_t)j1 * ld_x);
+    const typename V::T v2 = V::load(xc + (int64_t)j2 * ld_x);
+    vadd(acc, v0); vadd(acc, v1); vadd(acc, v2);
+  } else if (rem == 2) {
     const int j0 = __ldg(idx + e), j1 = __ldg(idx + e + 1);
     const typename V::T v0 = V::load(xc + (int64_t)j0 * ld_x);
     const typename V::T v1 = V::load(xc + (int64_t)j1 * ld_x);
     vadd(acc, v0); vadd(acc, v1);
-    e += 2;
+  } else if (rem == 1) {
+    vadd(acc, V::load(xc + (int64_t)__ldg(idx + e) * ld_x));
   }
-  if (e < e1) vadd(acc, V::load(xc + (int64_t)__ldg(idx + e) * ld_x));
   V::store(out + row * ld_out + c, acc);
 }
 
@@ -136,23 +169,35 @@ pool_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restri
   for (int v = 0; v < VEC; ++v) a[v] = 0;
   const int e0 = __ldg(row_ptr + row), e1 = __ldg(row_ptr + row + 1);
   int e = e0;
-  for (; e + 2 <= e1; e += 2) {
-    float u0[VEC], u1[VEC];
-    const int j0 = __ldg(col_idx + e), j1 = __ldg(col_idx + e + 1);
-    load(j0, u0);
-    load(j1, u1);
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      if (u0[v] > m[v]) { m[v] = u0[v]; a[v] = (uint8_t)(e - e0 + 1); }
-      if (u1[v] > m[v]) { m[v] = u1[v]; a[v] = (uint8_t)(e - e0 + 2); }
-    }
-  }
-  if (e < e1) {
-    float u0[VEC];
-    load(__ldg(col_idx + e), u0);
+  auto cmp = [&](const float* u, int slot) {
 #pragma unroll
     for (int v = 0; v < VEC; ++v)
-      if (u0[v] > m[v]) { m[v] = u0[v]; a[v] = (uint8_t)(e - e0 + 1); }
+      if (u[v] > m[v]) { m[v] = u[v]; a[v] = (uint8_t)slot; }
+  };
+  // up to four neighbour rows in flight at once (degree 3 and 4 used to pay two dependent round trips);
+  // the comparisons stay in slot order, so the first-slot tie rule is unchanged
+  for (; e + 4 <= e1; e += 4) {
+    float u0[VEC], u1[VEC], u2[VEC], u3[VEC];
+    const int j0 = __ldg(col_idx + e), j1 = __ldg(col_idx + e + 1), j2 = __ldg(col_idx + e + 2),
+              j3 = __ldg(col_idx + e + 3);
+    load(j0, u0); load(j1, u1); load(j2, u2); load(j3, u3);
+    cmp(u0, e - e0 + 1); cmp(u1, e - e0 + 2); cmp(u2, e - e0 + 3); cmp(u3, e - e0 + 4);
+  }
+  const int rem = e1 - e;
+  if (rem == 3) {
+    float u0[VEC], u1[VEC], u2[VEC];
+    const int j0 = __ldg(col_idx + e), j1 = __ldg(col_idx + e + 1), j2 = __ldg(col_idx + e + 2);
+    load(j0, u0); load(j1, u1); load(j2, u2);
+    cmp(u0, e - e0 + 1); cmp(u1, e - e0 + 2); cmp(u2, e - e0 + 3);
+  } else if (rem == 2) {
+    float u0[VEC], u1[VEC];
+    const int j0 = __ldg(col_idx + e), j1 = __ldg(col_idx + e + 1);
+    load(j0, u0); load(j1, u1);
+    cmp(u0, e - e0 + 1); cmp(u1, e - e0 + 2);
+  } else if (rem == 1) {
+    float u0[VEC];
+    load(__ldg(col_idx + e), u0);
+    cmp(u0, e - e0 + 1);
   }
   if (VEC == 4) {
     *reinterpret_cast<float4*>(out + row * ld_out + c) = make_float4(m[0], m[1 % VEC], m[2 % VEC], m[3 % VEC]);
@@ -347,26 +392,53 @@ extern "C" int dcgc_permute_rows(const float* src, int64_t ld_src, const int32_t
   return DCGC_OK;
 }
 
-extern "C" int dcgc_gather_sum(const float* x, int64_t ld_x, const int32_t* row_ptr, const int32_t* idx,
-                               int64_t n_rows_out, int32_t width, const float* addend, int64_t ld_add,
-                               float* out, int64_t ld_out, void* stream) {
+static int gather_sum_impl(const float* x, int64_t ld_x, const int32_t* row_ptr, const int64_t* deg_count,
+                           const int32_t* idx, int64_t n_rows_out, int32_t width, const float* addend, int64_t ld_add,
+                           float* out, int64_t ld_out, void* stream) {
   DCGC_CHECK_ARG(n_rows_out >= 0 && width >= 0 && ld_x >= width && ld_out >= width &&
                      (addend == nullptr || ld_add >= width), "dcgc_gather_sum: bad sizes");
   if (n_rows_out == 0 || width == 0) return DCGC_OK;
-  DCGC_CHECK_ARG(x && row_ptr && out, "dcgc_gather_sum: null pointer");
+  DCGC_CHECK_ARG(x && (row_ptr || deg_count) && out, "dcgc_gather_sum: null pointer");
+  DegBuckets bk{};
+  if (deg_count) {
+    int64_t r = 0, e = 0;
+    for (int d = 0; d < DCGC_N_DEG; ++d) {
+      DCGC_CHECK_ARG(deg_count[d] >= 0, "dcgc_gather_sum_bucketed: negative bucket size");
+      bk.row0[d] = (int)r;
+      bk.e0[d] = (int)e;
+      r += deg_count[d];
+      e += (int64_t)d * deg_count[d];
+    }
+    bk.row0[DCGC_N_DEG] = (int)r;
+    DCGC_CHECK_ARG(r == n_rows_out && e < ((int64_t)1 << 31), "dcgc_gather_sum_bucketed: bucket sizes do not add up to n_rows_out");
+  }
   DcgcProfScope prof_scope("dcgc_gather_sum", (cudaStream_t)stream);
   const bool v4 = width % 4 == 0 && ld_x % 4 == 0 && ld_out % 4 == 0 && aligned16(x) && aligned16(out) &&
                   (addend == nullptr || (ld_add % 4 == 0 && aligned16(addend)));
-  if (v4) {
-    const int groups = width / 4;
-    gather_sum_kernel<4><<<grid_for(n_rows_out * groups), kThreads, 0, (cudaStream_t)stream>>>(
-        x, ld_x, row_ptr, idx, n_rows_out, groups, width, addend, ld_add, out, ld_out);
-  } else {
-    gather_sum_kernel<1><<<grid_for(n_rows_out * width), kThreads, 0, (cudaStream_t)stream>>>(
-        x, ld_x, row_ptr, idx, n_rows_out, width, width, addend, ld_add, out, ld_out);
-  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int groups = v4 ? width / 4 : width;
+  const unsigned grid = grid_for(n_rows_out * groups);
+#define DCGC_GS_LAUNCH(V, B) \
+  gather_sum_kernel<V, B><<<grid, kThreads, 0, st>>>(x, ld_x, row_ptr, bk, idx, n_rows_out, groups, width, addend, ld_add, out, ld_out)
+  if (v4) { if (deg_count) DCGC_GS_LAUNCH(4, true); else DCGC_GS_LAUNCH(4, false); }
+  else { if (deg_count) DCGC_GS_LAUNCH(1, true); else DCGC_GS_LAUNCH(1, false); }
+#undef DCGC_GS_LAUNCH
   DCGC_CUDA_LAUNCH_CHECK("dcgc_gather_sum");
   return DCGC_OK;
+}
+
+extern "C" int dcgc_gather_sum(const float* x, int64_t ld_x, const int32_t* row_ptr, const int32_t* idx,
+                               int64_t n_rows_out, int32_t width, const float* addend, int64_t ld_add,
+                               float* out, int64_t ld_out, void* stream) {
+  DCGC_CHECK_ARG(row_ptr || n_rows_out == 0, "dcgc_gather_sum: null row_ptr");
+  return gather_sum_impl(x, ld_x, row_ptr, nullptr, idx, n_rows_out, width, addend, ld_add, out, ld_out, stream);
+}
+
+extern "C" int dcgc_gather_sum_bucketed(const float* x, int64_t ld_x, const int64_t* deg_count_host, const int32_t* idx,
+                                        int64_t n_rows_out, int32_t width, const float* addend, int64_t ld_add,
+                                        float* out, int64_t ld_out, void* stream) {
+  DCGC_CHECK_ARG(deg_count_host, "dcgc_gather_sum_bucketed: null deg_count");
+  return gather_sum_impl(x, ld_x, nullptr, deg_count_host, idx, n_rows_out, width, addend, ld_add, out, ld_out, stream);
 }
 
 extern "C" int dcgc_pool_fwd(const float* x, int64_t ld_x, const float* scale, const float* shift,

@@ -583,7 +583,7 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
     const int64_t ld = sv.ld_h[l];
     conv_bias_pack<<<blocks_for(DCGC_N_DEG * c), kT, 0, st>>>(params + lo.conv_b[l], c, sv.b11[l]);
     DCGC_CUDA_LAUNCH_CHECK("conv_bias_pack");
-    RET_IF(dcgc_gather_sum(h, ld, t->row_ptr, t->col_idx, N, fp, nullptr, 0, sv.s[l], fp, st));
+    RET_IF(dcgc_gather_sum_bucketed(h, ld, t->deg_count, t->col_idx, N, fp, nullptr, 0, sv.s[l], fp, st));
     const bool fuse_stats = cfg->batch_norm && training && cfg->gemm_mode == DCGC_GEMM_TF32X3;
     int32_t fused = -1;
     if (fuse_stats)
@@ -833,7 +833,10 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
       // [dP | d2] = G . W^T, then dP += transposed gather of d2
       RET_IF(dcgc_group_gemm_dgrad(cfg->gemm_mode, dA, c, c, params + lo.conv_w[l], fp, fp, t->tiles, t->n_tiles, 128,
                                    N, dP, fp, d2, fp, st));
-      RET_IF(dcgc_gather_sum(d2, fp, t->t_row_ptr, t->t_src, N, fp, dP, fp, dP, fp, st));
+      if (t->symmetric)
+        RET_IF(dcgc_gather_sum_bucketed(d2, fp, t->deg_count, t->t_src, N, fp, dP, fp, dP, fp, st));
+      else
+        RET_IF(dcgc_gather_sum(d2, fp, t->t_row_ptr, t->t_src, N, fp, dP, fp, dP, fp, st));
     }
   }
   return DCGC_OK;

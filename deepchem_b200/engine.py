@@ -38,6 +38,7 @@ def topology_struct(topo):
         st.deg_count[d] = topo.deg_count[d]
     for name in ("row_ptr", "col_idx", "t_row_ptr", "t_src", "t_slot", "mol_ptr", "mol_atoms", "membership", "tiles"):
         setattr(st, name, getattr(topo, name).data_ptr())
+    st.symmetric = 1 if getattr(topo, "symmetric", False) else 0
     topo._c_struct = st
     return st
 

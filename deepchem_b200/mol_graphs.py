@@ -189,6 +189,8 @@ class BatchLayout(object):
         self.deg_slice = self.deg_slice.reshape(11, 2)
         self.tiles = self.tiles.reshape(-1, 4)
         self.deg_count = [int(c) for c in info.deg_count]
+        # in-degree == degree for every atom (always true for molecular graphs; not with a master atom)
+        self.symmetric = bool(np.array_equal(self.row_ptr, self.t_row_ptr))
 
     n_atoms = property(lambda self: int(self.info.n_atoms))
     n_edges = property(lambda self: int(self.info.n_edges))
@@ -323,6 +325,7 @@ class DeviceTopology(object):
         self.n_atoms, self.n_edges = layout.n_atoms, layout.n_edges
         self.n_mols, self.n_segments, self.n_tiles = layout.n_mols, layout.n_segments, layout.n_tiles
         self.deg_count = layout.deg_count
+        self.symmetric = layout.symmetric
         self._deg_count_c = (ctypes.c_int64 * 11)(*self.deg_count)
 
     def deg_adjacency_lists(self):

@@ -190,3 +190,30 @@ def test_tc_group_gemm_fwd_fused_column_statistics(k, c):
     yd = y.double()
     assert _rel(tot[0], yd.sum(0)) < 1e-6
     assert _rel(tot[1], (yd * yd).sum(0)) < 1e-6
+
+
+def test_bucketed_gather_sum_is_bit_identical_to_csr_gather_sum():
+    """dcgc_gather_sum_bucketed (offsets computed from the 11 degree-bucket sizes) against dcgc_gather_sum
+    (offsets loaded from row_ptr): same bits, forward lists and (symmetric adjacency) transposed lists, all 11
+    buckets populated, with and without the fused addend."""
+    import ctypes
+    from deepchem_b200 import _lib, ops
+    dev = _cuda()
+    topo = _topo(n_mols=400, seed=12, shape="stress")
+    assert topo.symmetric
+    n = topo.n_atoms
+    g = torch.Generator(device=dev).manual_seed(9)
+    L = _lib.lib()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for width in (128, 76, 75):
+        x = torch.randn(n, width, device=dev, generator=g)
+        add = torch.randn(n, width, device=dev, generator=g)
+        for idx, ptr in ((topo.col_idx, topo.row_ptr), (topo.t_src, topo.t_row_ptr)):
+            for addend in (None, add):
+                ref = ops.gather_sum(x, ptr, idx, n, addend=addend.clone() if addend is not None else None)
+                out = torch.empty(n, width, device=dev)
+                a = addend.clone() if addend is not None else None
+                _lib.check(L.dcgc_gather_sum_bucketed(x.data_ptr(), width, topo._deg_count_c, idx.data_ptr(), n, width,
+                                                      a.data_ptr() if a is not None else None, width, out.data_ptr(),
+                                                      width, st))
+                assert torch.equal(out, ref)
