@@ -32,11 +32,12 @@ WORKLOAD = "zinc-synthetic B=4096/GPU, 25 atoms avg, F=75, GraphConv[128,128,128
 LAYERS = [128, 128, 128]
 DENSE = 128
 # dram__bytes_read.sum + dram__bytes_write.sum per gather_sum launch, mean over the 5 launches of one step
-# (1 layer-0 forward 33.3 MB, 2 forward 78.9 MB, 2 backward 134.5 MB), from the ncu --set full capture
-# summarised in profiles/r1c_ncu_gather_sum.md (kernel unchanged since): BELOW the algorithmic bytes
-# because the 52 MB activation tensors are still L2-resident when the gather reads them.
-NCU_GATHER_SUM_TRAFFIC = 92.0e6
-NCU_TRAFFIC_SOURCE = "profiles/r1c_ncu_gather_sum.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
+# (1 layer-0 forward 33.2 MB, 2 forward 77.6 MB, 2 backward 132.9 MB), from the ncu --set full capture of this
+# command summarised in profiles/r1p_ncu_gather_sum_bucketed.md: BELOW the algorithmic bytes because the
+# 52 MB activation tensors are partly still L2-resident when the gather reads them.
+NCU_GATHER_SUM_TRAFFIC = 90.9e6
+NCU_TRAFFIC_SOURCE = ("profiles/r1p_ncu_gather_sum_bucketed.md (ncu --set full, dram__bytes_read.sum + "
+                      "dram__bytes_write.sum, mean of the 5 launches of a step)")
 
 
 def parse():

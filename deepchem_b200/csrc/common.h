@@ -28,6 +28,8 @@ struct DcgcProfScope {
   cudaEvent_t e1_;
   cudaStream_t st_;
 };
+// tensor-core modes -> number of MMA terms (0 = not a tensor-core mode)
+static inline int dcgc_tc_terms(int mode) { return mode == DCGC_GEMM_TF32X3 ? 3 : (mode == DCGC_GEMM_BF16 ? 1 : 0); }
 #define DCGC_CUDA_LAUNCH_CHECK(what)                                        \
   do {                                                                      \
     g_dcgc_launches.fetch_add(1, std::memory_order_relaxed);                \
@@ -61,11 +63,11 @@ struct DcgcWgradArgs {
   int chunk_prefix[DCGC_N_DEG + 1];
   int a1_vec, a2_vec, g_vec;
 };
-int dcgc_tc_wgrad_stage1(const DcgcWgradArgs& p, int chunks, cudaStream_t st);
+int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p, int chunks, cudaStream_t st);
 int dcgc_tc_wgrad_grid_y(int k_total, int n);
 int dcgc_tc_num_sms();
 // tcgen05 path (gemm_tc.cu); see the comment there for the argument convention
-int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_t ld_a2, int k2, const float* w,
+int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2, int64_t ld_a2, int k2, const float* w,
                  int n_groups, int trans_w, const float* bias, int n1, int n2, const int32_t* tiles, int64_t n_tiles,
                  int64_t n_rows, int act, float* c1, int64_t ld_c1, float* c2, int64_t ld_c2, cudaStream_t st,
                  double* stats = nullptr, int* stats_chunks = nullptr);

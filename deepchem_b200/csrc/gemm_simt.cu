@@ -362,9 +362,9 @@ static int group_gemm_fwd_impl(int32_t mode, const float* a1, int64_t ld_a1, int
                                int32_t act, float* y, int64_t ld_y, double* stats, int32_t* stats_chunks,
                                void* stream) {
   if (stats_chunks) *stats_chunks = 0;
-  DCGC_CHECK_ARG(stats == nullptr || mode == DCGC_GEMM_TF32X3,
+  DCGC_CHECK_ARG(stats == nullptr || dcgc_tc_terms(mode) != 0,
                  "dcgc_group_gemm_fwd_stats: fused column statistics exist in DCGC_GEMM_TF32X3 mode only");
-  DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || mode == DCGC_GEMM_TF32X3,
+  DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || dcgc_tc_terms(mode) != 0,
                  "dcgc_group_gemm_fwd: GEMM mode %d is not available in this build", mode);
   DCGC_CHECK_ARG(k1 >= 0 && k2 >= 0 && n >= 0 && n_rows >= 0 && ld_a1 >= k1 && ld_y >= n,
                  "dcgc_group_gemm_fwd: bad sizes");
@@ -375,8 +375,8 @@ static int group_gemm_fwd_impl(int32_t mode, const float* a1, int64_t ld_a1, int
   if (n_rows == 0 || n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(a1 && w && y, "dcgc_group_gemm_fwd: null pointer");
   DcgcProfScope prof_scope("dcgc_group_gemm_fwd", (cudaStream_t)stream);
-  if (mode == DCGC_GEMM_TF32X3)
-    return dcgc_tc_gemm(a1, ld_a1, k1, a2, ld_a2, a2 ? k2 : 0, w, tiles ? DCGC_N_DEG : 1, 1, bias, n, 0, tiles, n_tiles,
+  if (dcgc_tc_terms(mode))
+    return dcgc_tc_gemm(dcgc_tc_terms(mode), a1, ld_a1, k1, a2, ld_a2, a2 ? k2 : 0, w, tiles ? DCGC_N_DEG : 1, 1, bias, n, 0, tiles, n_tiles,
                         n_rows, act, y, ld_y, nullptr, 0, (cudaStream_t)stream, stats, stats_chunks);
   GemmArgs p{};
   p.a1 = a1; p.ld_a1 = ld_a1; p.k1 = k1;
@@ -429,7 +429,7 @@ extern "C" int dcgc_group_gemm_dgrad(int32_t mode, const float* g, int64_t ld_g,
                                      int32_t k1, int32_t k2, const int32_t* tiles, int64_t n_tiles,
                                      int32_t tile_rows, int64_t n_rows, float* d1, int64_t ld_d1, float* d2,
                                      int64_t ld_d2, void* stream) {
-  DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || mode == DCGC_GEMM_TF32X3,
+  DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || dcgc_tc_terms(mode) != 0,
                  "dcgc_group_gemm_dgrad: GEMM mode %d is not available in this build", mode);
   DCGC_CHECK_ARG(k1 >= 0 && k2 >= 0 && n >= 0 && n_rows >= 0 && ld_g >= n, "dcgc_group_gemm_dgrad: bad sizes");
   DCGC_CHECK_ARG((d1 == nullptr || ld_d1 >= k1) && (d2 == nullptr || ld_d2 >= k2),
@@ -438,8 +438,8 @@ extern "C" int dcgc_group_gemm_dgrad(int32_t mode, const float* g, int64_t ld_g,
   if (n_rows == 0 || k1 + k2 == 0 || (!d1 && !d2)) return DCGC_OK;
   DCGC_CHECK_ARG(g && w, "dcgc_group_gemm_dgrad: null pointer");
   DcgcProfScope prof_scope("dcgc_group_gemm_dgrad", (cudaStream_t)stream);
-  if (mode == DCGC_GEMM_TF32X3)
-    return dcgc_tc_gemm(g, ld_g, n, nullptr, 0, 0, w, tiles ? DCGC_N_DEG : 1, 0, nullptr, k1, k2, tiles, n_tiles,
+  if (dcgc_tc_terms(mode))
+    return dcgc_tc_gemm(dcgc_tc_terms(mode), g, ld_g, n, nullptr, 0, 0, w, tiles ? DCGC_N_DEG : 1, 0, nullptr, k1, k2, tiles, n_tiles,
                         n_rows, DCGC_ACT_NONE, d1, ld_d1, d2, ld_d2, (cudaStream_t)stream);
   GemmArgs p{};
   p.a1 = g; p.ld_a1 = ld_g; p.k1 = n;
@@ -479,7 +479,7 @@ static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, 
                       int64_t ld_a2, int32_t k2, const float* g, int64_t ld_g, int32_t n,
                       const int64_t* deg_count, int32_t n_groups, float* dw, float* dbias,
                       void* workspace, int64_t workspace_bytes, int transpose, void* stream) {
-  DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || mode == DCGC_GEMM_TF32X3,
+  DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || dcgc_tc_terms(mode) != 0,
                  "dcgc_group_gemm_wgrad: GEMM mode %d is not available in this build", mode);
   DCGC_CHECK_ARG(k1 >= 0 && k2 >= 0 && n >= 0 && ld_a1 >= k1 && ld_g >= n, "dcgc_group_gemm_wgrad: bad sizes");
   DCGC_CHECK_ARG(n_groups >= 1 && n_groups <= DCGC_N_DEG && deg_count, "dcgc_group_gemm_wgrad: bad groups");
@@ -497,7 +497,7 @@ static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, 
   p.a1 = a1; p.ld_a1 = ld_a1; p.k1 = k1;
   p.a2 = a2; p.ld_a2 = ld_a2; p.k2 = a2 ? k2 : 0;
   p.g = g; p.ld_g = ld_g; p.n = n;
-  const bool tc = mode == DCGC_GEMM_TF32X3;
+  const bool tc = dcgc_tc_terms(mode) != 0;
   int64_t target = kTargetChunks;
   if (tc) {
     // one CTA per SM (the kernel takes the whole shared memory): keep the grid within one wave;
@@ -543,7 +543,7 @@ static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, 
   DcgcProfScope prof_scope("dcgc_group_gemm_wgrad", (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   if (chunks > 0 && tc) {
-    int st_ = dcgc_tc_wgrad_stage1(p, chunks, st);
+    int st_ = dcgc_tc_wgrad_stage1(dcgc_tc_terms(mode), p, chunks, st);
     if (st_ != DCGC_OK) return st_;
   } else if (chunks > 0) {
     const int tiles_m = (Kt + BM - 1) / BM;
@@ -582,17 +582,17 @@ static int linear_fwd_impl(int32_t mode, const float* x, int64_t ld_x, int32_t k
                            int32_t n, int64_t n_rows, int32_t act, float* y, int64_t ld_y, double* stats,
                            int32_t* stats_chunks, void* stream) {
   if (stats_chunks) *stats_chunks = 0;
-  DCGC_CHECK_ARG(stats == nullptr || mode == DCGC_GEMM_TF32X3,
+  DCGC_CHECK_ARG(stats == nullptr || dcgc_tc_terms(mode) != 0,
                  "dcgc_linear_fwd_stats: fused column statistics exist in DCGC_GEMM_TF32X3 mode only");
-  DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || mode == DCGC_GEMM_TF32X3,
+  DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || dcgc_tc_terms(mode) != 0,
                  "dcgc_linear_fwd: GEMM mode %d is not available in this build", mode);
   DCGC_CHECK_ARG(k >= 0 && n >= 0 && n_rows >= 0 && ld_x >= k && ld_y >= n, "dcgc_linear_fwd: bad sizes");
   DCGC_CHECK_ARG(act >= DCGC_ACT_NONE && act <= DCGC_ACT_TANH, "dcgc_linear_fwd: unknown activation %d", act);
   if (n_rows == 0 || n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(x && w && y, "dcgc_linear_fwd: null pointer");
   DcgcProfScope prof_scope("dcgc_linear_fwd", (cudaStream_t)stream);
-  if (mode == DCGC_GEMM_TF32X3)
-    return dcgc_tc_gemm(x, ld_x, k, nullptr, 0, 0, w, 1, 0, bias, n, 0, nullptr, 0, n_rows, act, y, ld_y, nullptr, 0,
+  if (dcgc_tc_terms(mode))
+    return dcgc_tc_gemm(dcgc_tc_terms(mode), x, ld_x, k, nullptr, 0, 0, w, 1, 0, bias, n, 0, nullptr, 0, n_rows, act, y, ld_y, nullptr, 0,
                         (cudaStream_t)stream, stats, stats_chunks);
   GemmArgs p{};
   p.a1 = x; p.ld_a1 = ld_x; p.k1 = k;

@@ -1,21 +1,15 @@
 // tcgen05 (5th-gen tensor core) degree-grouped GEMMs with TMEM accumulators for sm_100a.
 //
-// Arithmetic: DCGC_GEMM_TF32X3 — every fp32 operand is split into tf32 hi + lo parts and three
-// kind::tf32 MMAs (hi*hi + hi*lo + lo*hi) are accumulated in fp32 in TMEM: ~2^-21 relative error per
-// product, i.e. fp32-grade results (the 1e-5 parity mode on tensor cores).  DCGC_GEMM_BF16 (not built
-// yet) is the same pipeline with one kind::f16 MMA.
-//
-// Pipeline of one CTA (one 128-row tile of one degree bucket x one 128-column tile):
-//   * 8 producer warps in two groups that take alternate K chunks: LDG.128 of the fp32 operands
-//     ([X | S] concatenated along K for the forward, G for dgrad; weights pre-split and pre-transposed
-//     by tc_prep_weights), hi/lo split in registers, STS.128 into the canonical K-major SWIZZLE_128B
-//     layout, fence.proxy.async, mbarrier arrive;
-//   * 1 MMA warp: one lane waits on the "full" mbarrier of a stage, issues 4 K-steps x 3 tcgen05.mma
-//     (M=128, N=128, K=8) and tcgen05.commit's the stage's "empty" mbarrier; after the last chunk it
-//     commits the "accumulator ready" mbarrier;
-//   * epilogue (producer warps 0-3, which own TMEM lanes 32w..32w+31): tcgen05.ld 32 columns at a
-//     time, bias + activation, transpose through shared memory, 512-byte coalesced row stores.
-// 3 stages x (A hi, A lo, B hi, B lo) x 16 KB = 192 KB of shared memory, 128 TMEM columns.
+// Arithmetic modes (template parameter NT = number of MMA terms per product):
+//   DCGC_GEMM_TF32X3 (NT = 3): every fp32 operand is split into tf32 hi + lo parts and three kind::tf32 MMAs
+//     (lo*hi + hi*lo + hi*hi) are accumulated in fp32 in TMEM: ~2^-21 relative error per product, i.e.
+//     fp32-grade results (the 1e-5 parity mode on tensor cores);
+//   DCGC_GEMM_BF16 (NT = 1): both operands are rounded to bfloat16 (round to nearest even) and multiplied by
+//     ONE MMA with fp32 accumulation — bit-for-bit the arithmetic of a bf16 x bf16 -> fp32 tensor-core GEMM
+//     (every bf16 value is exactly representable in the tf32 container the tile is stored in), the 2e-2 mode.
+//     Half the shared-memory tiles and a third of the MMAs of TF32X3; native 2-byte kind::f16 tiles would halve
+//     the tile bytes again and are the next step.
+// Kernels: tc_gemm_kernel_v3 (forward / dgrad / linear), tc_wgrad_kernel (weight gradient), tc_prep_image.
 #include <stdlib.h>
 
 #include <map>
@@ -30,14 +24,9 @@ constexpr int TC_BM = 128;        // rows per tile (UMMA M)
 constexpr int TC_BN = 128;        // columns per tile (UMMA N)
 constexpr int TC_BK = 32;         // fp32 elements per K chunk = one 128-byte swizzle row
 constexpr int TC_UK = 8;          // tf32 UMMA K
-constexpr int TC_STAGES = 3;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KB
-constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;         // A hi, A lo, B hi, B lo
 constexpr int TC_PRODUCER_WARPS = 8;
 constexpr int TC_GROUP_THREADS = 128;                     // one producer group
-constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 1) * 32;  // + MMA warp
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 + 256;
-constexpr int TC_EPI_LD = TC_BN + 4;                      // padded row of the epilogue staging tile
 
 struct TcArgs {
   const float* a1; int64_t ld_a1; int k1;
@@ -130,6 +119,17 @@ __device__ __forceinline__ float tf32_hi(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+// round to nearest even to bfloat16 precision, kept in an fp32 container
+__device__ __forceinline__ float bf16_round(float x) {
+  uint32_t u = __float_as_uint(x);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return __uint_as_float(u & 0xffff0000u);
+}
+template <int NT>
+__device__ __forceinline__ float term_hi(float x) { return NT == 3 ? tf32_hi(x) : bf16_round(x); }
+__device__ __forceinline__ float4 round4_bf16(const float4 v) {
+  return make_float4(bf16_round(v.x), bf16_round(v.y), bf16_round(v.z), bf16_round(v.w));
+}
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
   lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
@@ -154,222 +154,6 @@ __device__ __forceinline__ float tc_act(float v, int act) {
   return v;
 }
 
-// ------------------------------------------------------------------------------------------
-// weight preparation: dst_hi/lo[g][n][k] (k contiguous, zero padded) from
-//   TRANS=1: src[g][k][n]   (forward: W[g] is [K, N])      K split as [k1 | pad | k2 | pad]
-//   TRANS=0: src[g][n][k]   (dgrad: rows of W[g] are the outputs, its columns the contraction)
-// ------------------------------------------------------------------------------------------
-struct PrepArgs {
-  const float* src; int64_t src_group_stride;
-  float* hi; float* lo; int64_t dst_group_stride;
-  int n, n_pad, k1, k2, k1_pad, k_pad, trans, src_ld;
-  int n1, n1_pad;  // TRANS=0: destination row j maps to source row (j < n1_pad ? j : n1 + j - n1_pad)
-};
-__global__ void __launch_bounds__(256) tc_prep_weights(const PrepArgs p) {
-  const int g = blockIdx.y;
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= (int64_t)p.n_pad * p.k_pad) return;
-  const int nn = (int)(i / p.k_pad), kk = (int)(i - (int64_t)nn * p.k_pad);
-  float v = 0.f;
-  if (p.trans) {
-    int ks = -1;
-    if (kk < p.k1_pad) { if (kk < p.k1) ks = kk; }
-    else if (kk - p.k1_pad < p.k2) ks = p.k1 + (kk - p.k1_pad);
-    if (nn < p.n && ks >= 0) v = __ldg(p.src + g * p.src_group_stride + (int64_t)ks * p.src_ld + nn);
-  } else {
-    int js = -1;
-    if (nn < p.n1_pad) { if (nn < p.n1) js = nn; }
-    else if (p.n1 + (nn - p.n1_pad) < p.n) js = p.n1 + (nn - p.n1_pad);
-    if (js >= 0 && kk < p.k1) v = __ldg(p.src + g * p.src_group_stride + (int64_t)js * p.src_ld + kk);
-  }
-  const float h = tf32_hi(v);
-  p.hi[g * p.dst_group_stride + i] = h;
-  p.lo[g * p.dst_group_stride + i] = v - h;
-}
-
-// ------------------------------------------------------------------------------------------
-// the GEMM kernel
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcArgs p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // stage tiles need 1024-byte alignment
-  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar_base = base + TC_STAGES * TC_STAGE_BYTES;
-  // barriers: full[s] at +8*s, empty[s] at +8*(3+s), accumulator-ready at +48, tmem pointer at +64
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + TC_STAGES * TC_STAGE_BYTES + 64);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int row0, rows, g;
-  if (p.tiles) {
-    const int4 t = __ldg(reinterpret_cast<const int4*>(p.tiles) + blockIdx.x);
-    row0 = t.x; rows = t.y; g = t.z;
-  } else {
-    row0 = blockIdx.x * TC_BM;
-    rows = (int)min((int64_t)TC_BM, p.n_rows - row0);
-    g = 0;
-  }
-  const int n0 = blockIdx.y * TC_BN;
-  const int N = p.n1 + p.n2;
-  const int chunks1 = (p.k1 + TC_BK - 1) / TC_BK, chunks2 = (p.k2 + TC_BK - 1) / TC_BK;
-  const int total = chunks1 + chunks2;
-
-  if (tid == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(bar_base + 8 * s, TC_GROUP_THREADS);
-      mbar_init(bar_base + 8 * (TC_STAGES + s), 1);
-    }
-    mbar_init(bar_base + 48, 1);
-    fence_barrier_init();
-  }
-  if (warp == TC_PRODUCER_WARPS) tmem_alloc(bar_base + 64, TC_BN);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp < TC_PRODUCER_WARPS) {
-    // ===== producers: group = warp / 4 takes chunks ch = group, group + 2, ... =====
-    const int group = warp >> 2, gt = tid & (TC_GROUP_THREADS - 1);
-    const float* bhi = p.bhi + (int64_t)g * p.b_group_stride + (int64_t)n0 * p.k_pad;
-    const float* blo = p.blo + (int64_t)g * p.b_group_stride + (int64_t)n0 * p.k_pad;
-    for (int ch = group; ch < total; ch += 2) {
-      const int s = ch % TC_STAGES, use = ch / TC_STAGES;
-      const float* src; int64_t ld; int ksrc, kbase; bool vec;
-      if (ch < chunks1) { src = p.a1; ld = p.ld_a1; ksrc = p.k1; kbase = ch * TC_BK; vec = p.a1_vec; }
-      else { src = p.a2; ld = p.ld_a2; ksrc = p.k2; kbase = (ch - chunks1) * TC_BK; vec = p.a2_vec; }
-      // issue every global load of this chunk first (8 A + 16 B float4 per thread in flight)
-      float4 ra[8], rh[8], rl[8];
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int f = gt + it * TC_GROUP_THREADS, r = f >> 3, k = kbase + 4 * (f & 7);
-        ra[it] = r < rows ? ld4_masked(src + (int64_t)(row0 + r) * ld + k, ksrc - k, vec)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int f = gt + it * TC_GROUP_THREADS, r = f >> 3, c = f & 7;
-        const int64_t o = (int64_t)r * p.k_pad + (int64_t)ch * TC_BK + 4 * c;
-        rh[it] = __ldg(reinterpret_cast<const float4*>(bhi + o));
-        rl[it] = __ldg(reinterpret_cast<const float4*>(blo + o));
-      }
-      mbar_wait(bar_base + 8 * (TC_STAGES + s), (use & 1) ^ 1);   // stage free?
-      uint8_t* st = sm + s * TC_STAGE_BYTES;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int f = gt + it * TC_GROUP_THREADS;
-        const uint32_t o = swz(f >> 3, f & 7);
-        float4 hi, lo;
-        split4(ra[it], hi, lo);
-        *reinterpret_cast<float4*>(st + o) = hi;
-        *reinterpret_cast<float4*>(st + TC_TILE_BYTES + o) = lo;
-        *reinterpret_cast<float4*>(st + 2 * TC_TILE_BYTES + o) = rh[it];
-        *reinterpret_cast<float4*>(st + 3 * TC_TILE_BYTES + o) = rl[it];
-      }
-      fence_proxy_async();               // generic-proxy writes -> visible to the tensor core
-      mbar_arrive(bar_base + 8 * s);
-    }
-  } else if (lane == 0) {
-    // ===== MMA issuer (one thread) =====
-    for (int ch = 0; ch < total; ++ch) {
-      const int s = ch % TC_STAGES, use = ch / TC_STAGES;
-      mbar_wait(bar_base + 8 * s, use & 1);
-      tc_fence_after();
-      const uint32_t sa = base + s * TC_STAGE_BYTES;
-#pragma unroll
-      for (int k = 0; k < TC_BK / TC_UK; ++k) {
-        const uint32_t ko = k * TC_UK * 4;
-        const uint64_t ahi = make_desc(sa + ko), alo = make_desc(sa + TC_TILE_BYTES + ko);
-        const uint64_t bhi = make_desc(sa + 2 * TC_TILE_BYTES + ko), blo = make_desc(sa + 3 * TC_TILE_BYTES + ko);
-        umma_tf32(tmem, alo, bhi, kIdescTf32, (ch | k) != 0);
-        umma_tf32(tmem, ahi, blo, kIdescTf32, 1);
-        umma_tf32(tmem, ahi, bhi, kIdescTf32, 1);
-      }
-      umma_commit(bar_base + 8 * (TC_STAGES + s));   // frees the stage when these MMAs retire
-    }
-    umma_commit(bar_base + 48);                       // accumulator complete
-  }
-
-  // ===== epilogue: warps 0-3 own TMEM lanes [32*warp, 32*warp+32) =====
-  if (warp < 4) {
-    if (total > 0) {
-      mbar_wait(bar_base + 48, 0);
-      tc_fence_after();
-    }
-    float* stage = reinterpret_cast<float*>(sm) + warp * 32 * TC_EPI_LD;   // reuses the pipeline stages
-    const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_group_stride : nullptr;
-#pragma unroll 1
-    for (int cb = 0; cb < TC_BN; cb += 32) {
-      uint32_t v[32];
-      if (total > 0) {
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cb, v);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = 0u;
-      }
-#pragma unroll
-      for (int i = 0; i < 32; i += 4) {
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int c = n0 + cb + i + e;
-          float t = __uint_as_float(v[i + e]);
-          if (bias && c < N) t += __ldg(bias + c);
-          o[e] = tc_act(t, p.act);
-        }
-        *reinterpret_cast<float4*>(stage + lane * TC_EPI_LD + cb + i) = make_float4(o[0], o[1], o[2], o[3]);
-      }
-    }
-    __syncwarp();
-    // coalesced stores: one row (128 columns = 32 lanes x float4) per iteration
-    const int c = n0 + 4 * lane;
-    for (int r = 0; r < 32; ++r) {
-      const int row = warp * 32 + r;
-      if (row >= rows) break;
-      const int64_t grow = row0 + row;
-      const float4 o = *reinterpret_cast<const float4*>(stage + r * TC_EPI_LD + 4 * lane);
-      if (c + 3 < p.n1 && p.c1_vec) {
-        *reinterpret_cast<float4*>(p.c1 + grow * p.ld_c1 + c) = o;
-      } else if (c >= p.n1 && c + 3 < N && p.c2_vec && ((c - p.n1) & 3) == 0) {
-        *reinterpret_cast<float4*>(p.c2 + grow * p.ld_c2 + (c - p.n1)) = o;
-      } else {
-        const float e[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int cc = c + q;
-          if (cc < p.n1) { if (p.c1) p.c1[grow * p.ld_c1 + cc] = e[q]; }
-          else if (cc < N) { if (p.c2) p.c2[grow * p.ld_c2 + (cc - p.n1)] = e[q]; }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == TC_PRODUCER_WARPS) {
-    tc_fence_after();
-    tmem_dealloc(tmem, TC_BN);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// v2: persistent, weight-resident kernel.  One CTA per SM keeps the (hi, lo) weight slice of its
-// column range resident in shared memory (reloaded only when the degree bucket of its tiles changes:
-// tiles are degree-sorted), streams A chunks through a small ring, double-buffers the accumulator
-// in TMEM so that the epilogue of tile i overlaps the MMAs of tile i+1, and stores straight from
-// registers (each thread owns one output row: 32 columns = one full 128-byte line per tcgen05.ld).
-//   warps 0-3  epilogue (TMEM lane quadrant = warp)      warps 4-11 producers (two groups)
-//   warp 12    MMA issuer + TMEM allocation
-// ------------------------------------------------------------------------------------------
-constexpr int V2_THREADS = 13 * 32;
-constexpr int V2_MAX_STAGES = 4;
-constexpr int V2_A_STAGE_BYTES = 2 * TC_TILE_BYTES;   // A hi + A lo
-
-struct TcArgs2 {
-  TcArgs a;
-  int n_row_tiles;   // number of 128-row tiles
-  int n_stages;      // A ring depth
-  int b_bytes;       // resident weight bytes (hi + lo) per CTA
-};
-
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ void tile_of(const TcArgs& p, int t, int& row0, int& rows, int& g) {
@@ -383,200 +167,6 @@ __device__ __forceinline__ void tile_of(const TcArgs& p, int t, int& row0, int& 
   }
 }
 
-template <int NCTA>
-__global__ void __launch_bounds__(V2_THREADS, 1) tc_gemm_kernel_v2(const TcArgs2 q) {
-  const TcArgs& p = q.a;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  const int S = q.n_stages;
-  const uint32_t b_half = (uint32_t)q.b_bytes / 2;                 // hi region, then lo region
-  const uint32_t a_base = base + q.b_bytes;                        // A ring
-  const uint32_t bar_base = a_base + S * V2_A_STAGE_BYTES;
-  // barriers: full[s] +8s, empty[s] +32+8s, tmem_full[a] +64+8a, tmem_empty[a] +80+8a, tmem slot +96
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + q.b_bytes + S * V2_A_STAGE_BYTES + 96);
-  constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NCTA >> 3) << 17) |
-                              ((uint32_t)(TC_BM >> 4) << 24);
-  constexpr uint32_t kBChunk = NCTA * 128;                          // bytes of one [NCTA x 32] weight chunk
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int P = gridDim.x, pid = blockIdx.x;
-  const int n0 = blockIdx.y * NCTA;
-  const int N = p.n1 + p.n2;
-  const int chunks1 = (p.k1 + TC_BK - 1) / TC_BK, chunks2 = (p.k2 + TC_BK - 1) / TC_BK;
-  const int total = chunks1 + chunks2;
-  const int my_tiles = pid < q.n_row_tiles ? (q.n_row_tiles - pid + P - 1) / P : 0;
-
-  if (tid == 0) {
-    for (int s = 0; s < V2_MAX_STAGES; ++s) {
-      mbar_init(bar_base + 8 * s, TC_GROUP_THREADS);
-      mbar_init(bar_base + 32 + 8 * s, 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_base + 64 + 8 * a, 1);
-      mbar_init(bar_base + 80 + 8 * a, 128);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 12) tmem_alloc(bar_base + 96, 2 * NCTA);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp >= 4 && warp < 12) {
-    // ===================== producers =====================
-    const int ptid = tid - 128, group = ptid >> 7, gt = ptid & 127;
-    int cur_g = -1, cc = 0;
-    for (int it = 0; it < my_tiles; ++it) {
-      int row0, rows, g;
-      tile_of(p, pid + it * P, row0, rows, g);
-      if (g != cur_g) {
-        // every chunk issued so far must have been consumed before the resident weights change
-        if (cc > 0) {
-          int lastc = ((cc - 1) & 1) == group ? cc - 1 : cc - 2;
-          if (lastc >= 0) mbar_wait(bar_base + 32 + 8 * (lastc % S), (lastc / S) & 1);
-        }
-        named_bar_sync(1, 256);
-        const float* bh = p.bhi + (int64_t)g * p.b_group_stride + (int64_t)n0 * p.k_pad;
-        const float* bl = p.blo + (int64_t)g * p.b_group_stride + (int64_t)n0 * p.k_pad;
-        const int per_chunk = NCTA * 8;                       // float4 per chunk
-        for (int f = ptid; f < total * per_chunk; f += 256) {
-          const int ch = f / per_chunk, w = f - ch * per_chunk, r = w >> 3, c = w & 7;
-          const int64_t o = (int64_t)r * p.k_pad + ch * TC_BK + 4 * c;
-          const uint32_t so = ch * kBChunk + swz(r, c);
-          *reinterpret_cast<float4*>(sm + so) = __ldg(reinterpret_cast<const float4*>(bh + o));
-          *reinterpret_cast<float4*>(sm + b_half + so) = __ldg(reinterpret_cast<const float4*>(bl + o));
-        }
-        fence_proxy_async();
-        named_bar_sync(1, 256);
-        cur_g = g;
-      }
-      for (int ch = 0; ch < total; ++ch, ++cc) {
-        if ((cc & 1) != group) continue;
-        const int s = cc % S, use = cc / S;
-        const float* src; int64_t ld; int ksrc, kbase; bool vec;
-        if (ch < chunks1) { src = p.a1; ld = p.ld_a1; ksrc = p.k1; kbase = ch * TC_BK; vec = p.a1_vec; }
-        else { src = p.a2; ld = p.ld_a2; ksrc = p.k2; kbase = (ch - chunks1) * TC_BK; vec = p.a2_vec; }
-        float4 ra[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int f = gt + u * TC_GROUP_THREADS, r = f >> 3, k = kbase + 4 * (f & 7);
-          ra[u] = r < rows ? ld4_masked(src + (int64_t)(row0 + r) * ld + k, ksrc - k, vec)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        mbar_wait(bar_base + 32 + 8 * s, (use & 1) ^ 1);
-        uint8_t* st = sm + q.b_bytes + s * V2_A_STAGE_BYTES;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int f = gt + u * TC_GROUP_THREADS;
-          const uint32_t o = swz(f >> 3, f & 7);
-          float4 hi, lo;
-          split4(ra[u], hi, lo);
-          *reinterpret_cast<float4*>(st + o) = hi;
-          *reinterpret_cast<float4*>(st + TC_TILE_BYTES + o) = lo;
-        }
-        fence_proxy_async();
-        mbar_arrive(bar_base + 8 * s);
-      }
-    }
-  } else if (warp == 12) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int cc = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const int acc = it & 1;
-        mbar_wait(bar_base + 80 + 8 * acc, ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
-        tc_fence_after();
-        const uint32_t d = tmem + acc * NCTA;
-        for (int ch = 0; ch < total; ++ch, ++cc) {
-          const int s = cc % S;
-          mbar_wait(bar_base + 8 * s, (cc / S) & 1);
-          tc_fence_after();
-          const uint32_t sa = a_base + s * V2_A_STAGE_BYTES, sb = base + ch * kBChunk;
-#pragma unroll
-          for (int k = 0; k < TC_BK / TC_UK; ++k) {
-            const uint32_t ko = k * TC_UK * 4;
-            const uint64_t ahi = make_desc(sa + ko), alo = make_desc(sa + TC_TILE_BYTES + ko);
-            const uint64_t bhi = make_desc(sb + ko), blo = make_desc(sb + b_half + ko);
-            umma_tf32(d, alo, bhi, kIdesc, (ch | k) != 0);
-            umma_tf32(d, ahi, blo, kIdesc, 1);
-            umma_tf32(d, ahi, bhi, kIdesc, 1);
-          }
-          umma_commit(bar_base + 32 + 8 * s);
-        }
-        umma_commit(bar_base + 64 + 8 * acc);
-      }
-    }
-  } else {
-    // ===================== epilogue (warps 0-3) =====================
-    for (int it = 0; it < my_tiles; ++it) {
-      int row0, rows, g;
-      tile_of(p, pid + it * P, row0, rows, g);
-      const int acc = it & 1;
-      mbar_wait(bar_base + 64 + 8 * acc, (it >> 1) & 1);
-      tc_fence_after();
-      const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_group_stride : nullptr;
-      const int row = warp * 32 + lane;
-      const int64_t grow = row0 + row;
-#pragma unroll 1
-      for (int cb = 0; cb < NCTA; cb += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + acc * NCTA + cb, v);
-        if (row < rows) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const int c = n0 + cb + i;
-            if (c >= N) break;
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float t = __uint_as_float(v[i + e]);
-              if (bias && c + e < N) t += __ldg(bias + c + e);
-              o[e] = tc_act(t, p.act);
-            }
-            if (c + 3 < p.n1 && p.c1_vec) {
-              *reinterpret_cast<float4*>(p.c1 + grow * p.ld_c1 + c) = make_float4(o[0], o[1], o[2], o[3]);
-            } else if (c >= p.n1 && c + 3 < N && p.c2_vec && ((c - p.n1) & 3) == 0) {
-              *reinterpret_cast<float4*>(p.c2 + grow * p.ld_c2 + (c - p.n1)) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int cc2 = c + e;
-                if (cc2 < p.n1) { if (p.c1) p.c1[grow * p.ld_c1 + cc2] = o[e]; }
-                else if (cc2 < N) { if (p.c2) p.c2[grow * p.ld_c2 + (cc2 - p.n1)] = o[e]; }
-              }
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(bar_base + 80 + 8 * acc);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 12) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 2 * NCTA);
-  }
-}
-
-
-
-// ------------------------------------------------------------------------------------------
-// v3: persistent kernel, weights STREAMED per K chunk by the TMA engine.
-//   * tc_prep_image writes the split weights as ready-made shared-memory images: for every
-//     (group, column tile, K chunk) one 32 KB block = [B hi | B lo], each a K-major SWIZZLE_128B
-//     [128 x 32] tile, so a chunk of B is ONE 1-D bulk copy (cp.async.bulk, UBLKCP) issued by a
-//     dedicated warp with mbarrier complete_tx — no tensor map, no register staging, and the full
-//     128-column tile at any K (the resident-weight v2 kernel had to halve N for K = 256 and read
-//     A twice);
-//   * A producers (two groups of 4 warps taking alternate chunks) keep TWO chunks of 128-bit loads
-//     in flight per group (two register sets) across tile boundaries;
-//   * double-buffered TMEM accumulators: the epilogue of tile i overlaps the MMAs of tile i+1.
-//   warps 0-3 epilogue | 4-11 A producers | 12 MMA issuer + TMEM | 13 B loader (TMA)
-// ------------------------------------------------------------------------------------------
 
 // A [32 rows x 32 cols] accumulator block arrives from TMEM as (lane = row, v[0..31] = columns).  Storing it
 // directly makes every STG.128 touch 32 different 128-byte lines with 16 bytes each (ncu: 32 half-filled
@@ -601,9 +191,13 @@ __device__ __forceinline__ void warp_transpose_store(float* stg, int lane, const
 }
 
 constexpr int V3_THREADS = 14 * 32;
-constexpr int V3_STAGES = 3;
-constexpr int V3_STAGE_BYTES = 4 * TC_TILE_BYTES;   // A hi, A lo, B hi, B lo
-constexpr int V3_SMEM_BYTES = V3_STAGES * V3_STAGE_BYTES + 1024 + 256 + EPI_BYTES;
+// NT = 3: 3 stages x (A hi, A lo, B hi, B lo); NT = 1: 6 stages x (A, B); 192 KB either way
+template <int NT> struct V3Cfg {
+  static constexpr int kStages = NT == 3 ? 3 : 6;
+  static constexpr int kATiles = NT == 3 ? 2 : 1;
+  static constexpr int kStageBytes = 2 * kATiles * TC_TILE_BYTES;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + EPI_BYTES;
+};
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -618,10 +212,12 @@ struct ImgArgs {
   float* img;                 // [G][n_tiles][chunks][2][128 x 32 swizzled]
   int n, k1, k2, k1_pad, trans, src_ld, n_tiles, chunks;
 };
+template <int NT>
 __global__ void __launch_bounds__(256) tc_prep_image(const ImgArgs p) {
   // one block = a quarter (1024 elements) of one [128 x 32] tile; 4 independent loads per thread
+  constexpr int kTiles = NT == 3 ? 2 : 1;   // (hi, lo) or the single bf16-rounded tile
   const int g = blockIdx.z, nt = blockIdx.y, ch = blockIdx.x >> 2, quarter = blockIdx.x & 3;
-  float* blk = p.img + (((int64_t)g * p.n_tiles + nt) * p.chunks + ch) * (2 * TC_BM * TC_BK);
+  float* blk = p.img + (((int64_t)g * p.n_tiles + nt) * p.chunks + ch) * (kTiles * TC_BM * TC_BK);
   float v[4];
   int r[4], kl[4];
 #pragma unroll
@@ -644,10 +240,10 @@ __global__ void __launch_bounds__(256) tc_prep_image(const ImgArgs p) {
   }
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    const float h = tf32_hi(v[u]);
+    const float h = term_hi<NT>(v[u]);
     const uint32_t o = (swz(r[u], kl[u] >> 2) >> 2) + (kl[u] & 3);   // float index inside the 16 KB tile
     blk[o] = h;
-    blk[TC_BM * TC_BK + o] = v[u] - h;
+    if (NT == 3) blk[TC_BM * TC_BK + o] = v[u] - h;
   }
 }
 
@@ -660,15 +256,18 @@ struct TcArgs3 {
                   // 128 no weight-image kernel — results are wrong, timing only
 };
 
+template <int NT>
 __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3 q) {
   const TcArgs& p = q.a;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  constexpr int S = V3_STAGES;
+  constexpr int S = V3Cfg<NT>::kStages;
+  constexpr int V3_STAGE_BYTES = V3Cfg<NT>::kStageBytes;
+  constexpr int kATiles = V3Cfg<NT>::kATiles;               // A tiles per stage; the B tiles follow them
   const uint32_t bar_base = base + S * V3_STAGE_BYTES;
-  // barriers: full[s] +8s, empty[s] +32+8s, tmem_full[a] +64+8a, tmem_empty[a] +80+8a, tmem slot +96
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + S * V3_STAGE_BYTES + 96);
+  // barriers: full[s] +8s, empty[s] +48+8s, tmem_full[a] +96+8a, tmem_empty[a] +112+8a, tmem slot +128
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + S * V3_STAGE_BYTES + 128);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int P = gridDim.x, pid = blockIdx.x;
@@ -682,15 +281,15 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
       mbar_init(bar_base + 8 * s, 4 + 1);        // 4 producer warps of one group + the B loader
-      mbar_init(bar_base + 32 + 8 * s, 1);
+      mbar_init(bar_base + 48 + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_base + 64 + 8 * a, 1);
-      mbar_init(bar_base + 80 + 8 * a, 128);
+      mbar_init(bar_base + 96 + 8 * a, 1);
+      mbar_init(bar_base + 112 + 8 * a, 128);
     }
     fence_barrier_init();
   }
-  if (warp == 12) tmem_alloc(bar_base + 96, 2 * TC_BN);
+  if (warp == 12) tmem_alloc(bar_base + 128, 2 * TC_BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -716,17 +315,21 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
     };
     auto commit = [&](const float4 (&r)[8], int cc) {
       const int s = cc % S, use = cc / S;
-      mbar_wait(bar_base + 32 + 8 * s, (use & 1) ^ 1);
+      mbar_wait(bar_base + 48 + 8 * s, (use & 1) ^ 1);
       uint8_t* st = sm + s * V3_STAGE_BYTES;
       if (!(q.knockout & 16)) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
           const int f = gt + u * TC_GROUP_THREADS;
           const uint32_t o = swz(f >> 3, f & 7);
-          float4 hi, lo;
-          split4(r[u], hi, lo);
-          *reinterpret_cast<float4*>(st + o) = hi;
-          *reinterpret_cast<float4*>(st + TC_TILE_BYTES + o) = lo;
+          if (NT == 3) {
+            float4 hi, lo;
+            split4(r[u], hi, lo);
+            *reinterpret_cast<float4*>(st + o) = hi;
+            *reinterpret_cast<float4*>(st + TC_TILE_BYTES + o) = lo;
+          } else {
+            *reinterpret_cast<float4*>(st + o) = round4_bf16(r[u]);
+          }
         }
       }
       if (!(q.knockout & 64)) fence_proxy_async();
@@ -748,14 +351,15 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
       for (int it = 0; it < my_tiles; ++it) {
         int row0, rows, g;
         tile_of(p, pid + it * P, row0, rows, g);
-        const float* src = q.img + ((int64_t)g * q.n_tiles_n + blockIdx.y) * total * (2 * TC_BM * TC_BK);
+        constexpr int kBFloats = kATiles * TC_BM * TC_BK;          // floats of one chunk of B (hi [+ lo])
+        constexpr uint32_t kBBytes = kATiles * TC_TILE_BYTES;
+        const float* src = q.img + ((int64_t)g * q.n_tiles_n + blockIdx.y) * total * kBFloats;
         for (int ch = 0; ch < total; ++ch, ++cc) {
           const int s = cc % S, use = cc / S;
-          mbar_wait(bar_base + 32 + 8 * s, (use & 1) ^ 1);
+          mbar_wait(bar_base + 48 + 8 * s, (use & 1) ^ 1);
           if (q.knockout & 8) { mbar_arrive(bar_base + 8 * s); continue; }
-          mbar_arrive_expect_tx(bar_base + 8 * s, 2 * TC_TILE_BYTES);
-          bulk_g2s(base + s * V3_STAGE_BYTES + 2 * TC_TILE_BYTES, src + (int64_t)ch * (2 * TC_BM * TC_BK),
-                   2 * TC_TILE_BYTES, bar_base + 8 * s);
+          mbar_arrive_expect_tx(bar_base + 8 * s, kBBytes);
+          bulk_g2s(base + s * V3_STAGE_BYTES + kBBytes, src + (int64_t)ch * kBFloats, kBBytes, bar_base + 8 * s);
         }
       }
     }
@@ -765,7 +369,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
       int cc = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const int acc = it & 1;
-        mbar_wait(bar_base + 80 + 8 * acc, ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+        mbar_wait(bar_base + 112 + 8 * acc, ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
         tc_fence_after();
         const uint32_t d = tmem + acc * TC_BN;
         for (int ch = 0; ch < total; ++ch, ++cc) {
@@ -777,16 +381,20 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
 #pragma unroll
             for (int k = 0; k < TC_BK / TC_UK; ++k) {
               const uint32_t ko = k * TC_UK * 4;
-              const uint64_t ahi = make_desc(sa + ko), alo = make_desc(sa + TC_TILE_BYTES + ko);
-              const uint64_t bhi = make_desc(sa + 2 * TC_TILE_BYTES + ko), blo = make_desc(sa + 3 * TC_TILE_BYTES + ko);
-              umma_tf32(d, alo, bhi, kIdescTf32, (ch | k) != 0);
-              umma_tf32(d, ahi, blo, kIdescTf32, 1);
-              umma_tf32(d, ahi, bhi, kIdescTf32, 1);
+              if (NT == 3) {
+                const uint64_t ahi = make_desc(sa + ko), alo = make_desc(sa + TC_TILE_BYTES + ko);
+                const uint64_t bhi = make_desc(sa + 2 * TC_TILE_BYTES + ko), blo = make_desc(sa + 3 * TC_TILE_BYTES + ko);
+                umma_tf32(d, alo, bhi, kIdescTf32, (ch | k) != 0);
+                umma_tf32(d, ahi, blo, kIdescTf32, 1);
+                umma_tf32(d, ahi, bhi, kIdescTf32, 1);
+              } else {
+                umma_tf32(d, make_desc(sa + ko), make_desc(sa + TC_TILE_BYTES + ko), kIdescTf32, (ch | k) != 0);
+              }
             }
           }
-          umma_commit(bar_base + 32 + 8 * s);
+          umma_commit(bar_base + 48 + 8 * s);
         }
-        umma_commit(bar_base + 64 + 8 * acc);
+        umma_commit(bar_base + 96 + 8 * acc);
       }
     }
   } else {
@@ -806,7 +414,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
       if (q.knockout & 1) rows = 0;
       const int acc = it & 1;
       if (total > 0) {
-        mbar_wait(bar_base + 64 + 8 * acc, (it >> 1) & 1);
+        mbar_wait(bar_base + 96 + 8 * acc, (it >> 1) & 1);
         tc_fence_after();
       }
       const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_group_stride : nullptr;
@@ -863,7 +471,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
 #undef DCGC_FOLD
       }
       tc_fence_before();
-      mbar_arrive(bar_base + 80 + 8 * acc);
+      mbar_arrive(bar_base + 112 + 8 * acc);
     }
     if (p.stats) {
       // lanes l, l+8, l+16, l+24 hold the same columns (different rows): fixed-order butterfly, then the four
@@ -919,18 +527,19 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
 // The partials are summed in chunk order by wgrad_reduce_kernel (gemm_simt.cu).
 // ------------------------------------------------------------------------------------------
 constexpr int WG_THREADS = 9 * 32;
-constexpr int WG_STAGES = 2;
 
-template <int MT>
+template <int MT, int NT>
 __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgradArgs p) {
   constexpr int NL = 4 * (MT + 1);                              // float4 loads per thread per chunk
-  constexpr int STAGE_BYTES = (2 * MT + 2) * TC_TILE_BYTES;     // (A hi, A lo) x MT, G hi, G lo
+  constexpr int TPO = NT == 3 ? 2 : 1;                          // tiles per operand: (hi, lo) or one
+  constexpr int WG_STAGES = NT == 3 ? 2 : 4;
+  constexpr int STAGE_BYTES = TPO * (MT + 1) * TC_TILE_BYTES;   // A tiles x MT, then the G tile(s)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t bar_base = base + WG_STAGES * STAGE_BYTES;
-  // barriers: full[s] +8s, empty[s] +16+8s, accumulator-ready +32, tmem slot +40
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + WG_STAGES * STAGE_BYTES + 40);
+  // barriers: full[s] +8s, empty[s] +32+8s, accumulator-ready +64, tmem slot +72
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + WG_STAGES * STAGE_BYTES + 72);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int chunk = blockIdx.x;
@@ -946,12 +555,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
   if (tid == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
       mbar_init(bar_base + 8 * s, TC_PRODUCER_WARPS);
-      mbar_init(bar_base + 16 + 8 * s, 1);
+      mbar_init(bar_base + 32 + 8 * s, 1);
     }
-    mbar_init(bar_base + 32, 1);
+    mbar_init(bar_base + 64, 1);
     fence_barrier_init();
   }
-  if (warp == TC_PRODUCER_WARPS) tmem_alloc(bar_base + 40, MT * TC_BN);
+  if (warp == TC_PRODUCER_WARPS) tmem_alloc(bar_base + 72, MT * TC_BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1000,26 +609,27 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
       }
     };
     auto sstore = [&](const float4 (&r)[NL], int c) {
-      const int s = c & 1, use = c >> 1;
-      mbar_wait(bar_base + 16 + 8 * s, (use & 1) ^ 1);           // the MMAs that read this stage retired
+      const int s = c % WG_STAGES, use = c / WG_STAGES;
+      mbar_wait(bar_base + 32 + 8 * s, (use & 1) ^ 1);           // the MMAs that read this stage retired
       uint8_t* st = sm + s * STAGE_BYTES;
       const uint32_t kofs = (uint32_t)(lane & 3) * 4;
       const int kc = lane >> 2;
 #pragma unroll
       for (int t = 0; t <= MT; ++t) {
-        uint8_t* hi_t = st + 2 * t * TC_TILE_BYTES;
+        uint8_t* hi_t = st + TPO * t * TC_TILE_BYTES;
         uint8_t* lo_t = hi_t + TC_TILE_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float4 hi, lo;
-          split4(r[4 * t + j], hi, lo);
+          if (NT == 3) { split4(r[4 * t + j], hi, lo); }
+          else { hi = round4_bf16(r[4 * t + j]); lo = hi; }
           const float h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const int rr = col + 4 * j + e;                       // row of the K-major tile
             const uint32_t o = (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128 + ((kc ^ (rr & 7)) << 4)) + kofs;
             *reinterpret_cast<float*>(hi_t + o) = h[e];
-            *reinterpret_cast<float*>(lo_t + o) = l[e];
+            if (NT == 3) *reinterpret_cast<float*>(lo_t + o) = l[e];
           }
         }
       }
@@ -1054,32 +664,36 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
     }
   } else if (lane == 0) {
     for (int c = 0; c < steps; ++c) {
-      const int s = c & 1;
-      mbar_wait(bar_base + 8 * s, (c >> 1) & 1);
+      const int s = c % WG_STAGES;
+      mbar_wait(bar_base + 8 * s, (c / WG_STAGES) & 1);
       tc_fence_after();
       const uint32_t sa = base + s * STAGE_BYTES;
-      const uint32_t sg_hi = sa + 2 * MT * TC_TILE_BYTES, sg_lo = sg_hi + TC_TILE_BYTES;
+      const uint32_t sg_hi = sa + TPO * MT * TC_TILE_BYTES, sg_lo = sg_hi + TC_TILE_BYTES;
 #pragma unroll
       for (int t = 0; t < MT; ++t) {
-        const uint32_t a_hi = sa + 2 * t * TC_TILE_BYTES, a_lo = a_hi + TC_TILE_BYTES;
+        const uint32_t a_hi = sa + TPO * t * TC_TILE_BYTES, a_lo = a_hi + TC_TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < TC_BK / TC_UK; ++k) {
           const uint32_t ko = k * TC_UK * 4;
           const uint64_t ahi = make_desc(a_hi + ko), alo = make_desc(a_lo + ko);
           const uint64_t ghi = make_desc(sg_hi + ko), glo = make_desc(sg_lo + ko);
-          umma_tf32(tmem + t * TC_BN, alo, ghi, kIdescTf32, (c | k) != 0);
-          umma_tf32(tmem + t * TC_BN, ahi, glo, kIdescTf32, 1);
-          umma_tf32(tmem + t * TC_BN, ahi, ghi, kIdescTf32, 1);
+          if (NT == 3) {
+            umma_tf32(tmem + t * TC_BN, alo, ghi, kIdescTf32, (c | k) != 0);
+            umma_tf32(tmem + t * TC_BN, ahi, glo, kIdescTf32, 1);
+            umma_tf32(tmem + t * TC_BN, ahi, ghi, kIdescTf32, 1);
+          } else {
+            umma_tf32(tmem + t * TC_BN, ahi, ghi, kIdescTf32, (c | k) != 0);
+          }
         }
       }
-      umma_commit(bar_base + 16 + 8 * s);
+      umma_commit(bar_base + 32 + 8 * s);
     }
-    umma_commit(bar_base + 32);
+    umma_commit(bar_base + 64);
   }
 
   if (warp < 4) {
     if (steps > 0) {
-      mbar_wait(bar_base + 32, 0);
+      mbar_wait(bar_base + 64, 0);
       tc_fence_after();
     }
     const bool n_vec = (p.n & 3) == 0 && (reinterpret_cast<uintptr_t>(p.ws) & 15) == 0;
@@ -1123,7 +737,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-constexpr int V2_SMEM_BUDGET = 227 * 1024 - 1024 - 256;   // after alignment slack and barriers
 
 int g_num_sms = 0;
 
@@ -1155,14 +768,14 @@ int prep_scratch(cudaStream_t st, size_t bytes, float** out) {
 int ensure_smem_attr() {
   static bool done = false;   // per process; the attribute is per function per device context
   if (!done) {
-    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v2<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        227 * 1024));
-    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v2<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        227 * 1024));
-    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v3, cudaFuncAttributeMaxDynamicSharedMemorySize, V3_SMEM_BYTES));
-    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        V3Cfg<3>::kSmemBytes));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        V3Cfg<1>::kSmemBytes));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int dev = 0;
     DCGC_CUDA_CALL(cudaGetDevice(&dev));
     DCGC_CUDA_CALL(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -1173,9 +786,10 @@ int ensure_smem_attr() {
 
 }  // namespace
 
-// Called by dcgc_group_gemm_fwd / _dgrad / dcgc_linear_* when mode == DCGC_GEMM_TF32X3.
+// Called by dcgc_group_gemm_fwd / _dgrad / dcgc_linear_* in the tensor-core modes; nt = 3 (DCGC_GEMM_TF32X3) or
+// 1 (DCGC_GEMM_BF16).
 //   trans_w = 1: w is [G][k1+k2][n] (forward);  trans_w = 0: w is [G][n1+n2][k1] (dgrad / nn.Linear forward)
-int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_t ld_a2, int k2, const float* w,
+int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2, int64_t ld_a2, int k2, const float* w,
                  int n_groups, int trans_w, const float* bias, int n1, int n2, const int32_t* tiles, int64_t n_tiles,
                  int64_t n_rows, int act, float* c1, int64_t ld_c1, float* c2, int64_t ld_c2, cudaStream_t st,
                  double* stats, int* stats_chunks) {
@@ -1187,11 +801,11 @@ int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_
   if (st_ != DCGC_OK) return st_;
   const int k1_pad = (k1 + TC_BK - 1) / TC_BK * TC_BK, k2_pad = (k2 + TC_BK - 1) / TC_BK * TC_BK;
   const int k_pad = k1_pad + k2_pad;
-  static const int variant = [] { const char* e = getenv("DCGC_TC_VARIANT"); return e ? atoi(e) : 3; }();
-  if (variant == 3 && row_tiles < (1 << 30)) {
+  if (row_tiles < (1 << 30)) {
     const int n_tiles_n = (N + TC_BN - 1) / TC_BN, chunks = k_pad / TC_BK;
     float* img = nullptr;
-    st_ = prep_scratch(st, (size_t)n_groups * n_tiles_n * (chunks > 0 ? chunks : 1) * 2 * TC_TILE_BYTES, &img);
+    const int b_tiles = nt == 3 ? 2 : 1;
+    st_ = prep_scratch(st, (size_t)n_groups * n_tiles_n * (chunks > 0 ? chunks : 1) * b_tiles * TC_TILE_BYTES, &img);
     if (st_ != DCGC_OK) return st_;
     static const int knockout = [] { const char* e = getenv("DCGC_TC_KNOCKOUT"); return e ? atoi(e) : 0; }();
     if (chunks > 0 && !(knockout & 128)) {
@@ -1201,7 +815,8 @@ int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_
       if (trans_w) { ia.src_ld = N; ia.src_group_stride = (int64_t)(k1 + k2) * N; }
       else { ia.src_ld = k1; ia.src_group_stride = (int64_t)N * k1; }
       dim3 pgrid((unsigned)chunks * 4, (unsigned)n_tiles_n, (unsigned)n_groups);
-      tc_prep_image<<<pgrid, 256, 0, st>>>(ia);
+      if (nt == 3) tc_prep_image<3><<<pgrid, 256, 0, st>>>(ia);
+      else tc_prep_image<1><<<pgrid, 256, 0, st>>>(ia);
       DCGC_CUDA_LAUNCH_CHECK("tc_prep_image");
     }
     TcArgs3 q3{};
@@ -1223,68 +838,13 @@ int dcgc_tc_gemm(const float* a1, int64_t ld_a1, int k1, const float* a2, int64_
     p3.stats = stats;
     if (stats_chunks) *stats_chunks = ctas;
     dim3 grid((unsigned)ctas, (unsigned)n_tiles_n);
-    tc_gemm_kernel_v3<<<grid, V3_THREADS, V3_SMEM_BYTES, st>>>(q3);
+    if (nt == 3) tc_gemm_kernel_v3<3><<<grid, V3_THREADS, V3Cfg<3>::kSmemBytes, st>>>(q3);
+    else tc_gemm_kernel_v3<1><<<grid, V3_THREADS, V3Cfg<1>::kSmemBytes, st>>>(q3);
     DCGC_CUDA_LAUNCH_CHECK("tc_gemm_kernel_v3");
     return DCGC_OK;
   }
-  // output column space: [0, n1) -> c1, [n1, n1+n2) -> c2 (contiguous: the kernel's epilogue maps them)
-  const int n_pad = (N + TC_BN - 1) / TC_BN * TC_BN;
-  const int64_t gstride = (int64_t)n_pad * k_pad;
-  float* prep = nullptr;
-  st_ = prep_scratch(st, (size_t)2 * n_groups * gstride * sizeof(float), &prep);
-  if (st_ != DCGC_OK) return st_;
-  PrepArgs q{};
-  q.src = w; q.hi = prep; q.lo = prep + (int64_t)n_groups * gstride; q.dst_group_stride = gstride;
-  q.n = N; q.n_pad = n_pad; q.k1 = k1; q.k2 = k2; q.k1_pad = k1_pad; q.k_pad = k_pad; q.trans = trans_w;
-  if (trans_w) { q.src_ld = N; q.src_group_stride = (int64_t)(k1 + k2) * N; q.n1 = N; q.n1_pad = n_pad; }
-  else { q.src_ld = k1; q.src_group_stride = (int64_t)N * k1; q.n1 = N; q.n1_pad = n_pad; }
-  {
-    dim3 grid((unsigned)((gstride + 255) / 256), (unsigned)n_groups);
-    tc_prep_weights<<<grid, 256, 0, st>>>(q);
-    DCGC_CUDA_LAUNCH_CHECK("tc_prep_weights");
-  }
-  if (stats) {
-    dcgc_set_error("dcgc_tc_gemm: fused column statistics need kernel variant 3");
-    return DCGC_ERR_INVALID;
-  }
-  TcArgs p{};
-  p.a1 = a1; p.ld_a1 = ld_a1; p.k1 = k1;
-  p.a2 = a2; p.ld_a2 = ld_a2; p.k2 = a2 ? k2 : 0;
-  p.bhi = q.hi; p.blo = q.lo; p.b_group_stride = gstride; p.k_pad = k_pad;
-  p.bias = bias; p.bias_group_stride = N;
-  p.n1 = n1; p.n2 = n2; p.c1 = c1; p.ld_c1 = ld_c1; p.c2 = c2; p.ld_c2 = ld_c2;
-  p.tiles = tiles; p.n_rows = n_rows; p.act = act;
-  p.a1_vec = ld_a1 % 4 == 0 && aligned16(a1);
-  p.a2_vec = a2 && ld_a2 % 4 == 0 && aligned16(a2);
-  p.c1_vec = c1 && ld_c1 % 4 == 0 && aligned16(c1);
-  p.c2_vec = c2 && ld_c2 % 4 == 0 && aligned16(c2);
-  // persistent weight-resident kernel when the (hi, lo) weight slice of a 128- or 64-column range fits
-  // next to at least two A stages; otherwise the one-tile-per-CTA kernel
-  int ncta = 0;
-  if ((int64_t)128 * k_pad * 8 + 2 * V2_A_STAGE_BYTES <= V2_SMEM_BUDGET) ncta = 128;
-  else if ((int64_t)64 * k_pad * 8 + 2 * V2_A_STAGE_BYTES <= V2_SMEM_BUDGET) ncta = 64;
-  if (ncta && row_tiles < (1 << 30)) {
-    TcArgs2 q2{};
-    q2.a = p;
-    q2.n_row_tiles = (int)row_tiles;
-    q2.b_bytes = ncta * k_pad * 8;
-    int stages = (V2_SMEM_BUDGET - q2.b_bytes) / V2_A_STAGE_BYTES;
-    q2.n_stages = stages > V2_MAX_STAGES ? V2_MAX_STAGES : stages;
-    const int slices = (N + ncta - 1) / ncta;
-    int ctas = g_num_sms / slices;
-    if (ctas < 1) ctas = 1;
-    if (ctas > row_tiles) ctas = (int)row_tiles;
-    const int smem = q2.b_bytes + q2.n_stages * V2_A_STAGE_BYTES + 1024 + 256;
-    dim3 grid((unsigned)ctas, (unsigned)slices);
-    if (ncta == 128) tc_gemm_kernel_v2<128><<<grid, V2_THREADS, smem, st>>>(q2);
-    else tc_gemm_kernel_v2<64><<<grid, V2_THREADS, smem, st>>>(q2);
-    DCGC_CUDA_LAUNCH_CHECK("tc_gemm_kernel_v2");
-  } else {
-    dim3 grid((unsigned)row_tiles, (unsigned)(n_pad / TC_BN));
-    tc_gemm_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(p);
-    DCGC_CUDA_LAUNCH_CHECK("tc_gemm_kernel");
-  }
-  return DCGC_OK;
+  dcgc_set_error("dcgc_tc_gemm: unsupported problem size");
+  return DCGC_ERR_INVALID;
 }
 
 // Stage 1 of dcgc_group_gemm_wgrad / dcgc_linear_wgrad in DCGC_GEMM_TF32X3 mode (stage 2 is the shared
@@ -1297,7 +857,7 @@ int dcgc_tc_num_sms() {
   if (ensure_smem_attr() != DCGC_OK) return 148;
   return g_num_sms > 0 ? g_num_sms : 148;
 }
-int dcgc_tc_wgrad_stage1(const DcgcWgradArgs& p_in, int chunks, cudaStream_t st) {
+int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p_in, int chunks, cudaStream_t st) {
   if (chunks <= 0) return DCGC_OK;
   int st_ = ensure_smem_attr();
   if (st_ != DCGC_OK) return st_;
@@ -1307,9 +867,15 @@ int dcgc_tc_wgrad_stage1(const DcgcWgradArgs& p_in, int chunks, cudaStream_t st)
   p.tiles_n = (p.n + TC_BN - 1) / TC_BN;
   const int m_pairs = (Kt + mt * TC_BM - 1) / (mt * TC_BM);
   dim3 grid((unsigned)chunks, (unsigned)(m_pairs * p.tiles_n));
-  const int smem = WG_STAGES * (2 * mt + 2) * TC_TILE_BYTES + 1024 + 256 + EPI_BYTES;
-  if (mt == 2) tc_wgrad_kernel<2><<<grid, WG_THREADS, smem, st>>>(p);
-  else tc_wgrad_kernel<1><<<grid, WG_THREADS, smem, st>>>(p);
+  // NT = 3: 2 stages x (hi, lo) x (mt + 1) tiles; NT = 1: 4 stages x (mt + 1) tiles — the same bytes
+  const int smem = 4 * (mt + 1) * TC_TILE_BYTES + 1024 + 256 + EPI_BYTES;
+  if (nt == 3) {
+    if (mt == 2) tc_wgrad_kernel<2, 3><<<grid, WG_THREADS, smem, st>>>(p);
+    else tc_wgrad_kernel<1, 3><<<grid, WG_THREADS, smem, st>>>(p);
+  } else {
+    if (mt == 2) tc_wgrad_kernel<2, 1><<<grid, WG_THREADS, smem, st>>>(p);
+    else tc_wgrad_kernel<1, 1><<<grid, WG_THREADS, smem, st>>>(p);
+  }
   DCGC_CUDA_LAUNCH_CHECK("tc_wgrad_kernel");
   return DCGC_OK;
 }

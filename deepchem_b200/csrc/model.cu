@@ -584,7 +584,7 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
     conv_bias_pack<<<blocks_for(DCGC_N_DEG * c), kT, 0, st>>>(params + lo.conv_b[l], c, sv.b11[l]);
     DCGC_CUDA_LAUNCH_CHECK("conv_bias_pack");
     RET_IF(dcgc_gather_sum_bucketed(h, ld, t->deg_count, t->col_idx, N, fp, nullptr, 0, sv.s[l], fp, st));
-    const bool fuse_stats = cfg->batch_norm && training && cfg->gemm_mode == DCGC_GEMM_TF32X3;
+    const bool fuse_stats = cfg->batch_norm && training && dcgc_tc_terms(cfg->gemm_mode) != 0;
     int32_t fused = -1;
     if (fuse_stats)
       RET_IF(dcgc_group_gemm_fwd_stats(cfg->gemm_mode, h, ld, fp, sv.s[l], fp, fp, params + lo.conv_w[l], sv.b11[l], c,
@@ -603,7 +603,7 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
   }
   // ---- atom-level dense + ReLU (+BN folded into the gather), GraphGather(tanh), head
   int32_t fused_d = -1;
-  if (cfg->batch_norm && training && cfg->gemm_mode == DCGC_GEMM_TF32X3)
+  if (cfg->batch_norm && training && dcgc_tc_terms(cfg->gemm_mode) != 0)
     RET_IF(dcgc_linear_fwd_stats(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], params + lo.dense_w,
                                  params + lo.dense_b, D, N, DCGC_ACT_RELU, sv.z, D, sv.part, &fused_d, st));
   else

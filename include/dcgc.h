@@ -40,7 +40,7 @@ extern "C" {
 
 /* GEMM arithmetic modes */
 #define DCGC_GEMM_FP32 0 /* SIMT FFMA, fp32 in / fp32 accumulate: the 1e-5 parity mode        */
-#define DCGC_GEMM_BF16 1 /* tcgen05 kind::f16, bf16 operands / fp32 accumulate: the 2e-2 mode  */
+#define DCGC_GEMM_BF16 1 /* tcgen05, operands rounded to bf16 / fp32 accumulate: the 2e-2 mode     */
 #define DCGC_GEMM_TF32X3 2 /* tcgen05 kind::tf32 with 3-term split: fp32-grade accuracy       */
 
 const char* dcgc_last_error(void);
@@ -189,7 +189,7 @@ int dcgc_group_gemm_fwd(int32_t mode, const float* a1_dev, int64_t ld_a1, int32_
  * (graphconvmodel.py:213-216): stats_part_dev [n_chunks][2][n] float64 receives, per chunk of rows, the
  * column sums of y and of y*y; *n_chunks_out (host) is the number of chunks written, at most
  * dcgc_gemm_stats_max_chunks().  Partials are combined in a fixed order (deterministic).
- * DCGC_GEMM_TF32X3 only (the statistics are accumulated in the tcgen05 kernel's epilogue). */
+ * Tensor-core modes only (the statistics are accumulated in the tcgen05 kernel's epilogue). */
 int dcgc_group_gemm_fwd_stats(int32_t mode, const float* a1_dev, int64_t ld_a1, int32_t k1,
                               const float* a2_dev, int64_t ld_a2, int32_t k2, const float* w_dev,
                               const float* bias_dev, int32_t n, const int32_t* tiles_dev, int64_t n_tiles,

