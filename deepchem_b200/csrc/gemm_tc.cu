@@ -176,12 +176,14 @@ constexpr int EPI_LD = 36;                              // floats per staged row
 constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
 constexpr int EPI_BYTES = 4 * EPI_WARP_FLOATS * 4;      // four epilogue warps
 template <typename F>
-__device__ __forceinline__ void warp_transpose_store(float* stg, int lane, const uint32_t (&v)[32], F&& f) {
+__device__ __forceinline__ void warp_transpose_store(float* stg, int lane, const uint32_t (&v)[32], F&& f,
+                                                     long long* ts = nullptr) {
 #pragma unroll
   for (int i = 0; i < 32; i += 4)
     *reinterpret_cast<float4*>(stg + lane * EPI_LD + i) =
         make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
   __syncwarp();
+  if (ts) *ts = clock64();
 #pragma unroll
   for (int i2 = 0; i2 < 8; ++i2) {
     const int rr = i2 * 4 + (lane >> 3), cc = 4 * (lane & 7);
@@ -251,6 +253,7 @@ struct TcArgs3 {
   TcArgs a;
   const float* img;
   int n_row_tiles, n_tiles_n;
+  long long* dbg;  // optional timeline buffer (dcgcdbg_tc_timeline): CTA (0,0) records clock64() per role and chunk
   int knockout;   // debugging aid (env DCGC_TC_KNOCKOUT): 1 no output stores, 2 no MMAs, 4 no A loads,
                   // 8 no weight copies, 16 no A shared-memory stores, 32 no TMEM loads, 64 no proxy fence,
                   // 128 no weight-image kernel — results are wrong, timing only
@@ -277,6 +280,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
   const int total = chunks1 + chunks2;
   const int my_tiles = pid < q.n_row_tiles ? (q.n_row_tiles - pid + P - 1) / P : 0;
   const int n_cc = my_tiles * total;
+  const bool dbg_on = q.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && n_cc <= 1024;
+  if (dbg_on && tid == 0) q.dbg[5000] = clock64();
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
@@ -335,6 +340,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
       if (!(q.knockout & 64)) fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_base + 8 * s);
+      if (dbg_on && gt == 0) q.dbg[(group ? 1024 : 0) + (cc >> 1)] = clock64();
     };
     float4 ra[8], rb[8];
     issue(ra, group);
@@ -360,6 +366,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
           if (q.knockout & 8) { mbar_arrive(bar_base + 8 * s); continue; }
           mbar_arrive_expect_tx(bar_base + 8 * s, kBBytes);
           bulk_g2s(base + s * V3_STAGE_BYTES + kBBytes, src + (int64_t)ch * kBFloats, kBBytes, bar_base + 8 * s);
+          if (dbg_on) q.dbg[2048 + cc] = clock64();
         }
       }
     }
@@ -376,6 +383,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
           const int s = cc % S;
           mbar_wait(bar_base + 8 * s, (cc / S) & 1);
           tc_fence_after();
+          if (dbg_on) q.dbg[3072 + cc] = clock64();
           const uint32_t sa = base + s * V3_STAGE_BYTES;
           if (!(q.knockout & 2)) {
 #pragma unroll
@@ -417,17 +425,21 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
         mbar_wait(bar_base + 96 + 8 * acc, (it >> 1) & 1);
         tc_fence_after();
       }
+      if (dbg_on && tid == 0) q.dbg[4096 + 2 * it] = clock64();
       const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_group_stride : nullptr;
 #pragma unroll 1   // (fully unrolled, the 32 copies of the store body overflowed the instruction cache: 2x slower)
       for (int cb = 0; cb < TC_BN; cb += 32) {
         uint32_t v[32];
         float ts[4] = {0.f, 0.f, 0.f, 0.f}, tq[4] = {0.f, 0.f, 0.f, 0.f};
+        const bool dbg_cb = dbg_on && tid == 0 && it == 2;
+        if (dbg_cb) q.dbg[5100 + (cb >> 5) * 4 + 0] = clock64();
         if (total > 0 && !(q.knockout & 32)) {
           tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + acc * TC_BN + cb, v);
         } else {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0u;
         }
+        if (dbg_cb) q.dbg[5100 + (cb >> 5) * 4 + 1] = clock64();
         const int c = n0 + cb + 4 * (lane & 7);       // the 4 columns this lane stores
         float bv[4] = {0.f, 0.f, 0.f, 0.f};
         if (bias) {
@@ -435,6 +447,29 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
           for (int e = 0; e < 4; ++e)
             if (c + e < N) bv[e] = __ldg(bias + c + e);
         }
+        // Fast path (decided once per 32-column block, warp-uniform): the whole block lands in one output
+        // with 16-byte aligned rows and the activation is none / ReLU.  The general lambda below (column
+        // split, scalar tails, tanh) compiled to ~240 instructions per stored float4 and made the EPILOGUE the
+        // critical path of the kernel (timeline: 15 k cycles per tile against 9 k for the main loop).
+        const int cblk = n0 + cb;
+        const bool fast1 = p.c1_vec && cblk + 32 <= p.n1;
+        const bool fast2 = !fast1 && p.c2_vec && cblk >= p.n1 && cblk + 32 <= N && ((cblk - p.n1) & 3) == 0;
+        long long* tsp = dbg_cb ? q.dbg + 5100 + (cb >> 5) * 4 + 2 : nullptr;
+        if ((fast1 || fast2) && p.act != DCGC_ACT_TANH) {
+          const int64_t ld = fast1 ? p.ld_c1 : p.ld_c2;
+          float* dst = (fast1 ? p.c1 + c : p.c2 + (c - p.n1)) + (int64_t)(row0 + warp * 32) * ld;
+          const int nrows = rows - warp * 32;
+          const bool relu = p.act == DCGC_ACT_RELU;
+          warp_transpose_store(stg, lane, v, [&](int rr, int, float4 t) {
+            if (rr >= nrows) return;
+            t.x += bv[0]; t.y += bv[1]; t.z += bv[2]; t.w += bv[3];
+            if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+            ts[0] += t.x; ts[1] += t.y; ts[2] += t.z; ts[3] += t.w;
+            tq[0] = fmaf(t.x, t.x, tq[0]); tq[1] = fmaf(t.y, t.y, tq[1]);
+            tq[2] = fmaf(t.z, t.z, tq[2]); tq[3] = fmaf(t.w, t.w, tq[3]);
+            *reinterpret_cast<float4*>(dst + (int64_t)rr * ld) = t;
+          }, tsp);
+        } else {
         warp_transpose_store(stg, lane, v, [&](int rr, int, float4 t) {
           const int row = warp * 32 + rr;
           if (row >= rows || c >= N) return;
@@ -455,7 +490,9 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
               else if (cc2 < N) { if (p.c2) p.c2[grow * p.ld_c2 + (cc2 - p.n1)] = o[e]; }
             }
           }
-        });
+        }, tsp);
+        }
+        if (dbg_cb) q.dbg[5100 + (cb >> 5) * 4 + 3] = clock64();
         // fold this block's sums into the statically indexed accumulators (cb is a run-time value here)
 #define DCGC_FOLD(SU, SQ)                                  \
   {                                                        \
@@ -472,6 +509,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
       }
       tc_fence_before();
       mbar_arrive(bar_base + 112 + 8 * acc);
+      if (dbg_on && tid == 0) q.dbg[4096 + 2 * it + 1] = clock64();
     }
     if (p.stats) {
       // lanes l, l+8, l+16, l+24 hold the same columns (different rows): fixed-order butterfly, then the four
@@ -567,19 +605,26 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
   const uint32_t tmem = *tmem_slot;
 
   if (warp < TC_PRODUCER_WARPS) {
-    float bsum[16];
+    // Lane mapping: a warp instruction covers 16 atoms x 8 features: lane = (atom = lane >> 1, 16-byte half =
+    // lane & 1), i.e. every atom row contributes one full 32-byte sector per LDG.128 (16 wavefronts; the first
+    // version read one row per lane: 32 half-used sectors per instruction and the LSU was the bound).  Warp w
+    // owns the 16 features 16w..16w+15 of every 128-wide tile; the four loads of a tile are (atom half h,
+    // feature group fg) = (j >> 1, j & 1).  The transposed 4-byte stores into the K-major SWIZZLE_128B tiles are
+    // conflict-free with compile-time offsets: bank = ((k >> 2) ^ (row & 7)) * 4 + (k & 3) takes 32 values.
+    float bsum[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) bsum[i] = 0.f;
-    const int col = 16 * warp;   // first column of this warp inside every 128-wide tile
+    for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
+    const int la = lane >> 1, lh = lane & 1;
+    const int col = 16 * warp + 4 * lh;          // first feature / column of this lane inside a tile (+ 8 fg)
 
     auto gload = [&](float4 (&r)[NL], int c) {
-      const int64_t row = r_begin + (int64_t)c * TC_BK + lane;
-      const bool live = row < r_end;
 #pragma unroll
-      for (int t = 0; t < MT; ++t) {
+      for (int j = 0; j < 4; ++j) {
+        const int64_t row = r_begin + (int64_t)c * TC_BK + 16 * (j >> 1) + la;
+        const bool live = row < r_end;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int m = m0 + t * TC_BM + col + 4 * j;
+        for (int t = 0; t < MT; ++t) {
+          const int m = m0 + t * TC_BM + col + 8 * (j & 1);
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (live && m < Kt) {
             if (m + 3 < p.k1) {
@@ -600,10 +645,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
           }
           r[4 * t + j] = v;
         }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = n0 + col + 4 * j;
+        const int n = n0 + col + 8 * (j & 1);
         r[4 * MT + j] = live ? ld4_masked(p.g + row * p.ld_g + n, p.n - n, p.g_vec)
                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -612,8 +654,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
       const int s = c % WG_STAGES, use = c / WG_STAGES;
       mbar_wait(bar_base + 32 + 8 * s, (use & 1) ^ 1);           // the MMAs that read this stage retired
       uint8_t* st = sm + s * STAGE_BYTES;
-      const uint32_t kofs = (uint32_t)(lane & 3) * 4;
-      const int kc = lane >> 2;
 #pragma unroll
       for (int t = 0; t <= MT; ++t) {
         uint8_t* hi_t = st + TPO * t * TC_TILE_BYTES;
@@ -624,9 +664,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
           if (NT == 3) { split4(r[4 * t + j], hi, lo); }
           else { hi = round4_bf16(r[4 * t + j]); lo = hi; }
           const float h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+          const int k = 16 * (j >> 1) + la;                      // atom = column of the K-major tile
+          const int kc = k >> 2;
+          const uint32_t kofs = (uint32_t)(k & 3) * 4;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int rr = col + 4 * j + e;                       // row of the K-major tile
+            const int rr = col + 8 * (j & 1) + e;                 // row of the K-major tile
             const uint32_t o = (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128 + ((kc ^ (rr & 7)) << 4)) + kofs;
             *reinterpret_cast<float*>(hi_t + o) = h[e];
             if (NT == 3) *reinterpret_cast<float*>(lo_t + o) = l[e];
@@ -635,8 +678,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        bsum[4 * j + 0] += r[4 * MT + j].x; bsum[4 * j + 1] += r[4 * MT + j].y;
-        bsum[4 * j + 2] += r[4 * MT + j].z; bsum[4 * j + 3] += r[4 * MT + j].w;
+        const int b0 = 4 * (j & 1);
+        bsum[b0 + 0] += r[4 * MT + j].x; bsum[b0 + 1] += r[4 * MT + j].y;
+        bsum[b0 + 2] += r[4 * MT + j].z; bsum[b0 + 3] += r[4 * MT + j].w;
       }
       fence_proxy_async();
       __syncwarp();
@@ -651,15 +695,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
       if (c + 2 < steps) gload(ra, c + 2);
       if (c + 1 < steps) sstore(rb, c + 1);
     }
-    // dbias partial: fixed-order butterfly over the 32 atom lanes
+    // dbias partial: bsum[4 fg + e] = this lane's sum of column col + 8 fg + e over its atoms; fixed-order
+    // butterfly over the 16 atom lanes (lanes with equal lane & 1 hold the same columns)
     if (mp == 0) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < 8; ++i) {
         float v = bsum[i];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const int n = n0 + col + i;
-        if (lane == 0 && n < p.n) p.wsb[(int64_t)chunk * p.n + n] = v;
+        for (int o = 16; o > 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int n = n0 + col + 8 * (i >> 2) + (i & 3);
+        if (la == 0 && n < p.n) p.wsb[(int64_t)chunk * p.n + n] = v;
       }
     }
   } else if (lane == 0) {
@@ -739,6 +784,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 
 int g_num_sms = 0;
+long long* g_timeline = nullptr;   // debugging aid, see dcgcdbg_tc_timeline
 
 // Split-weight scratch (hi | lo), one grow-only buffer per (device, stream): launches on one stream are
 // ordered, so the prep -> GEMM -> next prep sequence never races; no allocation on the steady-state path.
@@ -832,6 +878,7 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
     p3.c2_vec = c2 && ld_c2 % 4 == 0 && aligned16(c2);
     q3.img = img; q3.n_row_tiles = (int)row_tiles; q3.n_tiles_n = n_tiles_n;
     q3.knockout = knockout;
+    q3.dbg = g_timeline;
     int ctas = g_num_sms / n_tiles_n;
     if (ctas < 1) ctas = 1;
     if (ctas > row_tiles) ctas = (int)row_tiles;
@@ -879,3 +926,9 @@ int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p_in, int chunks, cudaStre
   DCGC_CUDA_LAUNCH_CHECK("tc_wgrad_kernel");
   return DCGC_OK;
 }
+
+// Debugging aid (not part of the ABI in include/dcgc.h): subsequent tensor-core GEMM launches make CTA (0,0)
+// record clock64() per role and K chunk into dev_buf (at least 6000 int64); nullptr switches it off.
+//   [0..1023] producer group 0 commit times, [1024..] group 1, [2048..] weight copies issued,
+//   [3072..] MMA issuer saw the chunk, [4096+2t, 4097+2t] epilogue start / end of tile t, [5000] kernel start
+extern "C" void dcgcdbg_tc_timeline(long long* dev_buf) { g_timeline = dev_buf; }
