@@ -1,0 +1,115 @@
+"""Secondary measurements (BASELINE configs 4 and 5; parity-test cases, not the bench line):
+  * D-MPNN (QM9-shaped, hidden 300, depth 3, 12 targets, B=4096): fwd + bwd + Adam molecules/s, device resident,
+    beside the CPU oracle on the host cores;
+  * large-batch inference: GraphConvModel.predict on PCBA-shaped molecules (128 tasks x 2 classes) through the
+    public API from host memory (layout build + H2D + forward + one D2H at the end).
+Prints one JSON line per measurement."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+
+dev = torch.device("cuda", 0)
+
+
+def dmpnn(mode, B=4096, steps=20):
+    from deepchem_b200.dmpnn import DMPNNModel, GraphDataset
+    from deepchem_b200.dmpnn_data import make_graphs
+    pg = make_graphs(B, seed=0, shape="qm9")
+    y = np.random.default_rng(0).standard_normal((B, 12)).astype(np.float32)
+    torch.manual_seed(0)
+    m = DMPNNModel(device=dev, n_tasks=12, batch_size=B, gemm_mode=mode)
+    ds = GraphDataset(pg, y)
+    batch = next(m.default_generator(ds, deterministic=True))
+    inputs, labels, weights = m._prepare_batch(batch)
+    m.model.train()
+
+    def step():
+        m._pytorch_optimizer.zero_grad(set_to_none=True)
+        loss = m._loss(m.model(inputs), labels, weights)
+        loss.backward()
+        m._pytorch_optimizer.step()
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    # end to end: host generator (C++ table builder) + H2D + step
+    t0 = time.perf_counter()
+    n = 0
+    for b in m.default_generator(ds, epochs=10, deterministic=True):
+        i2, l2, w2 = m._prepare_batch(b)
+        m._pytorch_optimizer.zero_grad(set_to_none=True)
+        loss = m._loss(m.model(i2), l2, w2)
+        loss.backward()
+        m._pytorch_optimizer.step()
+        n += 1
+    torch.cuda.synchronize()
+    ms2 = (time.perf_counter() - t0) / n * 1e3
+    print(json.dumps({"metric": "D-MPNN fwd+bwd molecules/sec", "gemm_mode": mode, "value": B / ms * 1e3, "ms_per_step": ms,
+                      "e2e": {"value": B / ms2 * 1e3, "ms_per_step": ms2},
+                      "config": {"workload": "qm9-synthetic B=%d, %d atoms, %d directed bonds, hidden 300, depth 3, "
+                                             "FFN 300x3, 12 targets" % (B, pg.n_atoms, pg.n_bonds)}}), flush=True)
+
+
+def dmpnn_cpu(B=4096):
+    from deepchem_b200.dmpnn_data import make_graphs
+    from oracle import dmpnn_torch as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    pg = make_graphs(B, seed=0, shape="qm9")
+    y = torch.from_numpy(np.random.default_rng(0).standard_normal((B, 12)).astype(np.float32))
+    torch.manual_seed(0)
+    om = O.OracleDMPNN(mode='regression', n_tasks=12)
+    opt = torch.optim.Adam(om.parameters(), lr=1e-3)
+    times = []
+    for it in range(3):
+        t0 = time.perf_counter()
+        vals = [O.mapper_values(O.OracleGraph(*pg.graph(i)[:3])) for i in range(pg.n_mols)]   # the reference re-maps every batch
+        batch = O.to_torch_batch(O.collate(vals))
+        opt.zero_grad()
+        loss = ((om(batch) - y) ** 2).mean()
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    s = min(times[1:])
+    print(json.dumps({"metric": "D-MPNN fwd+bwd molecules/sec", "impl": "cpu oracle port", "value": B / s,
+                      "ms_per_step": s * 1e3, "cores": torch.get_num_threads()}), flush=True)
+
+
+def predict(n_batches=32, B=4096):
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    from deepchem_b200.synthetic import PackedMols, make_molecules
+    shards = [make_molecules(B, seed=100 + i, shape="pcba") for i in range(4)]
+    big = PackedMols.concat([shards[i % 4] for i in range(n_batches)]).pin_memory()
+    ds = PackedDataset(big)
+    torch.manual_seed(0)
+    m = GraphConvModel(128, [64, 64], 128, mode="classification", n_classes=2, batch_size=B, device=dev,
+                       gemm_mode="tf32x3")
+    m.predict(PackedDataset(big.slice(0, 2 * B)))                    # warm up
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        t0 = time.perf_counter()
+        p = m.predict(ds)
+        best = min(best, time.perf_counter() - t0)
+    assert p.shape == (n_batches * B, 128, 2)
+    print(json.dumps({"metric": "GraphConvModel.predict molecules/sec (1 GPU, host to host)", "value": n_batches * B / best,
+                      "seconds": best, "config": {"workload": "pcba-synthetic %d molecules, 128 tasks x 2 classes, "
+                                                              "GraphConv[64,64]+dense128, batch %d" % (n_batches * B, B),
+                                                  "d2h_bytes": int(p.nbytes)}}), flush=True)
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["dmpnn", "predict", "cpu"]
+    if "dmpnn" in what:
+        for mode in ("fp32", "tf32x3", "bf16"):
+            dmpnn(mode)
+    if "predict" in what:
+        predict()
+    if "cpu" in what:
+        dmpnn_cpu()
