@@ -62,6 +62,7 @@ struct DcgcWgradArgs {
   int64_t group_row0[DCGC_N_DEG + 1];
   int chunk_prefix[DCGC_N_DEG + 1];
   int a1_vec, a2_vec, g_vec;
+  long long* dbg;   // optional timeline buffer (dcgcdbg_tc_timeline)
 };
 int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p, int chunks, cudaStream_t st);
 int dcgc_tc_wgrad_grid_y(int k_total, int n);

@@ -338,7 +338,16 @@ __global__ void __launch_bounds__(NT) wgrad_reduce_kernel(const ReduceArgs p) {
   const int c0 = p.chunk_prefix[g], c1 = p.chunk_prefix[g + 1];
   float s = 0.f;
   if (idx < p.kn) {
-    for (int c = c0; c < c1; ++c) s += __ldg(p.ws + (int64_t)c * p.kn + idx);
+    // chunk order is fixed (deterministic); 8 independent loads in flight per thread instead of one
+    int c = c0;
+    for (; c + 8 <= c1; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(p.ws + (int64_t)(c + u) * p.kn + idx);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; c < c1; ++c) s += __ldg(p.ws + (int64_t)c * p.kn + idx);
     int64_t o = idx;
     if (p.transpose) {
       const int64_t k = idx / p.n, j = idx - k * p.n;

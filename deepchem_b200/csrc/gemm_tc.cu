@@ -110,9 +110,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
+// MN-major operand tile (the contiguous dimension of the data is M or N, not K).  For 32-bit (tf32) operands
+// the only layout the tensor core accepts is SWIZZLE_128B_BASE32B (CUTLASS: "for mn-major tf32 operands,
+// SW128_32B is the only available smem layout"): swizzle atoms of 4 K-rows x 128 bytes (32 fp32 along MN) in
+// which the 32-byte chunk index is XORed with the row index (Swizzle<2,5,2>); atoms repeat along MN every
+// LBO = 512 bytes and along K (groups of 4 rows) every SBO = 2048 bytes, i.e. a [32 K x 128 MN] chunk is laid
+// out as [K group of 4][MN atom][4 rows x 128 B]; one K = 8 MMA reads two K groups.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (32ull << 16) | (128ull << 32) | (1ull << 46) | (1ull << 61);
+}
 // kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                                 ((uint32_t)(TC_BM >> 4) << 24);
+
+// same, both operands MN-major (bits 15 / 16): the tensor core transposes, the producers do not have to
+constexpr uint32_t kIdescTf32MN = kIdescTf32 | (1u << 15) | (1u << 16);
 
 __device__ __forceinline__ float tf32_hi(float x) {
   uint32_t r;
@@ -589,6 +601,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
   const int m0 = mp * MT * TC_BM, n0 = nt * TC_BN;
   const int Kt = p.k1 + p.k2;
   const int steps = (int)((r_end - r_begin + TC_BK - 1) / TC_BK);
+  const bool wdbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  if (wdbg && tid == 0) { p.dbg[5000] = clock64(); p.dbg[5001] = steps; }
 
   if (tid == 0) {
     for (int s = 0; s < WG_STAGES; ++s) {
@@ -605,26 +619,30 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
   const uint32_t tmem = *tmem_slot;
 
   if (warp < TC_PRODUCER_WARPS) {
-    // Lane mapping: a warp instruction covers 16 atoms x 8 features: lane = (atom = lane >> 1, 16-byte half =
-    // lane & 1), i.e. every atom row contributes one full 32-byte sector per LDG.128 (16 wavefronts; the first
-    // version read one row per lane: 32 half-used sectors per instruction and the LSU was the bound).  Warp w
-    // owns the 16 features 16w..16w+15 of every 128-wide tile; the four loads of a tile are (atom half h,
-    // feature group fg) = (j >> 1, j & 1).  The transposed 4-byte stores into the K-major SWIZZLE_128B tiles are
-    // conflict-free with compile-time offsets: bank = ((k >> 2) ^ (row & 7)) * 4 + (k & 3) takes 32 values.
-    float bsum[8];
+    // The contraction runs over the ATOMS, so both operands ([atoms, features] and [atoms, columns], row-major)
+    // have their M / N dimension contiguous: they are stored as MN-major SWIZZLE_128B_BASE32B tiles and the tensor core
+    // does the transposition (instruction-descriptor bits 15/16).  The producers only copy: a warp instruction
+    // covers 4 atoms x 32 features = four coalesced 128-byte row segments, stored as 16-byte chunks of one
+    // 128-byte smem row per atom (conflict-free).  (Two earlier versions transposed in the producers with
+    // 4-byte stores: ~100 STS + address arithmetic per thread and chunk made the producers the critical path,
+    // 4.7 k cycles per 32-atom chunk against 1.2 k for the MMAs: scripts/wgrad_timeline.py.)
+    // Warp w owns atoms 4w..4w+3 of the chunk; load j of a tile covers features 32j..32j+31.
+    float bsum[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
-    const int la = lane >> 1, lh = lane & 1;
-    const int col = 16 * warp + 4 * lh;          // first feature / column of this lane inside a tile (+ 8 fg)
+    for (int i = 0; i < 16; ++i) bsum[i] = 0.f;
+    const int la = lane >> 3, lc = lane & 7;
+    const int k = 4 * warp + la;                  // atom inside the 32-atom chunk = K index
+    // byte offset of this lane's 16 bytes inside the chunk: [K group k>>2][MN atom j][row k&3][32-byte chunk ^ row]
+    const uint32_t k_off = (uint32_t)((k >> 2) * 2048 + (k & 3) * 128 + (((lc >> 1) ^ (k & 3)) << 5) + (lc & 1) * 16);
 
     auto gload = [&](float4 (&r)[NL], int c) {
+      const int64_t row = r_begin + (int64_t)c * TC_BK + k;
+      const bool live = row < r_end;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int64_t row = r_begin + (int64_t)c * TC_BK + 16 * (j >> 1) + la;
-        const bool live = row < r_end;
+      for (int t = 0; t < MT; ++t) {
 #pragma unroll
-        for (int t = 0; t < MT; ++t) {
-          const int m = m0 + t * TC_BM + col + 8 * (j & 1);
+        for (int j = 0; j < 4; ++j) {
+          const int m = m0 + t * TC_BM + 32 * j + 4 * lc;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (live && m < Kt) {
             if (m + 3 < p.k1) {
@@ -645,7 +663,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
           }
           r[4 * t + j] = v;
         }
-        const int n = n0 + col + 8 * (j & 1);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int n = n0 + 32 * j + 4 * lc;
         r[4 * MT + j] = live ? ld4_masked(p.g + row * p.ld_g + n, p.n - n, p.g_vec)
                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -656,35 +677,29 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
       uint8_t* st = sm + s * STAGE_BYTES;
 #pragma unroll
       for (int t = 0; t <= MT; ++t) {
-        uint8_t* hi_t = st + TPO * t * TC_TILE_BYTES;
+        uint8_t* hi_t = st + TPO * t * TC_TILE_BYTES + k_off;
         uint8_t* lo_t = hi_t + TC_TILE_BYTES;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float4 hi, lo;
-          if (NT == 3) { split4(r[4 * t + j], hi, lo); }
-          else { hi = round4_bf16(r[4 * t + j]); lo = hi; }
-          const float h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
-          const int k = 16 * (j >> 1) + la;                      // atom = column of the K-major tile
-          const int kc = k >> 2;
-          const uint32_t kofs = (uint32_t)(k & 3) * 4;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int rr = col + 8 * (j & 1) + e;                 // row of the K-major tile
-            const uint32_t o = (uint32_t)((rr >> 3) * 1024 + (rr & 7) * 128 + ((kc ^ (rr & 7)) << 4)) + kofs;
-            *reinterpret_cast<float*>(hi_t + o) = h[e];
-            if (NT == 3) *reinterpret_cast<float*>(lo_t + o) = l[e];
+          if (NT == 3) {
+            float4 hi, lo;
+            split4(r[4 * t + j], hi, lo);
+            *reinterpret_cast<float4*>(hi_t + j * 512) = hi;
+            *reinterpret_cast<float4*>(lo_t + j * 512) = lo;
+          } else {
+            *reinterpret_cast<float4*>(hi_t + j * 512) = round4_bf16(r[4 * t + j]);
           }
         }
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int b0 = 4 * (j & 1);
-        bsum[b0 + 0] += r[4 * MT + j].x; bsum[b0 + 1] += r[4 * MT + j].y;
-        bsum[b0 + 2] += r[4 * MT + j].z; bsum[b0 + 3] += r[4 * MT + j].w;
+        bsum[4 * j + 0] += r[4 * MT + j].x; bsum[4 * j + 1] += r[4 * MT + j].y;
+        bsum[4 * j + 2] += r[4 * MT + j].z; bsum[4 * j + 3] += r[4 * MT + j].w;
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_base + 8 * s);
+      if (wdbg && tid == 0 && c < 1000) p.dbg[c] = clock64();
     };
 
     float4 ra[NL], rb[NL];
@@ -695,23 +710,33 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
       if (c + 2 < steps) gload(ra, c + 2);
       if (c + 1 < steps) sstore(rb, c + 1);
     }
-    // dbias partial: bsum[4 fg + e] = this lane's sum of column col + 8 fg + e over its atoms; fixed-order
-    // butterfly over the 16 atom lanes (lanes with equal lane & 1 hold the same columns)
+    // dbias partial: bsum[4j+e] = this lane's sum of column 32j + 4 lc + e over its atom of every chunk;
+    // combine the 4 atom lanes (fixed butterfly), then the 8 warps in warp order through shared memory
     if (mp == 0) {
+      float* sb = reinterpret_cast<float*>(sm + WG_STAGES * STAGE_BYTES + 256);   // [8 warps][128]: the epilogue staging area
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 16; ++i) {
         float v = bsum[i];
-#pragma unroll
-        for (int o = 16; o > 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const int n = n0 + col + 8 * (i >> 2) + (i & 3);
-        if (la == 0 && n < p.n) p.wsb[(int64_t)chunk * p.n + n] = v;
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (la == 0) sb[warp * TC_BN + 32 * (i >> 2) + 4 * lc + (i & 3)] = v;
       }
+      named_bar_sync(1, TC_PRODUCER_WARPS * 32);
+      if (tid < TC_BN) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < TC_PRODUCER_WARPS; ++w) v += sb[w * TC_BN + tid];
+        const int n = n0 + tid;
+        if (n < p.n) p.wsb[(int64_t)chunk * p.n + n] = v;
+      }
+      named_bar_sync(1, TC_PRODUCER_WARPS * 32);   // the staging area is reused by the epilogue warps
     }
   } else if (lane == 0) {
     for (int c = 0; c < steps; ++c) {
       const int s = c % WG_STAGES;
       mbar_wait(bar_base + 8 * s, (c / WG_STAGES) & 1);
       tc_fence_after();
+      if (wdbg && c < 1000) p.dbg[3072 + c] = clock64();
       const uint32_t sa = base + s * STAGE_BYTES;
       const uint32_t sg_hi = sa + TPO * MT * TC_TILE_BYTES, sg_lo = sg_hi + TC_TILE_BYTES;
 #pragma unroll
@@ -719,15 +744,15 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
         const uint32_t a_hi = sa + TPO * t * TC_TILE_BYTES, a_lo = a_hi + TC_TILE_BYTES;
 #pragma unroll
         for (int k = 0; k < TC_BK / TC_UK; ++k) {
-          const uint32_t ko = k * TC_UK * 4;
-          const uint64_t ahi = make_desc(a_hi + ko), alo = make_desc(a_lo + ko);
-          const uint64_t ghi = make_desc(sg_hi + ko), glo = make_desc(sg_lo + ko);
+          const uint32_t ko = k * 4096;                         // K rows 8k..8k+7 = two K groups of 4
+          const uint64_t ahi = make_desc_mn(a_hi + ko), alo = make_desc_mn(a_lo + ko);
+          const uint64_t ghi = make_desc_mn(sg_hi + ko), glo = make_desc_mn(sg_lo + ko);
           if (NT == 3) {
-            umma_tf32(tmem + t * TC_BN, alo, ghi, kIdescTf32, (c | k) != 0);
-            umma_tf32(tmem + t * TC_BN, ahi, glo, kIdescTf32, 1);
-            umma_tf32(tmem + t * TC_BN, ahi, ghi, kIdescTf32, 1);
+            umma_tf32(tmem + t * TC_BN, alo, ghi, kIdescTf32MN, (c | k) != 0);
+            umma_tf32(tmem + t * TC_BN, ahi, glo, kIdescTf32MN, 1);
+            umma_tf32(tmem + t * TC_BN, ahi, ghi, kIdescTf32MN, 1);
           } else {
-            umma_tf32(tmem + t * TC_BN, ahi, ghi, kIdescTf32, (c | k) != 0);
+            umma_tf32(tmem + t * TC_BN, ahi, ghi, kIdescTf32MN, (c | k) != 0);
           }
         }
       }
@@ -737,10 +762,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
   }
 
   if (warp < 4) {
+    if (wdbg && tid == 0) p.dbg[4096] = clock64();
     if (steps > 0) {
       mbar_wait(bar_base + 64, 0);
       tc_fence_after();
     }
+    if (wdbg && tid == 0) p.dbg[4097] = clock64();
     const bool n_vec = (p.n & 3) == 0 && (reinterpret_cast<uintptr_t>(p.ws) & 15) == 0;
     float* stg = reinterpret_cast<float*>(sm + WG_STAGES * STAGE_BYTES + 256) + warp * EPI_WARP_FLOATS;
 #pragma unroll 1
@@ -772,6 +799,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
       }
     }
   }
+  if (wdbg && tid == 0) p.dbg[4098] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == TC_PRODUCER_WARPS) {
@@ -909,6 +937,7 @@ int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p_in, int chunks, cudaStre
   int st_ = ensure_smem_attr();
   if (st_ != DCGC_OK) return st_;
   DcgcWgradArgs p = p_in;
+  p.dbg = g_timeline;
   const int Kt = p.k1 + p.k2;
   const int mt = Kt > TC_BM ? 2 : 1;
   p.tiles_n = (p.n + TC_BN - 1) / TC_BN;
