@@ -403,6 +403,7 @@ class DMPNNModel(object):
         self.output_types = ['prediction'] if mode == 'regression' else ['prediction', 'loss']
         self._pytorch_optimizer = torch.optim.Adam(self.model.parameters(), lr=learning_rate)
         self._global_step, self.log_frequency, self.model_dir = 0, log_frequency, model_dir
+        self._grad_slab = None
 
     # ------------------------------------------------------------------ batching
     def default_generator(self, dataset, epochs=1, mode='fit', deterministic=True, pad_batches=False, **kwargs):
@@ -468,10 +469,8 @@ class DMPNNModel(object):
         t0, n, last = time.time(), 0, None
         for batch in generator:
             inputs, labels, weights = self._prepare_batch(batch)
-            self._pytorch_optimizer.zero_grad(set_to_none=True)
-            loss = self._loss(self.model(inputs), labels, weights)
-            loss.backward()
-            self._pytorch_optimizer.step()
+            self._train_step(inputs, labels, weights)
+            loss = self._last_loss
             self._global_step += 1
             n += 1
             last = loss
@@ -479,6 +478,34 @@ class DMPNNModel(object):
                 logger.info('Ending global_step %d: loss %g' % (self._global_step, float(loss)))
         logger.info("TIMING: model fitting took %0.3f s" % (time.time() - t0))
         return float(last) if n else 0.0
+
+    def _train_step(self, inputs, labels, weights):
+        """zero_grad, forward, loss, backward, (gradient all-reduce), Adam step (torch_model.py:435-443)."""
+        slab = self._grad_slab
+        if slab is None:
+            self._pytorch_optimizer.zero_grad(set_to_none=True)
+        else:
+            slab.zero()
+            slab.attach()
+        loss = self._loss(self.model(inputs), labels, weights)
+        loss.backward()
+        if slab is not None:
+            slab.collect()
+            slab.all_reduce_mean()      # the one exchange of a data-parallel step (molecules never interact)
+        self._pytorch_optimizer.step()
+        self._last_loss = loss
+        return loss
+
+    def enable_data_parallel(self):
+        """Average gradients over the default process group every step (one all-reduce of a flat slab; equal
+        per-rank batches and a mean loss make the averaged gradient exact).  Parameters are broadcast from rank 0."""
+        import torch.distributed as dist
+        from .parallel import GradSlab, world_size
+        if world_size() > 1:
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, src=0)
+        self._grad_slab = GradSlab(self.model.parameters())
+        return self
 
     def fit_on_batch(self, X, y, w):
         ds = _GraphDataset(X if isinstance(X, PackedGraphs) else PackedGraphs.from_graphs(list(X), self.atom_fdim,
