@@ -110,6 +110,20 @@ class PackedDataset(_ArrayDataset):
             return self.packed.slice(int(idx[0]), int(idx[-1]) + 1)
         return self.packed.take(idx)
 
+    def save(self, path):
+        """Write the dataset as a packed on-disk shard (PackedMols.save + y / w / ids)."""
+        import os
+        self.packed.save(path)
+        for name, a in (("y", self._y), ("w", self._w), ("ids", self._ids)):
+            np.save(os.path.join(path, name + ".npy"), a)
+        return path
+
+    @staticmethod
+    def from_disk(path, mmap=True):
+        import os
+        ld = lambda n: np.load(os.path.join(path, n + ".npy"), mmap_mode="r" if mmap else None)  # noqa: E731
+        return PackedDataset(PackedMols.load(path, mmap), ld("y"), ld("w"), ld("ids"))
+
     def select_range(self, lo, hi):
         """Molecules [lo, hi) as a dataset sharing this one's memory (inference sharding)."""
         return PackedDataset(self.packed.slice(lo, hi), self._y[lo:hi], self._w[lo:hi], self._ids[lo:hi])

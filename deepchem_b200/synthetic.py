@@ -100,6 +100,32 @@ class PackedMols(object):
             if rows.size else np.zeros(0, np.int32)
         return PackedMols(atom_ptr, adj_ptr, adj, self.features[rows])
 
+    # ------------------------------------------------------------------ on-disk shard format
+    # One directory per shard with four raw .npy files (no pickled Python objects, unlike the reference's
+    # object-array shard-N-X.npy, deepchem/data/datasets.py:1359-1427): they memory-map, so a DiskDataset-like
+    # iterator can hand contiguous molecule ranges to the layout builder without deserialising anything.
+    _FILES = ("atom_ptr", "adj_ptr", "adj_idx", "features")
+
+    def save(self, path):
+        import os
+        os.makedirs(path, exist_ok=True)
+        for name in self._FILES:
+            np.save(os.path.join(path, name + ".npy"), getattr(self, name))
+        return path
+
+    @staticmethod
+    def load(path, mmap=True):
+        import os
+        arrs = [np.load(os.path.join(path, name + ".npy"), mmap_mode="r" if mmap else None)
+                for name in PackedMols._FILES]
+        out = PackedMols.__new__(PackedMols)
+        out.atom_ptr, out.adj_ptr, out.adj_idx, out.features = arrs
+        if not (out.atom_ptr.dtype == np.int32 and out.adj_ptr.dtype == np.int32 and out.adj_idx.dtype == np.int32
+                and out.features.dtype == np.float32 and out.features.ndim == 2):
+            raise ValueError("not a PackedMols shard: %s" % path)
+        out._pin = None
+        return out
+
     @staticmethod
     def concat(shards):
         """Concatenate shards into one."""

@@ -50,3 +50,24 @@ def test_parallel_generator_propagates_errors():
         assert "neighbour" in str(e) or "index" in str(e).lower()
     else:
         raise AssertionError("expected the layout builder's index error")
+
+
+def test_packed_shard_round_trips_through_disk(tmp_path):
+    """The packed on-disk shard format (raw .npy arrays, memory-mapped on load) feeds the layout builder with
+    the same integers as the in-memory shard."""
+    from deepchem_b200.mol_graphs import BatchLayout
+    pm = make_molecules(300, seed=4, shape="stress")
+    y = np.arange(600, dtype=np.float32).reshape(300, 2)
+    ds = PackedDataset(pm, y, np.ones((300, 2), np.float32))
+    ds.save(str(tmp_path / "shard0"))
+    back = PackedDataset.from_disk(str(tmp_path / "shard0"))
+    assert len(back) == 300 and np.array_equal(back.y, y)
+    m = _host_model(64, 1)
+    a = list(m.default_generator(ds, workers=1))
+    b = list(m.default_generator(back, workers=1))
+    for (ia, ya, _), (ib, yb, _) in zip(a, b):
+        assert np.array_equal(ya[0], yb[0])
+        for f in FIELDS:
+            assert np.array_equal(getattr(ia.layout, f), getattr(ib.layout, f)), f
+        assert np.array_equal(ia.packed_features, ib.packed_features)
+    assert np.array_equal(BatchLayout.build(back.packed).col_idx, BatchLayout.build(pm).col_idx)
