@@ -31,6 +31,7 @@ class LayoutInfo(Structure):
         ("off_row_ptr", c_int64), ("off_col_idx", c_int64), ("off_t_row_ptr", c_int64),
         ("off_t_src", c_int64), ("off_t_slot", c_int64), ("off_mol_ptr", c_int64),
         ("off_mol_atoms", c_int64), ("off_tiles", c_int64), ("slab_bytes", c_int64),
+        ("off_groups", c_int64), ("group_rows", c_int32), ("n_groups_alloc", c_int32),
     ]
 
 
@@ -45,6 +46,8 @@ class Topology(Structure):
         ("row_ptr", c_void_p), ("col_idx", c_void_p), ("t_row_ptr", c_void_p), ("t_src", c_void_p),
         ("t_slot", c_void_p), ("mol_ptr", c_void_p), ("mol_atoms", c_void_p), ("membership", c_void_p),
         ("tiles", c_void_p), ("symmetric", c_int32), ("reserved", c_int32),
+        ("groups", c_void_p), ("n_groups", c_int32), ("group_max_rows", c_int32),
+        ("group_max_entries", c_int32), ("reserved2", c_int32), ("mg_records", c_void_p),
     ]
 
 
@@ -89,6 +92,12 @@ _SIGNATURES = {
     "dcgc_permute_rows": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, c_int64, _P]),
     "dcgc_gather_sum": (c_int32, [_P, c_int64, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
     "dcgc_gather_sum_bucketed": (c_int32, [_P, c_int64, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
+    "dcgc_mg_supported": (c_int32, [_P, c_int64, c_int64]),
+    "dcgc_mg_record_bytes": (c_int64, [c_int64]),
+    "dcgc_mg_prepare": (c_int32, [_P, _P, _P]),
+    "dcgc_mg_gather_sum": (c_int32, [_P, c_int64, _P, c_int32, c_int32, _P, c_int64, _P, c_int64, _P]),
+    "dcgc_mg_pool_fwd": (c_int32, [_P, c_int64, _P, _P, _P, c_int32, _P, c_int64, _P, c_int64, _P]),
+    "dcgc_mg_pool_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, c_int32, _P, c_int64, _P]),
     "dcgc_pool_fwd": (c_int32, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
     "dcgc_pool_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, c_int64, _P]),
     "dcgc_gather_fwd": (c_int32, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int64, _P, _P]),

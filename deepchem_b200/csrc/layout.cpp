@@ -6,6 +6,7 @@
 // stable counting sort of all atoms keyed by degree, i.e. the batch order is
 // (degree, molecule, position inside the molecule).  Everything here is integer work and must
 // match the reference bit for bit (tests/test_layout.py).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -26,6 +27,16 @@ void dcgc_set_error(const char* fmt, ...) {
 extern "C" const char* dcgc_last_error(void) { return g_err; }
 extern "C" int dcgc_version(void) { return 100; }
 
+// row budget of a molecule group (dcgc.h); DCGC_GROUP_ROWS overrides it for tuning
+static int group_rows_setting() {
+  static const int v = [] {
+    const char* e = getenv("DCGC_GROUP_ROWS");
+    const int x = e ? atoi(e) : 0;
+    return x >= 8 && x <= 4096 ? x : DCGC_GROUP_ROWS_DEFAULT;
+  }();
+  return v;
+}
+
 static void plan_offsets(dcgc_layout_info* info) {
   const int64_t N = info->n_atoms, E = info->n_edges, S = info->n_segments;
   int64_t off = 0;
@@ -45,6 +56,7 @@ static void plan_offsets(dcgc_layout_info* info) {
   info->off_mol_ptr = take((S + 1) * 4);
   info->off_mol_atoms = take(N * 4);
   info->off_tiles = take(info->n_tiles * 16);
+  info->off_groups = take((int64_t)DCGC_GROUP_STRIDE * (info->n_groups_alloc + 2) * 4);
   info->slab_bytes = off;
 }
 
@@ -65,6 +77,8 @@ static int finish_plan(dcgc_layout_info* info, int64_t n_segments, int32_t tile_
   info->tile_rows = tile_rows;
   info->reserved = 0;
   info->n_segments = n_segments;
+  info->group_rows = group_rows_setting();
+  info->n_groups_alloc = (int32_t)(2 * N / info->group_rows + 2);
   plan_offsets(info);
   return DCGC_OK;
 }
@@ -92,7 +106,7 @@ extern "C" int dcgc_layout_plan(int64_t n_mols, const int32_t* atom_ptr, const i
 }
 
 // Shared tail: everything derivable from (deg_count, membership, col_idx).
-static void build_derived(const dcgc_layout_info* info, char* slab) {
+static void build_derived(const dcgc_layout_info* info, char* slab, bool check_neighbours) {
   const int64_t N = info->n_atoms, E = info->n_edges, S = info->n_segments;
   int64_t* deg_slice = (int64_t*)(slab + info->off_deg_slice);
   const int32_t* membership = (const int32_t*)(slab + info->off_membership);
@@ -149,6 +163,69 @@ static void build_derived(const dcgc_layout_info* info, char* slab) {
     std::vector<int32_t> cur(mol_ptr, mol_ptr + S);
     for (int64_t i = 0; i < N; ++i) mol_atoms[cur[membership[i]]++] = (int32_t)i;
   }
+
+  // molecule groups (dcgc.h): consecutive molecules are packed greedily into groups of at most R rows (a
+  // molecule larger than R is a group of its own).  Walking the molecules in order, every row of molecule m
+  // must be the next unconsumed row of its degree bucket (rows of a bucket are ordered by molecule); the table
+  // row of a group is the snapshot of the 11 bucket cursors when it starts.  Two consecutive groups always hold
+  // more than R rows together, hence at most 2N/R + 1 groups.
+  int32_t* gt = (int32_t*)(slab + info->off_groups);
+  const int R = info->group_rows;
+  memset(gt, 0, (size_t)DCGC_GROUP_STRIDE * (info->n_groups_alloc + 2) * 4);
+  int32_t* tab = gt + DCGC_GROUP_STRIDE;
+  int64_t cursor[DCGC_N_DEG + 1], bstart[DCGC_N_DEG + 1];
+  {
+    int64_t s0 = 0;
+    for (int d = 0; d < DCGC_N_DEG; ++d) { bstart[d] = cursor[d] = s0; s0 += info->deg_count[d]; }
+    bstart[DCGC_N_DEG] = s0;
+  }
+  bool valid = true;
+  int64_t G = 0, cur_rows = 0;   // groups opened so far, rows of the open group
+  auto snapshot = [&](int64_t mol) {
+    int32_t* row = tab + G * DCGC_GROUP_STRIDE;
+    for (int d = 0; d < DCGC_N_DEG; ++d) row[d] = (int32_t)cursor[d];
+    row[DCGC_N_DEG] = (int32_t)mol;
+  };
+  for (int64_t m = 0; m < S && valid; ++m) {
+    const int64_t n_m = mol_ptr[m + 1] - mol_ptr[m];
+    if (n_m == 0) continue;
+    if (G == 0 || cur_rows + n_m > R) {
+      if (G >= info->n_groups_alloc) { valid = false; break; }   // cannot happen (bound above)
+      snapshot(m);
+      ++G;
+      cur_rows = 0;
+    }
+    cur_rows += n_m;
+    int d = 0;
+    for (int32_t k = mol_ptr[m]; k < mol_ptr[m + 1]; ++k) {
+      const int64_t r = mol_atoms[k];
+      while (r >= bstart[d + 1]) ++d;
+      if (r != cursor[d]) { valid = false; break; }
+      ++cursor[d];
+    }
+  }
+  snapshot(S);   // closing row: every cursor at its bucket end
+  if (valid && check_neighbours) {
+    for (int64_t i = 0; i < N && valid; ++i)
+      for (int32_t k = row_ptr[i]; k < row_ptr[i + 1]; ++k)
+        if (membership[col_idx[k]] != membership[i]) { valid = false; break; }
+  }
+  int64_t max_rows = 0, max_entries = 0;
+  for (int64_t g = 0; g < G; ++g) {
+    int64_t rows = 0, entries = 0;
+    for (int d = 0; d < DCGC_N_DEG; ++d) {
+      const int64_t n = tab[(g + 1) * DCGC_GROUP_STRIDE + d] - tab[g * DCGC_GROUP_STRIDE + d];
+      rows += n;
+      entries += n * d;
+    }
+    max_rows = std::max(max_rows, rows);
+    max_entries = std::max(max_entries, entries);
+  }
+  gt[0] = valid ? (int32_t)G : 0;
+  gt[1] = (int32_t)max_rows;
+  gt[2] = (int32_t)max_entries;
+  gt[3] = valid ? 1 : 0;
+  gt[4] = R;
 }
 
 extern "C" int dcgc_layout_build(int64_t n_mols, const int32_t* atom_ptr, const int32_t* adj_ptr,
@@ -212,7 +289,7 @@ extern "C" int dcgc_layout_build(int64_t n_mols, const int32_t* atom_ptr, const 
       }
     }
   }
-  build_derived(info, slab);
+  build_derived(info, slab, false);
   return DCGC_OK;
 }
 
@@ -253,7 +330,7 @@ extern "C" int dcgc_layout_build_from_deg(const int64_t* deg_slice, const int32_
   memcpy(slab + info->off_col_idx, col_idx, (size_t)E * 4);
   int32_t* perm = (int32_t*)(slab + info->off_perm);
   for (int64_t i = 0; i < N; ++i) perm[i] = (int32_t)i;
-  build_derived(info, slab);
+  build_derived(info, slab, true);
   return DCGC_OK;
 }
 

@@ -15,6 +15,8 @@
 //   * the self-path and neighbour-path input gradients are added inside the transposed gather.
 #include <math.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace {
@@ -503,6 +505,16 @@ int check_topo(const dcgc_topology* t) {
   return DCGC_OK;
 }
 
+// staged (molecule-group) kernels unless DCGC_NO_STAGED=1 (A/B measurements)
+static bool staged_enabled() {
+  static const bool on = [] { const char* e = getenv("DCGC_NO_STAGED"); return !(e && e[0] == '1'); }();
+  return on;
+}
+static bool use_mg(const dcgc_topology* t, int64_t ld, int64_t ld_arg, const void* p0, const void* p1) {
+  return staged_enabled() && t->symmetric && dcgc_mg_supported(t, ld, ld_arg) &&
+         ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
+}
+
 #define RET_IF(expr)                \
   do {                              \
     int st__ = (expr);              \
@@ -583,7 +595,10 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
     const int64_t ld = sv.ld_h[l];
     conv_bias_pack<<<blocks_for(DCGC_N_DEG * c), kT, 0, st>>>(params + lo.conv_b[l], c, sv.b11[l]);
     DCGC_CUDA_LAUNCH_CHECK("conv_bias_pack");
-    RET_IF(dcgc_gather_sum_bucketed(h, ld, t->deg_count, t->col_idx, N, fp, nullptr, 0, sv.s[l], fp, st));
+    if (use_mg(t, ld, 0, h, sv.s[l]))
+      RET_IF(dcgc_mg_gather_sum(h, ld, t, 0, fp, nullptr, 0, sv.s[l], fp, st));
+    else
+      RET_IF(dcgc_gather_sum_bucketed(h, ld, t->deg_count, t->col_idx, N, fp, nullptr, 0, sv.s[l], fp, st));
     const bool fuse_stats = cfg->batch_norm && training && dcgc_tc_terms(cfg->gemm_mode) != 0;
     int32_t fused = -1;
     if (fuse_stats)
@@ -598,8 +613,11 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
       scale = sv.stats + sv.stats_off[l] + 2 * c;
       shift = scale + c;
     }
-    RET_IF(dcgc_pool_fwd(sv.y[l], c, scale, shift, t->row_ptr, t->col_idx, N, c, const_cast<float*>(sv.h[l + 1]), c,
-                         sv.arg[l], c, st));
+    if (use_mg(t, c, 0, sv.y[l], sv.h[l + 1]))
+      RET_IF(dcgc_mg_pool_fwd(sv.y[l], c, scale, shift, t, c, const_cast<float*>(sv.h[l + 1]), c, sv.arg[l], c, st));
+    else
+      RET_IF(dcgc_pool_fwd(sv.y[l], c, scale, shift, t->row_ptr, t->col_idx, N, c, const_cast<float*>(sv.h[l + 1]), c,
+                           sv.arg[l], c, st));
   }
   // ---- atom-level dense + ReLU (+BN folded into the gather), GraphGather(tanh), head
   int32_t fused_d = -1;
@@ -823,7 +841,10 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
   for (int l = L - 1; l >= 0; --l) {
     const int c = cfg->widths[l], fp = lo.fp[l];
     // GraphPool backward over CSR^T: dP (ld c) -> dA (ld c)
-    RET_IF(dcgc_pool_bwd(dP, c, sv.arg[l], c, nullptr, t->t_row_ptr, t->t_src, t->t_slot, N, c, dA, c, st));
+    if (use_mg(t, c, c, dP, sv.arg[l]) && (reinterpret_cast<uintptr_t>(dA) & 15) == 0)
+      RET_IF(dcgc_mg_pool_bwd(dP, c, sv.arg[l], c, nullptr, t, c, dA, c, st));
+    else
+      RET_IF(dcgc_pool_bwd(dP, c, sv.arg[l], c, nullptr, t->t_row_ptr, t->t_src, t->t_slot, N, c, dA, c, st));
     RET_IF(bn_backward(l, sv.y[l], c));
     RET_IF(dcgc_group_gemm_wgrad(cfg->gemm_mode, sv.h[l], sv.ld_h[l], fp, sv.s[l], fp, fp, dA, c, c, t->deg_count,
                                  DCGC_N_DEG, grads + lo.conv_w[l], db11, wg, wg_bytes, st));
@@ -833,7 +854,9 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
       // [dP | d2] = G . W^T, then dP += transposed gather of d2
       RET_IF(dcgc_group_gemm_dgrad(cfg->gemm_mode, dA, c, c, params + lo.conv_w[l], fp, fp, t->tiles, t->n_tiles, 128,
                                    N, dP, fp, d2, fp, st));
-      if (t->symmetric)
+      if (use_mg(t, fp, 0, d2, dP))
+        RET_IF(dcgc_mg_gather_sum(d2, fp, t, 1, fp, dP, fp, dP, fp, st));
+      else if (t->symmetric)
         RET_IF(dcgc_gather_sum_bucketed(d2, fp, t->deg_count, t->t_src, N, fp, dP, fp, dP, fp, st));
       else
         RET_IF(dcgc_gather_sum(d2, fp, t->t_row_ptr, t->t_src, N, fp, dP, fp, dP, fp, st));

@@ -39,6 +39,11 @@ def topology_struct(topo):
     for name in ("row_ptr", "col_idx", "t_row_ptr", "t_src", "t_slot", "mol_ptr", "mol_atoms", "membership", "tiles"):
         setattr(st, name, getattr(topo, name).data_ptr())
     st.symmetric = 1 if getattr(topo, "symmetric", False) else 0
+    st.groups = topo.groups[1:].data_ptr()      # past the header row
+    st.n_groups, st.group_max_rows = topo.n_groups, topo.group_max_rows
+    st.group_max_entries = topo.group_max_entries
+    rec = getattr(topo, "mg_records", None)
+    st.mg_records = rec.data_ptr() if rec is not None else None
     topo._c_struct = st
     return st
 

@@ -435,7 +435,7 @@ class GraphConvModel(object):
             # upper bound of the slab size without running the planner: 11 int32 arrays over atoms /
             # edges / segments plus alignment
             need = 4 * (5 * (packed.n_atoms + 2) + 3 * int(packed.adj_ptr[-1]) + (n_seg + 2)
-                        + 4 * (packed.n_atoms // 128 + 12)) + 256 * 16
+                        + 4 * (packed.n_atoms // 128 + 12) + 12 * (packed.n_atoms // 4 + 4)) + 256 * 16
             slot = self._staging_slab(need)
         layout = BatchLayout.build(packed, n_segments=n_seg, pinned=pinned,
                                    staging=slot[0] if slot is not None else None)
@@ -462,7 +462,8 @@ class GraphConvModel(object):
             raise TypeError("inputs must come from GraphConvModel.default_generator / batch_inputs")
         layout = inputs.layout
         buf = slot.get("slab", int(layout.info.slab_bytes), torch.uint8) if slot is not None else None
-        topo = layout.to_device(self.device, buffer=buf)
+        rec = slot.get("mgrec", 80 * layout.n_atoms, torch.uint8) if slot is not None else None
+        topo = layout.to_device(self.device, buffer=buf, record_buffer=rec)
         sslot = getattr(layout, "_staging_slot", None)
         if sslot is not None:
             sslot[1] = torch.cuda.Event()

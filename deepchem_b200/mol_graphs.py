@@ -172,7 +172,9 @@ _SLAB_FIELDS = (
     ("mol_ptr", "off_mol_ptr", np.int32, lambda i: i.n_segments + 1),
     ("mol_atoms", "off_mol_atoms", np.int32, lambda i: i.n_atoms),
     ("tiles", "off_tiles", np.int32, lambda i: 4 * i.n_tiles),
+    ("groups", "off_groups", np.int32, lambda i: GROUP_STRIDE * (i.n_groups_alloc + 2)),
 )
+GROUP_STRIDE = 12   # DCGC_GROUP_STRIDE
 
 
 class BatchLayout(object):
@@ -188,6 +190,9 @@ class BatchLayout(object):
             setattr(self, name, slab[off:off + n * np.dtype(dt).itemsize].view(dt))
         self.deg_slice = self.deg_slice.reshape(11, 2)
         self.tiles = self.tiles.reshape(-1, 4)
+        # molecule-group table of the staged kernels: header row, then one row per group (+ a closing row)
+        self.groups = self.groups.reshape(-1, GROUP_STRIDE)
+        self.n_groups, self.group_max_rows, self.group_max_entries = (int(v) for v in self.groups[0, :3])
         self.deg_count = [int(c) for c in info.deg_count]
         # in-degree == degree for every atom (always true for molecular graphs; not with a master atom)
         self.symmetric = bool(np.array_equal(self.row_ptr, self.t_row_ptr))
@@ -293,15 +298,15 @@ class BatchLayout(object):
         return [mm.get_atom_features(), mm.deg_slice, np.array(mm.membership),
                 np.array(self.n_mols if n_samples is None else n_samples)] + mm.deg_adj_lists[1:]
 
-    def to_device(self, device, non_blocking=True, buffer=None):
-        return DeviceTopology(self, device, non_blocking, buffer)
+    def to_device(self, device, non_blocking=True, buffer=None, record_buffer=None):
+        return DeviceTopology(self, device, non_blocking, buffer, record_buffer)
 
 
 class DeviceTopology(object):
     """Device-resident integer layout: one buffer, int32 views.  Everything the kernels need
     about the batch graph; features are NOT in here."""
 
-    def __init__(self, layout, device, non_blocking=True, buffer=None):
+    def __init__(self, layout, device, non_blocking=True, buffer=None, record_buffer=None):
         import torch
         self.layout = layout
         self.device = torch.device(device)
@@ -322,11 +327,29 @@ class DeviceTopology(object):
             setattr(self, name, view)
         self.deg_slice = self.deg_slice.view(11, 2)
         self.tiles = self.tiles.view(-1, 4)
+        self.groups = self.groups.view(-1, GROUP_STRIDE)
+        self.n_groups, self.group_max_rows = layout.n_groups, layout.group_max_rows
+        self.group_max_entries = layout.group_max_entries
         self.n_atoms, self.n_edges = layout.n_atoms, layout.n_edges
         self.n_mols, self.n_segments, self.n_tiles = layout.n_mols, layout.n_segments, layout.n_tiles
         self.deg_count = layout.deg_count
         self.symmetric = layout.symmetric
         self._deg_count_c = (ctypes.c_int64 * 11)(*self.deg_count)
+        # per-row records of the molecule-group staged kernels, derived on the device from the uploaded slab
+        # (same stream as the copy above)
+        self.mg_records = None
+        if self.n_groups > 0 and self.n_atoms > 0 and self.device.type == "cuda":
+            from .engine import topology_struct
+            L = _lib.lib()
+            nrec = int(L.dcgc_mg_record_bytes(self.n_atoms))
+            if record_buffer is not None and record_buffer.numel() >= nrec:
+                rec = record_buffer
+            else:
+                rec = torch.empty(nrec, dtype=torch.uint8, device=self.device)
+            _lib.check(L.dcgc_mg_prepare(ctypes.byref(topology_struct(self)), rec.data_ptr(),
+                                         ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+            self.mg_records = rec
+            self._c_struct = None       # rebuilt with the record pointer on next use
 
     def deg_adjacency_lists(self):
         out, off = [], 0

@@ -121,6 +121,41 @@ def gather_sum(x, row_ptr, idx, n_rows_out, addend=None, out=None):
     return out
 
 
+def _topo_struct(topo):
+    from .engine import topology_struct
+    return ctypes.byref(topology_struct(topo))
+
+
+def mg_supported(topo, ld_floats, ld_arg_bytes=0):
+    """True if the molecule-group staged kernels (csrc/molgroup_kernels.cu) can run on this topology with rows
+    of ld_floats floats (+ ld_arg_bytes argmax bytes): valid group table, symmetric adjacency, rows fit in
+    shared memory."""
+    if topo is None or not getattr(topo, "n_groups", 0) or not getattr(topo, "symmetric", False):
+        return False
+    return bool(_lib.lib().dcgc_mg_supported(_topo_struct(topo), int(ld_floats), int(ld_arg_bytes)))
+
+
+def _al16(*ts):
+    return all(t is None or t.data_ptr() % 16 == 0 for t in ts)
+
+
+def neighbor_sum(x, topo, transposed=False, addend=None):
+    """K1 / K5 over a DeviceTopology: the staged kernel when the layout allows it, else the CSR gather."""
+    x = _rowmajor(x)
+    n, width = topo.n_atoms, x.shape[1]
+    if n and width % 4 == 0 and _ld(x) % 4 == 0 and mg_supported(topo, _ld(x)) and \
+            (addend is None or _ld(addend) % 4 == 0):
+        out = addend if addend is not None else padded_empty(n, width, x.device)
+        if _al16(x, out):
+            check(_lib.lib().dcgc_mg_gather_sum(_p(x), _ld(x), _topo_struct(topo), 1 if transposed else 0, width,
+                                                _p(addend), _ld(addend) if addend is not None else 0,
+                                                _p(out), _ld(out), _stream()))
+            return out
+    if transposed:
+        return gather_sum(x, topo.t_row_ptr, topo.t_src, n, addend=addend)
+    return gather_sum(x, topo.row_ptr, topo.col_idx, n, addend=addend)
+
+
 def permute_rows(src, perm, n_feat=None, ld_out=None, out=None):
     src = _rowmajor(src)
     n_feat = src.shape[1] if n_feat is None else n_feat
@@ -206,12 +241,12 @@ class NeighborSum(torch.autograd.Function):
     def forward(ctx, x, topo):
         _check_dev(x, "atom_features")
         ctx.topo = topo
-        return gather_sum(x, topo.row_ptr, topo.col_idx, topo.n_atoms)
+        return neighbor_sum(x, topo)
 
     @staticmethod
     def backward(ctx, ds):
         topo = ctx.topo
-        return gather_sum(_rowmajor(ds), topo.t_row_ptr, topo.t_src, topo.n_atoms), None
+        return neighbor_sum(_rowmajor(ds), topo, transposed=True), None
 
 
 class GraphConvFn(torch.autograd.Function):
@@ -226,7 +261,7 @@ class GraphConvFn(torch.autograd.Function):
         x = _rowmajor(x)
         fp = w.shape[1] // 2
         xk = _widen(x, fp)
-        s = gather_sum(xk, topo.row_ptr, topo.col_idx, topo.n_atoms)
+        s = neighbor_sum(xk, topo)
         y = group_gemm_fwd(xk, s, w, bias, topo, act, mode)
         ctx.topo, ctx.act, ctx.mode, ctx.f = topo, act, mode, x.shape[1]
         ctx.save_for_backward(xk, s, w, y if act != ACT_NONE else None)
@@ -247,7 +282,7 @@ class GraphConvFn(torch.autograd.Function):
             dw, db = group_gemm_wgrad(xk, s, g, topo, 11, mode)
         if ctx.needs_input_grad[0]:
             d1, d2 = group_gemm_dgrad(g, w, fp, fp, topo, True, True, mode)
-            dx = gather_sum(d2, topo.t_row_ptr, topo.t_src, topo.n_atoms, addend=d1)
+            dx = neighbor_sum(d2, topo, transposed=True, addend=d1)
             dx = dx[:, :ctx.f]
         return dx, dw, db, None, None, None
 
@@ -305,8 +340,12 @@ class GraphPoolFn(torch.autograd.Function):
         out = padded_empty(n, c, x.device)
         ld_arg = (c + 3) // 4 * 4
         arg = torch.empty(n, ld_arg, dtype=torch.uint8, device=x.device) if x.requires_grad else None
-        check(_lib.lib().dcgc_pool_fwd(_p(x), _ld(x), None, None, _p(topo.row_ptr), _p(topo.col_idx),
-                                       n, c, _p(out), _ld(out), _p(arg), ld_arg, _stream()))
+        if n and c % 4 == 0 and _ld(x) % 4 == 0 and _al16(x, out) and mg_supported(topo, _ld(x)):
+            check(_lib.lib().dcgc_mg_pool_fwd(_p(x), _ld(x), None, None, _topo_struct(topo), c, _p(out), _ld(out),
+                                              _p(arg), ld_arg, _stream()))
+        else:
+            check(_lib.lib().dcgc_pool_fwd(_p(x), _ld(x), None, None, _p(topo.row_ptr), _p(topo.col_idx),
+                                           n, c, _p(out), _ld(out), _p(arg), ld_arg, _stream()))
         _count()
         ctx.topo = topo
         ctx.save_for_backward(arg)
@@ -319,8 +358,13 @@ class GraphPoolFn(torch.autograd.Function):
         dy = _rowmajor(dy)
         n, c = dy.shape
         dx = padded_empty(n, c, dy.device)
-        check(_lib.lib().dcgc_pool_bwd(_p(dy), _ld(dy), _p(arg), arg.stride(0), None, _p(topo.t_row_ptr),
-                                       _p(topo.t_src), _p(topo.t_slot), n, c, _p(dx), _ld(dx), _stream()))
+        if n and c % 4 == 0 and _ld(dy) % 4 == 0 and _al16(dy, dx, arg) and \
+                mg_supported(topo, _ld(dy), arg.stride(0)):
+            check(_lib.lib().dcgc_mg_pool_bwd(_p(dy), _ld(dy), _p(arg), arg.stride(0), None, _topo_struct(topo), c,
+                                              _p(dx), _ld(dx), _stream()))
+        else:
+            check(_lib.lib().dcgc_pool_bwd(_p(dy), _ld(dy), _p(arg), arg.stride(0), None, _p(topo.t_row_ptr),
+                                           _p(topo.t_src), _p(topo.t_slot), n, c, _p(dx), _ld(dx), _stream()))
         _count()
         return dx, None
 

@@ -94,7 +94,22 @@ typedef struct dcgc_layout_info {
   int64_t off_mol_atoms;  /* int32 [N]   rows of each molecule, ascending              */
   int64_t off_tiles;      /* int32 [n_tiles,4] = (row0, n_rows, degree, 0)             */
   int64_t slab_bytes;
+  /* Molecule groups for the shared-memory staged kernels (dcgc_mg_*): consecutive molecules are packed
+   * greedily into groups of at most group_rows atoms (a larger molecule is a group of its own).  Inside a degree
+   * bucket the rows are ordered by molecule, so the rows of a group are ONE contiguous range per bucket: a
+   * CTA stages them with one bulk copy per bucket and finds every neighbour in shared memory (no edge leaves
+   * a molecule).  int32 [DCGC_GROUP_STRIDE * (1 + n_groups_alloc + 1)]:
+   *   header  {n_groups, max rows of a group, max neighbour entries of a group, valid, group_rows, 0...}
+   *   row g   {first row of group g in bucket 0..10, first molecule of group g}; row n_groups closes the last
+   * `valid` is 0 when the layout does not have the property (rows of a bucket not ordered by molecule, or a
+   * neighbour in another molecule: possible only for hand-made dcgc_layout_build_from_deg inputs); the staged
+   * kernels then must not be used. */
+  int64_t off_groups;
+  int32_t group_rows;
+  int32_t n_groups_alloc;
 } dcgc_layout_info;
+#define DCGC_GROUP_STRIDE 12
+#define DCGC_GROUP_ROWS_DEFAULT 128
 
 /* Pass 1: validate degrees, count, and compute sizes / offsets.  O(N). */
 int dcgc_layout_plan(int64_t n_mols, const int32_t* atom_ptr, const int32_t* adj_ptr,
@@ -312,6 +327,13 @@ typedef struct dcgc_topology {
   int32_t symmetric;    /* 1 if t_row_ptr == row_ptr (every atom's in-degree equals its degree: true for
                            molecular graphs, false e.g. with a master atom, feat/graph_features.py:906-909) */
   int32_t reserved;
+  /* molecule-group table (device pointer to the first table row, i.e. past the header) and the header values
+   * read back on the host; n_groups == 0 disables the staged kernels */
+  const int32_t* groups;
+  int32_t n_groups, group_max_rows, group_max_entries, reserved2;
+  /* per-row records of the staged kernels: dcgc_mg_record_bytes(n_atoms) device bytes filled by dcgc_mg_prepare
+   * (NULL: staged kernels off) */
+  const void* mg_records;
 } dcgc_topology;
 
 typedef struct dcgc_gcmodel_config {
@@ -327,6 +349,33 @@ typedef struct dcgc_gcmodel_config {
   float bn_eps;                          /* 1e-3 */
   float bn_momentum;                     /* 0.99: weight of the NEW statistic (torch convention) */
 } dcgc_gcmodel_config;
+
+/* --------------------------------------------------------------------------------------------
+ * Molecule-group staged variants of K1/K5, K3 and K7 (csrc/molgroup_kernels.cu): one CTA per molecule group
+ * of the layout slab stages the group's atom rows in shared memory with one bulk (TMA) copy per degree bucket
+ * and gathers from there, so every activation row is read from HBM/L2 once, as a contiguous burst.  Same
+ * arithmetic and summation / tie order as dcgc_gather_sum_bucketed / dcgc_pool_fwd / dcgc_pool_bwd (bit
+ * identical results).  dcgc_mg_supported: 1 if the topology carries a valid group table and rows of
+ * ld_floats floats (plus, for the pool backward, ld_arg_bytes of argmax bytes) of its largest group fit in
+ * shared memory (at least two pipeline stages); leading dimensions must be multiples of 4 floats / 16 bytes.  transposed != 0 walks the
+ * transposed lists (t_src) and requires a symmetric adjacency.
+ * ------------------------------------------------------------------------------------------ */
+int dcgc_mg_supported(const dcgc_topology* topo, int64_t ld_floats, int64_t ld_arg_bytes);
+/* Once per batch, after the slab upload: fill topo-independent-of-width per-row records (row id, degree, the
+ * shared-memory slot of every neighbour inside the row's group; for the transposed lists also the slot of the
+ * row in each neighbour's list) into records_dev (dcgc_mg_record_bytes(n_atoms) bytes, 16-byte aligned).  The
+ * caller then stores the pointer in topo->mg_records.  topo->mg_records is not read by this call. */
+int64_t dcgc_mg_record_bytes(int64_t n_atoms);
+int dcgc_mg_prepare(const dcgc_topology* topo, void* records_dev, void* stream);
+int dcgc_mg_gather_sum(const float* x_dev, int64_t ld_x, const dcgc_topology* topo, int32_t transposed,
+                       int32_t width, const float* addend_dev, int64_t ld_add, float* out_dev, int64_t ld_out,
+                       void* stream);
+int dcgc_mg_pool_fwd(const float* x_dev, int64_t ld_x, const float* scale_dev, const float* shift_dev,
+                     const dcgc_topology* topo, int32_t width, float* out_dev, int64_t ld_out, uint8_t* arg_dev,
+                     int64_t ld_arg, void* stream);
+int dcgc_mg_pool_bwd(const float* dy_dev, int64_t ld_dy, const uint8_t* arg_dev, int64_t ld_arg,
+                     const float* scale_dev, const dcgc_topology* topo, int32_t width, float* dx_dev,
+                     int64_t ld_dx, void* stream);
 
 /* param_offsets: 4 per conv layer (W, b, gamma, beta), then dense (W, b, gamma, beta), then head
  * (W, b); -1 where batch_norm is off.  bn_offsets: (mean, var) per BN, conv layers then dense. */

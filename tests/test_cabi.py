@@ -40,9 +40,27 @@ def test_device_probe_does_not_crash_without_gpu():
     assert _lib.lib().dcgc_device_ok() in (0, 1)
 
 
-def test_struct_layout_matches_header():
-    # 5 int64 + 2 int32 + 11 int64 + 12 int64
-    assert ctypes.sizeof(_lib.LayoutInfo) == 5 * 8 + 8 + 11 * 8 + 12 * 8
+def test_struct_layout_matches_header(tmp_path):
+    """sizeof / offsetof of every struct in dcgc.h, as gcc lays them out, against the ctypes mirrors."""
+    import subprocess
+    structs = {"dcgc_layout_info": _lib.LayoutInfo, "dcgc_topology": _lib.Topology,
+               "dcgc_gcmodel_config": _lib.GcModelConfig, "dcgc_dmpnn_info": _lib.DmpnnInfo}
+    lines = []
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dcgc.h"\nint main(void) {\n%s\nreturn 0; }\n'
+                   % "\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+    assert ctypes.sizeof(_lib.LayoutInfo) == 5 * 8 + 8 + 11 * 8 + 12 * 8 + 16
 
 
 def test_ops_refuse_cpu_tensors():

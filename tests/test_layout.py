@@ -119,3 +119,87 @@ def test_asymmetric_adjacency_master_atom():
         for e in range(lay.t_row_ptr[j], lay.t_row_ptr[j + 1]):
             assert lay.col_idx[lay.row_ptr[lay.t_src[e]] + lay.t_slot[e]] == j
     assert lay.t_row_ptr[-1] == lay.n_edges == 7
+
+
+# ---------------------------------------------------------------------------- molecule-group table
+def _check_groups(lay, R):
+    """The table the staged kernels rely on: every group is one contiguous row range per degree bucket, those
+    ranges hold exactly the rows of the group's molecules, and every neighbour of a row is in its group."""
+    g = lay.groups
+    n_groups, max_rows, max_entries, valid, rows_budget = (int(v) for v in g[0, :5])
+    assert valid == 1 and rows_budget == R
+    N = lay.n_atoms
+    tab = g[1:n_groups + 2, :11].astype(np.int64)
+    starts = lay.deg_slice[:, 0] if N else np.zeros(11, np.int64)
+    counts = np.asarray(lay.deg_count, np.int64)
+    bstart = np.concatenate([[0], np.cumsum(counts)])[:11]
+    assert np.array_equal(tab[0], bstart) and np.array_equal(tab[-1], bstart + counts)
+    assert (np.diff(tab, axis=0) >= 0).all()
+    group_of_row = np.full(N, -1, np.int64)
+    seen_rows = seen_entries = 0
+    for k in range(n_groups):
+        rows = np.concatenate([np.arange(tab[k, d], tab[k + 1, d]) for d in range(11)])
+        group_of_row[rows] = k
+        n_ent = int(sum((tab[k + 1, d] - tab[k, d]) * d for d in range(11)))
+        seen_rows, seen_entries = max(seen_rows, rows.size), max(seen_entries, n_ent)
+    assert (group_of_row >= 0).all() and seen_rows == max_rows and seen_entries == max_entries
+    # greedy packing of consecutive molecules: the group is a non-decreasing function of the molecule, a group
+    # holds at most R rows unless it is a single molecule, and two consecutive groups never fit in one
+    sizes = np.diff(lay.mol_ptr).astype(np.int64)
+    mol_group = np.full(sizes.size, -1, np.int64)
+    mol_group[lay.membership] = group_of_row
+    assert all(np.unique(group_of_row[lay.membership == m]).size == 1 for m in np.unique(lay.membership)[:50])
+    mg = mol_group[sizes > 0]
+    assert (np.diff(mg) >= 0).all() and (n_groups == 0 or (mg[0] == 0 and mg[-1] == n_groups - 1))
+    rows_of_group = np.bincount(group_of_row, minlength=n_groups)
+    mols_of_group = np.bincount(mg, minlength=n_groups)
+    assert ((rows_of_group <= R) | (mols_of_group == 1)).all() and (rows_of_group > 0).all()
+    first_mol_rows = sizes[sizes > 0][np.searchsorted(mg, np.arange(n_groups))]
+    assert (rows_of_group[:-1] + first_mol_rows[1:] > R).all()
+    assert np.array_equal(g[1:n_groups + 2, 11], np.concatenate([np.flatnonzero(sizes > 0)[np.searchsorted(mg, np.arange(n_groups))], [lay.n_segments]]))
+    rows_of_entry = np.repeat(np.arange(N), np.diff(lay.row_ptr))
+    assert np.array_equal(group_of_row[lay.col_idx], group_of_row[rows_of_entry])
+    assert np.array_equal(group_of_row[lay.t_src], group_of_row[np.repeat(np.arange(N), np.diff(lay.t_row_ptr))])
+    del starts
+
+
+@pytest.mark.parametrize("shape,n,segs", [("zinc", 300, 300), ("stress", 257, 300), ("delaney", 5, 5),
+                                          ("zinc", 1, 2)])
+def test_group_table(shape, n, segs):
+    from deepchem_b200.synthetic import make_molecules
+    from deepchem_b200.mol_graphs import BatchLayout
+    pm = make_molecules(n, seed=11, shape=shape)
+    lay = BatchLayout.build(pm, n_segments=segs)
+    _check_groups(lay, int(lay.info.group_rows))
+    # the same table from the reference-shaped arrays (GraphConv layers handed plain tensors)
+    lay2 = BatchLayout.from_reference_arrays(lay.deg_slice, lay.membership, lay.deg_adjacency_lists(), segs)
+    assert np.array_equal(lay2.groups, lay.groups)
+
+
+def test_group_table_rejects_foreign_layouts():
+    """Hand-made layouts without the (degree, molecule) row order, or with an edge between molecules, get no
+    group table (n_groups == 0), which switches the staged kernels off."""
+    from deepchem_b200.synthetic import make_molecules
+    from deepchem_b200.mol_graphs import BatchLayout
+    pm = make_molecules(40, seed=3, shape="zinc")
+    lay = BatchLayout.build(pm)
+    mem = lay.membership.copy()
+    d2 = np.flatnonzero(np.diff(mem[:lay.deg_count[0] + lay.deg_count[1]]) > 0)
+    i = int(d2[0])
+    mem[i], mem[i + 1] = mem[i + 1], mem[i]          # rows of a bucket no longer ordered by molecule
+    bad = BatchLayout.from_reference_arrays(lay.deg_slice, mem, lay.deg_adjacency_lists(), 40)
+    assert bad.n_groups == 0 and int(bad.groups[0, 3]) == 0
+    adj = [a.copy() for a in lay.deg_adjacency_lists()]
+    first = int(lay.deg_slice[1, 0])
+    other = int(np.flatnonzero(lay.membership != lay.membership[first])[0])
+    adj[1][0, 0] = other                             # an edge into another molecule
+    bad = BatchLayout.from_reference_arrays(lay.deg_slice, lay.membership, adj, 40)
+    assert bad.n_groups == 0
+
+
+def test_empty_batch_has_no_groups():
+    from deepchem_b200.synthetic import PackedMols
+    from deepchem_b200.mol_graphs import BatchLayout
+    pm = PackedMols(np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros((0, 75), np.float32))
+    lay = BatchLayout.build(pm, n_segments=2)
+    assert lay.n_groups == 0 and lay.group_max_rows == 0
