@@ -31,12 +31,12 @@ if ROOT not in sys.path:
 WORKLOAD = "zinc-synthetic B=4096/GPU, 25 atoms avg, F=75, GraphConv[128,128,128]+dense128+BN, regression T=1"
 LAYERS = [128, 128, 128]
 DENSE = 128
-# dram__bytes_read.sum + dram__bytes_write.sum per gather_sum launch, mean over the 5 launches of one step
-# (1 layer-0 forward 33.2 MB, 2 forward 77.6 MB, 2 backward 132.9 MB), from the ncu --set full capture of this
-# command summarised in profiles/r1p_ncu_gather_sum_bucketed.md: BELOW the algorithmic bytes because the
-# 52 MB activation tensors are partly still L2-resident when the gather reads them.
-NCU_GATHER_SUM_TRAFFIC = 90.9e6
-NCU_TRAFFIC_SOURCE = ("profiles/r1p_ncu_gather_sum_bucketed.md (ncu --set full, dram__bytes_read.sum + "
+# dram__bytes_read.sum + dram__bytes_write.sum per gather-sum launch, mean over the 5 launches of one step
+# (layer-0 forward 34.9 MB, 2 forward 61.1 / 63.0 MB, 2 backward 116.8 / 118.4 MB), from the ncu --set full
+# capture of this command summarised in profiles/r2f_ncu_staged_kernels.md: BELOW the algorithmic bytes because
+# most of the 52 MB a launch writes is still in the 126 MB L2 when the kernel ends (DRAM writes 0.5-9 MB).
+NCU_GATHER_SUM_TRAFFIC = 78.8e6
+NCU_TRAFFIC_SOURCE = ("profiles/r2f_ncu_staged_kernels.md (ncu --set full, dram__bytes_read.sum + "
                       "dram__bytes_write.sum, mean of the 5 launches of a step)")
 
 
@@ -291,21 +291,36 @@ def run_ours(args):
         from deepchem_b200.data import PackedDataset
         from deepchem_b200.synthetic import PackedMols
         big = PackedMols.concat([pm for pm, _, _ in pool]).pin_memory()
+        from deepchem_b200 import graphconvmodel as G
+        feat_item = 1 if (big.features_i8 is not None and G._USE_I8) else 4   # exact int8 copy of 0/1 features
+        topos = [r[0][1]._dcgc_topology for r in resident]
+        h2d_bytes = int(np.mean([int(t_.layout.info.slab_bytes) + t_.n_atoms * pool[0][0].n_feat * feat_item
+                                 for t_ in topos])) + pool[0][1].nbytes + pool[0][2].nbytes
         ds = PackedDataset(big, np.concatenate([y for _, y, _ in pool]), np.concatenate([w for _, _, w in pool]))
         model.log_frequency = 1                                # loss read back to the host every step
         losses = []
-        warm = itertools.islice(model.default_generator(ds, epochs=1000, deterministic=True), 12)
-        model.fit_generator(warm, checkpoint_interval=0, all_losses=losses)
-        barrier()
-        gen = itertools.islice(model.default_generator(ds, epochs=1000, deterministic=True), K)
-        t0 = time.perf_counter()
-        model.fit_generator(gen, checkpoint_interval=0, all_losses=losses)
+        # ONE fit_generator call over warm-up + K batches (the pipeline is filled during the warm-up steps, as the
+        # W warm-up steps of the resident region fill caches); the clock starts in the callback of the last
+        # warm-up step, after a barrier + device synchronize, and stops after the same at the end
+        warm_steps = 12
+        mark = {}
+        step0 = model._global_step
+
+        def at_step(_model, step, **kw):
+            if step - step0 == warm_steps:
+                barrier()
+                mark["t0"] = time.perf_counter()
+
+        gen = itertools.islice(model.default_generator(ds, epochs=1000, deterministic=True), warm_steps + K)
+        model.fit_generator(gen, checkpoint_interval=0, all_losses=losses, callbacks=[at_step])
         torch.cuda.synchronize()
-        ms2 = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        ms2 = max_over_ranks((time.perf_counter() - mark["t0"]) * 1e3)
         barrier()
-        assert len(losses) == K + 12
+        assert len(losses) == K + warm_steps
         e2e = {"value": world * B * K / (ms2 * 1e-3), "unit": "molecules/s", "ms_per_step": ms2 / K,
                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+               "feature_upload": "int8 (exact copy of the integer-valued feature matrix kept by the packed shard)"
+                                 if feat_item == 1 else "fp32",
                "api": "GraphConvModel.fit_generator(default_generator(PackedDataset)) with log_frequency=1: "
                       "C++ layout build (worker threads) + H2D from pinned host memory + fwd/bwd/Adam + a 4-byte "
                       "loss readback for every step (asynchronous, consumed one step late); host work of the "
@@ -324,7 +339,7 @@ def run_ours(args):
     if prof and prof["launches"]:
         prof["bytes"] = gs_bytes
         achieved = prof["bytes"] / (prof["ms"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "gather_sum_kernel<4, bucketed> (K1 neighbour gather-sum fwd + K5 transposed bwd)",
+        roof = {"bound": "hbm", "kernel": "mg_kernel<GatherSumOp> (molecule-group staged K1 neighbour gather-sum fwd + K5 transposed bwd)",
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": peak_src, "traffic": NCU_GATHER_SUM_TRAFFIC, "traffic_source": NCU_TRAFFIC_SOURCE,
                 "launches": prof["launches"],

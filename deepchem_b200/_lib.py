@@ -89,7 +89,9 @@ _SIGNATURES = {
     "dcgc_layout_permute_features_host": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, c_int64, c_int32]),
     "dcgc_layout_plan_from_deg": (c_int32, [_P, c_int64, c_int32, POINTER(LayoutInfo)]),
     "dcgc_layout_build_from_deg": (c_int32, [_P, _P, _P, POINTER(LayoutInfo), _P]),
+    "dcgc_h2d_chunked": (c_int32, [_P, _P, c_int64, c_int64, _P]),
     "dcgc_permute_rows": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, c_int64, _P]),
+    "dcgc_permute_rows_i8": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, c_int64, _P]),
     "dcgc_gather_sum": (c_int32, [_P, c_int64, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
     "dcgc_gather_sum_bucketed": (c_int32, [_P, c_int64, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
     "dcgc_mg_supported": (c_int32, [_P, c_int64, c_int64]),
@@ -124,6 +126,7 @@ _SIGNATURES = {
     "dcgc_gcmodel_workspace_bytes": (c_int64, [POINTER(GcModelConfig), c_int64, c_int64]),
     "dcgc_gcmodel_forward": (c_int32, [POINTER(GcModelConfig), POINTER(Topology), _P, c_int64, c_int64, _P, _P,
                                        c_int32, _P, c_int64, _P, _P, _P, _P]),
+    "dcgc_gcmodel_set_forward_event": (c_int32, [_P]),
     "dcgc_gcmodel_train_step": (c_int32, [POINTER(GcModelConfig), POINTER(Topology), _P, c_int64, _P, _P, c_int64,
                                           _P, _P, _P, _P, c_int64, _P, _P, _P]),
     "dcgc_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, c_float, _P]),

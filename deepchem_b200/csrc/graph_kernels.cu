@@ -53,6 +53,25 @@ permute_rows_kernel(const float* __restrict__ src, int64_t ld_src, const int32_t
   dst[row * ld_dst + c] = c < n_feat ? __ldg(src + (int64_t)__ldg(perm + row) * ld_src + c) : 0.f;
 }
 
+// same, from an int8 feature matrix (PackedMols stores integer-valued feature matrices — one-hots, formal charge,
+// radical electrons: every ConvMol feature — as int8; the conversion to fp32 is exact)
+__global__ void __launch_bounds__(kThreads)
+permute_rows_i8_kernel(const int8_t* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ perm,
+                       int64_t n_rows, int n_feat, float* __restrict__ dst, int64_t ld_dst) {
+  const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int groups = (int)(ld_dst >> 2);
+  const int64_t row = t / groups;
+  const int c = (int)(t - row * groups) * 4;
+  if (row >= n_rows) return;
+  const int8_t* s = src + (int64_t)__ldg(perm + row) * ld_src;
+  float4 v;
+  v.x = c + 0 < n_feat ? (float)__ldg(s + c + 0) : 0.f;
+  v.y = c + 1 < n_feat ? (float)__ldg(s + c + 1) : 0.f;
+  v.z = c + 2 < n_feat ? (float)__ldg(s + c + 2) : 0.f;
+  v.w = c + 3 < n_feat ? (float)__ldg(s + c + 3) : 0.f;
+  *reinterpret_cast<float4*>(dst + row * ld_dst + c) = v;
+}
+
 // ------------------------------------------------------------------------------------------
 // K1/K5/K8: CSR gather-sum
 // ------------------------------------------------------------------------------------------
@@ -380,6 +399,21 @@ extern "C" int dcgc_device_ok(void) {
   return major == 10 ? 1 : 0;
 }
 
+extern "C" int dcgc_h2d_chunked(void* dst, const void* src, int64_t bytes, int64_t chunk_bytes, void* stream) {
+  DCGC_CHECK_ARG(bytes >= 0, "dcgc_h2d_chunked: negative size");
+  if (bytes == 0) return DCGC_OK;
+  DCGC_CHECK_ARG(dst && src, "dcgc_h2d_chunked: null pointer");
+  if (chunk_bytes <= 0 || chunk_bytes > bytes) chunk_bytes = bytes;
+  chunk_bytes = (chunk_bytes + 255) / 256 * 256;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int64_t o = 0; o < bytes; o += chunk_bytes) {
+    const int64_t n = bytes - o < chunk_bytes ? bytes - o : chunk_bytes;
+    DCGC_CUDA_CALL(cudaMemcpyAsync(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, (size_t)n,
+                                   cudaMemcpyHostToDevice, st));
+  }
+  return DCGC_OK;
+}
+
 extern "C" int dcgc_permute_rows(const float* src, int64_t ld_src, const int32_t* perm, int64_t n_rows,
                                  int32_t n_feat, float* dst, int64_t ld_dst, void* stream) {
   DCGC_CHECK_ARG(n_rows >= 0 && n_feat >= 0 && ld_src >= n_feat && ld_dst >= n_feat,
@@ -389,6 +423,18 @@ extern "C" int dcgc_permute_rows(const float* src, int64_t ld_src, const int32_t
   permute_rows_kernel<<<grid_for(n_rows * ld_dst), kThreads, 0, (cudaStream_t)stream>>>(
       src, ld_src, perm, n_rows, n_feat, dst, ld_dst);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_permute_rows");
+  return DCGC_OK;
+}
+
+extern "C" int dcgc_permute_rows_i8(const int8_t* src, int64_t ld_src, const int32_t* perm, int64_t n_rows,
+                                    int32_t n_feat, float* dst, int64_t ld_dst, void* stream) {
+  DCGC_CHECK_ARG(n_rows >= 0 && n_feat >= 0 && ld_src >= n_feat && ld_dst >= n_feat, "dcgc_permute_rows_i8: bad sizes");
+  if (n_rows == 0 || ld_dst == 0) return DCGC_OK;
+  DCGC_CHECK_ARG(src && perm && dst, "dcgc_permute_rows_i8: null pointer");
+  DCGC_CHECK_ARG(ld_dst % 4 == 0 && aligned16(dst), "dcgc_permute_rows_i8: dst rows must be 16-byte aligned");
+  permute_rows_i8_kernel<<<grid_for(n_rows * (ld_dst / 4)), kThreads, 0, (cudaStream_t)stream>>>(
+      src, ld_src, perm, n_rows, n_feat, dst, ld_dst);
+  DCGC_CUDA_LAUNCH_CHECK("dcgc_permute_rows_i8");
   return DCGC_OK;
 }
 

@@ -27,14 +27,12 @@ void dcgc_set_error(const char* fmt, ...) {
 extern "C" const char* dcgc_last_error(void) { return g_err; }
 extern "C" int dcgc_version(void) { return 100; }
 
-// row budget of a molecule group (dcgc.h); DCGC_GROUP_ROWS overrides it for tuning
+// row budget of a molecule group (dcgc.h); DCGC_GROUP_ROWS overrides it (read at every plan: tuning runs and the
+// wide-row tests change it inside one process)
 static int group_rows_setting() {
-  static const int v = [] {
-    const char* e = getenv("DCGC_GROUP_ROWS");
-    const int x = e ? atoi(e) : 0;
-    return x >= 8 && x <= 4096 ? x : DCGC_GROUP_ROWS_DEFAULT;
-  }();
-  return v;
+  const char* e = getenv("DCGC_GROUP_ROWS");
+  const int x = e ? atoi(e) : 0;
+  return x >= 8 && x <= 4096 ? x : DCGC_GROUP_ROWS_DEFAULT;
 }
 
 static void plan_offsets(dcgc_layout_info* info) {

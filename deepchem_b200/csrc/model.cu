@@ -726,6 +726,12 @@ extern "C" int dcgc_gcmodel_forward(const dcgc_gcmodel_config* cfg, const dcgc_t
   return DCGC_OK;
 }
 
+static thread_local cudaEvent_t g_forward_event = nullptr;
+extern "C" int dcgc_gcmodel_set_forward_event(void* event) {
+  g_forward_event = (cudaEvent_t)event;
+  return DCGC_OK;
+}
+
 extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcgc_topology* topo, const float* x,
                                        int64_t ld_x, const float* y, const float* w, int64_t n_samples,
                                        const float* params, float* grads, float* bn_running, void* workspace,
@@ -741,6 +747,11 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
   Arena ws{(char*)workspace, 0, workspace_bytes};
   Saved sv{};
   RET_IF(forward_impl(cfg, lo, t, x, ld_x, n_samples, params, bn_running, 1, 1, ws, sv, st));
+  if (g_forward_event) {
+    cudaEvent_t ev = g_forward_event;
+    g_forward_event = nullptr;
+    DCGC_CUDA_CALL(cudaEventRecord(ev, st));
+  }
 
   // ---- backward scratch
   int wmax = D, fmax = 0;

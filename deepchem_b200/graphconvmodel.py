@@ -27,6 +27,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _lib as _lib_mod
 from . import ops
 from ._lib import ACT_NONE, ACT_RELU
 from .data import NumpyDataset, PackedDataset  # noqa: F401  (re-exported)
@@ -47,6 +48,35 @@ def _default_host_workers():
         cores = os.cpu_count() or 2
     ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
     return max(1, min(4, cores // ranks - 2))
+
+
+# upload the exact int8 copy of the features when the shard has one (DCGC_FEATURES_I8=0: always fp32)
+_USE_I8 = os.environ.get("DCGC_FEATURES_I8", "1") != "0"
+
+
+def _lib_handle():
+    return _lib_mod.lib()
+
+
+def _lib_check(status):
+    return _lib_mod.check(status)
+
+
+def _chunked_h2d(dst, src):
+    """dst.copy_(src) from pinned host memory as a train of moderate asynchronous copies on the current stream
+    (one C call, GIL released; dcgc_h2d_chunked).  One 30 MB cudaMemcpyAsync running beside the training kernels
+    slowed the forward kernels by up to 20 % of a step on B200; the same bytes in DCGC_H2D_CHUNK_MB (default 0.25)
+    MiB pieces cost a fraction of that (scripts/interference.py, profiles/r2_interference.md)."""
+    from .mol_graphs import _h2d_chunk_bytes
+    step = _h2d_chunk_bytes()
+    if step <= 0 or not (src.is_contiguous() and dst.is_contiguous() and src.is_pinned() and dst.is_cuda) or \
+            src.dtype != dst.dtype or src.numel() != dst.numel():
+        dst.copy_(src, non_blocking=True)
+        return
+    import ctypes
+    from . import _lib
+    _lib.check(_lib.lib().dcgc_h2d_chunked(dst.data_ptr(), src.data_ptr(), src.numel() * src.element_size(), step,
+                                           ctypes.c_void_p(torch.cuda.current_stream(dst.device).cuda_stream)))
 
 
 class _DoneEvent(object):
@@ -185,6 +215,7 @@ class BatchInputs(list):
     layout = None
     packed_features = None
     packed_features_pinned = None
+    packed_features_i8_pinned = None
 
 
 class _DeviceSlot(object):
@@ -236,9 +267,18 @@ class _Prefetcher(object):
         try:
             torch.cuda.set_device(self.model.device)
             k = 0
-            for batch in self.generator:
+            tr = self.model._pipe_trace          # optional stage timers (DCGC_PIPE_TRACE=1), seconds
+            clock = time.perf_counter
+            it = iter(self.generator)
+            while True:
+                t0 = clock()
+                try:
+                    batch = next(it)
+                except StopIteration:
+                    break
                 if self.stop:
                     break
+                t1 = clock()
                 slot = self.slots[k % len(self.slots)]
                 k += 1
                 with torch.cuda.stream(self.stream):
@@ -246,11 +286,23 @@ class _Prefetcher(object):
                         self.stream.wait_event(slot.free_event)      # the consumer finished with these buffers
                     if slot.copied_event is not None:
                         slot.copied_event.synchronize()              # pinned staging may be rewritten
+                    t2 = clock()
+                    fe = self.model._last_fwd_event
+                    if fe is not None:
+                        self.stream.wait_event(fe)                   # upload beside the backward pass
                     prepared = self.model._prepare_batch(batch, slot)
                     ev = torch.cuda.Event()
                     ev.record(self.stream)
                     slot.copied_event = ev
+                t3 = clock()
                 self.q.put((prepared, ev, slot))
+                if tr is not None:
+                    t4 = clock()
+                    tr["pf_wait_generator"] += t1 - t0
+                    tr["pf_wait_slot"] += t2 - t1
+                    tr["pf_prepare"] += t3 - t2
+                    tr["pf_wait_queue"] += t4 - t3
+                    tr["pf_batches"] += 1
         except BaseException as e:      # surfaced in the consumer
             self.error = e
         finally:
@@ -356,6 +408,20 @@ class GraphConvModel(object):
         self._loss_ring = [torch.zeros((), dtype=torch.float32).pin_memory() if self.device.type == "cuda"
                            else torch.zeros(()) for _ in range(4)]
         self._device_slots = []     # reusable per-batch device buffers of the prefetch pipeline
+        # upload phase (DCGC_H2D_PHASE=bwd, default): the prefetch stream starts a batch's uploads only after the
+        # forward pass of the newest launched step — beside the GEMM-heavy backward instead of the HBM-bound forward
+        # kernels, which one concurrent 35 MB upload slowed by 30-60 % (profiles/r2_interference.md)
+        self._fwd_events = None
+        self._last_fwd_event = None
+        if self.device.type == "cuda" and os.environ.get("DCGC_H2D_PHASE", "bwd") == "bwd":
+            self._fwd_events = []
+            with torch.cuda.device(self.device):
+                for _ in range(8):
+                    ev = torch.cuda.Event()
+                    ev.record()                  # materialises the cudaEvent_t handle
+                    self._fwd_events.append(ev)
+        # per-stage host timers of the fit pipeline (scripts/e2e_stages.py); None = off
+        self._pipe_trace = collections.defaultdict(float) if os.environ.get("DCGC_PIPE_TRACE") == "1" else None
         self._staging = []          # ring of reusable pinned slabs: [tensor, event]
         self._staging_next = 0
         import threading
@@ -450,6 +516,9 @@ class GraphConvModel(object):
         # measured: the 0.8 ms copy serialised with the 1.7 ms step instead of overlapping it.)
         pin = getattr(packed, "_pin", None)
         inputs.packed_features_pinned = pin if (pin is not None and tuple(pin.shape) == packed.features.shape) else None
+        # exact int8 copy of the same rows (PackedMols.compact): a quarter of the upload
+        p8 = getattr(packed, "_pin_i8", None)
+        inputs.packed_features_i8_pinned = p8 if (p8 is not None and tuple(p8.shape) == packed.features.shape) else None
         return inputs
 
     def _prepare_batch(self, batch, slot=None):
@@ -468,13 +537,15 @@ class GraphConvModel(object):
         if sslot is not None:
             sslot[1] = torch.cuda.Event()
             sslot[1].record(torch.cuda.current_stream())
-        feats = getattr(inputs, "packed_features_pinned", None)
+        feats = getattr(inputs, "packed_features_i8_pinned", None) if (slot is not None and _USE_I8) else None
+        if feats is None:
+            feats = getattr(inputs, "packed_features_pinned", None)
         if feats is None:
             feats = torch.from_numpy(np.ascontiguousarray(inputs.packed_features, dtype=np.float32))
         n, f = feats.shape
         if slot is not None:
-            fdev = slot.get("feats", n * f, torch.float32)[:n * f].view(n, f)
-            fdev.copy_(feats, non_blocking=True)
+            fdev = slot.get("feats8" if feats.dtype == torch.int8 else "feats", n * f, feats.dtype)[:n * f].view(n, f)
+            _chunked_h2d(fdev, feats)
             x = ops.permute_rows(fdev, topo.perm, out=slot.get("x", n * ((f + 3) // 4 * 4), torch.float32))
         else:
             x = ops.permute_rows(feats.to(self.device, non_blocking=True), topo.perm)
@@ -545,11 +616,20 @@ class GraphConvModel(object):
 
         prepared_iter = _Prefetcher(self, generator, prefetch) if prefetch else \
             (self._prepare_batch(b) for b in generator)
+        tr = self._pipe_trace
+        t_prev = time.perf_counter()
         for prepared in prepared_iter:
             if restore:
                 self.restore()
                 restore = False
+            if tr is not None:
+                t_a = time.perf_counter()
+                tr["fit_wait_batch"] += t_a - t_prev
             batch_loss = self._train_step(*prepared)
+            if tr is not None:
+                t_prev = time.perf_counter()
+                tr["fit_train_step_host"] += t_prev - t_a
+                tr["fit_steps"] += 1
             self._global_step += 1
             step = self._global_step
             if batch_loss.is_cuda:
@@ -608,8 +688,16 @@ class GraphConvModel(object):
         eng = self._engine
         topo = inputs[1]._dcgc_topology
         w = weights[0] if weights and weights[0] is not None else None
+        fe = None
+        if self._fwd_events is not None:
+            # the C call records this event between forward and backward; the prefetch stream waits on the latest
+            # one before it uploads a batch, so uploads run beside the backward pass (see _Prefetcher._run)
+            fe = self._fwd_events[self._global_step % len(self._fwd_events)]
+            _lib_check(_lib_handle().dcgc_gcmodel_set_forward_event(fe.cuda_event))
         loss = eng.train_step(topo, inputs[0], labels[0].contiguous(), w.contiguous() if w is not None else None,
                               int(inputs[3]))
+        if fe is not None:
+            self._last_fwd_event = fe
         scale = 1.0
         if self._dp:
             import torch.distributed as dist

@@ -302,6 +302,14 @@ class BatchLayout(object):
         return DeviceTopology(self, device, non_blocking, buffer, record_buffer)
 
 
+def _h2d_chunk_bytes():
+    import os
+    try:
+        return int(float(os.environ.get("DCGC_H2D_CHUNK_MB", "0.25")) * (1 << 20))
+    except ValueError:
+        return 1 << 18
+
+
 class DeviceTopology(object):
     """Device-resident integer layout: one buffer, int32 views.  Everything the kernels need
     about the batch graph; features are NOT in here."""
@@ -317,7 +325,15 @@ class DeviceTopology(object):
         else:
             self.buffer = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
         if nbytes:
-            self.buffer[:nbytes].copy_(src[:nbytes], non_blocking=non_blocking)
+            # a train of moderate copies instead of one large one: see graphconvmodel._chunked_h2d
+            step = _h2d_chunk_bytes() if (non_blocking and src.is_pinned() and self.device.type == "cuda") else 0
+            if step <= 0 or nbytes <= step:
+                self.buffer[:nbytes].copy_(src[:nbytes], non_blocking=non_blocking)
+            else:
+                import torch
+                _lib.check(_lib.lib().dcgc_h2d_chunked(
+                    self.buffer.data_ptr(), src.data_ptr(), nbytes, step,
+                    ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
         info = layout.info
         for name, off_attr, dt, length in _SLAB_FIELDS:
             off = getattr(info, off_attr)

@@ -156,7 +156,27 @@ def neighbor_sum(x, topo, transposed=False, addend=None):
     return gather_sum(x, topo.row_ptr, topo.col_idx, n, addend=addend)
 
 
+def _permute_rows_i8(src, perm, n_feat=None, ld_out=None, out=None):
+    """int8 feature rows -> degree-major fp32 rows (exact), pad columns zeroed."""
+    if not src.is_cuda:
+        raise RuntimeError("src must be a CUDA tensor: the deepchem_b200 ops have no CPU path")
+    if src.dim() != 2 or src.stride(1) != 1:
+        src = src.contiguous()
+    n_feat = src.shape[1] if n_feat is None else n_feat
+    n = perm.shape[0]
+    ld_out = ld_out or (n_feat + 3) // 4 * 4
+    if out is None:
+        out = torch.empty(n, ld_out, device=src.device, dtype=torch.float32)
+    else:
+        out = out[:n * ld_out].view(n, ld_out)
+    check(_lib.lib().dcgc_permute_rows_i8(_p(src), src.stride(0), _p(perm), n, n_feat, _p(out), ld_out, _stream()))
+    _count()
+    return out[:, :n_feat]
+
+
 def permute_rows(src, perm, n_feat=None, ld_out=None, out=None):
+    if src.dtype == torch.int8:
+        return _permute_rows_i8(src, perm, n_feat, ld_out, out)
     src = _rowmajor(src)
     n_feat = src.shape[1] if n_feat is None else n_feat
     n = perm.shape[0]

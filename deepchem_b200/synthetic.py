@@ -23,9 +23,12 @@ class PackedMols(object):
     adj_ptr  [N+1] int32   CSR over atoms (concatenated, in each molecule's own order)
     adj_idx  [E]   int32   neighbour ids, molecule-local, in adjacency-list order
     features [N,F] float32
+    features_i8 [N,F] int8 or None: the same matrix when every entry is an integer in [-128, 127] (``compact()``;
+             true of every ConvMol feature: one-hots, formal charge, radical electrons) — a quarter of the bytes to
+             store and to upload, converted back to fp32 exactly on the device
     """
 
-    __slots__ = ("atom_ptr", "adj_ptr", "adj_idx", "features", "_pin")
+    __slots__ = ("atom_ptr", "adj_ptr", "adj_idx", "features", "_pin", "features_i8", "_pin_i8")
 
     def __init__(self, atom_ptr, adj_ptr, adj_idx, features):
         self.atom_ptr = np.ascontiguousarray(atom_ptr, dtype=np.int32)
@@ -33,6 +36,8 @@ class PackedMols(object):
         self.adj_idx = np.ascontiguousarray(adj_idx, dtype=np.int32)
         self.features = np.ascontiguousarray(features, dtype=np.float32)
         self._pin = None
+        self.features_i8 = None
+        self._pin_i8 = None
 
     @property
     def n_mols(self):
@@ -73,18 +78,53 @@ class PackedMols(object):
         out.features = self.features[a0:a1]
         pin = getattr(self, "_pin", None)
         out._pin = pin[a0:a1] if pin is not None else None     # torch view of the same pinned rows
+        f8, p8 = getattr(self, "features_i8", None), getattr(self, "_pin_i8", None)
+        out.features_i8 = f8[a0:a1] if f8 is not None else None
+        out._pin_i8 = p8[a0:a1] if p8 is not None else None
         return out
 
-    def pin_memory(self):
+    def compact(self):
+        """Add the int8 copy of the feature matrix when it is exact (one pass over the shard, done once when the
+        dataset is packed).  Returns True when the shard is compact."""
+        if getattr(self, "features_i8", None) is not None:
+            return True
+        f = self.features
+        if f.size == 0:
+            return False
+        ok = True
+        step = 1 << 16                                        # row blocks: no shard-sized temporaries
+        out = np.empty(f.shape, dtype=np.int8)
+        for r in range(0, f.shape[0], step):
+            blk = f[r:r + step]
+            if not np.isfinite(blk).all():
+                ok = False
+                break
+            q = np.clip(blk, -128, 127).astype(np.int8)
+            if not np.array_equal(q.astype(np.float32), blk):
+                ok = False
+                break
+            out[r:r + step] = q
+        if not ok:
+            return False
+        self.features_i8 = out
+        self._pin_i8 = None
+        return True
+
+    def pin_memory(self, compact=True):
         """Move the feature matrix into page-locked host memory (needs torch + CUDA) so that H2D
-        copies of batches are asynchronous DMA with no staging copy."""
+        copies of batches are asynchronous DMA with no staging copy.  ``compact``: also keep the exact int8
+        copy (see ``compact()``) pinned; batches then upload a quarter of the bytes."""
         import torch
-        if getattr(self, "_pin", None) is not None:
-            return self
-        t = torch.empty(self.features.shape, dtype=torch.float32, pin_memory=True)
-        t.numpy()[...] = self.features
-        self.features = t.numpy()
-        self._pin = t
+        if getattr(self, "_pin", None) is None:
+            t = torch.empty(self.features.shape, dtype=torch.float32, pin_memory=True)
+            t.numpy()[...] = self.features
+            self.features = t.numpy()
+            self._pin = t
+        if compact and self.compact() and getattr(self, "_pin_i8", None) is None:
+            t8 = torch.empty(self.features_i8.shape, dtype=torch.int8, pin_memory=True)
+            t8.numpy()[...] = self.features_i8
+            self.features_i8 = t8.numpy()
+            self._pin_i8 = t8
         return self
 
     def take(self, idx):
@@ -111,6 +151,8 @@ class PackedMols(object):
         os.makedirs(path, exist_ok=True)
         for name in self._FILES:
             np.save(os.path.join(path, name + ".npy"), getattr(self, name))
+        if getattr(self, "features_i8", None) is not None:
+            np.save(os.path.join(path, "features_i8.npy"), self.features_i8)
         return path
 
     @staticmethod
@@ -120,6 +162,12 @@ class PackedMols(object):
                 for name in PackedMols._FILES]
         out = PackedMols.__new__(PackedMols)
         out.atom_ptr, out.adj_ptr, out.adj_idx, out.features = arrs
+        out.features_i8 = out._pin_i8 = None
+        p8 = os.path.join(path, "features_i8.npy")
+        if os.path.exists(p8):
+            out.features_i8 = np.load(p8, mmap_mode="r" if mmap else None)
+            if out.features_i8.dtype != np.int8 or out.features_i8.shape != out.features.shape:
+                raise ValueError("not a PackedMols shard: %s" % path)
         if not (out.atom_ptr.dtype == np.int32 and out.adj_ptr.dtype == np.int32 and out.adj_idx.dtype == np.int32
                 and out.features.dtype == np.float32 and out.features.ndim == 2):
             raise ValueError("not a PackedMols shard: %s" % path)

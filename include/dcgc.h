@@ -133,10 +133,22 @@ int dcgc_layout_build_from_deg(const int64_t* deg_slice, const int32_t* membersh
  * Device kernels.  fp32 activations, row-major, leading dimensions in floats.
  * ------------------------------------------------------------------------------------------ */
 
+/* Host -> device upload of `bytes` bytes from PINNED host memory as a train of cudaMemcpyAsync calls of at most
+ * `chunk_bytes` each on `stream` (chunk_bytes <= 0: one copy).  Replaces the per-array `torch.as_tensor(x, device)`
+ * uploads of TorchModel._prepare_batch (torch_models/torch_model.py:923-952).  One 30 MB copy running beside the
+ * training kernels slows them measurably on B200; moderate chunks do not (profiles/r2_interference.md). */
+int dcgc_h2d_chunked(void* dst_dev, const void* src_host_pinned, int64_t bytes, int64_t chunk_bytes, void* stream);
+
 /* dst[i, 0:n_feat] = src[perm[i], 0:n_feat], pad columns zeroed (device-side feature permute,
  * replaces `atoms_by_deg[order]`, mol_graphs.py:277). */
 int dcgc_permute_rows(const float* src_dev, int64_t ld_src, const int32_t* perm_dev, int64_t n_rows,
                       int32_t n_feat, float* dst_dev, int64_t ld_dst, void* stream);
+
+/* Same from an int8 feature matrix (exact conversion to fp32; dst rows 16-byte aligned, ld_dst % 4 == 0): the packed
+ * shard format stores integer-valued feature matrices (every ConvMol feature of deepchem/feat/graph_features.py:
+ * 282-391 is a one-hot, a formal charge or a radical count) as int8, a quarter of the upload. */
+int dcgc_permute_rows_i8(const int8_t* src_dev, int64_t ld_src, const int32_t* perm_dev, int64_t n_rows,
+                         int32_t n_feat, float* dst_dev, int64_t ld_dst, void* stream);
 
 /* K1 / K5 / K8 — CSR gather-sum: out[i,:] = sum_{e in [row_ptr[i], row_ptr[i+1])} x[idx[e], :].
  * Forward of GraphConv.sum_neigh (torch_models/layers.py:6236-6246) with (row_ptr, col_idx);
@@ -391,6 +403,11 @@ int dcgc_gcmodel_forward(const dcgc_gcmodel_config* cfg, const dcgc_topology* to
                          int64_t ld_x, int64_t n_samples, const float* params_dev, float* bn_running_dev,
                          int32_t training, void* workspace_dev, int64_t workspace_bytes, float* out_dev,
                          float* probs_dev, float* fingerprint_dev, void* stream);
+/* Arms a one-shot hook for the calling thread: the next dcgc_gcmodel_train_step of this thread records `event`
+ * (a cudaEvent_t, or NULL to disarm) on its stream between the forward and the backward pass.  The host pipeline
+ * uses it to start the upload of a later batch while the GEMM-heavy backward runs instead of beside the
+ * HBM-bound forward kernels (profiles/r2_interference.md). */
+int dcgc_gcmodel_set_forward_event(void* event);
 /* One training forward + loss + backward.  y: [n_samples, n_tasks] (regression) or one-hot
  * [n_samples, n_tasks, n_classes]; w: [n_samples, n_tasks] (may be NULL = ones).  loss_dev receives
  * the scalar loss (mean over n_samples * n_tasks elements); every gradient is written (not

@@ -161,3 +161,43 @@ def test_state_dict_survives_flat_slab():
     m2.model.to("cuda:0")
     m2._engine.adopt()
     assert m2._engine.aliased()
+
+
+def test_int8_feature_upload_is_exact_and_fit_is_unchanged():
+    """The compact int8 copy of an integer-valued feature matrix (PackedMols.compact) converts back to exactly the
+    fp32 rows on the device, so a fit through the prefetch pipeline gives bit-identical losses either way."""
+    import itertools
+    from deepchem_b200 import graphconvmodel as G
+    from deepchem_b200 import mol_graphs as MG
+    from deepchem_b200 import ops
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.synthetic import make_labels, make_molecules
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    dev = torch.device("cuda", 0)
+    pm = make_molecules(256, seed=11, shape="stress")
+    pm.features[5, 40] = -1.0
+    assert pm.compact()
+    lay = MG.BatchLayout.build(pm, n_segments=256)
+    topo = lay.to_device(dev)
+    a = ops.permute_rows(torch.from_numpy(pm.features).to(dev), topo.perm)
+    b = ops.permute_rows(torch.from_numpy(pm.features_i8).to(dev), topo.perm)
+    assert a.shape == b.shape and torch.equal(a, b)
+    assert torch.equal(a.cpu(), torch.from_numpy(pm.features[lay.perm]))
+    pm.pin_memory()
+    y, w = make_labels(256, 2, "regression", seed=3)
+    ds = PackedDataset(pm, y, w)
+    runs = []
+    for use_i8 in (True, False):
+        G._USE_I8 = use_i8
+        try:
+            torch.manual_seed(0)
+            m = G.GraphConvModel(2, [64, 64], 128, mode="regression", batch_size=64, device=dev)
+            m.log_frequency = 1
+            losses = []
+            m.fit_generator(itertools.islice(m.default_generator(ds, epochs=3, deterministic=True), 10),
+                            checkpoint_interval=0, all_losses=losses)
+            runs.append(losses)
+        finally:
+            G._USE_I8 = True
+    assert len(runs[0]) == 10 and runs[0] == runs[1]

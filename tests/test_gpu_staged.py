@@ -18,11 +18,22 @@ def _cuda():
     return torch.device("cuda", 0)
 
 
-def _topo(shape, n, seed, segs=None):
+def _topo(shape, n, seed, segs=None, group_rows=None):
+    import os
     from deepchem_b200 import mol_graphs as MG
     from deepchem_b200.synthetic import make_molecules
     pm = make_molecules(n, seed=seed, shape=shape)
-    lay = MG.BatchLayout.build(pm, n_segments=segs or n)
+    old = os.environ.get("DCGC_GROUP_ROWS")
+    if group_rows:                      # wide rows: fewer rows per group so that two stages fit in shared memory
+        os.environ["DCGC_GROUP_ROWS"] = str(group_rows)
+    try:
+        lay = MG.BatchLayout.build(pm, n_segments=segs or n)
+    finally:
+        if group_rows:
+            if old is None:
+                os.environ.pop("DCGC_GROUP_ROWS", None)
+            else:
+                os.environ["DCGC_GROUP_ROWS"] = old
     return pm, lay, lay.to_device(_cuda())
 
 
@@ -33,7 +44,7 @@ CASES = [("zinc", 700, 1, 128), ("stress", 300, 2, 128), ("stress", 300, 3, 76),
 @pytest.mark.parametrize("shape,n,seed,width", CASES)
 def test_staged_gather_sum_is_bit_identical(shape, n, seed, width):
     from deepchem_b200 import ops
-    pm, lay, topo = _topo(shape, n, seed, segs=n + 3)
+    pm, lay, topo = _topo(shape, n, seed, segs=n + 3, group_rows=48 if width > 256 else None)
     assert topo.n_groups > 0 and ops.mg_supported(topo, width)
     g = torch.Generator(device="cpu").manual_seed(seed)
     x = torch.randn(topo.n_atoms, width, generator=g).cuda()

@@ -71,3 +71,24 @@ def test_packed_shard_round_trips_through_disk(tmp_path):
             assert np.array_equal(getattr(ia.layout, f), getattr(ib.layout, f)), f
         assert np.array_equal(ia.packed_features, ib.packed_features)
     assert np.array_equal(BatchLayout.build(back.packed).col_idx, BatchLayout.build(pm).col_idx)
+
+
+def test_compact_int8_features_are_exact_or_refused(tmp_path):
+    """PackedMols.compact(): the int8 copy exists only when it reproduces the fp32 matrix exactly (every ConvMol
+    feature is a one-hot, a formal charge or a radical count: graph_features.py:282-391); slices are views of it
+    and it round-trips through the on-disk shard."""
+    from deepchem_b200.synthetic import PackedMols
+    pm = make_molecules(200, seed=7, shape="stress")
+    pm.features[3, 10] = -1.0                                  # a formal charge
+    assert pm.compact() and pm.features_i8.dtype == np.int8
+    assert np.array_equal(pm.features_i8.astype(np.float32), pm.features)
+    part = pm.slice(17, 90)
+    assert np.array_equal(part.features_i8.astype(np.float32), part.features)
+    assert part.features_i8.base is not None                   # a view, not a copy
+    pm.save(str(tmp_path / "s"))
+    back = PackedMols.load(str(tmp_path / "s"))
+    assert np.array_equal(back.features_i8, pm.features_i8)
+    for bad in (0.5, 200.0, -129.0, float("nan")):
+        q = make_molecules(50, seed=8)
+        q.features[5, 5] = bad
+        assert not q.compact() and q.features_i8 is None
