@@ -100,6 +100,8 @@ _SIGNATURES = {
     "dcgc_mg_gather_sum": (c_int32, [_P, c_int64, _P, c_int32, c_int32, _P, c_int64, _P, c_int64, _P]),
     "dcgc_mg_pool_fwd": (c_int32, [_P, c_int64, _P, _P, _P, c_int32, _P, c_int64, _P, c_int64, _P]),
     "dcgc_mg_pool_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, c_int32, _P, c_int64, _P]),
+    "dcgc_mg_pool_bwd_stats": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int32, _P, c_int64, _P, c_int64, _P, _P,
+                                         POINTER(c_int32), _P]),
     "dcgc_pool_fwd": (c_int32, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, c_int64, _P, c_int64, _P]),
     "dcgc_pool_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, _P, _P, c_int64, c_int32, _P, c_int64, _P]),
     "dcgc_gather_fwd": (c_int32, [_P, c_int64, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int64, _P, _P]),

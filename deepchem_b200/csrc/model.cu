@@ -809,19 +809,21 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
   // ---- GraphGather backward -> dA (grad wrt the BN output of the dense layer)
   RET_IF(dcgc_gather_bwd(dfp, 2 * D, sv.fp, 2 * D, sv.argrow, t->membership, N, D, DCGC_ACT_TANH, dA, D, st));
 
-  auto bn_backward = [&](int idx, const float* yv, int width) -> int {
+  // fused_chunks >= 0: the stage-1 partials were already written by the kernel that produced dA
+  // (dcgc_mg_pool_bwd_stats), one row per CTA
+  auto bn_backward = [&](int idx, const float* yv, int width, int fused_chunks) -> int {
     // dA (ld = width) -> G in place; dgamma / dbeta into the gradient slab
     if (cfg->batch_norm) {
       const float* stats = sv.stats + sv.stats_off[idx];
       {
       DcgcProfScope prof_scope("bn_stats_bwd", st);
-      if (N > 0) {
+      if (N > 0 && fused_chunks < 0) {
         dim3 grid((unsigned)sv.n_chunks, (unsigned)((width + 127) / 128));
         col_moments_partial<<<grid, 32 * kMomLanes, 0, st>>>(dA, width, yv, width, N, width,
                                                              mom_rows(N, sv.n_chunks), sv.part);
         DCGC_CUDA_LAUNCH_CHECK("col_moments_partial (bwd)");
       }
-      bn_bwd_finalize<<<(width + 15) / 16, 512, 0, st>>>(sv.part, N > 0 ? sv.n_chunks : 0, width, N, stats,
+      bn_bwd_finalize<<<(width + 15) / 16, 512, 0, st>>>(sv.part, fused_chunks >= 0 ? fused_chunks : (N > 0 ? sv.n_chunks : 0), width, N, stats,
                                                            stats + width, stats + 2 * width, grads + lo.bn_g[idx],
                                                            grads + lo.bn_b[idx], coef);
       DCGC_CUDA_LAUNCH_CHECK("bn_bwd_finalize");
@@ -843,7 +845,7 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
   };
 
   // ---- dense layer backward
-  RET_IF(bn_backward(L, sv.z, D));
+  RET_IF(bn_backward(L, sv.z, D, -1));
   RET_IF(dcgc_linear_wgrad(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], dA, D, D, N, grads + lo.dense_w,
                            grads + lo.dense_b, wg, wg_bytes, st));
   RET_IF(dcgc_linear_dgrad(cfg->gemm_mode, dA, D, D, params + lo.dense_w, lo.f[L], N, dP, lo.f[L], st));
@@ -852,11 +854,19 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
   for (int l = L - 1; l >= 0; --l) {
     const int c = cfg->widths[l], fp = lo.fp[l];
     // GraphPool backward over CSR^T: dP (ld c) -> dA (ld c)
-    if (use_mg(t, c, c, dP, sv.arg[l]) && (reinterpret_cast<uintptr_t>(dA) & 15) == 0)
-      RET_IF(dcgc_mg_pool_bwd(dP, c, sv.arg[l], c, nullptr, t, c, dA, c, st));
-    else
+    int32_t fused = -1;
+    if (use_mg(t, c, c, dP, sv.arg[l]) && (reinterpret_cast<uintptr_t>(dA) & 15) == 0) {
+      // the BatchNorm-backward column sums of dA come out of the same kernel (DCGC_NO_FUSED_BN_BWD=1: separate pass)
+      static const bool no_fuse = [] { const char* e = getenv("DCGC_NO_FUSED_BN_BWD"); return e && e[0] == '1'; }();
+      if (cfg->batch_norm && !no_fuse && c % 4 == 0 && (reinterpret_cast<uintptr_t>(sv.y[l]) & 15) == 0)
+        RET_IF(dcgc_mg_pool_bwd_stats(dP, c, sv.arg[l], c, t, c, dA, c, sv.y[l], c, sv.stats + sv.stats_off[l], sv.part,
+                                      &fused, st));
+      else
+        RET_IF(dcgc_mg_pool_bwd(dP, c, sv.arg[l], c, nullptr, t, c, dA, c, st));
+    } else {
       RET_IF(dcgc_pool_bwd(dP, c, sv.arg[l], c, nullptr, t->t_row_ptr, t->t_src, t->t_slot, N, c, dA, c, st));
-    RET_IF(bn_backward(l, sv.y[l], c));
+    }
+    RET_IF(bn_backward(l, sv.y[l], c, fused));
     RET_IF(dcgc_group_gemm_wgrad(cfg->gemm_mode, sv.h[l], sv.ld_h[l], fp, sv.s[l], fp, fp, dA, c, c, t->deg_count,
                                  DCGC_N_DEG, grads + lo.conv_w[l], db11, wg, wg_bytes, st));
     conv_bias_unpack<<<blocks_for(21 * c), kT, 0, st>>>(db11, c, grads + lo.conv_b[l]);

@@ -293,9 +293,11 @@ struct GatherSumOp {
       s.acc.x += q.x; s.acc.y += q.y; s.acc.z += q.z; s.acc.w += q.w;
     }
   }
-  __device__ __forceinline__ void fin(const St& s, const MgItem& m, int) const {
+  __device__ __forceinline__ void pre(St&, const MgItem&, bool) const {}
+  __device__ __forceinline__ void fin(const St& s, const MgItem& m, int) {
     *reinterpret_cast<float4*>(out + (int64_t)m.row * ld_out) = s.acc;
   }
+  __device__ __forceinline__ void finish(char*, int, int, int) const {}
 };
 
 // GraphPool forward with the folded BatchNorm affine; first slot attaining the max wins (strict >)
@@ -331,22 +333,38 @@ struct PoolFwdOp {
       if (u.w > s.m.w) { s.m.w = u.w; s.a = (s.a & 0x00ffffffu) | (c << 24); }
     }
   }
-  __device__ __forceinline__ void fin(const St& s, const MgItem& m, int) const {
+  __device__ __forceinline__ void pre(St&, const MgItem&, bool) const {}
+  __device__ __forceinline__ void fin(const St& s, const MgItem& m, int) {
     *reinterpret_cast<float4*>(out + (int64_t)m.row * ld_out) = s.m;
     if (ARG) *reinterpret_cast<uint32_t*>(arg + (int64_t)m.row * ld_arg) = s.a;
   }
+  __device__ __forceinline__ void finish(char*, int, int, int) const {}
 };
 
-// GraphPool backward over the transposed lists of a symmetric adjacency (dy rows and arg rows staged)
-template <bool AFFINE>
+// GraphPool backward over the transposed lists of a symmetric adjacency (dy rows and arg rows staged).
+// STATS: the kernel also produces the per-column sums the BatchNorm backward needs from the rows it writes,
+//   sum_r dx[r,c]   and   sum_r dx[r,c] * y[r,c]      (y = the BatchNorm INPUT of the layer, read once, coalesced),
+// instead of a separate pass over dx and y (col_moments_partial: 38 us per layer in situ).  The column group of a
+// thread is fixed, so the sums live in 8 registers: fp32 over the ~N / (148 * 16) rows of the thread, centred on the
+// batch mean (sum dx * (y - mean): no cancellation later), float64 from the cross-thread reduction on; one
+// [2][width] row of partials per CTA, reduced by bn_bwd_finalize in CTA order (deterministic).
+template <bool AFFINE, bool STATS>
 struct PoolBwdOp {
   float4 sc;                                                         // this thread's column group
   float* dx; int ld_dx;                                              // already offset by the column group
-  struct St { float4 acc; uint32_t t0, t1; };                        // t0, t1: slots of this row in its neighbours' lists
+  struct St { float4 acc; uint32_t t0, t1; float4 yv; };             // t0, t1: slots of this row in its neighbours' lists
   const float* scale;
+  const float* y; int ld_y; const float* mean; double* part; int width;   // STATS only
+  float4 mu, sa, sc2;                                                // column means, sum dx, sum dx * (y - mean)
   __device__ __forceinline__ void bind(int cg) {
     if (AFFINE) sc = __ldg(reinterpret_cast<const float4*>(scale) + cg);
     dx += 4 * cg;
+    if (STATS) {
+      y += 4 * cg;
+      mu = __ldg(reinterpret_cast<const float4*>(mean) + cg);
+      sa = make_float4(0.f, 0.f, 0.f, 0.f);
+      sc2 = sa;
+    }
   }
   static __device__ __forceinline__ float4 pick(const float4 q, uint32_t b, uint32_t c) {
     float4 r;
@@ -366,10 +384,44 @@ struct PoolBwdOp {
       s.acc.x += r.x; s.acc.y += r.y; s.acc.z += r.z; s.acc.w += r.w;
     }
   }
-  __device__ __forceinline__ void fin(const St& s, const MgItem& m, int) const {
+  // all y loads of the items in flight are issued before the first one is used
+  __device__ __forceinline__ void pre(St& s, const MgItem& m, bool valid) const {
+    if (STATS) s.yv = valid ? __ldg(reinterpret_cast<const float4*>(y + (int64_t)m.row * ld_y)) : mu;
+  }
+  __device__ __forceinline__ void fin(const St& s, const MgItem& m, int) {
     float4 acc = s.acc;
     if (AFFINE) { acc.x *= sc.x; acc.y *= sc.y; acc.z *= sc.z; acc.w *= sc.w; }
     *reinterpret_cast<float4*>(dx + (int64_t)m.row * ld_dx) = acc;
+    if (STATS) {
+      sa.x += acc.x; sa.y += acc.y; sa.z += acc.z; sa.w += acc.w;
+      sc2.x = fmaf(acc.x, s.yv.x - mu.x, sc2.x); sc2.y = fmaf(acc.y, s.yv.y - mu.y, sc2.y);
+      sc2.z = fmaf(acc.z, s.yv.z - mu.z, sc2.z); sc2.w = fmaf(acc.w, s.yv.w - mu.w, sc2.w);
+    }
+  }
+  // CTA-level reduction (consumer threads only; the producers have left): thread (cg, row lane) -> shared memory,
+  // then one thread per (quantity, column) adds the row lanes in lane order in float64 and writes this CTA's row of
+  // partials: part[cta][0][c] = sum dx, part[cta][1][c] = sum dx * y  ( = centred sum + mean * sum dx ).
+  __device__ __forceinline__ void finish(char* scratch, int ct, int cgroups, int used) const {
+    if (!STATS) return;
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");      // every consumer is done with the stages
+    float* sh = reinterpret_cast<float*>(scratch);                     // [row lane][2][width]
+    const int cg = ct % cgroups, lane_r = ct / cgroups;
+    if (ct < used) {
+      float* q = sh + (size_t)lane_r * 2 * width + 4 * cg;
+      *reinterpret_cast<float4*>(q) = sa;
+      *reinterpret_cast<float4*>(q + width) = sc2;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+    const int lanes = used / cgroups;
+    for (int c = ct; c < width; c += kConsumers) {
+      double a = 0.0, b = 0.0;
+      for (int l = 0; l < lanes; ++l) {
+        a += (double)sh[(size_t)l * 2 * width + c];
+        b += (double)sh[(size_t)l * 2 * width + width + c];
+      }
+      part[((int64_t)blockIdx.x * 2) * width + c] = a;
+      part[((int64_t)blockIdx.x * 2 + 1) * width + c] = b + (double)__ldg(mean + c) * a;
+    }
   }
 };
 
@@ -458,6 +510,8 @@ mg_kernel(const MgGeom geo, const int32_t* __restrict__ groups, int n_groups, co
         }
       }
 #pragma unroll
+      for (int u = 0; u < kItems; ++u) op.pre(st[u], m[u], valid[u]);
+#pragma unroll
       for (int u = 0; u < kItems; ++u)
         if (valid[u] && (dbg_mode != 1 || m[u].d == 77)) op.fin(st[u], m[u], cg);
     }
@@ -467,6 +521,7 @@ mg_kernel(const MgGeom geo, const int32_t* __restrict__ groups, int n_groups, co
     stage += geo.stage_bytes;
     if (++s == S) { s = 0; phase ^= 1u; stage = smem0 + kHeaderBytes; }
   }
+  op.finish(smem + kHeaderBytes, ct, cgroups, used);
 }
 
 long long* g_mg_timeline = nullptr;   // debugging aid, see dcgcdbg_mg_timeline
@@ -606,11 +661,38 @@ extern "C" int dcgc_mg_pool_bwd(const float* dy, int64_t ld_dy, const uint8_t* a
   const MgGeom geo = mg_geom(t->group_max_rows, kRecB, (int)ld_dy * 4, (int)ld_arg);
   const int cg = width / 4;
   if (scale) {
-    PoolBwdOp<true> op;
-    op.scale = scale; op.dx = dx; op.ld_dx = (int)ld_dx; op.sc = make_float4(0.f, 0.f, 0.f, 0.f);
+    PoolBwdOp<true, false> op{};
+    op.scale = scale; op.dx = dx; op.ld_dx = (int)ld_dx;
     return mg_launch(t, geo, mg_rec(t, 1), dy, arg, cg, op, st, "dcgc_mg_pool_bwd");
   }
-  PoolBwdOp<false> op;
-  op.scale = nullptr; op.dx = dx; op.ld_dx = (int)ld_dx; op.sc = make_float4(0.f, 0.f, 0.f, 0.f);
+  PoolBwdOp<false, false> op{};
+  op.dx = dx; op.ld_dx = (int)ld_dx;
   return mg_launch(t, geo, mg_rec(t, 1), dy, arg, cg, op, st, "dcgc_mg_pool_bwd");
+}
+
+extern "C" int dcgc_mg_pool_bwd_stats(const float* dy, int64_t ld_dy, const uint8_t* arg, int64_t ld_arg,
+                                      const dcgc_topology* t, int32_t width, float* dx, int64_t ld_dx, const float* y,
+                                      int64_t ld_y, const float* mean, double* part, int32_t* n_chunks, void* stream) {
+  DCGC_CHECK_ARG(t && width > 0 && ld_dy >= width && ld_dx >= width && ld_arg >= width && ld_y >= width,
+                 "dcgc_mg_pool_bwd_stats: bad sizes");
+  DCGC_CHECK_ARG(n_chunks, "dcgc_mg_pool_bwd_stats: null n_chunks");
+  *n_chunks = 0;
+  if (t->n_atoms == 0) return DCGC_OK;
+  DCGC_CHECK_ARG(dy && arg && dx && y && mean && part, "dcgc_mg_pool_bwd_stats: null pointer");
+  DCGC_CHECK_ARG(t->symmetric, "dcgc_mg_pool_bwd_stats: the transposed lists are bucketed only for a symmetric adjacency");
+  DCGC_CHECK_ARG(dcgc_mg_supported(t, ld_dy, ld_arg) && width % 4 == 0 && ld_dx % 4 == 0 && ld_y % 4 == 0 && al16(dy) &&
+                     al16(dx) && al16(arg) && al16(y) && al16(mean),
+                 "dcgc_mg_pool_bwd_stats: layout not supported by the staged kernel (see dcgc_mg_supported)");
+  cudaStream_t st = (cudaStream_t)stream;
+  DcgcProfScope prof_scope("dcgc_pool_bwd", st);
+  const MgGeom geo = mg_geom(t->group_max_rows, kRecB, (int)ld_dy * 4, (int)ld_arg);
+  // the CTA-level reduction reuses the stage area: [row lanes][2][width] floats
+  DCGC_CHECK_ARG((int64_t)(kConsumers / (width / 4)) * 2 * width * 4 <= (int64_t)geo.n_stages * geo.stage_bytes,
+                 "dcgc_mg_pool_bwd_stats: stage area too small for the reduction");
+  PoolBwdOp<false, true> op{};
+  op.dx = dx; op.ld_dx = (int)ld_dx;
+  op.y = y; op.ld_y = (int)ld_y; op.mean = mean; op.part = part; op.width = width;
+  const int sms = dcgc_tc_num_sms();
+  *n_chunks = t->n_groups < sms ? t->n_groups : sms;     // = the grid of mg_launch: one row of partials per CTA
+  return mg_launch(t, geo, mg_rec(t, 1), dy, arg, width / 4, op, st, "dcgc_mg_pool_bwd_stats");
 }

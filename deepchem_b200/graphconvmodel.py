@@ -408,12 +408,12 @@ class GraphConvModel(object):
         self._loss_ring = [torch.zeros((), dtype=torch.float32).pin_memory() if self.device.type == "cuda"
                            else torch.zeros(()) for _ in range(4)]
         self._device_slots = []     # reusable per-batch device buffers of the prefetch pipeline
-        # upload phase (DCGC_H2D_PHASE=bwd, default): the prefetch stream starts a batch's uploads only after the
-        # forward pass of the newest launched step — beside the GEMM-heavy backward instead of the HBM-bound forward
-        # kernels, which one concurrent 35 MB upload slowed by 30-60 % (profiles/r2_interference.md)
+        # upload phase (DCGC_H2D_PHASE=bwd, off by default): the prefetch stream starts a batch's uploads only after
+        # the forward pass of the newest launched step.  Measured on B200 (profiles/r2_interference.md): no gain over
+        # the chunked int8 upload, so it stays an experiment switch.
         self._fwd_events = None
         self._last_fwd_event = None
-        if self.device.type == "cuda" and os.environ.get("DCGC_H2D_PHASE", "bwd") == "bwd":
+        if self.device.type == "cuda" and os.environ.get("DCGC_H2D_PHASE", "none") == "bwd":
             self._fwd_events = []
             with torch.cuda.device(self.device):
                 for _ in range(8):

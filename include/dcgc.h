@@ -389,6 +389,15 @@ int dcgc_mg_pool_bwd(const float* dy_dev, int64_t ld_dy, const uint8_t* arg_dev,
                      const float* scale_dev, const dcgc_topology* topo, int32_t width, float* dx_dev,
                      int64_t ld_dx, void* stream);
 
+/* dcgc_mg_pool_bwd that also emits the stage-1 column sums of the BatchNorm backward over the rows it writes:
+ * part[cta][0][c] = sum_r dx[r,c], part[cta][1][c] = sum_r dx[r,c] * y[r,c] (float64, *n_chunks rows = the kernel's
+ * grid, <= number of SMs), y = the BatchNorm input of the layer, mean = its batch column means (the products are
+ * accumulated centred on them).  Replaces a separate pass over dx and y (Keras BatchNormalization backward inside
+ * GraphConvModel, graph_models.py:862-902). */
+int dcgc_mg_pool_bwd_stats(const float* dy_dev, int64_t ld_dy, const uint8_t* arg_dev, int64_t ld_arg,
+                           const dcgc_topology* topo, int32_t width, float* dx_dev, int64_t ld_dx, const float* y_dev,
+                           int64_t ld_y, const float* mean_dev, double* part_dev, int32_t* n_chunks, void* stream);
+
 /* param_offsets: 4 per conv layer (W, b, gamma, beta), then dense (W, b, gamma, beta), then head
  * (W, b); -1 where batch_norm is off.  bn_offsets: (mean, var) per BN, conv layers then dense. */
 int dcgc_gcmodel_layout(const dcgc_gcmodel_config* cfg, int64_t* param_offsets, int64_t* bn_offsets,

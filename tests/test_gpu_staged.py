@@ -127,7 +127,7 @@ def test_staged_kernels_refuse_what_they_cannot_do():
 
 def test_engine_step_is_identical_with_and_without_staging():
     """The fused engine with the staged kernels (default) and with DCGC_NO_STAGED=1 semantics (a topology whose
-    group table is hidden) produces bit-identical losses, outputs and gradients."""
+    group table is hidden) produces bit-identical losses and outputs, and the same gradients."""
     from deepchem_b200 import mol_graphs as MG
     from deepchem_b200.graphconvmodel import GraphConvModel
     from deepchem_b200.synthetic import make_molecules, make_labels
@@ -148,5 +148,52 @@ def test_engine_step_is_identical_with_and_without_staging():
         x[:, :75] = torch.from_numpy(pm.features).to(dev)[topo.perm.long()]
         loss = eng.train_step(topo, x, torch.from_numpy(y).to(dev), torch.from_numpy(w).to(dev), 256)
         res.append((float(loss), eng.grads.clone()))
+    # the forward pass is bit-identical; in the backward pass the staged pool kernel also produces the BatchNorm
+    # column sums (dcgc_mg_pool_bwd_stats), whose float summation order differs from the separate statistics pass
     assert res[0][0] == res[1][0]
-    assert torch.equal(res[0][1], res[1][1])
+    scale = float(res[1][1].abs().max())
+    assert float((res[0][1] - res[1][1]).abs().max()) < 2e-6 * scale
+
+
+@pytest.mark.parametrize("shape,n,seed,width", [("zinc", 700, 1, 128), ("stress", 300, 2, 128), ("delaney", 64, 4, 64),
+                                                ("zinc", 3, 5, 32), ("zinc", 4096, 6, 128)])
+def test_staged_pool_bwd_with_fused_batchnorm_sums(shape, n, seed, width):
+    """dcgc_mg_pool_bwd_stats: dx bit-identical to dcgc_mg_pool_bwd, and the per-CTA partials add up to the float64
+    column sums of dx and dx * y (the stage-1 input of bn_bwd_finalize)."""
+    from deepchem_b200 import _lib
+    from deepchem_b200.engine import topology_struct
+    pm, lay, topo = _topo(shape, n, seed)
+    L = _lib.lib()
+    N = topo.n_atoms
+    g = torch.Generator(device="cpu").manual_seed(300 + seed)
+    x = (torch.randn(N, width, generator=g) * 2).round().div(2).cuda()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    out = torch.empty_like(x)
+    arg = torch.empty(N, width, dtype=torch.uint8, device="cuda")
+    ts = ctypes.byref(topology_struct(topo))
+    _lib.check(L.dcgc_mg_pool_fwd(p(x), width, None, None, ts, width, p(out), width, p(arg), width, st))
+    dy = torch.randn(N, width, generator=g).cuda()
+    y = (torch.randn(N, width, generator=g) * 3 + 5).cuda()          # a mean far from zero: centring matters
+    mean = y.double().mean(0).float().contiguous()
+    dx_r, dx_s = torch.empty_like(x), torch.empty_like(x)
+    _lib.check(L.dcgc_mg_pool_bwd(p(dy), width, p(arg), width, None, ts, width, p(dx_r), width, st))
+    part = torch.full((256, 2, width), float("nan"), dtype=torch.float64, device="cuda")
+    chunks = ctypes.c_int32(-1)
+    _lib.check(L.dcgc_mg_pool_bwd_stats(p(dy), width, p(arg), width, ts, width, p(dx_s), width, p(y), width, p(mean),
+                                        p(part), ctypes.byref(chunks), st))
+    torch.cuda.synchronize()
+    assert torch.equal(dx_s, dx_r)
+    k = chunks.value
+    assert k == min(topo.n_groups, torch.cuda.get_device_properties(0).multi_processor_count)
+    assert not torch.isnan(part[:k]).any() and torch.isnan(part[k:]).all()
+    got = part[:k].sum(0).cpu().numpy()
+    want_a = dx_r.double().sum(0).cpu().numpy()
+    want_ab = (dx_r.double() * y.double()).sum(0).cpu().numpy()
+    centred = (dx_r.double() * (y.double() - mean.double())).sum(0).cpu().numpy()
+    tol_a = 2e-6 * float(dx_r.abs().double().sum(0).max())
+    assert np.abs(got[0] - want_a).max() < tol_a
+    # the centred part carries the rounding error; the mean * sum part is exact in float64
+    tol_c = 2e-6 * float((dx_r.double() * (y.double() - mean.double())).abs().sum(0).max())
+    assert np.abs((got[1] - mean.double().cpu().numpy() * got[0]) - centred).max() < tol_c
+    assert np.abs(got[1] - want_ab).max() < tol_c + 10 * tol_a
