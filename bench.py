@@ -326,6 +326,12 @@ def run_ours(args):
                       "loss readback for every step (asynchronous, consumed one step late); host work of the "
                       "next batches overlaps the GPU on a prefetch thread"}
 
+    if e2e is not None and getattr(model, "_pipe_trace", None) is not None:
+        # DCGC_PIPE_TRACE=1: host-side stage timers of the fit pipeline of this rank (ms per step, incl. warm-up steps)
+        tr = model._pipe_trace
+        n_tr = max(1.0, tr.get("fit_steps", 1.0))
+        e2e["pipe_trace_ms_per_step"] = {k: round(v / n_tr * 1e3, 4) for k, v in tr.items()
+                                         if k not in ("fit_steps", "pf_batches")}
     if rank != 0:
         return
     peaks = {}

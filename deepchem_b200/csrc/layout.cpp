@@ -226,6 +226,164 @@ static void build_derived(const dcgc_layout_info* info, char* slab, bool check_n
   gt[4] = R;
 }
 
+// One pass over the molecules that writes EVERY section of the slab (the general path below makes five passes over
+// the batch with batch-sized scatter targets: 2.9 ms for 4096 molecules on one core; this one 1.2 ms).  It relies
+// on two facts: (1) the rows of one molecule, visited by (degree, position), are visited in ascending batch row
+// order, so the molecule's row list (mol_atoms), its transposed entries ordered by (source row, slot) and the group
+// cursors all fall out of a molecule-local walk with molecule-sized scratch; (2) for an adjacency in which every
+// atom is listed by exactly as many atoms as it lists itself (every molecular graph), the transposed CSR has the
+// row offsets of the forward CSR, which are arithmetic in the degree buckets.  Returns 1 when the batch has an
+// atom for which (2) fails (the caller then runs the general path), 0 on success, < 0 on error.
+static int build_single_pass(int64_t n_mols, const int32_t* atom_ptr, const int32_t* adj_ptr, const int32_t* adj_idx,
+                             const dcgc_layout_info* info, char* slab) {
+  const int64_t N = info->n_atoms, S = info->n_segments;
+  int64_t* deg_slice = (int64_t*)(slab + info->off_deg_slice);
+  int32_t* membership = (int32_t*)(slab + info->off_membership);
+  int32_t* perm = (int32_t*)(slab + info->off_perm);
+  int32_t* row_ptr = (int32_t*)(slab + info->off_row_ptr);
+  int32_t* col_idx = (int32_t*)(slab + info->off_col_idx);
+  int32_t* t_row_ptr = (int32_t*)(slab + info->off_t_row_ptr);
+  int32_t* t_src = (int32_t*)(slab + info->off_t_src);
+  int32_t* t_slot = (int32_t*)(slab + info->off_t_slot);
+  int32_t* mol_ptr = (int32_t*)(slab + info->off_mol_ptr);
+  int32_t* mol_atoms = (int32_t*)(slab + info->off_mol_atoms);
+  int32_t* tiles = (int32_t*)(slab + info->off_tiles);
+  int32_t* gt = (int32_t*)(slab + info->off_groups);
+  const int R = info->group_rows;
+
+  int64_t bstart[DCGC_N_DEG + 1], estart[DCGC_N_DEG + 1], cursor[DCGC_N_DEG];
+  {
+    int64_t s0 = 0, e0 = 0, t = 0;
+    for (int d = 0; d < DCGC_N_DEG; ++d) {
+      const int64_t cnt = info->deg_count[d];
+      bstart[d] = cursor[d] = s0;
+      estart[d] = e0;
+      deg_slice[2 * d] = s0;          // running starts, not zeroed for empty buckets (mol_graphs.py:295-305)
+      deg_slice[2 * d + 1] = cnt;
+      int32_t e = (int32_t)e0;
+      for (int64_t r = 0; r < cnt; ++r, e += d) row_ptr[s0 + r] = e;
+      for (int64_t r = 0; r < cnt; r += info->tile_rows) {
+        tiles[4 * t + 0] = (int32_t)(s0 + r);
+        tiles[4 * t + 1] = (int32_t)std::min<int64_t>(info->tile_rows, cnt - r);
+        tiles[4 * t + 2] = d;
+        tiles[4 * t + 3] = 0;
+        ++t;
+      }
+      s0 += cnt;
+      e0 += (int64_t)d * cnt;
+    }
+    bstart[DCGC_N_DEG] = s0;
+    estart[DCGC_N_DEG] = e0;
+    row_ptr[N] = (int32_t)e0;
+  }
+  memset(gt, 0, (size_t)DCGC_GROUP_STRIDE * (info->n_groups_alloc + 2) * 4);
+  int32_t* tab = gt + DCGC_GROUP_STRIDE;
+  int64_t G = 0, cur_rows = 0;
+  auto snapshot = [&](int64_t mol) {
+    int32_t* row = tab + G * DCGC_GROUP_STRIDE;
+    for (int d = 0; d < DCGC_N_DEG; ++d) row[d] = (int32_t)cursor[d];
+    row[DCGC_N_DEG] = (int32_t)mol;
+  };
+  // molecule-local scratch, grown to the largest molecule
+  std::vector<int32_t> new_id, order, fill, tbase, degs;   // (int32 degrees: a uint8 array would alias every store)
+  for (int64_t m = 0; m < n_mols; ++m) {
+    const int64_t base = atom_ptr[m];
+    const int n = (int)(atom_ptr[m + 1] - base);
+    mol_ptr[m] = (int32_t)base;
+    if (n <= 0) {
+      if (n < 0) { dcgc_set_error("dcgc_layout_build: atom_ptr decreases at molecule %lld", (long long)m); return DCGC_ERR_INVALID; }
+      continue;
+    }
+    if (G == 0 || cur_rows + n > R) {
+      if (G >= info->n_groups_alloc) { dcgc_set_error("dcgc_layout_build: group table overflow"); return DCGC_ERR_INVALID; }
+      snapshot(m);
+      ++G;
+      cur_rows = 0;
+    }
+    cur_rows += n;
+    if ((int)new_id.size() < n) { new_id.resize(n); order.resize(n); fill.resize(n); tbase.resize(n); degs.resize(n); }
+    // rows of this molecule: stable counting sort by degree, continuing the batch cursors
+    int cnt[DCGC_N_DEG + 1] = {0};
+    const int32_t* ap = adj_ptr + base;
+    for (int a = 0; a < n; ++a) {
+      const int d = ap[a + 1] - ap[a];
+      if (d < 0 || d > DCGC_MAX_DEG) {
+        dcgc_set_error("atom %lld has degree %d; the layout supports degrees 0..%d", (long long)(base + a), d, DCGC_MAX_DEG);
+        return DCGC_ERR_DEGREE;
+      }
+      degs[a] = d;
+      ++cnt[d + 1];
+    }
+    for (int d = 0; d < DCGC_N_DEG; ++d) cnt[d + 1] += cnt[d];        // cnt[d] = first position of degree d
+    int32_t* ma = mol_atoms + base;
+    for (int a = 0; a < n; ++a) {
+      const int d = degs[a];
+      const int64_t r = cursor[d]++;
+      if (r >= bstart[d + 1]) { dcgc_set_error("dcgc_layout_build: degree histogram changed since dcgc_layout_plan"); return DCGC_ERR_INVALID; }
+      new_id[a] = (int32_t)r;
+      perm[r] = (int32_t)(base + a);
+      membership[r] = (int32_t)m;
+      const int pos = cnt[d]++;
+      order[pos] = a;
+      ma[pos] = (int32_t)r;                                           // ascending: buckets ascend, cursors ascend
+      fill[a] = 0;
+      tbase[a] = (int32_t)(estart[d] + (r - bstart[d]) * d);          // first entry of row r, forward == transposed
+    }
+    // neighbour lists renumbered to batch rows in list order (mol_graphs.py:139-141, 327-336), and their transpose:
+    // sources are visited in ascending row order and slots in order, so every transposed list ends up ordered by
+    // (source row, slot) — the order of the counting sort of the general path
+    for (int pos = 0; pos < n; ++pos) {
+      const int a = order[pos];
+      const int d = degs[a];
+      const int32_t r = new_id[a];
+      int32_t* dst = col_idx + tbase[a];
+      const int32_t* src = adj_idx + ap[a];
+      for (int k = 0; k < d; ++k) {
+        const int64_t nb = src[k];
+        if (nb < 0 || nb >= n) {
+          dcgc_set_error("molecule %lld atom %lld: neighbour index %lld outside [0,%lld)", (long long)m, (long long)a,
+                         (long long)nb, (long long)n);
+          return DCGC_ERR_INDEX;
+        }
+        dst[k] = new_id[nb];
+        const int f = fill[nb]++;
+        if (f >= degs[nb]) return 1;                                  // listed more often than it lists: general path
+        const int32_t p = tbase[nb] + f;
+        t_src[p] = r;
+        t_slot[p] = k;
+      }
+    }
+    for (int a = 0; a < n; ++a)
+      if (fill[a] != degs[a]) return 1;
+  }
+  for (int d = 0; d < DCGC_N_DEG; ++d) {
+    if (cursor[d] != bstart[d + 1]) {
+      dcgc_set_error("dcgc_layout_build: degree histogram changed since dcgc_layout_plan");
+      return DCGC_ERR_INVALID;
+    }
+  }
+  for (int64_t g = n_mols; g <= S; ++g) mol_ptr[g] = (int32_t)N;
+  memcpy(t_row_ptr, row_ptr, (size_t)(N + 1) * 4);
+  snapshot(S);   // closing row: every cursor at its bucket end
+  int64_t max_rows = 0, max_entries = 0;
+  for (int64_t g = 0; g < G; ++g) {
+    int64_t rows = 0, entries = 0;
+    for (int d = 0; d < DCGC_N_DEG; ++d) {
+      const int64_t c = tab[(g + 1) * DCGC_GROUP_STRIDE + d] - tab[g * DCGC_GROUP_STRIDE + d];
+      rows += c;
+      entries += c * d;
+    }
+    max_rows = std::max(max_rows, rows);
+    max_entries = std::max(max_entries, entries);
+  }
+  gt[0] = (int32_t)G;
+  gt[1] = (int32_t)max_rows;
+  gt[2] = (int32_t)max_entries;
+  gt[3] = 1;
+  gt[4] = R;
+  return 0;
+}
+
 extern "C" int dcgc_layout_build(int64_t n_mols, const int32_t* atom_ptr, const int32_t* adj_ptr,
                                  const int32_t* adj_idx, const dcgc_layout_info* info, void* slab_v) {
   DCGC_CHECK_ARG(atom_ptr && adj_ptr && info && slab_v, "dcgc_layout_build: null argument");
@@ -233,6 +391,14 @@ extern "C" int dcgc_layout_build(int64_t n_mols, const int32_t* atom_ptr, const 
                  "dcgc_layout_build: info does not match the inputs");
   DCGC_CHECK_ARG(adj_idx || info->n_edges == 0, "dcgc_layout_build: null adj_idx");
   char* slab = (char*)slab_v;
+  {
+    const char* e = getenv("DCGC_LAYOUT_GENERAL");     // =1: always the general path (tests compare the two)
+    const bool general_only = e && e[0] == '1';
+    if (!general_only) {
+      const int rc = build_single_pass(n_mols, atom_ptr, adj_ptr, adj_idx, info, slab);
+      if (rc <= 0) return rc;     // done, or an input error; 1: not a symmetric adjacency -> general path below
+    }
+  }
   const int64_t N = info->n_atoms;
   int32_t* membership = (int32_t*)(slab + info->off_membership);
   int32_t* perm = (int32_t*)(slab + info->off_perm);

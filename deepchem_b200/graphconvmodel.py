@@ -54,6 +54,17 @@ def _default_host_workers():
 _USE_I8 = os.environ.get("DCGC_FEATURES_I8", "1") != "0"
 
 
+def _lower_thread_priority():
+    """Layout workers run at a lower priority than the threads that feed the GPU (kernel launches, uploads): with
+    one process per GPU and every core busy (8 ranks on 32 cores) a launch thread that waits for a core stalls the
+    device, a layout that finishes a little later does not."""
+    try:
+        import threading
+        os.setpriority(os.PRIO_PROCESS, threading.get_native_id(), 10)
+    except Exception:
+        pass
+
+
 def _lib_handle():
     return _lib_mod.lib()
 
@@ -65,7 +76,7 @@ def _lib_check(status):
 def _chunked_h2d(dst, src):
     """dst.copy_(src) from pinned host memory as a train of moderate asynchronous copies on the current stream
     (one C call, GIL released; dcgc_h2d_chunked).  One 30 MB cudaMemcpyAsync running beside the training kernels
-    slowed the forward kernels by up to 20 % of a step on B200; the same bytes in DCGC_H2D_CHUNK_MB (default 0.25)
+    slowed the forward kernels by up to 20 % of a step on B200; the same bytes in DCGC_H2D_CHUNK_MB (default 0.5)
     MiB pieces cost a fraction of that (scripts/interference.py, profiles/r2_interference.md)."""
     from .mol_graphs import _h2d_chunk_bytes
     step = _h2d_chunk_bytes()
@@ -463,7 +474,8 @@ class GraphConvModel(object):
         import collections
         from concurrent.futures import ThreadPoolExecutor
         pending = collections.deque()
-        with ThreadPoolExecutor(max_workers=workers, thread_name_prefix="dcgc-layout") as pool:
+        with ThreadPoolExecutor(max_workers=workers, thread_name_prefix="dcgc-layout",
+                                initializer=_lower_thread_priority) as pool:
             for X_b, y_b, w_b in batches():
                 pending.append((pool.submit(self.batch_inputs, X_b), y_b, w_b))
                 if len(pending) > workers:

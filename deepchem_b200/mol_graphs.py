@@ -305,7 +305,7 @@ class BatchLayout(object):
 def _h2d_chunk_bytes():
     import os
     try:
-        return int(float(os.environ.get("DCGC_H2D_CHUNK_MB", "0.25")) * (1 << 20))
+        return int(float(os.environ.get("DCGC_H2D_CHUNK_MB", "0.5")) * (1 << 20))
     except ValueError:
         return 1 << 18
 

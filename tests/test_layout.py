@@ -203,3 +203,51 @@ def test_empty_batch_has_no_groups():
     pm = PackedMols(np.zeros(1, np.int32), np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros((0, 75), np.float32))
     lay = BatchLayout.build(pm, n_segments=2)
     assert lay.n_groups == 0 and lay.group_max_rows == 0
+
+
+def _all_fields(lay):
+    names = ("deg_slice", "membership", "perm", "row_ptr", "col_idx", "t_row_ptr", "t_src", "t_slot", "mol_ptr",
+             "mol_atoms", "tiles", "groups")
+    return {f: np.array(getattr(lay, f)) for f in names}
+
+
+@pytest.mark.parametrize("shape,n,seed,segs", [("zinc", 2048, 0, 2048), ("stress", 1000, 1, 1003), ("delaney", 64, 2, 64),
+                                               ("qm9", 500, 3, 500), ("tox21", 777, 4, 800), ("zinc", 3, 5, 3),
+                                               ("stress", 50, 6, 50)])
+def test_single_pass_builder_equals_general_builder(shape, n, seed, segs, monkeypatch):
+    """dcgc_layout_build's molecule-local single pass (symmetric adjacencies) writes the same integers into every
+    section of the slab as the general multi-pass builder, which is pinned to the reference's arrays above."""
+    from deepchem_b200.mol_graphs import BatchLayout
+    from deepchem_b200.synthetic import make_molecules
+    pm = make_molecules(n, seed=seed, shape=shape)
+    monkeypatch.delenv("DCGC_LAYOUT_GENERAL", raising=False)
+    fast = _all_fields(BatchLayout.build(pm, n_segments=segs))
+    monkeypatch.setenv("DCGC_LAYOUT_GENERAL", "1")
+    general = _all_fields(BatchLayout.build(pm, n_segments=segs))
+    for f in fast:
+        assert np.array_equal(fast[f], general[f]), f
+
+
+def test_single_pass_builder_hands_asymmetric_batches_to_the_general_path(monkeypatch):
+    """An adjacency in which an atom is listed more (or less) often than it lists others is not a molecular graph;
+    the single pass detects it and the general builder answers, so both settings agree and `symmetric` is False."""
+    from deepchem_b200.mol_graphs import BatchLayout
+    from deepchem_b200.synthetic import PackedMols, make_molecules
+    pm = make_molecules(40, seed=9, shape="zinc")
+    # molecule 7: drop the last entry of its last atom that has >= 2 neighbours (its partner still lists it)
+    a0, a1 = int(pm.atom_ptr[7]), int(pm.atom_ptr[8])
+    deg = np.diff(pm.adj_ptr)
+    victim = max(a for a in range(a0, a1) if deg[a] >= 2)
+    cut = int(pm.adj_ptr[victim + 1]) - 1
+    adj_idx = np.delete(pm.adj_idx, cut)
+    adj_ptr = pm.adj_ptr.copy()
+    adj_ptr[victim + 1:] -= 1
+    bad = PackedMols(pm.atom_ptr, adj_ptr, adj_idx, pm.features)
+    monkeypatch.delenv("DCGC_LAYOUT_GENERAL", raising=False)
+    a = BatchLayout.build(bad)
+    monkeypatch.setenv("DCGC_LAYOUT_GENERAL", "1")
+    b = _all_fields(BatchLayout.build(bad))
+    assert not a.symmetric
+    fa = _all_fields(a)
+    for f in fa:
+        assert np.array_equal(fa[f], b[f]), f
