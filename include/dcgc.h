@@ -398,6 +398,38 @@ int dcgc_mg_pool_bwd_stats(const float* dy_dev, int64_t ld_dy, const uint8_t* ar
                            const dcgc_topology* topo, int32_t width, float* dx_dev, int64_t ld_dx, const float* y_dev,
                            int64_t ld_y, const float* mean_dev, double* part_dev, int32_t* n_chunks, void* stream);
 
+/* --------------------------------------------------------------------------------------------
+ * MPNN edge-network message passing, forward (the reference's torch port of these layers is forward-only).
+ * The dense contractions go through dcgc_group_gemm_fwd; these are the parts that are not GEMMs.
+ * ------------------------------------------------------------------------------------------ */
+
+/* EdgeNetwork (torch_models/layers.py:4006-4088), first half of its bilinear factorisation: for destination atom
+ * i with pairs q in [pair_ptr[i], pair_ptr[i+1])  (pairs grouped by atom_to_pair[:, 0], in pair order):
+ *   z[i, f*h + b] = sum_q pf[pair_id[q], f] * x[pair_src[q], b]   (f < n_pf),    z[i, n_pf*h + b] = sum_q x[pair_src[q], b]
+ * The message is then  z . W_ext  with  W_ext[f*h + b, a] = W[f, a*h + b],  W_ext[n_pf*h + b, a] = bias[a*h + b]
+ * (one dense [n, (n_pf+1) h] x [(n_pf+1) h, h] GEMM instead of an h x h matrix per pair).  n_pf <= 32. */
+int dcgc_pair_contract_fwd(const float* x_dev, int64_t ld_x, const float* pair_feat_dev, int64_t ld_pf,
+                           const int32_t* pair_ptr_dev, const int32_t* pair_id_dev, const int32_t* pair_src_dev,
+                           int64_t n_dst, int32_t n_pf, int32_t h, float* z_dev, int64_t ld_z, void* stream);
+/* GatedRecurrentUnit (layers.py:2884-2919) around two GEMMs: g = [x | h_prev] . [[Wz Wr Wh]; [Uz Ur 0]] ([n, 3h]);
+ *   gates:  z = sigmoid(g[:, 0:h] + bz),  r = sigmoid(g[:, h:2h] + br),  hr = h_prev * r
+ *   out:    (1 - z) * tanh(g[:, 2h:3h] + u + bh) + z * x      with u = hr . Uh  (x is the message, as the reference writes it) */
+int dcgc_gru_gates_fwd(const float* g_dev, int64_t ld_g, const float* bz_dev, const float* br_dev,
+                       const float* hprev_dev, int64_t ld_h, int64_t n, int32_t h, float* z_dev, int64_t ld_z,
+                       float* hr_dev, int64_t ld_hr, void* stream);
+int dcgc_gru_out_fwd(const float* g_dev, int64_t ld_g, const float* u_dev, int64_t ld_u, const float* bh_dev,
+                     const float* z_dev, int64_t ld_z, const float* x_dev, int64_t ld_x, int64_t n, int32_t h,
+                     float* out_dev, int64_t ld_out, void* stream);
+/* SetGather (layers.py:2976-3138), one set2set step: per molecule g with atoms mol_atoms[mol_ptr[g] .. mol_ptr[g+1])
+ * (ascending): e_i = <x_i, q_g>, a = softmax(e), qstar[g] = [q_g | sum_i a_i x_i]  (zeros for an empty molecule);
+ * then z = qstar . U + b (a GEMM) and the LSTM cell  i|f|o = sigmoid(z[0:3h]), c' = f c + i tanh(z[3h:4h]),
+ * h' = o tanh(c').  max_atoms = the largest molecule of the batch (sizes the shared-memory scratch). */
+int dcgc_setgather_attend_fwd(const float* x_dev, int64_t ld_x, const float* q_dev, int64_t ld_q,
+                              const int32_t* mol_ptr_dev, const int32_t* mol_atoms_dev, int64_t n_mols, int32_t h,
+                              int32_t max_atoms, float* qstar_dev, int64_t ld_qs, void* stream);
+int dcgc_lstm_step_fwd(const float* z_dev, int64_t ld_z, const float* c_in_dev, int64_t n, int32_t h,
+                       float* h_out_dev, float* c_out_dev, void* stream);
+
 /* param_offsets: 4 per conv layer (W, b, gamma, beta), then dense (W, b, gamma, beta), then head
  * (W, b); -1 where batch_norm is off.  bn_offsets: (mean, var) per BN, conv layers then dense. */
 int dcgc_gcmodel_layout(const dcgc_gcmodel_config* cfg, int64_t* param_offsets, int64_t* bn_offsets,
