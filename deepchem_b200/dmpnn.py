@@ -404,16 +404,45 @@ class DMPNNModel(object):
         self._pytorch_optimizer = torch.optim.Adam(self.model.parameters(), lr=learning_rate)
         self._global_step, self.log_frequency, self.model_dir = 0, log_frequency, model_dir
         self._grad_slab = None
+        self._prefetch_stream = None
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except Exception:
+            cores = os.cpu_count() or 2
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))
+        self.host_workers = int(os.environ.get("DCGC_HOST_WORKERS", max(1, min(4, cores // ranks - 2))))
 
     # ------------------------------------------------------------------ batching
-    def default_generator(self, dataset, epochs=1, mode='fit', deterministic=True, pad_batches=False, **kwargs):
-        """(packed graphs + host layout, [y], [w]) per batch (dmpnn.py:677-755)."""
-        for (X_b, y_b, w_b, ids_b) in dataset.iterbatches(batch_size=self.batch_size, epochs=epochs,
-                                                          deterministic=deterministic, pad_batches=pad_batches):
+    def default_generator(self, dataset, epochs=1, mode='fit', deterministic=True, pad_batches=False, workers=None,
+                          **kwargs):
+        """(packed graphs + host layout, [y], [w]) per batch (dmpnn.py:677-755).  ``workers`` > 1 builds the index
+        tables of upcoming batches concurrently on a thread pool (the C++ builder releases the GIL); batches are
+        still yielded in dataset order."""
+        workers = self.host_workers if workers is None else workers
+
+        def build(X_b):
             packed = X_b if isinstance(X_b, PackedGraphs) else PackedGraphs.from_graphs(list(X_b), self.atom_fdim,
                                                                                          self.bond_fdim)
-            layout = DmpnnLayout.build(packed, keep_pads=self.keep_pads, pinned=True)
-            yield ((packed, layout), [y_b], [w_b])
+            return packed, DmpnnLayout.build(packed, keep_pads=self.keep_pads, pinned=True)
+
+        batches = dataset.iterbatches(batch_size=self.batch_size, epochs=epochs, deterministic=deterministic,
+                                      pad_batches=pad_batches)
+        if workers <= 1:
+            for (X_b, y_b, w_b, ids_b) in batches:
+                yield (build(X_b), [y_b], [w_b])
+            return
+        import collections
+        from concurrent.futures import ThreadPoolExecutor
+        pending = collections.deque()
+        with ThreadPoolExecutor(max_workers=workers, thread_name_prefix="dcgc-dmpnn-layout") as pool:
+            for (X_b, y_b, w_b, ids_b) in batches:
+                pending.append((pool.submit(build, X_b), y_b, w_b))
+                if len(pending) > workers:
+                    fut, y0, w0 = pending.popleft()
+                    yield (fut.result(), [y0], [w0])
+            while pending:
+                fut, y0, w0 = pending.popleft()
+                yield (fut.result(), [y0], [w0])
 
     def _prepare_batch(self, batch):
         """Host -> device (dmpnn.py:645-675): integer slab + node / edge / global features, then f_ini assembled on
@@ -421,8 +450,10 @@ class DMPNNModel(object):
         (packed, layout), labels, weights = batch
         dev = self.device
         topo = layout.to_device(dev)
-        af = torch.from_numpy(packed.node_features).to(dev, non_blocking=True)
-        bf = torch.from_numpy(packed.edge_features).to(dev, non_blocking=True)
+        # page-locked torch views of the shard's rows when it was pinned (PackedGraphs.pin_memory): true async DMA
+        pn, pe = getattr(packed, "_pin_nf", None), getattr(packed, "_pin_ef", None)
+        af = (pn if pn is not None else torch.from_numpy(packed.node_features)).to(dev, non_blocking=True)
+        bf = (pe if pe is not None else torch.from_numpy(packed.edge_features)).to(dev, non_blocking=True)
         gf = torch.from_numpy(np.ascontiguousarray(packed.global_features).reshape(-1)).to(dev)
         fa = af.shape[1]
         af_pad = torch.zeros(af.shape[0], (fa + 3) // 4 * 4, device=dev)
@@ -438,6 +469,7 @@ class DMPNNModel(object):
         def conv(arrs):
             return [None if a is None else torch.as_tensor(np.asarray(a, dtype=np.float32), device=dev)
                     for a in (arrs or [])]
+        b._device_tensors = [topo.buffer, af, bf, gf, af_pad, f_ini]      # for record_stream in the prefetcher
         return b, conv(labels), conv(weights)
 
     # ------------------------------------------------------------------ loss
@@ -464,11 +496,63 @@ class DMPNNModel(object):
     def fit(self, dataset, nb_epoch=10, deterministic=False, **kwargs):
         return self.fit_generator(self.default_generator(dataset, epochs=nb_epoch, deterministic=deterministic))
 
-    def fit_generator(self, generator, **kwargs):
+    def _prefetched(self, generator, depth):
+        """Run ``_prepare_batch`` (uploads + f_ini assembly) for upcoming batches on a helper thread and a side
+        stream while the GPU trains on the current one — the role the reference gives to DiskDataset's prefetch
+        thread (data/datasets.py:1670-1693).  Tensors are handed to the training stream with an event and
+        ``record_stream`` (they were allocated on the side stream)."""
+        import queue
+        import threading
+        if self._prefetch_stream is None:
+            self._prefetch_stream = torch.cuda.Stream(device=self.device)
+        side, q, state = self._prefetch_stream, queue.Queue(maxsize=max(1, depth)), {"stop": False, "error": None}
+
+        def run():
+            try:
+                torch.cuda.set_device(self.device)
+                for batch in generator:
+                    if state["stop"]:
+                        break
+                    with torch.cuda.stream(side):
+                        prepared = self._prepare_batch(batch)
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                    q.put((prepared, ev))
+            except BaseException as e:      # surfaced in the consumer
+                state["error"] = e
+            finally:
+                q.put(None)
+
+        th = threading.Thread(target=run, daemon=True)
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                (inputs, labels, weights), ev = item
+                main = torch.cuda.current_stream(self.device)
+                main.wait_event(ev)
+                for t in list(getattr(inputs, "_device_tensors", [])) + [t for t in labels + weights if t is not None]:
+                    t.record_stream(main)
+                yield inputs, labels, weights
+            if state["error"] is not None:
+                raise state["error"]
+        finally:
+            state["stop"] = True
+            while th.is_alive():
+                try:
+                    q.get_nowait()
+                except Exception:
+                    pass
+                th.join(timeout=0.05)
+
+    def fit_generator(self, generator, prefetch=2, **kwargs):
         self.model.train()
         t0, n, last = time.time(), 0, None
-        for batch in generator:
-            inputs, labels, weights = self._prepare_batch(batch)
+        prepared_iter = self._prefetched(generator, prefetch) if (prefetch and self.device.type == "cuda") else \
+            (self._prepare_batch(b) for b in generator)
+        for inputs, labels, weights in prepared_iter:
             self._train_step(inputs, labels, weights)
             loss = self._last_loss
             self._global_step += 1

@@ -32,7 +32,7 @@ class PackedGraphs(object):
     node_features [A,Fa] f32, edge_features [E,Fb] f32, global_features [B,G] f32 (G may be 0)."""
 
     __slots__ = ("node_ptr", "edge_ptr", "edge_src", "edge_dst", "node_features", "edge_features",
-                 "global_features")
+                 "global_features", "_pin_nf", "_pin_ef")
 
     def __init__(self, node_ptr, edge_ptr, edge_src, edge_dst, node_features, edge_features, global_features=None):
         self.node_ptr = np.ascontiguousarray(node_ptr, dtype=np.int32)
@@ -45,6 +45,21 @@ class PackedGraphs(object):
         if global_features is None:
             global_features = np.zeros((n, 0), np.float32)
         self.global_features = np.ascontiguousarray(global_features, dtype=np.float32).reshape(n, -1)
+        self._pin_nf = self._pin_ef = None
+
+    def pin_memory(self):
+        """Move the two feature matrices into page-locked host memory (needs torch + CUDA): batches sliced from the
+        shard then upload with asynchronous DMA and no staging copy (the role PackedMols.pin_memory plays for
+        GraphConv batches)."""
+        import torch
+        if getattr(self, "_pin_nf", None) is None:
+            for name, pin in (("node_features", "_pin_nf"), ("edge_features", "_pin_ef")):
+                a = getattr(self, name)
+                t = torch.empty(a.shape, dtype=torch.float32, pin_memory=True)
+                t.numpy()[...] = a
+                setattr(self, name, t.numpy())
+                setattr(self, pin, t)
+        return self
 
     n_mols = property(lambda self: self.node_ptr.shape[0] - 1)
     n_atoms = property(lambda self: int(self.node_ptr[-1]))
@@ -74,6 +89,9 @@ class PackedGraphs(object):
         out.edge_src, out.edge_dst = self.edge_src[e0:e1], self.edge_dst[e0:e1]
         out.node_features, out.edge_features = self.node_features[a0:a1], self.edge_features[e0:e1]
         out.global_features = self.global_features[lo:hi]
+        pn, pe = getattr(self, "_pin_nf", None), getattr(self, "_pin_ef", None)
+        out._pin_nf = pn[a0:a1] if pn is not None else None       # torch views of the same pinned rows
+        out._pin_ef = pe[e0:e1] if pe is not None else None
         return out
 
     def take(self, idx):

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import ACT_NONE, GEMM_TF32X3
+from ._lib import ACT_NONE, GEMM_FP32, GEMM_TF32X3
 from .ops import _ld, _p, _stream, check, group_gemm_fwd, padded_empty
 
 
@@ -71,6 +71,8 @@ class EdgeNetwork(nn.Module):
         self._w = _WeightCache()
         self._pairs = (None, None)
 
+    K_SLICE = 320       # longest single tensor-core contraction (columns of z), see forward
+
     def __repr__(self):
         return '%s(n_pair_features:%s,n_hidden:%s,init:%s)' % (self.__class__.__name__, self.n_pair_features,
                                                                self.n_hidden, self.init)
@@ -117,7 +119,20 @@ class EdgeNetwork(nn.Module):
         z = padded_empty(n_dst, (P + 1) * h, dev)
         check(_lib.lib().dcgc_pair_contract_fwd(_p(x), _ld(x), _p(pf), _ld(pf), _p(ptr), _p(pid), _p(src), n_dst, P, h,
                                                 _p(z), _ld(z), _stream()))
-        return group_gemm_fwd(z, None, self._w_ext(dev), None, None, ACT_NONE, self.gemm_mode)
+        w_ext = self._w_ext(dev)
+        if self.gemm_mode == GEMM_FP32 or (P + 1) * h <= self.K_SLICE:
+            return group_gemm_fwd(z, None, w_ext, None, None, ACT_NONE, self.gemm_mode)
+        # The tensor core adds every MMA into its fp32 accumulator rounding toward zero, so the error of one long
+        # contraction grows with its length (measured 1.1e-5 of the output scale at K = 1500).  Slices of whole
+        # pair-feature blocks (<= K_SLICE columns of z) are contracted separately and their results added in
+        # fp32 round-to-nearest, in slice order: the bias of each slice is K_SLICE / K of that, with random signs.
+        fc = max(1, self.K_SLICE // h) * h
+        out = None
+        for k0 in range(0, (P + 1) * h, fc):
+            k1 = min((P + 1) * h, k0 + fc)
+            part = group_gemm_fwd(z[:, k0:k1], None, w_ext[k0:k1], None, None, ACT_NONE, self.gemm_mode)
+            out = part if out is None else out.add_(part)
+        return out
 
 
 class GatedRecurrentUnit(nn.Module):

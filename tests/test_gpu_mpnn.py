@@ -50,6 +50,7 @@ def test_edge_network_weave_sized_batch_matches_oracle():
     n, P, h = sum(sizes), 14, 100
     pf = ((rng.random((a2p.shape[0], P)) < 0.25).astype(np.float32))
     x = rng.standard_normal((n, h)).astype(np.float32)
+    torch.manual_seed(3)                      # the weight initialiser draws from torch's generator
     layer = EdgeNetwork(P, h)
     layer.b = T(rng.standard_normal(h * h).astype(np.float32) * 0.02)
     out = layer([T(pf), T(x), T(a2p)])
