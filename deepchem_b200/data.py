@@ -127,3 +127,44 @@ class PackedDataset(_ArrayDataset):
     def select_range(self, lo, hi):
         """Molecules [lo, hi) as a dataset sharing this one's memory (inference sharding)."""
         return PackedDataset(self.packed.slice(lo, hi), self._y[lo:hi], self._w[lo:hi], self._ids[lo:hi])
+
+
+class CSVLoader(object):
+    """``dc.data.CSVLoader(tasks, feature_field, featurizer).create_dataset(csv)`` (deepchem/data/data_loader.py:
+    ``CSVLoader``, labels / weights as ``_convert_df_to_numpy`` ``:35-69``: weights 1, missing labels -> y = 0, w = 0)
+    for SMILES files, over the RDKit-free reader: the molecules go straight into one ``PackedMols`` shard (no pickled
+    ``ConvMol`` objects), rows whose SMILES fail to parse are dropped as ``DataLoader`` drops failed datapoints."""
+
+    def __init__(self, tasks, featurizer=None, feature_field="smiles", id_field=None, smiles_field=None):
+        self.tasks = list(tasks)
+        self.feature_field = smiles_field if smiles_field is not None else feature_field
+        self.id_field = id_field
+        self.featurizer = featurizer          # accepted for signature compatibility; the 75-dim ConvMol features are built in
+
+    def create_dataset(self, inputs, data_dir=None, shard_size=None):
+        import csv
+        from .smiles import featurize_smiles_packed
+        paths = [inputs] if isinstance(inputs, str) else list(inputs)
+        rows = []
+        for path in paths:
+            with open(path, newline="") as fh:
+                rows.extend(csv.DictReader(fh))
+        smiles = [r[self.feature_field].strip() for r in rows]
+        packed, bad = featurize_smiles_packed(smiles)
+        keep = np.setdiff1d(np.arange(len(rows)), np.asarray(bad, dtype=np.int64))
+        y = np.zeros((len(keep), len(self.tasks)), np.float32)
+        w = np.ones((len(keep), len(self.tasks)), np.float32)
+        for i, k in enumerate(keep):
+            for t, task in enumerate(self.tasks):
+                v = (rows[k].get(task) or "").strip()
+                if v == "":
+                    w[i, t] = 0.0
+                else:
+                    y[i, t] = float(v)
+        ids = np.asarray([rows[k][self.id_field] if self.id_field else smiles[k] for k in keep], dtype=str)
+        ds = PackedDataset(packed, y, w, ids, n_tasks=len(self.tasks))
+        if data_dir is not None:
+            ds.save(data_dir)
+        return ds
+
+    featurize = create_dataset
