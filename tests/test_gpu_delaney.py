@@ -32,12 +32,12 @@ def test_real_molecules_against_reference_outputs():
         m.model.load_state_dict(sd)
         batch = next(m.default_generator(ds, deterministic=True, pad_batches=False))
         inputs, labels, weights = m._prepare_batch(batch)
+        m.model.train()                                   # the fixture ran train mode first: it moves the running statistics
+        for i, r in enumerate(m.model(inputs)):
+            assert rel_err(r.detach().cpu().numpy(), d["ref_train_out%d" % i]) < MODEL_TOL, (mode, i)
         m.model.eval()
         for i, r in enumerate(m.model(inputs)):
             assert rel_err(r.detach().cpu().numpy(), d["ref_eval_out%d" % i]) < MODEL_TOL, (mode, i)
-        m.model.train()
-        for i, r in enumerate(m.model(inputs)):
-            assert rel_err(r.detach().cpu().numpy(), d["ref_train_out%d" % i]) < MODEL_TOL, (mode, i)
         m.model.load_state_dict(sd)                       # undo the running-statistics update
         assert m._engine is not None
         loss = m._engine.train_step(inputs[1]._dcgc_topology, inputs[0], labels[0].contiguous(),
