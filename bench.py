@@ -268,7 +268,10 @@ def run_ours(args):
         gs_bytes += sum(2 * n_at * w_ * 4 + n_ed * 4 for w_ in widths_in)
         gs_bytes += sum(3 * n_at * w_ * 4 + n_ed * 4 for w_ in widths_in[1:])
 
-    if args.breakdown and rank == 0:
+    # ---- per-scope pass (rank 0, after the timed region, not part of it): the library's own CUDA-event scopes around
+    # every kernel family for 5 more resident steps -> the `kernels` table of the JSON line (and --breakdown FILE)
+    kernels = None
+    if rank == 0:
         ops.profile_begin("*")
         nb = 5
         for i in range(nb):
@@ -276,6 +279,8 @@ def run_ours(args):
         torch.cuda.synchronize()
         rep = ops.profile_report()
         tot = sum(v[0] for v in rep.values())
+        kernels = kernel_table(rep, nb, [r[0][1]._dcgc_topology for r in resident], B)
+    if args.breakdown and rank == 0:
         with open(args.breakdown, "w") as fh:
             fh.write("# in-situ CUDA-event breakdown, %d steps, %s, ms_per_step(timed)=%.4f\n" % (nb, args.gemm_mode, ms / K))
             fh.write("| scope | us/step | share | calls/step | us/call |\n|---|---:|---:|---:|---:|\n")
@@ -372,7 +377,46 @@ def run_ours(args):
                          % len(pool)},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
     }
+    if kernels is not None:
+        for row in kernels:
+            if row["algorithmic_mb_per_step"] is not None:
+                row["achieved_gbs"] = row["algorithmic_mb_per_step"] * 1e-3 / (row["us_per_step"] * 1e-6)
+                row["frac_of_hbm_peak"] = row["achieved_gbs"] / hbm_peak
+        line["kernels"] = {"source": "5 extra resident steps after the timed region with the library's CUDA-event scopes "
+                                     "around every kernel family (rank 0); bytes = activation operands touched once "
+                                     "(DESIGN.md section 3), weights and index tables of the GEMMs not counted",
+                           "rows": kernels}
     print(json.dumps(line), flush=True)
+
+
+def kernel_table(rep, n_steps, topos, B):
+    """Per kernel family of one training step: in-situ time and the algorithmic bytes DESIGN.md section 3 states for
+    it (mean over the rotated batches), so every family's distance from the HBM roofline is on the bench line, not
+    only the gather-sum's."""
+    N = float(np.mean([t.n_atoms for t in topos]))
+    E = float(np.mean([t.n_edges for t in topos]))
+    fp = [76] + LAYERS[:-1]                       # padded input width of each conv layer
+    C, D, L = LAYERS[-1], DENSE, len(LAYERS)
+    act = lambda w_: N * w_ * 4                   # noqa: E731  one fp32 activation matrix of width w_
+    bytes_per_step = {
+        "dcgc_gather_sum": sum(2 * act(w_) + E * 4 for w_ in fp) + sum(3 * act(w_) + E * 4 for w_ in fp[1:]),
+        "dcgc_pool_fwd": sum(2 * act(c) + E * 4 + N * c for c in LAYERS),
+        "dcgc_pool_bwd": sum(3 * act(c) + 2 * E * 4 + N * c for c in LAYERS),
+        "dcgc_gather_fwd": act(D) + N * 4 + 2 * B * D * 4,
+        "dcgc_gather_bwd": act(D) + N * 4 + 2 * B * D * 4,
+        # conv forward GEMMs read [X | S] and write Y; the 4th call of the scope is the dense layer's input gradient
+        "dcgc_group_gemm_fwd": sum(2 * act(w_) + act(c) for w_, c in zip(fp, LAYERS)) + act(D) + act(C),
+        "dcgc_group_gemm_dgrad": sum(act(c) + 2 * act(w_) for w_, c in zip(fp[1:], LAYERS[1:])),
+        "dcgc_group_gemm_wgrad": sum(2 * act(w_) + act(c) for w_, c in zip(fp, LAYERS)) + act(C) + act(D),
+        "dcgc_linear_fwd": act(C) + act(D),
+        "bn_relu_bwd_apply": sum(3 * act(c) for c in LAYERS) + 3 * act(D),
+    }
+    rows = []
+    for name, (t_ms, n_calls) in sorted(rep.items(), key=lambda kv: -kv[1][0]):
+        b = bytes_per_step.get(name)
+        rows.append({"scope": name, "us_per_step": t_ms * 1e3 / n_steps, "calls_per_step": n_calls / n_steps,
+                     "algorithmic_mb_per_step": None if b is None else b / 1e6})
+    return rows
 
 
 def main():

@@ -69,8 +69,31 @@ class DmpnnInfo(ctypes.Structure):
                                 "off_map_ptr", "off_map_idx", "off_map_t_ptr", "off_map_t_idx", "slab_bytes")]
 
 
+DMPNN_MAX_FFN = 8
+
+
+class DmpnnModelConfig(Structure):
+    """dcgc_dmpnn_model_config"""
+    _fields_ = [("atom_fdim", c_int32), ("bond_fdim", c_int32), ("hidden", c_int32), ("depth", c_int32),
+                ("ffn_layers", c_int32), ("ffn_hidden", c_int32), ("n_out", c_int32), ("aggregation", c_int32),
+                ("aggregation_norm", c_float), ("gemm_mode", c_int32)]
+
+
+class DmpnnTables(Structure):
+    """dcgc_dmpnn_tables"""
+    _fields_ = [("n_mols", c_int64), ("n_atoms", c_int64), ("n_rows", c_int64)] + \
+        [(n, c_void_p) for n in ("mol_ptr", "a2b_ptr", "a2b_idx", "a2b_t_ptr", "a2b_t_idx", "map_ptr", "map_idx",
+                                 "map_t_ptr", "map_t_idx")]
+
+
 _P = c_void_p
 _SIGNATURES = {
+    "dcgc_dmpnn_model_layout": (c_int32, [POINTER(DmpnnModelConfig), _P, POINTER(c_int64)]),
+    "dcgc_dmpnn_model_workspace_bytes": (c_int64, [POINTER(DmpnnModelConfig), c_int64, c_int64, c_int64]),
+    "dcgc_dmpnn_model_forward": (c_int32, [POINTER(DmpnnModelConfig), POINTER(DmpnnTables), _P, c_int64, _P, c_int64,
+                                           _P, _P, c_int64, _P, _P, _P]),
+    "dcgc_dmpnn_model_train_step": (c_int32, [POINTER(DmpnnModelConfig), POINTER(DmpnnTables), _P, c_int64, _P,
+                                              c_int64, _P, _P, _P, _P, _P, c_int64, _P, _P, _P]),
     "dcgc_dmpnn_plan": (c_int32, [c_int64, _P, _P, _P, _P, c_int32, POINTER(DmpnnInfo)]),
     "dcgc_dmpnn_build": (c_int32, [c_int64, _P, _P, _P, _P, POINTER(DmpnnInfo), _P]),
     "dcgc_dmpnn_concat_rows": (c_int32, [_P, c_int64, c_int32, _P, c_int64, c_int32, _P, _P, c_int64, _P, c_int64, _P]),

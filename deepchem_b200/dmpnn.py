@@ -404,6 +404,14 @@ class DMPNNModel(object):
         self._pytorch_optimizer = torch.optim.Adam(self.model.parameters(), lr=learning_rate)
         self._global_step, self.log_frequency, self.model_dir = 0, log_frequency, model_dir
         self._grad_slab = None
+        # fused engine (one C call per step over flat slabs, dcgc_dmpnn_model_*) for the configurations it covers;
+        # use_engine=False (or DCGC_DMPNN_ENGINE=0) keeps the per-layer autograd path over the same kernels
+        self._engine, self._dp = None, False
+        use_engine = kwargs.pop("use_engine", os.environ.get("DCGC_DMPNN_ENGINE", "1") != "0")
+        if use_engine and self.device.type == "cuda":
+            from .dmpnn_engine import DmpnnEngine
+            if DmpnnEngine.eligible(self.model, mode, global_features_size):
+                self._engine = DmpnnEngine(self.model, self.device, lr=learning_rate)
         self._prefetch_stream = None
         try:
             cores = len(os.sched_getaffinity(0))
@@ -565,6 +573,25 @@ class DMPNNModel(object):
 
     def _train_step(self, inputs, labels, weights):
         """zero_grad, forward, loss, backward, (gradient all-reduce), Adam step (torch_model.py:435-443)."""
+        eng = self._engine
+        if eng is not None and labels and labels[0] is not None and getattr(inputs, "topology", None) is not None:
+            topo = inputs.topology
+            y = labels[0].reshape(topo.n_mols, -1).contiguous()
+            w = weights[0] if (weights and weights[0] is not None) else None
+            if w is not None:
+                w = w.reshape(topo.n_mols, -1)
+                w = (w.expand_as(y) if w.shape != y.shape else w).contiguous()
+            loss = eng.train_step(topo, inputs['atom_features'], inputs['f_ini_atoms_bonds'], y, w)
+            scale = 1.0
+            if self._dp:
+                from .parallel import world_size
+                import torch.distributed as dist
+                if world_size() > 1:     # the one exchange of a data-parallel step: the flat gradient slab
+                    dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM)
+                    scale = 1.0 / world_size()
+            eng.adam_step(scale)
+            self._last_loss = loss
+            return loss
         slab = self._grad_slab
         if slab is None:
             self._pytorch_optimizer.zero_grad(set_to_none=True)
@@ -585,6 +612,11 @@ class DMPNNModel(object):
         per-rank batches and a mean loss make the averaged gradient exact).  Parameters are broadcast from rank 0."""
         import torch.distributed as dist
         from .parallel import GradSlab, world_size
+        if self._engine is not None:
+            if world_size() > 1:
+                dist.broadcast(self._engine.params, src=0)
+            self._dp = True
+            return self
         if world_size() > 1:
             for t in list(self.model.parameters()) + list(self.model.buffers()):
                 dist.broadcast(t.data, src=0)
@@ -606,7 +638,10 @@ class DMPNNModel(object):
         with torch.no_grad():
             for batch in self.default_generator(dataset, mode='predict', deterministic=True):
                 inputs, _, _ = self._prepare_batch(batch)
-                o = self.model(inputs)
+                if self._engine is not None:
+                    o = self._engine.forward(inputs.topology, inputs['atom_features'], inputs['f_ini_atoms_bonds'])
+                else:
+                    o = self.model(inputs)
                 outs.append((o if self.mode == 'regression' else o[0]).detach().cpu().numpy())
         return np.concatenate(outs, 0) if outs else np.zeros((0, self.n_tasks), np.float32)
 
@@ -628,7 +663,8 @@ class DMPNNModel(object):
         paths = [os.path.join(model_dir, 'checkpoint%d.pt' % (i + 1)) for i in range(max_checkpoints_to_keep)]
         tmp = os.path.join(model_dir, 'temp_checkpoint.pt')
         torch.save({'model_state_dict': self.model.state_dict(),
-                    'optimizer_state_dict': self._pytorch_optimizer.state_dict(),
+                    'optimizer_state_dict': (self._engine.state_dict() if self._engine is not None
+                                             else self._pytorch_optimizer.state_dict()),
                     'global_step': self._global_step}, tmp)
         if os.path.exists(paths[-1]):
             os.remove(paths[-1])
@@ -645,5 +681,8 @@ class DMPNNModel(object):
                 raise ValueError('No checkpoint found')
         data = torch.load(checkpoint, map_location=self.device)
         self.model.load_state_dict(data['model_state_dict'])
-        self._pytorch_optimizer.load_state_dict(data['optimizer_state_dict'])
+        if self._engine is not None:
+            self._engine.load_state_dict(data['optimizer_state_dict'])
+        else:
+            self._pytorch_optimizer.load_state_dict(data['optimizer_state_dict'])
         self._global_step = data['global_step']

@@ -308,6 +308,50 @@ int dcgc_segment_readout_bwd(const float* dout_dev, int64_t ld_dout, const int32
                              void* stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Fused D-MPNN model: DMPNN.forward (deepchem/models/torch_models/dmpnn.py:246-449: DMPNNEncoderLayer,
+ * torch_models/layers.py:1585-1649, + PositionwiseFeedForward, :795-910), the L2 loss under _StandardLoss
+ * (models/losses.py:76-94, torch_model.py:1267-1294) and the backward of all of it as one call over flat
+ * parameter / gradient slabs (the optimizer is dcgc_adam_step on the same slabs).  Covered configuration:
+ * ReLU activations, dropout 0, encoder bias False, regression, no global features, widths that are
+ * multiples of 4, >= 2 feed-forward linears, depth >= 2; anything else is served by the per-layer entry
+ * points above.
+ * ------------------------------------------------------------------------------------------ */
+#define DCGC_DMPNN_MAX_FFN 8
+typedef struct dcgc_dmpnn_model_config {
+  int32_t atom_fdim, bond_fdim, hidden, depth;
+  int32_t ffn_layers, ffn_hidden, n_out; /* ffn_layers linears: hidden -> ffn_hidden ... -> n_out */
+  int32_t aggregation;                   /* 0 mean, 1 sum, 2 norm (layers.py:1550-1583) */
+  float aggregation_norm;
+  int32_t gemm_mode;
+} dcgc_dmpnn_model_config;
+
+/* Device pointers into the uploaded slab of dcgc_dmpnn_build (keep_pads == 0). */
+typedef struct dcgc_dmpnn_tables {
+  int64_t n_mols, n_atoms, n_rows;
+  const int32_t* mol_ptr;                               /* [n_mols+1] first atom of each molecule */
+  const int32_t *a2b_ptr, *a2b_idx, *a2b_t_ptr, *a2b_t_idx; /* atom <- bond rows and its transpose */
+  const int32_t *map_ptr, *map_idx, *map_t_ptr, *map_t_idx; /* bond row <- bond rows and its transpose */
+} dcgc_dmpnn_tables;
+
+/* offsets (floats into the slabs): W_i [hidden, atom+bond], W_h [hidden, hidden], W_o [hidden, atom+hidden],
+ * b_o [hidden], then (W [out, in], b [out]) per feed-forward linear: 4 + 2 * ffn_layers entries, nn.Linear layout. */
+int dcgc_dmpnn_model_layout(const dcgc_dmpnn_model_config* cfg, int64_t* offsets, int64_t* n_params);
+int64_t dcgc_dmpnn_model_workspace_bytes(const dcgc_dmpnn_model_config* cfg, int64_t n_rows, int64_t n_atoms,
+                                         int64_t n_mols);
+/* out [n_mols, n_out] dense; encoding_out (optional) [n_mols, hidden] = the encoder's molecule vectors. */
+int dcgc_dmpnn_model_forward(const dcgc_dmpnn_model_config* cfg, const dcgc_dmpnn_tables* tables,
+                             const float* atom_feat_dev, int64_t ld_af, const float* f_ini_dev, int64_t ld_fi,
+                             const float* params_dev, void* workspace_dev, int64_t workspace_bytes, float* out_dev,
+                             float* encoding_out_dev, void* stream);
+/* y, w: [n_mols, n_out] (w may be NULL = ones); loss_dev receives mean(w * (out - y)^2); every gradient is
+ * written (not accumulated) into grads_dev; out_dev (optional) receives the predictions [n_mols, n_out]. */
+int dcgc_dmpnn_model_train_step(const dcgc_dmpnn_model_config* cfg, const dcgc_dmpnn_tables* tables,
+                                const float* atom_feat_dev, int64_t ld_af, const float* f_ini_dev, int64_t ld_fi,
+                                const float* y_dev, const float* w_dev, const float* params_dev, float* grads_dev,
+                                void* workspace_dev, int64_t workspace_bytes, float* loss_dev, float* out_dev,
+                                void* stream);
+
+/* --------------------------------------------------------------------------------------------
  * Whole-model engine: GraphConvModel forward / loss / backward in one call over flat slabs.
  * Replaces the per-step Python of TorchModel.fit_generator (torch_model.py:428-443) +
  * _GraphConvTorchModel.forward (graphconvmodel.py:188-249) + autograd.  Layer widths and the

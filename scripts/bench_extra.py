@@ -24,10 +24,7 @@ def dmpnn(mode, B=4096, steps=20):
     m.model.train()
 
     def step():
-        m._pytorch_optimizer.zero_grad(set_to_none=True)
-        loss = m._loss(m.model(inputs), labels, weights)
-        loss.backward()
-        m._pytorch_optimizer.step()
+        m._train_step(inputs, labels, weights)      # fused engine (one C call + Adam) when the configuration is covered
     for _ in range(5):
         step()
     torch.cuda.synchronize()
@@ -50,7 +47,7 @@ def dmpnn(mode, B=4096, steps=20):
     torch.cuda.synchronize()
     n = 40
     ms2 = (time.perf_counter() - t0) / n * 1e3
-    print(json.dumps({"metric": "D-MPNN fwd+bwd molecules/sec", "gemm_mode": mode, "value": B / ms * 1e3, "ms_per_step": ms,
+    print(json.dumps({"metric": "D-MPNN fwd+bwd molecules/sec", "gemm_mode": mode, "engine": m._engine is not None, "value": B / ms * 1e3, "ms_per_step": ms,
                       "e2e": {"value": B / ms2 * 1e3, "ms_per_step": ms2},
                       "config": {"workload": "qm9-synthetic B=%d, %d atoms, %d directed bonds, hidden 300, depth 3, "
                                              "FFN 300x3, 12 targets" % (B, pg.n_atoms, pg.n_bonds)}}), flush=True)

@@ -157,3 +157,79 @@ def test_model_trains_and_predicts():
     mc.fit(GraphDataset(pg, yc), nb_epoch=2, deterministic=True)
     pr = mc.predict(GraphDataset(pg, yc))
     assert pr.shape == (64, 2, 3) and np.allclose(pr.sum(-1), 1.0, atol=1e-5)
+
+
+def _engine_pair(dev, mode, **kw):
+    """The same D-MPNN twice: fused engine (dcgc_dmpnn_model_*) and the per-layer autograd path."""
+    from oracle import dmpnn_torch as O
+    torch.manual_seed(0)
+    om = O.OracleDMPNN(mode='regression', n_tasks=12, **kw)
+    me = _model(dev, n_tasks=12, batch_size=500, gemm_mode=mode, **kw)
+    ma = _model(dev, n_tasks=12, batch_size=500, gemm_mode=mode, use_engine=False, **kw)
+    assert me._engine is not None and ma._engine is None
+    me.model.load_state_dict(om.state_dict())
+    ma.model.load_state_dict(om.state_dict())
+    assert me._engine.aliased()
+    return om, me, ma
+
+
+@pytest.mark.parametrize("mode,depth,agg", [("fp32", 3, "mean"), ("tf32x3", 3, "mean"), ("tf32x3", 2, "sum"),
+                                            ("tf32x3", 4, "norm")])
+def test_fused_engine_step_against_autograd_path_and_oracle(mode, depth, agg):
+    """One C call (forward + L2 loss + backward) against the per-layer autograd path over the same kernels, and
+    against the float64 CPU oracle: predictions, loss, every parameter gradient.  500 QM9-shaped molecules incl.
+    bond-free ones, 10 % zero weights, hidden 300, FFN 300x3, 12 tasks (BASELINE config 4 shape)."""
+    dev = _cuda()
+    from deepchem_b200.dmpnn import GraphDataset
+    from deepchem_b200.dmpnn_data import make_graphs
+    from oracle import dmpnn_torch as O
+    pg = make_graphs(500, seed=5, shape="qm9", no_bond_fraction=0.03)
+    rng = np.random.default_rng(0)
+    y = rng.standard_normal((500, 12)).astype(np.float32)
+    w = (rng.random((500, 12)) > 0.1).astype(np.float32)
+    om, me, ma = _engine_pair(dev, mode, depth=depth, aggregation=agg)
+    ds = GraphDataset(pg, y, w)
+    inputs, labels, weights = me._prepare_batch(next(me.default_generator(ds, deterministic=True)))
+    out = torch.empty(500, 12, device=dev)
+    eng = me._engine
+    loss_e = float(eng.train_step(inputs.topology, inputs['atom_features'], inputs['f_ini_atoms_bonds'],
+                                  labels[0].contiguous(), weights[0].contiguous(), out=out))
+    g_e = {n: p.grad.detach().clone() for n, p in me.model.named_parameters()}
+    out_a = ma.model(inputs)
+    loss_a = ma._loss(out_a, labels, weights)
+    loss_a.backward()
+    assert _rel(out, out_a.detach()) < 2e-6 and abs(loss_e - float(loss_a)) < 1e-6 * max(1.0, abs(loss_e))
+    assert _rel(eng.forward(inputs.topology, inputs['atom_features'], inputs['f_ini_atoms_bonds']), out) == 0.0
+    for n, p in ma.model.named_parameters():
+        assert _rel(g_e[n], p.grad) < 1e-4, (n, _rel(g_e[n], p.grad))
+    # float64 oracle
+    vals = [O.mapper_values(O.OracleGraph(*pg.graph(i))) for i in range(pg.n_mols)]
+    o = om.double()
+    oo = o(O.to_torch_batch(O.collate(vals), torch.float64))
+    lo = ((oo - torch.from_numpy(y).double()) ** 2 * torch.from_numpy(w).double()).mean()
+    lo.backward()
+    assert _rel(out, oo.detach()) < 2e-5 and abs(loss_e - float(lo)) < 1e-5 * max(1.0, abs(float(lo)))
+    for n, p in o.named_parameters():
+        assert _rel(g_e[n], p.grad) < 5e-2, n          # flip-tolerant ReLU bound, see the test above
+
+
+def test_fused_engine_adam_trajectory_and_predict():
+    """Five training steps through DMPNNModel.fit_on_batch (engine + fused Adam) against the autograd path with
+    torch.optim.Adam; predict() through the engine's forward."""
+    dev = _cuda()
+    from deepchem_b200.dmpnn import GraphDataset
+    from deepchem_b200.dmpnn_data import make_graphs
+    pg = make_graphs(200, seed=6, shape="qm9")
+    y = np.random.default_rng(2).standard_normal((200, 12)).astype(np.float32)
+    w = np.ones_like(y)
+    om, me, ma = _engine_pair(dev, "tf32x3")
+    me.batch_size = ma.batch_size = 200
+    for step in range(5):
+        le, la = me.fit_on_batch(pg, y, w), ma.fit_on_batch(pg, y, w)
+        assert abs(le - la) < 2e-5 * max(1.0, abs(la)), (step, le, la)
+    sa = ma.model.state_dict()
+    for k, v in me.model.state_dict().items():
+        assert _rel(v, sa[k]) < 2e-4, k
+    assert me._engine.step_count == 5
+    ds = GraphDataset(pg, y)
+    assert _rel(me.predict(ds), ma.predict(ds)) < 1e-4
