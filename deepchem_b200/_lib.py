@@ -112,6 +112,9 @@ _SIGNATURES = {
     "dcgc_layout_permute_features_host": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, c_int64, c_int32]),
     "dcgc_layout_plan_from_deg": (c_int32, [_P, c_int64, c_int32, POINTER(LayoutInfo)]),
     "dcgc_layout_build_from_deg": (c_int32, [_P, _P, _P, POINTER(LayoutInfo), _P]),
+    "dcgc_packed_take_plan": (c_int32, [c_int64, _P, c_int64, _P, _P, POINTER(c_int64), POINTER(c_int64)]),
+    "dcgc_packed_take": (c_int32, [c_int64, _P, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P,
+                                   c_int32]),
     "dcgc_h2d_chunked": (c_int32, [_P, _P, c_int64, c_int64, _P]),
     "dcgc_permute_rows": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, c_int64, _P]),
     "dcgc_permute_rows_i8": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, c_int64, _P]),

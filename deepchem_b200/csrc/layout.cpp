@@ -524,3 +524,82 @@ extern "C" int dcgc_layout_permute_features_host(const float* src, int64_t ld_sr
   for (auto& th : pool) th.join();
   return DCGC_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Gather of molecules out of a packed shard (PackedMols.take): what a SHUFFLED epoch does for every batch
+// (DiskDataset.iterbatches with deterministic=False, deepchem/data/datasets.py:1598-1730, permutes the sample
+// indices of a shard).  Molecules are contiguous blocks of the shard, so the gather is one memcpy per molecule
+// and array; adjacency entries are molecule-local and are copied unchanged.
+// ------------------------------------------------------------------------------------------
+extern "C" int dcgc_packed_take_plan(int64_t n_take, const int64_t* idx, int64_t n_src_mols, const int32_t* atom_ptr,
+                                     const int32_t* adj_ptr, int64_t* n_atoms_out, int64_t* n_entries_out) {
+  DCGC_CHECK_ARG(n_take >= 0 && n_src_mols >= 0 && n_atoms_out && n_entries_out, "dcgc_packed_take_plan: bad arguments");
+  DCGC_CHECK_ARG((idx && atom_ptr && adj_ptr) || n_take == 0, "dcgc_packed_take_plan: null argument");
+  int64_t na = 0, ne = 0;
+  for (int64_t i = 0; i < n_take; ++i) {
+    const int64_t m = idx[i];
+    if (m < 0 || m >= n_src_mols) {
+      dcgc_set_error("dcgc_packed_take_plan: molecule index %lld out of range [0, %lld)", (long long)m, (long long)n_src_mols);
+      return DCGC_ERR_INDEX;
+    }
+    na += atom_ptr[m + 1] - atom_ptr[m];
+    ne += adj_ptr[atom_ptr[m + 1]] - adj_ptr[atom_ptr[m]];
+  }
+  DCGC_CHECK_ARG(na < ((int64_t)1 << 31) && ne < ((int64_t)1 << 31), "dcgc_packed_take_plan: batch too large for int32 offsets");
+  *n_atoms_out = na;
+  *n_entries_out = ne;
+  return DCGC_OK;
+}
+
+// features / features2 (either may be null): row-major per-atom matrices with row_bytes / row_bytes2 bytes per atom
+// (the fp32 feature matrix and its exact int8 copy); outputs sized by dcgc_packed_take_plan.
+extern "C" int dcgc_packed_take(int64_t n_take, const int64_t* idx, int64_t n_src_mols, const int32_t* atom_ptr,
+                                const int32_t* adj_ptr, const int32_t* adj_idx, const void* features, int64_t row_bytes,
+                                const void* features2, int64_t row_bytes2, int32_t* out_atom_ptr, int32_t* out_adj_ptr,
+                                int32_t* out_adj_idx, void* out_features, void* out_features2, int32_t n_threads) {
+  DCGC_CHECK_ARG(n_take >= 0 && out_atom_ptr && out_adj_ptr, "dcgc_packed_take: bad arguments");
+  DCGC_CHECK_ARG((idx && atom_ptr && adj_ptr) || n_take == 0, "dcgc_packed_take: null argument");
+  DCGC_CHECK_ARG((features == nullptr) == (out_features == nullptr) && (features2 == nullptr) == (out_features2 == nullptr),
+                 "dcgc_packed_take: feature input / output mismatch");
+  std::vector<int64_t> a0((size_t)n_take + 1), e0((size_t)n_take + 1);
+  a0[0] = e0[0] = 0;
+  for (int64_t i = 0; i < n_take; ++i) {
+    const int64_t m = idx[i];
+    if (m < 0 || m >= n_src_mols) {
+      dcgc_set_error("dcgc_packed_take: molecule index %lld out of range [0, %lld)", (long long)m, (long long)n_src_mols);
+      return DCGC_ERR_INDEX;
+    }
+    a0[i + 1] = a0[i] + (atom_ptr[m + 1] - atom_ptr[m]);
+    e0[i + 1] = e0[i] + (adj_ptr[atom_ptr[m + 1]] - adj_ptr[atom_ptr[m]]);
+    out_atom_ptr[i] = (int32_t)a0[i];
+  }
+  out_atom_ptr[n_take] = (int32_t)a0[n_take];
+  out_adj_ptr[a0[n_take]] = (int32_t)e0[n_take];
+  DCGC_CHECK_ARG(e0[n_take] == 0 || (adj_idx && out_adj_idx), "dcgc_packed_take: null adjacency");
+  auto work = [&](int64_t lo, int64_t hi) {
+    for (int64_t i = lo; i < hi; ++i) {
+      const int64_t m = idx[i], s = atom_ptr[m], n = atom_ptr[m + 1] - s;
+      const int64_t es = adj_ptr[s], shift = e0[i] - es;
+      for (int64_t r = 0; r < n; ++r) out_adj_ptr[a0[i] + r] = (int32_t)(adj_ptr[s + r] + shift);
+      if (e0[i + 1] > e0[i]) memcpy(out_adj_idx + e0[i], adj_idx + es, (size_t)(e0[i + 1] - e0[i]) * 4);
+      if (features)
+        memcpy(static_cast<char*>(out_features) + a0[i] * row_bytes, static_cast<const char*>(features) + s * row_bytes,
+               (size_t)(n * row_bytes));
+      if (features2)
+        memcpy(static_cast<char*>(out_features2) + a0[i] * row_bytes2, static_cast<const char*>(features2) + s * row_bytes2,
+               (size_t)(n * row_bytes2));
+    }
+  };
+  if (n_threads <= 1 || n_take < 512) {
+    work(0, n_take);
+    return DCGC_OK;
+  }
+  std::vector<std::thread> pool;
+  const int64_t chunk = (n_take + n_threads - 1) / n_threads;
+  for (int t = 0; t < n_threads; ++t) {
+    const int64_t lo = t * chunk, hi = std::min(n_take, lo + chunk);
+    if (lo < hi) pool.emplace_back(work, lo, hi);
+  }
+  for (auto& th : pool) th.join();
+  return DCGC_OK;
+}

@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-from .synthetic import PackedMols
+from .synthetic import LazyTake, PackedMols
 
 
 def pad_batch(batch_size, X_b, y_b, w_b, ids_b):
@@ -20,7 +20,7 @@ def pad_batch(batch_size, X_b, y_b, w_b, ids_b):
     if n == batch_size:
         return X_b, y_b, w_b, ids_b
     reps = np.arange(batch_size) % n
-    X_out = X_b.take(reps) if isinstance(X_b, PackedMols) else X_b[reps]
+    X_out = X_b.take(reps) if isinstance(X_b, (PackedMols, LazyTake)) else X_b[reps]
     y_out = None if y_b is None else y_b[reps]
     ids_out = ids_b[reps]
     if w_b is None:
@@ -58,10 +58,12 @@ class _ArrayDataset(object):
     def get_shape(self):
         return (len(self),), self._y.shape, self._w.shape, self._ids.shape
 
-    def _take_X(self, idx, contiguous):
+    def _take_X(self, idx, contiguous, lazy=False):
         raise NotImplementedError
 
-    def iterbatches(self, batch_size=None, epochs=1, deterministic=False, pad_batches=False):
+    def iterbatches(self, batch_size=None, epochs=1, deterministic=False, pad_batches=False, lazy=False):
+        """``lazy``: non-contiguous batches of a packed shard come back as ``LazyTake`` (indices only) so that the
+        consumer gathers them — the model's layout workers do, in parallel and into pinned memory."""
         n = len(self)
         if batch_size is None:
             batch_size = n
@@ -69,7 +71,7 @@ class _ArrayDataset(object):
             perm = np.arange(n) if deterministic else np.random.permutation(n)
             for b in range(math.ceil(n / batch_size) if n else 0):
                 idx = perm[b * batch_size:min(n, (b + 1) * batch_size)]
-                batch = (self._take_X(idx, deterministic), self._y[idx], self._w[idx], self._ids[idx])
+                batch = (self._take_X(idx, deterministic, lazy), self._y[idx], self._w[idx], self._ids[idx])
                 if pad_batches:
                     batch = pad_batch(batch_size, *batch)
                 yield batch
@@ -89,7 +91,7 @@ class NumpyDataset(_ArrayDataset):
 
     X = property(lambda self: self._X)
 
-    def _take_X(self, idx, contiguous):
+    def _take_X(self, idx, contiguous, lazy=False):
         return self._X[idx]
 
     def select_range(self, lo, hi):
@@ -105,10 +107,10 @@ class PackedDataset(_ArrayDataset):
 
     X = property(lambda self: self.packed)
 
-    def _take_X(self, idx, contiguous):
+    def _take_X(self, idx, contiguous, lazy=False):
         if contiguous and len(idx):
             return self.packed.slice(int(idx[0]), int(idx[-1]) + 1)
-        return self.packed.take(idx)
+        return self.packed.take_lazy(idx) if lazy else self.packed.take(idx)
 
     def save(self, path):
         """Write the dataset as a packed on-disk shard (PackedMols.save + y / w / ids)."""

@@ -95,8 +95,17 @@ class PackedGraphs(object):
         return out
 
     def take(self, idx):
-        return PackedGraphs.from_graphs([GraphData(*self.graph(int(i))) for i in idx],
-                                        self.node_features.shape[1], self.edge_features.shape[1])
+        """Molecules idx[0], idx[1], ... (repeats allowed) as a new shard; vectorised (a shuffled epoch takes this
+        path for every batch)."""
+        from .synthetic import _ranges
+        idx = np.asarray(idx, dtype=np.int64)
+        n_at = (self.node_ptr[idx + 1] - self.node_ptr[idx]).astype(np.int64)
+        n_ed = (self.edge_ptr[idx + 1] - self.edge_ptr[idx]).astype(np.int64)
+        rows = _ranges(np.asarray(self.node_ptr)[idx], n_at)
+        eds = _ranges(np.asarray(self.edge_ptr)[idx], n_ed)
+        return PackedGraphs(np.concatenate([[0], np.cumsum(n_at)]), np.concatenate([[0], np.cumsum(n_ed)]),
+                            np.asarray(self.edge_src)[eds], np.asarray(self.edge_dst)[eds], self.node_features[rows],
+                            self.edge_features[eds], self.global_features[idx])
 
     @staticmethod
     def from_graphs(graphs, atom_fdim=None, bond_fdim=None):

@@ -34,7 +34,7 @@ from .data import NumpyDataset, PackedDataset  # noqa: F401  (re-exported)
 from .engine import FlatEngine
 from .layers import GraphConv, GraphGather, GraphPool, gemm_mode_code
 from .mol_graphs import BatchLayout, pack_convmols
-from .synthetic import PackedMols
+from .synthetic import LazyTake, PackedMols
 
 logger = logging.getLogger(__name__)
 
@@ -323,14 +323,18 @@ class _Prefetcher(object):
         try:
             prev = None
             while True:
-                item = self.q.get()
                 if prev is not None:
                     # the consumer has issued all its work on the previous batch: its slot may be refilled once
-                    # that work has run
+                    # that work has run.  This must be published BEFORE q.get(): taking an item is what unblocks a
+                    # producer waiting on the full queue, and its next slot is this one — set afterwards, the
+                    # producer could read the slot's previous (long completed) event and overwrite device buffers
+                    # that the kernels of this batch were still reading (seen as an illegal memory access with 8
+                    # distinct batches per epoch).
                     fe = torch.cuda.Event()
                     fe.record(torch.cuda.current_stream())
                     prev.free_event = fe
                     prev = None
+                item = self.q.get()
                 if item is None:
                     break
                 prepared, ev, slot = item
@@ -435,6 +439,7 @@ class GraphConvModel(object):
         self._pipe_trace = collections.defaultdict(float) if os.environ.get("DCGC_PIPE_TRACE") == "1" else None
         self._staging = []          # ring of reusable pinned slabs: [tensor, event]
         self._staging_next = 0
+        self._feat_staging, self._feat_staging_next = [], 0   # same, for gathered features of shuffled batches
         import threading
         self._staging_lock = threading.Lock()
         # host threads building batch layouts ahead of the GPU (default_generator)
@@ -459,9 +464,12 @@ class GraphConvModel(object):
             workers = self.host_workers
 
         def batches():
+            kw = {}
+            if not deterministic and isinstance(dataset, PackedDataset) and os.environ.get("DCGC_LAZY_TAKE", "1") != "0":
+                kw["lazy"] = True          # shuffled batches are gathered by the layout workers (batch_inputs)
             for (X_b, y_b, w_b, ids_b) in dataset.iterbatches(batch_size=self.batch_size, epochs=epochs,
                                                               deterministic=deterministic,
-                                                              pad_batches=pad_batches):
+                                                              pad_batches=pad_batches, **kw):
                 if y_b is not None and self.mode == 'classification' and not (mode == 'predict'):
                     y_b = to_one_hot(np.asarray(y_b).flatten(), self.n_classes).reshape(
                         -1, self.n_tasks, self.n_classes)
@@ -504,11 +512,41 @@ class GraphConvModel(object):
             slot[0] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
         return slot
 
+    def _feature_staging(self, nbytes):
+        """Pinned staging buffer for the gathered features of a shuffled batch (same ring discipline as
+        ``_staging_slab``: reused only after the upload that read it has finished)."""
+        ring = 2 * max(1, self.host_workers) + 8
+        with self._staging_lock:
+            if len(self._feat_staging) < ring:
+                self._feat_staging.append([torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True), None])
+                return self._feat_staging[-1]
+            slot = self._feat_staging[self._feat_staging_next % ring]
+            self._feat_staging_next += 1
+        if slot[1] is not None:
+            slot[1].synchronize()
+            slot[1] = None
+        if slot[0].numel() < nbytes:
+            slot[0] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
+        return slot
+
     def batch_inputs(self, X_b, pinned=True):
+        pinned = pinned and torch.cuda.is_available()     # host-only callers (tests) get plain memory
+        feat_slot = None
+        if isinstance(X_b, LazyTake):
+            # a shuffled batch: gather the molecules here (worker thread, GIL released in C), features straight into
+            # page-locked staging memory — their exact int8 copy alone when the shard has one
+            alloc = None
+            if pinned:
+                def alloc(n_atoms, n_feat, dtype):
+                    nonlocal feat_slot
+                    nbytes = n_atoms * n_feat * np.dtype(dtype).itemsize
+                    feat_slot = self._feature_staging(nbytes)
+                    tdt = torch.int8 if np.dtype(dtype) == np.int8 else torch.float32
+                    return feat_slot[0][:nbytes].view(tdt).view(n_atoms, n_feat)
+            X_b = X_b.resolve(alloc=alloc, prefer_i8=bool(pinned and _USE_I8), n_threads=1)
         packed = X_b if isinstance(X_b, PackedMols) else pack_convmols(X_b)
         n_seg = max(self.batch_size, packed.n_mols)
         slot = None
-        pinned = pinned and torch.cuda.is_available()     # host-only callers (tests) get plain memory
         if pinned:
             # upper bound of the slab size without running the planner: 11 int32 arrays over atoms /
             # edges / segments plus alignment
@@ -531,6 +569,7 @@ class GraphConvModel(object):
         # exact int8 copy of the same rows (PackedMols.compact): a quarter of the upload
         p8 = getattr(packed, "_pin_i8", None)
         inputs.packed_features_i8_pinned = p8 if (p8 is not None and tuple(p8.shape) == packed.features.shape) else None
+        inputs.feature_staging_slot = feat_slot
         return inputs
 
     def _prepare_batch(self, batch, slot=None):
@@ -561,6 +600,10 @@ class GraphConvModel(object):
             x = ops.permute_rows(fdev, topo.perm, out=slot.get("x", n * ((f + 3) // 4 * 4), torch.float32))
         else:
             x = ops.permute_rows(feats.to(self.device, non_blocking=True), topo.perm)
+        fslot = getattr(inputs, "feature_staging_slot", None)
+        if fslot is not None:                  # the gathered features may be overwritten once this upload is done
+            fslot[1] = torch.cuda.Event()
+            fslot[1].record(torch.cuda.current_stream())
         x._dcgc_zero_padded = True
         dev_inputs = topo.model_inputs(x, n_samples=int(inputs[3]))
 

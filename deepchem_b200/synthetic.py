@@ -16,6 +16,35 @@ Shapes:
 import numpy as np
 
 
+def _ranges(starts, lens):
+    """concatenate([arange(s, s + l) for s, l in zip(starts, lens)]) without the Python loop."""
+    lens = np.asarray(lens, dtype=np.int64)
+    total = int(lens.sum())
+    if total == 0:
+        return np.zeros(0, np.int64)
+    first = np.cumsum(lens) - lens                      # position of every range in the output
+    return np.arange(total, dtype=np.int64) + np.repeat(np.asarray(starts, dtype=np.int64) - first, lens)
+
+
+class LazyTake(object):
+    """Molecule numbers into a source shard, gathered later by whoever consumes the batch (the layout worker threads
+    of the model's host pipeline, into pinned staging memory) instead of by the dataset iterator."""
+
+    def __init__(self, src, idx):
+        self.src, self.idx = src, np.ascontiguousarray(idx, dtype=np.int64)
+
+    def __len__(self):
+        return int(self.idx.shape[0])
+
+    n_mols = property(__len__)
+
+    def take(self, reps):
+        return LazyTake(self.src, self.idx[np.asarray(reps, dtype=np.int64)])
+
+    def resolve(self, **kw):
+        return self.src.take(self.idx, **kw)
+
+
 class PackedMols(object):
     """A shard of molecules with no Python objects inside.
 
@@ -127,18 +156,55 @@ class PackedMols(object):
             self._pin_i8 = t8
         return self
 
-    def take(self, idx):
-        """Molecules idx[0], idx[1], ... (repeats allowed) as a new PackedMols."""
-        idx = np.asarray(idx, dtype=np.int64)
-        n_per = (self.atom_ptr[idx + 1] - self.atom_ptr[idx]).astype(np.int64)
-        atom_ptr = np.concatenate([[0], np.cumsum(n_per)])
-        rows = np.concatenate([np.arange(self.atom_ptr[i], self.atom_ptr[i + 1]) for i in idx]) \
-            if idx.size else np.zeros(0, np.int64)
-        deg = (self.adj_ptr[rows + 1] - self.adj_ptr[rows]).astype(np.int64)
-        adj_ptr = np.concatenate([[0], np.cumsum(deg)])
-        adj = np.concatenate([self.adj_idx[self.adj_ptr[r]:self.adj_ptr[r + 1]] for r in rows]) \
-            if rows.size else np.zeros(0, np.int32)
-        return PackedMols(atom_ptr, adj_ptr, adj, self.features[rows])
+    def take(self, idx, alloc=None, prefer_i8=False, n_threads=1):
+        """Molecules idx[0], idx[1], ... (repeats allowed) as a new PackedMols: one memcpy per molecule and array in C
+        (``dcgc_packed_take``) — a shuffled epoch takes this path for every batch.  ``alloc(n_atoms, n_feat, dtype)``
+        may return a page-locked torch tensor for the gathered features (the host pipeline's staging ring), which then
+        upload with asynchronous DMA; ``prefer_i8``: when the shard has its exact int8 copy, gather only that one (the
+        result's ``features`` is then the int8 matrix)."""
+        import ctypes
+        from . import _lib
+        L = _lib.lib()
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        n = int(idx.shape[0])
+        atom_ptr = np.ascontiguousarray(self.atom_ptr, dtype=np.int32)
+        adj_ptr = np.ascontiguousarray(self.adj_ptr, dtype=np.int32)
+        adj_idx = np.ascontiguousarray(self.adj_idx, dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)     # noqa: E731
+        na, ne = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(L.dcgc_packed_take_plan(n, p(idx), self.n_mols, p(atom_ptr), p(adj_ptr), ctypes.byref(na),
+                                           ctypes.byref(ne)))
+        na, ne = na.value, ne.value
+        f = self.n_feat
+        i8 = self.features_i8 if getattr(self, "features_i8", None) is not None else None
+        only_i8 = bool(prefer_i8 and i8 is not None)
+
+        def out(dtype):
+            if alloc is not None:
+                t = alloc(na, f, dtype)
+                return t.numpy(), t
+            return np.empty((na, f), dtype), None
+        o32 = o8 = t32 = t8 = None
+        src32 = src8 = None
+        if not only_i8:
+            o32, t32 = out(np.float32)
+            src32 = np.ascontiguousarray(self.features, dtype=np.float32)
+        if i8 is not None:
+            o8, t8 = out(np.int8)
+            src8 = np.ascontiguousarray(i8)
+        o_atom, o_adjp, o_adj = np.empty(n + 1, np.int32), np.empty(na + 1, np.int32), np.empty(ne, np.int32)
+        _lib.check(L.dcgc_packed_take(
+            n, p(idx), self.n_mols, p(atom_ptr), p(adj_ptr), p(adj_idx), p(src32) if src32 is not None else None, 4 * f,
+            p(src8) if src8 is not None else None, f, p(o_atom), p(o_adjp), p(o_adj),
+            p(o32) if o32 is not None else None, p(o8) if o8 is not None else None, int(n_threads)))
+        res = PackedMols.__new__(PackedMols)
+        res.atom_ptr, res.adj_ptr, res.adj_idx = o_atom, o_adjp, o_adj
+        res.features = o32 if o32 is not None else o8
+        res._pin, res.features_i8, res._pin_i8 = t32, o8, t8
+        return res
+
+    def take_lazy(self, idx):
+        return LazyTake(self, idx)
 
     # ------------------------------------------------------------------ on-disk shard format
     # One directory per shard with four raw .npy files (no pickled Python objects, unlike the reference's

@@ -122,6 +122,19 @@ int dcgc_layout_build(int64_t n_mols, const int32_t* atom_ptr, const int32_t* ad
 int dcgc_layout_permute_features_host(const float* src, int64_t ld_src, const int32_t* perm,
                                       int64_t n_atoms, int32_t n_feat, float* dst, int64_t ld_dst,
                                       int32_t n_threads);
+/* Gather of molecules out of a packed shard (what a shuffled epoch does for every batch: DiskDataset.iterbatches
+ * with deterministic=False permutes the sample indices, deepchem/data/datasets.py:1598-1730).  idx[n_take] are molecule
+ * numbers of the source shard (repeats allowed: pad_batch tiles them, datasets.py:142-218).  _plan returns the sizes
+ * of the outputs; features / features2 are optional per-atom row-major matrices (row_bytes bytes per atom each: the
+ * fp32 feature matrix and its exact int8 copy) gathered with one memcpy per molecule, into pinned staging memory when
+ * the caller provides it.  Adjacency entries are molecule-local and are copied unchanged. */
+int dcgc_packed_take_plan(int64_t n_take, const int64_t* idx, int64_t n_src_mols, const int32_t* atom_ptr,
+                          const int32_t* adj_ptr, int64_t* n_atoms_out, int64_t* n_entries_out);
+int dcgc_packed_take(int64_t n_take, const int64_t* idx, int64_t n_src_mols, const int32_t* atom_ptr,
+                     const int32_t* adj_ptr, const int32_t* adj_idx, const void* features, int64_t row_bytes,
+                     const void* features2, int64_t row_bytes2, int32_t* out_atom_ptr, int32_t* out_adj_ptr,
+                     int32_t* out_adj_idx, void* out_features, void* out_features2, int32_t n_threads);
+
 /* Derive the same slab from an already-agglomerated reference layout (deg_slice, membership,
  * col_idx = concatenated deg_adj lists): used when a caller hands the layers plain tensors. */
 int dcgc_layout_plan_from_deg(const int64_t* deg_slice, int64_t n_segments, int32_t tile_rows,

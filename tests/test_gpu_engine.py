@@ -43,12 +43,13 @@ def _oracle_step(om, mode, pm, y_onehot_or_y, w, n):
 @pytest.mark.parametrize("mode,layers,bn,shape", [("regression", [64, 64], True, "stress"),
                                                   ("classification", [128, 128, 128], True, "zinc"),
                                                   ("regression", [32, 64], False, "stress"),
-                                                  ("classification", [64], True, "delaney")])
+                                                  ("classification", [64], True, "delaney"),
+                                                  ("classification", [64, 64], True, "tox21")])
 def test_engine_train_step_matches_oracle(mode, layers, bn, shape):
     from deepchem_b200.data import PackedDataset
     from deepchem_b200.synthetic import make_labels, make_molecules
     _cuda()
-    n_tasks, dense, bsz = 3, 128, 72
+    n_tasks, dense, bsz = (12 if shape == "tox21" else 3), 128, 72     # tox21: BASELINE config 2 (12 tasks, missing labels)
     pm = make_molecules(70, seed=11, shape=shape)
     y, w = make_labels(pm.n_mols, n_tasks, mode, seed=2, missing=0.25)
     om, m = _pair(mode, layers, dense, n_tasks, bsz, bn)
@@ -201,3 +202,26 @@ def test_int8_feature_upload_is_exact_and_fit_is_unchanged():
         finally:
             G._USE_I8 = True
     assert len(runs[0]) == 10 and runs[0] == runs[1]
+
+
+def test_shuffled_fit_lazy_gather_equals_eager_batches(monkeypatch):
+    """fit(deterministic=False): batches gathered by the layout workers into pinned staging memory (int8 feature copy)
+    train exactly like batches gathered eagerly by the dataset iterator (same permutations)."""
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    from deepchem_b200.synthetic import make_labels, make_molecules
+    _cuda()
+    pm = make_molecules(300, seed=15, shape="stress")
+    assert pm.compact()
+    pm.pin_memory()
+    y, w = make_labels(300, 2, "regression", seed=5)
+    finals = []
+    for lazy in ("1", "0"):
+        monkeypatch.setenv("DCGC_LAZY_TAKE", lazy)
+        torch.manual_seed(3)
+        np.random.seed(7)
+        m = GraphConvModel(2, [64, 64], 128, mode="regression", batch_size=64)
+        m.fit(PackedDataset(pm, y, w), nb_epoch=3, deterministic=False)
+        finals.append({k: v.detach().cpu().clone() for k, v in m.model.state_dict().items()})
+    for k in finals[0]:
+        assert torch.equal(finals[0][k], finals[1][k]), k

@@ -3,6 +3,7 @@ produces the same layouts as the single-threaded generator (graphconvmodel.py:38
 import threading
 
 import numpy as np
+import pytest
 
 from deepchem_b200 import graphconvmodel as G
 from deepchem_b200.data import PackedDataset
@@ -92,3 +93,53 @@ def test_compact_int8_features_are_exact_or_refused(tmp_path):
         q = make_molecules(50, seed=8)
         q.features[5, 5] = bad
         assert not q.compact() and q.features_i8 is None
+
+
+def test_packed_take_matches_per_molecule_gather():
+    """PackedMols.take (dcgc_packed_take: one memcpy per molecule) against a per-molecule rebuild: repeats, slices of a
+    shard, the int8-only form, the empty selection, an out-of-range index."""
+    from deepchem_b200.synthetic import PackedMols, make_molecules
+    pm = make_molecules(600, seed=2, shape="stress")
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, 600, size=777)
+    ref = PackedMols.from_list([pm.mol(int(i)) for i in idx], 75)
+    for threads in (1, 3):
+        got = pm.take(idx, n_threads=threads)
+        for k in ("atom_ptr", "adj_ptr", "adj_idx", "features"):
+            assert np.array_equal(getattr(got, k), getattr(ref, k)) and getattr(got, k).dtype == getattr(ref, k).dtype, k
+    pc = make_molecules(600, seed=2, shape="stress")
+    assert pc.compact()
+    only8 = pc.take(idx, prefer_i8=True)
+    assert only8.features.dtype == np.int8 and np.array_equal(only8.features.astype(np.float32), ref.features)
+    both = pc.take(idx)
+    assert both.features.dtype == np.float32 and np.array_equal(both.features_i8, only8.features)
+    sl = pm.slice(100, 400)
+    sub = sl.take(np.array([5, 5, 0, 299]))
+    want = PackedMols.from_list([sl.mol(i) for i in (5, 5, 0, 299)], 75)
+    for k in ("atom_ptr", "adj_ptr", "adj_idx", "features"):
+        assert np.array_equal(getattr(sub, k), getattr(want, k)), k
+    assert pm.take(np.zeros(0, np.int64)).n_mols == 0
+    with pytest.raises(ValueError):
+        pm.take(np.array([600]))
+
+
+def test_lazy_shuffled_batches_equal_eager_ones():
+    """iterbatches(lazy=True) hands out index lists; resolving them (what the layout workers do) gives the batches of
+    the eager iterator, padding included."""
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.synthetic import LazyTake, make_labels, make_molecules
+    pm = make_molecules(230, seed=5, shape="zinc")
+    y, w = make_labels(230, 2, "regression", seed=1)
+    ds = PackedDataset(pm, y, w)
+    np.random.seed(11)
+    eager = list(ds.iterbatches(batch_size=64, deterministic=False, pad_batches=True))
+    np.random.seed(11)
+    lazy = list(ds.iterbatches(batch_size=64, deterministic=False, pad_batches=True, lazy=True))
+    assert len(eager) == len(lazy) == 4
+    for (Xe, ye, we, ie), (Xl, yl, wl, il) in zip(eager, lazy):
+        assert isinstance(Xl, LazyTake) and len(Xl) == 64
+        Xr = Xl.resolve()
+        for k in ("atom_ptr", "adj_ptr", "adj_idx", "features"):
+            assert np.array_equal(getattr(Xr, k), getattr(Xe, k)), k
+        assert np.array_equal(ye, yl) and np.array_equal(we, wl) and np.array_equal(ie, il)
+    assert float(lazy[-1][2][230 - 192:].sum()) == 0.0            # the padded copies carry zero weights
