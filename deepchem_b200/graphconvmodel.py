@@ -251,6 +251,9 @@ class _DeviceSlot(object):
         return t
 
 
+_PINNED_RESULT_LIMIT = 4 << 30      # predict(): largest result kept in one page-locked array
+
+
 class _Prefetcher(object):
     """Runs ``model._prepare_batch`` for upcoming batches on a helper thread and a side CUDA stream;
     the consumer's stream waits on an event before touching a prepared batch."""
@@ -798,17 +801,19 @@ class GraphConvModel(object):
         return float(loss)
 
     # ------------------------------------------------------------------ inference
-    def _predict(self, generator, output_idx):
+    def _predict(self, generator, output_idx, n_rows=None):
         """Forward-only pass over the batches (torch_model.py:547-652).  With the fused engine the batches are
-        prepared ahead on the prefetch thread, every batch is one C call, outputs stay on the device and come
-        back in ONE device-to-host copy at the end (the reference copies every output of every batch,
-        torch_model.py:606)."""
+        prepared ahead on the prefetch thread and every batch is one C call.  ``n_rows`` (rows of every requested
+        output over the whole pass, known to ``predict``): each batch's outputs are copied asynchronously into their
+        place in ONE page-locked result array (the reference copies every output of every batch synchronously,
+        torch_model.py:606); without it the outputs stay on the device and come back in one copy at the end."""
         self.model.eval()
         results = None
         with torch.no_grad():
             if self._engine is not None:
                 cls = self.mode == "classification"
                 chunks = None
+                host, offs = None, None
                 for inputs, _, _ in _Prefetcher(self, generator, 2):
                     topo, n = inputs[1]._dcgc_topology, int(inputs[3])
                     out, probs, fp = self._engine.forward(topo, inputs[0], n, training=False, want_probs=cls)
@@ -819,11 +824,28 @@ class GraphConvModel(object):
                     vals = [outs[i] for i in output_idx]
                     if chunks is None:
                         chunks = [[] for _ in vals]
-                    for c, v in zip(chunks, vals):
-                        c.append(v)
+                        if n_rows is not None:
+                            nbytes = sum(r * v[0].numel() * 4 for r, v in zip(n_rows, vals))
+                            if nbytes <= _PINNED_RESULT_LIMIT:
+                                host = [torch.empty((r,) + tuple(v.shape[1:]), dtype=torch.float32, pin_memory=True)
+                                        for r, v in zip(n_rows, vals)]
+                                offs = [0] * len(vals)
+                    if host is not None:
+                        for i, v in enumerate(vals):
+                            if offs[i] + v.shape[0] > host[i].shape[0]:
+                                raise ValueError("predict: more output rows than the dataset announced")
+                            host[i][offs[i]:offs[i] + v.shape[0]].copy_(v, non_blocking=True)
+                            offs[i] += v.shape[0]
+                    else:
+                        for c, v in zip(chunks, vals):
+                            c.append(v)
                 if chunks is None:
                     return []
-                final = [torch.cat(c, dim=0).cpu().numpy() for c in chunks]
+                if host is not None:
+                    torch.cuda.current_stream().synchronize()
+                    final = [h[:o].numpy() for h, o in zip(host, offs)]      # views keep the pinned tensors alive
+                else:
+                    final = [torch.cat(c, dim=0).cpu().numpy() for c in chunks]
                 return final[0] if len(final) == 1 else final
             for batch in generator:
                 inputs, _, _ = self._prepare_batch(batch)
@@ -847,7 +869,7 @@ class GraphConvModel(object):
             lo, hi = shard_range(len(dataset), int(shard[0]), int(shard[1]))
             dataset = dataset.select_range(lo, hi)
         gen = self.default_generator(dataset, mode='predict', deterministic=True, pad_batches=False)
-        return self._predict(gen, self._prediction_outputs)
+        return self._predict(gen, self._prediction_outputs, n_rows=[len(dataset)] * len(self._prediction_outputs))
 
     def predict_on_batch(self, X):
         ds = PackedDataset(X) if isinstance(X, PackedMols) else NumpyDataset(X)
