@@ -13,14 +13,18 @@ import numpy as np
 from .synthetic import LazyTake, PackedMols
 
 
-def pad_batch(batch_size, X_b, y_b, w_b, ids_b):
+def pad_batch(batch_size, X_b, y_b, w_b, ids_b, lazy=False):
     """Pad by tiling the samples; only the first copy keeps its weights
-    (deepchem/data/datasets.py:142-218)."""
+    (deepchem/data/datasets.py:142-218).  ``lazy``: a packed shard is tiled as an index list (LazyTake) for the
+    consumer to gather."""
     n = len(X_b)
     if n == batch_size:
         return X_b, y_b, w_b, ids_b
     reps = np.arange(batch_size) % n
-    X_out = X_b.take(reps) if isinstance(X_b, (PackedMols, LazyTake)) else X_b[reps]
+    if isinstance(X_b, PackedMols):
+        X_out = X_b.take_lazy(reps) if lazy else X_b.take(reps)
+    else:
+        X_out = X_b.take(reps) if isinstance(X_b, LazyTake) else X_b[reps]
     y_out = None if y_b is None else y_b[reps]
     ids_out = ids_b[reps]
     if w_b is None:
@@ -73,7 +77,7 @@ class _ArrayDataset(object):
                 idx = perm[b * batch_size:min(n, (b + 1) * batch_size)]
                 batch = (self._take_X(idx, deterministic, lazy), self._y[idx], self._w[idx], self._ids[idx])
                 if pad_batches:
-                    batch = pad_batch(batch_size, *batch)
+                    batch = pad_batch(batch_size, *batch, lazy=lazy)
                 yield batch
 
 

@@ -468,8 +468,8 @@ class GraphConvModel(object):
 
         def batches():
             kw = {}
-            if not deterministic and isinstance(dataset, PackedDataset) and os.environ.get("DCGC_LAZY_TAKE", "1") != "0":
-                kw["lazy"] = True          # shuffled batches are gathered by the layout workers (batch_inputs)
+            if isinstance(dataset, PackedDataset) and os.environ.get("DCGC_LAZY_TAKE", "1") != "0":
+                kw["lazy"] = True          # shuffled / padded batches are gathered by the layout workers (batch_inputs)
             for (X_b, y_b, w_b, ids_b) in dataset.iterbatches(batch_size=self.batch_size, epochs=epochs,
                                                               deterministic=deterministic,
                                                               pad_batches=pad_batches, **kw):
