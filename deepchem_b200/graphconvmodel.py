@@ -534,18 +534,18 @@ class GraphConvModel(object):
 
     def batch_inputs(self, X_b, pinned=True):
         pinned = pinned and torch.cuda.is_available()     # host-only callers (tests) get plain memory
-        feat_slot = None
+        feat_slots = []
         if isinstance(X_b, LazyTake):
             # a shuffled batch: gather the molecules here (worker thread, GIL released in C), features straight into
             # page-locked staging memory — their exact int8 copy alone when the shard has one
             alloc = None
             if pinned:
                 def alloc(n_atoms, n_feat, dtype):
-                    nonlocal feat_slot
                     nbytes = n_atoms * n_feat * np.dtype(dtype).itemsize
-                    feat_slot = self._feature_staging(nbytes)
+                    fs = self._feature_staging(nbytes)
+                    feat_slots.append(fs)
                     tdt = torch.int8 if np.dtype(dtype) == np.int8 else torch.float32
-                    return feat_slot[0][:nbytes].view(tdt).view(n_atoms, n_feat)
+                    return fs[0][:nbytes].view(tdt).view(n_atoms, n_feat)
             X_b = X_b.resolve(alloc=alloc, prefer_i8=bool(pinned and _USE_I8), n_threads=1)
         packed = X_b if isinstance(X_b, PackedMols) else pack_convmols(X_b)
         n_seg = max(self.batch_size, packed.n_mols)
@@ -572,7 +572,7 @@ class GraphConvModel(object):
         # exact int8 copy of the same rows (PackedMols.compact): a quarter of the upload
         p8 = getattr(packed, "_pin_i8", None)
         inputs.packed_features_i8_pinned = p8 if (p8 is not None and tuple(p8.shape) == packed.features.shape) else None
-        inputs.feature_staging_slot = feat_slot
+        inputs.feature_staging_slots = feat_slots
         return inputs
 
     def _prepare_batch(self, batch, slot=None):
@@ -603,10 +603,12 @@ class GraphConvModel(object):
             x = ops.permute_rows(fdev, topo.perm, out=slot.get("x", n * ((f + 3) // 4 * 4), torch.float32))
         else:
             x = ops.permute_rows(feats.to(self.device, non_blocking=True), topo.perm)
-        fslot = getattr(inputs, "feature_staging_slot", None)
-        if fslot is not None:                  # the gathered features may be overwritten once this upload is done
-            fslot[1] = torch.cuda.Event()
-            fslot[1].record(torch.cuda.current_stream())
+        fslots = getattr(inputs, "feature_staging_slots", None)
+        if fslots:                             # the gathered features may be overwritten once this upload is done
+            fev = torch.cuda.Event()
+            fev.record(torch.cuda.current_stream())
+            for fs in fslots:
+                fs[1] = fev
         x._dcgc_zero_padded = True
         dev_inputs = topo.model_inputs(x, n_samples=int(inputs[3]))
 
