@@ -72,6 +72,10 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
                  int n_groups, int trans_w, const float* bias, int n1, int n2, const int32_t* tiles, int64_t n_tiles,
                  int64_t n_rows, int act, float* c1, int64_t ld_c1, float* c2, int64_t ld_c2, cudaStream_t st,
                  double* stats = nullptr, int* stats_chunks = nullptr);
+// early weight images (gemm_tc.cu): build on any stream, hand to the next dcgc_tc_gemm of this thread
+int64_t dcgc_tc_image_bytes(int nt, int k1, int k2, int N, int n_groups);
+int dcgc_tc_prep_weights(int nt, const float* w, int n_groups, int trans_w, int k1, int k2, int N, float* img, cudaStream_t st);
+void dcgc_tc_set_next_image(const float* img);
 #endif
 
 static inline int64_t dcgc_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }

@@ -860,6 +860,51 @@ int ensure_smem_attr() {
 
 }  // namespace
 
+// ---- split-weight images ----------------------------------------------------------------------------------
+// The image of one GEMM's weights ([G][n_tiles_n][chunks][hi | lo][128 x 32 swizzled]) is normally built by
+// tc_prep_image right in front of the GEMM (5 us on the critical path, 7 times per training step).  A caller that
+// knows its weights ahead (the fused engine: they only change in the Adam launch) can build the images early, on
+// another stream, with dcgc_tc_prep_weights and hand each one to the matching GEMM with dcgc_tc_set_next_image.
+namespace {
+struct ImgShape { int k1_pad, k_pad, n_tiles_n, chunks, b_tiles; size_t bytes; };
+ImgShape img_shape(int nt, int k1, int k2, int N, int n_groups) {
+  ImgShape s;
+  s.k1_pad = (k1 + TC_BK - 1) / TC_BK * TC_BK;
+  s.k_pad = s.k1_pad + (k2 + TC_BK - 1) / TC_BK * TC_BK;
+  s.n_tiles_n = (N + TC_BN - 1) / TC_BN;
+  s.chunks = s.k_pad / TC_BK;
+  s.b_tiles = nt == 3 ? 2 : 1;
+  s.bytes = (size_t)n_groups * s.n_tiles_n * (s.chunks > 0 ? s.chunks : 1) * s.b_tiles * TC_TILE_BYTES;
+  return s;
+}
+int launch_prep(int nt, const float* w, int n_groups, int trans_w, int k1, int k2, int N, float* img, cudaStream_t st) {
+  const ImgShape sh = img_shape(nt, k1, k2, N, n_groups);
+  if (sh.chunks <= 0 || N <= 0) return DCGC_OK;
+  ImgArgs ia{};
+  ia.src = w; ia.img = img; ia.n = N; ia.k1 = k1; ia.k2 = k2; ia.k1_pad = sh.k1_pad; ia.trans = trans_w;
+  ia.n_tiles = sh.n_tiles_n; ia.chunks = sh.chunks;
+  if (trans_w) { ia.src_ld = N; ia.src_group_stride = (int64_t)(k1 + k2) * N; }
+  else { ia.src_ld = k1; ia.src_group_stride = (int64_t)N * k1; }
+  dim3 pgrid((unsigned)sh.chunks * 4, (unsigned)sh.n_tiles_n, (unsigned)n_groups);
+  if (nt == 3) tc_prep_image<3><<<pgrid, 256, 0, st>>>(ia);
+  else tc_prep_image<1><<<pgrid, 256, 0, st>>>(ia);
+  DCGC_CUDA_LAUNCH_CHECK("tc_prep_image");
+  return DCGC_OK;
+}
+thread_local const float* tls_next_img = nullptr;
+}  // namespace
+
+// k2 = 0 when the GEMM has no second operand.  Bytes are 1024-aligned sizes (whole 16 KB tiles).
+int64_t dcgc_tc_image_bytes(int nt, int k1, int k2, int N, int n_groups) { return (int64_t)img_shape(nt, k1, k2, N, n_groups).bytes; }
+int dcgc_tc_prep_weights(int nt, const float* w, int n_groups, int trans_w, int k1, int k2, int N, float* img, cudaStream_t st) {
+  DCGC_CHECK_ARG(w && img && (reinterpret_cast<uintptr_t>(img) & 127) == 0, "dcgc_tc_prep_weights: bad pointer");
+  int st_ = ensure_smem_attr();
+  if (st_ != DCGC_OK) return st_;
+  return launch_prep(nt, w, n_groups, trans_w, k1, k2, N, img, st);
+}
+// One-shot, per thread: the next dcgc_tc_gemm of this thread reads this image instead of building one.
+void dcgc_tc_set_next_image(const float* img) { tls_next_img = img; }
+
 // Called by dcgc_group_gemm_fwd / _dgrad / dcgc_linear_* in the tensor-core modes; nt = 3 (DCGC_GEMM_TF32X3) or
 // 1 (DCGC_GEMM_BF16).
 //   trans_w = 1: w is [G][k1+k2][n] (forward);  trans_w = 0: w is [G][n1+n2][k1] (dgrad / nn.Linear forward)
@@ -868,6 +913,8 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
                  int64_t n_rows, int act, float* c1, int64_t ld_c1, float* c2, int64_t ld_c2, cudaStream_t st,
                  double* stats, int* stats_chunks) {
   const int N = n1 + n2;
+  const float* ready_img = tls_next_img;     // consumed (and cleared) on every path, used or not
+  tls_next_img = nullptr;
   if (stats_chunks) *stats_chunks = 0;
   const int64_t row_tiles = tiles ? n_tiles : (n_rows + TC_BM - 1) / TC_BM;
   if (row_tiles == 0 || N == 0) return DCGC_OK;   // *stats_chunks == 0: the caller's finalize sees no partials
@@ -877,21 +924,15 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
   const int k_pad = k1_pad + k2_pad;
   if (row_tiles < (1 << 30)) {
     const int n_tiles_n = (N + TC_BN - 1) / TC_BN, chunks = k_pad / TC_BK;
-    float* img = nullptr;
-    const int b_tiles = nt == 3 ? 2 : 1;
-    st_ = prep_scratch(st, (size_t)n_groups * n_tiles_n * (chunks > 0 ? chunks : 1) * b_tiles * TC_TILE_BYTES, &img);
-    if (st_ != DCGC_OK) return st_;
+    float* img = const_cast<float*>(ready_img);
     static const int knockout = [] { const char* e = getenv("DCGC_TC_KNOCKOUT"); return e ? atoi(e) : 0; }();
-    if (chunks > 0 && !(knockout & 128)) {
-      ImgArgs ia{};
-      ia.src = w; ia.img = img; ia.n = N; ia.k1 = k1; ia.k2 = a2 ? k2 : 0; ia.k1_pad = k1_pad; ia.trans = trans_w;
-      ia.n_tiles = n_tiles_n; ia.chunks = chunks;
-      if (trans_w) { ia.src_ld = N; ia.src_group_stride = (int64_t)(k1 + k2) * N; }
-      else { ia.src_ld = k1; ia.src_group_stride = (int64_t)N * k1; }
-      dim3 pgrid((unsigned)chunks * 4, (unsigned)n_tiles_n, (unsigned)n_groups);
-      if (nt == 3) tc_prep_image<3><<<pgrid, 256, 0, st>>>(ia);
-      else tc_prep_image<1><<<pgrid, 256, 0, st>>>(ia);
-      DCGC_CUDA_LAUNCH_CHECK("tc_prep_image");
+    if (img == nullptr) {
+      st_ = prep_scratch(st, img_shape(nt, k1, a2 ? k2 : 0, N, n_groups).bytes, &img);
+      if (st_ != DCGC_OK) return st_;
+      if (chunks > 0 && !(knockout & 128)) {
+        st_ = launch_prep(nt, w, n_groups, trans_w, k1, a2 ? k2 : 0, N, img, st);
+        if (st_ != DCGC_OK) return st_;
+      }
     }
     TcArgs3 q3{};
     TcArgs& p3 = q3.a;

@@ -17,6 +17,9 @@
 
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+
 #include "common.h"
 
 namespace {
@@ -492,7 +495,36 @@ struct Saved {
   float* b11[DCGC_MODEL_MAX_LAYERS];
   double* part;    // column-moment partials
   int n_chunks;
+  // weight images built ahead on the side stream (train step, tensor-core modes; null = built in front of the GEMM)
+  const float* img_fwd[DCGC_MODEL_MAX_LAYERS];
+  const float* img_dense;
+  cudaEvent_t img_fwd_ready;   // main stream waits on it before the first GEMM
 };
+
+// ---- early weight images: one side stream + three events per device, created on first use
+struct SideStream { cudaStream_t s; cudaEvent_t e0, e1, e2; };
+std::mutex g_side_mu;
+std::map<int, SideStream> g_side;
+int side_stream(SideStream** out) {
+  int dev = 0;
+  DCGC_CUDA_CALL(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  auto it = g_side.find(dev);
+  if (it == g_side.end()) {
+    SideStream ss{};
+    DCGC_CUDA_CALL(cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking));
+    DCGC_CUDA_CALL(cudaEventCreateWithFlags(&ss.e0, cudaEventDisableTiming));
+    DCGC_CUDA_CALL(cudaEventCreateWithFlags(&ss.e1, cudaEventDisableTiming));
+    DCGC_CUDA_CALL(cudaEventCreateWithFlags(&ss.e2, cudaEventDisableTiming));
+    it = g_side.emplace(dev, ss).first;
+  }
+  *out = &it->second;
+  return DCGC_OK;
+}
+bool early_images_on() {
+  static const bool on = [] { const char* e = getenv("DCGC_EARLY_IMAGES"); return e && e[0] == '1'; }();   // opt-in until measured
+  return on;
+}
 
 int check_topo(const dcgc_topology* t) {
   DCGC_CHECK_ARG(t, "dcgc_gcmodel: null topology");
@@ -601,12 +633,15 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
       RET_IF(dcgc_gather_sum_bucketed(h, ld, t->deg_count, t->col_idx, N, fp, nullptr, 0, sv.s[l], fp, st));
     const bool fuse_stats = cfg->batch_norm && training && dcgc_tc_terms(cfg->gemm_mode) != 0;
     int32_t fused = -1;
+    if (l == 0 && sv.img_fwd_ready) DCGC_CUDA_CALL(cudaStreamWaitEvent(st, sv.img_fwd_ready, 0));
+    dcgc_tc_set_next_image(sv.img_fwd[l]);
     if (fuse_stats)
       RET_IF(dcgc_group_gemm_fwd_stats(cfg->gemm_mode, h, ld, fp, sv.s[l], fp, fp, params + lo.conv_w[l], sv.b11[l], c,
                                        t->tiles, t->n_tiles, 128, N, DCGC_ACT_RELU, sv.y[l], c, sv.part, &fused, st));
     else
       RET_IF(dcgc_group_gemm_fwd(cfg->gemm_mode, h, ld, fp, sv.s[l], fp, fp, params + lo.conv_w[l], sv.b11[l], c,
                                  t->tiles, t->n_tiles, 128, N, DCGC_ACT_RELU, sv.y[l], c, st));
+    dcgc_tc_set_next_image(nullptr);      // (a call that returned before its GEMM must not leak the image)
     const float *scale = nullptr, *shift = nullptr;
     if (cfg->batch_norm) {
       RET_IF(bn_forward(cfg, lo, l, sv.y[l], c, N, c, params, bn_running, training, sv, st, fused));
@@ -621,12 +656,14 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
   }
   // ---- atom-level dense + ReLU (+BN folded into the gather), GraphGather(tanh), head
   int32_t fused_d = -1;
+  dcgc_tc_set_next_image(sv.img_dense);
   if (cfg->batch_norm && training && dcgc_tc_terms(cfg->gemm_mode) != 0)
     RET_IF(dcgc_linear_fwd_stats(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], params + lo.dense_w,
                                  params + lo.dense_b, D, N, DCGC_ACT_RELU, sv.z, D, sv.part, &fused_d, st));
   else
     RET_IF(dcgc_linear_fwd(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], params + lo.dense_w, params + lo.dense_b, D,
                            N, DCGC_ACT_RELU, sv.z, D, st));
+  dcgc_tc_set_next_image(nullptr);
   const float *scale = nullptr, *shift = nullptr;
   if (cfg->batch_norm) {
     RET_IF(bn_forward(cfg, lo, L, sv.z, D, N, D, params, bn_running, training, sv, st, fused_d));
@@ -698,6 +735,14 @@ extern "C" int64_t dcgc_gcmodel_workspace_bytes(const dcgc_gcmodel_config* cfg, 
   wg = wg > bd ? wg : bd;
   bytes += wg;
   bytes += (int64_t)(L + 1) * 16 * wmax * 4 + (int64_t)L * DCGC_N_DEG * wmax * 8 + 3 * (int64_t)wmax * 4;
+  const int nt = dcgc_tc_terms(cfg->gemm_mode);
+  if (nt != 0) {   // early weight images of the train step
+    for (int l = 0; l < L; ++l) {
+      bytes += dcgc_tc_image_bytes(nt, lo.fp[l], lo.fp[l], cfg->widths[l], DCGC_N_DEG) + 256;
+      if (l > 0) bytes += dcgc_tc_image_bytes(nt, cfg->widths[l], 0, 2 * lo.fp[l], DCGC_N_DEG) + 256;
+    }
+    bytes += dcgc_tc_image_bytes(nt, lo.f[L], 0, D, 1) + dcgc_tc_image_bytes(nt, D, 0, lo.f[L], 1) + 512;
+  }
   return bytes + 256 * 64;  // alignment slack for every carve
 }
 
@@ -746,7 +791,42 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
   const int64_t N = t->n_atoms, S = t->n_segments;
   Arena ws{(char*)workspace, 0, workspace_bytes};
   Saved sv{};
+  // ---- weight images of all seven GEMMs, built now on the side stream (the weights only change in the Adam launch,
+  // which precedes this call on `st`): they run beside the first gather-sum instead of in front of every GEMM
+  const float* img_dgrad[DCGC_MODEL_MAX_LAYERS] = {};
+  const float* img_dense_dgrad = nullptr;
+  SideStream* side = nullptr;
+  const int nt = dcgc_tc_terms(cfg->gemm_mode);
+  if (nt != 0 && early_images_on() && N > 0) {
+    RET_IF(side_stream(&side));
+    float* imf[DCGC_MODEL_MAX_LAYERS]; float* imd[DCGC_MODEL_MAX_LAYERS] = {};
+    for (int l = 0; l < L; ++l) {
+      imf[l] = ws.take<float>(dcgc_tc_image_bytes(nt, lo.fp[l], lo.fp[l], cfg->widths[l], DCGC_N_DEG) / 4);
+      if (l > 0) imd[l] = ws.take<float>(dcgc_tc_image_bytes(nt, cfg->widths[l], 0, 2 * lo.fp[l], DCGC_N_DEG) / 4);
+    }
+    float* im_dense = ws.take<float>(dcgc_tc_image_bytes(nt, lo.f[L], 0, D, 1) / 4);
+    float* im_dense_d = ws.take<float>(dcgc_tc_image_bytes(nt, D, 0, lo.f[L], 1) / 4);
+    if (!ws.ok) {
+      dcgc_set_error("dcgc_gcmodel_train_step: workspace too small for the weight images");
+      return DCGC_ERR_NOMEM;
+    }
+    DCGC_CUDA_CALL(cudaEventRecord(side->e0, st));
+    DCGC_CUDA_CALL(cudaStreamWaitEvent(side->s, side->e0, 0));
+    for (int l = 0; l < L; ++l)       // forward: [X | S] . W[g], W stored [G][2 fp][c]
+      RET_IF(dcgc_tc_prep_weights(nt, params + lo.conv_w[l], DCGC_N_DEG, 1, lo.fp[l], lo.fp[l], cfg->widths[l], imf[l], side->s));
+    RET_IF(dcgc_tc_prep_weights(nt, params + lo.dense_w, 1, 0, lo.f[L], 0, D, im_dense, side->s));   // nn.Linear layout
+    DCGC_CUDA_CALL(cudaEventRecord(side->e1, side->s));
+    RET_IF(dcgc_tc_prep_weights(nt, params + lo.dense_w, 1, 1, D, 0, lo.f[L], im_dense_d, side->s)); // dx = g . w
+    for (int l = L - 1; l >= 1; --l)  // dgrad: G . W[g]^T, the same W read as [G][2 fp][c] = [n1 + n2][k1]
+      RET_IF(dcgc_tc_prep_weights(nt, params + lo.conv_w[l], DCGC_N_DEG, 0, cfg->widths[l], 0, 2 * lo.fp[l], imd[l], side->s));
+    DCGC_CUDA_CALL(cudaEventRecord(side->e2, side->s));
+    for (int l = 0; l < L; ++l) { sv.img_fwd[l] = imf[l]; img_dgrad[l] = imd[l]; }
+    sv.img_dense = im_dense;
+    img_dense_dgrad = im_dense_d;
+    sv.img_fwd_ready = side->e1;
+  }
   RET_IF(forward_impl(cfg, lo, t, x, ld_x, n_samples, params, bn_running, 1, 1, ws, sv, st));
+  if (side) DCGC_CUDA_CALL(cudaStreamWaitEvent(st, side->e2, 0));     // the backward's images (long done by now)
   if (g_forward_event) {
     cudaEvent_t ev = g_forward_event;
     g_forward_event = nullptr;
@@ -848,7 +928,9 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
   RET_IF(bn_backward(L, sv.z, D, -1));
   RET_IF(dcgc_linear_wgrad(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], dA, D, D, N, grads + lo.dense_w,
                            grads + lo.dense_b, wg, wg_bytes, st));
+  dcgc_tc_set_next_image(img_dense_dgrad);
   RET_IF(dcgc_linear_dgrad(cfg->gemm_mode, dA, D, D, params + lo.dense_w, lo.f[L], N, dP, lo.f[L], st));
+  dcgc_tc_set_next_image(nullptr);
 
   // ---- conv stack backward
   for (int l = L - 1; l >= 0; --l) {
@@ -873,8 +955,10 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
     DCGC_CUDA_LAUNCH_CHECK("conv_bias_unpack");
     if (l > 0) {
       // [dP | d2] = G . W^T, then dP += transposed gather of d2
+      dcgc_tc_set_next_image(img_dgrad[l]);
       RET_IF(dcgc_group_gemm_dgrad(cfg->gemm_mode, dA, c, c, params + lo.conv_w[l], fp, fp, t->tiles, t->n_tiles, 128,
                                    N, dP, fp, d2, fp, st));
+      dcgc_tc_set_next_image(nullptr);
       if (use_mg(t, fp, 0, d2, dP))
         RET_IF(dcgc_mg_gather_sum(d2, fp, t, 1, fp, dP, fp, dP, fp, st));
       else if (t->symmetric)
