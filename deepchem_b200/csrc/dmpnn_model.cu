@@ -60,6 +60,72 @@ __global__ void __launch_bounds__(kT) mask_add_kernel(float4* __restrict__ ds, c
   v.x += t.x > 0.f ? m.x : 0.f; v.y += t.y > 0.f ? m.y : 0.f; v.z += t.z > 0.f ? m.z : 0.f; v.w += t.w > 0.f ? m.w : 0.f;
   ds[i] = v;
 }
+// CSR gather-sum with the element-wise neighbours of the D-MPNN step folded in (one thread per 16-byte column group
+// of one output row, entries summed in index order exactly as dcgc_gather_sum does):
+//   RELU_IN  the source rows are read through ReLU        (message = act(input), layers.py:1624, never materialised)
+//   MODE 0   out = sum
+//   MODE 1   out = (mask > 0) ? sum : 0                   (ReLU backward of h_message on the scattered gradient)
+//   MODE 2   out = addend + ((mask > 0) ? sum : 0)        (d input = d s + act'(input) * d message; out may alias addend)
+template <bool RELU_IN, int MODE>
+__global__ void __launch_bounds__(kT) fused_gather_kernel(const float* __restrict__ x, const int32_t* __restrict__ row_ptr,
+                                                          const int32_t* __restrict__ idx, int64_t n_rows, int width,
+                                                          const float* __restrict__ mask, const float* addend,
+                                                          float* out) {
+  const int groups = width >> 2;
+  const int64_t t = (int64_t)blockIdx.x * kT + threadIdx.x;
+  const int64_t row = t / groups;
+  if (row >= n_rows) return;
+  const int c = (int)(t - row * groups) * 4;
+  int e = __ldg(row_ptr + row);
+  const int e1 = __ldg(row_ptr + row + 1);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto add = [&](float4 v) {
+    if (RELU_IN) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  };
+  const float* xc = x + c;
+  for (; e + 4 <= e1; e += 4) {      // four independent row loads in flight
+    const int j0 = __ldg(idx + e), j1 = __ldg(idx + e + 1), j2 = __ldg(idx + e + 2), j3 = __ldg(idx + e + 3);
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(xc + (int64_t)j0 * width));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(xc + (int64_t)j1 * width));
+    const float4 v2 = __ldg(reinterpret_cast<const float4*>(xc + (int64_t)j2 * width));
+    const float4 v3 = __ldg(reinterpret_cast<const float4*>(xc + (int64_t)j3 * width));
+    add(v0); add(v1); add(v2); add(v3);
+  }
+  const int rem = e1 - e;
+  if (rem > 0) {
+    const int j0 = __ldg(idx + e), j1 = rem > 1 ? __ldg(idx + e + 1) : j0, j2 = rem > 2 ? __ldg(idx + e + 2) : j0;
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(xc + (int64_t)j0 * width));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(xc + (int64_t)j1 * width));
+    const float4 v2 = __ldg(reinterpret_cast<const float4*>(xc + (int64_t)j2 * width));
+    add(v0);
+    if (rem > 1) add(v1);
+    if (rem > 2) add(v2);
+  }
+  const int64_t o = row * width + c;
+  if (MODE != 0) {
+    const float4 m = *reinterpret_cast<const float4*>(mask + o);
+    acc.x = m.x > 0.f ? acc.x : 0.f; acc.y = m.y > 0.f ? acc.y : 0.f;
+    acc.z = m.z > 0.f ? acc.z : 0.f; acc.w = m.w > 0.f ? acc.w : 0.f;
+  }
+  if (MODE == 2) {
+    const float4 a = *reinterpret_cast<const float4*>(addend + o);
+    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+  }
+  *reinterpret_cast<float4*>(out + o) = acc;
+}
+
+template <bool RELU_IN, int MODE>
+int fused_gather(const float* x, const int32_t* row_ptr, const int32_t* idx, int64_t n_rows, int width, const float* mask,
+                 const float* addend, float* out, cudaStream_t st) {
+  if (n_rows == 0) return DCGC_OK;
+  DcgcProfScope prof_scope("dcgc_gather_sum", st);
+  fused_gather_kernel<RELU_IN, MODE><<<blocks_for(n_rows * (width >> 2)), kT, 0, st>>>(x, row_ptr, idx, n_rows, width, mask,
+                                                                                      addend, out);
+  DCGC_CUDA_LAUNCH_CHECK("dmpnn fused_gather");
+  return DCGC_OK;
+}
+
 // dst[c, r] = src[r, c]   (nn.Linear weight [n, k] <-> the [k, n] layout of the two-operand GEMM entry points)
 __global__ void __launch_bounds__(kT) transpose_kernel(const float* __restrict__ src, int rows, int cols,
                                                        float* __restrict__ dst) {
@@ -207,14 +273,13 @@ int forward_impl(const dcgc_dmpnn_model_config* c, const Layout& lo, const dcgc_
   const int64_t r4 = R * H / 4;
   // input = W_i(f_ini)  (layers.py:1622);  message = act(input)  (:1624)
   RET_IF(dcgc_linear_fwd(mode, fini, ld_fi, fi, params + lo.w_i, nullptr, H, R, DCGC_ACT_NONE, w.r0, H, st));
-  if (r4 > 0) {
-    relu_copy_kernel<<<blocks_for(r4), kT, 0, st>>>(reinterpret_cast<const float4*>(w.r0), reinterpret_cast<float4*>(w.r1), r4);
-    DCGC_CUDA_LAUNCH_CHECK("dmpnn relu_copy");
-  }
-  // message = message[mapping].sum(1), depth - 1 times  (:1627-1629)
+  // message = message[mapping].sum(1), depth - 1 times  (:1627-1629); the first gather reads act(input) on the fly
   float *src = w.r1, *dst = w.r2;
   for (int d = 1; d < c->depth; ++d) {
-    RET_IF(dcgc_gather_sum(src, H, t->map_ptr, t->map_idx, R, H, nullptr, 0, dst, H, st));
+    if (d == 1)
+      RET_IF((fused_gather<true, 0>(w.r0, t->map_ptr, t->map_idx, R, H, nullptr, nullptr, dst, st)));
+    else
+      RET_IF(dcgc_gather_sum(src, H, t->map_ptr, t->map_idx, R, H, nullptr, 0, dst, H, st));
     float* tmp = src; src = dst; dst = tmp;
   }
   // src == msg_final; h_message = act(input + W_h(message))  (:1630-1633, only the last product is live)
@@ -389,21 +454,18 @@ extern "C" int dcgc_dmpnn_model_train_step(const dcgc_dmpnn_model_config* cfg, c
   float* mf = msg_final(w, cfg->depth);   // message after the gathers (input of W_h)
   float* mo = msg_other(w, cfg->depth);   // held W_h(message); free now
   // d(h_message) = scatter of d(m2a) over a2b  -> mo;  d(pre-activation) = mask by h > 0
-  RET_IF(dcgc_gather_sum(w.a1, H, t->a2b_t_ptr, t->a2b_t_idx, R, H, nullptr, 0, mo, H, st));
-  relu_mask_kernel<<<blocks_for(r4), kT, 0, st>>>(reinterpret_cast<float4*>(mo), reinterpret_cast<const float4*>(w.r3), r4);
-  DCGC_CUDA_LAUNCH_CHECK("dmpnn relu_mask bonds");
+  RET_IF((fused_gather<false, 1>(w.a1, t->a2b_t_ptr, t->a2b_t_idx, R, H, w.r3, nullptr, mo, st)));
   RET_IF(dcgc_linear_wgrad(mode, mf, H, H, mo, H, H, R, grads + lo.w_h, nullptr, w.wgrad_ws, w.wgrad_bytes, st));
   // d(message) = ds . W_h  -> r3 (h is not needed any more), then depth - 1 transposed gathers r3 -> mf -> r3 ...
   RET_IF(dcgc_linear_dgrad(mode, mo, H, H, params + lo.w_h, H, R, w.r3, H, st));
   float *src = w.r3, *dst = mf;
   for (int d = 1; d < cfg->depth; ++d) {
-    RET_IF(dcgc_gather_sum(src, H, t->map_t_ptr, t->map_t_idx, R, H, nullptr, 0, dst, H, st));
+    if (d == cfg->depth - 1)   // the last one lands on message_0 = act(input): d(input) = ds + (input > 0) * it, in place in mo
+      RET_IF((fused_gather<false, 2>(src, t->map_t_ptr, t->map_t_idx, R, H, w.r0, mo, mo, st)));
+    else
+      RET_IF(dcgc_gather_sum(src, H, t->map_t_ptr, t->map_t_idx, R, H, nullptr, 0, dst, H, st));
     float* tmp = src; src = dst; dst = tmp;
   }
-  // d(input) = ds + (input > 0) * d(message_0)   (in place in mo)
-  mask_add_kernel<<<blocks_for(r4), kT, 0, st>>>(reinterpret_cast<float4*>(mo), reinterpret_cast<const float4*>(src),
-                                                reinterpret_cast<const float4*>(w.r0), r4);
-  DCGC_CUDA_LAUNCH_CHECK("dmpnn mask_add");
   RET_IF(dcgc_linear_wgrad(mode, f_ini, ld_fi, fi, mo, H, H, R, grads + lo.w_i, nullptr, w.wgrad_ws, w.wgrad_bytes, st));
   return DCGC_OK;
 }

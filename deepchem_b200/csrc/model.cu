@@ -522,7 +522,8 @@ int side_stream(SideStream** out) {
   return DCGC_OK;
 }
 bool early_images_on() {
-  static const bool on = [] { const char* e = getenv("DCGC_EARLY_IMAGES"); return e && e[0] == '1'; }();   // opt-in until measured
+  // measured (profiles/r3i_*): forward GEMM scopes 239 -> 210 us, dgrad 141 -> 131 us, step 1.2445 -> 1.2333 ms
+  static const bool on = [] { const char* e = getenv("DCGC_EARLY_IMAGES"); return !(e && e[0] == '0'); }();
   return on;
 }
 
