@@ -270,13 +270,16 @@ def run_ours(args):
 
     # ---- per-scope pass (rank 0, after the timed region, not part of it): the library's own CUDA-event scopes around
     # every kernel family for 5 more resident steps -> the `kernels` table of the JSON line (and --breakdown FILE)
+    # EVERY rank runs the extra steps (a data-parallel step holds a collective: ranks must stay in lockstep); only
+    # rank 0 brackets them with the event scopes
     kernels = None
+    nb = 5
     if rank == 0:
         ops.profile_begin("*")
-        nb = 5
-        for i in range(nb):
-            step_resident(i)
-        torch.cuda.synchronize()
+    for i in range(nb):
+        step_resident(i)
+    torch.cuda.synchronize()
+    if rank == 0:
         rep = ops.profile_report()
         tot = sum(v[0] for v in rep.values())
         kernels = kernel_table(rep, nb, [r[0][1]._dcgc_topology for r in resident], B)
