@@ -1,7 +1,13 @@
 """Data-parallel D-MPNN through the fused engine on 2 GPUs (torchrun): each rank trains on its half of every global batch
-with ONE all-reduce of the flat gradient slab per step; rank 0 also trains a single-GPU replica on the whole batch.  Equal
-shards and a mean loss make the averaged gradient exact, so the parameters must agree after every step.  Also times the
-data-parallel step (max over ranks, CUDA events).
+with ONE all-reduce of the flat gradient slab per step; rank 0 also trains a single-GPU replica on the whole batch and an
+in-process emulation of the two ranks (two engines, slabs added by hand, no NCCL).  Equal shards and a mean loss make the
+averaged gradient exact: the check is (1) the first step's averaged gradient slab equals the whole-batch gradient within
+1e-5 of its largest entry, and (2) the data-parallel parameters are bit-identical to the emulation after every step, i.e.
+the exchange adds nothing but the sum.  The parameters of the whole-batch replica are reported but not asserted after the
+first step: Adam divides by |g| + 1e-8, so entries with |g| <= 1e-8 turn summation-order noise of 1e-7 into differences
+of a fraction of the learning rate that grow step by step (1.5e-4 -> 1.8e-2 of the largest weight over 4 steps, measured;
+the same happens between two single-GPU runs that split the batch differently).  Also times the data-parallel step (max
+over ranks, CUDA events).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 scripts/dmpnn_dp2.py
 """
@@ -33,15 +39,69 @@ inputs, labels, weights = m._prepare_batch(next(m.default_generator(mine, determ
 if rank == 0:
     rin, rl, rw = ref._prepare_batch(next(ref.default_generator(GraphDataset(pg, y, w), deterministic=True)))
 worst = 0.0
+detail = []
+# emulation of the two ranks inside rank 0's process (no NCCL): engines ea / eb take one half each, the gradient
+# slabs are added by hand, Adam runs with scale 1/2 on ea and the parameters are copied to eb
+emu = None
+if rank == 0 and os.environ.get("DP2_EMULATE", "1") == "1":
+    emu = []
+    for r in range(world):
+        torch.manual_seed(0)
+        e = DMPNNModel(device=dev, n_tasks=12, batch_size=B, gemm_mode="tf32x3")
+        e.model.load_state_dict({k: v.clone() for k, v in m.model.state_dict().items()})
+        ds_r = GraphDataset(pg.slice(r * B, (r + 1) * B), y[r * B:(r + 1) * B], w[r * B:(r + 1) * B])
+        emu.append((e, e._prepare_batch(next(e.default_generator(ds_r, deterministic=True)))))
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / max(float(b.abs().max()), 1e-12))
+
+
 for step in range(4):
+    # gradient of this step's forward/backward, before the exchange: the first-step gradients are comparable
     m._train_step(inputs, labels, weights)
     if rank == 0:
         ref._train_step(rin, rl, rw)
         sa, sb = m.model.state_dict(), ref.model.state_dict()
+        row = {"step": step}
         for k in sa:
-            d = float((sa[k] - sb[k]).abs().max() / max(float(sb[k].abs().max()), 1e-12))
+            d = rel(sa[k], sb[k])
+            row[k] = d
             worst = max(worst, d)
+        row["grad_slab_dp_vs_ref_x_world"] = rel(m._engine.grads / world, ref._engine.grads)
+        if emu is not None:
+            for e, (ei, el, ew) in emu:
+                topo = ei.topology
+                yy = el[0].reshape(topo.n_mols, -1).contiguous()
+                ww = ew[0].reshape(topo.n_mols, -1).expand_as(yy).contiguous()
+                e._engine.train_step(topo, ei['atom_features'], ei['f_ini_atoms_bonds'], yy, ww)
+            ea, eb = emu[0][0]._engine, emu[1][0]._engine
+            ea.grads += eb.grads
+            row["grad_slab_emu_vs_ref"] = rel(ea.grads / world, ref._engine.grads)
+            row["grad_slab_emu_vs_dp"] = rel(ea.grads, m._engine.grads)
+            ea.adam_step(1.0 / world)
+            eb.params.copy_(ea.params)
+            row["params_emu_vs_ref"] = rel(ea.params, ref._engine.params)
+            row["params_emu_vs_dp"] = rel(ea.params, m._engine.params)
+        detail.append(row)
 torch.cuda.synchronize()
+
+
+def verdict():
+    g0 = detail[0]["grad_slab_dp_vs_ref_x_world"]
+    emu_exact = emu is None or all(r["params_emu_vs_dp"] == 0.0 and r["grad_slab_emu_vs_dp"] == 0.0 for r in detail)
+    return {"first_step_grad_rel_diff_vs_whole_batch": g0, "dp_bit_identical_to_emulation": emu_exact,
+            "max_rel_param_diff_vs_whole_batch_replica_4_adam_steps": worst, "ok": bool(g0 < 1e-5 and emu_exact)}
+
+
+if rank == 0:
+    print(json.dumps({"detail": detail}), flush=True)
+if os.environ.get("DP2_NO_TIMING") == "1":
+    if rank == 0:
+        print(json.dumps(verdict()), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0)
 # timing: B = 4096 per rank
 B2 = 4096
 pg2 = make_graphs(B2, seed=20 + rank, shape="qm9")
@@ -61,8 +121,9 @@ dist.barrier(); torch.cuda.synchronize()
 t = torch.tensor([e0.elapsed_time(e1) / 20], device=dev, dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print(json.dumps({"check": "2-rank data-parallel D-MPNN engine vs single-GPU replica on the whole batch, 4 Adam steps",
-                      "max_rel_param_diff": worst, "ok": worst < 2e-5,
-                      "dp_ms_per_step": float(t), "molecules_per_s": world * B2 / float(t) * 1e3, "n_gpus": world}), flush=True)
-    assert worst < 2e-5, worst
+    v = verdict()
+    v.update({"check": "2-rank data-parallel D-MPNN engine vs whole-batch replica and in-process emulation, 4 Adam steps",
+              "dp_ms_per_step": float(t), "molecules_per_s": world * B2 / float(t) * 1e3, "n_gpus": world})
+    print(json.dumps(v), flush=True)
+    assert v["ok"], v
 dist.destroy_process_group()
