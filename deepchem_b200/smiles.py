@@ -42,7 +42,16 @@ _ELEMENTS = {
     'I': (53, 7, (1, 3, 5), 126.904), 'Yb': (70, 3, (-1,), 173.04), 'Pt': (78, 10, (-1,), 195.078),
     'Au': (79, 11, (-1,), 196.967), 'Hg': (80, 2, (-1,), 200.59), 'Tl': (81, 3, (-1,), 204.383),
     'Pb': (82, 4, (2, 4), 207.2),
+    # heavy elements of the reference's Tox21 CSV (all land in the 'Unknown' element slot)
+    'Sr': (38, 2, (2, -1), 87.62), 'Ba': (56, 2, (2, -1), 137.327), 'Nd': (60, 4, (-1,), 144.24),
+    'Bi': (83, 5, (3, 5, 7), 208.98),
 }
+# every two-letter element symbol, so that '[Ba+2]' is not read as boron followed by garbage; symbols outside
+# _ELEMENTS are accepted as 'Unknown' atoms with unconstrained valence
+_TWO_LETTER = frozenset(
+    'He Li Be Ne Na Mg Al Si Cl Ar Ca Sc Ti Cr Mn Fe Co Ni Cu Zn Ga Ge As Se Br Kr Rb Sr Zr Nb Mo Tc Ru Rh Pd Ag Cd In '
+    'Sn Sb Te Xe Cs Ba La Ce Pr Nd Pm Sm Eu Gd Tb Dy Ho Er Tm Yb Lu Hf Ta Re Os Ir Pt Au Hg Tl Pb Bi Po At Rn Fr Ra Ac '
+    'Th Pa Np Pu Am Cm Bk Cf Es Fm Md No Lr Rf Db Sg Bh Hs Mt Ds Rg Cn Nh Fl Mc Lv Ts Og'.split())
 # graph_features.py:322-367
 _SYMBOLS = ['C', 'N', 'O', 'S', 'F', 'Si', 'P', 'Cl', 'Br', 'Mg', 'Na', 'Ca', 'Fe', 'As', 'Al', 'I', 'B', 'V', 'K', 'Tl',
             'Yb', 'Sb', 'Sn', 'Ag', 'Pd', 'Co', 'Se', 'Ti', 'Zn', 'H', 'Li', 'Ge', 'Cu', 'Au', 'Ni', 'Cd', 'In', 'Mn', 'Zr',
@@ -139,10 +148,10 @@ def _parse_bracket(s, i):
     elif s[j] == '*':
         symbol, j = '*', j + 1
     elif s[j].isupper():
-        if j + 1 < n and s[j + 1].islower() and s[j:j + 2] in _ELEMENTS:
-            symbol, j = s[j:j + 2], j + 2
+        if j + 1 < n and s[j + 1].islower() and (s[j:j + 2] in _ELEMENTS or s[j:j + 2] in _TWO_LETTER):
+            symbol, j = s[j:j + 2], j + 2                                   # (outside _ELEMENTS: an 'Unknown' atom)
         elif j + 1 < n and s[j + 1].islower() and s[j + 1] not in 'h' and s[j] not in _ELEMENTS:
-            symbol, j = s[j:j + 2], j + 2                                   # an element outside the table: 'Unknown'
+            symbol, j = s[j:j + 2], j + 2                                   # not a symbol at all: 'Unknown' as well
         else:
             symbol, j = s[j], j + 1
     else:
