@@ -153,7 +153,12 @@ class CSVLoader(object):
         paths = [inputs] if isinstance(inputs, str) else list(inputs)
         rows = []
         for path in paths:
-            with open(path, newline="") as fh:
+            if path.endswith(".gz"):                   # pandas (the reference's reader) infers gzip from the suffix
+                import gzip
+                fh = gzip.open(path, "rt", newline="")
+            else:
+                fh = open(path, newline="")
+            with fh:
                 rows.extend(csv.DictReader(fh))
         smiles = [r[self.feature_field].strip() for r in rows]
         packed, bad = featurize_smiles_packed(smiles)
