@@ -98,6 +98,8 @@ class FlatEngine(object):
         uncertainty head, widths that are multiples of 4.  Anything else uses the autograd layers."""
         if getattr(model, "uncertainty", False):
             return False
+        if getattr(model, "sync_batch_norm", False):       # statistics exchanged between ranks inside the step:
+            return False                                   # the per-layer autograd path with parallel.SyncBatchNorm1d
         if len(model.graph_convs) > _lib.MODEL_MAX_LAYERS:
             return False
         widths = [c.out_channel for c in model.graph_convs] + [model.dense.out_features]

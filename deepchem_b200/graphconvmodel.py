@@ -117,7 +117,7 @@ class _GraphConvTorchModel(nn.Module):
                  graph_conv_layers: List[int] = [64, 64], dense_layer_size: int = 128, dropout=0.0,
                  mode: str = "classification", number_atom_features: int = 75, n_classes: int = 2,
                  batch_normalize: bool = True, uncertainty: bool = False, batch_size: int = 100,
-                 gemm_mode: str = "fp32"):
+                 gemm_mode: str = "fp32", sync_batch_norm: bool = False):
         super(_GraphConvTorchModel, self).__init__()
         if mode not in ['classification', 'regression']:
             raise ValueError("mode must be either 'classification' or 'regression'")
@@ -141,9 +141,17 @@ class _GraphConvTorchModel(nn.Module):
             GraphConv(layer_size, input_size, activation_fn=F.relu, gemm_mode=gemm_mode)
             for layer_size, input_size in zip(graph_conv_layers, number_input_features)])
 
+        # sync_batch_norm (not in the reference, whose statistics are per process): training statistics over the atoms
+        # of every data-parallel rank, parallel.SyncBatchNorm1d — same parameters, buffers and state_dict keys
+        self.sync_batch_norm = bool(sync_batch_norm and batch_normalize)
+        if self.sync_batch_norm:
+            from .parallel import SyncBatchNorm1d as bn_cls
+        else:
+            bn_cls = nn.BatchNorm1d
+
         def bn(width):
-            return nn.BatchNorm1d(num_features=width, eps=1e-3, momentum=0.99, affine=True,
-                                  track_running_stats=True) if batch_normalize else nn.Identity()
+            return bn_cls(num_features=width, eps=1e-3, momentum=0.99, affine=True,
+                          track_running_stats=True) if batch_normalize else nn.Identity()
         self.batch_norms = nn.ModuleList([bn(c) for c in graph_conv_layers] + [bn(dense_layer_size)])
         self.dropouts = nn.ModuleList([nn.Dropout(rate) if rate > 0.0 else nn.Identity() for rate in dropout])
         self.graph_pools = nn.ModuleList([GraphPool() for _ in graph_conv_layers])
@@ -365,13 +373,18 @@ class GraphConvModel(object):
     dense_layer_size, ...)`` (Keras reference, graph_models.py:922-933) are both accepted; a single
     positional list is read as ``number_input_features`` only if it starts with
     ``number_atom_features``.
+
+    ``sync_batch_norm=True`` (an addition): in a data-parallel run the BatchNorm layers take their training
+    statistics over the atoms of every rank (``parallel.SyncBatchNorm1d``: two small all-reduces per layer and
+    direction) instead of per process as the reference does; the model then runs on the per-layer autograd path, not
+    the fused engine.  Checkpoints are interchangeable with the default model.
     """
 
     def __init__(self, n_tasks, *args, graph_conv_layers=None, number_input_features=None,
                  dense_layer_size=128, dropout=0.0, mode="classification", number_atom_features=75,
                  n_classes=2, batch_size=100, batch_normalize=True, uncertainty=False,
                  learning_rate=0.001, model_dir=None, device=None, gemm_mode="fp32", log_frequency=100,
-                 use_engine=True, **kwargs):
+                 use_engine=True, sync_batch_norm=False, **kwargs):
         args = list(args)
         if args and isinstance(args[0], (list, tuple)):
             first = list(args.pop(0))
@@ -404,7 +417,7 @@ class GraphConvModel(object):
             dense_layer_size=dense_layer_size, dropout=dropout, mode=mode,
             number_atom_features=number_atom_features, n_classes=n_classes,
             batch_normalize=batch_normalize, uncertainty=uncertainty, batch_size=batch_size,
-            gemm_mode=gemm_mode).to(self.device)
+            gemm_mode=gemm_mode, sync_batch_norm=sync_batch_norm).to(self.device)
         if mode == "classification":
             self.output_types = ['prediction', 'loss', 'embedding']
         elif uncertainty:

@@ -77,3 +77,73 @@ def shard_range(n, rank, world):
     per = (n + world - 1) // world
     lo = min(n, rank * per)
     return lo, min(n, lo + per)
+
+
+class _SyncBatchNormFn(torch.autograd.Function):
+    """Training-mode batch normalisation of [rows, C] over the rows of ALL ranks: two small all-reduces per call
+    (forward: per-column sum, sum of squares and the row count as one float64 vector of 2C+1; backward: the two
+    per-column sums of the input gradient, 2C).  Ranks may hold different numbers of rows (atoms per batch vary)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, group):
+        c = x.shape[1]
+        xd = x.double()
+        stats = torch.cat([xd.sum(0), (xd * xd).sum(0), xd.new_tensor([float(x.shape[0])])])
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
+        n = stats[2 * c]
+        mean = stats[:c] / n
+        var = (stats[c:2 * c] / n - mean * mean).clamp_min_(0.0)          # biased, as F.batch_norm normalises
+        invstd = torch.rsqrt(var + eps)
+        mean32, invstd32 = mean.float(), invstd.float()
+        xhat = (x - mean32) * invstd32
+        ctx.save_for_backward(xhat, weight, invstd32, n)      # (n stays on the device: no host synchronisation)
+        ctx.group = group
+        ctx.mark_non_differentiable(mean, var, n)
+        y = xhat * weight + bias if weight is not None else xhat
+        return y, mean, var, n
+
+    @staticmethod
+    def backward(ctx, dy, _dmean, _dvar, _dn):
+        xhat, weight, invstd, n = ctx.saved_tensors
+        c = dy.shape[1]
+        dyd = dy.double()
+        sums = torch.cat([dyd.sum(0), (dyd * xhat.double()).sum(0)])
+        local = sums.clone()                 # parameter gradients stay local: the gradient exchange sums them over ranks
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=ctx.group)
+        mean_dy = (sums[:c] / n).float()
+        mean_dy_xhat = (sums[c:] / n).float()
+        scale = invstd * weight if weight is not None else invstd
+        dx = (dy - mean_dy - xhat * mean_dy_xhat) * scale
+        dw = local[c:].float() if weight is not None else None
+        db = local[:c].float() if weight is not None else None
+        return dx, dw, db, None, None
+
+
+class SyncBatchNorm1d(torch.nn.BatchNorm1d):
+    """``BatchNorm1d`` whose TRAINING statistics are taken over the rows of every rank of the process group, so that a
+    data-parallel run normalises with the statistics a single process would see on the concatenated batch (SURVEY 8e:
+    the reference's BatchNorm is per process; this is the opt-in alternative).  Same parameters, buffers and
+    ``state_dict`` keys as ``BatchNorm1d`` (eps / momentum as the model sets them: 1e-3 / 0.99,
+    ``torch_models/graphconvmodel.py:160-170``); eval mode and single-process runs take the stock code path.  Works on
+    any backend that all-reduces float64 (NCCL, gloo), which is what lets ``tests/test_parallel_gloo.py`` check it on
+    CPU against ``BatchNorm1d`` over the concatenated rows."""
+
+    def __init__(self, *args, process_group=None, **kwargs):
+        super(SyncBatchNorm1d, self).__init__(*args, **kwargs)
+        self.process_group = process_group
+
+    def forward(self, x):
+        if not (self.training and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size(self.process_group) > 1):
+            return super(SyncBatchNorm1d, self).forward(x)
+        if x.dim() != 2:
+            raise ValueError("SyncBatchNorm1d expects [rows, channels], got %s" % (tuple(x.shape),))
+        y, mean, var, n = _SyncBatchNormFn.apply(x, self.weight, self.bias, self.eps, self.process_group)
+        if self.track_running_stats:
+            with torch.no_grad():
+                self.num_batches_tracked += 1
+                m = self.momentum if self.momentum is not None else 1.0 / float(self.num_batches_tracked)
+                unbiased = var * (n / (n - 1.0).clamp_min(1.0))
+                self.running_mean.mul_(1.0 - m).add_(mean.to(self.running_mean.dtype), alpha=m)
+                self.running_var.mul_(1.0 - m).add_(unbiased.to(self.running_var.dtype), alpha=m)
+        return y

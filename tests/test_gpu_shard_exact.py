@@ -118,3 +118,39 @@ def test_dmpnn_two_rank_exchange_is_bit_identical_to_the_hand_summed_slabs():
     import json
     verdict = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert verdict["ok"], verdict
+
+
+def test_sync_batch_norm_model_on_one_process_equals_the_default_model():
+    """sync_batch_norm=True selects parallel.SyncBatchNorm1d and the per-layer autograd path; with one process it must
+    be the default model: same state_dict keys, same loss and gradients as the fused engine (the cross-rank arithmetic
+    of the layer itself is checked on CPU under gloo, tests/test_parallel_gloo.py)."""
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    from deepchem_b200.parallel import SyncBatchNorm1d
+    from deepchem_b200.synthetic import make_labels, make_molecules
+    dev = _cuda()
+    B = 128
+    pm = make_molecules(B, seed=33, shape="zinc")
+    y, w = make_labels(B, 2, "regression", seed=8)
+    torch.manual_seed(5)
+    a = GraphConvModel(2, graph_conv_layers=[64, 64], dense_layer_size=128, mode="regression", batch_size=B, device=dev,
+                       gemm_mode="tf32x3")
+    b = GraphConvModel(2, graph_conv_layers=[64, 64], dense_layer_size=128, mode="regression", batch_size=B, device=dev,
+                       gemm_mode="tf32x3", sync_batch_norm=True)
+    assert a._engine is not None and b._engine is None
+    assert all(isinstance(m, SyncBatchNorm1d) for m in b.model.batch_norms)
+    assert list(a.model.state_dict().keys()) == list(b.model.state_dict().keys())
+    b.model.load_state_dict(a.model.state_dict())
+    batch = next(a.default_generator(PackedDataset(pm, y, w), deterministic=True, pad_batches=False))
+    inputs, labels, weights = a._prepare_batch(batch)
+    loss_a = float(a._engine.train_step(inputs[1]._dcgc_topology, inputs[0], labels[0].contiguous(),
+                                        weights[0].contiguous(), B))
+    g_a = {n: p.grad.clone() for n, p in a.model.named_parameters()}
+    b.model.train()
+    outs = b.model(inputs)
+    loss_b = b._loss_fn([outs[0]], labels, weights)
+    loss_b.backward()
+    assert abs(loss_a - float(loss_b)) < 1e-5 * max(1.0, abs(loss_a))
+    for n, p in b.model.named_parameters():
+        scale = max(float(g_a[n].abs().max()), 1e-6)
+        assert float((p.grad - g_a[n]).abs().max()) < 1e-4 * scale + 1e-9, n

@@ -101,3 +101,90 @@ def test_gradient_slab_allreduce_and_inference_sharding(tmp_path):
             spans = [parallel.shard_range(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SyncBatchNorm1d ("offer SyncBN to reproduce single-GPU large-batch statistics")
+# ---------------------------------------------------------------------------------------------------------
+_SBN_ROWS = (37, 52)          # rows (atoms) held by rank 0 / rank 1: unequal on purpose
+_SBN_C = 12
+
+
+def _sbn_data():
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(sum(_SBN_ROWS), _SBN_C, generator=g) * 2.0 + 0.5
+    t = torch.randn(sum(_SBN_ROWS), _SBN_C, generator=g)
+    return x, t
+
+
+def _sbn_module(cls):
+    torch.manual_seed(4)
+    bn = cls(_SBN_C, eps=1e-3, momentum=0.99)
+    with torch.no_grad():
+        bn.weight.add_(torch.randn(_SBN_C) * 0.3)
+        bn.bias.add_(torch.randn(_SBN_C) * 0.3)
+    return bn
+
+
+def _sbn_worker(rank, world, port, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    from deepchem_b200 import parallel
+    parallel.init_from_env("gloo")
+    x, t = _sbn_data()
+    lo = sum(_SBN_ROWS[:rank])
+    hi = lo + _SBN_ROWS[rank]
+    bn = _sbn_module(parallel.SyncBatchNorm1d)
+    bn.train()
+    out = {}
+    for step in range(2):                                     # two steps: the running statistics are updated twice
+        xr = x[lo:hi].clone().requires_grad_(True)
+        y = bn(xr)
+        loss = (torch.tanh(y) * t[lo:hi]).sum() / 10.0        # a sum: the global loss is the sum of the rank losses
+        bn.zero_grad()
+        loss.backward()
+        out["y%d" % step], out["dx%d" % step] = y.detach().clone(), xr.grad.clone()
+        out["dw%d" % step], out["db%d" % step] = bn.weight.grad.clone(), bn.bias.grad.clone()
+    out["running_mean"], out["running_var"] = bn.running_mean.clone(), bn.running_var.clone()
+    out["num_batches_tracked"] = bn.num_batches_tracked.clone()
+    bn.eval()                                                 # eval mode: stock BatchNorm1d path, no collective
+    out["eval"] = bn(x[lo:hi]).detach().clone()
+    torch.save(out, os.path.join(out_dir, "sbn%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sync_batch_norm_equals_batch_norm_on_the_concatenated_rows(tmp_path):
+    world, port = 2, _free_port()
+    mp.spawn(_sbn_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    from deepchem_b200 import parallel
+    parts = [torch.load(os.path.join(str(tmp_path), "sbn%d.pt" % r)) for r in range(world)]
+    x, t = _sbn_data()
+    ref = _sbn_module(torch.nn.BatchNorm1d)
+    ref.train()
+    for step in range(2):
+        xr = x.clone().requires_grad_(True)
+        y = ref(xr)
+        loss = (torch.tanh(y) * t).sum() / 10.0
+        ref.zero_grad()
+        loss.backward()
+        cat = lambda k: torch.cat([p["%s%d" % (k, step)] for p in parts])       # noqa: E731
+        assert torch.allclose(cat("y"), y.detach(), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(cat("dx"), xr.grad, rtol=1e-4, atol=1e-6)
+        # parameter gradients are local sums: the gradient exchange of the training step adds them up
+        assert torch.allclose(sum(p["dw%d" % step] for p in parts), ref.weight.grad, rtol=1e-4, atol=1e-6)
+        assert torch.allclose(sum(p["db%d" % step] for p in parts), ref.bias.grad, rtol=1e-4, atol=1e-6)
+    for p in parts:
+        assert torch.allclose(p["running_mean"], ref.running_mean, rtol=1e-5, atol=1e-6)
+        assert torch.allclose(p["running_var"], ref.running_var, rtol=1e-5, atol=1e-6)
+        assert int(p["num_batches_tracked"]) == 2
+    ref.eval()
+    assert torch.allclose(torch.cat([p["eval"] for p in parts]), ref(x).detach(), rtol=1e-5, atol=1e-6)
+    # single process, no group: the stock path, same state_dict keys as BatchNorm1d
+    solo = _sbn_module(parallel.SyncBatchNorm1d)
+    solo.train()
+    plain = _sbn_module(torch.nn.BatchNorm1d)
+    plain.train()
+    assert torch.equal(solo(x), plain(x))
+    assert list(solo.state_dict().keys()) == list(plain.state_dict().keys())
