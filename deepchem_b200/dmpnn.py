@@ -643,7 +643,11 @@ class DMPNNModel(object):
                 else:
                     o = self.model(inputs)
                 outs.append((o if self.mode == 'regression' else o[0]).detach().cpu().numpy())
-        return np.concatenate(outs, 0) if outs else np.zeros((0, self.n_tasks), np.float32)
+        y = np.concatenate(outs, 0) if outs else np.zeros((0, self.n_tasks), np.float32)
+        for t in reversed(list(transformers)):              # deepchem.trans.undo_transforms (torch_model.py:625-634)
+            if getattr(t, "transform_y", False):
+                y = t.untransform(y)
+        return y
 
     def predict_on_batch(self, X):
         ds = _GraphDataset(X if isinstance(X, PackedGraphs) else PackedGraphs.from_graphs(list(X), self.atom_fdim,

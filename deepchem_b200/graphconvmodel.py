@@ -219,6 +219,21 @@ def _standard_loss(mode, uncertainty):
     return loss
 
 
+def _undo_transforms(y, transformers):
+    """deepchem.trans.undo_transforms applied as TorchModel._predict does (torch_model.py:625-634): y-transformers are
+    undone in reverse order; several outputs cannot be untransformed."""
+    if not transformers:
+        return y
+    if isinstance(y, list):
+        if len(y) > 1:
+            raise ValueError("predict() does not support Transformers for models with multiple outputs.")
+        return y
+    for t in reversed(list(transformers)):
+        if getattr(t, "transform_y", False):
+            y = t.untransform(y)
+    return y
+
+
 def to_one_hot(y, n_classes=2):
     """deepchem.metrics.to_one_hot"""
     y = np.asarray(y).astype(np.int64).reshape(-1)
@@ -884,11 +899,44 @@ class GraphConvModel(object):
             lo, hi = shard_range(len(dataset), int(shard[0]), int(shard[1]))
             dataset = dataset.select_range(lo, hi)
         gen = self.default_generator(dataset, mode='predict', deterministic=True, pad_batches=False)
-        return self._predict(gen, self._prediction_outputs, n_rows=[len(dataset)] * len(self._prediction_outputs))
+        out = self._predict(gen, self._prediction_outputs, n_rows=[len(dataset)] * len(self._prediction_outputs))
+        return _undo_transforms(out, transformers)
 
-    def predict_on_batch(self, X):
+    def predict_on_generator(self, generator, transformers=[], output_types=None):
+        """Predictions for batches from a generator (torch_model.py:654-690).  ``output_types``: names from
+        ``self.output_types`` ('prediction', 'loss', 'variance', 'embedding') to return instead of the predictions."""
+        idx = self._prediction_outputs
+        if output_types is not None:
+            wanted = [output_types] if isinstance(output_types, str) else list(output_types)
+            idx = [i for i, t in enumerate(self.output_types) if t in wanted]
+            if not idx:
+                raise ValueError('This model cannot compute other outputs since no other output_types were specified.')
+        return _undo_transforms(self._predict(generator, idx), transformers)
+
+    def predict_on_batch(self, X, transformers=[]):
         ds = PackedDataset(X) if isinstance(X, PackedMols) else NumpyDataset(X)
-        return self.predict(ds)
+        return self.predict(ds, transformers)
+
+    def predict_uncertainty(self, dataset, masks=50):
+        """(prediction, standard deviation) per sample and task (torch_model.py:763-817): ``masks`` passes are
+        averaged, std = sqrt(E[y^2] - E[y]^2 + E[var]).  As in the torch reference the passes run the module in eval
+        mode without its ``training`` argument (torch_model.py:597-603), so no dropout mask is drawn, all
+        passes agree and the deviation is the aleatoric part sqrt(exp(log_var)); one pass is computed and reused."""
+        if not self._variance_outputs:
+            raise ValueError('This model cannot compute uncertainties')
+        if len(self._variance_outputs) != len(self._prediction_outputs):
+            raise ValueError('The number of variances must exactly match the number of outputs')
+        if masks < 1:
+            raise ValueError('masks must be positive')
+        gen = self.default_generator(dataset, mode='uncertainty', deterministic=True, pad_batches=False)
+        res = self._predict(gen, self._prediction_outputs + self._variance_outputs)
+        k = len(self._prediction_outputs)
+        pairs = [(p, np.sqrt(np.maximum(v, 0.0))) for p, v in zip(res[:k], res[k:])]     # E[y^2] - E[y]^2 = 0 here
+        return pairs[0] if len(pairs) == 1 else pairs
+
+    def predict_uncertainty_on_batch(self, X, masks=50):
+        ds = PackedDataset(X) if isinstance(X, PackedMols) else NumpyDataset(X)
+        return self.predict_uncertainty(ds, masks)
 
     def predict_embedding(self, dataset):
         """Untrimmed fingerprints, batch_size rows per batch, as the reference returns them."""

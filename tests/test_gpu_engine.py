@@ -225,3 +225,51 @@ def test_shuffled_fit_lazy_gather_equals_eager_batches(monkeypatch):
         finals.append({k: v.detach().cpu().clone() for k, v in m.model.state_dict().items()})
     for k in finals[0]:
         assert torch.equal(finals[0][k], finals[1][k]), k
+
+
+def test_uncertainty_mode_against_reference_outputs_and_loss():
+    """Rows a11 / a13 on the CUDA path: the five outputs [y, exp(log_var), y, log_var, fingerprint], the uncertainty
+    loss, predict_uncertainty and predict_on_generator against the fixture the reference's own
+    GraphConvModel(uncertainty=True) produced (tests/golden/make_golden_uncertainty.py)."""
+    from helpers import load_golden, unpack_mols
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    from deepchem_b200.synthetic import PackedMols
+    _cuda()
+    d = load_golden("ref_model_uncertainty.npz")
+    mols = unpack_mols(d)
+    n, bsz = len(mols), int(d["batch_size"])
+    pm = PackedMols.from_list(mols)
+    ds = PackedDataset(pm, d["y"], d["w"])
+    sd = {k[3:]: torch.from_numpy(v) for k, v in d.items() if k.startswith("sd:")}
+    for mode in ("tf32x3", "fp32"):
+        m = GraphConvModel(3, [64, 64], 128, mode="regression", uncertainty=True, dropout=0.25, batch_size=bsz,
+                           gemm_mode=mode)
+        assert m._engine is None and m.output_types == ['prediction', 'variance', 'loss', 'loss', 'embedding']
+        m.model.load_state_dict(sd)
+        batch = next(m.default_generator(ds, deterministic=True, pad_batches=False))
+        inputs, labels, weights = m._prepare_batch(batch)
+        m.model.train()
+        outs = m.model(inputs)
+        assert len(outs) == 5
+        for i, r in enumerate(outs):
+            assert rel_err(r.detach().cpu().numpy(), d["ref_train_out%d" % i]) < MODEL_TOL, (mode, i)
+        loss = m._loss_fn([outs[i] for i in m._loss_outputs], labels, weights)
+        ref = float(d["ref_train_loss"])
+        assert abs(float(loss) - ref) < 2e-5 * max(1.0, abs(ref)), mode
+        loss.backward()
+        assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.model.parameters())
+        m.model.load_state_dict(sd)                        # undo the running-statistics update
+        pred, std = m.predict_uncertainty(ds)
+        assert rel_err(pred, d["ref_eval_out0"]) < MODEL_TOL and rel_err(std, np.sqrt(d["ref_eval_out1"])) < MODEL_TOL
+        assert rel_err(m.predict(ds), d["ref_eval_out0"]) < MODEL_TOL
+        gen = m.default_generator(ds, mode='predict', deterministic=True, pad_batches=False)
+        var = m.predict_on_generator(gen, output_types='variance')
+        assert rel_err(var, d["ref_eval_out1"]) < MODEL_TOL
+
+        class Shift(object):                               # a y-transformer: predictions come back untransformed
+            transform_y = True
+
+            def untransform(self, y):
+                return y * 2.0 + 1.0
+        assert rel_err(m.predict(ds, [Shift()]), d["ref_eval_out0"] * 2.0 + 1.0) < MODEL_TOL

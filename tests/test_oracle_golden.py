@@ -168,6 +168,30 @@ def test_model_against_reference_outputs(mode):
         assert rel_err(r.detach().numpy(), d["ref_eval_out%d" % i]) < 2e-6, i
 
 
+def test_uncertainty_model_against_reference_outputs_and_loss():
+    """Rows a11 / a13: [y, exp(log_var), y, log_var, fingerprint] and the reference's uncertainty loss closure
+    (graphconvmodel.py:238-246, 360-372), fixture generated by tests/golden/make_golden_uncertainty.py."""
+    d = load_golden("ref_model_uncertainty.npz")
+    mols = unpack_mols(d)
+    _, mm = oracle_batch(mols)
+    m = O.OracleGraphConvModel(3, [64, 64], 128, mode="regression", uncertainty=True, dropout=0.25,
+                               batch_size=int(d["batch_size"]))
+    sd = {k[3:]: torch.from_numpy(v) for k, v in d.items() if k.startswith("sd:")}
+    assert set(sd) == set(m.state_dict())
+    m.load_state_dict(sd)
+    args = torch_args(mm, len(mols))
+    m.train()
+    out = m(args)
+    assert len(out) == 5
+    for i, r in enumerate(out):
+        assert rel_err(r.detach().numpy(), d["ref_train_out%d" % i]) < 2e-6, i
+    loss = O.standard_loss("regression", out, torch.from_numpy(d["y"]), torch.from_numpy(d["w"]), uncertainty=True)
+    assert abs(float(loss.detach()) - float(d["ref_train_loss"])) < 1e-6 * max(1.0, abs(float(d["ref_train_loss"])))
+    m.eval()
+    for i, r in enumerate(m(args)):
+        assert rel_err(r.detach().numpy(), d["ref_eval_out%d" % i]) < 2e-6, i
+
+
 def test_segment_max_ties_first_row_and_empty():
     x = torch.tensor([[1., 5.], [3., 5.], [3., 2.], [0., 0.]], dtype=torch.float64, requires_grad=True)
     ids = torch.tensor([0, 0, 0, 2])
