@@ -259,7 +259,7 @@ def test_uncertainty_mode_against_reference_outputs_and_loss():
         assert abs(float(loss) - ref) < 2e-5 * max(1.0, abs(ref)), mode
         loss.backward()
         assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.model.parameters())
-        m.model.load_state_dict(sd)                        # undo the running-statistics update
+        # (the fixture's eval-mode outputs were taken after its one train-mode pass: same running statistics here)
         pred, std = m.predict_uncertainty(ds)
         assert rel_err(pred, d["ref_eval_out0"]) < MODEL_TOL and rel_err(std, np.sqrt(d["ref_eval_out1"])) < MODEL_TOL
         assert rel_err(m.predict(ds), d["ref_eval_out0"]) < MODEL_TOL
