@@ -690,3 +690,29 @@ class DMPNNModel(object):
         else:
             self._pytorch_optimizer.load_state_dict(data['optimizer_state_dict'])
         self._global_step = data['global_step']
+
+    def get_checkpoints(self, model_dir=None):
+        """Checkpoint files, newest first (torch_model.py:1044-1059)."""
+        model_dir = model_dir or self.model_dir
+        if not model_dir or not os.path.isdir(model_dir):
+            return []
+        files = [f for f in os.listdir(model_dir) if f.startswith("checkpoint") and f.endswith(".pt")]
+        files.sort(key=lambda f: int(f[len("checkpoint"):-3]))
+        return [os.path.join(model_dir, f) for f in files]
+
+    def get_global_step(self):
+        return self._global_step
+
+    def evaluate(self, dataset, metrics, transformers=[], per_task_metrics=False):
+        """{name: score} for metric callables f(y_true, y_pred) or dc.metrics.Metric-like objects exposing
+        ``compute_metric(y, y_pred, w)`` (models.py:191-236)."""
+        y_pred = self.predict(dataset, transformers)
+        if not isinstance(metrics, (list, tuple)):
+            metrics = [metrics]
+        out = {}
+        for m in metrics:
+            if hasattr(m, "compute_metric"):
+                out[getattr(m, "name", m.__class__.__name__)] = m.compute_metric(dataset.y, y_pred, dataset.w)
+            else:
+                out[getattr(m, "__name__", "metric")] = m(dataset.y, y_pred)
+        return out

@@ -946,7 +946,7 @@ class GraphConvModel(object):
     def evaluate(self, dataset, metrics, transformers=[], per_task_metrics=False):
         """{name: score} for metric callables f(y_true, y_pred[, w]) or dc.metrics.Metric-like
         objects exposing ``compute_metric(y, y_pred, w)``."""
-        y_pred = self.predict(dataset)
+        y_pred = self.predict(dataset, transformers)
         if not isinstance(metrics, (list, tuple)):
             metrics = [metrics]
         out = {}

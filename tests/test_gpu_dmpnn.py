@@ -151,6 +151,27 @@ def test_model_trains_and_predicts():
     m.fit(ds, nb_epoch=60, deterministic=True)
     l1 = float(((m.predict(ds) - y) ** 2).mean())
     assert l1 < 0.5 * l0
+    # the TorchModel surface around fit / predict: evaluate, y-transformers, checkpoints (torch_model.py:996-1090)
+    import tempfile
+
+    def mse(y_true, y_pred):
+        return float(((y_true - y_pred) ** 2).mean())
+
+    class Shift(object):
+        transform_y = True
+
+        def untransform(self, v):
+            return v * 2.0 + 1.0
+    assert abs(m.evaluate(ds, [mse])["mse"] - l1) < 1e-6
+    assert np.allclose(m.predict(ds, [Shift()]), m.predict(ds) * 2.0 + 1.0, atol=1e-6)
+    with tempfile.TemporaryDirectory() as tmp:
+        m.save_checkpoint(model_dir=tmp)
+        assert [os.path.basename(c) for c in m.get_checkpoints(tmp)] == ["checkpoint1.pt"]
+        torch.manual_seed(2)
+        m2 = _model(dev, n_tasks=2, enc_hidden=64, ffn_hidden=64, batch_size=32, learning_rate=3e-3)
+        m2.restore(model_dir=tmp)
+        assert m2.get_global_step() == m.get_global_step() > 0
+        assert np.array_equal(m2.predict(ds), m.predict(ds))
     # classification head: probabilities + logits, sparse labels (losses.py:262-297)
     mc = _model(dev, mode='classification', n_tasks=2, n_classes=3, enc_hidden=32, ffn_hidden=32, batch_size=64)
     yc = rng.integers(0, 3, size=(64, 2)).astype(np.float32)
