@@ -14,6 +14,7 @@ import torch
 
 from . import _lib
 from ._lib import check
+from .mol_graphs import GROUP_STRIDE
 
 _workspaces = {}
 
@@ -36,10 +37,11 @@ def topology_struct(topo):
     st.n_atoms, st.n_edges, st.n_segments, st.n_tiles = topo.n_atoms, topo.n_edges, topo.n_segments, topo.n_tiles
     for d in range(11):
         st.deg_count[d] = topo.deg_count[d]
+    ptr = getattr(topo, "ptr", None) or (lambda name: getattr(topo, name).data_ptr())
     for name in ("row_ptr", "col_idx", "t_row_ptr", "t_src", "t_slot", "mol_ptr", "mol_atoms", "membership", "tiles"):
-        setattr(st, name, getattr(topo, name).data_ptr())
+        setattr(st, name, ptr(name))
     st.symmetric = 1 if getattr(topo, "symmetric", False) else 0
-    st.groups = topo.groups[1:].data_ptr()      # past the header row
+    st.groups = ptr("groups") + 4 * GROUP_STRIDE      # past the header row
     st.n_groups, st.group_max_rows = topo.n_groups, topo.group_max_rows
     st.group_max_entries = topo.group_max_entries
     rec = getattr(topo, "mg_records", None)

@@ -334,16 +334,13 @@ class DeviceTopology(object):
                 _lib.check(_lib.lib().dcgc_h2d_chunked(
                     self.buffer.data_ptr(), src.data_ptr(), nbytes, step,
                     ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        # typed views of the slab sections are made on first use (__getattr__): the fused engine only needs their
+        # addresses (ptr()), and two dozen tensor slicing calls per batch were a fifth of the host time of a
+        # small-batch step (profiles/r3o_small_batch.md)
         info = layout.info
-        for name, off_attr, dt, length in _SLAB_FIELDS:
-            off = getattr(info, off_attr)
-            n = int(length(info))
-            tdt = torch.int64 if dt is np.int64 else torch.int32
-            view = self.buffer[off:off + n * np.dtype(dt).itemsize].view(tdt)
-            setattr(self, name, view)
-        self.deg_slice = self.deg_slice.view(11, 2)
-        self.tiles = self.tiles.view(-1, 4)
-        self.groups = self.groups.view(-1, GROUP_STRIDE)
+        self._base = self.buffer.data_ptr()
+        self._fields = {name: (int(getattr(info, off_attr)), int(length(info)) * np.dtype(dt).itemsize,
+                               dt is np.int64) for name, off_attr, dt, length in _SLAB_FIELDS}
         self.n_groups, self.group_max_rows = layout.n_groups, layout.group_max_rows
         self.group_max_entries = layout.group_max_entries
         self.n_atoms, self.n_edges = layout.n_atoms, layout.n_edges
@@ -365,7 +362,27 @@ class DeviceTopology(object):
             _lib.check(L.dcgc_mg_prepare(ctypes.byref(topology_struct(self)), rec.data_ptr(),
                                          ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
             self.mg_records = rec
-            self._c_struct = None       # rebuilt with the record pointer on next use
+            self._c_struct.mg_records = rec.data_ptr()
+
+    _SHAPES = {"deg_slice": (11, 2), "tiles": (-1, 4), "groups": (-1, GROUP_STRIDE)}
+
+    def __getattr__(self, name):
+        # only reached when normal lookup fails: the lazily made int32 / int64 views of the device slab
+        fields = self.__dict__.get("_fields")
+        if fields is None or name not in fields:
+            raise AttributeError(name)
+        import torch
+        off, nbytes, is64 = fields[name]
+        view = self.buffer[off:off + nbytes].view(torch.int64 if is64 else torch.int32)
+        shape = self._SHAPES.get(name)
+        if shape is not None:
+            view = view.view(*shape)
+        self.__dict__[name] = view
+        return view
+
+    def ptr(self, name):
+        """Device address of a slab section (no tensor view is created)."""
+        return self._base + self._fields[name][0]
 
     def deg_adjacency_lists(self):
         out, off = [], 0
@@ -382,7 +399,41 @@ class DeviceTopology(object):
         deg_slice = self.deg_slice
         attach(deg_slice, self)
         ns = torch.tensor(self.n_mols if n_samples is None else n_samples)
-        return [features, deg_slice, self.membership, ns] + self.deg_adjacency_lists()[1:]
+        return _ModelInputs(self, features, deg_slice, ns)
+
+
+class _ModelInputs(list):
+    """``[features, deg_slice, membership, n_samples, deg_adj_1..10]`` whose membership and adjacency entries (eleven
+    tensor views the fused engine never reads: it takes the topology attached to ``deg_slice``) are made when an
+    element other than 0, 1 or 3 is first asked for; iteration, slicing, ``len`` and concatenation see the full list."""
+
+    def __init__(self, topo, features, deg_slice, n_samples):
+        list.__init__(self, [features, deg_slice, None, n_samples] + [None] * 10)
+        self._topo = topo
+
+    def _fill(self):
+        topo = self.__dict__.pop("_topo", None)
+        if topo is not None:
+            list.__setitem__(self, 2, topo.membership)
+            for i, a in enumerate(topo.deg_adjacency_lists()[1:]):
+                list.__setitem__(self, 4 + i, a)
+
+    def __getitem__(self, i):
+        if not (isinstance(i, int) and i in (0, 1, 3)):
+            self._fill()
+        return list.__getitem__(self, i)
+
+    def __iter__(self):
+        self._fill()
+        return list.__iter__(self)
+
+    def __add__(self, other):
+        self._fill()
+        return list(list.__iter__(self)) + list(other)
+
+    def __reduce__(self):
+        self._fill()
+        return (list, (list(list.__iter__(self)),))
 
 
 def attach(tensor, topo):
