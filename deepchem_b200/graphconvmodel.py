@@ -227,7 +227,7 @@ def _undo_transforms(y, transformers):
     if isinstance(y, list):
         if len(y) > 1:
             raise ValueError("predict() does not support Transformers for models with multiple outputs.")
-        return y
+        return [_undo_transforms(v, transformers) for v in y]
     for t in reversed(list(transformers)):
         if getattr(t, "transform_y", False):
             y = t.untransform(y)

@@ -143,3 +143,21 @@ def test_lazy_shuffled_batches_equal_eager_ones():
             assert np.array_equal(getattr(Xr, k), getattr(Xe, k)), k
         assert np.array_equal(ye, yl) and np.array_equal(we, wl) and np.array_equal(ie, il)
     assert float(lazy[-1][2][230 - 192:].sum()) == 0.0            # the padded copies carry zero weights
+
+
+def test_undo_transforms_follows_the_reference_order_and_limits():
+    """deepchem.trans.undo_transforms as TorchModel._predict applies it (torch_model.py:625-634): y-transformers are
+    undone last-to-first, X-transformers are skipped, several outputs cannot be untransformed."""
+    class T(object):
+        def __init__(self, transform_y, scale, shift):
+            self.transform_y, self.scale, self.shift = transform_y, scale, shift
+
+        def untransform(self, y):
+            return y * self.scale + self.shift
+    y = np.arange(6, dtype=np.float32).reshape(3, 2)
+    assert G._undo_transforms(y, []) is y
+    chain = [T(True, 2.0, 1.0), T(False, 100.0, 100.0), T(True, 3.0, -1.0)]      # forward order of the transforms
+    assert np.array_equal(G._undo_transforms(y, chain), (y * 3.0 - 1.0) * 2.0 + 1.0)
+    assert np.array_equal(G._undo_transforms([y], chain)[0], (y * 3.0 - 1.0) * 2.0 + 1.0)   # a single output in a list
+    with pytest.raises(ValueError):
+        G._undo_transforms([y, y], chain)

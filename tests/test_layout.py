@@ -251,3 +251,38 @@ def test_single_pass_builder_hands_asymmetric_batches_to_the_general_path(monkey
     fa = _all_fields(a)
     for f in fa:
         assert np.array_equal(fa[f], b[f]), f
+
+
+def test_device_topology_views_are_lazy_and_equal_the_host_slab():
+    """DeviceTopology (here on the CPU device: the class is device-agnostic) makes the typed views of the slab sections
+    on first use; ptr() gives their addresses without a view; the C struct is filled from addresses alone; the
+    model-input list materialises membership / adjacency entries only when they are asked for."""
+    import torch
+    from deepchem_b200.engine import topology_struct
+    pm = make_molecules(50, seed=1, shape="tox21")
+    lay = MG.BatchLayout.build(pm)
+    topo = lay.to_device("cpu")
+    assert not any(name in topo.__dict__ for name, *_ in MG._SLAB_FIELDS)          # nothing made yet
+    st = topology_struct(topo)
+    assert not any(name in topo.__dict__ for name, *_ in MG._SLAB_FIELDS)          # the struct needs addresses only
+    for name, *_ in MG._SLAB_FIELDS:
+        view, host = getattr(topo, name), getattr(lay, name)
+        assert name in topo.__dict__ and getattr(topo, name) is view                 # cached after the first access
+        assert np.array_equal(view.numpy().reshape(-1), np.asarray(host).reshape(-1)), name
+        assert view.numel() == 0 or view.data_ptr() == topo.ptr(name), name
+    assert topo.deg_slice.shape == (11, 2) and topo.deg_slice.dtype == torch.int64
+    assert topo.tiles.shape[1] == 4 and topo.groups.shape[1] == MG.GROUP_STRIDE
+    assert st.membership == topo.membership.data_ptr() and st.col_idx == topo.ptr("col_idx")
+    assert st.groups == topo.groups[1:].data_ptr()                                    # past the header row
+    with pytest.raises(AttributeError):
+        topo.no_such_section
+    x = torch.zeros(lay.n_atoms, 76)
+    mi = topo.model_inputs(x, n_samples=50)
+    assert len(mi) == 14 and mi[0] is x and int(mi[3]) == 50 and mi[1]._dcgc_topology is topo
+    assert list.__getitem__(mi, 2) is None and list.__getitem__(mi, 13) is None     # engine path: never materialised
+    assert mi[2].shape[0] == lay.n_atoms and list.__getitem__(mi, 13) is not None   # first other access fills all
+    for make in (lambda m: list(m), lambda m: m[4:], lambda m: m + [], lambda m: [t for t in m][4:], lambda m: m[-10:]):
+        got = make(topo.model_inputs(x))
+        adj = got[-10:]
+        assert all(a is not None for a in got) and [a.shape[1] for a in adj] == list(range(1, 11))
+        assert sum(a.shape[0] for a in adj) + lay.deg_count[0] == lay.n_atoms
