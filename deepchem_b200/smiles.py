@@ -331,29 +331,42 @@ def _cleanup(mol):
 
 
 def _mark_rings(mol):
-    """A bond is a ring bond iff its ends stay connected without it."""
+    """A bond is a ring bond iff its ends stay connected without it, i.e. iff it is not a bridge: one depth-first walk
+    with low-links (Tarjan) over every fragment instead of one search per bond."""
+    n = len(mol.atoms)
+    order, low = [-1] * n, [0] * n
     for b in mol.bonds:
-        b.in_ring = _on_cycle(mol, b)
+        b.in_ring = True
+    clock = 0
+    for root in range(n):
+        if order[root] >= 0:
+            continue
+        order[root] = low[root] = clock
+        clock += 1
+        stack = [(root, -1, 0)]                       # (atom, bond it was entered by, next position in its bond list)
+        while stack:
+            v, via, pos = stack.pop()
+            bonds = mol.atoms[v].bonds
+            if pos < len(bonds):
+                stack.append((v, via, pos + 1))
+                k = bonds[pos]
+                if k == via:
+                    continue
+                w = mol.bonds[k].other(v)
+                if order[w] < 0:
+                    order[w] = low[w] = clock
+                    clock += 1
+                    stack.append((w, k, 0))
+                elif order[w] < low[v]:
+                    low[v] = order[w]
+            elif via >= 0:
+                parent = mol.bonds[via].other(v)
+                if low[v] < low[parent]:
+                    low[parent] = low[v]
+                if low[v] > order[parent]:
+                    mol.bonds[via].in_ring = False    # nothing below v reaches parent or above: a bridge
     for a in mol.atoms:
         a.in_ring = any(mol.bonds[k].in_ring for k in a.bonds)
-
-
-def _on_cycle(mol, bond):
-    """Is there a path a -> b that avoids this bond?"""
-    seen, todo = {bond.a}, [bond.a]
-    while todo:
-        v = todo.pop()
-        for k in mol.atoms[v].bonds:
-            b = mol.bonds[k]
-            if b is bond:
-                continue
-            w = b.other(v)
-            if w == bond.b:
-                return True
-            if w not in seen:
-                seen.add(w)
-                todo.append(w)
-    return False
 
 
 def _usable_valences(atom):
