@@ -141,8 +141,9 @@ class CSVLoader(object):
     for SMILES files, over the RDKit-free reader: the molecules go straight into one ``PackedMols`` shard (no pickled
     ``ConvMol`` objects), rows whose SMILES fail to parse are dropped as ``DataLoader`` drops failed datapoints."""
 
-    def __init__(self, tasks, featurizer=None, feature_field="smiles", id_field=None, smiles_field=None):
+    def __init__(self, tasks, featurizer=None, feature_field="smiles", id_field=None, smiles_field=None, n_jobs=1):
         self.tasks = list(tasks)
+        self.n_jobs = n_jobs                  # worker processes of the SMILES reader (smiles.featurize_smiles_packed)
         self.feature_field = smiles_field if smiles_field is not None else feature_field
         self.id_field = id_field
         self.featurizer = featurizer          # accepted for signature compatibility; the 75-dim ConvMol features are built in
@@ -161,7 +162,7 @@ class CSVLoader(object):
             with fh:
                 rows.extend(csv.DictReader(fh))
         smiles = [r[self.feature_field].strip() for r in rows]
-        packed, bad = featurize_smiles_packed(smiles)
+        packed, bad = featurize_smiles_packed(smiles, n_jobs=self.n_jobs)
         keep = np.setdiff1d(np.arange(len(rows)), np.asarray(bad, dtype=np.int64))
         y = np.zeros((len(keep), len(self.tasks)), np.float32)
         w = np.ones((len(keep), len(self.tasks)), np.float32)
