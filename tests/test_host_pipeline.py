@@ -161,3 +161,44 @@ def test_undo_transforms_follows_the_reference_order_and_limits():
     assert np.array_equal(G._undo_transforms([y], chain)[0], (y * 3.0 - 1.0) * 2.0 + 1.0)   # a single output in a list
     with pytest.raises(ValueError):
         G._undo_transforms([y, y], chain)
+
+
+@pytest.mark.parametrize("source", ["convmol_objects", "packed_shard"])
+def test_default_generator_equals_the_reference_generator(source):
+    """Row a3 against the reference itself (tests/golden/make_golden_generator.py): 23 molecules, batch 10,
+    classification with 2 tasks.  Every array the reference's ``default_generator`` yields — permuted features,
+    deg_slice (int64), membership, n_samples, deg_adj_1..10, one-hot labels, weights, the third batch padded by
+    ``pad_batch`` — is reproduced bit for bit, from an object array of ConvMol and from a packed shard; in 'predict' mode
+    with ``pad_batches=False`` the labels stay class indices and the last batch keeps its 3 molecules."""
+    from helpers import load_golden, unpack_mols
+    from deepchem_b200.data import NumpyDataset
+    from deepchem_b200.mol_graphs import ConvMol
+    from deepchem_b200.synthetic import PackedMols
+    d = load_golden("ref_generator.npz")
+    mols = unpack_mols(d)
+    if source == "packed_shard":
+        ds = PackedDataset(PackedMols.from_list(mols), d["y"], d["w"])
+    else:
+        X = np.empty(len(mols), dtype=object)
+        for i, (f, adj) in enumerate(mols):
+            X[i] = ConvMol(np.asarray(f, dtype=np.float64), adj)
+        ds = NumpyDataset(X, d["y"], d["w"])
+    m = _host_model(10, 1)
+    m.mode, m.n_tasks, m.n_classes = 'classification', 2, 2
+    for tag, kw in (("fit", dict(mode="fit", pad_batches=True)), ("predict", dict(mode="predict", pad_batches=False))):
+        got = list(m.default_generator(ds, epochs=1, deterministic=True, **kw))
+        assert len(got) == int(d["%s_batches" % tag])
+        for n, (inputs, labels, weights) in enumerate(got):
+            lay = inputs.layout
+            feats = lay.permute_features(np.asarray(inputs.packed_features, dtype=np.float32))
+            assert np.array_equal(feats, d["%s_b%d_in0" % (tag, n)]), (tag, n)
+            ref_slice = d["%s_b%d_in1" % (tag, n)]
+            assert inputs[1].dtype == ref_slice.dtype == np.int64 and np.array_equal(inputs[1], ref_slice)
+            assert np.array_equal(inputs[2], d["%s_b%d_in2" % (tag, n)])
+            assert int(inputs[3]) == int(d["%s_b%d_in3" % (tag, n)])
+            assert len(inputs) == 14
+            for k in range(4, 14):
+                ref_adj = d["%s_b%d_in%d" % (tag, n, k)]
+                assert inputs[k].shape == ref_adj.shape and np.array_equal(inputs[k], ref_adj), (tag, n, k)
+            assert np.array_equal(np.asarray(labels[0], dtype=np.float32), d["%s_b%d_y" % (tag, n)]), (tag, n)
+            assert np.array_equal(np.asarray(weights[0], dtype=np.float32), d["%s_b%d_w" % (tag, n)]), (tag, n)
