@@ -82,3 +82,27 @@ def test_builder_rejects_bad_bond_index():
     pg.edge_dst[0] = 99
     with pytest.raises(ValueError):
         DmpnnLayout.build(pg)
+
+
+def test_encoder_and_ffn_state_dicts_have_the_reference_layout():
+    """Checkpoint compatibility without a device: the encoder / feed-forward modules carry exactly the parameter
+    names and shapes of the reference modules whose weights the fixture holds (with and without encoder bias)."""
+    import torch
+    from deepchem_b200.dmpnn import DMPNNEncoderLayer, PositionwiseFeedForward
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_dmpnn.npz"), allow_pickle=False)
+    for ci in (0, 1, 2):
+        agg, bias, depth = G["enc%d_cfg" % ci]
+        enc = DMPNNEncoderLayer(use_default_fdim=False, atom_fdim=133, bond_fdim=14, d_hidden=64, depth=int(depth),
+                                bias=bias == "True", aggregation=str(agg), aggregation_norm=7)
+        want = {k[len("enc%d_" % ci):]: G[k] for k in G.files
+                if k.startswith("enc%d_W_" % ci)}
+        own = enc.state_dict()
+        assert sorted(own) == sorted(want)
+        for k, v in own.items():
+            assert tuple(v.shape) == want[k].shape, (ci, k)
+        enc.load_state_dict({k: torch.from_numpy(v) for k, v in want.items()}, strict=True)
+    want = {k[len("ffn_"):]: G[k] for k in G.files if k.startswith("ffn_linears")}
+    d_in, d_hid, d_out = want["linears.0.weight"].shape[1], want["linears.0.weight"].shape[0], want["linears.2.weight"].shape[0]
+    ffn = PositionwiseFeedForward(d_input=d_in, d_hidden=d_hid, d_output=d_out, activation='relu', n_layers=3)
+    own = ffn.state_dict()
+    assert sorted(own) == sorted(want) and all(tuple(own[k].shape) == want[k].shape for k in own)

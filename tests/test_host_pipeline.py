@@ -202,3 +202,28 @@ def test_default_generator_equals_the_reference_generator(source):
                 assert inputs[k].shape == ref_adj.shape and np.array_equal(inputs[k], ref_adj), (tag, n, k)
             assert np.array_equal(np.asarray(labels[0], dtype=np.float32), d["%s_b%d_y" % (tag, n)]), (tag, n)
             assert np.array_equal(np.asarray(weights[0], dtype=np.float32), d["%s_b%d_w" % (tag, n)]), (tag, n)
+
+
+@pytest.mark.parametrize("fixture,kw", [("ref_model_classification.npz", dict(mode="classification")),
+                                        ("ref_model_regression.npz", dict(mode="regression")),
+                                        ("ref_model_uncertainty.npz", dict(mode="regression", uncertainty=True, dropout=0.25)),
+                                        ("ref_tox21_real.npz", dict(mode="classification", n_tasks=12))])
+def test_module_state_dict_is_the_reference_checkpoint_layout(fixture, kw):
+    """SURVEY 8b checkpoint compatibility, without a device: the module's state_dict has exactly the reference's keys,
+    shapes and dtypes (fixtures hold the reference model's own state_dict) and loads it strictly — also with the
+    opt-in synchronised BatchNorm."""
+    import torch
+    from helpers import load_golden
+    d = load_golden(fixture)
+    sd = {k[3:]: torch.from_numpy(v) for k, v in d.items() if k.startswith("sd:")}
+    kw = dict(kw)
+    n_tasks = kw.pop("n_tasks", 3)
+    for sync in (False, True):
+        m = G._GraphConvTorchModel(n_tasks, graph_conv_layers=[64, 64], dense_layer_size=128, batch_size=32,
+                                   sync_batch_norm=sync, **kw)
+        own = m.state_dict()
+        assert list(own.keys()) == list(sd.keys())
+        for k, v in own.items():
+            assert tuple(v.shape) == tuple(sd[k].shape) and v.dtype == sd[k].dtype, k
+        m.load_state_dict(sd, strict=True)
+        assert all(torch.equal(v, sd[k]) for k, v in m.state_dict().items())
