@@ -7,7 +7,8 @@
         ``pad_batches=True``: per batch the input list [features, deg_slice, membership, n_samples, deg_adj_1..10],
         the one-hot labels and the weights — the third batch holds 3 molecules and is padded to 10 by
         ``pad_batch`` (data/datasets.py:142-218: the molecules repeated, zero weights on the copies).  Also a 'predict'
-        pass with ``pad_batches=False`` (labels stay class indices, the last batch keeps 3 molecules).
+        pass with ``pad_batches=False`` (labels stay class indices, the last batch keeps 3 molecules), and a 'tiny' pass:
+        the first 3 molecules alone with batch_size 10 (the batch is filled by repeating the dataset 3 1/3 times).
 """
 import os
 import sys
@@ -50,6 +51,17 @@ def main():
             n += 1
         d["%s_batches" % tag] = np.array(n)
         print(tag, "batches", n, "last n_samples", int(inputs[3]), "labels", np.asarray(labels[0]).shape)
+    tiny = NumpyDataset(X[:3], y[:3], w[:3])
+    got = list(ref.default_generator(tiny, epochs=1, deterministic=True, mode="fit", pad_batches=True))
+    assert len(got) == 1
+    inputs, labels, weights = got[0]
+    for k, a in enumerate(inputs):
+        a = np.asarray(a)
+        d["tiny_b0_in%d" % k] = a.astype(np.float32) if a.dtype == np.float64 else a
+    d["tiny_b0_y"] = np.asarray(labels[0], dtype=np.float32)
+    d["tiny_b0_w"] = np.asarray(weights[0], dtype=np.float32)
+    d["tiny_batches"] = np.array(1)
+    print("tiny: n_samples", int(inputs[3]), "atoms", np.asarray(inputs[0]).shape[0], "weights", np.asarray(weights[0])[:, 0])
     np.savez_compressed(os.path.join(HERE, "ref_generator.npz"), **d)
 
 

@@ -185,8 +185,10 @@ def test_default_generator_equals_the_reference_generator(source):
         ds = NumpyDataset(X, d["y"], d["w"])
     m = _host_model(10, 1)
     m.mode, m.n_tasks, m.n_classes = 'classification', 2, 2
-    for tag, kw in (("fit", dict(mode="fit", pad_batches=True)), ("predict", dict(mode="predict", pad_batches=False))):
-        got = list(m.default_generator(ds, epochs=1, deterministic=True, **kw))
+    for tag, kw in (("fit", dict(mode="fit", pad_batches=True)), ("predict", dict(mode="predict", pad_batches=False)),
+                    ("tiny", dict(mode="fit", pad_batches=True))):
+        src = ds.select_range(0, 3) if tag == "tiny" else ds      # 3 molecules in a batch of 10: repeated 3 1/3 times
+        got = list(m.default_generator(src, epochs=1, deterministic=True, **kw))
         assert len(got) == int(d["%s_batches" % tag])
         for n, (inputs, labels, weights) in enumerate(got):
             lay = inputs.layout
