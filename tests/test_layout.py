@@ -286,3 +286,35 @@ def test_device_topology_views_are_lazy_and_equal_the_host_slab():
         adj = got[-10:]
         assert all(a is not None for a in got) and [a.shape[1] for a in adj] == list(range(1, 11))
         assert sum(a.shape[0] for a in adj) + lay.deg_count[0] == lay.n_atoms
+
+
+def test_reference_mol_graphs_known_answers():
+    """The hand-written expectations of the reference's own tests (feat/tests/test_mol_graphs.py:21-141) against the
+    ConvMol class here and the C++ batch builder: deg_slice of a 4-ring, degree-sorted features, renumbered adjacency,
+    the three-molecule agglomeration golden, the null molecule."""
+    from deepchem_b200.mol_graphs import ConvMol
+    ring = ConvMol(np.array([[20, 21, 22, 23], [24, 25, 26, 27], [28, 29, 30, 31], [32, 33, 34, 35]]),
+                   [[1, 2], [0, 3], [0, 3], [1, 2]])
+    assert np.array_equal(ring.get_deg_slice(), np.array([[0, 0], [0, 0], [0, 4]] + [[0, 0]] * 8))      # :21-42
+    f5 = np.array([[40, 41, 42, 43], [44, 45, 46, 47], [48, 49, 50, 51], [52, 53, 54, 55], [56, 57, 58, 59]])
+    five = ConvMol(f5, [[1, 2], [0, 3], [0, 3], [1, 2, 4], [3]])
+    assert np.array_equal(five.get_atom_features(), f5[[4, 0, 1, 2, 3]])                                 # :44-60
+    assert five.get_adjacency_list() == [[4], [2, 3], [1, 4], [1, 4], [2, 3, 0]]                          # :62-75
+    chain = ConvMol(np.array([[1, 2, 3, 4], [5, 6, 7, 8], [9, 10, 11, 12]]), [[1], [0, 2], [1]])
+    for batch in (ConvMol.agglomerate_mols([chain, ring, five]),                                          # :77-126
+                  MG.BatchLayout.build(MG.pack_convmols([chain, ring, five])).multi_conv_mol(
+                      np.concatenate([m.atom_features for m in (chain, ring, five)]).astype(np.float32))):
+        assert batch.get_num_atoms() == 12 and batch.get_num_molecules() == 3
+        x = batch.get_atom_features()
+        assert np.array_equal(x[0], [1, 2, 3, 4]) and np.array_equal(x[2], [56, 57, 58, 59])
+        assert np.array_equal(x[11], [52, 53, 54, 55]) and np.array_equal(x[4], [20, 21, 22, 23])
+        adj = batch.get_deg_adjacency_lists()
+        assert adj[0].shape == (0, 0)
+        assert np.array_equal(adj[1], [[3], [3], [11]])
+        assert np.array_equal(adj[2], [[0, 1], [5, 6], [4, 7], [4, 7], [5, 6], [9, 10], [8, 11], [8, 11]])
+        assert np.array_equal(adj[3], [[9, 10, 2]])
+        assert adj[4].shape == (0, 4) and adj[5].shape == (0, 5)
+    null = ConvMol.get_null_mol(4)                                                                       # :128-141
+    adj = null.get_deg_adjacency_lists()
+    assert np.array_equal(adj[10], [[10] * 10]) and np.array_equal(adj[1], [[1]])
+    assert np.array_equal(null.get_deg_slice(), [[d, 1] for d in range(11)])
