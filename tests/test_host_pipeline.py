@@ -229,3 +229,20 @@ def test_module_state_dict_is_the_reference_checkpoint_layout(fixture, kw):
             assert tuple(v.shape) == tuple(sd[k].shape) and v.dtype == sd[k].dtype, k
         m.load_state_dict(sd, strict=True)
         assert all(torch.equal(v, sd[k]) for k, v in m.state_dict().items())
+
+
+def test_constructor_errors_follow_the_reference():
+    """graphconvmodel.py:121-140: ValueError for an unknown mode, a dropout list of the wrong length, uncertainty
+    outside regression and uncertainty without dropout in every layer."""
+    make = G._GraphConvTorchModel
+    with pytest.raises(ValueError, match="mode must be either"):
+        make(2, mode="ranking")
+    with pytest.raises(ValueError, match="Wrong number of dropout probabilities"):
+        make(2, graph_conv_layers=[64, 64], dropout=[0.1, 0.1])
+    with pytest.raises(ValueError, match="only supported in regression"):
+        make(2, mode="classification", uncertainty=True, dropout=0.2)
+    with pytest.raises(ValueError, match="Dropout must be included"):
+        make(2, mode="regression", uncertainty=True, dropout=[0.2, 0.0, 0.2])
+    m = make(2, graph_conv_layers=[64, 64], dropout=[0.1, 0.2, 0.3], mode="regression", uncertainty=True)
+    assert [d.p for d in m.dropouts] == [0.1, 0.2, 0.3] and hasattr(m, "uncertainty_dense")
+    assert len(m.graph_convs[0].W_list) == 21 and tuple(m.graph_convs[0].W_list[0].shape) == (75, 64)    # layers.py:6140-6151
