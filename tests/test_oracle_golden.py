@@ -227,3 +227,12 @@ def test_oracle_gradcheck_fp64():
         y = O.graph_pool(y, args[1], args[3:])
         return O.graph_gather(y, args[2], len(mols), torch.tanh)
     assert torch.autograd.gradcheck(f, (x, *W, *b), eps=1e-6, atol=1e-5)
+
+
+def test_segment_ops_reproduce_the_reference_docstring_examples():
+    """The worked examples in the reference's own docstrings (utils/pytorch_utils.py:38-53 and :490-506): segment ids
+    [0, 1, 0] over three rows."""
+    ids = torch.tensor([0, 1, 0])
+    data = torch.tensor([[1., 2., 3., 4.], [5., 6., 7., 8.], [4., 3., 2., 1.]])
+    assert O.segment_sum(data, ids, 2).tolist() == [[5., 5., 5., 5.], [5., 6., 7., 8.]]
+    assert O.segment_max(data, ids, 2).tolist() == [[4., 3., 3., 4.], [5., 6., 7., 8.]]
