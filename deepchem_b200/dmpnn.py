@@ -214,7 +214,7 @@ class DMPNNEncoderLayer(nn.Module):
     """Encoder of the Directed Message Passing Neural Network (layers.py:1261-1649)."""
 
     def __init__(self, use_default_fdim=True, atom_fdim=133, bond_fdim=14, d_hidden=300, depth=3, bias=False,
-                 activation='relu', dropout_p=0.0, aggregation='mean', aggregation_norm=100, gemm_mode="fp32"):
+                 activation='relu', dropout_p=0.0, aggregation='mean', aggregation_norm=100, gemm_mode="tf32x3"):
         super(DMPNNEncoderLayer, self).__init__()
         if use_default_fdim:       # GraphConvConstants.ATOM_FDIM / BOND_FDIM (dmpnn_featurizer.py)
             atom_fdim, bond_fdim = 133, 14
@@ -265,7 +265,7 @@ class PositionwiseFeedForward(nn.Module):
     """layers.py:795-910, linears through the GEMM kernels."""
 
     def __init__(self, d_input=1024, d_hidden=1024, d_output=1024, activation='leakyrelu', n_layers=1,
-                 dropout_p=0.0, dropout_at_input_no_act=False, gemm_mode="fp32"):
+                 dropout_p=0.0, dropout_at_input_no_act=False, gemm_mode="tf32x3"):
         super(PositionwiseFeedForward, self).__init__()
         self.dropout_at_input_no_act = dropout_at_input_no_act
         if activation == "linear":
@@ -320,7 +320,7 @@ class DMPNN(nn.Module):
                  atom_fdim=133, bond_fdim=14, enc_hidden=300, depth=3, bias=False, enc_activation='relu',
                  enc_dropout_p=0.0, aggregation='mean', aggregation_norm=100, ffn_hidden=300,
                  ffn_activation='relu', ffn_layers=3, ffn_dropout_p=0.0, ffn_dropout_at_input_no_act=True,
-                 gemm_mode="fp32"):
+                 gemm_mode="tf32x3"):
         super(DMPNN, self).__init__()
         self.mode, self.n_classes, self.n_tasks = mode, n_classes, n_tasks
         self.encoder = DMPNNEncoderLayer(use_default_fdim=use_default_fdim, atom_fdim=atom_fdim, bond_fdim=bond_fdim,
@@ -382,7 +382,7 @@ class DMPNNModel(object):
                  use_default_fdim=True, atom_fdim=133, bond_fdim=14, enc_hidden=300, depth=3, bias=False,
                  enc_activation='relu', enc_dropout_p=0.0, aggregation='mean', aggregation_norm=100, ffn_hidden=300,
                  ffn_activation='relu', ffn_layers=3, ffn_dropout_p=0.0, ffn_dropout_at_input_no_act=True,
-                 learning_rate=0.001, model_dir=None, device=None, gemm_mode="fp32", log_frequency=100, **kwargs):
+                 learning_rate=0.001, model_dir=None, device=None, gemm_mode="tf32x3", log_frequency=100, **kwargs):
         if mode not in ('regression', 'classification'):
             raise ValueError("mode must be either 'regression' or 'classification'")
         if device is None:
@@ -501,8 +501,12 @@ class DMPNNModel(object):
         return (per * w).mean()
 
     # ------------------------------------------------------------------ training / inference
-    def fit(self, dataset, nb_epoch=10, deterministic=False, **kwargs):
-        return self.fit_generator(self.default_generator(dataset, epochs=nb_epoch, deterministic=deterministic))
+    def fit(self, dataset, nb_epoch=10, max_checkpoints_to_keep=5, checkpoint_interval=1000, deterministic=False,
+            restore=False, callbacks=[], all_losses=None):
+        """TorchModel.fit (torch_model.py:288-343)."""
+        return self.fit_generator(self.default_generator(dataset, epochs=nb_epoch, deterministic=deterministic),
+                                  max_checkpoints_to_keep, checkpoint_interval, restore, callbacks=callbacks,
+                                  all_losses=all_losses)
 
     def _prefetched(self, generator, depth):
         """Run ``_prepare_batch`` (uploads + f_ini assembly) for upcoming batches on a helper thread and a side
@@ -555,21 +559,49 @@ class DMPNNModel(object):
                     pass
                 th.join(timeout=0.05)
 
-    def fit_generator(self, generator, prefetch=2, **kwargs):
+    def fit_generator(self, generator, max_checkpoints_to_keep=5, checkpoint_interval=1000, restore=False,
+                      callbacks=[], all_losses=None, prefetch=2):
+        """TorchModel.fit_generator (torch_model.py:345-496): ``restore`` reloads the newest checkpoint before the first
+        step, a checkpoint is written every ``checkpoint_interval`` steps and at the end (``model_dir`` set and
+        interval > 0; rank 0 only in a data-parallel run), ``callbacks`` are called as f(model, step) after every step,
+        ``all_losses`` collects the average loss of every ``log_frequency`` steps.  Returns the last average."""
+        if not isinstance(callbacks, (list, tuple)):
+            callbacks = [callbacks]
         self.model.train()
-        t0, n, last = time.time(), 0, None
+        t0 = time.time()
+        if restore:
+            self.restore()
+        avg_sum, avg_n, last_avg = 0.0, 0, 0.0
         prepared_iter = self._prefetched(generator, prefetch) if (prefetch and self.device.type == "cuda") else \
             (self._prepare_batch(b) for b in generator)
         for inputs, labels, weights in prepared_iter:
             self._train_step(inputs, labels, weights)
-            loss = self._last_loss
             self._global_step += 1
-            n += 1
-            last = loss
-            if self._global_step % self.log_frequency == 0:
-                logger.info('Ending global_step %d: loss %g' % (self._global_step, float(loss)))
+            step = self._global_step
+            want_loss = all_losses is not None or step % self.log_frequency == 0
+            if want_loss:                       # a device->host read: only when somebody looks at it
+                avg_sum += float(self._last_loss)
+                avg_n += 1
+            if step % self.log_frequency == 0 and avg_n:
+                last_avg = avg_sum / avg_n
+                logger.info('Ending global_step %d: Average loss %g' % (step, last_avg))
+                if all_losses is not None:
+                    all_losses.append(last_avg)
+                avg_sum, avg_n = 0.0, 0
+            if self.model_dir and checkpoint_interval > 0 and step % checkpoint_interval == checkpoint_interval - 1:
+                self.save_checkpoint(max_checkpoints_to_keep)
+            for c in callbacks:
+                c(self, step)
+        if avg_n:
+            last_avg = avg_sum / avg_n
+            if all_losses is not None:
+                all_losses.append(last_avg)
+        elif self._global_step and last_avg == 0.0 and getattr(self, "_last_loss", None) is not None:
+            last_avg = float(self._last_loss)
+        if self.model_dir and checkpoint_interval > 0:
+            self.save_checkpoint(max_checkpoints_to_keep)
         logger.info("TIMING: model fitting took %0.3f s" % (time.time() - t0))
-        return float(last) if n else 0.0
+        return last_avg
 
     def _train_step(self, inputs, labels, weights):
         """zero_grad, forward, loss, backward, (gradient all-reduce), Adam step (torch_model.py:435-443)."""
@@ -663,6 +695,10 @@ class DMPNNModel(object):
         model_dir = model_dir or self.model_dir
         if model_dir is None:
             raise ValueError("model_dir is not set")
+        if self._dp:
+            from .parallel import rank
+            if rank() != 0:                      # replicas are identical: one writer
+                return
         os.makedirs(model_dir, exist_ok=True)
         paths = [os.path.join(model_dir, 'checkpoint%d.pt' % (i + 1)) for i in range(max_checkpoints_to_keep)]
         tmp = os.path.join(model_dir, 'temp_checkpoint.pt')
@@ -703,16 +739,9 @@ class DMPNNModel(object):
     def get_global_step(self):
         return self._global_step
 
-    def evaluate(self, dataset, metrics, transformers=[], per_task_metrics=False):
-        """{name: score} for metric callables f(y_true, y_pred) or dc.metrics.Metric-like objects exposing
-        ``compute_metric(y, y_pred, w)`` (models.py:191-236)."""
-        y_pred = self.predict(dataset, transformers)
-        if not isinstance(metrics, (list, tuple)):
-            metrics = [metrics]
-        out = {}
-        for m in metrics:
-            if hasattr(m, "compute_metric"):
-                out[getattr(m, "name", m.__class__.__name__)] = m.compute_metric(dataset.y, y_pred, dataset.w)
-            else:
-                out[getattr(m, "__name__", "metric")] = m(dataset.y, y_pred)
-        return out
+    def evaluate(self, dataset, metrics, transformers=[], per_task_metrics=False, use_sample_weights=False,
+                 n_classes=2):
+        """Model.evaluate (models.py:191-236) through the Evaluator's logic: labels and predictions both have the
+        y-transformers undone (deepchem/utils/evaluate.py:303-307)."""
+        from .graphconvmodel import evaluate_model
+        return evaluate_model(self, dataset, metrics, transformers, per_task_metrics, use_sample_weights, n_classes)

@@ -11,6 +11,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import check
+from .engine import AdamSlabState
 
 _AGG = {"mean": 0, "sum": 1, "norm": 2}
 _workspaces = {}
@@ -39,7 +40,7 @@ def tables_struct(topo):
     return st
 
 
-class DmpnnEngine(object):
+class DmpnnEngine(AdamSlabState):
     """Owns the parameter / gradient / Adam slabs of one ``DMPNN`` module."""
 
     def __init__(self, model, device, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
@@ -151,9 +152,7 @@ class DmpnnEngine(object):
                                         self.betas[1], self.eps, self.step_count, grad_scale, self._stream()))
 
     def state_dict(self):
-        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count}
+        return self.optimizer_state_dict(self.model.parameters())
 
     def load_state_dict(self, sd):
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.step_count = int(sd["step"])
+        self.load_optimizer_state_dict(sd, self.model.parameters())

@@ -50,7 +50,68 @@ def topology_struct(topo):
     return st
 
 
-class FlatEngine(object):
+class AdamSlabState(object):
+    """Optimizer state of a flat-slab engine in ``torch.optim.Adam``'s own ``state_dict`` layout.
+
+    The reference stores ``optimizer.state_dict()`` under 'optimizer_state_dict' (torch_model.py:1011-1017) and its
+    restore calls ``Adam.load_state_dict`` on it (torch_model.py:1085-1090); the engines keep their moments in two
+    slabs, so checkpoints are written per parameter — ``state[i] = {step, exp_avg, exp_avg_sq}`` in the order of
+    ``model.parameters()`` plus ``param_groups`` — and read back from that layout.  A checkpoint written by an
+    engine model therefore restores into the per-layer autograd model (plain ``torch.optim.Adam``), into the
+    reference, and the other way round.  Needs: ``_slots`` [(parameter, slab view, grad view)], ``params``,
+    ``exp_avg``, ``exp_avg_sq``, ``step_count``, ``lr``, ``betas``, ``eps``."""
+
+    def _moment_views(self, p_view):
+        off = p_view.storage_offset() - self.params.storage_offset()
+        return (torch.as_strided(self.exp_avg, p_view.shape, p_view.stride(), off),
+                torch.as_strided(self.exp_avg_sq, p_view.shape, p_view.stride(), off))
+
+    def optimizer_state_dict(self, parameters):
+        parameters = list(parameters)
+        view_of = {id(p): v for p, v, _ in self._slots}
+        state = {}
+        if self.step_count > 0:                       # torch creates a parameter's state at its first step
+            for i, p in enumerate(parameters):
+                ea, eas = self._moment_views(view_of[id(p)])
+                state[i] = {"step": torch.tensor(float(self.step_count)), "exp_avg": ea.clone(),
+                            "exp_avg_sq": eas.clone()}
+        group = dict(torch.optim.Adam([torch.zeros(1)], lr=self.lr, betas=tuple(self.betas),
+                                      eps=self.eps).state_dict()["param_groups"][0])
+        group["params"] = list(range(len(parameters)))
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, sd, parameters):
+        if "exp_avg" in sd and "state" not in sd:     # round-1 checkpoints: the raw slabs
+            self.exp_avg.copy_(sd["exp_avg"])
+            self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+            self.step_count = int(sd["step"])
+            return
+        parameters = list(parameters)
+        groups = sd["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) != len(parameters):
+            raise ValueError("optimizer state has %d parameters, the model has %d" % (len(ids), len(parameters)))
+        view_of = {id(p): v for p, v, _ in self._slots}
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        step = 0
+        for key, p in zip(ids, parameters):
+            st = sd["state"].get(key)
+            if st is None:
+                continue
+            ea, eas = self._moment_views(view_of[id(p)])
+            if tuple(st["exp_avg"].shape) != tuple(ea.shape):
+                raise ValueError("optimizer state of parameter %d has shape %s, expected %s"
+                                 % (key, tuple(st["exp_avg"].shape), tuple(ea.shape)))
+            ea.copy_(st["exp_avg"])
+            eas.copy_(st["exp_avg_sq"])
+            step = max(step, int(float(st["step"])))
+        self.step_count = step
+        g0 = groups[0]
+        self.lr, self.betas, self.eps = float(g0["lr"]), tuple(g0["betas"]), float(g0["eps"])
+
+
+class FlatEngine(AdamSlabState):
     """Owns the parameter / gradient / optimizer slabs of one model."""
 
     def __init__(self, model, device, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
@@ -234,9 +295,7 @@ class FlatEngine(object):
         return fwd + bwd + 1
 
     def state_dict(self):
-        return {"exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq, "step": self.step_count}
+        return self.optimizer_state_dict(self.model.parameters())
 
     def load_state_dict(self, sd):
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
-        self.step_count = int(sd["step"])
+        self.load_optimizer_state_dict(sd, self.model.parameters())

@@ -117,7 +117,7 @@ class _GraphConvTorchModel(nn.Module):
                  graph_conv_layers: List[int] = [64, 64], dense_layer_size: int = 128, dropout=0.0,
                  mode: str = "classification", number_atom_features: int = 75, n_classes: int = 2,
                  batch_normalize: bool = True, uncertainty: bool = False, batch_size: int = 100,
-                 gemm_mode: str = "fp32", sync_batch_norm: bool = False):
+                 gemm_mode: str = "tf32x3", sync_batch_norm: bool = False):
         super(_GraphConvTorchModel, self).__init__()
         if mode not in ['classification', 'regression']:
             raise ValueError("mode must be either 'classification' or 'regression'")
@@ -234,6 +234,48 @@ def _undo_transforms(y, transformers):
     return y
 
 
+def evaluate_model(model, dataset, metrics, transformers=[], per_task_metrics=False, use_sample_weights=False,
+                   n_classes=2):
+    """Evaluator.compute_model_performance (deepchem/utils/evaluate.py:246-333): the y-transformers are undone on the
+    dataset's labels AND on the predictions before the metrics see them (:303-307), metrics may be
+    ``dc.metrics.Metric``-like objects (``compute_metric(y, y_pred, w, per_task_metrics=, n_tasks=, n_classes=,
+    use_sample_weights=)``, name in ``.name``) or plain functions f(y_true, y_pred), which get the reference's default
+    wrapping: the mean over tasks of f on each task column.  -> {name: score}, and with ``per_task_metrics`` a second
+    dict {name: per-task scores}."""
+    import inspect
+    y = _undo_transforms(np.asarray(dataset.y), transformers)
+    w = dataset.w
+    y_pred = model.predict(dataset, transformers)
+    n_tasks = int(y.shape[1]) if np.ndim(y) > 1 else 1
+    if not isinstance(metrics, (list, tuple)):
+        metrics = [metrics]
+    scores, per_task = {}, {}
+    for m in metrics:
+        if hasattr(m, "compute_metric"):
+            name = getattr(m, "name", m.__class__.__name__)
+            try:
+                accepted = set(inspect.signature(m.compute_metric).parameters)
+            except (TypeError, ValueError):
+                accepted = set()
+            kw = {k: v for k, v in (("per_task_metrics", per_task_metrics), ("n_tasks", n_tasks),
+                                    ("n_classes", n_classes), ("use_sample_weights", use_sample_weights))
+                  if k in accepted}
+            res = m.compute_metric(y, y_pred, w, **kw)
+            if per_task_metrics and "per_task_metrics" in kw:
+                scores[name], per_task[name] = res
+            else:
+                scores[name] = res
+        else:
+            name = getattr(m, "__name__", "metric")
+            yt = np.reshape(y, (len(y), n_tasks))
+            yp = np.reshape(y_pred, (len(y_pred), n_tasks, -1))
+            yp = yp[..., 0] if yp.shape[-1] == 1 else yp
+            per = [float(m(yt[:, t], yp[:, t])) for t in range(n_tasks)]
+            scores[name] = float(np.mean(per))
+            per_task[name] = per
+    return (scores, per_task) if per_task_metrics else scores
+
+
 def to_one_hot(y, n_classes=2):
     """deepchem.metrics.to_one_hot"""
     y = np.asarray(y).astype(np.int64).reshape(-1)
@@ -275,6 +317,64 @@ class _DeviceSlot(object):
 
 
 _PINNED_RESULT_LIMIT = 4 << 30      # predict(): largest result kept in one page-locked array
+
+
+class _PinnedRing(object):
+    """Reusable page-locked staging buffers for the host side of a batch (page-locked allocations cost milliseconds,
+    so they are made once).  A slot is handed out again only when (1) nothing references the arrays built in it any
+    more — a weak reference to the root numpy array every view of the batch hangs off (or to the tensor handed to the
+    gather) — and (2) the upload that read it has finished.  A caller that keeps batches alive — ``list(model.
+    default_generator(ds))``, multi-epoch reuse of a materialised list, a consumer lagging behind — therefore never
+    sees an earlier batch overwritten (the reference's generator yields independent arrays, graphconvmodel.py:382-422):
+    the ring grows up to ``max_slots`` and, past that, ``take`` returns ``(None, None)`` and the caller builds into
+    ordinary memory."""
+
+    def __init__(self, max_slots=64, pin=True):
+        import threading
+        self.pin = pin
+        self.slots = []              # [tensor, upload event or None, weakref to the owner or None / _BUSY]
+        self.next = 0
+        self.max_slots = max_slots
+        self.lock = threading.Lock()
+
+    _BUSY = object()                 # handed out, owner not registered yet
+
+    @staticmethod
+    def _free(slot):
+        o = slot[2]
+        return o is None or (o is not _PinnedRing._BUSY and o() is None)
+
+    def take(self, nbytes):
+        import weakref
+        slot = None
+        with self.lock:
+            n = len(self.slots)
+            for k in range(n):
+                cand = self.slots[(self.next + k) % n]
+                if self._free(cand):
+                    slot = cand
+                    self.next = (self.next + k + 1) % n
+                    break
+            if slot is None:
+                if n >= self.max_slots:
+                    return None, None
+                slot = [torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=self.pin), None, None]
+                self.slots.append(slot)
+            slot[2] = self._BUSY
+        if slot[1] is not None:
+            slot[1].synchronize()    # the H2D copy that read the previous batch out of this buffer
+            slot[1] = None
+        if slot[0].numel() < nbytes:
+            slot[0] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=self.pin)
+        root = slot[0].numpy()
+        slot[2] = weakref.ref(root)
+        return slot, root
+
+    @staticmethod
+    def own(slot, obj):
+        """The object whose lifetime keeps the slot busy (default: the root array returned by take)."""
+        import weakref
+        slot[2] = weakref.ref(obj)
 
 
 class _Prefetcher(object):
@@ -398,7 +498,7 @@ class GraphConvModel(object):
     def __init__(self, n_tasks, *args, graph_conv_layers=None, number_input_features=None,
                  dense_layer_size=128, dropout=0.0, mode="classification", number_atom_features=75,
                  n_classes=2, batch_size=100, batch_normalize=True, uncertainty=False,
-                 learning_rate=0.001, model_dir=None, device=None, gemm_mode="fp32", log_frequency=100,
+                 learning_rate=0.001, model_dir=None, device=None, gemm_mode="tf32x3", log_frequency=100,
                  use_engine=True, sync_batch_norm=False, **kwargs):
         args = list(args)
         if args and isinstance(args[0], (list, tuple)):
@@ -468,11 +568,8 @@ class GraphConvModel(object):
                     self._fwd_events.append(ev)
         # per-stage host timers of the fit pipeline (scripts/e2e_stages.py); None = off
         self._pipe_trace = collections.defaultdict(float) if os.environ.get("DCGC_PIPE_TRACE") == "1" else None
-        self._staging = []          # ring of reusable pinned slabs: [tensor, event]
-        self._staging_next = 0
-        self._feat_staging, self._feat_staging_next = [], 0   # same, for gathered features of shuffled batches
-        import threading
-        self._staging_lock = threading.Lock()
+        self._staging = _PinnedRing()          # reusable pinned slabs of the batch layouts
+        self._feat_staging = _PinnedRing()     # same, for the gathered features of shuffled batches
         # host threads building batch layouts ahead of the GPU (default_generator)
         self.host_workers = int(os.environ.get("DCGC_HOST_WORKERS", _default_host_workers()))
         # fused whole-model engine (flat parameter slab, one C call per step) when the model shape
@@ -525,40 +622,12 @@ class GraphConvModel(object):
                 yield (fut.result(), [y0], [w0])
 
     def _staging_slab(self, nbytes):
-        """Next pinned staging buffer of the ring (page-locked allocations are expensive, so they are
-        made once and reused; a slot is reused only after the H2D copy that read it has finished).
-        The ring is longer than the deepest host pipeline (layout workers + prefetch queue), so a
-        slot is never handed out again before its previous batch has been uploaded."""
-        ring = 2 * max(1, self.host_workers) + 8
-        with self._staging_lock:
-            if len(self._staging) < ring:
-                self._staging.append([torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True), None])
-                return self._staging[-1]
-            slot = self._staging[self._staging_next % ring]
-            self._staging_next += 1
-        if slot[1] is not None:
-            slot[1].synchronize()
-            slot[1] = None
-        if slot[0].numel() < nbytes:
-            slot[0] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
-        return slot
+        """-> (slot, root) from the ring of pinned slabs, or (None, None) when every slot is still referenced."""
+        return self._staging.take(nbytes)
 
     def _feature_staging(self, nbytes):
-        """Pinned staging buffer for the gathered features of a shuffled batch (same ring discipline as
-        ``_staging_slab``: reused only after the upload that read it has finished)."""
-        ring = 2 * max(1, self.host_workers) + 8
-        with self._staging_lock:
-            if len(self._feat_staging) < ring:
-                self._feat_staging.append([torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True), None])
-                return self._feat_staging[-1]
-            slot = self._feat_staging[self._feat_staging_next % ring]
-            self._feat_staging_next += 1
-        if slot[1] is not None:
-            slot[1].synchronize()
-            slot[1] = None
-        if slot[0].numel() < nbytes:
-            slot[0] = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, pin_memory=True)
-        return slot
+        """Same ring discipline for the gathered features of a shuffled batch."""
+        return self._feat_staging.take(nbytes)
 
     def batch_inputs(self, X_b, pinned=True):
         pinned = pinned and torch.cuda.is_available()     # host-only callers (tests) get plain memory
@@ -570,22 +639,27 @@ class GraphConvModel(object):
             if pinned:
                 def alloc(n_atoms, n_feat, dtype):
                     nbytes = n_atoms * n_feat * np.dtype(dtype).itemsize
-                    fs = self._feature_staging(nbytes)
-                    feat_slots.append(fs)
                     tdt = torch.int8 if np.dtype(dtype) == np.int8 else torch.float32
-                    return fs[0][:nbytes].view(tdt).view(n_atoms, n_feat)
+                    fs, _ = self._feature_staging(nbytes)
+                    if fs is None:               # every slot still referenced by batches the caller keeps
+                        return torch.empty((n_atoms, n_feat), dtype=tdt)
+                    t = fs[0][:nbytes].view(tdt).view(n_atoms, n_feat)
+                    _PinnedRing.own(fs, t)       # busy while the gathered shard (its _pin / _pin_i8) is alive
+                    feat_slots.append(fs)
+                    return t
             X_b = X_b.resolve(alloc=alloc, prefer_i8=bool(pinned and _USE_I8), n_threads=1)
         packed = X_b if isinstance(X_b, PackedMols) else pack_convmols(X_b)
         n_seg = max(self.batch_size, packed.n_mols)
-        slot = None
+        slot = root = None
         if pinned:
             # upper bound of the slab size without running the planner: 11 int32 arrays over atoms /
             # edges / segments plus alignment
             need = 4 * (5 * (packed.n_atoms + 2) + 3 * int(packed.adj_ptr[-1]) + (n_seg + 2)
                         + 4 * (packed.n_atoms // 128 + 12) + 12 * (packed.n_atoms // 4 + 4)) + 256 * 16
-            slot = self._staging_slab(need)
-        layout = BatchLayout.build(packed, n_segments=n_seg, pinned=pinned,
-                                   staging=slot[0] if slot is not None else None)
+            slot, root = self._staging_slab(need)
+        layout = BatchLayout.build(packed, n_segments=n_seg, pinned=pinned and slot is not None,
+                                   staging=slot[0] if slot is not None else None,
+                                   staging_root=root if slot is not None else None)
         layout._staging_slot = slot
         inputs = BatchInputs([None, layout.deg_slice, layout.membership, np.array(packed.n_mols)]
                              + layout.deg_adjacency_lists()[1:])
@@ -943,19 +1017,10 @@ class GraphConvModel(object):
         gen = self.default_generator(dataset, mode='predict', deterministic=True, pad_batches=False)
         return self._predict(gen, self._embedding_outputs)
 
-    def evaluate(self, dataset, metrics, transformers=[], per_task_metrics=False):
-        """{name: score} for metric callables f(y_true, y_pred[, w]) or dc.metrics.Metric-like
-        objects exposing ``compute_metric(y, y_pred, w)``."""
-        y_pred = self.predict(dataset, transformers)
-        if not isinstance(metrics, (list, tuple)):
-            metrics = [metrics]
-        out = {}
-        for m in metrics:
-            if hasattr(m, "compute_metric"):
-                out[getattr(m, "name", m.__class__.__name__)] = m.compute_metric(dataset.y, y_pred, dataset.w)
-            else:
-                out[getattr(m, "__name__", "metric")] = m(dataset.y, y_pred)
-        return out
+    def evaluate(self, dataset, metrics, transformers=[], per_task_metrics=False, use_sample_weights=False,
+                 n_classes=2):
+        """Model.evaluate (models.py:191-236) through the Evaluator's logic (``evaluate_model``)."""
+        return evaluate_model(self, dataset, metrics, transformers, per_task_metrics, use_sample_weights, n_classes)
 
     # ------------------------------------------------------------------ checkpoints
     def get_checkpoints(self, model_dir=None):
@@ -971,6 +1036,10 @@ class GraphConvModel(object):
         model_dir = model_dir or self.model_dir
         if model_dir is None:
             raise ValueError("model_dir is not set")
+        if self._dp:
+            from .parallel import rank
+            if rank() != 0:                      # replicas are identical: one writer (ranks raced on the same files)
+                return
         os.makedirs(model_dir, exist_ok=True)
         opt = self._engine.state_dict() if self._engine is not None else self._pytorch_optimizer.state_dict()
         data = {'model_state_dict': self.model.state_dict(), 'optimizer_state_dict': opt,
@@ -993,10 +1062,15 @@ class GraphConvModel(object):
             checkpoint = cps[0]
         data = torch.load(checkpoint, map_location=self.device)
         self.model.load_state_dict(data['model_state_dict'])
-        if self._engine is not None and 'exp_avg' in data['optimizer_state_dict']:
-            self._engine.load_state_dict(data['optimizer_state_dict'])
-        elif self._engine is None:
-            self._pytorch_optimizer.load_state_dict(data['optimizer_state_dict'])
+        opt = data['optimizer_state_dict']
+        if self._engine is not None:
+            self._engine.load_state_dict(opt)           # torch.optim.Adam layout (or a round-1 slab checkpoint)
+        elif 'state' in opt:
+            self._pytorch_optimizer.load_state_dict(opt)
+        else:
+            raise ValueError("this checkpoint holds the raw moment slabs of the fused engine (written before the "
+                             "optimizer state was saved in torch.optim.Adam's layout); restore it into a model "
+                             "that uses the engine")
         self._global_step = data['global_step']
 
     def get_global_step(self):

@@ -212,9 +212,11 @@ class BatchLayout(object):
         return np.empty(nbytes, dtype=np.uint8), None
 
     @staticmethod
-    def build(packed, n_segments=None, pinned=False, staging=None):
+    def build(packed, n_segments=None, pinned=False, staging=None, staging_root=None):
         """Run the C++ builder on a PackedMols shard (replaces agglomerate_mols).  ``staging``: an
-        optional reusable pinned torch uint8 tensor to build into (grown by the caller)."""
+        optional reusable pinned torch uint8 tensor to build into (grown by the caller);
+        ``staging_root``: its numpy view that every array of the layout should hang off (the caller
+        tracks that array's lifetime to know when the buffer may be reused)."""
         L = _lib.lib()
         n_mols = packed.n_mols
         if n_segments is None:
@@ -223,7 +225,8 @@ class BatchLayout(object):
         _lib.check(L.dcgc_layout_plan(n_mols, _ptr(packed.atom_ptr), _ptr(packed.adj_ptr), n_segments,
                                       _lib.TILE_ROWS, ctypes.byref(info)))
         if staging is not None and staging.numel() >= int(info.slab_bytes):
-            slab, t = staging.numpy()[:int(info.slab_bytes)], staging
+            root = staging_root if staging_root is not None else staging.numpy()
+            slab, t = root[:int(info.slab_bytes)], staging
         else:
             slab, t = BatchLayout._alloc(int(info.slab_bytes), pinned)
         _lib.check(L.dcgc_layout_build(n_mols, _ptr(packed.atom_ptr), _ptr(packed.adj_ptr),

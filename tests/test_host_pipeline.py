@@ -17,7 +17,7 @@ def _host_model(batch_size, workers):
     m = G.GraphConvModel.__new__(G.GraphConvModel)      # host-only: no CUDA objects are created
     m.batch_size, m.mode, m.n_tasks, m.n_classes = batch_size, 'regression', 1, 2
     m.host_workers = workers
-    m._staging, m._staging_next, m._staging_lock = [], 0, threading.Lock()
+    m._staging, m._feat_staging = G._PinnedRing(pin=False), G._PinnedRing(pin=False)
     return m
 
 
@@ -246,3 +246,64 @@ def test_constructor_errors_follow_the_reference():
     m = make(2, graph_conv_layers=[64, 64], dropout=[0.1, 0.2, 0.3], mode="regression", uncertainty=True)
     assert [d.p for d in m.dropouts] == [0.1, 0.2, 0.3] and hasattr(m, "uncertainty_dense")
     assert len(m.graph_convs[0].W_list) == 21 and tuple(m.graph_convs[0].W_list[0].shape) == (75, 64)    # layers.py:6140-6151
+
+
+def test_staging_ring_never_overwrites_a_batch_that_is_still_referenced():
+    """The reference's generator yields independent arrays (graphconvmodel.py:382-422): a materialised list of
+    batches, or a consumer lagging behind, must not see earlier batches change.  The pinned staging ring hands a
+    slot out again only after every array built in it is gone."""
+    import gc
+    ring = G._PinnedRing(max_slots=4, pin=False)
+    held = []
+    for i in range(4):
+        slot, root = ring.take(1024)
+        root[:8] = i
+        held.append(root[:8])                     # a VIEW keeps the slot busy, not only the root
+        del root
+    assert len(ring.slots) == 4
+    assert ring.take(1024) == (None, None)        # every slot referenced: the caller must use ordinary memory
+    assert [int(h[0]) for h in held] == [0, 1, 2, 3]
+    held.pop(1)
+    gc.collect()
+    slot, root = ring.take(1024)                  # the released slot is found again, the others are untouched
+    assert slot is ring.slots[1]
+    root[:8] = 9
+    assert [int(h[0]) for h in held] == [0, 2, 3]
+    # a slot grows when a larger batch needs it
+    del root
+    gc.collect()
+    slot, root = ring.take(1 << 20)
+    assert root.shape[0] >= 1 << 20
+
+
+def test_materialised_generator_keeps_every_batch_intact():
+    """list(default_generator(ds)) with more batches than the ring holds: every layout still equals a fresh build."""
+    from deepchem_b200.mol_graphs import BatchLayout
+    pm = make_molecules(600, seed=9, shape="stress")
+    ds = PackedDataset(pm, np.zeros((600, 1), np.float32), np.ones((600, 1), np.float32))
+    m = _host_model(16, 2)
+    m._staging = G._PinnedRing(max_slots=6, pin=False)
+    real_take = m._staging.take
+    m.batch_inputs = lambda X_b, pinned=True: _batch_inputs_with_ring(m, X_b)
+    batches = list(m.default_generator(ds, workers=2))
+    assert len(batches) == 38 > 6
+    for k, (inp, _, _) in enumerate(batches):
+        fresh = BatchLayout.build(pm.take(np.arange(16 * k, min(600, 16 * k + 16))) if 16 * k + 16 <= 600
+                                  else inp.layout_source, n_segments=16)
+        for f in FIELDS:
+            assert np.array_equal(getattr(inp.layout, f), getattr(fresh, f)), (k, f)
+    assert real_take is not None
+
+
+def _batch_inputs_with_ring(m, X_b):
+    """batch_inputs with the ring in use although no GPU is present (the product only uses it for pinned memory)."""
+    from deepchem_b200.mol_graphs import BatchLayout
+    packed = X_b.resolve() if isinstance(X_b, G.LazyTake) else X_b
+    slot, root = m._staging.take(1 << 16)
+    layout = BatchLayout.build(packed, n_segments=max(m.batch_size, packed.n_mols),
+                               staging=slot[0] if slot is not None else None, staging_root=root)
+    inputs = G.BatchInputs([None, layout.deg_slice, layout.membership, np.array(packed.n_mols)]
+                           + layout.deg_adjacency_lists()[1:])
+    inputs.layout = layout
+    inputs.layout_source = packed
+    return inputs
