@@ -57,6 +57,7 @@ class GcModelConfig(Structure):
         ("n_layers", c_int32), ("n_feat", c_int32), ("widths", c_int32 * MODEL_MAX_LAYERS),
         ("dense", c_int32), ("n_out", c_int32), ("n_classes", c_int32), ("mode", c_int32),
         ("batch_norm", c_int32), ("gemm_mode", c_int32), ("bn_eps", c_float), ("bn_momentum", c_float),
+        ("input_exact", c_int32), ("reserved", c_int32),
     ]
 
 

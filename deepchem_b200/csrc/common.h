@@ -62,7 +62,18 @@ struct DcgcWgradArgs {
   int64_t group_row0[DCGC_N_DEG + 1];
   int chunk_prefix[DCGC_N_DEG + 1];
   int a1_vec, a2_vec, g_vec;
+  int a_exact;      // [a1 | a2] holds tf32-exact values (see DcgcGemmOpts): the lo(A) tiles and their MMA are skipped
   long long* dbg;   // optional timeline buffer (dcgcdbg_tc_timeline)
+};
+// Explicit per-call options of the tensor-core GEMMs (no thread-local side channels):
+//   img      a weight image built ahead with dcgc_tc_prep_weights (e.g. on another stream); null = the call builds
+//            its own in a stream-ordered scratch allocation (cudaMallocAsync / cudaFreeAsync on the launch stream)
+//   a_exact  every value of the A operand is exactly representable in tf32 (integer-valued atom features and
+//            their neighbour sums below 2^11): its lo part is identically zero, so the lo(A) tile and the
+//            lo(A) * hi(W) term are skipped — a third of the tensor time, bit-identical results
+struct DcgcGemmOpts {
+  const float* img = nullptr;
+  int a_exact = 0;
 };
 int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p, int chunks, cudaStream_t st);
 int dcgc_tc_wgrad_grid_y(int k_total, int n);
@@ -71,11 +82,27 @@ int dcgc_tc_num_sms();
 int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2, int64_t ld_a2, int k2, const float* w,
                  int n_groups, int trans_w, const float* bias, int n1, int n2, const int32_t* tiles, int64_t n_tiles,
                  int64_t n_rows, int act, float* c1, int64_t ld_c1, float* c2, int64_t ld_c2, cudaStream_t st,
-                 double* stats = nullptr, int* stats_chunks = nullptr);
-// early weight images (gemm_tc.cu): build on any stream, hand to the next dcgc_tc_gemm of this thread
+                 double* stats = nullptr, int* stats_chunks = nullptr, const DcgcGemmOpts* opts = nullptr);
+// early weight images (gemm_tc.cu): build on any stream, pass to the GEMM in DcgcGemmOpts::img
 int64_t dcgc_tc_image_bytes(int nt, int k1, int k2, int N, int n_groups);
 int dcgc_tc_prep_weights(int nt, const float* w, int n_groups, int trans_w, int k1, int k2, int N, float* img, cudaStream_t st);
-void dcgc_tc_set_next_image(const float* img);
+// the C-ABI entry points of gemm_simt.cu with explicit options (used by the fused engines)
+int dcgc_group_gemm_fwd_opts(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2, int64_t ld_a2,
+                             int32_t k2, const float* w, const float* bias, int32_t n, const int32_t* tiles,
+                             int64_t n_tiles, int32_t tile_rows, int64_t n_rows, int32_t act, float* y, int64_t ld_y,
+                             double* stats_part, int32_t* n_chunks_out, const DcgcGemmOpts& opts, void* stream);
+int dcgc_group_gemm_dgrad_opts(int32_t mode, const float* g, int64_t ld_g, int32_t n, const float* w, int32_t k1,
+                               int32_t k2, const int32_t* tiles, int64_t n_tiles, int32_t tile_rows, int64_t n_rows,
+                               float* d1, int64_t ld_d1, float* d2, int64_t ld_d2, const DcgcGemmOpts& opts, void* stream);
+int dcgc_linear_fwd_opts(int32_t mode, const float* x, int64_t ld_x, int32_t k, const float* w, const float* bias,
+                         int32_t n, int64_t n_rows, int32_t act, float* y, int64_t ld_y, double* stats_part,
+                         int32_t* n_chunks_out, const DcgcGemmOpts& opts, void* stream);
+int dcgc_linear_dgrad_opts(int32_t mode, const float* g, int64_t ld_g, int32_t n, const float* w, int32_t k,
+                           int64_t n_rows, float* dx, int64_t ld_dx, const DcgcGemmOpts& opts, void* stream);
+int dcgc_group_gemm_wgrad_opts(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2, int64_t ld_a2,
+                               int32_t k2, const float* g, int64_t ld_g, int32_t n, const int64_t* deg_count,
+                               int32_t n_groups, float* dw, float* dbias, void* workspace, int64_t workspace_bytes,
+                               int a_exact, void* stream);
 #endif
 
 static inline int64_t dcgc_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }

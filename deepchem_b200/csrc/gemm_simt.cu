@@ -369,7 +369,7 @@ static int group_gemm_fwd_impl(int32_t mode, const float* a1, int64_t ld_a1, int
                                int64_t ld_a2, int32_t k2, const float* w, const float* bias, int32_t n,
                                const int32_t* tiles, int64_t n_tiles, int32_t tile_rows, int64_t n_rows,
                                int32_t act, float* y, int64_t ld_y, double* stats, int32_t* stats_chunks,
-                               void* stream) {
+                               void* stream, const DcgcGemmOpts* opts = nullptr) {
   if (stats_chunks) *stats_chunks = 0;
   DCGC_CHECK_ARG(stats == nullptr || dcgc_tc_terms(mode) != 0,
                  "dcgc_group_gemm_fwd_stats: fused column statistics exist in DCGC_GEMM_TF32X3 mode only");
@@ -386,7 +386,7 @@ static int group_gemm_fwd_impl(int32_t mode, const float* a1, int64_t ld_a1, int
   DcgcProfScope prof_scope("dcgc_group_gemm_fwd", (cudaStream_t)stream);
   if (dcgc_tc_terms(mode))
     return dcgc_tc_gemm(dcgc_tc_terms(mode), a1, ld_a1, k1, a2, ld_a2, a2 ? k2 : 0, w, tiles ? DCGC_N_DEG : 1, 1, bias, n, 0, tiles, n_tiles,
-                        n_rows, act, y, ld_y, nullptr, 0, (cudaStream_t)stream, stats, stats_chunks);
+                        n_rows, act, y, ld_y, nullptr, 0, (cudaStream_t)stream, stats, stats_chunks, opts);
   GemmArgs p{};
   p.a1 = a1; p.ld_a1 = ld_a1; p.k1 = k1;
   p.a2 = a2; p.ld_a2 = ld_a2; p.k2 = a2 ? k2 : 0;
@@ -434,10 +434,10 @@ extern "C" int dcgc_group_gemm_fwd_stats(int32_t mode, const float* a1, int64_t 
 
 extern "C" int32_t dcgc_gemm_stats_max_chunks(void) { return dcgc_tc_num_sms(); }
 
-extern "C" int dcgc_group_gemm_dgrad(int32_t mode, const float* g, int64_t ld_g, int32_t n, const float* w,
-                                     int32_t k1, int32_t k2, const int32_t* tiles, int64_t n_tiles,
-                                     int32_t tile_rows, int64_t n_rows, float* d1, int64_t ld_d1, float* d2,
-                                     int64_t ld_d2, void* stream) {
+static int group_gemm_dgrad_impl(int32_t mode, const float* g, int64_t ld_g, int32_t n, const float* w,
+                                 int32_t k1, int32_t k2, const int32_t* tiles, int64_t n_tiles,
+                                 int32_t tile_rows, int64_t n_rows, float* d1, int64_t ld_d1, float* d2,
+                                 int64_t ld_d2, void* stream, const DcgcGemmOpts* opts) {
   DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || dcgc_tc_terms(mode) != 0,
                  "dcgc_group_gemm_dgrad: GEMM mode %d is not available in this build", mode);
   DCGC_CHECK_ARG(k1 >= 0 && k2 >= 0 && n >= 0 && n_rows >= 0 && ld_g >= n, "dcgc_group_gemm_dgrad: bad sizes");
@@ -449,7 +449,7 @@ extern "C" int dcgc_group_gemm_dgrad(int32_t mode, const float* g, int64_t ld_g,
   DcgcProfScope prof_scope("dcgc_group_gemm_dgrad", (cudaStream_t)stream);
   if (dcgc_tc_terms(mode))
     return dcgc_tc_gemm(dcgc_tc_terms(mode), g, ld_g, n, nullptr, 0, 0, w, tiles ? DCGC_N_DEG : 1, 0, nullptr, k1, k2, tiles, n_tiles,
-                        n_rows, DCGC_ACT_NONE, d1, ld_d1, d2, ld_d2, (cudaStream_t)stream);
+                        n_rows, DCGC_ACT_NONE, d1, ld_d1, d2, ld_d2, (cudaStream_t)stream, nullptr, nullptr, opts);
   GemmArgs p{};
   p.a1 = g; p.ld_a1 = ld_g; p.k1 = n;
   p.a2 = nullptr; p.ld_a2 = 0; p.k2 = 0;
@@ -478,6 +478,28 @@ extern "C" int dcgc_group_gemm_dgrad(int32_t mode, const float* g, int64_t ld_g,
   return DCGC_OK;
 }
 
+extern "C" int dcgc_group_gemm_dgrad(int32_t mode, const float* g, int64_t ld_g, int32_t n, const float* w,
+                                     int32_t k1, int32_t k2, const int32_t* tiles, int64_t n_tiles,
+                                     int32_t tile_rows, int64_t n_rows, float* d1, int64_t ld_d1, float* d2,
+                                     int64_t ld_d2, void* stream) {
+  return group_gemm_dgrad_impl(mode, g, ld_g, n, w, k1, k2, tiles, n_tiles, tile_rows, n_rows, d1, ld_d1, d2, ld_d2,
+                               stream, nullptr);
+}
+int dcgc_group_gemm_dgrad_opts(int32_t mode, const float* g, int64_t ld_g, int32_t n, const float* w, int32_t k1,
+                               int32_t k2, const int32_t* tiles, int64_t n_tiles, int32_t tile_rows, int64_t n_rows,
+                               float* d1, int64_t ld_d1, float* d2, int64_t ld_d2, const DcgcGemmOpts& opts,
+                               void* stream) {
+  return group_gemm_dgrad_impl(mode, g, ld_g, n, w, k1, k2, tiles, n_tiles, tile_rows, n_rows, d1, ld_d1, d2, ld_d2,
+                               stream, &opts);
+}
+int dcgc_group_gemm_fwd_opts(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2, int64_t ld_a2,
+                             int32_t k2, const float* w, const float* bias, int32_t n, const int32_t* tiles,
+                             int64_t n_tiles, int32_t tile_rows, int64_t n_rows, int32_t act, float* y, int64_t ld_y,
+                             double* stats_part, int32_t* n_chunks_out, const DcgcGemmOpts& opts, void* stream) {
+  return group_gemm_fwd_impl(mode, a1, ld_a1, k1, a2, ld_a2, k2, w, bias, n, tiles, n_tiles, tile_rows, n_rows, act, y,
+                             ld_y, stats_part, n_chunks_out, stream, &opts);
+}
+
 extern "C" int64_t dcgc_group_gemm_wgrad_workspace(int32_t k1, int32_t k2, int32_t n, int32_t n_groups) {
   if (k1 < 0 || k2 < 0 || n < 0 || n_groups < 1 || n_groups > DCGC_N_DEG) return 0;
   const int64_t chunks = kTargetChunks + n_groups;
@@ -487,7 +509,7 @@ extern "C" int64_t dcgc_group_gemm_wgrad_workspace(int32_t k1, int32_t k2, int32
 static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2,
                       int64_t ld_a2, int32_t k2, const float* g, int64_t ld_g, int32_t n,
                       const int64_t* deg_count, int32_t n_groups, float* dw, float* dbias,
-                      void* workspace, int64_t workspace_bytes, int transpose, void* stream) {
+                      void* workspace, int64_t workspace_bytes, int transpose, void* stream, int a_exact = 0) {
   DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || dcgc_tc_terms(mode) != 0,
                  "dcgc_group_gemm_wgrad: GEMM mode %d is not available in this build", mode);
   DCGC_CHECK_ARG(k1 >= 0 && k2 >= 0 && n >= 0 && ld_a1 >= k1 && ld_g >= n, "dcgc_group_gemm_wgrad: bad sizes");
@@ -549,6 +571,7 @@ static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, 
   p.a1_vec = ld_a1 % 4 == 0 && aligned16(a1);
   p.a2_vec = a2 && ld_a2 % 4 == 0 && aligned16(a2);
   p.g_vec = ld_g % 4 == 0 && aligned16(g);
+  p.a_exact = (a_exact && mode == DCGC_GEMM_TF32X3) ? 1 : 0;
   DcgcProfScope prof_scope("dcgc_group_gemm_wgrad", (cudaStream_t)stream);
   cudaStream_t st = (cudaStream_t)stream;
   if (chunks > 0 && tc) {
@@ -582,6 +605,13 @@ extern "C" int dcgc_group_gemm_wgrad(int32_t mode, const float* a1, int64_t ld_a
   return wgrad_impl(mode, a1, ld_a1, k1, a2, ld_a2, k2, g, ld_g, n, deg_count, n_groups, dw, dbias, workspace,
                     workspace_bytes, 0, stream);
 }
+int dcgc_group_gemm_wgrad_opts(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2, int64_t ld_a2,
+                               int32_t k2, const float* g, int64_t ld_g, int32_t n, const int64_t* deg_count,
+                               int32_t n_groups, float* dw, float* dbias, void* workspace, int64_t workspace_bytes,
+                               int a_exact, void* stream) {
+  return wgrad_impl(mode, a1, ld_a1, k1, a2, ld_a2, k2, g, ld_g, n, deg_count, n_groups, dw, dbias, workspace,
+                    workspace_bytes, 0, stream, a_exact);
+}
 
 // ------------------------------------------------------------------------------------------
 // nn.Linear-layout helpers (weight stored [n_out, k_in] as torch does): the atom-level Dense
@@ -589,7 +619,7 @@ extern "C" int dcgc_group_gemm_wgrad(int32_t mode, const float* a1, int64_t ld_a
 // ------------------------------------------------------------------------------------------
 static int linear_fwd_impl(int32_t mode, const float* x, int64_t ld_x, int32_t k, const float* w, const float* bias,
                            int32_t n, int64_t n_rows, int32_t act, float* y, int64_t ld_y, double* stats,
-                           int32_t* stats_chunks, void* stream) {
+                           int32_t* stats_chunks, void* stream, const DcgcGemmOpts* opts = nullptr) {
   if (stats_chunks) *stats_chunks = 0;
   DCGC_CHECK_ARG(stats == nullptr || dcgc_tc_terms(mode) != 0,
                  "dcgc_linear_fwd_stats: fused column statistics exist in DCGC_GEMM_TF32X3 mode only");
@@ -602,7 +632,7 @@ static int linear_fwd_impl(int32_t mode, const float* x, int64_t ld_x, int32_t k
   DcgcProfScope prof_scope("dcgc_linear_fwd", (cudaStream_t)stream);
   if (dcgc_tc_terms(mode))
     return dcgc_tc_gemm(dcgc_tc_terms(mode), x, ld_x, k, nullptr, 0, 0, w, 1, 0, bias, n, 0, nullptr, 0, n_rows, act, y, ld_y, nullptr, 0,
-                        (cudaStream_t)stream, stats, stats_chunks);
+                        (cudaStream_t)stream, stats, stats_chunks, opts);
   GemmArgs p{};
   p.a1 = x; p.ld_a1 = ld_x; p.k1 = k;
   p.w = w; p.w_group_stride = 0; p.ld_w = k;
@@ -637,6 +667,17 @@ extern "C" int dcgc_linear_fwd_stats(int32_t mode, const float* x, int64_t ld_x,
                                      int64_t ld_y, double* stats_part, int32_t* n_chunks_out, void* stream) {
   DCGC_CHECK_ARG(stats_part && n_chunks_out, "dcgc_linear_fwd_stats: null statistics buffer");
   return linear_fwd_impl(mode, x, ld_x, k, w, bias, n, n_rows, act, y, ld_y, stats_part, n_chunks_out, stream);
+}
+
+int dcgc_linear_fwd_opts(int32_t mode, const float* x, int64_t ld_x, int32_t k, const float* w, const float* bias,
+                         int32_t n, int64_t n_rows, int32_t act, float* y, int64_t ld_y, double* stats_part,
+                         int32_t* n_chunks_out, const DcgcGemmOpts& opts, void* stream) {
+  return linear_fwd_impl(mode, x, ld_x, k, w, bias, n, n_rows, act, y, ld_y, stats_part, n_chunks_out, stream, &opts);
+}
+int dcgc_linear_dgrad_opts(int32_t mode, const float* g, int64_t ld_g, int32_t n, const float* w, int32_t k,
+                           int64_t n_rows, float* dx, int64_t ld_dx, const DcgcGemmOpts& opts, void* stream) {
+  return group_gemm_fwd_impl(mode, g, ld_g, n, nullptr, 0, 0, w, nullptr, k, nullptr, 0, BM, n_rows, DCGC_ACT_NONE, dx,
+                             ld_dx, nullptr, nullptr, stream, &opts);
 }
 
 extern "C" int dcgc_linear_dgrad(int32_t mode, const float* g, int64_t ld_g, int32_t n, const float* w, int32_t k,

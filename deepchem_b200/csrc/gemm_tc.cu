@@ -142,9 +142,13 @@ __device__ __forceinline__ float term_hi(float x) { return NT == 3 ? tf32_hi(x) 
 __device__ __forceinline__ float4 round4_bf16(const float4 v) {
   return make_float4(bf16_round(v.x), bf16_round(v.y), bf16_round(v.z), bf16_round(v.w));
 }
+// x = hi + lo with hi = rna_tf32(x), lo = x - hi (exact in fp32).  The tensor core reads lo as tf32, i.e. cuts its
+// low 13 mantissa bits: an error of at most 2^-21 |x| per element.  (Rounding lo to tf32 first — one more cvt per
+// value — was measured: no visible change in any parity figure, +5 us per weight-gradient launch; not kept.)
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return x - hi; }
 __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
   hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
-  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+  lo.x = tf32_lo(v.x, hi.x); lo.y = tf32_lo(v.y, hi.y); lo.z = tf32_lo(v.z, hi.z); lo.w = tf32_lo(v.w, hi.w);
 }
 // byte offset of 16-byte chunk `c` (0..7) of row `r` (0..127) inside a [128 x 32 fp32] swizzled tile
 __device__ __forceinline__ uint32_t swz(int r, int c) {
@@ -257,7 +261,7 @@ __global__ void __launch_bounds__(256) tc_prep_image(const ImgArgs p) {
     const float h = term_hi<NT>(v[u]);
     const uint32_t o = (swz(r[u], kl[u] >> 2) >> 2) + (kl[u] & 3);   // float index inside the 16 KB tile
     blk[o] = h;
-    if (NT == 3) blk[TC_BM * TC_BK + o] = v[u] - h;
+    if (NT == 3) blk[TC_BM * TC_BK + o] = tf32_lo(v[u], h);
   }
 }
 
@@ -266,6 +270,8 @@ struct TcArgs3 {
   const float* img;
   int n_row_tiles, n_tiles_n;
   long long* dbg;  // optional timeline buffer (dcgcdbg_tc_timeline): CTA (0,0) records clock64() per role and chunk
+  int a_exact;    // v4: every A value is exactly representable in tf32 (integer-valued features and their neighbour
+                  // sums): the lo(A) tile is identically zero, its stores and the lo(A)*hi(W) MMA are skipped
   int knockout;   // debugging aid (env DCGC_TC_KNOCKOUT): 1 no output stores, 2 no MMAs, 4 no A loads,
                   // 8 no weight copies, 16 no A shared-memory stores, 32 no TMEM loads, 64 no proxy fence,
                   // 128 no weight-image kernel — results are wrong, timing only
@@ -563,6 +569,433 @@ __global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3
 }
 
 // ------------------------------------------------------------------------------------------
+// tc_gemm_kernel_v4: the TS form — the A operand lives in TENSOR MEMORY, never in shared memory.
+//
+// Why (profiles/r3c_gemm_timeline.md, B300_MICROARCH.md): with both operands in shared memory a 128x128x8 tf32 MMA
+// reads 8 KB of smem in its 64-cycle floor — the whole 128 B/cycle port — and the TF32x3 main loop also has to WRITE
+// 32 KB of A hi/lo tiles and 32 KB of weight tiles per 32-column chunk: 160 KB of port traffic per chunk = 1 250 cycles
+// against 768 of tensor time, which is the 1 060-1 500 cycles per chunk v3 measures.  Here the producers put A straight
+// from registers into TMEM (tcgen05.st, its own 256 B/cycle path) and the MMAs read only the weight tiles from smem
+// (48 KB + 32 KB of fills per chunk = 640 cycles): the main loop is bound by the tensor pipe, and no smem is left in the
+// epilogue either.
+//
+// One persistent CTA per SM, 18 warps:
+//   warps 0-7   epilogue: warp w drains TMEM lanes 32 (w & 3) .. +31, accumulator columns 64 (w >> 2) .. +63 with
+//               tcgen05.ld.16x256b — a thread then holds PAIRS of adjacent columns of rows r, r + 8, so a warp store
+//               instruction writes 8 rows x 32 bytes = whole sectors with no transposition through shared memory;
+//               bias + activation + per-column BatchNorm sums fused; double-buffered accumulators (tile i's epilogue
+//               runs beside tile i+1's MMAs);
+//   warps 8-15  A producers, two sets of four (set g takes chunks g, g + 2, ...): the same 16x256b fragment layout
+//               makes the global loads 8-byte accesses that fill whole 32-byte sectors (8 rows x 32 B per instruction);
+//               tf32 hi / lo split in registers, 4 x tcgen05.st.16x256b.x4 per chunk, two chunks in flight per warp;
+//   warp 16     weight loader: one cp.async.bulk per chunk of the ready-made image (tc_prep_image), as in v3;
+//   warp 17     MMA issuer (one lane): 12 x tcgen05.mma.kind::tf32 [D], [A in TMEM], B-desc per chunk.
+// TMEM (all 512 columns): accumulators at 0 and 128, four A stages of 64 columns (32 hi + 32 lo) from 256.
+// ------------------------------------------------------------------------------------------
+constexpr int V4_THREADS = 18 * 32;
+constexpr int V4_STAGES = 4;
+constexpr uint32_t V4_A_COL0 = 256;            // first TMEM column of the A stages
+template <int NT> struct V4Cfg {
+  static constexpr int kBTiles = NT == 3 ? 2 : 1;                       // (hi, lo) or the single bf16-rounded tile
+  static constexpr int kStageBytes = kBTiles * TC_TILE_BYTES;           // weights only
+  static constexpr int kSmemBytes = V4_STAGES * kStageBytes + 1024 + 256 + 8 * 2 * 64 * 8;   // + stats staging
+};
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int NT>
+__global__ void __launch_bounds__(V4_THREADS, 1) tc_gemm_kernel_v4(const TcArgs3 q) {
+  const TcArgs& p = q.a;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  constexpr int S = V4_STAGES;
+  constexpr int STAGE_BYTES = V4Cfg<NT>::kStageBytes;
+  const uint32_t bar_base = base + S * STAGE_BYTES;
+  // barriers: full[s] +8s, empty[s] +48+8s, tmem_full[a] +96+8a, tmem_empty[a] +112+8a, tmem slot +128
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + S * STAGE_BYTES + 128);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int P = gridDim.x, pid = blockIdx.x;
+  const int n0 = blockIdx.y * TC_BN;
+  const int N = p.n1 + p.n2;
+  const int chunks1 = (p.k1 + TC_BK - 1) / TC_BK, chunks2 = (p.k2 + TC_BK - 1) / TC_BK;
+  const int total = chunks1 + chunks2;
+  const int my_tiles = pid < q.n_row_tiles ? (q.n_row_tiles - pid + P - 1) / P : 0;
+  const int n_cc = my_tiles * total;
+  const bool dbg_on = q.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && n_cc <= 1024;
+  if (dbg_on && tid == 0) q.dbg[5000] = clock64();
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(bar_base + 8 * s, 4 + 1);        // the 4 producer warps of one set + the weight loader
+      mbar_init(bar_base + 48 + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_base + 96 + 8 * a, 1);
+      mbar_init(bar_base + 112 + 8 * a, 8);      // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 17) tmem_alloc(bar_base + 128, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= 8 && warp < 16) {
+    // ===================== A producers: global -> registers -> (split) -> tensor memory =====================
+    // (the first version spent ~1 500 cycles of issue per chunk on address arithmetic, per-load predicates and an
+    // integer division: the producers, not the tensor pipe, set the pace.  Now: one 64-bit base per chunk, the other
+    // three row groups at +8/+16/+24 ld, the four column groups as immediate offsets, chunk -> (tile, chunk-of-tile)
+    // kept incrementally, and the K-tail / unaligned path only where a chunk needs it.)
+    const int pw = warp - 8, set = pw >> 2, qd = pw & 3;
+    const int r_lo = lane >> 2, cp = lane & 3;
+    const int r_base = qd * 32 + r_lo;                       // this thread's rows: r_base + 8 m, m = 0..3
+    struct Cur { int it, ch, row0, rows; };
+    auto cur_init = [&](Cur& c, int cc) {
+      c.it = cc / total; c.ch = cc - c.it * total; c.row0 = 0; c.rows = 0;
+      if (cc < n_cc) { int g_; tile_of(p, pid + c.it * P, c.row0, c.rows, g_); }
+    };
+    auto cur_advance = [&](Cur& c, int cc_next) {            // + 4 chunks
+      c.ch += 4;
+      bool moved = false;
+      while (c.ch >= total) { c.ch -= total; ++c.it; moved = true; }
+      if (moved && cc_next < n_cc) { int g_; tile_of(p, pid + c.it * P, c.row0, c.rows, g_); }
+    };
+    auto issue = [&](uint2 (&r)[16], const Cur& c, int cc) {
+      if (cc >= n_cc) return;
+      const float* src; int64_t ld; int ksrc, kbase; bool vec;
+      if (c.ch < chunks1) { src = p.a1; ld = p.ld_a1; ksrc = p.k1; kbase = c.ch * TC_BK; vec = p.a1_vec; }
+      else { src = p.a2; ld = p.ld_a2; ksrc = p.k2; kbase = (c.ch - chunks1) * TC_BK; vec = p.a2_vec; }
+      const float* b0 = src + (int64_t)(c.row0 + r_base) * ld + (kbase + 2 * cp);
+      const int64_t ld8 = 8 * ld;
+      const int live_rows = (q.knockout & 4) ? 0 : c.rows;
+      if (vec && kbase + TC_BK <= ksrc) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {                         // m = 2 h + rr
+          const uint2* rp = reinterpret_cast<const uint2*>(b0 + m * ld8);
+          const bool live = r_base + 8 * m < live_rows;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            r[(m >> 1) * 8 + j * 2 + (m & 1)] = live ? __ldg(rp + 4 * j) : make_uint2(0u, 0u);
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          const float* rp = b0 + m * ld8;
+          const bool live = r_base + 8 * m < live_rows;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = kbase + 8 * j + 2 * cp;
+            uint2 v = make_uint2(0u, 0u);
+            if (live && k < ksrc) v.x = __float_as_uint(__ldg(rp + 8 * j));
+            if (live && k + 1 < ksrc) v.y = __float_as_uint(__ldg(rp + 8 * j + 1));
+            r[(m >> 1) * 8 + j * 2 + (m & 1)] = v;
+          }
+        }
+      }
+    };
+    auto commit = [&](const uint2 (&r)[16], int cc) {
+      const int s = cc % S, use = cc / S;
+      const bool dbg_p = dbg_on && lane == 0 && pw == 0 && cc < 128;
+      if (dbg_p) q.dbg[5200 + 4 * (cc >> 1)] = clock64();
+      mbar_wait(bar_base + 48 + 8 * s, (use & 1) ^ 1);        // the MMAs that read this A stage have retired
+      tc_fence_after();
+      if (dbg_p) q.dbg[5201 + 4 * (cc >> 1)] = clock64();
+      const uint32_t a_col = V4_A_COL0 + (uint32_t)s * 64u;
+      if (!(q.knockout & 16))
+      // 16 columns (two 8-column groups) per store: 8 registers of temporaries at a time — 18 warps leave 96
+      // registers per thread (5 warps on one SM sub-partition), 64 of which hold the two chunks in flight
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int jp = 0; jp < 2; ++jp) {
+          const uint32_t taddr = tmem + ((uint32_t)(qd * 32 + h * 16) << 16) + a_col + 16u * jp;
+          uint32_t hi[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            hi[2 * i] = __float_as_uint(term_hi<NT>(__uint_as_float(r[h * 8 + jp * 4 + i].x)));
+            hi[2 * i + 1] = __float_as_uint(term_hi<NT>(__uint_as_float(r[h * 8 + jp * 4 + i].y)));
+          }
+          tmem_st8(taddr, hi);
+          if (NT == 3 && !q.a_exact) {
+            uint32_t lo[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              lo[2 * i] = __float_as_uint(tf32_lo(__uint_as_float(r[h * 8 + jp * 4 + i].x), __uint_as_float(hi[2 * i])));
+              lo[2 * i + 1] = __float_as_uint(tf32_lo(__uint_as_float(r[h * 8 + jp * 4 + i].y), __uint_as_float(hi[2 * i + 1])));
+            }
+            tmem_st8(taddr + 32u, lo);
+          }
+        }
+      }
+      if (dbg_p) q.dbg[5202 + 4 * (cc >> 1)] = clock64();
+      tmem_st_wait();
+      if (dbg_p) q.dbg[5203 + 4 * (cc >> 1)] = clock64();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_base + 8 * s);
+      if (dbg_on && lane == 0 && qd == 0) q.dbg[(set ? 1024 : 0) + (cc >> 1)] = clock64();
+    };
+    uint2 ra[16], rb[16];
+    Cur ca, cb;
+    cur_init(ca, set);
+    cur_init(cb, set + 2);
+    issue(ra, ca, set);
+    issue(rb, cb, set + 2);
+    for (int cc = set; cc < n_cc; cc += 4) {
+      commit(ra, cc);
+      cur_advance(ca, cc + 4);
+      issue(ra, ca, cc + 4);
+      if (cc + 2 < n_cc) {
+        commit(rb, cc + 2);
+        cur_advance(cb, cc + 6);
+        issue(rb, cb, cc + 6);
+      }
+    }
+  } else if (warp == 16) {
+    // ===================== weight loader: one bulk copy per chunk =====================
+    if (lane == 0) {
+      int cc = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        int row0, rows, g;
+        tile_of(p, pid + it * P, row0, rows, g);
+        constexpr int kBFloats = V4Cfg<NT>::kBTiles * TC_BM * TC_BK;
+        constexpr uint32_t kBBytes = V4Cfg<NT>::kStageBytes;
+        const float* src = q.img + ((int64_t)g * q.n_tiles_n + blockIdx.y) * total * kBFloats;
+        for (int ch = 0; ch < total; ++ch, ++cc) {
+          const int s = cc % S, use = cc / S;
+          mbar_wait(bar_base + 48 + 8 * s, (use & 1) ^ 1);
+          if (q.knockout & 8) { mbar_arrive(bar_base + 8 * s); continue; }
+          mbar_arrive_expect_tx(bar_base + 8 * s, kBBytes);
+          bulk_g2s(base + s * STAGE_BYTES, src + (int64_t)ch * kBFloats, kBBytes, bar_base + 8 * s);
+          if (dbg_on) q.dbg[2048 + cc] = clock64();
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int cc = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int acc = it & 1;
+        mbar_wait(bar_base + 112 + 8 * acc, ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem + acc * TC_BN;
+        for (int ch = 0; ch < total; ++ch, ++cc) {
+          const int s = cc % S;
+          mbar_wait(bar_base + 8 * s, (cc / S) & 1);
+          tc_fence_after();
+          if (dbg_on) q.dbg[3072 + cc] = clock64();
+          const uint32_t sb = base + s * STAGE_BYTES;
+          const uint32_t a_hi = tmem + V4_A_COL0 + (uint32_t)s * 64u, a_lo = a_hi + 32u;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UK; ++k) {
+            const uint32_t ko = k * TC_UK * 4;
+            if (NT == 3) {
+              const uint64_t bhi = make_desc(sb + ko), blo = make_desc(sb + TC_TILE_BYTES + ko);
+              if (!q.a_exact) {
+                umma_tf32_ts(d, a_lo + k * TC_UK, bhi, kIdescTf32, (ch | k) != 0);
+                umma_tf32_ts(d, a_hi + k * TC_UK, blo, kIdescTf32, 1);
+              } else {
+                umma_tf32_ts(d, a_hi + k * TC_UK, blo, kIdescTf32, (ch | k) != 0);
+              }
+              umma_tf32_ts(d, a_hi + k * TC_UK, bhi, kIdescTf32, 1);
+            } else {
+              umma_tf32_ts(d, a_hi + k * TC_UK, make_desc(sb + ko), kIdescTf32, (ch | k) != 0);
+            }
+          }
+          umma_commit(bar_base + 48 + 8 * s);
+        }
+        umma_commit(bar_base + 96 + 8 * acc);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 0-7) =====================
+    // Compact on purpose: the fully unrolled first version (32 store sites, each with its scalar fallback) did not fit
+    // the instruction cache — 29 k cycles for the first tile, 7.5-9 k for the others (profiles/r4f).  The 32-column
+    // block loop stays unrolled twice (the statistics registers are indexed by it), the lane-half loop is rolled, and
+    // the bounds-checked scalar path is one out-of-line loop.
+    const int qd = warp & 3, chalf = warp >> 2;
+    const int r_lo = lane >> 2, cp = lane & 3;
+    // fused BatchNorm statistics: this thread's column sums over the rows it stores, 16 columns (2 blocks x 4 pairs)
+    float su[16], sq[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { su[i] = 0.f; sq[i] = 0.f; }
+    const int act = p.act;
+    for (int it = 0; it < my_tiles; ++it) {
+      int row0, rows, g;
+      tile_of(p, pid + it * P, row0, rows, g);
+      if (q.knockout & 1) rows = 0;
+      const int acc = it & 1;
+      if (total > 0) {
+        mbar_wait(bar_base + 96 + 8 * acc, (it >> 1) & 1);
+        tc_fence_after();
+      }
+      if (dbg_on && tid == 0) q.dbg[4096 + 2 * it] = clock64();
+      const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_group_stride : nullptr;
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        const int cb = chalf * 64 + blk * 32;                  // first accumulator column of this 32-column block
+        const int cblk = n0 + cb;
+        float2 bv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = cblk + 8 * j + 2 * cp;
+          bv[j] = make_float2(0.f, 0.f);
+          if (bias) {
+            if (c < N) bv[j].x = __ldg(bias + c);
+            if (c + 1 < N) bv[j].y = __ldg(bias + c + 1);
+          }
+        }
+        // the block lands in one output with 8-byte aligned pairs (warp-uniform); otherwise the scalar path
+        const bool fast1 = p.c1_vec && cblk + 32 <= p.n1;
+        const bool fast2 = !fast1 && p.c2_vec && cblk >= p.n1 && cblk + 32 <= N && ((cblk - p.n1) & 1) == 0;
+        float* dst = nullptr; int64_t ld = 0;
+        if (fast1) { dst = p.c1 + cblk + 2 * cp; ld = p.ld_c1; }
+        else if (fast2) { dst = p.c2 + (cblk - p.n1) + 2 * cp; ld = p.ld_c2; }
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[16];
+          if (total > 0) {
+            tmem_ld16(tmem + ((uint32_t)(qd * 32 + h * 16) << 16) + acc * TC_BN + cb, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0u;
+          }
+          const int row_a = qd * 32 + h * 16 + r_lo;           // and row_a + 8
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+              float ox = __uint_as_float(v[4 * j + 2 * rr]) + bv[j].x;
+              float oy = __uint_as_float(v[4 * j + 2 * rr + 1]) + bv[j].y;
+              if (act == DCGC_ACT_RELU) { ox = fmaxf(ox, 0.f); oy = fmaxf(oy, 0.f); }
+              else if (act == DCGC_ACT_TANH) { ox = tanhf(ox); oy = tanhf(oy); }
+              o[4 * j + 2 * rr] = ox; o[4 * j + 2 * rr + 1] = oy;
+            }
+          }
+          if (dst != nullptr) {
+            float* d0 = dst + (int64_t)(row0 + row_a) * ld;
+            float* d1 = d0 + 8 * ld;
+            const bool l0 = row_a < rows, l1 = row_a + 8 < rows;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (l0) *reinterpret_cast<float2*>(d0 + 8 * j) = make_float2(o[4 * j], o[4 * j + 1]);
+              if (l1) *reinterpret_cast<float2*>(d1 + 8 * j) = make_float2(o[4 * j + 2], o[4 * j + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (!(((i >> 1) & 1) ? l1 : l0)) o[i] = 0.f;
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < 16; ++i) {                    // i = 4 j + 2 rr + e
+              const int row = row_a + 8 * ((i >> 1) & 1), c = cblk + 8 * (i >> 2) + 2 * cp + (i & 1);
+              float val = 0.f;
+#pragma unroll
+              for (int t2 = 0; t2 < 16; ++t2) val = (t2 == i) ? o[t2] : val;     // (no dynamic register indexing)
+              const bool ok = row < rows && c < N;
+              if (ok) {
+                const int64_t grow = row0 + row;
+                if (c < p.n1) { if (p.c1) p.c1[grow * p.ld_c1 + c] = val; }
+                else if (p.c2) p.c2[grow * p.ld_c2 + (c - p.n1)] = val;
+              }
+#pragma unroll
+              for (int t2 = 0; t2 < 16; ++t2) o[t2] = (t2 == i && !ok) ? 0.f : o[t2];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float a = o[4 * j + e], b = o[4 * j + 2 + e];
+              su[blk * 8 + 2 * j + e] += a + b;
+              sq[blk * 8 + 2 * j + e] = fmaf(a, a, fmaf(b, b, sq[blk * 8 + 2 * j + e]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_base + 112 + 8 * acc);
+      if (dbg_on && tid == 0) q.dbg[4096 + 2 * it + 1] = clock64();
+    }
+    if (p.stats) {
+      // lanes with the same (lane & 3) hold the same columns (different rows): fixed-order butterfly over lane bits
+      // 2..4 in float64, then the four row quarters of each column half are combined in quarter order through shared
+      // memory (deterministic); one row of partials per CTA
+      double* shd = reinterpret_cast<double*>(sm + S * STAGE_BYTES + 256);   // [8 warps][2][64]
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        double a = (double)su[i], b = (double)sq[i];
+        a += __shfl_xor_sync(0xffffffffu, a, 4);  b += __shfl_xor_sync(0xffffffffu, b, 4);
+        a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
+        a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
+        if (lane < 4) {
+          const int col = (i >> 3) * 32 + ((i & 7) >> 1) * 8 + 2 * lane + (i & 1);   // inside this warp's 64 columns
+          shd[(warp * 2 + 0) * 64 + col] = a;
+          shd[(warp * 2 + 1) * 64 + col] = b;
+        }
+      }
+      named_bar_sync(2, 256);
+      if (qd == 0) {                       // warps 0 and 4: one thread per (quantity, column of the half)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int idx = lane + 32 * e;   // 0..127 = quantity * 64 + column
+          const int qn = idx >> 6, col = idx & 63;
+          double t = 0.0;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) t += shd[((chalf * 4 + w4) * 2 + qn) * 64 + col];
+          const int c = n0 + chalf * 64 + col;
+          if (c < N) p.stats[((int64_t)pid * 2 + qn) * N + c] = t;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // wgrad on tensor cores: dW[g] = [a1|a2]_g^T . grad_g, a contraction over the ROWS (atoms) of one
 // degree bucket.  One CTA owns one chunk of rows of one group (fixed split => deterministic) and
 // MT 128-row tiles of dW x one 128-column tile:
@@ -679,13 +1112,14 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
       for (int t = 0; t <= MT; ++t) {
         uint8_t* hi_t = st + TPO * t * TC_TILE_BYTES + k_off;
         uint8_t* lo_t = hi_t + TC_TILE_BYTES;
+        const bool want_lo = !(p.a_exact && t < MT);          // exact A operand: its lo tiles are identically zero
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (NT == 3) {
             float4 hi, lo;
             split4(r[4 * t + j], hi, lo);
             *reinterpret_cast<float4*>(hi_t + j * 512) = hi;
-            *reinterpret_cast<float4*>(lo_t + j * 512) = lo;
+            if (want_lo) *reinterpret_cast<float4*>(lo_t + j * 512) = lo;
           } else {
             *reinterpret_cast<float4*>(hi_t + j * 512) = round4_bf16(r[4 * t + j]);
           }
@@ -748,8 +1182,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
           const uint64_t ahi = make_desc_mn(a_hi + ko), alo = make_desc_mn(a_lo + ko);
           const uint64_t ghi = make_desc_mn(sg_hi + ko), glo = make_desc_mn(sg_lo + ko);
           if (NT == 3) {
-            umma_tf32(tmem + t * TC_BN, alo, ghi, kIdescTf32MN, (c | k) != 0);
-            umma_tf32(tmem + t * TC_BN, ahi, glo, kIdescTf32MN, 1);
+            if (!p.a_exact) {
+              umma_tf32(tmem + t * TC_BN, alo, ghi, kIdescTf32MN, (c | k) != 0);
+              umma_tf32(tmem + t * TC_BN, ahi, glo, kIdescTf32MN, 1);
+            } else {
+              umma_tf32(tmem + t * TC_BN, ahi, glo, kIdescTf32MN, (c | k) != 0);
+            }
             umma_tf32(tmem + t * TC_BN, ahi, ghi, kIdescTf32MN, 1);
           } else {
             umma_tf32(tmem + t * TC_BN, ahi, ghi, kIdescTf32MN, (c | k) != 0);
@@ -814,31 +1252,6 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 int g_num_sms = 0;
 long long* g_timeline = nullptr;   // debugging aid, see dcgcdbg_tc_timeline
 
-// Split-weight scratch (hi | lo), one grow-only buffer per (device, stream): launches on one stream are
-// ordered, so the prep -> GEMM -> next prep sequence never races; no allocation on the steady-state path.
-struct PrepBuf { float* p; size_t bytes; };
-std::mutex g_prep_mu;
-std::map<std::pair<int, cudaStream_t>, PrepBuf> g_prep;
-
-int prep_scratch(cudaStream_t st, size_t bytes, float** out) {
-  int dev = 0;
-  DCGC_CUDA_CALL(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lk(g_prep_mu);
-  PrepBuf& b = g_prep[std::make_pair(dev, st)];
-  if (b.bytes < bytes) {
-    if (b.p) {
-      DCGC_CUDA_CALL(cudaStreamSynchronize(st));
-      DCGC_CUDA_CALL(cudaFree(b.p));
-      b.p = nullptr; b.bytes = 0;
-    }
-    const size_t want = bytes + bytes / 2;
-    DCGC_CUDA_CALL(cudaMalloc((void**)&b.p, want));
-    b.bytes = want;
-  }
-  *out = b.p;
-  return DCGC_OK;
-}
-
 int ensure_smem_attr() {
   static bool done = false;   // per process; the attribute is per function per device context
   if (!done) {
@@ -846,6 +1259,10 @@ int ensure_smem_attr() {
                                         V3Cfg<3>::kSmemBytes));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         V3Cfg<1>::kSmemBytes));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        V4Cfg<3>::kSmemBytes));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        V4Cfg<1>::kSmemBytes));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -864,7 +1281,7 @@ int ensure_smem_attr() {
 // The image of one GEMM's weights ([G][n_tiles_n][chunks][hi | lo][128 x 32 swizzled]) is normally built by
 // tc_prep_image right in front of the GEMM (5 us on the critical path, 7 times per training step).  A caller that
 // knows its weights ahead (the fused engine: they only change in the Adam launch) can build the images early, on
-// another stream, with dcgc_tc_prep_weights and hand each one to the matching GEMM with dcgc_tc_set_next_image.
+// another stream, with dcgc_tc_prep_weights and hand each one to the matching GEMM in DcgcGemmOpts::img.
 namespace {
 struct ImgShape { int k1_pad, k_pad, n_tiles_n, chunks, b_tiles; size_t bytes; };
 ImgShape img_shape(int nt, int k1, int k2, int N, int n_groups) {
@@ -891,7 +1308,6 @@ int launch_prep(int nt, const float* w, int n_groups, int trans_w, int k1, int k
   DCGC_CUDA_LAUNCH_CHECK("tc_prep_image");
   return DCGC_OK;
 }
-thread_local const float* tls_next_img = nullptr;
 }  // namespace
 
 // k2 = 0 when the GEMM has no second operand.  Bytes are 1024-aligned sizes (whole 16 KB tiles).
@@ -902,8 +1318,6 @@ int dcgc_tc_prep_weights(int nt, const float* w, int n_groups, int trans_w, int 
   if (st_ != DCGC_OK) return st_;
   return launch_prep(nt, w, n_groups, trans_w, k1, k2, N, img, st);
 }
-// One-shot, per thread: the next dcgc_tc_gemm of this thread reads this image instead of building one.
-void dcgc_tc_set_next_image(const float* img) { tls_next_img = img; }
 
 // Called by dcgc_group_gemm_fwd / _dgrad / dcgc_linear_* in the tensor-core modes; nt = 3 (DCGC_GEMM_TF32X3) or
 // 1 (DCGC_GEMM_BF16).
@@ -911,10 +1325,9 @@ void dcgc_tc_set_next_image(const float* img) { tls_next_img = img; }
 int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2, int64_t ld_a2, int k2, const float* w,
                  int n_groups, int trans_w, const float* bias, int n1, int n2, const int32_t* tiles, int64_t n_tiles,
                  int64_t n_rows, int act, float* c1, int64_t ld_c1, float* c2, int64_t ld_c2, cudaStream_t st,
-                 double* stats, int* stats_chunks) {
+                 double* stats, int* stats_chunks, const DcgcGemmOpts* opts) {
   const int N = n1 + n2;
-  const float* ready_img = tls_next_img;     // consumed (and cleared) on every path, used or not
-  tls_next_img = nullptr;
+  const float* ready_img = opts ? opts->img : nullptr;
   if (stats_chunks) *stats_chunks = 0;
   const int64_t row_tiles = tiles ? n_tiles : (n_rows + TC_BM - 1) / TC_BM;
   if (row_tiles == 0 || N == 0) return DCGC_OK;   // *stats_chunks == 0: the caller's finalize sees no partials
@@ -926,12 +1339,15 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
     const int n_tiles_n = (N + TC_BN - 1) / TC_BN, chunks = k_pad / TC_BK;
     float* img = const_cast<float*>(ready_img);
     static const int knockout = [] { const char* e = getenv("DCGC_TC_KNOCKOUT"); return e ? atoi(e) : 0; }();
+    float* own_img = nullptr;
     if (img == nullptr) {
-      st_ = prep_scratch(st, img_shape(nt, k1, a2 ? k2 : 0, N, n_groups).bytes, &img);
-      if (st_ != DCGC_OK) return st_;
+      // no image from the caller: a stream-ordered scratch allocation (no hidden buffer, no synchronisation; the
+      // driver's pool makes it an O(1) call after the first use) freed in stream order right after the launch
+      DCGC_CUDA_CALL(cudaMallocAsync((void**)&own_img, img_shape(nt, k1, a2 ? k2 : 0, N, n_groups).bytes, st));
+      img = own_img;
       if (chunks > 0 && !(knockout & 128)) {
         st_ = launch_prep(nt, w, n_groups, trans_w, k1, a2 ? k2 : 0, N, img, st);
-        if (st_ != DCGC_OK) return st_;
+        if (st_ != DCGC_OK) { cudaFreeAsync(own_img, st); return st_; }
       }
     }
     TcArgs3 q3{};
@@ -947,6 +1363,7 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
     p3.c2_vec = c2 && ld_c2 % 4 == 0 && aligned16(c2);
     q3.img = img; q3.n_row_tiles = (int)row_tiles; q3.n_tiles_n = n_tiles_n;
     q3.knockout = knockout;
+    q3.a_exact = (opts && opts->a_exact && nt == 3) ? 1 : 0;
     q3.dbg = g_timeline;
     int ctas = g_num_sms / n_tiles_n;
     if (ctas < 1) ctas = 1;
@@ -954,9 +1371,23 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
     p3.stats = stats;
     if (stats_chunks) *stats_chunks = ctas;
     dim3 grid((unsigned)ctas, (unsigned)n_tiles_n);
-    if (nt == 3) tc_gemm_kernel_v3<3><<<grid, V3_THREADS, V3Cfg<3>::kSmemBytes, st>>>(q3);
-    else tc_gemm_kernel_v3<1><<<grid, V3_THREADS, V3Cfg<1>::kSmemBytes, st>>>(q3);
-    DCGC_CUDA_LAUNCH_CHECK("tc_gemm_kernel_v3");
+    // DCGC_TC_V3=1: the previous kernel (both operands in shared memory), kept for A/B measurements
+    static const bool use_v3 = [] { const char* e = getenv("DCGC_TC_V3"); return e && e[0] == '1'; }();
+    if (use_v3) {
+      q3.a_exact = 0;
+      if (nt == 3) tc_gemm_kernel_v3<3><<<grid, V3_THREADS, V3Cfg<3>::kSmemBytes, st>>>(q3);
+      else tc_gemm_kernel_v3<1><<<grid, V3_THREADS, V3Cfg<1>::kSmemBytes, st>>>(q3);
+    } else {
+      if (nt == 3) tc_gemm_kernel_v4<3><<<grid, V4_THREADS, V4Cfg<3>::kSmemBytes, st>>>(q3);
+      else tc_gemm_kernel_v4<1><<<grid, V4_THREADS, V4Cfg<1>::kSmemBytes, st>>>(q3);
+    }
+    const cudaError_t launch_err = cudaGetLastError();
+    if (own_img) cudaFreeAsync(own_img, st);
+    g_dcgc_launches.fetch_add(1, std::memory_order_relaxed);
+    if (launch_err != cudaSuccess) {
+      dcgc_set_error("tc_gemm_kernel: %s", cudaGetErrorString(launch_err));
+      return DCGC_ERR_CUDA;
+    }
     return DCGC_OK;
   }
   dcgc_set_error("dcgc_tc_gemm: unsupported problem size");

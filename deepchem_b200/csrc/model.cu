@@ -635,14 +635,12 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
     const bool fuse_stats = cfg->batch_norm && training && dcgc_tc_terms(cfg->gemm_mode) != 0;
     int32_t fused = -1;
     if (l == 0 && sv.img_fwd_ready) DCGC_CUDA_CALL(cudaStreamWaitEvent(st, sv.img_fwd_ready, 0));
-    dcgc_tc_set_next_image(sv.img_fwd[l]);
-    if (fuse_stats)
-      RET_IF(dcgc_group_gemm_fwd_stats(cfg->gemm_mode, h, ld, fp, sv.s[l], fp, fp, params + lo.conv_w[l], sv.b11[l], c,
-                                       t->tiles, t->n_tiles, 128, N, DCGC_ACT_RELU, sv.y[l], c, sv.part, &fused, st));
-    else
-      RET_IF(dcgc_group_gemm_fwd(cfg->gemm_mode, h, ld, fp, sv.s[l], fp, fp, params + lo.conv_w[l], sv.b11[l], c,
-                                 t->tiles, t->n_tiles, 128, N, DCGC_ACT_RELU, sv.y[l], c, st));
-    dcgc_tc_set_next_image(nullptr);      // (a call that returned before its GEMM must not leak the image)
+    DcgcGemmOpts go;
+    go.img = sv.img_fwd[l];
+    go.a_exact = (l == 0 && cfg->input_exact) ? 1 : 0;      // integer-valued features: [X | S] is exact in tf32
+    RET_IF(dcgc_group_gemm_fwd_opts(cfg->gemm_mode, h, ld, fp, sv.s[l], fp, fp, params + lo.conv_w[l], sv.b11[l], c,
+                                    t->tiles, t->n_tiles, 128, N, DCGC_ACT_RELU, sv.y[l], c,
+                                    fuse_stats ? sv.part : nullptr, fuse_stats ? &fused : nullptr, go, st));
     const float *scale = nullptr, *shift = nullptr;
     if (cfg->batch_norm) {
       RET_IF(bn_forward(cfg, lo, l, sv.y[l], c, N, c, params, bn_running, training, sv, st, fused));
@@ -657,14 +655,14 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
   }
   // ---- atom-level dense + ReLU (+BN folded into the gather), GraphGather(tanh), head
   int32_t fused_d = -1;
-  dcgc_tc_set_next_image(sv.img_dense);
-  if (cfg->batch_norm && training && dcgc_tc_terms(cfg->gemm_mode) != 0)
-    RET_IF(dcgc_linear_fwd_stats(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], params + lo.dense_w,
-                                 params + lo.dense_b, D, N, DCGC_ACT_RELU, sv.z, D, sv.part, &fused_d, st));
-  else
-    RET_IF(dcgc_linear_fwd(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], params + lo.dense_w, params + lo.dense_b, D,
-                           N, DCGC_ACT_RELU, sv.z, D, st));
-  dcgc_tc_set_next_image(nullptr);
+  {
+    const bool fuse_d = cfg->batch_norm && training && dcgc_tc_terms(cfg->gemm_mode) != 0;
+    DcgcGemmOpts go;
+    go.img = sv.img_dense;
+    RET_IF(dcgc_linear_fwd_opts(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], params + lo.dense_w, params + lo.dense_b,
+                                D, N, DCGC_ACT_RELU, sv.z, D, fuse_d ? sv.part : nullptr, fuse_d ? &fused_d : nullptr,
+                                go, st));
+  }
   const float *scale = nullptr, *shift = nullptr;
   if (cfg->batch_norm) {
     RET_IF(bn_forward(cfg, lo, L, sv.z, D, N, D, params, bn_running, training, sv, st, fused_d));
@@ -929,9 +927,11 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
   RET_IF(bn_backward(L, sv.z, D, -1));
   RET_IF(dcgc_linear_wgrad(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], dA, D, D, N, grads + lo.dense_w,
                            grads + lo.dense_b, wg, wg_bytes, st));
-  dcgc_tc_set_next_image(img_dense_dgrad);
-  RET_IF(dcgc_linear_dgrad(cfg->gemm_mode, dA, D, D, params + lo.dense_w, lo.f[L], N, dP, lo.f[L], st));
-  dcgc_tc_set_next_image(nullptr);
+  {
+    DcgcGemmOpts go;
+    go.img = img_dense_dgrad;
+    RET_IF(dcgc_linear_dgrad_opts(cfg->gemm_mode, dA, D, D, params + lo.dense_w, lo.f[L], N, dP, lo.f[L], go, st));
+  }
 
   // ---- conv stack backward
   for (int l = L - 1; l >= 0; --l) {
@@ -950,16 +950,17 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
       RET_IF(dcgc_pool_bwd(dP, c, sv.arg[l], c, nullptr, t->t_row_ptr, t->t_src, t->t_slot, N, c, dA, c, st));
     }
     RET_IF(bn_backward(l, sv.y[l], c, fused));
-    RET_IF(dcgc_group_gemm_wgrad(cfg->gemm_mode, sv.h[l], sv.ld_h[l], fp, sv.s[l], fp, fp, dA, c, c, t->deg_count,
-                                 DCGC_N_DEG, grads + lo.conv_w[l], db11, wg, wg_bytes, st));
+    RET_IF(dcgc_group_gemm_wgrad_opts(cfg->gemm_mode, sv.h[l], sv.ld_h[l], fp, sv.s[l], fp, fp, dA, c, c, t->deg_count,
+                                      DCGC_N_DEG, grads + lo.conv_w[l], db11, wg, wg_bytes,
+                                      (l == 0 && cfg->input_exact) ? 1 : 0, st));
     conv_bias_unpack<<<blocks_for(21 * c), kT, 0, st>>>(db11, c, grads + lo.conv_b[l]);
     DCGC_CUDA_LAUNCH_CHECK("conv_bias_unpack");
     if (l > 0) {
       // [dP | d2] = G . W^T, then dP += transposed gather of d2
-      dcgc_tc_set_next_image(img_dgrad[l]);
-      RET_IF(dcgc_group_gemm_dgrad(cfg->gemm_mode, dA, c, c, params + lo.conv_w[l], fp, fp, t->tiles, t->n_tiles, 128,
-                                   N, dP, fp, d2, fp, st));
-      dcgc_tc_set_next_image(nullptr);
+      DcgcGemmOpts go;
+      go.img = img_dgrad[l];
+      RET_IF(dcgc_group_gemm_dgrad_opts(cfg->gemm_mode, dA, c, c, params + lo.conv_w[l], fp, fp, t->tiles, t->n_tiles,
+                                        128, N, dP, fp, d2, fp, go, st));
       if (use_mg(t, fp, 0, d2, dP))
         RET_IF(dcgc_mg_gather_sum(d2, fp, t, 1, fp, dP, fp, dP, fp, st));
       else if (t->symmetric)

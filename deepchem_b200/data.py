@@ -180,3 +180,38 @@ class CSVLoader(object):
         return ds
 
     featurize = create_dataset
+
+
+class ReplayDataset(object):
+    """``n`` molecules streamed from a small packed shard replayed cyclically (molecule i of the dataset is molecule
+    ``(start + i) % len(shard)`` of the shard): the inference stream of BASELINE configs[4] — 10 M PCBA-shaped
+    molecules — without holding 10 M molecules in host memory.  Supports what ``predict`` needs: ``len``,
+    ``iterbatches`` (labels are ``None``) and ``select_range`` for rank sharding."""
+
+    def __init__(self, shard, n, start=0):
+        self.shard, self.n, self.start = shard, int(n), int(start)
+
+    def __len__(self):
+        return self.n
+
+    y = w = None
+    ids = property(lambda self: np.arange(self.start, self.start + self.n))
+
+    def select_range(self, lo, hi):
+        return ReplayDataset(self.shard, max(0, int(hi) - int(lo)), self.start + int(lo))
+
+    def iterbatches(self, batch_size=None, epochs=1, deterministic=True, pad_batches=False, lazy=False):
+        m = self.shard.n_mols
+        bs = self.n if batch_size is None else int(batch_size)
+        for _ in range(epochs):
+            done = 0
+            while done < self.n:
+                k = min(bs, self.n - done)
+                off = (self.start + done) % m
+                if off + k <= m:
+                    X = self.shard.slice(off, off + k)
+                else:
+                    idx = (off + np.arange(k)) % m
+                    X = self.shard.take_lazy(idx) if lazy else self.shard.take(idx)
+                yield X, None, None, np.arange(self.start + done, self.start + done + k)
+                done += k

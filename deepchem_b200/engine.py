@@ -253,6 +253,7 @@ class FlatEngine(AdamSlabState):
         if not self.aliased():
             self.adopt()
         L = _lib.lib()
+        self.cfg.input_exact = 1 if getattr(x, "_dcgc_input_exact", False) else 0
         nbytes = int(L.dcgc_gcmodel_workspace_bytes(ctypes.byref(self.cfg), topo.n_atoms, topo.n_segments))
         ws = _ws(nbytes, self.device)
         check(L.dcgc_gcmodel_train_step(
@@ -268,6 +269,7 @@ class FlatEngine(AdamSlabState):
             self.adopt()
         L = _lib.lib()
         cfg = self.cfg
+        cfg.input_exact = 1 if getattr(x, "_dcgc_input_exact", False) else 0
         nbytes = int(L.dcgc_gcmodel_workspace_bytes(ctypes.byref(cfg), topo.n_atoms, topo.n_segments))
         ws = _ws(nbytes, self.device)
         out = torch.empty(n_samples, cfg.n_out, dtype=torch.float32, device=self.device)

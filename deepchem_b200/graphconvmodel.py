@@ -335,6 +335,7 @@ class _PinnedRing(object):
         self.slots = []              # [tensor, upload event or None, weakref to the owner or None / _BUSY]
         self.next = 0
         self.max_slots = max_slots
+        self.gc_at = 12              # ring length from which a full ring first tries the cyclic collector
         self.lock = threading.Lock()
 
     _BUSY = object()                 # handed out, owner not registered yet
@@ -349,12 +350,17 @@ class _PinnedRing(object):
         slot = None
         with self.lock:
             n = len(self.slots)
-            for k in range(n):
-                cand = self.slots[(self.next + k) % n]
-                if self._free(cand):
-                    slot = cand
-                    self.next = (self.next + k + 1) % n
+            for attempt in range(2):
+                for k in range(n):
+                    cand = self.slots[(self.next + k) % n]
+                    if self._free(cand):
+                        slot = cand
+                        self.next = (self.next + k + 1) % n
+                        break
+                if slot is not None or n < self.gc_at or attempt:
                     break
+                import gc
+                gc.collect()         # batches kept alive only by reference cycles: cheaper than a page-locked allocation
             if slot is None:
                 if n >= self.max_slots:
                     return None, None
@@ -712,6 +718,10 @@ class GraphConvModel(object):
             for fs in fslots:
                 fs[1] = fev
         x._dcgc_zero_padded = True
+        # integer-valued features (the shard keeps their exact int8 copy, PackedMols.compact): the first layer's GEMM
+        # operands are exact in tf32 and the engine skips the identically-zero lo(A) term (dcgc_gcmodel_config.input_exact)
+        x._dcgc_input_exact = bool(feats.dtype == torch.int8
+                                   or getattr(inputs, "packed_features_i8_pinned", None) is not None)
         dev_inputs = topo.model_inputs(x, n_samples=int(inputs[3]))
 
         def conv(arrs, tag):
@@ -778,6 +788,7 @@ class GraphConvModel(object):
 
         prepared_iter = _Prefetcher(self, generator, prefetch) if prefetch else \
             (self._prepare_batch(b) for b in generator)
+        self._active_prefetcher = prepared_iter if prefetch else None      # (bench.py reads its queue depth)
         tr = self._pipe_trace
         t_prev = time.perf_counter()
         for prepared in prepared_iter:

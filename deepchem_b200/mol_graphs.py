@@ -399,7 +399,11 @@ class DeviceTopology(object):
         """[features, deg_slice, membership, n_samples, deg_adj_1..10] as device tensors, with
         this topology attached to the deg_slice tensor so that the layers find it."""
         import torch
-        deg_slice = self.deg_slice
+        # a FRESH view carries the back-reference: attached to the view cached in self.__dict__ it would close a
+        # reference cycle (topology -> tensor -> topology) and the batch's host staging memory would only be released
+        # by the cyclic collector, long after the step (the pinned ring then looks exhausted)
+        off, nbytes, _ = self._fields["deg_slice"]
+        deg_slice = self.buffer[off:off + nbytes].view(torch.int64).view(11, 2)
         attach(deg_slice, self)
         ns = torch.tensor(self.n_mols if n_samples is None else n_samples)
         return _ModelInputs(self, features, deg_slice, ns)

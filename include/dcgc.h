@@ -417,6 +417,11 @@ typedef struct dcgc_gcmodel_config {
   int32_t gemm_mode;                     /* DCGC_GEMM_* */
   float bn_eps;                          /* 1e-3 */
   float bn_momentum;                     /* 0.99: weight of the NEW statistic (torch convention) */
+  int32_t input_exact;                   /* set per call: every entry of x is an integer with |neighbour sum| < 2048 (true of
+                                            every ConvMol feature: one-hots, formal charge, radical electrons), so the first
+                                            layer's operands are exact in tf32 and DCGC_GEMM_TF32X3 skips the identically-zero
+                                            lo(A) * hi(W) term in its forward and weight-gradient GEMMs (same results) */
+  int32_t reserved;
 } dcgc_gcmodel_config;
 
 /* --------------------------------------------------------------------------------------------

@@ -35,5 +35,8 @@ for mode, name in ((_lib.GEMM_TF32X3, "tf32x3"), (_lib.GEMM_BF16, "bf16")):
     e = (t[5100:5116] - t[5100]).reshape(4, 4)
     print("epilogue of tile 2, warp 0, per 32-column block: [start, after tcgen05.ld, after STS+syncwarp, after stores]")
     print(e.tolist())
+    pr = (t[5200:5200 + 4 * 24] - t0).reshape(24, 4)
+    print("producer warp 8 (set 0), per chunk [enter commit, stage free, stores issued, stores done]:")
+    print(pr[8:20].tolist())
     mm = t[3072:3072 + tiles * total] - t0
     print("mma chunk-to-chunk deltas (cycles):", np.diff(mm)[:24].tolist())

@@ -58,16 +58,18 @@ def test_engine_train_step_matches_oracle(mode, layers, bn, shape):
     eng = m._engine
     out = torch.empty(pm.n_mols, eng.cfg.n_out, device=m.device)
     loss = eng.train_step(inputs[1]._dcgc_topology, inputs[0], labels[0], weights[0], pm.n_mols, out=out)
-    # float64-anchored bound (helpers.py): within 1e-5 of the tensor scale, or as close to float64 as the fp32 oracle
+    # float64-anchored bound (helpers.py): within 1e-5 of the tensor scale, or as close to float64 as the fp32 oracle;
+    # a batch of ~1.7 k atoms gets the discontinuity allowance of one ReLU / argmax decision (flip = 2 / atoms)
+    flip = 2.0 / max(1, pm.n_atoms)
     _, mm = oracle_batch(pm.to_list())
     res = oracle_fp32_fp64(om, mode, mm, pm.n_mols, batch[1][0], w)
     o32, l32, g32 = res[torch.float32]
     o64, l64, g64 = res[torch.float64]
     k = 1 if mode == "classification" else 0
     assert_fp64_anchored("output", out.cpu().reshape(o64[k].shape), o32[k], o64[k])
-    assert abs(float(loss) - l64) <= max(1e-5, 1.5 * abs(l32 - l64) / abs(l64)) * abs(l64)
+    assert abs(float(loss) - l64) <= max(1e-5, 3 * abs(l32 - l64) / abs(l64)) * abs(l64)
     for name, p in m.model.named_parameters():
-        assert_fp64_anchored(name, p.grad, g32[name], g64[name])
+        assert_fp64_anchored(name, p.grad, g32[name], g64[name], flip=flip)
     om.train()
     om(torch_args(mm, pm.n_mols))                       # the fp32 oracle's running statistics
     for (k, v), (_, vo) in zip(m.model.state_dict().items(), om.state_dict().items()):
@@ -345,3 +347,31 @@ def test_materialised_generator_survives_the_staging_ring():
     m2.fit_generator(m2.default_generator(ds, deterministic=True), checkpoint_interval=0)
     for (k, v1), (_, v2) in zip(m1.model.state_dict().items(), m2.model.state_dict().items()):
         assert torch.equal(v1, v2), k
+
+
+def test_exact_input_path_is_bit_identical():
+    """dcgc_gcmodel_config.input_exact: with integer-valued features the first layer's operands are exact in tf32, the
+    lo(A) tile is identically zero and the TF32x3 GEMMs skip its term — every gradient must be bit-identical to the
+    full three-term evaluation."""
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    from deepchem_b200.synthetic import make_labels, make_molecules
+    _cuda()
+    B = 600
+    y, w = make_labels(B, 2, "regression", seed=3)
+    res = []
+    for compact in (False, True):
+        pm = make_molecules(B, seed=17, shape="stress")
+        if compact:
+            pm = pm.pin_memory()
+            assert pm.features_i8 is not None
+        torch.manual_seed(0)
+        m = GraphConvModel(2, [128, 64], 128, mode="regression", batch_size=B, gemm_mode="tf32x3")
+        batch = next(m.default_generator(PackedDataset(pm, y, w), deterministic=True))
+        inputs, labels, weights = m._prepare_batch(batch)
+        assert bool(getattr(inputs[0], "_dcgc_input_exact", False)) == compact
+        loss = m._engine.train_step(inputs[1]._dcgc_topology, inputs[0], labels[0], weights[0], B)
+        assert m._engine.cfg.input_exact == int(compact)
+        res.append((float(loss), m._engine.grads.clone()))
+    assert res[0][0] == res[1][0]
+    assert torch.equal(res[0][1], res[1][1])

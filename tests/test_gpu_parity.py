@@ -238,17 +238,19 @@ def test_model_forward_loss_and_gradients(mode, layers):
     loss = m._loss_fn([outs[i] for i in m._loss_outputs], labels, weights)
     loss.backward()
 
-    # float64-anchored bound (helpers.py): within 1e-5 of the tensor scale, or as close to float64 as the fp32 oracle
+    # float64-anchored bound (helpers.py): within 1e-5 of the tensor scale, or as close to float64 as the fp32 oracle;
+    # a batch of ~1.7 k atoms gets the discontinuity allowance of one ReLU / argmax decision (flip = 2 / atoms)
+    flip = 2.0 / max(1, pm.n_atoms)
     _, mm = oracle_batch(pm.to_list())
     res = oracle_fp32_fp64(om, mode, mm, pm.n_mols, batch[1][0], w)
     o32, l32, g32 = res[torch.float32]
     o64, l64, g64 = res[torch.float64]
     for i, a in enumerate(outs):
         assert_fp64_anchored("output %d" % i, a, o32[i], o64[i])
-    assert abs(float(loss) - l64) <= max(1e-5, 1.5 * abs(l32 - l64) / abs(l64)) * abs(l64)
+    assert abs(float(loss) - l64) <= max(1e-5, 3 * abs(l32 - l64) / abs(l64)) * abs(l64)
     for name, p in m.model.named_parameters():
         got = p.grad if p.grad is not None else torch.zeros_like(p)
-        assert_fp64_anchored(name, got, g32[name], g64[name])
+        assert_fp64_anchored(name, got, g32[name], g64[name], flip=flip)
     # running statistics follow torch's momentum convention (new = 0.01*old + 0.99*batch)
     om.train()
     om(torch_args(mm, pm.n_mols))

@@ -307,3 +307,26 @@ def _batch_inputs_with_ring(m, X_b):
     inputs.layout = layout
     inputs.layout_source = packed
     return inputs
+
+
+def test_replay_dataset_streams_and_shards():
+    """ReplayDataset (the 10 M-molecule inference stream of BASELINE configs[4] without 10 M molecules in memory):
+    molecule i is molecule (start + i) % len(shard); rank shards are contiguous and cover the stream exactly once."""
+    from deepchem_b200.data import ReplayDataset
+    from deepchem_b200.parallel import shard_range
+    shard = make_molecules(24, seed=3, shape="delaney")
+    ds = ReplayDataset(shard, 100)
+    assert len(ds) == 100
+    seen = []
+    for rank in range(3):
+        lo, hi = shard_range(len(ds), rank, 3)
+        part = ds.select_range(lo, hi)
+        assert len(part) == hi - lo
+        for X, y, w, ids in part.iterbatches(batch_size=16, deterministic=True):
+            assert y is None and w is None and X.n_mols == len(ids) <= 16
+            for j, i in enumerate(ids):
+                a = X.mol(j)
+                b = shard.mol(int(i) % 24)
+                assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+            seen.extend(int(i) for i in ids)
+    assert seen == list(range(100))
