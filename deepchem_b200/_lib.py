@@ -162,9 +162,10 @@ _SIGNATURES = {
     "dcgc_gcmodel_workspace_bytes": (c_int64, [POINTER(GcModelConfig), c_int64, c_int64]),
     "dcgc_gcmodel_forward": (c_int32, [POINTER(GcModelConfig), POINTER(Topology), _P, c_int64, c_int64, _P, _P,
                                        c_int32, _P, c_int64, _P, _P, _P, _P]),
-    "dcgc_gcmodel_set_forward_event": (c_int32, [_P]),
     "dcgc_gcmodel_train_step": (c_int32, [POINTER(GcModelConfig), POINTER(Topology), _P, c_int64, _P, _P, c_int64,
                                           _P, _P, _P, _P, c_int64, _P, _P, _P]),
+    "dcgc_gcmodel_train_step_ev": (c_int32, [POINTER(GcModelConfig), POINTER(Topology), _P, c_int64, _P, _P, c_int64,
+                                          _P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int32, _P]),
     "dcgc_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, c_float, _P]),
 }
 

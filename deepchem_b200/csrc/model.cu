@@ -770,21 +770,30 @@ extern "C" int dcgc_gcmodel_forward(const dcgc_gcmodel_config* cfg, const dcgc_t
   return DCGC_OK;
 }
 
-static thread_local cudaEvent_t g_forward_event = nullptr;
-extern "C" int dcgc_gcmodel_set_forward_event(void* event) {
-  g_forward_event = (cudaEvent_t)event;
-  return DCGC_OK;
-}
-
 extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcgc_topology* topo, const float* x,
                                        int64_t ld_x, const float* y, const float* w, int64_t n_samples,
                                        const float* params, float* grads, float* bn_running, void* workspace,
                                        int64_t workspace_bytes, float* loss_dev, float* out, void* stream) {
+  return dcgc_gcmodel_train_step_ev(cfg, topo, x, ld_x, y, w, n_samples, params, grads, bn_running, workspace,
+                                    workspace_bytes, loss_dev, out, nullptr, nullptr, 0, stream);
+}
+
+extern "C" int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const dcgc_topology* topo, const float* x,
+                                          int64_t ld_x, const float* y, const float* w, int64_t n_samples,
+                                          const float* params, float* grads, float* bn_running, void* workspace,
+                                          int64_t workspace_bytes, float* loss_dev, float* out, void* forward_event,
+                                          void* const* grad_events, int32_t n_grad_events, void* stream) {
   Layout lo;
   RET_IF(make_layout(cfg, &lo));
   RET_IF(check_topo(topo));
   DCGC_CHECK_ARG(params && grads && y && loss_dev && workspace, "dcgc_gcmodel_train_step: null pointer");
+  DCGC_CHECK_ARG(n_grad_events >= 0 && n_grad_events <= cfg->n_layers + 1 && (n_grad_events == 0 || grad_events),
+                 "dcgc_gcmodel_train_step_ev: at most n_layers + 1 gradient events");
   cudaStream_t st = (cudaStream_t)stream;
+  auto slice_done = [&](int i) -> int {
+    if (i < n_grad_events && grad_events[i]) DCGC_CUDA_CALL(cudaEventRecord((cudaEvent_t)grad_events[i], st));
+    return DCGC_OK;
+  };
   const dcgc_topology* t = topo;
   const int L = lo.L, D = cfg->dense, T = cfg->n_out;
   const int64_t N = t->n_atoms, S = t->n_segments;
@@ -826,11 +835,7 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
   }
   RET_IF(forward_impl(cfg, lo, t, x, ld_x, n_samples, params, bn_running, 1, 1, ws, sv, st));
   if (side) DCGC_CUDA_CALL(cudaStreamWaitEvent(st, side->e2, 0));     // the backward's images (long done by now)
-  if (g_forward_event) {
-    cudaEvent_t ev = g_forward_event;
-    g_forward_event = nullptr;
-    DCGC_CUDA_CALL(cudaEventRecord(ev, st));
-  }
+  if (forward_event) DCGC_CUDA_CALL(cudaEventRecord((cudaEvent_t)forward_event, st));
 
   // ---- backward scratch
   int wmax = D, fmax = 0;
@@ -927,6 +932,7 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
   RET_IF(bn_backward(L, sv.z, D, -1));
   RET_IF(dcgc_linear_wgrad(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], dA, D, D, N, grads + lo.dense_w,
                            grads + lo.dense_b, wg, wg_bytes, st));
+  RET_IF(slice_done(0));            // head, dense layer and its BatchNorm
   {
     DcgcGemmOpts go;
     go.img = img_dense_dgrad;
@@ -955,6 +961,7 @@ extern "C" int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcg
                                       (l == 0 && cfg->input_exact) ? 1 : 0, st));
     conv_bias_unpack<<<blocks_for(21 * c), kT, 0, st>>>(db11, c, grads + lo.conv_b[l]);
     DCGC_CUDA_LAUNCH_CHECK("conv_bias_unpack");
+    RET_IF(slice_done(1 + (L - 1 - l)));
     if (l > 0) {
       // [dP | d2] = G . W^T, then dP += transposed gather of d2
       DcgcGemmOpts go;

@@ -248,19 +248,33 @@ class FlatEngine(AdamSlabState):
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def train_step(self, topo, x, y, w, n_samples, out=None):
-        """forward + loss + backward; gradients land in self.grads.  Returns the device loss scalar."""
+    def grad_slices(self):
+        """[(lo, hi)] of the gradient slab in the order the backward pass completes them (the order of the
+        ``grad_events`` of dcgc_gcmodel_train_step_ev): [dense, its BatchNorm, head], then conv layer L-1 ... 0."""
+        L = self.cfg.n_layers
+        conv_w = [self.offsets[4 * l] for l in range(L)] + [self.offsets[4 * L]]
+        return [(conv_w[L], self.n_params)] + [(conv_w[l], conv_w[l + 1]) for l in range(L - 1, -1, -1)]
+
+    def train_step(self, topo, x, y, w, n_samples, out=None, forward_event=None, grad_events=None):
+        """forward + loss + backward; gradients land in self.grads.  Returns the device loss scalar.
+        ``forward_event`` / ``grad_events`` (torch.cuda.Event): recorded between forward and backward / when each
+        slice of ``grad_slices()`` is final."""
         if not self.aliased():
             self.adopt()
         L = _lib.lib()
         self.cfg.input_exact = 1 if getattr(x, "_dcgc_input_exact", False) else 0
         nbytes = int(L.dcgc_gcmodel_workspace_bytes(ctypes.byref(self.cfg), topo.n_atoms, topo.n_segments))
         ws = _ws(nbytes, self.device)
-        check(L.dcgc_gcmodel_train_step(
+        n_ev, evs = 0, None
+        if grad_events:
+            n_ev = len(grad_events)
+            evs = (ctypes.c_void_p * n_ev)(*[e.cuda_event for e in grad_events])
+        check(L.dcgc_gcmodel_train_step_ev(
             ctypes.byref(self.cfg), ctypes.byref(topology_struct(topo)), x.data_ptr(), x.stride(0),
             y.data_ptr(), w.data_ptr() if w is not None else None, n_samples, self.params.data_ptr(),
             self.grads.data_ptr(), self.bn_running.data_ptr() if self.n_bn else None, ws.data_ptr(), ws.numel(),
-            self.loss.data_ptr(), out.data_ptr() if out is not None else None, self._stream()))
+            self.loss.data_ptr(), out.data_ptr() if out is not None else None,
+            forward_event.cuda_event if forward_event is not None else None, evs, n_ev, self._stream()))
         return self.loss
 
     def forward(self, topo, x, n_samples, training=False, want_probs=True):

@@ -866,22 +866,57 @@ class GraphConvModel(object):
             # the C call records this event between forward and backward; the prefetch stream waits on the latest
             # one before it uploads a batch, so uploads run beside the backward pass (see _Prefetcher._run)
             fe = self._fwd_events[self._global_step % len(self._fwd_events)]
-            _lib_check(_lib_handle().dcgc_gcmodel_set_forward_event(fe.cuda_event))
+        dp = False
+        if self._dp:
+            from .parallel import world_size
+            dp = world_size() > 1
+        overlap = dp and os.environ.get("DCGC_NO_OVERLAP", "0") != "1"     # =1: one all-reduce after the step (A/B)
+        gev = self._dp_events() if overlap else None
         loss = eng.train_step(topo, inputs[0], labels[0].contiguous(), w.contiguous() if w is not None else None,
-                              int(inputs[3]))
+                              int(inputs[3]), forward_event=fe, grad_events=gev)
         if fe is not None:
             self._last_fwd_event = fe
         scale = 1.0
-        if self._dp:
+        if dp and not overlap:
             import torch.distributed as dist
             from .parallel import world_size
-            if world_size() > 1:
-                dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM)
-                scale = 1.0 / world_size()
+            dist.all_reduce(eng.grads, op=dist.ReduceOp.SUM)
+            scale = 1.0 / world_size()
+        elif dp:
+            # Overlapped gradient exchange: the C call above only ENQUEUED the step, and recorded one event
+            # per gradient slice in the order the backward pass finishes them (head + dense, then conv layer L-1 .. 0).
+            # Each slice is all-reduced on a communication stream as soon as its event fires, beside the rest of the
+            # backward pass; the Adam launch waits for the last one.  (One all-reduce after the whole step cost 77 us of
+            # a 1.23 ms step at 8 GPUs.)
+            import torch.distributed as dist
+            from .parallel import world_size
+            comm = self._comm_stream
+            works = []
+            for ev, (lo, hi) in zip(gev, eng.grad_slices()):
+                comm.wait_event(ev)
+                with torch.cuda.stream(comm):
+                    works.append(dist.all_reduce(eng.grads[lo:hi], op=dist.ReduceOp.SUM, async_op=True))
+            for wk in works:
+                wk.wait()                    # stream-level: the training stream waits, the host does not
+            scale = 1.0 / world_size()
         eng.adam_step(scale)
         if eng.cfg.batch_norm:
             torch._foreach_add_([bn.num_batches_tracked for bn in self.model.batch_norms], 1)
         return loss
+
+    def _dp_events(self):
+        """Events of the gradient slices (one set per step in flight) and the communication stream, made on first use."""
+        if getattr(self, "_grad_event_sets", None) is None:
+            n = len(self._engine.grad_slices())
+            self._grad_event_sets = []
+            with torch.cuda.device(self.device):
+                for _ in range(4):
+                    evs = [torch.cuda.Event() for _ in range(n)]
+                    for e in evs:
+                        e.record()           # materialises the cudaEvent_t handle
+                    self._grad_event_sets.append(evs)
+                self._comm_stream = torch.cuda.Stream(device=self.device)
+        return self._grad_event_sets[self._global_step % len(self._grad_event_sets)]
 
     def enable_data_parallel(self):
         """Average gradients over the default process group every step (equal per-rank batches

@@ -506,11 +506,6 @@ int dcgc_gcmodel_forward(const dcgc_gcmodel_config* cfg, const dcgc_topology* to
                          int64_t ld_x, int64_t n_samples, const float* params_dev, float* bn_running_dev,
                          int32_t training, void* workspace_dev, int64_t workspace_bytes, float* out_dev,
                          float* probs_dev, float* fingerprint_dev, void* stream);
-/* Arms a one-shot hook for the calling thread: the next dcgc_gcmodel_train_step of this thread records `event`
- * (a cudaEvent_t, or NULL to disarm) on its stream between the forward and the backward pass.  The host pipeline
- * uses it to start the upload of a later batch while the GEMM-heavy backward runs instead of beside the
- * HBM-bound forward kernels (profiles/r2_interference.md). */
-int dcgc_gcmodel_set_forward_event(void* event);
 /* One training forward + loss + backward.  y: [n_samples, n_tasks] (regression) or one-hot
  * [n_samples, n_tasks, n_classes]; w: [n_samples, n_tasks] (may be NULL = ones).  loss_dev receives
  * the scalar loss (mean over n_samples * n_tasks elements); every gradient is written (not
@@ -520,6 +515,20 @@ int dcgc_gcmodel_train_step(const dcgc_gcmodel_config* cfg, const dcgc_topology*
                             const float* params_dev, float* grads_dev, float* bn_running_dev,
                             void* workspace_dev, int64_t workspace_bytes, float* loss_dev,
                             float* out_dev, void* stream);
+/* The same step with explicit event hooks (cudaEvent_t handles, every one optional) recorded on `stream`:
+ *   forward_event      between the forward and the backward pass (the host pipeline can start the upload of a later
+ *                      batch beside the GEMM-heavy backward instead of beside the HBM-bound forward kernels);
+ *   grad_events[i]     when gradient slice i of grads_dev is final, i < n_grad_events <= n_layers + 1:
+ *                      slice 0 = [dense, its BatchNorm, head] = offsets [dense_w, n_params),
+ *                      slice 1 + k = graph-conv layer n_layers - 1 - k with its BatchNorm = [conv_w[l], conv_w[l+1])
+ *                      (conv_w[n_layers] := dense_w; offsets from dcgc_gcmodel_layout).
+ * A data-parallel caller waits for each event on a communication stream and all-reduces that slice while the rest of
+ * the backward pass runs ("issue per-layer as soon as that layer's wgrad is written"). */
+int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const dcgc_topology* topo, const float* x_dev,
+                               int64_t ld_x, const float* y_dev, const float* w_dev, int64_t n_samples,
+                               const float* params_dev, float* grads_dev, float* bn_running_dev,
+                               void* workspace_dev, int64_t workspace_bytes, float* loss_dev, float* out_dev,
+                               void* forward_event, void* const* grad_events, int32_t n_grad_events, void* stream);
 /* Fused Adam over a flat slab, torch.optim.Adam semantics (models/optimizers.py:190-241);
  * grads are multiplied by grad_scale first (1/world_size after a summing all-reduce). */
 int dcgc_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
