@@ -375,3 +375,28 @@ def test_exact_input_path_is_bit_identical():
         res.append((float(loss), m._engine.grads.clone()))
     assert res[0][0] == res[1][0]
     assert torch.equal(res[0][1], res[1][1])
+
+
+def test_predict_through_the_staged_result_ring_equals_the_direct_copy(monkeypatch):
+    """Large predict() results go through a small ring of reusable pinned buffers + copier threads into pageable
+    arrays (cfg5: 1.28 GB of probabilities per GPU); the numbers must be those of the direct single-array path."""
+    from deepchem_b200 import graphconvmodel as G
+    from deepchem_b200.data import PackedDataset, ReplayDataset
+    from deepchem_b200.synthetic import make_molecules
+    _cuda()
+    shard = make_molecules(700, seed=31, shape="pcba").pin_memory()
+    torch.manual_seed(0)
+    m = G.GraphConvModel(16, [64, 64], 128, mode="classification", n_classes=2, batch_size=256)
+    ds = ReplayDataset(shard, 3000)
+    direct = m.predict(ds)
+    monkeypatch.setattr(G, "_PINNED_DIRECT_LIMIT", 1 << 10)
+    monkeypatch.setattr(G._StagedResult, "BUF_BYTES", 1 << 16)       # several seals per pass
+    staged = m.predict(ds)
+    assert staged.shape == direct.shape == (3000, 16, 2)
+    assert np.array_equal(staged, direct)
+    # rank shards of the replayed stream reassemble the whole pass
+    parts = [m.predict(ds, shard=(r, 3)) for r in range(3)]
+    assert np.array_equal(np.concatenate(parts, axis=0), direct)
+    # and the stream really replays the shard
+    assert np.array_equal(direct[:700], m.predict(PackedDataset(shard)))
+    assert np.array_equal(direct[700:1400], direct[:700])
