@@ -64,6 +64,7 @@ struct DcgcWgradArgs {
   int a1_vec, a2_vec, g_vec;
   int a_exact;      // [a1 | a2] holds tf32-exact values (see DcgcGemmOpts): the lo(A) tiles and their MMA are skipped
   long long* dbg;   // optional timeline buffer (dcgcdbg_tc_timeline)
+  int knob;         // measurement switches of tc_wgrad_kernel_v2 (env DCGC_WG2_KNOB), 0 in production
 };
 // Explicit per-call options of the tensor-core GEMMs (no thread-local side channels):
 //   img      a weight image built ahead with dcgc_tc_prep_weights (e.g. on another stream); null = the call builds
@@ -103,6 +104,32 @@ int dcgc_group_gemm_wgrad_opts(int32_t mode, const float* a1, int64_t ld_a1, int
                                int32_t k2, const float* g, int64_t ld_g, int32_t n, const int64_t* deg_count,
                                int32_t n_groups, float* dw, float* dbias, void* workspace, int64_t workspace_bytes,
                                int a_exact, void* stream);
+#endif
+
+#ifdef __CUDACC__
+// mbarrier wait shared by the tcgen05 GEMMs and the molecule-group kernels.  The wait itself is the hardware's
+// (try_wait suspends the thread); the guard around it is WALL-CLOCK based (%globaltimer, 20 s): a protocol bug still
+// traps instead of hanging the GPU, but a context that is preempted, time-sliced (MPS) or replayed by a profiler is
+// not killed by a spin count it happened to exceed.
+__device__ __forceinline__ void dcgc_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  unsigned long long t0 = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && (spin & 0xfffu) == 0xfffu) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) __trap();
+    }
+  }
+}
 #endif
 
 static inline int64_t dcgc_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }

@@ -16,6 +16,8 @@
 #include <mutex>
 #include <utility>
 
+#include <cuda.h>
+
 #include "common.h"
 
 namespace {
@@ -54,20 +56,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  // bounded spin: a protocol bug traps instead of hanging the GPU
-  for (uint32_t spin = 0; !done; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (spin > (1u << 22)) __trap();
-  }
-}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) { dcgc_mbar_wait(bar, parity); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -635,6 +624,161 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// Epilogue of the TS-form kernels (v4, v5), run by warps 0-7 of the CTA: warp w drains TMEM lanes 32 (w & 3) .. +31,
+// accumulator columns 64 (w >> 2) .. +63 with tcgen05.ld.16x256b and stores 8 rows x 32 bytes per instruction.
+// bar_acc_full / bar_acc_empty: the two-entry mbarrier arrays of the double-buffered accumulators (empty counts one
+// arrival per epilogue warp); shd: 8 KB of shared memory for the BatchNorm-statistics reduction.
+__device__ __forceinline__ void ts_epilogue(const TcArgs3& q, uint32_t tmem, uint32_t bar_acc_full, uint32_t bar_acc_empty,
+                                            double* shd, int my_tiles, int total, bool dbg_on) {
+  const TcArgs& p = q.a;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int P = gridDim.x, pid = blockIdx.x;
+  const int n0 = blockIdx.y * TC_BN;
+  const int N = p.n1 + p.n2;
+  // ===================== epilogue (warps 0-7) =====================
+  // Compact on purpose: the fully unrolled first version (32 store sites, each with its scalar fallback) did not fit
+  // the instruction cache — 29 k cycles for the first tile, 7.5-9 k for the others (profiles/r4f).  The 32-column
+  // block loop stays unrolled twice (the statistics registers are indexed by it), the lane-half loop is rolled, and
+  // the bounds-checked scalar path is one out-of-line loop.
+  const int qd = warp & 3, chalf = warp >> 2;
+  const int r_lo = lane >> 2, cp = lane & 3;
+  // fused BatchNorm statistics: this thread's column sums over the rows it stores, 16 columns (2 blocks x 4 pairs)
+  float su[16], sq[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { su[i] = 0.f; sq[i] = 0.f; }
+  const int act = p.act;
+  for (int it = 0; it < my_tiles; ++it) {
+    int row0, rows, g;
+    tile_of(p, pid + it * P, row0, rows, g);
+    if (q.knockout & 1) rows = 0;
+    const int acc = it & 1;
+    if (total > 0) {
+      mbar_wait(bar_acc_full + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+    }
+    if (dbg_on && tid == 0) q.dbg[4096 + 2 * it] = clock64();
+    const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_group_stride : nullptr;
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+      const int cb = chalf * 64 + blk * 32;                  // first accumulator column of this 32-column block
+      const int cblk = n0 + cb;
+      float2 bv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = cblk + 8 * j + 2 * cp;
+        bv[j] = make_float2(0.f, 0.f);
+        if (bias) {
+          if (c < N) bv[j].x = __ldg(bias + c);
+          if (c + 1 < N) bv[j].y = __ldg(bias + c + 1);
+        }
+      }
+      // the block lands in one output with 8-byte aligned pairs (warp-uniform); otherwise the scalar path
+      const bool fast1 = p.c1_vec && cblk + 32 <= p.n1;
+      const bool fast2 = !fast1 && p.c2_vec && cblk >= p.n1 && cblk + 32 <= N && ((cblk - p.n1) & 1) == 0;
+      float* dst = nullptr; int64_t ld = 0;
+      if (fast1) { dst = p.c1 + cblk + 2 * cp; ld = p.ld_c1; }
+      else if (fast2) { dst = p.c2 + (cblk - p.n1) + 2 * cp; ld = p.ld_c2; }
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[16];
+        if (total > 0) {
+          tmem_ld16(tmem + ((uint32_t)(qd * 32 + h * 16) << 16) + acc * TC_BN + cb, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = 0u;
+        }
+        const int row_a = qd * 32 + h * 16 + r_lo;           // and row_a + 8
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int rr = 0; rr < 2; ++rr) {
+            float ox = __uint_as_float(v[4 * j + 2 * rr]) + bv[j].x;
+            float oy = __uint_as_float(v[4 * j + 2 * rr + 1]) + bv[j].y;
+            if (act == DCGC_ACT_RELU) { ox = fmaxf(ox, 0.f); oy = fmaxf(oy, 0.f); }
+            else if (act == DCGC_ACT_TANH) { ox = tanhf(ox); oy = tanhf(oy); }
+            o[4 * j + 2 * rr] = ox; o[4 * j + 2 * rr + 1] = oy;
+          }
+        }
+        if (dst != nullptr) {
+          float* d0 = dst + (int64_t)(row0 + row_a) * ld;
+          float* d1 = d0 + 8 * ld;
+          const bool l0 = row_a < rows, l1 = row_a + 8 < rows;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (l0) *reinterpret_cast<float2*>(d0 + 8 * j) = make_float2(o[4 * j], o[4 * j + 1]);
+            if (l1) *reinterpret_cast<float2*>(d1 + 8 * j) = make_float2(o[4 * j + 2], o[4 * j + 3]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (!(((i >> 1) & 1) ? l1 : l0)) o[i] = 0.f;
+        } else {
+#pragma unroll 1
+          for (int i = 0; i < 16; ++i) {                    // i = 4 j + 2 rr + e
+            const int row = row_a + 8 * ((i >> 1) & 1), c = cblk + 8 * (i >> 2) + 2 * cp + (i & 1);
+            float val = 0.f;
+#pragma unroll
+            for (int t2 = 0; t2 < 16; ++t2) val = (t2 == i) ? o[t2] : val;     // (no dynamic register indexing)
+            const bool ok = row < rows && c < N;
+            if (ok) {
+              const int64_t grow = row0 + row;
+              if (c < p.n1) { if (p.c1) p.c1[grow * p.ld_c1 + c] = val; }
+              else if (p.c2) p.c2[grow * p.ld_c2 + (c - p.n1)] = val;
+            }
+#pragma unroll
+            for (int t2 = 0; t2 < 16; ++t2) o[t2] = (t2 == i && !ok) ? 0.f : o[t2];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float a = o[4 * j + e], b = o[4 * j + 2 + e];
+            su[blk * 8 + 2 * j + e] += a + b;
+            sq[blk * 8 + 2 * j + e] = fmaf(a, a, fmaf(b, b, sq[blk * 8 + 2 * j + e]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_acc_empty + 8 * acc);
+    if (dbg_on && tid == 0) q.dbg[4096 + 2 * it + 1] = clock64();
+  }
+  if (p.stats) {
+    // lanes with the same (lane & 3) hold the same columns (different rows): fixed-order butterfly over lane bits
+    // 2..4 in float64, then the four row quarters of each column half are combined in quarter order through shared
+    // memory (deterministic); one row of partials per CTA
+    // shd: [8 warps][2][64] doubles of shared memory
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      double a = (double)su[i], b = (double)sq[i];
+      a += __shfl_xor_sync(0xffffffffu, a, 4);  b += __shfl_xor_sync(0xffffffffu, b, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
+      if (lane < 4) {
+        const int col = (i >> 3) * 32 + ((i & 7) >> 1) * 8 + 2 * lane + (i & 1);   // inside this warp's 64 columns
+        shd[(warp * 2 + 0) * 64 + col] = a;
+        shd[(warp * 2 + 1) * 64 + col] = b;
+      }
+    }
+    named_bar_sync(2, 256);
+    if (qd == 0) {                       // warps 0 and 4: one thread per (quantity, column of the half)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int idx = lane + 32 * e;   // 0..127 = quantity * 64 + column
+        const int qn = idx >> 6, col = idx & 63;
+        double t = 0.0;
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) t += shd[((chalf * 4 + w4) * 2 + qn) * 64 + col];
+        const int c = n0 + chalf * 64 + col;
+        if (c < N) p.stats[((int64_t)pid * 2 + qn) * N + c] = t;
+      }
+    }
+  }
+}
+
 template <int NT>
 __global__ void __launch_bounds__(V4_THREADS, 1) tc_gemm_kernel_v4(const TcArgs3 q) {
   const TcArgs& p = q.a;
@@ -844,148 +988,238 @@ __global__ void __launch_bounds__(V4_THREADS, 1) tc_gemm_kernel_v4(const TcArgs3
       }
     }
   } else {
-    // ===================== epilogue (warps 0-7) =====================
-    // Compact on purpose: the fully unrolled first version (32 store sites, each with its scalar fallback) did not fit
-    // the instruction cache — 29 k cycles for the first tile, 7.5-9 k for the others (profiles/r4f).  The 32-column
-    // block loop stays unrolled twice (the statistics registers are indexed by it), the lane-half loop is rolled, and
-    // the bounds-checked scalar path is one out-of-line loop.
-    const int qd = warp & 3, chalf = warp >> 2;
-    const int r_lo = lane >> 2, cp = lane & 3;
-    // fused BatchNorm statistics: this thread's column sums over the rows it stores, 16 columns (2 blocks x 4 pairs)
-    float su[16], sq[16];
+    ts_epilogue(q, tmem, bar_base + 96, bar_base + 112, reinterpret_cast<double*>(sm + S * STAGE_BYTES + 256), my_tiles, total,
+                dbg_on);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// tc_gemm_kernel_v5: v4 with the A operand FED BY TMA.
+//
+// Why (profiles/r4g_gemm_timeline_v4.log): in v4 the producers load A with LDG into registers; with two chunks in
+// flight per warp the loads of a chunk come back 2-3.5 k cycles after they were issued and a chunk leaves the
+// producers every ~1 500 cycles, while one chunk of MMAs is 768 cycles of tensor time and the HBM floor of the
+// forward GEMM (16 KB of A + 8 KB of output per chunk and SM at 6.55 TB/s) is ~1 075 cycles.  The GEMM is memory
+// bound, so what it needs is BYTES IN FLIGHT: here one thread issues a tensor-map TMA load per chunk
+// (cp.async.bulk.tensor.2d, SWIZZLE_128B, SASS UTMALDG) into a five-deep ring of raw fp32 tiles — 80 KB in flight per
+// SM without a register — and the converter warps only move a landed tile from shared memory into tensor memory:
+// one row per thread, 8 conflict-free LDS.128 (the swizzle spreads the 8 rows of a quarter-warp over the 8 16-byte
+// chunks), tf32 hi / lo split, tcgen05.st.32x32b.  Rows past the tile (next degree bucket) are loaded and multiplied
+// but never stored; rows past the matrix and the K tail are zero-filled by the TMA unit.  Numerically identical to v4.
+// Shared-memory port per chunk: 16 KB A in + 16 KB A out + 32 KB weights in + 48 KB weights read by the MMAs =
+// 112 KB = 875 cycles, under the HBM floor.
+//
+// One persistent CTA per SM, 19 warps: 0-7 epilogue (ts_epilogue), 8-15 converters (two sets of four; set g takes
+// chunks g, g + 2, ...), 16 A loader, 17 MMA issuer, 18 weight loader (one cp.async.bulk of the ready-made image per
+// chunk).  TMEM: accumulators at columns 0 and 128, four A stages of 64 columns (32 hi + 32 lo) from 256; the weight
+// ring has the same depth and index as the A stages in tensor memory, so ONE tcgen05.commit frees both.
+// ------------------------------------------------------------------------------------------
+constexpr int V5_THREADS = 19 * 32;
+constexpr int V5_A_STAGES = 5;
+constexpr int V5_W_STAGES = 4;
+template <int NT> struct V5Cfg {
+  static constexpr int kBTiles = NT == 3 ? 2 : 1;
+  static constexpr int kWStageBytes = kBTiles * TC_TILE_BYTES;
+  static constexpr int kABytes = V5_A_STAGES * TC_TILE_BYTES;
+  static constexpr int kSmemBytes = kABytes + V5_W_STAGES * kWStageBytes + 1024 + 256 + 8 * 2 * 64 * 8;
+};
+// barrier offsets from bar_base
+constexpr uint32_t V5_A_FULL = 0, V5_A_EMPTY = 40, V5_W_FULL = 80, V5_T_FULL = 112, V5_WT_EMPTY = 144, V5_ACC_FULL = 176,
+                   V5_ACC_EMPTY = 192, V5_TMEM_SLOT = 208;
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_smem), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(V5_THREADS, 1)
+tc_gemm_kernel_v5(const TcArgs3 q, const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2) {
+  const TcArgs& p = q.a;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  constexpr int SA = V5_A_STAGES, SW = V5_W_STAGES;
+  constexpr int W_STAGE_BYTES = V5Cfg<NT>::kWStageBytes;
+  constexpr uint32_t A_BYTES = V5Cfg<NT>::kABytes;
+  const uint32_t w_base = base + A_BYTES;
+  const uint32_t bar_base = w_base + SW * W_STAGE_BYTES;
+  uint8_t* bar_ptr = sm + A_BYTES + SW * W_STAGE_BYTES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + V5_TMEM_SLOT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int P = gridDim.x, pid = blockIdx.x;
+  const int chunks1 = (p.k1 + TC_BK - 1) / TC_BK, chunks2 = (p.k2 + TC_BK - 1) / TC_BK;
+  const int total = chunks1 + chunks2;
+  const int my_tiles = pid < q.n_row_tiles ? (q.n_row_tiles - pid + P - 1) / P : 0;
+  const int n_cc = my_tiles * total;
+  const bool dbg_on = q.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && n_cc <= 1024;
+  if (dbg_on && tid == 0) q.dbg[5000] = clock64();
+
+  if (tid == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(bar_base + V5_A_FULL + 8 * s, 1);          // the loader's arrive.expect_tx (+ the TMA bytes)
+      mbar_init(bar_base + V5_A_EMPTY + 8 * s, 4);         // the four converter warps of one set
+    }
+    for (int s = 0; s < SW; ++s) {
+      mbar_init(bar_base + V5_W_FULL + 8 * s, 1);
+      mbar_init(bar_base + V5_T_FULL + 8 * s, 4);
+      mbar_init(bar_base + V5_WT_EMPTY + 8 * s, 1);        // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_base + V5_ACC_FULL + 8 * a, 1);
+      mbar_init(bar_base + V5_ACC_EMPTY + 8 * a, 8);       // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 17) tmem_alloc(bar_base + V5_TMEM_SLOT, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= 8 && warp < 16) {
+    // ===================== converters: shared memory (raw fp32, SWIZZLE_128B) -> tf32 hi / lo -> tensor memory ======
+    const int pw = warp - 8, set = pw >> 2, qd = pw & 3;
+    const int row = qd * 32 + lane;                                  // this thread's row of the tile = its TMEM lane
+    const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+    const uint32_t sw7 = (uint32_t)(row & 7);
+    const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
+    for (int cc = set; cc < n_cc; cc += 2) {
+      const int sa = cc % SA, st = cc % SW;
+      mbar_wait(bar_base + V5_A_FULL + 8 * sa, (cc / SA) & 1);               // the tile has landed
+      mbar_wait(bar_base + V5_WT_EMPTY + 8 * st, ((cc / SW) & 1) ^ 1);       // the MMAs that read this TMEM stage retired
+      tc_fence_after();
+      const uint8_t* tile = sm + sa * TC_TILE_BYTES + row_off;
+      const uint32_t a_col = V4_A_COL0 + (uint32_t)st * 64u;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { su[i] = 0.f; sq[i] = 0.f; }
-    const int act = p.act;
-    for (int it = 0; it < my_tiles; ++it) {
-      int row0, rows, g;
-      tile_of(p, pid + it * P, row0, rows, g);
-      if (q.knockout & 1) rows = 0;
-      const int acc = it & 1;
-      if (total > 0) {
-        mbar_wait(bar_base + 96 + 8 * acc, (it >> 1) & 1);
-        tc_fence_after();
-      }
-      if (dbg_on && tid == 0) q.dbg[4096 + 2 * it] = clock64();
-      const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_group_stride : nullptr;
+      for (int h = 0; h < 2; ++h) {
+        float4 v[4];
 #pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
-        const int cb = chalf * 64 + blk * 32;                  // first accumulator column of this 32-column block
-        const int cblk = n0 + cb;
-        float2 bv[4];
+        for (int c = 0; c < 4; ++c)
+          v[c] = *reinterpret_cast<const float4*>(tile + ((((uint32_t)(4 * h + c)) ^ sw7) << 4));
+        uint32_t hi[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c = cblk + 8 * j + 2 * cp;
-          bv[j] = make_float2(0.f, 0.f);
-          if (bias) {
-            if (c < N) bv[j].x = __ldg(bias + c);
-            if (c + 1 < N) bv[j].y = __ldg(bias + c + 1);
-          }
+        for (int c = 0; c < 4; ++c) {
+          hi[4 * c + 0] = __float_as_uint(term_hi<NT>(v[c].x));
+          hi[4 * c + 1] = __float_as_uint(term_hi<NT>(v[c].y));
+          hi[4 * c + 2] = __float_as_uint(term_hi<NT>(v[c].z));
+          hi[4 * c + 3] = __float_as_uint(term_hi<NT>(v[c].w));
         }
-        // the block lands in one output with 8-byte aligned pairs (warp-uniform); otherwise the scalar path
-        const bool fast1 = p.c1_vec && cblk + 32 <= p.n1;
-        const bool fast2 = !fast1 && p.c2_vec && cblk >= p.n1 && cblk + 32 <= N && ((cblk - p.n1) & 1) == 0;
-        float* dst = nullptr; int64_t ld = 0;
-        if (fast1) { dst = p.c1 + cblk + 2 * cp; ld = p.ld_c1; }
-        else if (fast2) { dst = p.c2 + (cblk - p.n1) + 2 * cp; ld = p.ld_c2; }
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[16];
-          if (total > 0) {
-            tmem_ld16(tmem + ((uint32_t)(qd * 32 + h * 16) << 16) + acc * TC_BN + cb, v);
-            tmem_ld_wait();
-          } else {
+        tmem_st32x16(t_lane + a_col + 16u * h, hi);
+        if (NT == 3 && !q.a_exact) {
+          uint32_t lo[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0u;
+          for (int c = 0; c < 4; ++c) {
+            lo[4 * c + 0] = __float_as_uint(tf32_lo(v[c].x, __uint_as_float(hi[4 * c + 0])));
+            lo[4 * c + 1] = __float_as_uint(tf32_lo(v[c].y, __uint_as_float(hi[4 * c + 1])));
+            lo[4 * c + 2] = __float_as_uint(tf32_lo(v[c].z, __uint_as_float(hi[4 * c + 2])));
+            lo[4 * c + 3] = __float_as_uint(tf32_lo(v[c].w, __uint_as_float(hi[4 * c + 3])));
           }
-          const int row_a = qd * 32 + h * 16 + r_lo;           // and row_a + 8
-          float o[16];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-              float ox = __uint_as_float(v[4 * j + 2 * rr]) + bv[j].x;
-              float oy = __uint_as_float(v[4 * j + 2 * rr + 1]) + bv[j].y;
-              if (act == DCGC_ACT_RELU) { ox = fmaxf(ox, 0.f); oy = fmaxf(oy, 0.f); }
-              else if (act == DCGC_ACT_TANH) { ox = tanhf(ox); oy = tanhf(oy); }
-              o[4 * j + 2 * rr] = ox; o[4 * j + 2 * rr + 1] = oy;
-            }
-          }
-          if (dst != nullptr) {
-            float* d0 = dst + (int64_t)(row0 + row_a) * ld;
-            float* d1 = d0 + 8 * ld;
-            const bool l0 = row_a < rows, l1 = row_a + 8 < rows;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (l0) *reinterpret_cast<float2*>(d0 + 8 * j) = make_float2(o[4 * j], o[4 * j + 1]);
-              if (l1) *reinterpret_cast<float2*>(d1 + 8 * j) = make_float2(o[4 * j + 2], o[4 * j + 3]);
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (!(((i >> 1) & 1) ? l1 : l0)) o[i] = 0.f;
-          } else {
-#pragma unroll 1
-            for (int i = 0; i < 16; ++i) {                    // i = 4 j + 2 rr + e
-              const int row = row_a + 8 * ((i >> 1) & 1), c = cblk + 8 * (i >> 2) + 2 * cp + (i & 1);
-              float val = 0.f;
-#pragma unroll
-              for (int t2 = 0; t2 < 16; ++t2) val = (t2 == i) ? o[t2] : val;     // (no dynamic register indexing)
-              const bool ok = row < rows && c < N;
-              if (ok) {
-                const int64_t grow = row0 + row;
-                if (c < p.n1) { if (p.c1) p.c1[grow * p.ld_c1 + c] = val; }
-                else if (p.c2) p.c2[grow * p.ld_c2 + (c - p.n1)] = val;
-              }
-#pragma unroll
-              for (int t2 = 0; t2 < 16; ++t2) o[t2] = (t2 == i && !ok) ? 0.f : o[t2];
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const float a = o[4 * j + e], b = o[4 * j + 2 + e];
-              su[blk * 8 + 2 * j + e] += a + b;
-              sq[blk * 8 + 2 * j + e] = fmaf(a, a, fmaf(b, b, sq[blk * 8 + 2 * j + e]));
-            }
-          }
+          tmem_st32x16(t_lane + a_col + 32u + 16u * h, lo);
         }
       }
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_base + 112 + 8 * acc);
-      if (dbg_on && tid == 0) q.dbg[4096 + 2 * it + 1] = clock64();
-    }
-    if (p.stats) {
-      // lanes with the same (lane & 3) hold the same columns (different rows): fixed-order butterfly over lane bits
-      // 2..4 in float64, then the four row quarters of each column half are combined in quarter order through shared
-      // memory (deterministic); one row of partials per CTA
-      double* shd = reinterpret_cast<double*>(sm + S * STAGE_BYTES + 256);   // [8 warps][2][64]
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        double a = (double)su[i], b = (double)sq[i];
-        a += __shfl_xor_sync(0xffffffffu, a, 4);  b += __shfl_xor_sync(0xffffffffu, b, 4);
-        a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
-        a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
-        if (lane < 4) {
-          const int col = (i >> 3) * 32 + ((i & 7) >> 1) * 8 + 2 * lane + (i & 1);   // inside this warp's 64 columns
-          shd[(warp * 2 + 0) * 64 + col] = a;
-          shd[(warp * 2 + 1) * 64 + col] = b;
-        }
+      if (lane == 0) {
+        mbar_arrive(bar_base + V5_A_EMPTY + 8 * sa);       // the raw tile may be overwritten
+        mbar_arrive(bar_base + V5_T_FULL + 8 * st);        // A (hi, lo) of this chunk is in tensor memory
       }
-      named_bar_sync(2, 256);
-      if (qd == 0) {                       // warps 0 and 4: one thread per (quantity, column of the half)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int idx = lane + 32 * e;   // 0..127 = quantity * 64 + column
-          const int qn = idx >> 6, col = idx & 63;
-          double t = 0.0;
-#pragma unroll
-          for (int w4 = 0; w4 < 4; ++w4) t += shd[((chalf * 4 + w4) * 2 + qn) * 64 + col];
-          const int c = n0 + chalf * 64 + col;
-          if (c < N) p.stats[((int64_t)pid * 2 + qn) * N + c] = t;
+      if (dbg_on && lane == 0 && qd == 0) q.dbg[(set ? 1024 : 0) + (cc >> 1)] = clock64();
+    }
+  } else if (warp == 16) {
+    // ===================== A loader: one tensor-map TMA load per chunk =====================
+    if (lane == 0) {
+      int cc = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        int row0, rows, g;
+        tile_of(p, pid + it * P, row0, rows, g);
+        for (int ch = 0; ch < total; ++ch, ++cc) {
+          const int s = cc % SA;
+          mbar_wait(bar_base + V5_A_EMPTY + 8 * s, ((cc / SA) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_base + V5_A_FULL + 8 * s, (uint32_t)TC_TILE_BYTES);
+          if (ch < chunks1) tma_load_2d(base + s * TC_TILE_BYTES, &map1, ch * TC_BK, row0, bar_base + V5_A_FULL + 8 * s);
+          else tma_load_2d(base + s * TC_TILE_BYTES, &map2, (ch - chunks1) * TC_BK, row0, bar_base + V5_A_FULL + 8 * s);
+          if (dbg_on) q.dbg[2048 + cc] = clock64();
         }
       }
     }
+  } else if (warp == 18) {
+    // ===================== weight loader: one bulk copy of the ready-made image per chunk =====================
+    if (lane == 0) {
+      int cc = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        int row0, rows, g;
+        tile_of(p, pid + it * P, row0, rows, g);
+        constexpr int kBFloats = V5Cfg<NT>::kBTiles * TC_BM * TC_BK;
+        constexpr uint32_t kBBytes = (uint32_t)W_STAGE_BYTES;
+        const float* src = q.img + ((int64_t)g * q.n_tiles_n + blockIdx.y) * total * kBFloats;
+        for (int ch = 0; ch < total; ++ch, ++cc) {
+          const int s = cc % SW;
+          mbar_wait(bar_base + V5_WT_EMPTY + 8 * s, ((cc / SW) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_base + V5_W_FULL + 8 * s, kBBytes);
+          bulk_g2s(w_base + s * W_STAGE_BYTES, src + (int64_t)ch * kBFloats, kBBytes, bar_base + V5_W_FULL + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int cc = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int acc = it & 1;
+        mbar_wait(bar_base + V5_ACC_EMPTY + 8 * acc, ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem + acc * TC_BN;
+        for (int ch = 0; ch < total; ++ch, ++cc) {
+          const int s = cc % SW;
+          const uint32_t par = (cc / SW) & 1;
+          mbar_wait(bar_base + V5_W_FULL + 8 * s, par);
+          mbar_wait(bar_base + V5_T_FULL + 8 * s, par);
+          tc_fence_after();
+          if (dbg_on) q.dbg[3072 + cc] = clock64();
+          const uint32_t sb = w_base + s * W_STAGE_BYTES;
+          const uint32_t a_hi = tmem + V4_A_COL0 + (uint32_t)s * 64u, a_lo = a_hi + 32u;
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UK; ++k) {
+            const uint32_t ko = k * TC_UK * 4;
+            if (NT == 3) {
+              const uint64_t bhi = make_desc(sb + ko), blo = make_desc(sb + TC_TILE_BYTES + ko);
+              if (!q.a_exact) {
+                umma_tf32_ts(d, a_lo + k * TC_UK, bhi, kIdescTf32, (ch | k) != 0);
+                umma_tf32_ts(d, a_hi + k * TC_UK, blo, kIdescTf32, 1);
+              } else {
+                umma_tf32_ts(d, a_hi + k * TC_UK, blo, kIdescTf32, (ch | k) != 0);
+              }
+              umma_tf32_ts(d, a_hi + k * TC_UK, bhi, kIdescTf32, 1);
+            } else {
+              umma_tf32_ts(d, a_hi + k * TC_UK, make_desc(sb + ko), kIdescTf32, (ch | k) != 0);
+            }
+          }
+          umma_commit(bar_base + V5_WT_EMPTY + 8 * s);
+        }
+        umma_commit(bar_base + V5_ACC_FULL + 8 * acc);
+      }
+    }
+  } else {
+    ts_epilogue(q, tmem, bar_base + V5_ACC_FULL, bar_base + V5_ACC_EMPTY, reinterpret_cast<double*>(bar_ptr + 256), my_tiles,
+                total, dbg_on);
   }
   tc_fence_before();
   __syncthreads();
@@ -1246,6 +1480,361 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// tc_wgrad_kernel_v2: the weight gradient with the operand roles SWAPPED and the MMAs 256 columns wide.
+//
+// Why (scripts/mma_rate.py, profiles/r5d_mma_rate.md): one tcgen05.mma with N = 128 occupies the tensor pipe for
+// 110-116 cycles whatever its operands, one with N = 256 and the A operand in tensor memory for 138 — twice the work
+// for 1.2x the time.  The first kernel computed dW[features, channels] with the features as M (two 128-row MMAs per
+// K step and term, N = 128 channels): 24 MMAs = 2 640 cycles per 32-atom chunk, above the chunk's HBM floor of 2 150.
+// Here the CHANNELS are M and the 256 features [a1 | a2] are N:
+//     D[channel, feature] = sum over atoms  G^T[channel, atom] . [a1 | a2]^T[feature, atom]
+//   * A operand = G^T, in TENSOR MEMORY: a loader thread owns one channel, reads its 32 values of a chunk with 32
+//     coalesced 4-byte loads (a warp instruction = 128 contiguous bytes of one atom row), splits them and writes them
+//     with tcgen05.st.32x32b — lane = channel, column = atom: the transposition costs nothing; the column sums of G
+//     (the bias gradient) are one register per thread;
+//   * B operand = [a1 | a2]: MN-major SWIZZLE_128B_BASE32B tiles in shared memory as before (the producers only copy
+//     and split), now ONE 256-feature tile per term;
+//   * 12 MMAs of N = 256 per chunk = 1 656 cycles; shared-memory port: 64 KB of stores + 96 KB of MMA reads = 1 250.
+//   * D[128 channels x 256 features] stays in tensor memory for the whole CTA; the epilogue thread of lane n stores
+//     dW[m][n] for 32 features m at a time — consecutive lanes are consecutive channels, so the partials are written
+//     with coalesced stores and no transposition.
+// Warps 0-3 G loaders (then epilogue), 4-11 [a1 | a2] producers, 12 MMA issuer.  TMEM: D at columns 0..255, four
+// G stages of 64 columns (32 hi + 32 lo) from 256.  NB = number of 128-feature blocks of the CTA's tile (1 or 2).
+// ------------------------------------------------------------------------------------------
+constexpr int WG2_THREADS = 13 * 32;
+constexpr int WG2_B_STAGES = 3;
+constexpr int WG2_G_STAGES = 4;
+__device__ __forceinline__ uint64_t make_desc_mn_nb(uint32_t saddr, int nb) {
+  // MN atoms (32 fp32) 512 bytes apart, K groups (4 atoms) nb * 2048 bytes apart
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (32ull << 16) | ((uint64_t)(nb * 128) << 32) | (1ull << 46) | (1ull << 61);
+}
+
+template <int NB, int NT>
+__global__ void __launch_bounds__(WG2_THREADS, 1) tc_wgrad_kernel_v2(const DcgcWgradArgs p) {
+  constexpr int TPO = NT == 3 ? 2 : 1;                          // tiles per operand: (hi, lo) or one
+  constexpr int B_TILE_BYTES = NB * TC_TILE_BYTES;              // one term of the [32 atoms x NB * 128 features] chunk
+  constexpr int STAGE_BYTES = TPO * B_TILE_BYTES;
+  constexpr int NLB = 4 * NB;                                   // float4 loads per producer thread and chunk
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar_base = base + WG2_B_STAGES * STAGE_BYTES;
+  // barriers: b_full[s] +8s, b_empty[s] +24+8s, g_full[s] +48+8s, g_empty[s] +80+8s, accumulator ready +112, tmem slot +120
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + WG2_B_STAGES * STAGE_BYTES + 120);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x;
+  int g = 0;
+  while (g + 1 < p.n_groups && chunk >= p.chunk_prefix[g + 1]) ++g;
+  const int64_t r_begin = p.group_row0[g] + (int64_t)(chunk - p.chunk_prefix[g]) * p.chunk_rows;
+  const int64_t r_end = min(p.group_row0[g + 1], r_begin + p.chunk_rows);
+  const int mp = blockIdx.y / p.tiles_n, nt = blockIdx.y - mp * p.tiles_n;
+  const int m0 = mp * NB * TC_BM, n0 = nt * TC_BN;
+  const int Kt = p.k1 + p.k2;
+  const int steps = (int)((r_end - r_begin + TC_BK - 1) / TC_BK);
+  const bool wdbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  if (wdbg && tid == 0) { p.dbg[5000] = clock64(); p.dbg[5001] = steps; }
+  if (p.dbg != nullptr && tid == 0 && blockIdx.y == 0 && blockIdx.x < 512) {      // whole-grid view: [6000 + 4 b ..] =
+    unsigned long long gt;                                                          // start ns, end ns, chunks, SM id
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.dbg[6000 + 4 * blockIdx.x] = (long long)gt; p.dbg[6002 + 4 * blockIdx.x] = steps; p.dbg[6003 + 4 * blockIdx.x] = smid;
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < WG2_B_STAGES; ++s) {
+      mbar_init(bar_base + 8 * s, 8);                // the eight producer warps
+      mbar_init(bar_base + 24 + 8 * s, 1);           // tcgen05.commit
+    }
+    for (int s = 0; s < WG2_G_STAGES; ++s) {
+      mbar_init(bar_base + 48 + 8 * s, 4);           // the four loader warps
+      mbar_init(bar_base + 80 + 8 * s, 1);
+    }
+    mbar_init(bar_base + 112, 1);
+    fence_barrier_init();
+  }
+  if (warp == 12) tmem_alloc(bar_base + 120, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== G loaders: lane = channel, registers = the 32 atoms of a chunk =====================
+    const int n = n0 + 32 * warp + lane;
+    const bool n_ok = n < p.n;
+    const float* gcol = p.g + n;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * warp) << 16) + V4_A_COL0;
+    float bsum = 0.f;
+    auto gload = [&](float (&v)[32], int c) {
+      const int64_t row0 = r_begin + (int64_t)c * TC_BK;
+      const float* src = gcol + row0 * p.ld_g;
+#pragma unroll
+      for (int a = 0; a < 32; ++a)
+        v[a] = (n_ok && row0 + a < r_end) ? __ldg(src + (int64_t)a * p.ld_g) : 0.f;
+    };
+    auto gstore = [&](const float (&v)[32], int c) {
+      const int s = c % WG2_G_STAGES;
+      mbar_wait(bar_base + 80 + 8 * s, ((c / WG2_G_STAGES) & 1) ^ 1);      // the MMAs that read this stage retired
+      tc_fence_after();
+      const uint32_t col = t_lane + (uint32_t)s * 64u;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t hi[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hi[i] = __float_as_uint(term_hi<NT>(v[16 * h + i]));
+        tmem_st32x16(col + 16u * h, hi);
+        if (NT == 3) {
+          uint32_t lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) lo[i] = __float_as_uint(tf32_lo(v[16 * h + i], __uint_as_float(hi[i])));
+          tmem_st32x16(col + 32u + 16u * h, lo);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 32; ++a) bsum += v[a];
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_base + 48 + 8 * s);
+      if (wdbg && tid == 0 && c < 1000) p.dbg[2048 + c] = clock64();
+    };
+    float va[32], vb[32];
+    if (steps > 0) gload(va, 0);
+    for (int c = 0; c < steps; c += 2) {
+      if (c + 1 < steps) gload(vb, c + 1);
+      gstore(va, c);
+      if (c + 2 < steps) gload(va, c + 2);
+      if (c + 1 < steps) gstore(vb, c + 1);
+    }
+    // bias-gradient partial of this chunk: atoms in chunk order (deterministic)
+    if (mp == 0 && n_ok) p.wsb[(int64_t)chunk * p.n + n] = bsum;
+  } else if (warp < 12) {
+    // ===================== [a1 | a2] producers: copy + split into MN-major tiles (see tc_wgrad_kernel) ============
+    const int pw = warp - 4;
+    const int la = lane >> 3, lc = lane & 7;
+    const int k = 4 * pw + la;                    // atom inside the 32-atom chunk = K index
+    // [K group k>>2][MN atom (32 features)][row k&3][32-byte chunk ^ row]; MN atoms 512 B apart, K groups NB * 2048 B
+    const uint32_t k_off = (uint32_t)((k >> 2) * (NB * 2048) + (k & 3) * 128 + (((lc >> 1) ^ (k & 3)) << 5) + (lc & 1) * 16);
+    // Branch-free loads when every float4 lies inside one operand (rows 16-byte aligned, k1 and k2 multiples of 4 —
+    // the layouts of the engines): two base pointers, one select and one predicated LDG.128 per load.  (The first
+    // version took the general path — a three-way branch per load — and needed 7-10 k cycles to ISSUE the loads of
+    // one chunk the first time round and ~1.5 k later: instruction fetch, not memory, set the pace.)
+    const bool fast = p.a1_vec && (p.k2 == 0 || p.a2_vec) && (p.k1 & 3) == 0 && (p.k2 & 3) == 0;
+    const float* bp1 = p.a1 + (r_begin + k) * p.ld_a1 + 4 * lc;
+    const float* bp2 = p.k2 > 0 ? p.a2 + (r_begin + k) * p.ld_a2 + 4 * lc - p.k1 : bp1;
+    const int64_t cs1 = (int64_t)TC_BK * p.ld_a1, cs2 = (int64_t)TC_BK * p.ld_a2;
+    auto gload = [&](float4 (&r)[NLB], int c) {
+      const int64_t row = r_begin + (int64_t)c * TC_BK + k;
+      const bool live = row < r_end;
+      if (fast) {
+        const float* q1 = bp1 + c * cs1;
+        const float* q2 = bp2 + c * cs2;
+#pragma unroll
+        for (int j = 0; j < NLB; ++j) {
+          const int mb = m0 + 32 * j, m = mb + 4 * lc;
+          const float* src = m < p.k1 ? q1 + mb : q2 + mb;
+          r[j] = (live && m < Kt) ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return;
+      }
+#pragma unroll 1
+      for (int j = 0; j < NLB; ++j) {
+        const int m = m0 + 32 * j + 4 * lc;
+        float e[4] = {0.f, 0.f, 0.f, 0.f};
+        if (live) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int fe = m + q;
+            if (fe < p.k1) e[q] = __ldg(p.a1 + row * p.ld_a1 + fe);
+            else if (fe < Kt) e[q] = __ldg(p.a2 + row * p.ld_a2 + (fe - p.k1));
+          }
+        }
+        const float4 v = make_float4(e[0], e[1], e[2], e[3]);
+#pragma unroll
+        for (int jj = 0; jj < NLB; ++jj)
+          if (jj == j) r[jj] = v;                 // (no dynamic register indexing)
+      }
+    };
+    auto sstore = [&](const float4 (&r)[NLB], int c) {
+      const int s = c % WG2_B_STAGES;
+      if (wdbg && tid == 128 && c < 1000) p.dbg[1024 + c] = clock64();
+      mbar_wait(bar_base + 24 + 8 * s, ((c / WG2_B_STAGES) & 1) ^ 1);
+      uint8_t* hi_t = sm + s * STAGE_BYTES + k_off;
+      uint8_t* lo_t = hi_t + B_TILE_BYTES;
+#pragma unroll
+      for (int j = 0; j < NLB; ++j) {
+        if (NT == 3) {
+          float4 hi, lo;
+          split4(r[j], hi, lo);
+          *reinterpret_cast<float4*>(hi_t + j * 512) = hi;
+          if (!p.a_exact) *reinterpret_cast<float4*>(lo_t + j * 512) = lo;
+        } else {
+          *reinterpret_cast<float4*>(hi_t + j * 512) = round4_bf16(r[j]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_base + 8 * s);
+      if (wdbg && tid == 128 && c < 1000) p.dbg[c] = clock64();
+    };
+    float4 ra[NLB], rb[NLB], rc[NLB];
+    if (steps > 0) gload(ra, 0);
+    if (!(p.knob & 1)) {              // two chunks in flight; knob 1: three (measured: later first commit, same pace)
+      for (int c = 0; c < steps; c += 2) {
+        if (c + 1 < steps) gload(rb, c + 1);
+        sstore(ra, c);
+        if (c + 2 < steps) gload(ra, c + 2);
+        if (c + 1 < steps) sstore(rb, c + 1);
+      }
+    } else {
+      if (steps > 1) gload(rb, 1);
+      for (int c = 0; c < steps; c += 3) {
+        if (c + 2 < steps) gload(rc, c + 2);
+        sstore(ra, c);
+        if (c + 3 < steps) gload(ra, c + 3);
+        if (c + 1 < steps) sstore(rb, c + 1);
+        if (c + 4 < steps) gload(rb, c + 4);
+        if (c + 2 < steps) sstore(rc, c + 2);
+      }
+    }
+  } else if (lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)((NB * TC_BN) >> 3) << 17) |
+                               ((uint32_t)(TC_BM >> 4) << 24);        // A (TMEM) K-major, B MN-major, N = NB * 128
+    for (int c = 0; c < steps; ++c) {
+      const int sb = c % WG2_B_STAGES, sg = c % WG2_G_STAGES;
+      mbar_wait(bar_base + 8 * sb, (c / WG2_B_STAGES) & 1);
+      mbar_wait(bar_base + 48 + 8 * sg, (c / WG2_G_STAGES) & 1);
+      tc_fence_after();
+      if (wdbg && c < 1000) p.dbg[3072 + c] = clock64();
+      const uint32_t b_hi = base + sb * STAGE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+      const uint32_t g_hi = tmem + V4_A_COL0 + (uint32_t)sg * 64u, g_lo = g_hi + 32u;
+#pragma unroll
+      for (int k = 0; k < TC_BK / TC_UK; ++k) {
+        const uint32_t ko = (uint32_t)k * (2u * NB * 2048u);          // K rows 8k..8k+7 = two K groups of 4
+        const uint64_t bhi = make_desc_mn_nb(b_hi + ko, NB), blo = make_desc_mn_nb(b_lo + ko, NB);
+        if (NT == 3) {
+          umma_tf32_ts(tmem, g_lo + k * TC_UK, bhi, idesc, (c | k) != 0);
+          if (!p.a_exact) umma_tf32_ts(tmem, g_hi + k * TC_UK, blo, idesc, 1);
+          umma_tf32_ts(tmem, g_hi + k * TC_UK, bhi, idesc, 1);
+        } else {
+          umma_tf32_ts(tmem, g_hi + k * TC_UK, bhi, idesc, (c | k) != 0);
+        }
+      }
+      umma_commit(bar_base + 24 + 8 * sb);
+      umma_commit(bar_base + 80 + 8 * sg);
+    }
+    umma_commit(bar_base + 112);
+  }
+  if (warp < 12) {
+    // ===================== epilogue: D[lane = channel, column = feature] -> ws[chunk][feature][channel] =========
+    // all twelve loader / producer warps: warp w drains TMEM lanes 32 (w & 3) .. +31 and every third 32-column block
+    // (four warps alone needed 12 k cycles for the 128 KB of partials: ~47 cycles per 128-byte store instruction)
+    const int qd = warp & 3, third = warp >> 2;
+    const int n = n0 + 32 * qd + lane;
+    const bool n_ok = n < p.n;
+    if (wdbg && tid == 0) p.dbg[4096] = clock64();
+    if (steps > 0) {
+      mbar_wait(bar_base + 112, 0);
+      tc_fence_after();
+    }
+    if (wdbg && tid == 0) p.dbg[4097] = clock64();
+    float* dst = p.ws + ((int64_t)chunk * Kt + m0) * p.n + n;
+#pragma unroll 1
+    for (int cb = 32 * third; cb < NB * TC_BM; cb += 96) {
+      if (m0 + cb >= Kt) break;
+      uint32_t v[32];
+      if (steps > 0) {
+        tmem_ld32(tmem + ((uint32_t)(32 * qd) << 16) + cb, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+      if (n_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (m0 + cb + i < Kt) dst[(int64_t)(cb + i) * p.n] = __uint_as_float(v[i]);
+      }
+    }
+    if (wdbg && tid == 0) p.dbg[4098] = clock64();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (p.dbg != nullptr && tid == 0 && blockIdx.y == 0 && blockIdx.x < 512) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[6001 + 4 * blockIdx.x] = (long long)gt;
+  }
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Debugging aid (not part of the ABI): the issue rate of tcgen05.mma in the forms the kernels above use.
+// One warp of one CTA per SM issues `reps` back-to-back MMAs of one variant over zero-filled operands, commits, waits,
+// and reports clock64() cycles per MMA.  variant bits: 0 = A from TMEM (TS) instead of shared memory (SS);
+// 1 = N 256 instead of 128; 2 = alternate between two accumulators; 3 = cycle over 4 different B tiles (and A tiles);
+// 4 = kind::f16 (bf16 operands, K 16) instead of kind::tf32 (K 8).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_f16_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int variant, int reps, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  // 4 A tiles of 16 KB + 4 B tiles of 32 KB (N up to 256 rows x 128 bytes), zero filled; barrier + tmem slot behind
+  const uint32_t bar = base + 196608;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + 196608 + 16);
+  for (int i = threadIdx.x; i < 196608 / 16; i += blockDim.x) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  fence_proxy_async();
+  if (threadIdx.x < 32) tmem_alloc(base + 196608 + 16, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const bool ts = variant & 1, n256 = variant & 2, alt = variant & 4, cyc = variant & 8, f16 = variant & 16;
+  const int nn = n256 ? 256 : 128;
+  // idesc: D f32; kind::tf32 A = B = tf32 (2), kind::f16 A = B = bf16 (1); K-major both; N, M = 128
+  const uint32_t idesc = (1u << 4) | ((f16 ? 1u : 2u) << 7) | ((f16 ? 1u : 2u) << 10) | ((uint32_t)(nn >> 3) << 17) |
+                         ((uint32_t)(128 >> 4) << 24);
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      const int sel = cyc ? (r & 3) : 0;
+      const uint32_t d = tmem + ((alt && (r & 1)) ? (uint32_t)nn : 0u);
+      const uint64_t bd = make_desc(base + 65536 + sel * 32768 + (r & 3) * 32);
+      if (ts) {
+        const uint32_t a = tmem + (n256 && alt ? 0u : (alt ? 2u : 1u) * nn) + (uint32_t)sel * 8u;   // (N 256 + two accumulators: A overlaps D, timing only)
+        if (f16) umma_f16_ts(d, a, bd, idesc, 1); else umma_tf32_ts(d, a, bd, idesc, 1);
+      } else {
+        const uint64_t ad = make_desc(base + sel * 16384 + (r & 3) * 32);
+        if (f16) umma_f16_ss(d, ad, bd, idesc, 1); else umma_tf32(d, ad, bd, idesc, 1);
+      }
+    }
+    umma_commit(bar);
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 
@@ -1263,6 +1852,14 @@ int ensure_smem_attr() {
                                         V4Cfg<3>::kSmemBytes));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         V4Cfg<1>::kSmemBytes));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v5<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        V5Cfg<3>::kSmemBytes));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v5<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        V5Cfg<1>::kSmemBytes));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v2<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v2<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v2<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v2<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1275,6 +1872,39 @@ int ensure_smem_attr() {
   return DCGC_OK;
 }
 
+
+// ---- tensor maps (TMA descriptors) of row-major fp32 operands -------------------------------------------------------
+// cuTensorMapEncodeTiled is a driver entry point; it is resolved through the runtime once per process (libdcgc does
+// not link libcuda).  The box is one K chunk of one row tile: 32 floats (= the 128-byte swizzle span) x 128 rows.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+// rows x k floats, leading dimension ld (floats; ld % 4 == 0, base 16-byte aligned)
+int make_a_map(CUtensorMap* map, const float* a, int64_t rows, int k, int64_t ld, uint32_t box_k, uint32_t box_rows,
+               CUtensorMapSwizzle swz) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) { dcgc_set_error("cuTensorMapEncodeTiled is not available from this driver"); return DCGC_ERR_CUDA; }
+  const cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {box_k, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(a), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { dcgc_set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return DCGC_ERR_CUDA; }
+  return DCGC_OK;
+}
 }  // namespace
 
 // ---- split-weight images ----------------------------------------------------------------------------------
@@ -1373,13 +2003,23 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
     dim3 grid((unsigned)ctas, (unsigned)n_tiles_n);
     // DCGC_TC_V3=1: the previous kernel (both operands in shared memory), kept for A/B measurements
     static const bool use_v3 = [] { const char* e = getenv("DCGC_TC_V3"); return e && e[0] == '1'; }();
+    static const bool use_v4 = [] { const char* e = getenv("DCGC_TC_V4"); return e && e[0] == '1'; }();
     if (use_v3) {
       q3.a_exact = 0;
       if (nt == 3) tc_gemm_kernel_v3<3><<<grid, V3_THREADS, V3Cfg<3>::kSmemBytes, st>>>(q3);
       else tc_gemm_kernel_v3<1><<<grid, V3_THREADS, V3Cfg<1>::kSmemBytes, st>>>(q3);
-    } else {
+    } else if (use_v4 || !p3.a1_vec || (a2 && !p3.a2_vec) || n_rows >= (1ll << 31)) {
+      // register-fed producers: operands whose rows are not 16-byte aligned (no tensor map), or DCGC_TC_V4=1
       if (nt == 3) tc_gemm_kernel_v4<3><<<grid, V4_THREADS, V4Cfg<3>::kSmemBytes, st>>>(q3);
       else tc_gemm_kernel_v4<1><<<grid, V4_THREADS, V4Cfg<1>::kSmemBytes, st>>>(q3);
+    } else {
+      alignas(64) CUtensorMap m1, m2;
+      st_ = make_a_map(&m1, a1, n_rows, k1, ld_a1, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (st_ == DCGC_OK) st_ = a2 ? make_a_map(&m2, a2, n_rows, k2, ld_a2, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B)
+                                   : make_a_map(&m2, a1, n_rows, k1, ld_a1, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (st_ != DCGC_OK) { if (own_img) cudaFreeAsync(own_img, st); return st_; }
+      if (nt == 3) tc_gemm_kernel_v5<3><<<grid, V5_THREADS, V5Cfg<3>::kSmemBytes, st>>>(q3, m1, m2);
+      else tc_gemm_kernel_v5<1><<<grid, V5_THREADS, V5Cfg<1>::kSmemBytes, st>>>(q3, m1, m2);
     }
     const cudaError_t launch_err = cudaGetLastError();
     if (own_img) cudaFreeAsync(own_img, st);
@@ -1410,12 +2050,28 @@ int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p_in, int chunks, cudaStre
   if (st_ != DCGC_OK) return st_;
   DcgcWgradArgs p = p_in;
   p.dbg = g_timeline;
+  static const int wg_knob = [] { const char* e = getenv("DCGC_WG2_KNOB"); return e ? atoi(e) : 0; }();
+  p.knob = wg_knob;
   const int Kt = p.k1 + p.k2;
   const int mt = Kt > TC_BM ? 2 : 1;
   p.tiles_n = (p.n + TC_BN - 1) / TC_BN;
   const int m_pairs = (Kt + mt * TC_BM - 1) / (mt * TC_BM);
   dim3 grid((unsigned)chunks, (unsigned)(m_pairs * p.tiles_n));
   // NT = 3: 2 stages x (hi, lo) x (mt + 1) tiles; NT = 1: 4 stages x (mt + 1) tiles — the same bytes
+  // DCGC_WGRAD_V1=1: the first kernel (features as M, N = 128), kept for A/B measurements
+  static const bool use_v1 = [] { const char* e = getenv("DCGC_WGRAD_V1"); return e && e[0] == '1'; }();
+  if (!use_v1) {
+    const int smem2 = WG2_B_STAGES * (nt == 3 ? 2 : 1) * mt * TC_TILE_BYTES + 1024 + 256;
+    if (nt == 3) {
+      if (mt == 2) tc_wgrad_kernel_v2<2, 3><<<grid, WG2_THREADS, smem2, st>>>(p);
+      else tc_wgrad_kernel_v2<1, 3><<<grid, WG2_THREADS, smem2, st>>>(p);
+    } else {
+      if (mt == 2) tc_wgrad_kernel_v2<2, 1><<<grid, WG2_THREADS, smem2, st>>>(p);
+      else tc_wgrad_kernel_v2<1, 1><<<grid, WG2_THREADS, smem2, st>>>(p);
+    }
+    DCGC_CUDA_LAUNCH_CHECK("tc_wgrad_kernel_v2");
+    return DCGC_OK;
+  }
   const int smem = 4 * (mt + 1) * TC_TILE_BYTES + 1024 + 256 + EPI_BYTES;
   if (nt == 3) {
     if (mt == 2) tc_wgrad_kernel<2, 3><<<grid, WG_THREADS, smem, st>>>(p);
@@ -1433,3 +2089,13 @@ int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p_in, int chunks, cudaStre
 //   [0..1023] producer group 0 commit times, [1024..] group 1, [2048..] weight copies issued,
 //   [3072..] MMA issuer saw the chunk, [4096+2t, 4097+2t] epilogue start / end of tile t, [5000] kernel start
 extern "C" void dcgcdbg_tc_timeline(long long* dev_buf) { g_timeline = dev_buf; }
+
+// Debugging aid: cycles for `reps` back-to-back tcgen05.mma of `variant` (see mma_rate_kernel) on `ctas` CTAs;
+// out_dev receives one int64 per CTA.
+extern "C" int dcgcdbg_mma_rate(int variant, int reps, int ctas, long long* out_dev, void* stream) {
+  const int smem = 196608 + 1024 + 64;
+  DCGC_CUDA_CALL(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mma_rate_kernel<<<ctas, 128, smem, (cudaStream_t)stream>>>(variant, reps, out_dev);
+  DCGC_CUDA_LAUNCH_CHECK("mma_rate_kernel");
+  return DCGC_OK;
+}

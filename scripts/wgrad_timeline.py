@@ -13,7 +13,7 @@ L.dcgcdbg_tc_timeline.argtypes = [ctypes.c_void_p]; L.dcgcdbg_tc_timeline.restyp
 for mode, name in ((_lib.GEMM_TF32X3, "tf32x3"), (_lib.GEMM_BF16, "bf16")):
     for _ in range(3):
         ops.group_gemm_wgrad(x, s, g, topo, 11, mode)
-    buf = torch.zeros(6000, dtype=torch.int64, device=dev)
+    buf = torch.zeros(8192, dtype=torch.int64, device=dev)
     L.dcgcdbg_tc_timeline(ctypes.c_void_p(buf.data_ptr()))
     ops.group_gemm_wgrad(x, s, g, topo, 11, mode)
     torch.cuda.synchronize()
@@ -23,7 +23,18 @@ for mode, name in ((_lib.GEMM_TF32X3, "tf32x3"), (_lib.GEMM_BF16, "bf16")):
     print("== %s: %d chunks of 32 atoms on CTA 0 (cycles from kernel start)" % (name, steps))
     print("producer commits:", (t[0:steps] - t0).tolist())
     print("mma saw chunk   :", (t[3072:3072 + steps] - t0).tolist())
+    if t[1024] > 0:
+        print("producer enters store:", (t[1024:1024 + steps] - t0).tolist())
+        print("G loader commits     :", (t[2048:2048 + steps] - t0).tolist())
     print("epilogue: entered %d, accumulators ready %d, stores done %d" % (t[4096] - t0, t[4097] - t0, t[4098] - t0))
+    gv = t[6000:6000 + 4 * 512].reshape(512, 4)
+    gv = gv[gv[:, 0] > 0]
+    if len(gv):
+        st, en = gv[:, 0] - gv[:, 0].min(), gv[:, 1] - gv[:, 0].min()
+        print("whole grid (%d CTAs): start ns min/median/max %d/%d/%d, end ns min/median/max %d/%d/%d; chunks min/max %d/%d" % (
+            len(gv), st.min(), np.median(st), st.max(), en.min(), np.median(en), en.max(), gv[:, 2].min(), gv[:, 2].max()))
+        dur = (gv[:, 1] - gv[:, 0]) / np.maximum(gv[:, 2], 1)
+        print("  ns per chunk over CTAs: min %.0f median %.0f max %.0f; CTAs with < 20 chunks: %d" % (dur.min(), np.median(dur), dur.max(), int((gv[:, 2] < 20).sum())))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
