@@ -66,6 +66,7 @@ struct DcgcWgradArgs {
   long long* dbg;   // optional timeline buffer (dcgcdbg_tc_timeline)
   int knob;         // measurement switches of tc_wgrad_kernel_v2 (env DCGC_WG2_KNOB), 0 in production
 };
+struct DcgcBnFin;
 // Explicit per-call options of the tensor-core GEMMs (no thread-local side channels):
 //   img      a weight image built ahead with dcgc_tc_prep_weights (e.g. on another stream); null = the call builds
 //            its own in a stream-ordered scratch allocation (cudaMallocAsync / cudaFreeAsync on the launch stream)
@@ -75,7 +76,15 @@ struct DcgcWgradArgs {
 struct DcgcGemmOpts {
   const float* img = nullptr;
   int a_exact = 0;
+  const DcgcBnFin* fin = nullptr;   // BatchNorm finalize by the last CTA (only with the fused column statistics)
 };
+int dcgc_gather_bwd_stats(const float* dout, int64_t ld_dout, const float* out, int64_t ld_out, const int32_t* argrow,
+                          const int32_t* membership, int64_t n_rows, int32_t width, int32_t act, float* dx,
+                          int64_t ld_dx, const float* z, int64_t ld_z, int max_chunks, double* part,
+                          int32_t* n_chunks_out, const DcgcBnFin* fin, void* stream);
+int dcgc_mg_pool_bwd_stats_fin(const float* dy, int64_t ld_dy, const uint8_t* arg, int64_t ld_arg, const dcgc_topology* t,
+                               int32_t width, float* dx, int64_t ld_dx, const float* y, int64_t ld_y, const float* stats,
+                               double* part, int32_t* n_chunks, const DcgcBnFin* fin, void* stream);
 int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p, int chunks, cudaStream_t st);
 int dcgc_tc_wgrad_grid_y(int k_total, int n);
 int dcgc_tc_num_sms();
@@ -103,7 +112,7 @@ int dcgc_linear_dgrad_opts(int32_t mode, const float* g, int64_t ld_g, int32_t n
 int dcgc_group_gemm_wgrad_opts(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2, int64_t ld_a2,
                                int32_t k2, const float* g, int64_t ld_g, int32_t n, const int64_t* deg_count,
                                int32_t n_groups, float* dw, float* dbias, void* workspace, int64_t workspace_bytes,
-                               int a_exact, void* stream);
+                               int a_exact, void* stream, float* dbias21 = nullptr);
 #endif
 
 #ifdef __CUDACC__
@@ -129,6 +138,110 @@ __device__ __forceinline__ void dcgc_mbar_wait(uint32_t bar, uint32_t parity) {
       else if (now - t0 > 20000000000ull) __trap();
     }
   }
+}
+#endif
+
+#ifdef __CUDACC__
+// ---- BatchNorm finalize by the LAST CTA of the kernel that produced the column-sum partials ---------------------------
+// The kernels that emit per-CTA partial sums (GEMM epilogue: sum y, sum y^2; GraphPool / GraphGather backward: sum dA,
+// sum dA y) used to be followed by a one-block-per-16-columns finalize kernel: 4.5-5.6 us each, eight per training
+// step, nothing but launch and memory latency.  With a DcgcBnFin the CTAs count themselves on `counter` after their
+// partials are written (threadfence + atomic: the classic last-block pattern); the last one adds the partial rows in
+// ROW ORDER (deterministic, whichever CTA it is) and writes what the finalize kernel wrote.  counter must be zero at
+// launch; the last CTA resets it.  kind 0 = off.
+struct DcgcBnFin {
+  unsigned int* counter;
+  int kind;                 // 1: forward statistics -> mean / invstd / scale / shift + running statistics
+                            // 2: backward sums -> dgamma / dbeta + the three coefficients of the apply pass
+  int width;
+  long long n_rows;
+  const double* part;       // [chunks][2][width]
+  const float* gamma; const float* beta; float eps, momentum; float* running_mean; float* running_var;
+  float* mean_out; float* invstd_out; float* scale_out; float* shift_out;
+  const float* mean; const float* invstd; const float* scale; float* dgamma; float* dbeta; float* coef;
+};
+// Called by every thread of the group that wrote the partials (t = 0 .. n - 1 inside named barrier `bar`), after the
+// writes; n_chunks = partial rows, n_ctas = CTAs of the grid that make this call; scratch = shared memory the group no
+// longer needs, at least 2 * (n / width) * width doubles (n >= width).
+// The last CTA pulls the whole partial table (chunks x 2 x width doubles, 300 KB at the bench shape) through ONE SM,
+// so the loads must be spread over every thread and kept 32 deep: thread t owns column t % width and the
+// (t / width)-th slice of the rows; the slices are then added in slice order.  (A first version with one thread per
+// column and 16 loads in flight needed ~9 us — more than the finalize kernel it replaced.)
+__device__ __forceinline__ void dcgc_bn_fin_last_cta(const DcgcBnFin& f, int n_chunks, unsigned n_ctas, int bar, int n, int t,
+                                                     double* scratch) {
+  if (f.kind == 0) return;
+  __shared__ int last_flag;
+  __threadfence();
+  asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory");
+  if (t == 0) last_flag = atomicAdd(f.counter, 1u) == n_ctas - 1u;
+  asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory");
+  if (!last_flag) return;
+  __threadfence();
+  const int slices = n / f.width;
+  const int per = (n_chunks + slices - 1) / slices;
+  if (t < slices * f.width) {
+    const int c = t % f.width, sl = t / f.width;
+    const int k0 = sl * per, k1 = min(n_chunks, k0 + per);
+    double a = 0.0, b = 0.0;
+    int k = k0;
+    for (; k + 16 <= k1; k += 16) {
+      double va[16], vb[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        va[u] = __ldcg(f.part + ((size_t)(k + u) * 2) * f.width + c);
+        vb[u] = __ldcg(f.part + ((size_t)(k + u) * 2 + 1) * f.width + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) { a += va[u]; b += vb[u]; }
+    }
+    {
+      double va[16], vb[16];                   // the ragged tail, still one round of loads
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        va[u] = k + u < k1 ? __ldcg(f.part + ((size_t)(k + u) * 2) * f.width + c) : 0.0;
+        vb[u] = k + u < k1 ? __ldcg(f.part + ((size_t)(k + u) * 2 + 1) * f.width + c) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) { a += va[u]; b += vb[u]; }
+    }
+    scratch[(size_t)(2 * sl) * f.width + c] = a;
+    scratch[(size_t)(2 * sl + 1) * f.width + c] = b;
+  }
+  asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(n) : "memory");
+  const double rows = (double)f.n_rows;
+  for (int c = t; c < f.width; c += n) {
+    double a = 0.0, b = 0.0;
+    for (int sl = 0; sl < slices; ++sl) {
+      a += scratch[(size_t)(2 * sl) * f.width + c];
+      b += scratch[(size_t)(2 * sl + 1) * f.width + c];
+    }
+    if (f.kind == 1) {
+      // torch semantics (graphconvmodel.py:150-158): normalise with the biased batch variance, running_var unbiased
+      const double mean = rows > 0 ? a / rows : 0.0;
+      double var = rows > 0 ? b / rows - mean * mean : 0.0;
+      if (var < 0) var = 0;
+      const double invstd = 1.0 / sqrt(var + (double)f.eps);
+      const float g = f.gamma ? f.gamma[c] : 1.f, be = f.beta ? f.beta[c] : 0.f;
+      const float sc = (float)(g * invstd);
+      f.mean_out[c] = (float)mean;
+      f.invstd_out[c] = (float)invstd;
+      f.scale_out[c] = sc;
+      f.shift_out[c] = (float)(be - mean * (double)sc);
+      if (f.running_mean) {
+        const double unbiased = rows > 1 ? var * rows / (rows - 1.0) : var;
+        f.running_mean[c] = (float)((1.0 - f.momentum) * f.running_mean[c] + f.momentum * mean);
+        f.running_var[c] = (float)((1.0 - f.momentum) * f.running_var[c] + f.momentum * unbiased);
+      }
+    } else {
+      const double dg = (double)f.invstd[c] * (b - (double)f.mean[c] * a);      // sum dA * xhat
+      if (f.dgamma) f.dgamma[c] = (float)dg;
+      if (f.dbeta) f.dbeta[c] = (float)a;
+      f.coef[c] = f.scale[c];
+      f.coef[f.width + c] = rows > 0 ? (float)(a / rows) : 0.f;
+      f.coef[2 * f.width + c] = rows > 0 ? (float)(dg / rows) : 0.f;
+    }
+  }
+  if (t == 0) *f.counter = 0u;
 }
 #endif
 

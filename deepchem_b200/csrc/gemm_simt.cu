@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(NT, 2) wgrad_kernel(const WgradArgs p) {
 struct ReduceArgs {
   const float* ws; const float* wsb;
   float* dw; float* dbias;
+  float* dbias21;  // optional: the same sums scattered to GraphConv's 21 bias rows (row 20 <- group 0, rows 2(g-1), 2(g-1)+1 <- group g)
   int64_t kn;  // (k1+k2)*n
   int n, n_groups;
   int transpose;  // write dw[g][j][k] instead of dw[g][k][j] (nn.Linear weight layout)
@@ -358,6 +359,14 @@ __global__ void __launch_bounds__(NT) wgrad_reduce_kernel(const ReduceArgs p) {
     const int64_t j = idx - p.kn;
     for (int c = c0; c < c1; ++c) s += __ldg(p.wsb + (int64_t)c * p.n + j);
     p.dbias[(int64_t)g * p.n + j] = s;
+    if (p.dbias21) {
+      if (g == 0) {
+        p.dbias21[(int64_t)20 * p.n + j] = s;
+      } else {
+        p.dbias21[(int64_t)(2 * (g - 1)) * p.n + j] = s;
+        p.dbias21[(int64_t)(2 * (g - 1) + 1) * p.n + j] = s;
+      }
+    }
   }
 }
 
@@ -509,7 +518,8 @@ extern "C" int64_t dcgc_group_gemm_wgrad_workspace(int32_t k1, int32_t k2, int32
 static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2,
                       int64_t ld_a2, int32_t k2, const float* g, int64_t ld_g, int32_t n,
                       const int64_t* deg_count, int32_t n_groups, float* dw, float* dbias,
-                      void* workspace, int64_t workspace_bytes, int transpose, void* stream, int a_exact = 0) {
+                      void* workspace, int64_t workspace_bytes, int transpose, void* stream, int a_exact = 0,
+                      float* dbias21 = nullptr) {
   DCGC_CHECK_ARG(mode == DCGC_GEMM_FP32 || dcgc_tc_terms(mode) != 0,
                  "dcgc_group_gemm_wgrad: GEMM mode %d is not available in this build", mode);
   DCGC_CHECK_ARG(k1 >= 0 && k2 >= 0 && n >= 0 && ld_a1 >= k1 && ld_g >= n, "dcgc_group_gemm_wgrad: bad sizes");
@@ -592,6 +602,7 @@ static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, 
   }
   q.ws = p.ws; q.wsb = p.wsb; q.dw = dw; q.dbias = dbias; q.kn = kn; q.n = n; q.n_groups = n_groups;
   q.transpose = transpose;
+  q.dbias21 = (dbias && n_groups == DCGC_N_DEG) ? dbias21 : nullptr;
   dim3 rgrid((unsigned)((kn + n + NT - 1) / NT), (unsigned)n_groups);
   wgrad_reduce_kernel<<<rgrid, NT, 0, st>>>(q);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_group_gemm_wgrad (stage 2)");
@@ -608,9 +619,9 @@ extern "C" int dcgc_group_gemm_wgrad(int32_t mode, const float* a1, int64_t ld_a
 int dcgc_group_gemm_wgrad_opts(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2, int64_t ld_a2,
                                int32_t k2, const float* g, int64_t ld_g, int32_t n, const int64_t* deg_count,
                                int32_t n_groups, float* dw, float* dbias, void* workspace, int64_t workspace_bytes,
-                               int a_exact, void* stream) {
+                               int a_exact, void* stream, float* dbias21) {
   return wgrad_impl(mode, a1, ld_a1, k1, a2, ld_a2, k2, g, ld_g, n, deg_count, n_groups, dw, dbias, workspace,
-                    workspace_bytes, 0, stream, a_exact);
+                    workspace_bytes, 0, stream, a_exact, dbias21);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -261,6 +261,7 @@ struct TcArgs3 {
   long long* dbg;  // optional timeline buffer (dcgcdbg_tc_timeline): CTA (0,0) records clock64() per role and chunk
   int a_exact;    // v4: every A value is exactly representable in tf32 (integer-valued features and their neighbour
                   // sums): the lo(A) tile is identically zero, its stores and the lo(A)*hi(W) MMA are skipped
+  DcgcBnFin bnfin; // v4 / v5 with column statistics: BatchNorm finalize by the last CTA (kind 0 = off)
   int knockout;   // debugging aid (env DCGC_TC_KNOCKOUT): 1 no output stores, 2 no MMAs, 4 no A loads,
                   // 8 no weight copies, 16 no A shared-memory stores, 32 no TMEM loads, 64 no proxy fence,
                   // 128 no weight-image kernel — results are wrong, timing only
@@ -776,6 +777,7 @@ __device__ __forceinline__ void ts_epilogue(const TcArgs3& q, uint32_t tmem, uin
         if (c < N) p.stats[((int64_t)pid * 2 + qn) * N + c] = t;
       }
     }
+    dcgc_bn_fin_last_cta(q.bnfin, (int)gridDim.x, gridDim.x * gridDim.y, 2, 256, tid, shd);
   }
 }
 
@@ -1994,6 +1996,7 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
     q3.img = img; q3.n_row_tiles = (int)row_tiles; q3.n_tiles_n = n_tiles_n;
     q3.knockout = knockout;
     q3.a_exact = (opts && opts->a_exact && nt == 3) ? 1 : 0;
+    if (opts && opts->fin && stats && opts->fin->width <= 256) q3.bnfin = *opts->fin;   // (needs one thread per column)
     q3.dbg = g_timeline;
     int ctas = g_num_sms / n_tiles_n;
     if (ctas < 1) ctas = 1;
@@ -2006,6 +2009,7 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
     static const bool use_v4 = [] { const char* e = getenv("DCGC_TC_V4"); return e && e[0] == '1'; }();
     if (use_v3) {
       q3.a_exact = 0;
+      if (q3.bnfin.kind != 0) { dcgc_set_error("DCGC_TC_V3: the last-CTA BatchNorm finalize needs the v4 / v5 kernels"); return DCGC_ERR_INVALID; }
       if (nt == 3) tc_gemm_kernel_v3<3><<<grid, V3_THREADS, V3Cfg<3>::kSmemBytes, st>>>(q3);
       else tc_gemm_kernel_v3<1><<<grid, V3_THREADS, V3Cfg<1>::kSmemBytes, st>>>(q3);
     } else if (use_v4 || !p3.a1_vec || (a2 && !p3.a2_vec) || n_rows >= (1ll << 31)) {

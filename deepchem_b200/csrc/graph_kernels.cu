@@ -382,6 +382,76 @@ gather_bwd_vec_kernel(const float* __restrict__ dout, int64_t ld_dout, const flo
   *reinterpret_cast<float4*>(dx + row * ld_dx + c) = o;
 }
 
+// GraphGather backward with the BatchNorm-backward column sums of its result fused in: besides dx it emits, per block,
+// sum_r dx[r, c] and sum_r dx[r, c] * z[r, c] (z = the BatchNorm input of the same rows) — what a separate
+// two-tensor pass over dx and z (col_moments_partial: 2 x N x width x 4 bytes, 25 us at the bench shape) computed.
+// Block = 32 column lanes (float4 -> 128 columns) x 16 row lanes; a block walks a contiguous row range with four rows
+// in flight per thread (the one-row-per-thread kernel above sits at 0.35 of the HBM peak: five dependent loads and
+// no second row to overlap them with).  fp32 partial sums over four rows, float64 from there on, the 16 row lanes
+// combined in lane order through shared memory: deterministic.  part: [blocks][2][width] doubles.
+constexpr int kGbRowLanes = 16;
+__global__ void __launch_bounds__(32 * kGbRowLanes, 2)
+gather_bwd_stats_kernel(const float* __restrict__ dout, int64_t ld_dout, const float* __restrict__ out, int64_t ld_out,
+                        const int32_t* __restrict__ argrow, const int32_t* __restrict__ membership, int64_t n_rows,
+                        int width, int act, float* __restrict__ dx, int64_t ld_dx, const float* __restrict__ z,
+                        int64_t ld_z, int64_t rows_per_chunk, double* __restrict__ part, const DcgcBnFin bnfin) {
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.y * 128 + 4 * cx;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
+  const int64_t r1 = min(n_rows, r0 + rows_per_chunk);
+  double da[4] = {0, 0, 0, 0}, dab[4] = {0, 0, 0, 0};
+  if (c < width) {
+    for (int64_t rb = r0 + ry; rb < r1; rb += 4 * kGbRowLanes) {
+      int64_t g[4];
+      float4 zv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t r = rb + (int64_t)u * kGbRowLanes;
+        g[u] = r < r1 ? (int64_t)__ldg(membership + r) : -1;
+        zv[u] = r < r1 ? ldg4(z + r * ld_z + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float4 o[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        o[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g[u] < 0) continue;
+        const int r32 = (int)(rb + (int64_t)u * kGbRowLanes);
+        const float4 ds = ldg4(dout + g[u] * ld_dout + c), os = ldg4(out + g[u] * ld_out + c);
+        const float4 dm = ldg4(dout + g[u] * ld_dout + width + c), om = ldg4(out + g[u] * ld_out + width + c);
+        const int4 ar = __ldg(reinterpret_cast<const int4*>(argrow + g[u] * (int64_t)width + c));
+        o[u].x = ds.x * act_grad_from_out(os.x, act) + (ar.x == r32 ? dm.x * act_grad_from_out(om.x, act) : 0.f);
+        o[u].y = ds.y * act_grad_from_out(os.y, act) + (ar.y == r32 ? dm.y * act_grad_from_out(om.y, act) : 0.f);
+        o[u].z = ds.z * act_grad_from_out(os.z, act) + (ar.z == r32 ? dm.z * act_grad_from_out(om.z, act) : 0.f);
+        o[u].w = ds.w * act_grad_from_out(os.w, act) + (ar.w == r32 ? dm.w * act_grad_from_out(om.w, act) : 0.f);
+        *reinterpret_cast<float4*>(dx + (int64_t)r32 * ld_dx + c) = o[u];
+      }
+      float sa[4] = {0, 0, 0, 0}, sab[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        sa[0] += o[u].x; sa[1] += o[u].y; sa[2] += o[u].z; sa[3] += o[u].w;
+        sab[0] = fmaf(o[u].x, zv[u].x, sab[0]); sab[1] = fmaf(o[u].y, zv[u].y, sab[1]);
+        sab[2] = fmaf(o[u].z, zv[u].z, sab[2]); sab[3] = fmaf(o[u].w, zv[u].w, sab[3]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { da[e] += sa[e]; dab[e] += sab[e]; }
+    }
+  }
+  __shared__ double sh[2][kGbRowLanes][128];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { sh[0][ry][4 * cx + e] = da[e]; sh[1][ry][4 * cx + e] = dab[e]; }
+  __syncthreads();
+  if (threadIdx.x < 256) {
+    const int q = threadIdx.x >> 7, col = threadIdx.x & 127;
+    double s = 0.0;
+#pragma unroll
+    for (int l = 0; l < kGbRowLanes; ++l) s += sh[q][l][col];
+    const int cc = blockIdx.y * 128 + col;
+    if (cc < width) part[((int64_t)blockIdx.x * 2 + q) * width + cc] = s;
+  }
+  __syncthreads();                                                     // sh is free again
+  dcgc_bn_fin_last_cta(bnfin, (int)gridDim.x, gridDim.x * gridDim.y, 0, 32 * kGbRowLanes, (int)threadIdx.x, &sh[0][0][0]);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -586,5 +656,33 @@ extern "C" int dcgc_gather_bwd(const float* dout, int64_t ld_dout, const float* 
     gather_bwd_kernel<4><<<grid_for(n_rows * groups), kThreads, 0, (cudaStream_t)stream>>>(
         dout, ld_dout, out, ld_out, argrow, membership, n_rows, groups, width, act, dx, ld_dx);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_gather_bwd");
+  return DCGC_OK;
+}
+
+// Fused-engine variant of dcgc_gather_bwd (declared in common.h, not part of the ABI): also writes the
+// BatchNorm-backward column sums of dx against z, one row of partials per block; *n_chunks_out = rows written.
+// Needs 16-byte aligned rows; returns DCGC_ERR_INVALID otherwise (the caller then takes the two-pass route).
+int dcgc_gather_bwd_stats(const float* dout, int64_t ld_dout, const float* out, int64_t ld_out, const int32_t* argrow,
+                          const int32_t* membership, int64_t n_rows, int32_t width, int32_t act, float* dx,
+                          int64_t ld_dx, const float* z, int64_t ld_z, int max_chunks, double* part,
+                          int32_t* n_chunks_out, const DcgcBnFin* fin, void* stream) {
+  DCGC_CHECK_ARG(n_rows > 0 && width > 0 && dout && out && argrow && membership && dx && z && part && n_chunks_out,
+                 "dcgc_gather_bwd_stats: bad arguments");
+  DCGC_CHECK_ARG(width % 4 == 0 && ld_dout % 4 == 0 && ld_out % 4 == 0 && ld_dx % 4 == 0 && ld_z % 4 == 0 &&
+                     aligned16(dout) && aligned16(out) && aligned16(dx) && aligned16(argrow) && aligned16(z),
+                 "dcgc_gather_bwd_stats: rows must be 16-byte aligned");
+  DcgcProfScope prof_scope("dcgc_gather_bwd", (cudaStream_t)stream);
+  int64_t chunks = (n_rows + 127) / 128;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  int64_t rows = (n_rows + chunks - 1) / chunks;
+  rows = (rows + kGbRowLanes - 1) / kGbRowLanes * kGbRowLanes;
+  chunks = (n_rows + rows - 1) / rows;
+  dim3 grid((unsigned)chunks, (unsigned)((width + 127) / 128));
+  gather_bwd_stats_kernel<<<grid, 32 * kGbRowLanes, 0, (cudaStream_t)stream>>>(
+      dout, ld_dout, out, ld_out, argrow, membership, n_rows, width, act, dx, ld_dx, z, ld_z, rows, part,
+      fin ? *fin : DcgcBnFin{});
+  DCGC_CUDA_LAUNCH_CHECK("dcgc_gather_bwd_stats");
+  *n_chunks_out = (int32_t)chunks;
   return DCGC_OK;
 }

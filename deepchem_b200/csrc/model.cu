@@ -259,21 +259,16 @@ relu_bwd_apply(const float* da, int64_t ld_da, const float* __restrict__ y, int6
 // ------------------------------------------------------------------------------------------
 // GraphConv bias packing: reference order b[0..20] (layers.py:6189-6226) <-> per-degree sums
 // ------------------------------------------------------------------------------------------
-__global__ void conv_bias_pack(const float* __restrict__ b21, int c_out, float* __restrict__ b11) {
+struct BiasPackAll { const float* b21[DCGC_MODEL_MAX_LAYERS]; float* b11[DCGC_MODEL_MAX_LAYERS]; int c[DCGC_MODEL_MAX_LAYERS]; };
+// every conv layer of the model in one launch (blockIdx.y = layer)
+__global__ void conv_bias_pack_all(const BiasPackAll a) {
+  const int l = blockIdx.y, c_out = a.c[l];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= DCGC_N_DEG * c_out) return;
   const int d = i / c_out, c = i - d * c_out;
-  b11[i] = d == 0 ? b21[20 * c_out + c]
-                  : b21[(2 * (d - 1)) * c_out + c] + b21[(2 * (d - 1) + 1) * c_out + c];
+  const float* b21 = a.b21[l];
+  a.b11[l][i] = d == 0 ? b21[20 * c_out + c] : b21[(2 * (d - 1)) * c_out + c] + b21[(2 * (d - 1) + 1) * c_out + c];
 }
-__global__ void conv_bias_unpack(const float* __restrict__ db11, int c_out, float* __restrict__ db21) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 21 * c_out) return;
-  const int k = i / c_out, c = i - k * c_out;
-  const int d = k == 20 ? 0 : k / 2 + 1;
-  db21[i] = db11[d * c_out + c];
-}
-
 // ------------------------------------------------------------------------------------------
 // head: out[b,t] = fp[b,:] . Wh[t,:] + bh[t]   (one warp per output element)
 // ------------------------------------------------------------------------------------------
@@ -392,6 +387,171 @@ head_bwd_input(const float* __restrict__ dout, const float* __restrict__ wh, int
 }
 
 // ------------------------------------------------------------------------------------------
+// Fused head for small output widths (n_out <= 32): output layer, loss, d(out), d(fingerprint) and the per-block
+// partials of dWh / dbh / loss in ONE kernel over blocks of 32 samples, then one small kernel that adds the partials
+// in block order.  Replaces head_fwd + loss_fwd_bwd + loss_reduce + head_bwd_partial + head_bwd_final +
+// head_bwd_input (six dependent launches, 38 us of a 1.2 ms step in the ncu launch list, none of them with more than
+// a few hundred microseconds of bandwidth-bound work).  The block keeps its 32 fingerprint rows and the whole Wh in
+// shared memory; rows are padded by one float so that threads walking different samples hit different banks.
+// ------------------------------------------------------------------------------------------
+constexpr int kHfRows = 32;
+__global__ void __launch_bounds__(kT)
+head_fused_kernel(const float* __restrict__ fp, int64_t ld_fp, const float* __restrict__ wh, const float* __restrict__ bh,
+                  const float* __restrict__ y, const float* __restrict__ w, int64_t n_samples, int64_t n_seg, int k,
+                  int n_out, int n_classes, int mode, int64_t n_elems, float* __restrict__ out, float* __restrict__ dfp,
+                  float* __restrict__ part /* [blocks][n_out][k + 1] */, double* __restrict__ loss_part /* [blocks] */) {
+  extern __shared__ float hsm[];
+  const int kp = k + 1;
+  float* fp_s = hsm;                          // [32][k + 1]
+  float* wh_s = fp_s + kHfRows * kp;          // [n_out][k]
+  float* out_s = wh_s + n_out * k;            // [32][n_out]
+  float* dout_s = out_s + kHfRows * n_out;    // [32][n_out]
+  float* le_s = dout_s + kHfRows * n_out;     // [32][per_row] per-element losses
+  const int per_row = mode == 1 ? n_out / n_classes : n_out;
+  const int64_t b0 = (int64_t)blockIdx.x * kHfRows;
+  const int tid = threadIdx.x;
+  // staging: eight independent loads in flight per thread (a load -> store loop left to the compiler ran one L2 round
+  // trip per iteration: 17 us for this kernel in the first version)
+  for (int i0 = tid; i0 < n_out * k; i0 += 8 * kT) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = i0 + u * kT < n_out * k ? __ldg(wh + i0 + u * kT) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (i0 + u * kT < n_out * k) wh_s[i0 + u * kT] = v[u];
+  }
+  for (int j = tid; j < k; j += kT) {
+    for (int base = 0; base < kHfRows; base += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = b0 + base + u < n_samples ? __ldg(fp + (b0 + base + u) * ld_fp + j) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) fp_s[(base + u) * kp + j] = v[u];
+    }
+  }
+  __syncthreads();
+  // ---- output layer.  Few outputs: one WARP per (sample, output), lanes over the fingerprint; many: one thread each
+  if (kHfRows * n_out <= kT) {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int task = warp; task < kHfRows * n_out; task += kT / 32) {
+      const int bl = task & (kHfRows - 1), t = task >> 5;
+      float acc = 0.f;
+      for (int j = lane; j < k; j += 32) acc = fmaf(fp_s[bl * kp + j], wh_s[t * k + j], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) {
+        acc += bh ? __ldg(bh + t) : 0.f;
+        out_s[bl * n_out + t] = acc;
+        dout_s[bl * n_out + t] = 0.f;
+        if (b0 + bl < n_samples) out[(b0 + bl) * n_out + t] = acc;
+      }
+    }
+  } else {
+    for (int task = tid; task < kHfRows * n_out; task += kT) {
+      const int bl = task & (kHfRows - 1), t = task >> 5;
+      const float* fr = fp_s + bl * kp;
+      const float* wr = wh_s + t * k;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // four independent chains
+      int j = 0;
+      for (; j + 4 <= k; j += 4) {
+        a0 = fmaf(fr[j], wr[j], a0); a1 = fmaf(fr[j + 1], wr[j + 1], a1);
+        a2 = fmaf(fr[j + 2], wr[j + 2], a2); a3 = fmaf(fr[j + 3], wr[j + 3], a3);
+      }
+      for (; j < k; ++j) a0 = fmaf(fr[j], wr[j], a0);
+      float acc = (a0 + a1) + (a2 + a3);
+      acc += bh ? __ldg(bh + t) : 0.f;
+      out_s[bl * n_out + t] = acc;
+      dout_s[bl * n_out + t] = 0.f;
+      if (b0 + bl < n_samples) out[(b0 + bl) * n_out + t] = acc;
+    }
+  }
+  __syncthreads();
+  // ---- loss and d(out) per (sample, loss element); torch_model.py:1275-1294, losses.py:76-94 / 236-259
+  const float inv = 1.f / (float)n_elems;
+  for (int task = tid; task < kHfRows * per_row; task += kT) {
+    const int bl = task / per_row, te = task - bl * per_row;
+    float l = 0.f;
+    if (b0 + bl < n_samples) {
+      const int64_t i = (b0 + bl) * per_row + te;
+      const float wi = w ? __ldg(w + i) : 1.f;
+      if (mode == 0) {
+        const float d = out_s[bl * n_out + te] - __ldg(y + i);
+        l = wi * d * d;
+        dout_s[bl * n_out + te] = 2.f * wi * d * inv;
+      } else {
+        const float* lg = out_s + bl * n_out + te * n_classes;
+        const float* yy = y + i * n_classes;
+        float mx = -INFINITY;
+        for (int c = 0; c < n_classes; ++c) mx = fmaxf(mx, lg[c]);
+        float se = 0.f, sy = 0.f;
+        for (int c = 0; c < n_classes; ++c) { se += expf(lg[c] - mx); sy += __ldg(yy + c); }
+        const float lse = mx + logf(se);
+        for (int c = 0; c < n_classes; ++c) {
+          const float logp = lg[c] - lse, yc = __ldg(yy + c);
+          l -= yc * logp;
+          dout_s[bl * n_out + te * n_classes + c] = wi * inv * (expf(logp) * sy - yc);
+        }
+        l *= wi;
+      }
+    }
+    le_s[task] = l;
+  }
+  __syncthreads();
+  // ---- d(fingerprint) rows (zero for the padded segments) and this block's partial dWh / dbh
+  for (int j = tid; j < k; j += kT) {
+    for (int bl = 0; bl < kHfRows; ++bl) {
+      if (b0 + bl >= n_seg) break;
+      float acc = 0.f;
+      for (int t = 0; t < n_out; ++t) acc = fmaf(dout_s[bl * n_out + t], wh_s[t * k + j], acc);
+      dfp[(b0 + bl) * k + j] = acc;
+    }
+    for (int t = 0; t < n_out; ++t) {
+      float acc = 0.f;
+      for (int bl = 0; bl < kHfRows; ++bl) acc = fmaf(dout_s[bl * n_out + t], fp_s[bl * kp + j], acc);
+      part[((int64_t)blockIdx.x * n_out + t) * kp + j] = acc;
+    }
+  }
+  if (tid < n_out) {
+    float acc = 0.f;
+    for (int bl = 0; bl < kHfRows; ++bl) acc += dout_s[bl * n_out + tid];
+    part[((int64_t)blockIdx.x * n_out + tid) * kp + k] = acc;
+  }
+  if (tid == 0) {
+    double acc = 0.0;
+    for (int i = 0; i < kHfRows * per_row; ++i) acc += (double)le_s[i];
+    loss_part[blockIdx.x] = acc;
+  }
+}
+// partials -> dWh, dbh and the mean loss.  One WARP per output element: lane l adds the partials of blocks l, l + 32,
+// ... in block order (independent loads: one memory latency, where a single thread per element walked all blocks one
+// dependent round trip after the other) and the 32 lane sums are combined by a fixed shuffle tree: deterministic.
+__global__ void __launch_bounds__(kT)
+head_fused_final(const float* __restrict__ part, const double* __restrict__ loss_part, int n_blocks, int k, int n_out,
+                 int64_t n_elems, float* __restrict__ dwh, float* __restrict__ dbh, float* __restrict__ loss) {
+  const int64_t i = ((int64_t)blockIdx.x * kT + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_el = (int64_t)n_out * (k + 1);
+  if (i < n_el) {
+    float acc = 0.f;
+    for (int c = lane; c < n_blocks; c += 32) acc += __ldg(part + (int64_t)c * n_el + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const int t = (int)(i / (k + 1)), j = (int)(i - (int64_t)t * (k + 1));
+      if (j < k) dwh[(int64_t)t * k + j] = acc;
+      else if (dbh) dbh[t] = acc;
+    }
+  } else if (i == n_el) {
+    double acc = 0.0;
+    for (int c = lane; c < n_blocks; c += 32) acc += loss_part[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) *loss = n_elems > 0 ? (float)(acc / (double)n_elems) : 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Adam on the flat slab (torch.optim.Adam semantics, models/optimizers.py:190-241)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kT)
@@ -406,6 +566,27 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   v[i] = vi;
   const float denom = sqrtf(vi) / bc2_sqrt + eps;
   p[i] -= (lr / bc1) * (mi / denom);
+}
+
+// four parameters per thread (the slab and the optimizer state are 16-byte aligned allocations)
+__global__ void __launch_bounds__(kT)
+adam_kernel_vec(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                int64_t n4, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+  const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
+  if (i >= n4) return;
+  const float4 gv = g[i];
+  float4 mv = m[i], vv = v[i], pv = p[i];
+  const float step = lr / bc1;
+#define DCGC_ADAM1(X)                                           \
+  {                                                             \
+    const float gi = gv.X * grad_scale;                         \
+    mv.X = b1 * mv.X + (1.f - b1) * gi;                         \
+    vv.X = b2 * vv.X + (1.f - b2) * gi * gi;                    \
+    pv.X -= step * (mv.X / (sqrtf(vv.X) / bc2_sqrt + eps));     \
+  }
+  DCGC_ADAM1(x) DCGC_ADAM1(y) DCGC_ADAM1(z) DCGC_ADAM1(w)
+#undef DCGC_ADAM1
+  m[i] = mv; v[i] = vv; p[i] = pv;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -499,6 +680,7 @@ struct Saved {
   const float* img_fwd[DCGC_MODEL_MAX_LAYERS];
   const float* img_dense;
   cudaEvent_t img_fwd_ready;   // main stream waits on it before the first GEMM
+  unsigned int* fin_counters;  // train step: zeroed counters of the last-CTA BatchNorm finalizes (2 per BatchNorm), or null
 };
 
 // ---- early weight images: one side stream + three events per device, created on first use
@@ -548,16 +730,51 @@ static bool use_mg(const dcgc_topology* t, int64_t ld, int64_t ld_arg, const voi
          ((reinterpret_cast<uintptr_t>(p0) | reinterpret_cast<uintptr_t>(p1)) & 15) == 0;
 }
 
+// the fused head (head_fused_kernel) serves small output widths; shared memory: 32 fingerprint rows + Wh + out/dout/loss
+static bool head_fused_ok(const dcgc_gcmodel_config* cfg) {
+  static const bool off = [] { const char* e = getenv("DCGC_NO_FUSED_HEAD"); return e && e[0] == '1'; }();
+  return !off && cfg->n_out <= 32 && 2 * cfg->dense <= 512;
+}
+static size_t head_fused_smem(const dcgc_gcmodel_config* cfg) {
+  const int k = 2 * cfg->dense, T = cfg->n_out;
+  return (size_t)(kHfRows * (k + 1) + T * k + 3 * kHfRows * T) * 4;
+}
+
 #define RET_IF(expr)                \
   do {                              \
     int st__ = (expr);              \
     if (st__ != DCGC_OK) return st__; \
   } while (0)
 
-// fused_chunks >= 0: the stage-1 partials were already written by the GEMM epilogue (dcgc_*_fwd_stats)
+// Measured (profiles/r5p_last_cta_fin.md): at the bench shape (102 k atoms, 148 rows of partials = 300 KB pulled through
+// one SM, plus a threadfence in every CTA's tail) the last-CTA finalize costs 7 us per step MORE than the eight small
+// finalize kernels it replaces; for small batches (a few CTAs, launch-latency-bound steps) it removes eight of ~50
+// launches.  So: on below kLastCtaFinAtoms atoms, off above; DCGC_LAST_CTA_FIN=0 / 1 forces it.
+constexpr int64_t kLastCtaFinAtoms = 16384;
+static bool last_cta_fin_on(int64_t n_atoms) {
+  static const int forced = [] { const char* e = getenv("DCGC_LAST_CTA_FIN"); return e ? (e[0] == '1' ? 1 : 0) : -1; }();
+  return forced >= 0 ? forced == 1 : n_atoms <= kLastCtaFinAtoms;
+}
+// forward finalize of BatchNorm idx by the last CTA of the kernel that writes the statistics partials
+static DcgcBnFin fwd_fin(const dcgc_gcmodel_config* cfg, const Layout& lo, int idx, int width, int64_t n,
+                         const float* params, float* bn_running, const Saved& sv) {
+  DcgcBnFin f{};
+  if (!sv.fin_counters || width > 256) return f;     // (one thread per column in the last CTA)
+  float* stats = sv.stats + sv.stats_off[idx];
+  f.counter = sv.fin_counters + 2 * idx; f.kind = 1; f.width = width; f.n_rows = n; f.part = sv.part;
+  f.gamma = params + lo.bn_g[idx]; f.beta = params + lo.bn_b[idx]; f.eps = cfg->bn_eps; f.momentum = cfg->bn_momentum;
+  f.running_mean = bn_running ? bn_running + lo.bn_mean[idx] : nullptr;
+  f.running_var = bn_running ? bn_running + lo.bn_var[idx] : nullptr;
+  f.mean_out = stats; f.invstd_out = stats + width; f.scale_out = stats + 2 * width; f.shift_out = stats + 3 * width;
+  return f;
+}
+
+// fused_chunks >= 0: the stage-1 partials were already written by the GEMM epilogue (dcgc_*_fwd_stats);
+// finalized: ... and the last CTA of that kernel has already written mean / invstd / scale / shift
 int bn_forward(const dcgc_gcmodel_config* cfg, const Layout& lo, int idx, const float* y, int64_t ld_y, int64_t n,
                int width, const float* params, float* bn_running, int training, Saved& sv, cudaStream_t st,
-               int fused_chunks = -1) {
+               int fused_chunks = -1, bool finalized = false) {
+  if (finalized && training && fused_chunks >= 0) return DCGC_OK;
   float* stats = sv.stats + sv.stats_off[idx];
   float *mean = stats, *invstd = stats + width, *scale = stats + 2 * width, *shift = stats + 3 * width;
   const float* gamma = params + lo.bn_g[idx];
@@ -589,7 +806,7 @@ int bn_forward(const dcgc_gcmodel_config* cfg, const Layout& lo, int idx, const 
 
 int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_topology* t, const float* x,
                  int64_t ld_x, int64_t n_samples, const float* params, float* bn_running, int training,
-                 int keep_arg, Arena& ws, Saved& sv, cudaStream_t st) {
+                 int keep_arg, Arena& ws, Saved& sv, cudaStream_t st, bool skip_head = false) {
   const int L = lo.L, D = cfg->dense;
   const int64_t N = t->n_atoms, S = t->n_segments;
   DCGC_CHECK_ARG(ld_x >= lo.fp[0] || N == 0, "dcgc_gcmodel: x must be zero-padded to a leading dimension >= %d",
@@ -622,12 +839,21 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
     return DCGC_ERR_NOMEM;
   }
   // ---- conv stack
+  {
+    BiasPackAll bp{};
+    int cmax = 0;
+    for (int l = 0; l < L; ++l) {
+      bp.b21[l] = params + lo.conv_b[l]; bp.b11[l] = sv.b11[l]; bp.c[l] = cfg->widths[l];
+      cmax = cmax > cfg->widths[l] ? cmax : cfg->widths[l];
+    }
+    dim3 grid(blocks_for(DCGC_N_DEG * cmax), (unsigned)L);
+    conv_bias_pack_all<<<grid, kT, 0, st>>>(bp);
+    DCGC_CUDA_LAUNCH_CHECK("conv_bias_pack_all");
+  }
   for (int l = 0; l < L; ++l) {
     const int c = cfg->widths[l], fp = lo.fp[l];
     const float* h = sv.h[l];
     const int64_t ld = sv.ld_h[l];
-    conv_bias_pack<<<blocks_for(DCGC_N_DEG * c), kT, 0, st>>>(params + lo.conv_b[l], c, sv.b11[l]);
-    DCGC_CUDA_LAUNCH_CHECK("conv_bias_pack");
     if (use_mg(t, ld, 0, h, sv.s[l]))
       RET_IF(dcgc_mg_gather_sum(h, ld, t, 0, fp, nullptr, 0, sv.s[l], fp, st));
     else
@@ -638,12 +864,14 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
     DcgcGemmOpts go;
     go.img = sv.img_fwd[l];
     go.a_exact = (l == 0 && cfg->input_exact) ? 1 : 0;      // integer-valued features: [X | S] is exact in tf32
+    const DcgcBnFin fin = fuse_stats ? fwd_fin(cfg, lo, l, c, N, params, bn_running, sv) : DcgcBnFin{};
+    if (fin.kind) go.fin = &fin;
     RET_IF(dcgc_group_gemm_fwd_opts(cfg->gemm_mode, h, ld, fp, sv.s[l], fp, fp, params + lo.conv_w[l], sv.b11[l], c,
                                     t->tiles, t->n_tiles, 128, N, DCGC_ACT_RELU, sv.y[l], c,
                                     fuse_stats ? sv.part : nullptr, fuse_stats ? &fused : nullptr, go, st));
     const float *scale = nullptr, *shift = nullptr;
     if (cfg->batch_norm) {
-      RET_IF(bn_forward(cfg, lo, l, sv.y[l], c, N, c, params, bn_running, training, sv, st, fused));
+      RET_IF(bn_forward(cfg, lo, l, sv.y[l], c, N, c, params, bn_running, training, sv, st, fused, fin.kind != 0));
       scale = sv.stats + sv.stats_off[l] + 2 * c;
       shift = scale + c;
     }
@@ -655,23 +883,26 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
   }
   // ---- atom-level dense + ReLU (+BN folded into the gather), GraphGather(tanh), head
   int32_t fused_d = -1;
+  DcgcBnFin fin_d{};
   {
     const bool fuse_d = cfg->batch_norm && training && dcgc_tc_terms(cfg->gemm_mode) != 0;
     DcgcGemmOpts go;
     go.img = sv.img_dense;
+    fin_d = fuse_d ? fwd_fin(cfg, lo, L, D, N, params, bn_running, sv) : DcgcBnFin{};
+    if (fin_d.kind) go.fin = &fin_d;
     RET_IF(dcgc_linear_fwd_opts(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], params + lo.dense_w, params + lo.dense_b,
                                 D, N, DCGC_ACT_RELU, sv.z, D, fuse_d ? sv.part : nullptr, fuse_d ? &fused_d : nullptr,
                                 go, st));
   }
   const float *scale = nullptr, *shift = nullptr;
   if (cfg->batch_norm) {
-    RET_IF(bn_forward(cfg, lo, L, sv.z, D, N, D, params, bn_running, training, sv, st, fused_d));
+    RET_IF(bn_forward(cfg, lo, L, sv.z, D, N, D, params, bn_running, training, sv, st, fused_d, fin_d.kind != 0));
     scale = sv.stats + sv.stats_off[L] + 2 * D;
     shift = scale + D;
   }
   RET_IF(dcgc_gather_fwd(sv.z, D, scale, shift, t->mol_ptr, t->mol_atoms, S, D, DCGC_ACT_TANH, sv.fp, 2 * D,
                          sv.argrow, st));
-  if (n_samples > 0) {
+  if (n_samples > 0 && !skip_head) {
     head_fwd<<<blocks_for(n_samples * cfg->n_out * 32), kT, 0, st>>>(sv.fp, 2 * D, params + lo.head_w,
                                                                     params + lo.head_b, n_samples, 2 * D, cfg->n_out,
                                                                     sv.out);
@@ -724,7 +955,7 @@ extern "C" int64_t dcgc_gcmodel_workspace_bytes(const dcgc_gcmodel_config* cfg, 
   bytes += n_segments * (int64_t)(2 * D * 2 + D) * 4;            // fp, dfp, argrow
   bytes += n_segments * (int64_t)cfg->n_out * 4 * 3;              // out, dout, per-element loss
   bytes += (int64_t)(part_chunks(n_atoms) + 1) * 2 * (int64_t)wmax * 8;
-  bytes += ((n_segments + kHeadChunk - 1) / kHeadChunk + 1) * (int64_t)cfg->n_out * (2 * D + 1) * 4;
+  bytes += ((n_segments + kHfRows - 1) / kHfRows + 1) * ((int64_t)cfg->n_out * (2 * D + 1) * 4 + 8) + 256;
   int64_t wg = 0;
   for (int l = 0; l < L; ++l) {
     const int64_t b = dcgc_group_gemm_wgrad_workspace(lo.fp[l], lo.fp[l], cfg->widths[l], DCGC_N_DEG);
@@ -833,7 +1064,17 @@ extern "C" int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const 
     img_dense_dgrad = im_dense_d;
     sv.img_fwd_ready = side->e1;
   }
-  RET_IF(forward_impl(cfg, lo, t, x, ld_x, n_samples, params, bn_running, 1, 1, ws, sv, st));
+  if (cfg->batch_norm && nt != 0 && N > 0 && last_cta_fin_on(N)) {
+    // counters of the last-CTA BatchNorm finalizes (forward 2 idx, backward 2 idx + 1): zero at every launch
+    sv.fin_counters = ws.take<unsigned int>(2 * (DCGC_MODEL_MAX_LAYERS + 1));
+    if (!ws.ok) {
+      dcgc_set_error("dcgc_gcmodel_train_step: workspace too small");
+      return DCGC_ERR_NOMEM;
+    }
+    DCGC_CUDA_CALL(cudaMemsetAsync(sv.fin_counters, 0, 2 * (DCGC_MODEL_MAX_LAYERS + 1) * sizeof(unsigned int), st));
+  }
+  const bool fused_head = head_fused_ok(cfg);
+  RET_IF(forward_impl(cfg, lo, t, x, ld_x, n_samples, params, bn_running, 1, 1, ws, sv, st, fused_head));
   if (side) DCGC_CUDA_CALL(cudaStreamWaitEvent(st, side->e2, 0));     // the backward's images (long done by now)
   if (forward_event) DCGC_CUDA_CALL(cudaEventRecord((cudaEvent_t)forward_event, st));
 
@@ -849,7 +1090,10 @@ extern "C" int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const 
   const int n_loss_elems_per_row = cfg->mode == 1 ? T / cfg->n_classes : T;
   float* per_elem = ws.take<float>((n_samples > 0 ? n_samples : 1) * n_loss_elems_per_row);
   const int head_chunks = (int)((n_samples + kHeadChunk - 1) / kHeadChunk);
-  float* head_part = ws.take<float>((int64_t)(head_chunks > 0 ? head_chunks : 1) * T * (2 * D + 1));
+  const int head_blocks = (int)((S + kHfRows - 1) / kHfRows);
+  const int64_t part_rows = fused_head ? head_blocks : head_chunks;
+  float* head_part = ws.take<float>((part_rows > 0 ? part_rows : 1) * T * (2 * D + 1));
+  double* loss_part = ws.take<double>(head_blocks > 0 ? head_blocks : 1);
   float* coef = ws.take<float>(3 * (int64_t)wmax);
   float* db11 = ws.take<float>(DCGC_N_DEG * (int64_t)wmax);
   int64_t wg_bytes = dcgc_linear_wgrad_workspace(lo.f[L], D);
@@ -868,6 +1112,25 @@ extern "C" int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const 
   const int64_t n_elems = n_samples * n_loss_elems_per_row;
   {
   DcgcProfScope prof_scope("head_loss_bwd", st);
+  if (fused_head) {
+    static bool attr_done = false;       // per process; 65 KB at the widest supported head
+    if (!attr_done) {
+      DCGC_CUDA_CALL(cudaFuncSetAttribute(head_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr_done = true;
+    }
+    if (head_blocks > 0) {
+      head_fused_kernel<<<head_blocks, kT, head_fused_smem(cfg), st>>>(
+          sv.fp, 2 * D, params + lo.head_w, params + lo.head_b, y, w, n_samples, S, 2 * D, T,
+          cfg->mode == 1 ? cfg->n_classes : 1, cfg->mode, n_elems, sv.out, dfp, head_part, loss_part);
+      DCGC_CUDA_LAUNCH_CHECK("head_fused_kernel");
+    }
+    head_fused_final<<<blocks_for(((int64_t)T * (2 * D + 1) + 1) * 32), kT, 0, st>>>(head_part, loss_part, head_blocks, 2 * D, T,
+                                                                          n_elems, grads + lo.head_w,
+                                                                          grads + lo.head_b, loss_dev);
+    DCGC_CUDA_LAUNCH_CHECK("head_fused_final");
+    if (out && n_samples > 0)
+      DCGC_CUDA_CALL(cudaMemcpyAsync(out, sv.out, (size_t)n_samples * T * 4, cudaMemcpyDeviceToDevice, st));
+  } else {
   if (n_elems > 0) {
     loss_fwd_bwd<<<blocks_for(n_elems), kT, 0, st>>>(sv.out, y, w, n_elems, cfg->mode == 1 ? cfg->n_classes : 1,
                                                      cfg->mode, per_elem, dout);
@@ -890,12 +1153,35 @@ extern "C" int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const 
     DCGC_CUDA_LAUNCH_CHECK("head_bwd_input");
   }
   }
+  }
+  // backward finalize of BatchNorm idx by the last CTA of the kernel that writes dA and its column sums
+  auto bwd_fin = [&](int idx, int width) -> DcgcBnFin {
+    DcgcBnFin f{};
+    if (!sv.fin_counters || !cfg->batch_norm || width > 256) return f;
+    const float* stats = sv.stats + sv.stats_off[idx];
+    f.counter = sv.fin_counters + 2 * idx + 1; f.kind = 2; f.width = width; f.n_rows = N; f.part = sv.part;
+    f.mean = stats; f.invstd = stats + width; f.scale = stats + 2 * width;
+    f.dgamma = grads + lo.bn_g[idx]; f.dbeta = grads + lo.bn_b[idx]; f.coef = coef;
+    return f;
+  };
   // ---- GraphGather backward -> dA (grad wrt the BN output of the dense layer)
-  RET_IF(dcgc_gather_bwd(dfp, 2 * D, sv.fp, 2 * D, sv.argrow, t->membership, N, D, DCGC_ACT_TANH, dA, D, st));
+  // (with BatchNorm: the kernel also emits the BatchNorm-backward column sums of dA against z, one pass less)
+  int32_t fused_gather = -1;
+  DcgcBnFin fin_gather{};
+  if (cfg->batch_norm && N > 0 && D % 4 == 0 &&
+      ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(sv.z) | reinterpret_cast<uintptr_t>(dfp) |
+        reinterpret_cast<uintptr_t>(sv.fp) | reinterpret_cast<uintptr_t>(sv.argrow)) & 15) == 0)
+  {
+    fin_gather = bwd_fin(L, D);
+    RET_IF(dcgc_gather_bwd_stats(dfp, 2 * D, sv.fp, 2 * D, sv.argrow, t->membership, N, D, DCGC_ACT_TANH, dA, D, sv.z, D,
+                                 part_chunks(N), sv.part, &fused_gather, fin_gather.kind ? &fin_gather : nullptr, st));
+  }
+  else
+    RET_IF(dcgc_gather_bwd(dfp, 2 * D, sv.fp, 2 * D, sv.argrow, t->membership, N, D, DCGC_ACT_TANH, dA, D, st));
 
   // fused_chunks >= 0: the stage-1 partials were already written by the kernel that produced dA
   // (dcgc_mg_pool_bwd_stats), one row per CTA
-  auto bn_backward = [&](int idx, const float* yv, int width, int fused_chunks) -> int {
+  auto bn_backward = [&](int idx, const float* yv, int width, int fused_chunks, bool finalized = false) -> int {
     // dA (ld = width) -> G in place; dgamma / dbeta into the gradient slab
     if (cfg->batch_norm) {
       const float* stats = sv.stats + sv.stats_off[idx];
@@ -907,10 +1193,12 @@ extern "C" int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const 
                                                              mom_rows(N, sv.n_chunks), sv.part);
         DCGC_CUDA_LAUNCH_CHECK("col_moments_partial (bwd)");
       }
-      bn_bwd_finalize<<<(width + 15) / 16, 512, 0, st>>>(sv.part, fused_chunks >= 0 ? fused_chunks : (N > 0 ? sv.n_chunks : 0), width, N, stats,
-                                                           stats + width, stats + 2 * width, grads + lo.bn_g[idx],
-                                                           grads + lo.bn_b[idx], coef);
-      DCGC_CUDA_LAUNCH_CHECK("bn_bwd_finalize");
+      if (!(finalized && fused_chunks >= 0)) {
+        bn_bwd_finalize<<<(width + 15) / 16, 512, 0, st>>>(sv.part, fused_chunks >= 0 ? fused_chunks : (N > 0 ? sv.n_chunks : 0), width, N, stats,
+                                                             stats + width, stats + 2 * width, grads + lo.bn_g[idx],
+                                                             grads + lo.bn_b[idx], coef);
+        DCGC_CUDA_LAUNCH_CHECK("bn_bwd_finalize");
+      }
       }
       DcgcProfScope prof_scope("bn_relu_bwd_apply", st);
       if (N > 0) {
@@ -929,7 +1217,7 @@ extern "C" int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const 
   };
 
   // ---- dense layer backward
-  RET_IF(bn_backward(L, sv.z, D, -1));
+  RET_IF(bn_backward(L, sv.z, D, fused_gather, fin_gather.kind != 0));
   RET_IF(dcgc_linear_wgrad(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], dA, D, D, N, grads + lo.dense_w,
                            grads + lo.dense_b, wg, wg_bytes, st));
   RET_IF(slice_done(0));            // head, dense layer and its BatchNorm
@@ -944,23 +1232,27 @@ extern "C" int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const 
     const int c = cfg->widths[l], fp = lo.fp[l];
     // GraphPool backward over CSR^T: dP (ld c) -> dA (ld c)
     int32_t fused = -1;
+    DcgcBnFin fin_pool{};
     if (use_mg(t, c, c, dP, sv.arg[l]) && (reinterpret_cast<uintptr_t>(dA) & 15) == 0) {
       // the BatchNorm-backward column sums of dA come out of the same kernel (DCGC_NO_FUSED_BN_BWD=1: separate pass)
       static const bool no_fuse = [] { const char* e = getenv("DCGC_NO_FUSED_BN_BWD"); return e && e[0] == '1'; }();
       if (cfg->batch_norm && !no_fuse && c % 4 == 0 && (reinterpret_cast<uintptr_t>(sv.y[l]) & 15) == 0)
-        RET_IF(dcgc_mg_pool_bwd_stats(dP, c, sv.arg[l], c, t, c, dA, c, sv.y[l], c, sv.stats + sv.stats_off[l], sv.part,
-                                      &fused, st));
+      {
+        fin_pool = bwd_fin(l, c);
+        RET_IF(dcgc_mg_pool_bwd_stats_fin(dP, c, sv.arg[l], c, t, c, dA, c, sv.y[l], c, sv.stats + sv.stats_off[l], sv.part,
+                                          &fused, fin_pool.kind ? &fin_pool : nullptr, st));
+      }
       else
         RET_IF(dcgc_mg_pool_bwd(dP, c, sv.arg[l], c, nullptr, t, c, dA, c, st));
     } else {
       RET_IF(dcgc_pool_bwd(dP, c, sv.arg[l], c, nullptr, t->t_row_ptr, t->t_src, t->t_slot, N, c, dA, c, st));
     }
-    RET_IF(bn_backward(l, sv.y[l], c, fused));
+    RET_IF(bn_backward(l, sv.y[l], c, fused, fin_pool.kind != 0));
+    // (the reduction of the weight-gradient partials also scatters the 11 per-degree bias sums to the reference's 21
+    // bias rows)
     RET_IF(dcgc_group_gemm_wgrad_opts(cfg->gemm_mode, sv.h[l], sv.ld_h[l], fp, sv.s[l], fp, fp, dA, c, c, t->deg_count,
                                       DCGC_N_DEG, grads + lo.conv_w[l], db11, wg, wg_bytes,
-                                      (l == 0 && cfg->input_exact) ? 1 : 0, st));
-    conv_bias_unpack<<<blocks_for(21 * c), kT, 0, st>>>(db11, c, grads + lo.conv_b[l]);
-    DCGC_CUDA_LAUNCH_CHECK("conv_bias_unpack");
+                                      (l == 0 && cfg->input_exact) ? 1 : 0, st, grads + lo.conv_b[l]));
     RET_IF(slice_done(1 + (L - 1 - l)));
     if (l > 0) {
       // [dP | d2] = G . W^T, then dP += transposed gather of d2
@@ -988,8 +1280,16 @@ extern "C" int dcgc_adam_step(float* params, const float* grads, float* exp_avg,
   DcgcProfScope prof_scope("dcgc_adam_step", (cudaStream_t)stream);
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  adam_kernel<<<blocks_for(n), kT, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                              eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  const int64_t n4 = ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
+                       reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0 ? n / 4 : 0;
+  if (n4 > 0)
+    adam_kernel_vec<<<blocks_for(n4), kT, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4*>(params), reinterpret_cast<const float4*>(grads), reinterpret_cast<float4*>(exp_avg),
+        reinterpret_cast<float4*>(exp_avg_sq), n4, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  if (n - 4 * n4 > 0)      // the tail (or everything, for unaligned slabs): identical arithmetic per element
+    adam_kernel<<<blocks_for(n - 4 * n4), kT, 0, (cudaStream_t)stream>>>(params + 4 * n4, grads + 4 * n4, exp_avg + 4 * n4,
+                                                                       exp_avg_sq + 4 * n4, n - 4 * n4, lr, beta1, beta2,
+                                                                       eps, (float)bc1, (float)sqrt(bc2), grad_scale);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_adam_step");
   return DCGC_OK;
 }

@@ -343,6 +343,7 @@ struct PoolBwdOp {
   struct St { float4 acc; uint32_t t0, t1; float4 yv; };             // t0, t1: slots of this row in its neighbours' lists
   const float* scale;
   const float* y; int ld_y; const float* mean; double* part; int width;   // STATS only
+  DcgcBnFin bnfin;                                                   // STATS only: finalize by the last CTA (kind 0 = off)
   float4 mu, sa, sc2;                                                // column means, sum dx, sum dx * (y - mean)
   __device__ __forceinline__ void bind(int cg) {
     if (AFFINE) sc = __ldg(reinterpret_cast<const float4*>(scale) + cg);
@@ -410,6 +411,8 @@ struct PoolBwdOp {
       part[((int64_t)blockIdx.x * 2) * width + c] = a;
       part[((int64_t)blockIdx.x * 2 + 1) * width + c] = b + (double)__ldg(mean + c) * a;
     }
+    asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");      // the float staging above is no longer read
+    dcgc_bn_fin_last_cta(bnfin, (int)gridDim.x, gridDim.x, 1, kConsumers, ct, reinterpret_cast<double*>(scratch));
   }
 };
 
@@ -661,6 +664,14 @@ extern "C" int dcgc_mg_pool_bwd(const float* dy, int64_t ld_dy, const uint8_t* a
 extern "C" int dcgc_mg_pool_bwd_stats(const float* dy, int64_t ld_dy, const uint8_t* arg, int64_t ld_arg,
                                       const dcgc_topology* t, int32_t width, float* dx, int64_t ld_dx, const float* y,
                                       int64_t ld_y, const float* mean, double* part, int32_t* n_chunks, void* stream) {
+  return dcgc_mg_pool_bwd_stats_fin(dy, ld_dy, arg, ld_arg, t, width, dx, ld_dx, y, ld_y, mean, part, n_chunks, nullptr,
+                                    stream);
+}
+
+// the same with an optional BatchNorm finalize by the last CTA (fused engine; not part of the ABI)
+int dcgc_mg_pool_bwd_stats_fin(const float* dy, int64_t ld_dy, const uint8_t* arg, int64_t ld_arg, const dcgc_topology* t,
+                               int32_t width, float* dx, int64_t ld_dx, const float* y, int64_t ld_y, const float* mean,
+                               double* part, int32_t* n_chunks, const DcgcBnFin* fin, void* stream) {
   DCGC_CHECK_ARG(t && width > 0 && ld_dy >= width && ld_dx >= width && ld_arg >= width && ld_y >= width,
                  "dcgc_mg_pool_bwd_stats: bad sizes");
   DCGC_CHECK_ARG(n_chunks, "dcgc_mg_pool_bwd_stats: null n_chunks");
@@ -680,6 +691,7 @@ extern "C" int dcgc_mg_pool_bwd_stats(const float* dy, int64_t ld_dy, const uint
   PoolBwdOp<false, true> op{};
   op.dx = dx; op.ld_dx = (int)ld_dx;
   op.y = y; op.ld_y = (int)ld_y; op.mean = mean; op.part = part; op.width = width;
+  if (fin) op.bnfin = *fin;
   const int sms = dcgc_tc_num_sms();
   *n_chunks = t->n_groups < sms ? t->n_groups : sms;     // = the grid of mg_launch: one row of partials per CTA
   return mg_launch(t, geo, mg_rec(t, 1), dy, arg, width / 4, op, st, "dcgc_mg_pool_bwd_stats");
