@@ -158,6 +158,14 @@ _SIGNATURES = {
     "dcgc_setgather_attend_fwd": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, c_int64, c_int32, c_int32, _P, c_int64,
                                             _P]),
     "dcgc_lstm_step_fwd": (c_int32, [_P, c_int64, _P, c_int64, c_int32, _P, _P, _P]),
+    "dcgc_pair_contract_bwd_x": (c_int32, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int32, c_int32, _P, c_int64, _P]),
+    "dcgc_gru_out_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P, c_int64, c_int64, c_int32,
+                                   _P, c_int64, _P, c_int64, _P, c_int64, _P]),
+    "dcgc_gru_gates_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int64,
+                                     c_int32, _P, c_int64, _P, c_int64, _P]),
+    "dcgc_setgather_attend_bwd": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int64, _P, _P, c_int64, c_int32, c_int32,
+                                            _P, c_int64, _P, c_int64, _P]),
+    "dcgc_lstm_step_bwd": (c_int32, [_P, c_int64, _P, _P, _P, c_int64, c_int32, _P, c_int64, _P, _P]),
     "dcgc_gcmodel_layout": (c_int32, [POINTER(GcModelConfig), _P, _P, POINTER(c_int64), POINTER(c_int64)]),
     "dcgc_gcmodel_workspace_bytes": (c_int64, [POINTER(GcModelConfig), c_int64, c_int64]),
     "dcgc_gcmodel_forward": (c_int32, [POINTER(GcModelConfig), POINTER(Topology), _P, c_int64, c_int64, _P, _P,

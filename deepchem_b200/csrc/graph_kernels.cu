@@ -309,24 +309,37 @@ gather_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __rest
     sc[v] = scale ? __ldg(scale + c + v) : 1.f;
     sh[v] = scale ? __ldg(shift + c + v) : 0.f;
   }
+  // Eight atoms at a time: their row indices, then their rows, are loaded as independent requests and only then added
+  // in ascending row order (sum order and the lowest-row tie rule of the max are unchanged).  One atom per iteration
+  // was one dependent index -> row round trip after the other: 0.49 of the HBM peak in situ.
+  constexpr int U = 8;
   const int e1 = __ldg(mol_ptr + g + 1);
-  for (int e = __ldg(mol_ptr + g); e < e1; ++e) {
-    const int32_t r = __ldg(mol_atoms + e);
-    float u[VEC];
-    if (VEC == 4) {
-      const float4 q = __ldg(reinterpret_cast<const float4*>(x + (int64_t)r * ld_x + c));
-      u[0] = q.x; u[1 % VEC] = q.y; u[2 % VEC] = q.z; u[3 % VEC] = q.w;
-    } else {
-      u[0] = __ldg(x + (int64_t)r * ld_x + c);
-    }
-    if (scale) {
+  for (int e = __ldg(mol_ptr + g); e < e1; e += U) {
+    int32_t r[U];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) u[v] = fmaf(u[v], sc[v], sh[v]);
+    for (int i = 0; i < U; ++i) r[i] = e + i < e1 ? __ldg(mol_atoms + e + i) : -1;
+    float u[U][VEC];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      if (r[i] < 0) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) u[i][v] = 0.f;
+      } else if (VEC == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(x + (int64_t)r[i] * ld_x + c));
+        u[i][0] = q.x; u[i][1 % VEC] = q.y; u[i][2 % VEC] = q.z; u[i][3 % VEC] = q.w;
+      } else {
+        u[i][0] = __ldg(x + (int64_t)r[i] * ld_x + c);
+      }
     }
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      s[v] += u[v];
-      if (u[v] > m[v] || a[v] < 0) { m[v] = u[v]; a[v] = r; }
+    for (int i = 0; i < U; ++i) {
+      if (r[i] < 0) continue;
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float t2 = scale ? fmaf(u[i][v], sc[v], sh[v]) : u[i][v];
+        s[v] += t2;
+        if (t2 > m[v] || a[v] < 0) { m[v] = t2; a[v] = r[i]; }
+      }
     }
   }
 #pragma unroll

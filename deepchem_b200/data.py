@@ -35,6 +35,16 @@ def pad_batch(batch_size, X_b, y_b, w_b, ids_b, lazy=False):
     return X_out, y_out, w_out, ids_out
 
 
+def pad_features(batch_size, X_b):
+    """Tile the features of a short batch up to ``batch_size`` (deepchem/data/datasets.py:83-138)."""
+    n = len(X_b)
+    if n > batch_size:
+        raise ValueError("Cannot pad an array longer than `batch_size`")
+    if n == batch_size:
+        return X_b
+    return X_b[np.arange(batch_size) % n]
+
+
 class _ArrayDataset(object):
     def _init_arrays(self, n, y, w, ids, n_tasks):
         if y is None:

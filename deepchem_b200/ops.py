@@ -345,7 +345,7 @@ class GroupLinearFn(torch.autograd.Function):
             dw, db = dw[0], db[0]
         if ctx.needs_input_grad[0]:
             dx, _ = group_gemm_dgrad(g, w, x.shape[1], 0, None, True, False, ctx.mode)
-        return dx, dw, db, None, None
+        return dx, (dw if ctx.needs_input_grad[1] else None), (db if ctx.needs_input_grad[2] else None), None, None
 
 
 class GraphPoolFn(torch.autograd.Function):

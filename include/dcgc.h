@@ -461,8 +461,9 @@ int dcgc_mg_pool_bwd_stats(const float* dy_dev, int64_t ld_dy, const uint8_t* ar
                            int64_t ld_y, const float* mean_dev, double* part_dev, int32_t* n_chunks, void* stream);
 
 /* --------------------------------------------------------------------------------------------
- * MPNN edge-network message passing, forward (the reference's torch port of these layers is forward-only).
- * The dense contractions go through dcgc_group_gemm_fwd; these are the parts that are not GEMMs.
+ * MPNN edge-network message passing, forward and backward (the reference's torch port of these layers is forward-only;
+ * the Keras originals, models/layers.py:3648-3887, train: the backward entry points are the gradients of the same
+ * formulas).  The dense contractions go through dcgc_group_gemm_*; these are the parts that are not GEMMs.
  * ------------------------------------------------------------------------------------------ */
 
 /* EdgeNetwork (torch_models/layers.py:4006-4088), first half of its bilinear factorisation: for destination atom
@@ -491,6 +492,34 @@ int dcgc_setgather_attend_fwd(const float* x_dev, int64_t ld_x, const float* q_d
                               int32_t max_atoms, float* qstar_dev, int64_t ld_qs, void* stream);
 int dcgc_lstm_step_fwd(const float* z_dev, int64_t ld_z, const float* c_in_dev, int64_t n, int32_t h,
                        float* h_out_dev, float* c_out_dev, void* stream);
+
+/* Backward of dcgc_pair_contract_fwd with respect to x (the pair features are data): for source atom j with the pairs
+ * src_pair[src_ptr[j] .. src_ptr[j+1]) that read it (pair ids in ascending order: deterministic, no atomics),
+ *   dx[j, b] = sum_q ( sum_f pf[p, f] * dz[pair_dst[p], f*h + b] + dz[pair_dst[p], n_pf*h + b] ),   p = src_pair[q]. */
+int dcgc_pair_contract_bwd_x(const float* dz_dev, int64_t ld_z, const float* pair_feat_dev, int64_t ld_pf,
+                             const int32_t* src_ptr_dev, const int32_t* src_pair_dev, const int32_t* pair_dst_dev,
+                             int64_t n_src, int32_t n_pf, int32_t h, float* dx_dev, int64_t ld_dx, void* stream);
+/* Backward of dcgc_gru_out_fwd: dzg = d out (x - cand), dx = d out z, dpre = d out (1 - z)(1 - cand^2) with
+ * cand = tanh(g[:, 2h:3h] + u + bh) recomputed (dpre is the gradient of g[:, 2h:3h], of u and, summed over rows, of bh). */
+int dcgc_gru_out_bwd(const float* dout_dev, int64_t ld_do, const float* g_dev, int64_t ld_g, const float* u_dev,
+                     int64_t ld_u, const float* bh_dev, const float* z_dev, int64_t ld_z, const float* x_dev,
+                     int64_t ld_x, int64_t n, int32_t h, float* dzg_dev, int64_t ld_dz, float* dx_dev, int64_t ld_dx,
+                     float* dpre_dev, int64_t ld_dp, void* stream);
+/* Backward of dcgc_gru_gates_fwd: dg = [dzg z (1 - z) | dhr h_prev r (1 - r) | dpre] ([n, 3h], the gradient of g and,
+ * summed over rows, of bz / br / -), dh = dhr * r (the direct part of d h_prev). */
+int dcgc_gru_gates_bwd(const float* dzg_dev, int64_t ld_dz, const float* dhr_dev, int64_t ld_dhr, const float* dpre_dev,
+                       int64_t ld_dp, const float* g_dev, int64_t ld_g, const float* bz_dev, const float* br_dev,
+                       const float* hprev_dev, int64_t ld_h, int64_t n, int32_t h, float* dg_dev, int64_t ld_dg,
+                       float* dh_dev, int64_t ld_dh, void* stream);
+/* Backward of dcgc_setgather_attend_fwd: given d qstar [n_mols, 2h] writes dx (every atom row once) and dq. */
+int dcgc_setgather_attend_bwd(const float* x_dev, int64_t ld_x, const float* q_dev, int64_t ld_q, const float* dqs_dev,
+                              int64_t ld_dqs, const int32_t* mol_ptr_dev, const int32_t* mol_atoms_dev, int64_t n_mols,
+                              int32_t h, int32_t max_atoms, float* dx_dev, int64_t ld_dx, float* dq_dev, int64_t ld_dq,
+                              void* stream);
+/* Backward of dcgc_lstm_step_fwd: dh / dc_out may be null (zero); writes dz [n, 4h] and dc_in [n, h]. */
+int dcgc_lstm_step_bwd(const float* z_dev, int64_t ld_z, const float* c_in_dev, const float* dh_dev,
+                       const float* dc_out_dev, int64_t n, int32_t h, float* dz_dev, int64_t ld_dz, float* dc_in_dev,
+                       void* stream);
 
 /* param_offsets: 4 per conv layer (W, b, gamma, beta), then dense (W, b, gamma, beta), then head
  * (W, b); -1 where batch_norm is off.  bn_offsets: (mean, var) per BN, conv layers then dense. */

@@ -101,3 +101,50 @@ def set_gather(atom_features, atom_split, U, b, M, batch_size, n_hidden):
         q_star = torch.cat([h, r], dim=1)
         h, c = lstm_step(q_star, c, U, b, n_hidden)
     return q_star
+
+
+# ---- differentiable, dtype-generic restatements (the Keras originals train: models/layers.py:3648-3887,
+# graph_models.py:1045-1247).  Used in float64 as the gradient oracle of the CUDA backward kernels.
+def lstm_step_d(h, c, U, b, n_hidden):
+    """lstm_step without the float32 casts (layers.py:3081-3108)."""
+    z = h @ U + b
+    i = torch.sigmoid(z[:, :n_hidden])
+    f = torch.sigmoid(z[:, n_hidden:2 * n_hidden])
+    o = torch.sigmoid(z[:, 2 * n_hidden:3 * n_hidden])
+    c_out = f * c + i * torch.tanh(z[:, 3 * n_hidden:])
+    return o * torch.tanh(c_out), c_out
+
+
+def set_gather_d(x, atom_split, U, b, M, batch_size, n_hidden):
+    """set_gather with tensors of any floating dtype, differentiable end to end (Keras semantics: the gradient flows
+    through the LSTM state; the torch port detaches it).  atom_split must be sorted, as its callers guarantee."""
+    split = torch.as_tensor(np.asarray(atom_split)).long()
+    c = x.new_zeros((batch_size, n_hidden))
+    h = x.new_zeros((batch_size, n_hidden))
+    q_star = None
+    for _ in range(M):
+        e = (x * h[split]).sum(dim=-1)
+        m = torch.full((batch_size,), -float("inf"), dtype=x.dtype).scatter_reduce(0, split, e.detach(), "amax")
+        ex = torch.exp(e - m[split])
+        den = x.new_zeros((batch_size,)).index_add(0, split, ex)
+        a = ex / den[split]
+        r = x.new_zeros((batch_size, n_hidden)).index_add(0, split, a.unsqueeze(1) * x)
+        q_star = torch.cat([h, r], dim=1)
+        h, c = lstm_step_d(q_star, c, U, b, n_hidden)
+    return q_star
+
+
+def mpnn_model(params, inputs, T, M, n_hidden, batch_size, mode="regression", n_tasks=1, n_classes=2):
+    """The MPNNModel network (graph_models.py:1121-1160): MessagePassing -> Dense -> SetGather -> Dense(relu) -> Dense.
+    params: dict with enn (W, b), gru (9 tensors), atom_dense (kernel, bias), set_gather (U, b), dense1, out."""
+    atom_features, pair_features, atom_split, atom_to_pair, n_samples = inputs
+    a2p = torch.as_tensor(np.asarray(atom_to_pair)).long()
+    h = message_passing(atom_features, pair_features, a2p, T, n_hidden, params["enn"], params["gru"])
+    emb = h @ params["atom_dense"][0] + params["atom_dense"][1]
+    mol = set_gather_d(emb, atom_split, params["set_gather"][0], params["set_gather"][1], M, batch_size, n_hidden)
+    d1 = torch.relu(mol @ params["dense1"][0] + params["dense1"][1])
+    out = d1 @ params["out"][0] + params["out"][1]
+    if mode == "classification":
+        logits = out.reshape(-1, n_tasks, n_classes)[:int(n_samples)]
+        return [torch.softmax(logits, dim=2), logits]
+    return [out[:int(n_samples)]]

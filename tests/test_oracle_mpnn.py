@@ -52,3 +52,52 @@ def test_message_passing_pads_and_rejects_wide_inputs():
         assert "Too large" in str(e)
     else:
         raise AssertionError("expected ValueError")
+
+
+def test_weave_collation_equals_the_reference_loop():
+    """MPNNModel.default_generator's collation (graph_models.py:1214-1246) restated with explicit loops: pairs of a
+    molecule in row-major (destination, source) order, destinations ascending, pair features reshaped row-major."""
+    from deepchem_b200.mpnn import weave_batch_inputs
+
+    class Mol(object):
+        def __init__(self, n, seed):
+            r = np.random.RandomState(seed)
+            self.n, self.af, self.pf = n, r.randn(n, 4).astype(np.float32), r.randn(n, n, 3).astype(np.float32)
+
+        def get_num_atoms(self):
+            return self.n
+
+        def get_atom_features(self):
+            return self.af
+
+        def get_pair_features(self):
+            return self.pf
+    mols = [Mol(3, 0), Mol(1, 1), Mol(4, 2)]
+    af, pf, split, a2p = weave_batch_inputs(mols, 3)
+    exp_a2p, exp_pf, exp_split, start = [], [], [], 0
+    for im, m in enumerate(mols):
+        for i in range(m.n):
+            exp_split.append(im)
+            for j in range(m.n):
+                exp_a2p.append([start + i, start + j])
+                exp_pf.append(m.pf[i, j])
+        start += m.n
+    assert np.array_equal(a2p, np.array(exp_a2p)) and np.array_equal(split, np.array(exp_split))
+    assert np.array_equal(pf, np.array(exp_pf)) and np.array_equal(af, np.concatenate([m.af for m in mols]))
+    assert bool(np.all(np.diff(a2p[:, 0]) >= 0))          # what EdgeNetwork's segment sum needs
+
+
+def test_set_gather_differentiable_restatement_and_gradcheck():
+    """set_gather_d (dtype-generic, differentiable) equals the literal set_gather, and its float64 autograd — the
+    gradient oracle of the CUDA backward kernels — passes gradcheck."""
+    torch.manual_seed(0)
+    h, B = 6, 4
+    split = np.array([0, 0, 0, 1, 1, 3, 3, 3, 3])           # molecule 2 is empty
+    x = torch.randn(9, h)
+    U, b = torch.randn(2 * h, 4 * h) * 0.2, torch.randn(4 * h) * 0.1
+    a = M.set_gather(x.numpy(), split, U, b, 3, B, h)
+    d = M.set_gather_d(x, split, U, b, 3, B, h)
+    assert float((a - d).abs().max()) < 1e-6
+    x64, U64, b64 = x.double().requires_grad_(), U.double().requires_grad_(), b.double().requires_grad_()
+    assert torch.autograd.gradcheck(lambda xx, uu, bb: M.set_gather_d(xx, split, uu, bb, 2, B, h), (x64, U64, b64),
+                                    eps=1e-6, atol=1e-7)
