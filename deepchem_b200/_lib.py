@@ -61,6 +61,15 @@ class GcModelConfig(Structure):
     ]
 
 
+SYNC_MAX_RANKS = 8
+
+
+class BnSync(Structure):
+    """dcgc_bn_sync"""
+    _fields_ = [("world", c_int32), ("rank", c_int32), ("cap", c_int32), ("reserved", c_int32),
+                ("seq0", ctypes.c_uint64), ("mailbox", ctypes.c_void_p * SYNC_MAX_RANKS)]
+
+
 class DmpnnInfo(ctypes.Structure):
     _fields_ = [(n, c_int64) for n in ("n_mols", "n_atoms", "n_bonds", "n_rows", "k", "n_a2b_entries",
                                        "n_map_entries")] + \
@@ -174,6 +183,13 @@ _SIGNATURES = {
                                           _P, _P, _P, _P, c_int64, _P, _P, _P]),
     "dcgc_gcmodel_train_step_ev": (c_int32, [POINTER(GcModelConfig), POINTER(Topology), _P, c_int64, _P, _P, c_int64,
                                           _P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int32, _P]),
+    "dcgc_gcmodel_train_step_sync": (c_int32, [POINTER(GcModelConfig), POINTER(Topology), _P, c_int64, _P, _P, c_int64,
+                                               _P, _P, _P, _P, c_int64, _P, _P, _P, _P, c_int32, POINTER(BnSync), _P]),
+    "dcgc_bn_sync_mailbox_bytes": (c_int64, [c_int32, c_int32]),
+    "dcgc_p2p_alloc": (c_int32, [c_int64, POINTER(ctypes.c_void_p), _P]),
+    "dcgc_p2p_open": (c_int32, [_P, POINTER(ctypes.c_void_p)]),
+    "dcgc_p2p_close": (c_int32, [_P]),
+    "dcgc_p2p_free": (c_int32, [_P]),
     "dcgc_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, c_float, _P]),
 }
 

@@ -257,6 +257,140 @@ relu_bwd_apply(const float* da, int64_t ld_da, const float* __restrict__ y, int6
 }
 
 // ------------------------------------------------------------------------------------------
+// Synchronised BatchNorm: the finalize kernels with the cross-rank exchange inside (include/dcgc.h, dcgc_bn_sync).
+// ONE block: thread c owns column c.  (1) local sums of the partial rows; (2) they are stored into the mailbox row
+// [this rank][slot] of EVERY rank (peer stores over NVLink), system fence, then the sequence flag of that row;
+// (3) wait until all `world` rows of the own mailbox carry the flag; (4) add the rows in rank order — every rank sees
+// the same values in the same order: bit-identical statistics — and finalize with the global row count.
+// KIND 1: forward (mean / invstd / scale / shift, running statistics); KIND 2: backward (dgamma / dbeta from the LOCAL
+// sums: the gradient exchange adds them over ranks; the apply coefficients from the global ones).
+// ------------------------------------------------------------------------------------------
+struct SyncArgs {
+  int world, rank, cap;
+  unsigned long long seq;
+  double* mailbox[DCGC_SYNC_MAX_RANKS];
+};
+template <int KIND>
+__global__ void __launch_bounds__(512)
+bn_sync_kernel(const SyncArgs sy, const double* __restrict__ part, int n_chunks, int width, long long n_rows_local,
+               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+               float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_io,
+               float* __restrict__ invstd_io, float* __restrict__ scale_io, float* __restrict__ shift_out,
+               float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+  const int t = threadIdx.x;
+  const int slot = (int)(sy.seq & 1ull);
+  const size_t row = 2 * (size_t)sy.cap + 2;
+  double a_loc[2] = {0.0, 0.0}, b_loc[2] = {0.0, 0.0};          // up to two columns per thread (width <= 1024)
+  __shared__ double sh_a[512], sh_b[512];
+  const bool sliced = width <= 256;        // every thread takes a slice of the partial rows of one column (16 loads deep)
+  if (sliced) {
+    const int slices = 512 / width, per = (n_chunks + slices - 1) / slices;
+    const int c = t % width, sl = t / width;
+    double a = 0.0, b = 0.0;
+    if (sl < slices) {
+      const int k1 = min(n_chunks, (sl + 1) * per);
+      for (int k = sl * per; k < k1; k += 16) {
+        double va[16], vb[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          va[u] = k + u < k1 ? part[((size_t)(k + u) * 2) * width + c] : 0.0;
+          vb[u] = k + u < k1 ? part[((size_t)(k + u) * 2 + 1) * width + c] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { a += va[u]; b += vb[u]; }
+      }
+    }
+    sh_a[t] = a; sh_b[t] = b;
+    __syncthreads();
+    if (t < width)
+      for (int q = 0; q < slices; ++q) { a_loc[0] += sh_a[q * width + t]; b_loc[0] += sh_b[q * width + t]; }
+  }
+  for (int i = 0, c = t; c < width; c += 512, ++i) {
+    double a = a_loc[i], b = b_loc[i];
+    if (!sliced) {
+      int k = 0;
+      for (; k + 8 <= n_chunks; k += 8) {
+        double va[8], vb[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          va[u] = part[((size_t)(k + u) * 2) * width + c];
+          vb[u] = part[((size_t)(k + u) * 2 + 1) * width + c];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a += va[u]; b += vb[u]; }
+      }
+      for (; k < n_chunks; ++k) { a += part[((size_t)k * 2) * width + c]; b += part[((size_t)k * 2 + 1) * width + c]; }
+      a_loc[i] = a; b_loc[i] = b;
+    }
+    for (int p = 0; p < sy.world; ++p) {
+      double* dst = sy.mailbox[p] + ((size_t)sy.rank * 2 + slot) * row;
+      dst[c] = a;
+      dst[sy.cap + c] = b;
+    }
+  }
+  if (t == 0)
+    for (int p = 0; p < sy.world; ++p) (sy.mailbox[p] + ((size_t)sy.rank * 2 + slot) * row)[2 * sy.cap] = (double)n_rows_local;
+  __threadfence_system();
+  __syncthreads();
+  if (t < sy.world) {
+    volatile unsigned long long* flag =
+        reinterpret_cast<volatile unsigned long long*>(sy.mailbox[t] + ((size_t)sy.rank * 2 + slot) * row + 2 * sy.cap + 1);
+    *flag = sy.seq;
+  }
+  double* mine = sy.mailbox[sy.rank];
+  if (t < sy.world) {
+    volatile unsigned long long* flag =
+        reinterpret_cast<volatile unsigned long long*>(mine + ((size_t)t * 2 + slot) * row + 2 * sy.cap + 1);
+    unsigned long long t0 = 0;
+    for (unsigned spin = 0; *flag != sy.seq; ++spin) {
+      if ((spin & 0x3ffu) == 0x3ffu) {         // wall-clock bound (60 s): a dead peer traps instead of hanging the GPU
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 60000000000ull) __trap();
+      }
+    }
+  }
+  __syncthreads();
+  __threadfence_system();
+  double rows = 0.0;
+  for (int r = 0; r < sy.world; ++r) rows += __ldcv(mine + ((size_t)r * 2 + slot) * row + 2 * sy.cap);
+  for (int i = 0, c = t; c < width; c += 512, ++i) {
+    double a = 0.0, b = 0.0;
+    for (int r = 0; r < sy.world; ++r) {
+      a += __ldcv(mine + ((size_t)r * 2 + slot) * row + c);
+      b += __ldcv(mine + ((size_t)r * 2 + slot) * row + sy.cap + c);
+    }
+    if (KIND == 1) {
+      const double mean = rows > 0 ? a / rows : 0.0;
+      double var = rows > 0 ? b / rows - mean * mean : 0.0;
+      if (var < 0) var = 0;
+      const double invstd = 1.0 / sqrt(var + (double)eps);
+      const float g = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+      const float sc = (float)(g * invstd);
+      mean_io[c] = (float)mean;
+      invstd_io[c] = (float)invstd;
+      scale_io[c] = sc;
+      shift_out[c] = (float)(be - mean * (double)sc);
+      if (running_mean) {
+        const double unbiased = rows > 1 ? var * rows / (rows - 1.0) : var;
+        running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+        running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * unbiased);
+      }
+    } else {
+      const double is = (double)invstd_io[c], mu = (double)mean_io[c];
+      const double dg_loc = is * (b_loc[i] - mu * a_loc[i]);
+      const double dg = is * (b - mu * a);
+      if (dgamma) dgamma[c] = (float)dg_loc;
+      if (dbeta) dbeta[c] = (float)a_loc[i];
+      coef[c] = scale_io[c];
+      coef[width + c] = rows > 0 ? (float)(a / rows) : 0.f;
+      coef[2 * width + c] = rows > 0 ? (float)(dg / rows) : 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // GraphConv bias packing: reference order b[0..20] (layers.py:6189-6226) <-> per-degree sums
 // ------------------------------------------------------------------------------------------
 struct BiasPackAll { const float* b21[DCGC_MODEL_MAX_LAYERS]; float* b11[DCGC_MODEL_MAX_LAYERS]; int c[DCGC_MODEL_MAX_LAYERS]; };
@@ -681,7 +815,14 @@ struct Saved {
   const float* img_dense;
   cudaEvent_t img_fwd_ready;   // main stream waits on it before the first GEMM
   unsigned int* fin_counters;  // train step: zeroed counters of the last-CTA BatchNorm finalizes (2 per BatchNorm), or null
+  const dcgc_bn_sync* sync;    // synchronised BatchNorm (world > 1), or null
 };
+static SyncArgs sync_args(const dcgc_bn_sync* sy, unsigned long long seq) {
+  SyncArgs a{};
+  a.world = sy->world; a.rank = sy->rank; a.cap = sy->cap; a.seq = seq;
+  for (int r = 0; r < sy->world; ++r) a.mailbox[r] = static_cast<double*>(sy->mailbox[r]);
+  return a;
+}
 
 // ---- early weight images: one side stream + three events per device, created on first use
 struct SideStream { cudaStream_t s; cudaEvent_t e0, e1, e2; };
@@ -792,6 +933,14 @@ int bn_forward(const dcgc_gcmodel_config* cfg, const Layout& lo, int idx, const 
                                                              sv.part);
         DCGC_CUDA_LAUNCH_CHECK("col_moments_partial");
       }
+    }
+    if (sv.sync) {
+      // statistics over the rows of every rank: exchange through the peer mailboxes inside the finalize kernel
+      bn_sync_kernel<1><<<1, 512, 0, st>>>(sync_args(sv.sync, sv.sync->seq0 + (unsigned long long)idx), sv.part, chunks,
+                                           width, (long long)n, gamma, beta, cfg->bn_eps, cfg->bn_momentum, rm, rv, mean,
+                                           invstd, scale, shift, nullptr, nullptr, nullptr);
+      DCGC_CUDA_LAUNCH_CHECK("bn_sync_kernel (forward)");
+      return DCGC_OK;
     }
     bn_fwd_finalize<<<(width + 15) / 16, 512, 0, st>>>(sv.part, chunks, width, n, gamma, beta, cfg->bn_eps,
                                                        cfg->bn_momentum, rm, rv, mean, invstd, scale, shift);
@@ -1014,9 +1163,41 @@ extern "C" int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const 
                                           const float* params, float* grads, float* bn_running, void* workspace,
                                           int64_t workspace_bytes, float* loss_dev, float* out, void* forward_event,
                                           void* const* grad_events, int32_t n_grad_events, void* stream) {
+  return dcgc_gcmodel_train_step_sync(cfg, topo, x, ld_x, y, w, n_samples, params, grads, bn_running, workspace,
+                                      workspace_bytes, loss_dev, out, forward_event, grad_events, n_grad_events, nullptr,
+                                      stream);
+}
+
+extern "C" int dcgc_gcmodel_train_step_sync(const dcgc_gcmodel_config* cfg, const dcgc_topology* topo, const float* x,
+                                            int64_t ld_x, const float* y, const float* w, int64_t n_samples,
+                                            const float* params, float* grads, float* bn_running, void* workspace,
+                                            int64_t workspace_bytes, float* loss_dev, float* out, void* forward_event,
+                                            void* const* grad_events, int32_t n_grad_events, const dcgc_bn_sync* sync,
+                                            void* stream) {
   Layout lo;
   RET_IF(make_layout(cfg, &lo));
   RET_IF(check_topo(topo));
+  if (sync && (sync->world <= 1 || !cfg->batch_norm)) sync = nullptr;
+  if (sync) {
+    int wmax_s = cfg->dense;
+    for (int l = 0; l < cfg->n_layers; ++l) wmax_s = wmax_s > cfg->widths[l] ? wmax_s : cfg->widths[l];
+    DCGC_CHECK_ARG(sync->world <= DCGC_SYNC_MAX_RANKS && sync->rank >= 0 && sync->rank < sync->world && sync->seq0 > 0 &&
+                       sync->cap >= wmax_s && wmax_s <= 1024,
+                   "dcgc_gcmodel_train_step_sync: bad dcgc_bn_sync (world %d, rank %d, cap %d for width %d)", sync->world,
+                   sync->rank, sync->cap, wmax_s);
+    for (int r = 0; r < sync->world; ++r)
+      DCGC_CHECK_ARG(sync->mailbox[r], "dcgc_gcmodel_train_step_sync: mailbox of rank %d is not mapped", r);
+    // The exchange kernels wait for a peer inside the kernel.  With lazy module loading the FIRST launch of a kernel
+    // may need the device idle: were that to happen behind a waiting exchange kernel of the same device (two ranks
+    // sharing one GPU), the host would block and the peer's step would never be enqueued.  Load both variants now.
+    static bool loaded = false;
+    if (!loaded) {
+      cudaFuncAttributes fa;
+      DCGC_CUDA_CALL(cudaFuncGetAttributes(&fa, bn_sync_kernel<1>));
+      DCGC_CUDA_CALL(cudaFuncGetAttributes(&fa, bn_sync_kernel<2>));
+      loaded = true;
+    }
+  }
   DCGC_CHECK_ARG(params && grads && y && loss_dev && workspace, "dcgc_gcmodel_train_step: null pointer");
   DCGC_CHECK_ARG(n_grad_events >= 0 && n_grad_events <= cfg->n_layers + 1 && (n_grad_events == 0 || grad_events),
                  "dcgc_gcmodel_train_step_ev: at most n_layers + 1 gradient events");
@@ -1030,6 +1211,7 @@ extern "C" int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const 
   const int64_t N = t->n_atoms, S = t->n_segments;
   Arena ws{(char*)workspace, 0, workspace_bytes};
   Saved sv{};
+  sv.sync = sync;
   // ---- weight images of all seven GEMMs, built now on the side stream (the weights only change in the Adam launch,
   // which precedes this call on `st`): they run beside the first gather-sum instead of in front of every GEMM
   const float* img_dgrad[DCGC_MODEL_MAX_LAYERS] = {};
@@ -1064,7 +1246,7 @@ extern "C" int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const 
     img_dense_dgrad = im_dense_d;
     sv.img_fwd_ready = side->e1;
   }
-  if (cfg->batch_norm && nt != 0 && N > 0 && last_cta_fin_on(N)) {
+  if (cfg->batch_norm && nt != 0 && N > 0 && last_cta_fin_on(N) && !sync) {
     // counters of the last-CTA BatchNorm finalizes (forward 2 idx, backward 2 idx + 1): zero at every launch
     sv.fin_counters = ws.take<unsigned int>(2 * (DCGC_MODEL_MAX_LAYERS + 1));
     if (!ws.ok) {
@@ -1193,7 +1375,15 @@ extern "C" int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const 
                                                              mom_rows(N, sv.n_chunks), sv.part);
         DCGC_CUDA_LAUNCH_CHECK("col_moments_partial (bwd)");
       }
-      if (!(finalized && fused_chunks >= 0)) {
+      if (sv.sync) {
+        const int chunks = fused_chunks >= 0 ? fused_chunks : (N > 0 ? sv.n_chunks : 0);
+        float* stats_w = sv.stats + sv.stats_off[idx];
+        bn_sync_kernel<2><<<1, 512, 0, st>>>(
+            sync_args(sv.sync, sv.sync->seq0 + (unsigned long long)(L + 1 + (L - idx))), sv.part, chunks, width,
+            (long long)N, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, stats_w, stats_w + width, stats_w + 2 * width,
+            nullptr, grads + lo.bn_g[idx], grads + lo.bn_b[idx], coef);
+        DCGC_CUDA_LAUNCH_CHECK("bn_sync_kernel (backward)");
+      } else if (!(finalized && fused_chunks >= 0)) {
         bn_bwd_finalize<<<(width + 15) / 16, 512, 0, st>>>(sv.part, fused_chunks >= 0 ? fused_chunks : (N > 0 ? sv.n_chunks : 0), width, N, stats,
                                                              stats + width, stats + 2 * width, grads + lo.bn_g[idx],
                                                              grads + lo.bn_b[idx], coef);

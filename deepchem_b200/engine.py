@@ -9,6 +9,7 @@ runs forward + loss + backward and writes every gradient into a parallel flat gr
 fused Adam launch.
 """
 import ctypes
+import os
 
 import torch
 
@@ -119,6 +120,7 @@ class FlatEngine(AdamSlabState):
         self.device = torch.device(device)
         self.lr, self.betas, self.eps = lr, betas, eps
         self.step_count = 0
+        self._mailboxes = None        # parallel.PeerMailboxes of a sync_batch_norm model, made at the first step
         L = len(model.graph_convs)
         cfg = _lib.GcModelConfig()
         cfg.n_layers = L
@@ -161,8 +163,15 @@ class FlatEngine(AdamSlabState):
         uncertainty head, widths that are multiples of 4.  Anything else uses the autograd layers."""
         if getattr(model, "uncertainty", False):
             return False
-        if getattr(model, "sync_batch_norm", False):       # statistics exchanged between ranks inside the step:
-            return False                                   # the per-layer autograd path with parallel.SyncBatchNorm1d
+        if getattr(model, "sync_batch_norm", False):
+            # statistics exchanged between ranks inside the step: the engine does it through peer-memory mailboxes
+            # (dcgc_gcmodel_train_step_sync) for the ranks of one node on CUDA; otherwise the per-layer autograd path
+            # with parallel.SyncBatchNorm1d (any backend, e.g. gloo on the CPU)
+            import torch.distributed as dist
+            if not (torch.cuda.is_available() and dist.is_available() and dist.is_initialized()
+                    and dist.get_backend() == "nccl" and dist.get_world_size() <= _lib.SYNC_MAX_RANKS
+                    and os.environ.get("DCGC_ENGINE_SYNCBN", "1") != "0"):
+                return False
         if len(model.graph_convs) > _lib.MODEL_MAX_LAYERS:
             return False
         widths = [c.out_channel for c in model.graph_convs] + [model.dense.out_features]
@@ -269,12 +278,21 @@ class FlatEngine(AdamSlabState):
         if grad_events:
             n_ev = len(grad_events)
             evs = (ctypes.c_void_p * n_ev)(*[e.cuda_event for e in grad_events])
-        check(L.dcgc_gcmodel_train_step_ev(
+        sync = None
+        if getattr(self.model, "sync_batch_norm", False) and self.cfg.batch_norm:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                if self._mailboxes is None:
+                    from .parallel import PeerMailboxes
+                    cap = max([self.cfg.widths[l] for l in range(self.cfg.n_layers)] + [self.cfg.dense])
+                    self._mailboxes = PeerMailboxes(cap)
+                sync = ctypes.byref(self._mailboxes.struct(2 * (self.cfg.n_layers + 1)))
+        check(L.dcgc_gcmodel_train_step_sync(
             ctypes.byref(self.cfg), ctypes.byref(topology_struct(topo)), x.data_ptr(), x.stride(0),
             y.data_ptr(), w.data_ptr() if w is not None else None, n_samples, self.params.data_ptr(),
             self.grads.data_ptr(), self.bn_running.data_ptr() if self.n_bn else None, ws.data_ptr(), ws.numel(),
             self.loss.data_ptr(), out.data_ptr() if out is not None else None,
-            forward_event.cuda_event if forward_event is not None else None, evs, n_ev, self._stream()))
+            forward_event.cuda_event if forward_event is not None else None, evs, n_ev, sync, self._stream()))
         return self.loss
 
     def forward(self, topo, x, n_samples, training=False, want_probs=True):

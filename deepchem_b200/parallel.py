@@ -151,3 +151,60 @@ class SyncBatchNorm1d(torch.nn.BatchNorm1d):
                 self.running_mean.mul_(1.0 - m).add_(mean.to(self.running_mean.dtype), alpha=m)
                 self.running_var.mul_(1.0 - m).add_(unbiased.to(self.running_var.dtype), alpha=m)
         return y
+
+
+class PeerMailboxes(object):
+    """The peer-memory mailboxes of the synchronised BatchNorm inside the fused engine (include/dcgc.h, dcgc_bn_sync):
+    every rank of the node allocates one IPC-shareable device buffer, the 64-byte handles travel once through the
+    process group, every rank maps the buffers of its peers.  From then on the BatchNorm finalize kernels exchange
+    their column sums with plain stores over NVLink — no collective call and no host round trip inside the step.
+    ``struct(n_uses)`` hands out the dcgc_bn_sync of the next step and advances the sequence number."""
+
+    def __init__(self, cap, group=None):
+        import ctypes
+        from . import _lib
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("PeerMailboxes needs an initialised process group")
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > _lib.SYNC_MAX_RANKS:
+            raise ValueError("at most %d ranks (one node)" % _lib.SYNC_MAX_RANKS)
+        self.cap = int(cap)
+        L = _lib.lib()
+        nbytes = int(L.dcgc_bn_sync_mailbox_bytes(self.world, self.cap))
+        own = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        _lib.check(L.dcgc_p2p_alloc(nbytes, ctypes.byref(own), handle))
+        self._own = own.value
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        self._peers = []
+        self.ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                self.ptrs.append(self._own)
+                continue
+            ptr = ctypes.c_void_p()
+            _lib.check(L.dcgc_p2p_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(ptr)))
+            self._peers.append(ptr.value)
+            self.ptrs.append(ptr.value)
+        dist.barrier(group=group)          # every mailbox is zeroed and mapped before the first kernel writes one
+        self.seq = 1
+        self._struct = _lib.BnSync()
+        self._struct.world, self._struct.rank, self._struct.cap = self.world, self.rank, self.cap
+        for r, ptr in enumerate(self.ptrs):
+            self._struct.mailbox[r] = ptr
+
+    def struct(self, n_uses):
+        self._struct.seq0 = self.seq
+        self.seq += int(n_uses)
+        return self._struct
+
+    def close(self):
+        from . import _lib
+        L = _lib.lib()
+        for ptr in self._peers:
+            L.dcgc_p2p_close(ptr)
+        self._peers = []
+        if self._own:
+            L.dcgc_p2p_free(self._own)
+            self._own = None

@@ -558,6 +558,40 @@ int dcgc_gcmodel_train_step_ev(const dcgc_gcmodel_config* cfg, const dcgc_topolo
                                const float* params_dev, float* grads_dev, float* bn_running_dev,
                                void* workspace_dev, int64_t workspace_bytes, float* loss_dev, float* out_dev,
                                void* forward_event, void* const* grad_events, int32_t n_grad_events, void* stream);
+
+/* ---- synchronised BatchNorm inside the fused step (SURVEY 8e opt-in): statistics over the atoms of every rank ----------
+ * The ranks of one node exchange their per-column sums through PEER MEMORY: every rank owns a small mailbox
+ * (dcgc_p2p_alloc: device memory with a CUDA IPC handle) that its peers map (dcgc_p2p_open) and write with plain stores
+ * over NVLink from inside the BatchNorm finalize kernel — sums + row count, a system-scope fence, then a sequence flag;
+ * the kernel then waits for the flags of all ranks in ITS OWN mailbox and adds the contributions in rank order, so
+ * every rank obtains bit-identical global statistics without a library collective or a host round trip (two kernels
+ * of one block per BatchNorm and direction, a few microseconds each).  Mailbox layout (doubles):
+ *   [sender rank][slot = use & 1][2 * cap sums | row count | flag]   with cap >= the widest BatchNorm of the model;
+ * bytes = dcgc_bn_sync_mailbox_bytes(world, cap).  `seq` numbers the BatchNorm uses since the mailboxes were zeroed:
+ * the step consumes 2 * (n_layers + 1) numbers starting at seq0 (the caller advances it), every rank must pass the same. */
+#define DCGC_SYNC_MAX_RANKS 8
+typedef struct dcgc_bn_sync {
+  int32_t world, rank;
+  int32_t cap;                 /* columns a mailbox row holds */
+  int32_t reserved;
+  uint64_t seq0;               /* first sequence number of this step (> 0) */
+  void* mailbox[DCGC_SYNC_MAX_RANKS];   /* mailbox of rank r as mapped in THIS process (own: the dcgc_p2p_alloc pointer) */
+} dcgc_bn_sync;
+int64_t dcgc_bn_sync_mailbox_bytes(int32_t world, int32_t cap);
+/* device memory shareable between the processes of one node: handle_out = 64 bytes (cudaIpcMemHandle_t), zero-filled */
+int dcgc_p2p_alloc(int64_t bytes, void** ptr_out, void* handle_out);
+int dcgc_p2p_open(const void* handle, void** ptr_out);
+int dcgc_p2p_close(void* ptr);
+int dcgc_p2p_free(void* ptr);
+/* dcgc_gcmodel_train_step_ev with synchronised BatchNorm (sync may be NULL or world == 1: identical to _ev).  The
+ * gradients of gamma / beta stay LOCAL sums (the caller's gradient exchange adds them over ranks, as for every other
+ * parameter); tensor-core GEMM modes only. */
+int dcgc_gcmodel_train_step_sync(const dcgc_gcmodel_config* cfg, const dcgc_topology* topo, const float* x_dev,
+                                 int64_t ld_x, const float* y_dev, const float* w_dev, int64_t n_samples,
+                                 const float* params_dev, float* grads_dev, float* bn_running_dev,
+                                 void* workspace_dev, int64_t workspace_bytes, float* loss_dev, float* out_dev,
+                                 void* forward_event, void* const* grad_events, int32_t n_grad_events,
+                                 const dcgc_bn_sync* sync, void* stream);
 /* Fused Adam over a flat slab, torch.optim.Adam semantics (models/optimizers.py:190-241);
  * grads are multiplied by grad_scale first (1/world_size after a summing all-reduce). */
 int dcgc_adam_step(float* params_dev, const float* grads_dev, float* exp_avg_dev, float* exp_avg_sq_dev,

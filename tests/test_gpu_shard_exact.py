@@ -154,3 +154,97 @@ def test_sync_batch_norm_model_on_one_process_equals_the_default_model():
     for n, p in b.model.named_parameters():
         scale = max(float(g_a[n].abs().max()), 1e-6)
         assert float((p.grad - g_a[n]).abs().max()) < 1e-4 * scale + 1e-9, n
+
+
+def test_synchronised_batchnorm_in_the_engine_equals_one_process_on_the_whole_batch():
+    """dcgc_gcmodel_train_step_sync (SURVEY 8e opt-in): two "ranks" — two engines on two streams of ONE device, their
+    mailboxes two plain allocations of this process, so no IPC — exchange the BatchNorm column sums through the
+    mailboxes from inside the finalize kernels.  With statistics over both shards the model IS the single-process
+    function of the concatenated batch: averaged loss, averaged gradient slab and running statistics must match one
+    engine on the whole batch, and both ranks must hold bit-identical running statistics.  (The two-GPU version over
+    NVLink with IPC-mapped mailboxes: scripts/syncbn_check.py, profiles/r5s_syncbn_2gpu.json.)"""
+    import ctypes
+    from deepchem_b200 import _lib
+    from deepchem_b200.data import PackedDataset
+    from deepchem_b200.engine import _ws, topology_struct
+    from deepchem_b200.graphconvmodel import GraphConvModel
+    from deepchem_b200.synthetic import make_labels, make_molecules
+    dev = _cuda()
+    world, B = 2, 160
+    pm = make_molecules(world * B, seed=33, shape="zinc")
+    y, w = make_labels(world * B, 2, "regression", seed=8)
+
+    def build(bsz):
+        torch.manual_seed(5)
+        m = GraphConvModel(2, graph_conv_layers=[64, 128], dense_layer_size=128, mode="regression", batch_size=bsz,
+                           device=dev, gemm_mode="tf32x3")
+        assert m._engine is not None and m._engine.cfg.batch_norm == 1
+        m.model.train()
+        return m
+
+    def prepared(m, pm_, y_, w_):
+        batch = next(m.default_generator(PackedDataset(pm_, y_, w_), deterministic=True, pad_batches=False))
+        return m._prepare_batch(batch)
+
+    whole = build(world * B)
+    inputs, labels, weights = prepared(whole, pm, y, w)
+    loss_whole = float(whole._engine.train_step(inputs[1]._dcgc_topology, inputs[0], labels[0].contiguous(),
+                                                weights[0].contiguous(), world * B))
+    g_whole, bn_whole = whole._engine.grads.clone(), whole._engine.bn_running.clone()
+
+    L = _lib.lib()
+    cap = 128
+    nbytes = int(L.dcgc_bn_sync_mailbox_bytes(world, cap))
+    boxes, handle = [], ctypes.create_string_buffer(64)
+    for _ in range(world):
+        ptr = ctypes.c_void_p()
+        _lib.check(L.dcgc_p2p_alloc(nbytes, ctypes.byref(ptr), handle))
+        boxes.append(ptr.value)
+    try:
+        shards, preps, streams = [], [], [torch.cuda.Stream(device=dev) for _ in range(world)]
+        for r in range(world):
+            s = build(B)
+            s.model.load_state_dict(whole.model.state_dict(), strict=False)
+            for b_ in s.model.batch_norms:
+                b_.reset_running_stats()
+            s._engine.adopt()
+            shards.append(s)
+            preps.append(prepared(s, pm.slice(r * B, (r + 1) * B), y[r * B:(r + 1) * B], w[r * B:(r + 1) * B]))
+            # one plain step first: every kernel of the step is loaded before a kernel of this device waits for a peer
+            # (CUDA loads modules lazily, and a load behind a waiting kernel would block the host: see model.cu)
+            ins, lab, wts = preps[r]
+            s._engine.train_step(ins[1]._dcgc_topology, ins[0], lab[0].contiguous(), wts[0].contiguous(), B)
+            for b_ in s.model.batch_norms:
+                b_.reset_running_stats()
+        torch.cuda.synchronize()
+        for r in range(world):                    # enqueue rank r's whole step on its own stream; nothing blocks the host
+            eng = shards[r]._engine
+            ins, lab, wts = preps[r]
+            topo = ins[1]._dcgc_topology
+            sy = _lib.BnSync()
+            sy.world, sy.rank, sy.cap, sy.seq0 = world, r, cap, 1
+            for q in range(world):
+                sy.mailbox[q] = boxes[q]
+            ws = torch.empty(int(L.dcgc_gcmodel_workspace_bytes(ctypes.byref(eng.cfg), topo.n_atoms, topo.n_segments)) + 256,
+                             dtype=torch.uint8, device=dev)
+            eng._test_ws = ws
+            yb, wb = lab[0].contiguous(), wts[0].contiguous()
+            eng._test_keep = (yb, wb)
+            with torch.cuda.stream(streams[r]):
+                _lib.check(L.dcgc_gcmodel_train_step_sync(
+                    ctypes.byref(eng.cfg), ctypes.byref(topology_struct(topo)), ins[0].data_ptr(), ins[0].stride(0),
+                    yb.data_ptr(), wb.data_ptr(), B, eng.params.data_ptr(), eng.grads.data_ptr(), eng.bn_running.data_ptr(),
+                    ws.data_ptr(), ws.numel(), eng.loss.data_ptr(), None, None, None, 0, ctypes.byref(sy),
+                    ctypes.c_void_p(streams[r].cuda_stream)))
+        torch.cuda.synchronize()
+        g_avg = sum(s._engine.grads for s in shards) / world
+        loss_avg = sum(float(s._engine.loss) for s in shards) / world
+        assert torch.equal(shards[0]._engine.bn_running, shards[1]._engine.bn_running)
+        assert _rel(shards[0]._engine.bn_running, bn_whole) < 1e-6
+        assert abs(loss_avg - loss_whole) < 1e-5 * max(1.0, abs(loss_whole))
+        assert float(g_whole.abs().max()) > 0
+        assert _rel(g_avg, g_whole) < TOL
+    finally:
+        torch.cuda.synchronize()
+        for ptr in boxes:
+            L.dcgc_p2p_free(ptr)
