@@ -1777,6 +1777,256 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) tc_wgrad_kernel_v2(const DcgcW
 }
 
 // ------------------------------------------------------------------------------------------
+// tc_wgrad_kernel_v3: tc_wgrad_kernel_v2 with all three operands FED BY TMA.
+//
+// Why (profiles/r5g_wgrad_v2_timeline.log, whole-grid timers): v2's register-fed loads keep ~48 KB per SM in flight and
+// the grid as a whole reads 2.8 of the 6.55 TB/s it is bound by (2.2 us per 48 KB chunk for the median CTA).  Here one
+// thread issues three tensor-map loads per 32-atom chunk — a1 [32 x <=128], a2 [32 x <=128], G [32 x 128], plain
+// row-major boxes, no swizzle — into a two-deep ring of 48 KB: 96 KB in flight per SM without a register.  The roles
+// of v2 become CONVERTERS that read a landed chunk from shared memory:
+//   * warps 0-3 (G): thread = channel, 32 LDS.32 down its column (consecutive lanes = consecutive banks), rows past
+//     the CTA's range masked, tf32 split, tcgen05.st.32x32b (lane = channel, column = atom), bias column sum;
+//   * warps 4-11 ([a1 | a2]): LDS.128 of the row-major chunk (a warp instruction = four 128-byte row segments),
+//     split, STS.128 into the MN-major SWIZZLE_128B_BASE32B hi / lo tiles the MMAs read (as v2);
+//   * warp 12 MMA issuer (12 MMAs of N = 256 per chunk), warp 13 the TMA loader.
+// No software pipelining in the converters (shared-memory latency, not HBM latency): a third of v2's code.
+// Shared-memory port per chunk: 48 KB TMA in + 48 KB LDS + 64 KB STS + 96 KB MMA reads = 256 KB = 2 000 cycles, at
+// the chunk's HBM floor of 2 150.  Needs 16-byte aligned rows, k1 and k2 multiples of 4 and <= 128; otherwise v2 runs.
+// ------------------------------------------------------------------------------------------
+constexpr int WG3_THREADS = 14 * 32;
+constexpr int WG3_RAW_STAGES = 2;
+constexpr int WG3_B_STAGES = 2;
+constexpr int WG3_RAW_TILE = 32 * 128 * 4;      // one [32 atoms x 128 floats] box
+
+template <int NB, int NT>
+__global__ void __launch_bounds__(WG3_THREADS, 1)
+tc_wgrad_kernel_v3(const DcgcWgradArgs p, const __grid_constant__ CUtensorMap map_a1,
+                   const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_g) {
+  constexpr int TPO = NT == 3 ? 2 : 1;
+  constexpr int B_TILE_BYTES = NB * TC_TILE_BYTES;
+  constexpr int STAGE_BYTES = TPO * B_TILE_BYTES;
+  constexpr int RAW_STAGE_BYTES = 3 * WG3_RAW_TILE;            // a1 | a2 | G (a2 unused for a single operand)
+  constexpr int NLB = 4 * NB;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t raw_base = base + WG3_B_STAGES * STAGE_BYTES;
+  uint8_t* raw_ptr = sm + WG3_B_STAGES * STAGE_BYTES;
+  const uint32_t bar_base = raw_base + WG3_RAW_STAGES * RAW_STAGE_BYTES;
+  // barriers: b_full[s] +8s, b_empty[s] +16+8s, raw_full[s] +32+8s, raw_empty[s] +48+8s, g_full[s] +64+8s,
+  // g_empty[s] +96+8s, accumulator ready +128, tmem slot +136
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_ptr + WG3_RAW_STAGES * RAW_STAGE_BYTES + 136);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int chunk = blockIdx.x;
+  int g = 0;
+  while (g + 1 < p.n_groups && chunk >= p.chunk_prefix[g + 1]) ++g;
+  const int64_t r_begin = p.group_row0[g] + (int64_t)(chunk - p.chunk_prefix[g]) * p.chunk_rows;
+  const int64_t r_end = min(p.group_row0[g + 1], r_begin + p.chunk_rows);
+  const int nt = blockIdx.y;                      // (one feature tile: Kt <= NB * 128)
+  const int n0 = nt * TC_BN;
+  const int Kt = p.k1 + p.k2;
+  const int steps = (int)((r_end - r_begin + TC_BK - 1) / TC_BK);
+  const bool wdbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  if (wdbg && tid == 0) { p.dbg[5000] = clock64(); p.dbg[5001] = steps; }
+  if (p.dbg != nullptr && tid == 0 && blockIdx.y == 0 && blockIdx.x < 512) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[6000 + 4 * blockIdx.x] = (long long)gt; p.dbg[6002 + 4 * blockIdx.x] = steps;
+  }
+
+  if (tid == 0) {
+    for (int s = 0; s < WG3_B_STAGES; ++s) {
+      mbar_init(bar_base + 8 * s, 8);                 // the eight [a1 | a2] converter warps
+      mbar_init(bar_base + 16 + 8 * s, 1);            // tcgen05.commit
+    }
+    for (int s = 0; s < WG3_RAW_STAGES; ++s) {
+      mbar_init(bar_base + 32 + 8 * s, 1);            // the loader's arrive.expect_tx (+ the TMA bytes)
+      mbar_init(bar_base + 48 + 8 * s, 12);           // all twelve converter warps have read the raw chunk
+    }
+    for (int s = 0; s < WG2_G_STAGES; ++s) {
+      mbar_init(bar_base + 64 + 8 * s, 4);
+      mbar_init(bar_base + 96 + 8 * s, 1);
+    }
+    mbar_init(bar_base + 128, 1);
+    fence_barrier_init();
+  }
+  if (warp == 12) tmem_alloc(bar_base + 136, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 13) {
+    // ===================== TMA loader =====================
+    if (lane == 0) {
+      const bool two = p.k2 > 0;
+      for (int c = 0; c < steps; ++c) {
+        const int s = c % WG3_RAW_STAGES;
+        mbar_wait(bar_base + 48 + 8 * s, ((c / WG3_RAW_STAGES) & 1) ^ 1);
+        const uint32_t dst = raw_base + s * RAW_STAGE_BYTES, bar = bar_base + 32 + 8 * s;
+        const int row = (int)(r_begin + (int64_t)c * TC_BK);
+        mbar_arrive_expect_tx(bar, (uint32_t)((two ? 3 : 2) * WG3_RAW_TILE));
+        tma_load_2d(dst, &map_a1, 0, row, bar);
+        if (two) tma_load_2d(dst + WG3_RAW_TILE, &map_a2, 0, row, bar);
+        tma_load_2d(dst + 2 * WG3_RAW_TILE, &map_g, n0, row, bar);
+        if (wdbg && c < 1000) p.dbg[2048 + c] = clock64();
+      }
+    }
+  } else if (warp < 4) {
+    // ===================== G converters: shared-memory column -> tf32 hi / lo -> tensor memory =====================
+    const int nl = 32 * warp + lane;                           // channel inside the tile = TMEM lane
+    const bool n_ok = n0 + nl < p.n;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * warp) << 16) + V4_A_COL0;
+    float bsum = 0.f;
+    for (int c = 0; c < steps; ++c) {
+      const int sr = c % WG3_RAW_STAGES, sg = c % WG2_G_STAGES;
+      mbar_wait(bar_base + 32 + 8 * sr, (c / WG3_RAW_STAGES) & 1);                 // the chunk has landed
+      const float* gr = reinterpret_cast<const float*>(raw_ptr + sr * RAW_STAGE_BYTES + 2 * WG3_RAW_TILE) + nl;
+      const int live = (int)min((int64_t)TC_BK, r_end - (r_begin + (int64_t)c * TC_BK));
+      float v[32];
+#pragma unroll
+      for (int a = 0; a < 32; ++a) v[a] = (n_ok && a < live) ? gr[a * 128] : 0.f;
+      mbar_wait(bar_base + 96 + 8 * sg, ((c / WG2_G_STAGES) & 1) ^ 1);             // the MMAs that read this G stage retired
+      tc_fence_after();
+      const uint32_t col = t_lane + (uint32_t)sg * 64u;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t hi[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hi[i] = __float_as_uint(term_hi<NT>(v[16 * h + i]));
+        tmem_st32x16(col + 16u * h, hi);
+        if (NT == 3) {
+          uint32_t lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) lo[i] = __float_as_uint(tf32_lo(v[16 * h + i], __uint_as_float(hi[i])));
+          tmem_st32x16(col + 32u + 16u * h, lo);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 32; ++a) bsum += v[a];
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_base + 48 + 8 * sr);          // raw chunk read
+        mbar_arrive(bar_base + 64 + 8 * sg);          // G (hi, lo) of this chunk is in tensor memory
+      }
+    }
+    if (n_ok) p.wsb[(int64_t)chunk * p.n + n0 + nl] = bsum;
+  } else if (warp < 12) {
+    // ===================== [a1 | a2] converters: row-major chunk -> MN-major hi / lo tiles =====================
+    const int pw = warp - 4;
+    const int la = lane >> 3, lc = lane & 7;
+    const int k = 4 * pw + la;                    // atom inside the chunk = K index
+    const uint32_t k_off = (uint32_t)((k >> 2) * (NB * 2048) + (k & 3) * 128 + (((lc >> 1) ^ (k & 3)) << 5) + (lc & 1) * 16);
+    for (int c = 0; c < steps; ++c) {
+      const int sr = c % WG3_RAW_STAGES, sb = c % WG3_B_STAGES;
+      mbar_wait(bar_base + 32 + 8 * sr, (c / WG3_RAW_STAGES) & 1);
+      const bool live = r_begin + (int64_t)c * TC_BK + k < r_end;
+      const uint8_t* rs = raw_ptr + sr * RAW_STAGE_BYTES + k * 512;
+      float4 r[NLB];
+#pragma unroll
+      for (int j = 0; j < NLB; ++j) {
+        const int m = 32 * j + 4 * lc;              // feature of the tile: a1 below k1, a2 from there
+        const uint8_t* src = m < p.k1 ? rs + 4 * m : rs + WG3_RAW_TILE + 4 * (m - p.k1);
+        r[j] = (live && m < Kt) ? *reinterpret_cast<const float4*>(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      mbar_wait(bar_base + 16 + 8 * sb, ((c / WG3_B_STAGES) & 1) ^ 1);             // the MMAs that read this stage retired
+      uint8_t* hi_t = sm + sb * STAGE_BYTES + k_off;
+      uint8_t* lo_t = hi_t + B_TILE_BYTES;
+#pragma unroll
+      for (int j = 0; j < NLB; ++j) {
+        if (NT == 3) {
+          float4 hi, lo;
+          split4(r[j], hi, lo);
+          *reinterpret_cast<float4*>(hi_t + j * 512) = hi;
+          if (!p.a_exact) *reinterpret_cast<float4*>(lo_t + j * 512) = lo;
+        } else {
+          *reinterpret_cast<float4*>(hi_t + j * 512) = round4_bf16(r[j]);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_base + 48 + 8 * sr);
+        mbar_arrive(bar_base + 8 * sb);
+      }
+      if (wdbg && tid == 128 && c < 1000) p.dbg[c] = clock64();
+    }
+  } else if (lane == 0) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)((NB * TC_BN) >> 3) << 17) |
+                               ((uint32_t)(TC_BM >> 4) << 24);
+    for (int c = 0; c < steps; ++c) {
+      const int sb = c % WG3_B_STAGES, sg = c % WG2_G_STAGES;
+      mbar_wait(bar_base + 8 * sb, (c / WG3_B_STAGES) & 1);
+      mbar_wait(bar_base + 64 + 8 * sg, (c / WG2_G_STAGES) & 1);
+      tc_fence_after();
+      if (wdbg && c < 1000) p.dbg[3072 + c] = clock64();
+      const uint32_t b_hi = base + sb * STAGE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+      const uint32_t g_hi = tmem + V4_A_COL0 + (uint32_t)sg * 64u, g_lo = g_hi + 32u;
+#pragma unroll
+      for (int k = 0; k < TC_BK / TC_UK; ++k) {
+        const uint32_t ko = (uint32_t)k * (2u * NB * 2048u);
+        const uint64_t bhi = make_desc_mn_nb(b_hi + ko, NB), blo = make_desc_mn_nb(b_lo + ko, NB);
+        if (NT == 3) {
+          umma_tf32_ts(tmem, g_lo + k * TC_UK, bhi, idesc, (c | k) != 0);
+          if (!p.a_exact) umma_tf32_ts(tmem, g_hi + k * TC_UK, blo, idesc, 1);
+          umma_tf32_ts(tmem, g_hi + k * TC_UK, bhi, idesc, 1);
+        } else {
+          umma_tf32_ts(tmem, g_hi + k * TC_UK, bhi, idesc, (c | k) != 0);
+        }
+      }
+      umma_commit(bar_base + 16 + 8 * sb);
+      umma_commit(bar_base + 96 + 8 * sg);
+    }
+    umma_commit(bar_base + 128);
+  }
+  if (warp < 12) {
+    // ===================== epilogue (as v2): D[lane = channel, column = feature] -> ws[chunk][feature][channel] =====
+    const int qd = warp & 3, third = warp >> 2;
+    const int n = n0 + 32 * qd + lane;
+    const bool n_ok = n < p.n;
+    if (wdbg && tid == 0) p.dbg[4096] = clock64();
+    if (steps > 0) {
+      mbar_wait(bar_base + 128, 0);
+      tc_fence_after();
+    }
+    if (wdbg && tid == 0) p.dbg[4097] = clock64();
+    float* dst = p.ws + ((int64_t)chunk * Kt) * p.n + n;
+#pragma unroll 1
+    for (int cb = 32 * third; cb < NB * TC_BM; cb += 96) {
+      if (cb >= Kt) break;
+      uint32_t v[32];
+      if (steps > 0) {
+        tmem_ld32(tmem + ((uint32_t)(32 * qd) << 16) + cb, v);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = 0u;
+      }
+      if (n_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          if (cb + i < Kt) dst[(int64_t)(cb + i) * p.n] = __uint_as_float(v[i]);
+      }
+    }
+    if (wdbg && tid == 0) p.dbg[4098] = clock64();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (p.dbg != nullptr && tid == 0 && blockIdx.y == 0 && blockIdx.x < 512) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.dbg[6001 + 4 * blockIdx.x] = (long long)gt;
+  }
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Debugging aid (not part of the ABI): the issue rate of tcgen05.mma in the forms the kernels above use.
 // One warp of one CTA per SM issues `reps` back-to-back MMAs of one variant over zero-filled operands, commits, waits,
 // and reports clock64() cycles per MMA.  variant bits: 0 = A from TMEM (TS) instead of shared memory (SS);
@@ -1858,6 +2108,10 @@ int ensure_smem_attr() {
                                         V5Cfg<3>::kSmemBytes));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v5<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         V5Cfg<1>::kSmemBytes));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v3<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v3<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v3<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v3<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v2<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v2<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v2<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -2064,6 +2318,30 @@ int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p_in, int chunks, cudaStre
   // NT = 3: 2 stages x (hi, lo) x (mt + 1) tiles; NT = 1: 4 stages x (mt + 1) tiles — the same bytes
   // DCGC_WGRAD_V1=1: the first kernel (features as M, N = 128), kept for A/B measurements
   static const bool use_v1 = [] { const char* e = getenv("DCGC_WGRAD_V1"); return e && e[0] == '1'; }();
+  // v3 (TMA-fed) where its layout conditions hold; DCGC_WGRAD_V2=1 forces the register-fed kernel (A/B measurements)
+  static const bool use_v2 = [] { const char* e = getenv("DCGC_WGRAD_V2"); return e && e[0] == '1'; }();
+  const bool v3_ok = !use_v1 && !use_v2 && p.a1_vec && (p.k2 == 0 || p.a2_vec) && p.g_vec && (p.k1 & 3) == 0 &&
+                     (p.k2 & 3) == 0 && p.k1 <= 128 && p.k2 <= 128 && m_pairs == 1 && p.group_row0[p.n_groups] < (1ll << 31);
+  if (v3_ok) {
+    const int64_t rows_total = p.group_row0[p.n_groups];
+    alignas(64) CUtensorMap m1, m2, mg;
+    st_ = make_a_map(&m1, p.a1, rows_total, p.k1, p.ld_a1, 128, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (st_ == DCGC_OK)
+      st_ = p.k2 > 0 ? make_a_map(&m2, p.a2, rows_total, p.k2, p.ld_a2, 128, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE)
+                     : make_a_map(&m2, p.a1, rows_total, p.k1, p.ld_a1, 128, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (st_ == DCGC_OK) st_ = make_a_map(&mg, p.g, rows_total, p.n, p.ld_g, 128, TC_BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (st_ != DCGC_OK) return st_;
+    const int smem3 = WG3_B_STAGES * (nt == 3 ? 2 : 1) * mt * TC_TILE_BYTES + WG3_RAW_STAGES * 3 * WG3_RAW_TILE + 1024 + 256;
+    if (nt == 3) {
+      if (mt == 2) tc_wgrad_kernel_v3<2, 3><<<grid, WG3_THREADS, smem3, st>>>(p, m1, m2, mg);
+      else tc_wgrad_kernel_v3<1, 3><<<grid, WG3_THREADS, smem3, st>>>(p, m1, m2, mg);
+    } else {
+      if (mt == 2) tc_wgrad_kernel_v3<2, 1><<<grid, WG3_THREADS, smem3, st>>>(p, m1, m2, mg);
+      else tc_wgrad_kernel_v3<1, 1><<<grid, WG3_THREADS, smem3, st>>>(p, m1, m2, mg);
+    }
+    DCGC_CUDA_LAUNCH_CHECK("tc_wgrad_kernel_v3");
+    return DCGC_OK;
+  }
   if (!use_v1) {
     const int smem2 = WG2_B_STAGES * (nt == 3 ? 2 : 1) * mt * TC_TILE_BYTES + 1024 + 256;
     if (nt == 3) {

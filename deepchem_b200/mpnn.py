@@ -241,8 +241,10 @@ class EdgeNetwork(nn.Module):
 
     def _pair_csr(self, atom_to_pair, dev):
         """Pairs grouped by destination (host, cached per index tensor): (pair_ptr, pair_id, pair_src, n_dst)."""
-        key = (id(atom_to_pair), getattr(atom_to_pair, "_version", 0))
-        if self._pairs[0] == key:
+        # cached per index OBJECT (MessagePassing calls the layer T times with the same one); the cache keeps a reference
+        # to it, so its id cannot be handed to another array while the entry lives
+        key = (atom_to_pair, getattr(atom_to_pair, "_version", 0))
+        if self._pairs[0] is not None and self._pairs[0][0] is atom_to_pair and self._pairs[0][1] == key[1]:
             return self._pairs[1]
         a2p = atom_to_pair.detach().cpu().numpy() if torch.is_tensor(atom_to_pair) else np.asarray(atom_to_pair)
         if a2p.ndim != 2 or a2p.shape[1] != 2:
