@@ -2087,6 +2087,67 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int variant, int reps,
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// The same measurement for CTA PAIRS (cta_group::2, a cluster of two CTAs on one TPC): M = 256 (128 rows per CTA),
+// one thread of the leader CTA issues for both.  variant bits as above (bit 0 TS form, bit 1 N = 256).
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma_rate2_kernel(int variant, int reps, long long* out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t bar = base + 196608;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + 196608 + 16);
+  for (int i = threadIdx.x; i < 196608 / 16; i += blockDim.x) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  fence_proxy_async();
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + 196608 + 16), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const bool ts = variant & 1, n256 = variant & 2;
+  const int nn = n256 ? 256 : 128;
+  const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(nn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  const bool leader = cluster_ctarank() == 0;
+  long long t0 = 0;
+  if (threadIdx.x == 0 && leader) {
+    t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      // per CTA: B = its half of the N columns (N / 2 rows of 128 bytes), the same offsets in both CTAs
+      const uint64_t bd = make_desc(base + 65536 + (r & 3) * 32);
+      if (ts) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                     ::"r"(tmem), "r"(tmem + (uint32_t)nn), "l"(bd), "r"(idesc), "r"(1) : "memory");
+      } else {
+        const uint64_t ad = make_desc(base + (r & 3) * 32);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(1) : "memory");
+      }
+    }
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+  }
+  if (threadIdx.x == 0) {
+    mbar_wait(bar, 0);
+    if (leader) out[blockIdx.x >> 1] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (threadIdx.x < 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 
@@ -2376,6 +2437,12 @@ extern "C" void dcgcdbg_tc_timeline(long long* dev_buf) { g_timeline = dev_buf; 
 // out_dev receives one int64 per CTA.
 extern "C" int dcgcdbg_mma_rate(int variant, int reps, int ctas, long long* out_dev, void* stream) {
   const int smem = 196608 + 1024 + 64;
+  if (variant & 32) {          // CTA pairs: `ctas` pairs, one int64 per pair
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    mma_rate2_kernel<<<2 * ctas, 128, smem, (cudaStream_t)stream>>>(variant, reps, out_dev);
+    DCGC_CUDA_LAUNCH_CHECK("mma_rate2_kernel");
+    return DCGC_OK;
+  }
   DCGC_CUDA_CALL(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   mma_rate_kernel<<<ctas, 128, smem, (cudaStream_t)stream>>>(variant, reps, out_dev);
   DCGC_CUDA_LAUNCH_CHECK("mma_rate_kernel");

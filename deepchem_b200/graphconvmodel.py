@@ -951,7 +951,18 @@ class GraphConvModel(object):
         if self._dp:
             from .parallel import world_size
             dp = world_size() > 1
-        overlap = dp and os.environ.get("DCGC_NO_OVERLAP", "0") != "1"     # =1: one all-reduce after the step (A/B)
+        # Per-slice exchange beside the backward pass, or ONE all-reduce after the step?  Measured (profiles/r5v_dp8.md):
+        # 2 GPUs 1.2151 against 1.2246 ms/step for the overlapped form, 8 GPUs 1.128 against 1.110 — NCCL's CTAs take
+        # SMs away from the persistent one-CTA-per-SM kernels of the backward pass (their displaced CTAs run as a tail),
+        # and four asynchronous calls per step cost the Python thread more than one.  Default: overlap on 2 ranks,
+        # one all-reduce above; DCGC_NO_OVERLAP=1 / DCGC_OVERLAP=1 force either.
+        if os.environ.get("DCGC_NO_OVERLAP", "0") == "1":
+            overlap = False
+        elif os.environ.get("DCGC_OVERLAP", "0") == "1":
+            overlap = dp
+        else:
+            from .parallel import world_size as _ws_
+            overlap = dp and _ws_() <= 2
         gev = self._dp_events() if overlap else None
         loss = eng.train_step(topo, inputs[0], labels[0].contiguous(), w.contiguous() if w is not None else None,
                               int(inputs[3]), forward_event=fe, grad_events=gev)

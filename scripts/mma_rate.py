@@ -33,3 +33,21 @@ for v in (0, 1, 2, 3, 4, 5, 8, 9, 12, 13, 16, 17, 18, 19):
     print("| %s | %s | %d | %d | %s | %.1f | %.1f |" % ("f16/bf16 K16" if v & 16 else "tf32 K8", "TMEM" if v & 1 else "smem",
                                                       256 if v & 2 else 128, 2 if v & 4 else 1,
                                                       "4 rotating" if v & 8 else "fixed", row[0], row[1]))
+
+print()
+print("| CTA pair (cta_group::2, M = 256) kind | A from | N | cycles / MMA (1 pair) | cycles / MMA (74 pairs, median) |")
+print("|---|---|---:|---:|---:|")
+for v in (32, 33, 34, 35):
+    row = []
+    for pairs in (1, 74):
+        best = None
+        for reps in (256, 1280):
+            for _ in range(3):
+                _lib.check(L.dcgcdbg_mma_rate(v, reps, pairs, ctypes.c_void_p(out.data_ptr()),
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                torch.cuda.synchronize()
+            tt = out[:pairs].cpu().double().median().item()
+            best = (reps, tt) if best is None else best + (reps, tt)
+        r1, t1, r2, t2 = best
+        row.append((t2 - t1) / (r2 - r1))
+    print("| tf32 K8 | %s | %d | %.1f | %.1f |" % ("TMEM" if v & 1 else "smem", 256 if v & 2 else 128, row[0], row[1]))
