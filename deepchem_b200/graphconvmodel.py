@@ -371,7 +371,10 @@ class _StagedResult(object):
 
     def _seal(self):
         if self.cur_recs:
-            ev = torch.cuda.Event()
+            # blocking=True: a host thread that waits on this event SLEEPS (cudaEventBlockingSync) instead of spinning on
+            # a core — with 4 cores per rank (8 ranks on a 32-core host) the spinning copier / prefetch threads starved
+            # the thread that launches the kernels (8 ms to issue one forward pass, profiles/r5w_host_threads.md)
+            ev = torch.cuda.Event(blocking=True)
             ev.record()
             self.todo.put((self.cur, ev, self.cur_recs))
             self.cur, self.cur_off, self.cur_recs = self.free.get(), 0, []
@@ -515,7 +518,7 @@ class _Prefetcher(object):
                     if fe is not None:
                         self.stream.wait_event(fe)                   # upload beside the backward pass
                     prepared = self.model._prepare_batch(batch, slot)
-                    ev = torch.cuda.Event()
+                    ev = torch.cuda.Event(blocking=True)
                     ev.record(self.stream)
                     slot.copied_event = ev
                 t3 = clock()
@@ -778,7 +781,7 @@ class GraphConvModel(object):
         topo = layout.to_device(self.device, buffer=buf, record_buffer=rec)
         sslot = getattr(layout, "_staging_slot", None)
         if sslot is not None:
-            sslot[1] = torch.cuda.Event()
+            sslot[1] = torch.cuda.Event(blocking=True)
             sslot[1].record(torch.cuda.current_stream())
         feats = getattr(inputs, "packed_features_i8_pinned", None) if (slot is not None and _USE_I8) else None
         if feats is None:
@@ -794,7 +797,7 @@ class GraphConvModel(object):
             x = ops.permute_rows(feats.to(self.device, non_blocking=True), topo.perm)
         fslots = getattr(inputs, "feature_staging_slots", None)
         if fslots:                             # the gathered features may be overwritten once this upload is done
-            fev = torch.cuda.Event()
+            fev = torch.cuda.Event(blocking=True)
             fev.record(torch.cuda.current_stream())
             for fs in fslots:
                 fs[1] = fev
@@ -889,7 +892,7 @@ class GraphConvModel(object):
             if batch_loss.is_cuda:
                 host = self._loss_ring[step % len(self._loss_ring)]
                 host.copy_(batch_loss.detach(), non_blocking=True)
-                ev = torch.cuda.Event()
+                ev = torch.cuda.Event(blocking=True)
                 ev.record()
             else:
                 host, ev = batch_loss.detach().clone(), _DoneEvent()
