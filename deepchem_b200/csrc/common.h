@@ -82,6 +82,17 @@ int dcgc_gather_bwd_stats(const float* dout, int64_t ld_dout, const float* out, 
                           const int32_t* membership, int64_t n_rows, int32_t width, int32_t act, float* dx,
                           int64_t ld_dx, const float* z, int64_t ld_z, int max_chunks, double* part,
                           int32_t* n_chunks_out, const DcgcBnFin* fin, void* stream);
+int dcgc_gather_fwd_train(const float* x, int64_t ld_x, const float* scale, const float* shift, const int32_t* mol_ptr,
+                          const int32_t* mol_atoms, int64_t n_segments, int32_t width, int32_t act, float* out,
+                          int64_t ld_out, int32_t* argrow, const float* mean, float* zc_sum, float* zc_arg,
+                          void* stream);
+int dcgc_dense_bn_sums(const float* dout, int64_t ld_dout, const float* out, int64_t ld_out, const int32_t* argrow,
+                       const int32_t* mol_ptr, int64_t n_segments, int32_t width, int32_t act, const float* zc_sum,
+                       const float* zc_arg, const float* mean, double* part, int32_t* n_chunks_out, void* stream);
+int dcgc_gather_bwd_apply(const float* dout, int64_t ld_dout, const float* out, int64_t ld_out, const int32_t* argrow,
+                          const int32_t* membership, int64_t n_rows, int32_t width, int32_t act, const float* z,
+                          int64_t ld_z, const float* mean, const float* invstd, const float* coef, float* g,
+                          int64_t ld_g, void* stream);
 int dcgc_mg_pool_bwd_stats_fin(const float* dy, int64_t ld_dy, const uint8_t* arg, int64_t ld_arg, const dcgc_topology* t,
                                int32_t width, float* dx, int64_t ld_dx, const float* y, int64_t ld_y, const float* stats,
                                double* part, int32_t* n_chunks, const DcgcBnFin* fin, void* stream);

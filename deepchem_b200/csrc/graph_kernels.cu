@@ -296,18 +296,24 @@ __global__ void __launch_bounds__(kThreads)
 gather_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ scale,
                   const float* __restrict__ shift, const int32_t* __restrict__ mol_ptr,
                   const int32_t* __restrict__ mol_atoms, int64_t n_seg, int groups, int width, int act,
-                  float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argrow) {
+                  float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argrow,
+                  const float* __restrict__ mean, float* __restrict__ zc_sum, float* __restrict__ zc_arg) {
+  // zc_sum / zc_arg (training with BatchNorm folded in, optional): per molecule the sum over its rows of the RAW input
+  // centred on the batch mean, and the centred raw value of the row that attains the max — what the BatchNorm backward
+  // of the layer in front needs to form its column sums at MOLECULE level (dense_bn_sums_kernel, model.cu)
   const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t g = t / groups;
   const int c = (int)(t - g * groups) * VEC;
   if (g >= n_seg || c >= width) return;
-  float s[VEC], m[VEC], sc[VEC], sh[VEC];
+  float s[VEC], m[VEC], sc[VEC], sh[VEC], mu[VEC], zs[VEC], za[VEC];
   int32_t a[VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
     s[v] = 0.f; m[v] = -INFINITY; a[v] = -1;
     sc[v] = scale ? __ldg(scale + c + v) : 1.f;
     sh[v] = scale ? __ldg(shift + c + v) : 0.f;
+    mu[v] = zc_sum ? __ldg(mean + c + v) : 0.f;
+    zs[v] = 0.f; za[v] = 0.f;
   }
   // Eight atoms at a time: their row indices, then their rows, are loaded as independent requests and only then added
   // in ascending row order (sum order and the lowest-row tie rule of the max are unchanged).  One atom per iteration
@@ -338,8 +344,16 @@ gather_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __rest
       for (int v = 0; v < VEC; ++v) {
         const float t2 = scale ? fmaf(u[i][v], sc[v], sh[v]) : u[i][v];
         s[v] += t2;
-        if (t2 > m[v] || a[v] < 0) { m[v] = t2; a[v] = r[i]; }
+        zs[v] += u[i][v] - mu[v];
+        if (t2 > m[v] || a[v] < 0) { m[v] = t2; a[v] = r[i]; za[v] = u[i][v] - mu[v]; }
       }
+    }
+  }
+  if (zc_sum) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      zc_sum[g * (int64_t)width + c + v] = zs[v];
+      zc_arg[g * (int64_t)width + c + v] = za[v];
     }
   }
 #pragma unroll
@@ -395,6 +409,114 @@ gather_bwd_vec_kernel(const float* __restrict__ dout, int64_t ld_dout, const flo
   *reinterpret_cast<float4*>(dx + row * ld_dx + c) = o;
 }
 
+constexpr int kGbRowLanes = 16;
+
+// GraphGather backward that writes the gradient of the layer BEHIND the BatchNorm + ReLU in front of it directly:
+//   dA = d sum + [row is the arg-max] d max      (as gather_bwd_vec_kernel),
+//   G  = relu'(z) * c1 * (dA - c2 - (z - mean) * invstd * c3)      (as bn_relu_bwd_apply)
+// with the per-column coefficients already known (dense_bn_sums_kernel + finalize): the separate apply pass over dA and
+// z (3 x N x width x 4 bytes) disappears.  Same walk as gather_bwd_stats_kernel: four rows in flight per thread.
+__global__ void __launch_bounds__(32 * kGbRowLanes, 2)
+gather_bwd_apply_kernel(const float* __restrict__ dout, int64_t ld_dout, const float* __restrict__ out, int64_t ld_out,
+                        const int32_t* __restrict__ argrow, const int32_t* __restrict__ membership, int64_t n_rows,
+                        int width, int act, const float* __restrict__ z, int64_t ld_z, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, const float* __restrict__ coef, float* __restrict__ g,
+                        int64_t ld_g, int64_t rows_per_chunk) {
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.y * 128 + 4 * cx;
+  if (c >= width) return;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
+  const int64_t r1 = min(n_rows, r0 + rows_per_chunk);
+  const float4 m = ldg4(mean + c), is = ldg4(invstd + c);
+  const float4 c1 = ldg4(coef + c), c2 = ldg4(coef + width + c), c3 = ldg4(coef + 2 * width + c);
+  for (int64_t rb = r0 + ry; rb < r1; rb += 4 * kGbRowLanes) {
+    int64_t mol[4];
+    float4 zv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t r = rb + (int64_t)u * kGbRowLanes;
+      mol[u] = r < r1 ? (int64_t)__ldg(membership + r) : -1;
+      zv[u] = r < r1 ? ldg4(z + r * ld_z + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (mol[u] < 0) continue;
+      const int r32 = (int)(rb + (int64_t)u * kGbRowLanes);
+      const float4 ds = ldg4(dout + mol[u] * ld_dout + c), os = ldg4(out + mol[u] * ld_out + c);
+      const float4 dm = ldg4(dout + mol[u] * ld_dout + width + c), om = ldg4(out + mol[u] * ld_out + width + c);
+      const int4 ar = __ldg(reinterpret_cast<const int4*>(argrow + mol[u] * (int64_t)width + c));
+      float4 o;
+      o.x = ds.x * act_grad_from_out(os.x, act) + (ar.x == r32 ? dm.x * act_grad_from_out(om.x, act) : 0.f);
+      o.y = ds.y * act_grad_from_out(os.y, act) + (ar.y == r32 ? dm.y * act_grad_from_out(om.y, act) : 0.f);
+      o.z = ds.z * act_grad_from_out(os.z, act) + (ar.z == r32 ? dm.z * act_grad_from_out(om.z, act) : 0.f);
+      o.w = ds.w * act_grad_from_out(os.w, act) + (ar.w == r32 ? dm.w * act_grad_from_out(om.w, act) : 0.f);
+      const float4 v = zv[u];
+      float4 q;
+      q.x = v.x > 0.f ? c1.x * (o.x - c2.x - (v.x - m.x) * is.x * c3.x) : 0.f;
+      q.y = v.y > 0.f ? c1.y * (o.y - c2.y - (v.y - m.y) * is.y * c3.y) : 0.f;
+      q.z = v.z > 0.f ? c1.z * (o.z - c2.z - (v.z - m.z) * is.z * c3.z) : 0.f;
+      q.w = v.w > 0.f ? c1.w * (o.w - c2.w - (v.w - m.w) * is.w * c3.w) : 0.f;
+      *reinterpret_cast<float4*>(g + (int64_t)r32 * ld_g + c) = q;
+    }
+  }
+}
+
+// Column sums of dA = GraphGather-backward(d fingerprint) WITHOUT forming dA: every atom of a molecule receives the
+// molecule's d sum and one atom per column its d max, so
+//   sum_r dA[r, c]             = sum_mol ( atoms(mol) * ds[mol, c] + dm[mol, c] )
+//   sum_r dA[r, c] (z - mean)  = sum_mol ( ds[mol, c] * zc_sum[mol, c] + dm[mol, c] * zc_arg[mol, c] )
+// (ds / dm = d fingerprint times the activation derivative; dm only where the molecule has atoms).  4096 molecules
+// instead of 102 k atoms.  Block = 32 columns x 8 molecule lanes over a chunk of 128 molecules; float64 sums, lanes
+// combined in order; one row of partials per chunk in the layout bn_bwd_finalize reads (part[1] = uncentred).
+constexpr int kDbsMols = 128;
+constexpr int kDbsLanes = 32;      // molecule lanes per block: 32 columns x 32 lanes = 1 024 threads, 4 molecules each
+__global__ void __launch_bounds__(32 * kDbsLanes)
+dense_bn_sums_kernel(const float* __restrict__ dout, int64_t ld_dout, const float* __restrict__ out, int64_t ld_out,
+                     const int32_t* __restrict__ argrow, const int32_t* __restrict__ mol_ptr, int64_t n_seg, int width,
+                     int act, const float* __restrict__ zc_sum, const float* __restrict__ zc_arg,
+                     const float* __restrict__ mean, double* __restrict__ part) {
+  const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + cx;
+  const int64_t m0 = (int64_t)blockIdx.x * kDbsMols, m1 = min(n_seg, m0 + kDbsMols);
+  double a = 0.0, b = 0.0;
+  if (c < width) {
+    // every load of the thread's four molecules is issued before the first use (the first version walked 16 molecules
+    // per thread with two dependent round trips each: 31 us for a 20 MB problem)
+    constexpr int U = kDbsMols / kDbsLanes;
+    int cnt[U], ar[U];
+    float d0[U], o0[U], d1[U], o1[U], zs[U], za[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t mol = m0 + ly + (int64_t)u * kDbsLanes;
+      const bool ok = mol < m1;
+      const int64_t mm = ok ? mol : m0;
+      cnt[u] = ok ? __ldg(mol_ptr + mm + 1) - __ldg(mol_ptr + mm) : 0;
+      ar[u] = __ldg(argrow + mm * (int64_t)width + c);
+      d0[u] = __ldg(dout + mm * ld_dout + c); o0[u] = __ldg(out + mm * ld_out + c);
+      d1[u] = __ldg(dout + mm * ld_dout + width + c); o1[u] = __ldg(out + mm * ld_out + width + c);
+      zs[u] = __ldg(zc_sum + mm * (int64_t)width + c); za[u] = __ldg(zc_arg + mm * (int64_t)width + c);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (cnt[u] <= 0) continue;
+      const float ds = d0[u] * act_grad_from_out(o0[u], act);
+      const float dm = ar[u] >= 0 ? d1[u] * act_grad_from_out(o1[u], act) : 0.f;
+      a += (double)cnt[u] * (double)ds + (double)dm;
+      b += (double)ds * (double)zs[u] + (double)dm * (double)za[u];
+    }
+  }
+  __shared__ double sh[2][kDbsLanes][32];
+  sh[0][ly][cx] = a; sh[1][ly][cx] = b;
+  __syncthreads();
+  if (ly == 0 && c < width) {
+    double sa = 0.0, sb = 0.0;
+#pragma unroll
+    for (int l = 0; l < kDbsLanes; ++l) { sa += sh[0][l][cx]; sb += sh[1][l][cx]; }
+    part[((int64_t)blockIdx.x * 2) * width + c] = sa;
+    part[((int64_t)blockIdx.x * 2 + 1) * width + c] = sb + (double)__ldg(mean + c) * sa;
+  }
+}
+
 // GraphGather backward with the BatchNorm-backward column sums of its result fused in: besides dx it emits, per block,
 // sum_r dx[r, c] and sum_r dx[r, c] * z[r, c] (z = the BatchNorm input of the same rows) — what a separate
 // two-tensor pass over dx and z (col_moments_partial: 2 x N x width x 4 bytes, 25 us at the bench shape) computed.
@@ -402,7 +524,6 @@ gather_bwd_vec_kernel(const float* __restrict__ dout, int64_t ld_dout, const flo
 // in flight per thread (the one-row-per-thread kernel above sits at 0.35 of the HBM peak: five dependent loads and
 // no second row to overlap them with).  fp32 partial sums over four rows, float64 from there on, the 16 row lanes
 // combined in lane order through shared memory: deterministic.  part: [blocks][2][width] doubles.
-constexpr int kGbRowLanes = 16;
 __global__ void __launch_bounds__(32 * kGbRowLanes, 2)
 gather_bwd_stats_kernel(const float* __restrict__ dout, int64_t ld_dout, const float* __restrict__ out, int64_t ld_out,
                         const int32_t* __restrict__ argrow, const int32_t* __restrict__ membership, int64_t n_rows,
@@ -629,6 +750,18 @@ extern "C" int dcgc_gather_fwd(const float* x, int64_t ld_x, const float* scale,
                                const int32_t* mol_ptr, const int32_t* mol_atoms, int64_t n_segments,
                                int32_t width, int32_t act, float* out, int64_t ld_out, int32_t* argrow,
                                void* stream) {
+  return dcgc_gather_fwd_train(x, ld_x, scale, shift, mol_ptr, mol_atoms, n_segments, width, act, out, ld_out, argrow,
+                               nullptr, nullptr, nullptr, stream);
+}
+
+// dcgc_gather_fwd that also writes the centred raw per-molecule sum / arg-max value (see gather_fwd_kernel); fused
+// engine only, declared in common.h
+int dcgc_gather_fwd_train(const float* x, int64_t ld_x, const float* scale, const float* shift, const int32_t* mol_ptr,
+                          const int32_t* mol_atoms, int64_t n_segments, int32_t width, int32_t act, float* out,
+                          int64_t ld_out, int32_t* argrow, const float* mean, float* zc_sum, float* zc_arg,
+                          void* stream) {
+  DCGC_CHECK_ARG((zc_sum == nullptr) == (zc_arg == nullptr) && (zc_sum == nullptr || (mean && argrow)),
+                 "dcgc_gather_fwd_train: zc_sum, zc_arg, mean and argrow go together");
   DCGC_CHECK_ARG((scale == nullptr) == (shift == nullptr), "dcgc_gather_fwd: scale and shift go together");
   DCGC_CHECK_ARG(n_segments >= 0 && width >= 0 && ld_x >= width && ld_out >= 2 * (int64_t)width,
                  "dcgc_gather_fwd: bad sizes");
@@ -642,7 +775,8 @@ extern "C" int dcgc_gather_fwd(const float* x, int64_t ld_x, const float* scale,
   cudaStream_t st = (cudaStream_t)stream;
 #define DCGC_GATHER_LAUNCH(V, R)                                                                    \
   gather_fwd_kernel<V, R><<<grid, kThreads, 0, st>>>(x, ld_x, scale, shift, mol_ptr, mol_atoms,      \
-                                                     n_segments, groups, width, act, out, ld_out, argrow)
+                                                     n_segments, groups, width, act, out, ld_out, argrow, mean,  \
+                                                     zc_sum, zc_arg)
   if (v4) { if (argrow) DCGC_GATHER_LAUNCH(4, true); else DCGC_GATHER_LAUNCH(4, false); }
   else { if (argrow) DCGC_GATHER_LAUNCH(1, true); else DCGC_GATHER_LAUNCH(1, false); }
 #undef DCGC_GATHER_LAUNCH
@@ -697,5 +831,46 @@ int dcgc_gather_bwd_stats(const float* dout, int64_t ld_dout, const float* out, 
       fin ? *fin : DcgcBnFin{});
   DCGC_CUDA_LAUNCH_CHECK("dcgc_gather_bwd_stats");
   *n_chunks_out = (int32_t)chunks;
+  return DCGC_OK;
+}
+
+// Fused-engine pair for the dense layer's BatchNorm + ReLU backward (declared in common.h, not part of the ABI):
+// dcgc_dense_bn_sums writes the column-sum partials at molecule level (*n_chunks_out rows), dcgc_gather_bwd_apply writes
+// G = relu'(z) * BatchNorm-backward(GraphGather-backward(d fingerprint)) given the finalized coefficients.
+int dcgc_dense_bn_sums(const float* dout, int64_t ld_dout, const float* out, int64_t ld_out, const int32_t* argrow,
+                       const int32_t* mol_ptr, int64_t n_segments, int32_t width, int32_t act, const float* zc_sum,
+                       const float* zc_arg, const float* mean, double* part, int32_t* n_chunks_out, void* stream) {
+  DCGC_CHECK_ARG(n_segments > 0 && width > 0 && dout && out && argrow && mol_ptr && zc_sum && zc_arg && mean && part &&
+                     n_chunks_out, "dcgc_dense_bn_sums: bad arguments");
+  DcgcProfScope prof_scope("bn_stats_bwd", (cudaStream_t)stream);
+  const int64_t chunks = (n_segments + kDbsMols - 1) / kDbsMols;
+  dim3 grid((unsigned)chunks, (unsigned)((width + 31) / 32));
+  dense_bn_sums_kernel<<<grid, 32 * kDbsLanes, 0, (cudaStream_t)stream>>>(dout, ld_dout, out, ld_out, argrow, mol_ptr, n_segments, width,
+                                                             act, zc_sum, zc_arg, mean, part);
+  DCGC_CUDA_LAUNCH_CHECK("dcgc_dense_bn_sums");
+  *n_chunks_out = (int32_t)chunks;
+  return DCGC_OK;
+}
+
+int dcgc_gather_bwd_apply(const float* dout, int64_t ld_dout, const float* out, int64_t ld_out, const int32_t* argrow,
+                          const int32_t* membership, int64_t n_rows, int32_t width, int32_t act, const float* z,
+                          int64_t ld_z, const float* mean, const float* invstd, const float* coef, float* g,
+                          int64_t ld_g, void* stream) {
+  DCGC_CHECK_ARG(n_rows > 0 && width > 0 && dout && out && argrow && membership && z && mean && invstd && coef && g,
+                 "dcgc_gather_bwd_apply: bad arguments");
+  DCGC_CHECK_ARG(width % 4 == 0 && ld_dout % 4 == 0 && ld_out % 4 == 0 && ld_g % 4 == 0 && ld_z % 4 == 0 &&
+                     aligned16(dout) && aligned16(out) && aligned16(g) && aligned16(argrow) && aligned16(z) &&
+                     aligned16(mean) && aligned16(invstd) && aligned16(coef),
+                 "dcgc_gather_bwd_apply: rows must be 16-byte aligned");
+  DcgcProfScope prof_scope("dcgc_gather_bwd", (cudaStream_t)stream);
+  int64_t chunks = (n_rows + 127) / 128;
+  if (chunks > 592) chunks = 592;                  // four waves of one block per SM at most; each walks a row range
+  int64_t rows = (n_rows + chunks - 1) / chunks;
+  rows = (rows + kGbRowLanes - 1) / kGbRowLanes * kGbRowLanes;
+  chunks = (n_rows + rows - 1) / rows;
+  dim3 grid((unsigned)chunks, (unsigned)((width + 127) / 128));
+  gather_bwd_apply_kernel<<<grid, 32 * kGbRowLanes, 0, (cudaStream_t)stream>>>(
+      dout, ld_dout, out, ld_out, argrow, membership, n_rows, width, act, z, ld_z, mean, invstd, coef, g, ld_g, rows);
+  DCGC_CUDA_LAUNCH_CHECK("dcgc_gather_bwd_apply");
   return DCGC_OK;
 }

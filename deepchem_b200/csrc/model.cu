@@ -100,37 +100,36 @@ col_moments_partial(const float* __restrict__ a, int64_t ld_a, const float* __re
   }
 }
 
-// Sum of the stage-1 partials.  Block = 16 columns (x) x 32 chunk lanes (y): chunk lane y owns chunks
-// y, y+32, ... (at most kPartPerLane, all loads issued before the first add: one memory latency instead of
-// one per chunk), then the 32 lanes are combined in lane order through shared memory (deterministic).
+// Sum of the stage-1 partials.  One WARP per column (8 columns per 256-thread block, so 16 blocks at width 128 instead
+// of the 8 blocks of 16 columns x 32 chunk lanes this replaced: the kernel is pure latency, 5.6 us in the launch list):
+// lane l owns chunks l, l + 32, ... with all its loads issued before the first add (one memory latency), then the 32
+// lane sums are combined by a fixed butterfly of double shuffles — deterministic, no shared memory, no block barrier.
+constexpr int kFinCols = 8;        // columns (= warps) per block
 constexpr int kPartPerLane = 10;   // covers 320 chunks; more are handled by the strided loop below
 __device__ __forceinline__ bool reduce_partials(const double* __restrict__ part, int n_chunks, int width,
                                                 double& s, double& ss, int& c_out) {
-  __shared__ double sh[2][32][17];
-  const int cx = threadIdx.x & 15, ky = threadIdx.x >> 4;
-  const int c = blockIdx.x * 16 + cx;
-  const int cc = c < width ? c : width - 1;
+  const int lane = threadIdx.x & 31, c = blockIdx.x * kFinCols + (threadIdx.x >> 5);
+  if (c >= width) return false;              // (whole warps: the shuffles below stay converged)
   double va[kPartPerLane], vb[kPartPerLane];
 #pragma unroll
   for (int u = 0; u < kPartPerLane; ++u) {
-    const int k = ky + 32 * u;
-    va[u] = k < n_chunks ? part[((int64_t)k * 2) * width + cc] : 0.0;
-    vb[u] = k < n_chunks ? part[((int64_t)k * 2 + 1) * width + cc] : 0.0;
+    const int k = lane + 32 * u;
+    va[u] = k < n_chunks ? part[((int64_t)k * 2) * width + c] : 0.0;
+    vb[u] = k < n_chunks ? part[((int64_t)k * 2 + 1) * width + c] : 0.0;
   }
   double a = 0.0, b = 0.0;
 #pragma unroll
   for (int u = 0; u < kPartPerLane; ++u) { a += va[u]; b += vb[u]; }
-  for (int k = ky + 32 * kPartPerLane; k < n_chunks; k += 32) {
-    a += part[((int64_t)k * 2) * width + cc];
-    b += part[((int64_t)k * 2 + 1) * width + cc];
+  for (int k = lane + 32 * kPartPerLane; k < n_chunks; k += 32) {
+    a += part[((int64_t)k * 2) * width + c];
+    b += part[((int64_t)k * 2 + 1) * width + c];
   }
-  sh[0][ky][cx] = a;
-  sh[1][ky][cx] = b;
-  __syncthreads();
-  if (ky != 0 || c >= width) return false;
-  a = 0.0; b = 0.0;
 #pragma unroll
-  for (int l = 0; l < 32; ++l) { a += sh[0][l][cx]; b += sh[1][l][cx]; }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (lane != 0) return false;
   s = a; ss = b; c_out = c;
   return true;
 }
@@ -138,7 +137,7 @@ __device__ __forceinline__ bool reduce_partials(const double* __restrict__ part,
 // BatchNorm forward finalize: batch statistics -> folded scale/shift, running-stat update.
 // torch semantics (graphconvmodel.py:150-158: eps=1e-3, momentum=0.99 meaning new-stat weight):
 //   normalise with the biased batch variance; running_var uses the unbiased one.
-__global__ void __launch_bounds__(512) bn_fwd_finalize(const double* __restrict__ part, int n_chunks, int width, int64_t n_rows,
+__global__ void __launch_bounds__(32 * kFinCols) bn_fwd_finalize(const double* __restrict__ part, int n_chunks, int width, int64_t n_rows,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                 float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                 float* __restrict__ mean_out, float* __restrict__ invstd_out,
@@ -178,7 +177,7 @@ __global__ void bn_eval_fold(const float* __restrict__ gamma, const float* __res
 
 // BatchNorm backward finalize: dgamma, dbeta and the three per-channel coefficients of
 //   dY = c1 * (dA - mean_dA - xhat * mean_dAx),  xhat = (Y - mean) * invstd
-__global__ void __launch_bounds__(512) bn_bwd_finalize(const double* __restrict__ part, int n_chunks, int width, int64_t n_rows,
+__global__ void __launch_bounds__(32 * kFinCols) bn_bwd_finalize(const double* __restrict__ part, int n_chunks, int width, int64_t n_rows,
                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                 const float* __restrict__ scale, float* __restrict__ dgamma,
                                 float* __restrict__ dbeta, float* __restrict__ coef /* [3, width] */) {
@@ -805,6 +804,8 @@ struct Saved {
   float* stats;    // per BN: mean, invstd, scale, shift (4 * width each)
   int64_t stats_off[DCGC_MODEL_MAX_LAYERS + 1];
   float* fp;       // fingerprint [n_seg, 2D]
+  float* zc_sum;   // training + BatchNorm: per molecule, sum over its rows of (z - batch mean) and the same for the
+  float* zc_arg;   // arg-max row, [n_seg, D] each (dcgc_gather_fwd_train) — for the molecule-level BatchNorm-backward sums
   int32_t* argrow;
   float* out;      // [n_samples, n_out]
   float* b11[DCGC_MODEL_MAX_LAYERS];
@@ -942,7 +943,7 @@ int bn_forward(const dcgc_gcmodel_config* cfg, const Layout& lo, int idx, const 
       DCGC_CUDA_LAUNCH_CHECK("bn_sync_kernel (forward)");
       return DCGC_OK;
     }
-    bn_fwd_finalize<<<(width + 15) / 16, 512, 0, st>>>(sv.part, chunks, width, n, gamma, beta, cfg->bn_eps,
+    bn_fwd_finalize<<<(width + kFinCols - 1) / kFinCols, 32 * kFinCols, 0, st>>>(sv.part, chunks, width, n, gamma, beta, cfg->bn_eps,
                                                        cfg->bn_momentum, rm, rv, mean, invstd, scale, shift);
     DCGC_CUDA_LAUNCH_CHECK("bn_fwd_finalize");
   } else {
@@ -981,6 +982,9 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
   sv.z = ws.take<float>(N * D);
   sv.fp = ws.take<float>(S * 2 * D);
   sv.argrow = keep_arg ? ws.take<int32_t>(S * D) : nullptr;
+  const bool want_zc = keep_arg && training && cfg->batch_norm && S > 0 && N > 0 && (S + 127) / 128 <= part_chunks(N);
+  sv.zc_sum = want_zc ? ws.take<float>(S * D) : nullptr;
+  sv.zc_arg = want_zc ? ws.take<float>(S * D) : nullptr;
   sv.out = ws.take<float>((n_samples > 0 ? n_samples : 1) * cfg->n_out);
   if (!ws.ok) {
     dcgc_set_error("dcgc_gcmodel: workspace too small (%lld bytes needed so far, %lld given)", (long long)ws.off,
@@ -1049,8 +1053,8 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
     scale = sv.stats + sv.stats_off[L] + 2 * D;
     shift = scale + D;
   }
-  RET_IF(dcgc_gather_fwd(sv.z, D, scale, shift, t->mol_ptr, t->mol_atoms, S, D, DCGC_ACT_TANH, sv.fp, 2 * D,
-                         sv.argrow, st));
+  RET_IF(dcgc_gather_fwd_train(sv.z, D, scale, shift, t->mol_ptr, t->mol_atoms, S, D, DCGC_ACT_TANH, sv.fp, 2 * D,
+                               sv.argrow, sv.zc_sum ? sv.stats + sv.stats_off[L] : nullptr, sv.zc_sum, sv.zc_arg, st));
   if (n_samples > 0 && !skip_head) {
     head_fwd<<<blocks_for(n_samples * cfg->n_out * 32), kT, 0, st>>>(sv.fp, 2 * D, params + lo.head_w,
                                                                     params + lo.head_b, n_samples, 2 * D, cfg->n_out,
@@ -1101,7 +1105,7 @@ extern "C" int64_t dcgc_gcmodel_workspace_bytes(const dcgc_gcmodel_config* cfg, 
   for (int l = 0; l <= L; ++l) fmax = fmax > lo.fp[l] ? fmax : lo.fp[l];
   per_atom += 2 * (int64_t)wmax + 2 * (int64_t)fmax;  // backward scratch: dA, dP, d1, d2
   int64_t bytes = n_atoms * per_atom * 4;
-  bytes += n_segments * (int64_t)(2 * D * 2 + D) * 4;            // fp, dfp, argrow
+  bytes += n_segments * (int64_t)(2 * D * 2 + D + 2 * D) * 4;    // fp, dfp, argrow, zc_sum, zc_arg
   bytes += n_segments * (int64_t)cfg->n_out * 4 * 3;              // out, dout, per-element loss
   bytes += (int64_t)(part_chunks(n_atoms) + 1) * 2 * (int64_t)wmax * 8;
   bytes += ((n_segments + kHfRows - 1) / kHfRows + 1) * ((int64_t)cfg->n_out * (2 * D + 1) * 4 + 8) + 256;
@@ -1346,24 +1350,10 @@ extern "C" int dcgc_gcmodel_train_step_sync(const dcgc_gcmodel_config* cfg, cons
     f.dgamma = grads + lo.bn_g[idx]; f.dbeta = grads + lo.bn_b[idx]; f.coef = coef;
     return f;
   };
-  // ---- GraphGather backward -> dA (grad wrt the BN output of the dense layer)
-  // (with BatchNorm: the kernel also emits the BatchNorm-backward column sums of dA against z, one pass less)
-  int32_t fused_gather = -1;
-  DcgcBnFin fin_gather{};
-  if (cfg->batch_norm && N > 0 && D % 4 == 0 &&
-      ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(sv.z) | reinterpret_cast<uintptr_t>(dfp) |
-        reinterpret_cast<uintptr_t>(sv.fp) | reinterpret_cast<uintptr_t>(sv.argrow)) & 15) == 0)
-  {
-    fin_gather = bwd_fin(L, D);
-    RET_IF(dcgc_gather_bwd_stats(dfp, 2 * D, sv.fp, 2 * D, sv.argrow, t->membership, N, D, DCGC_ACT_TANH, dA, D, sv.z, D,
-                                 part_chunks(N), sv.part, &fused_gather, fin_gather.kind ? &fin_gather : nullptr, st));
-  }
-  else
-    RET_IF(dcgc_gather_bwd(dfp, 2 * D, sv.fp, 2 * D, sv.argrow, t->membership, N, D, DCGC_ACT_TANH, dA, D, st));
-
   // fused_chunks >= 0: the stage-1 partials were already written by the kernel that produced dA
   // (dcgc_mg_pool_bwd_stats), one row per CTA
-  auto bn_backward = [&](int idx, const float* yv, int width, int fused_chunks, bool finalized = false) -> int {
+  auto bn_backward = [&](int idx, const float* yv, int width, int fused_chunks, bool finalized = false,
+                         bool skip_apply = false) -> int {
     // dA (ld = width) -> G in place; dgamma / dbeta into the gradient slab
     if (cfg->batch_norm) {
       const float* stats = sv.stats + sv.stats_off[idx];
@@ -1384,12 +1374,13 @@ extern "C" int dcgc_gcmodel_train_step_sync(const dcgc_gcmodel_config* cfg, cons
             nullptr, grads + lo.bn_g[idx], grads + lo.bn_b[idx], coef);
         DCGC_CUDA_LAUNCH_CHECK("bn_sync_kernel (backward)");
       } else if (!(finalized && fused_chunks >= 0)) {
-        bn_bwd_finalize<<<(width + 15) / 16, 512, 0, st>>>(sv.part, fused_chunks >= 0 ? fused_chunks : (N > 0 ? sv.n_chunks : 0), width, N, stats,
+        bn_bwd_finalize<<<(width + kFinCols - 1) / kFinCols, 32 * kFinCols, 0, st>>>(sv.part, fused_chunks >= 0 ? fused_chunks : (N > 0 ? sv.n_chunks : 0), width, N, stats,
                                                              stats + width, stats + 2 * width, grads + lo.bn_g[idx],
                                                              grads + lo.bn_b[idx], coef);
         DCGC_CUDA_LAUNCH_CHECK("bn_bwd_finalize");
       }
       }
+      if (skip_apply) return DCGC_OK;     // the consumer applies the coefficients itself (dcgc_gather_bwd_apply)
       DcgcProfScope prof_scope("bn_relu_bwd_apply", st);
       if (N > 0) {
         const int groups = width / 4;
@@ -1406,8 +1397,41 @@ extern "C" int dcgc_gcmodel_train_step_sync(const dcgc_gcmodel_config* cfg, cons
     return DCGC_OK;
   };
 
+  // ---- GraphGather backward -> dA (grad wrt the BN output of the dense layer)
+  // With BatchNorm and the molecule-level sums of the forward pass: column sums from 4 096 molecules instead of 102 k
+  // atoms, finalize, then ONE kernel writes G = relu'(z) * BatchNorm-backward(dA) without dA ever being stored
+  // (DCGC_NO_DENSE_FUSION=1: the previous route, dA + sums in one kernel, then the apply pass).
+  static const bool no_dense_fusion = [] { const char* e = getenv("DCGC_NO_DENSE_FUSION"); return e && e[0] == '1'; }();
+  const bool al16 = ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(sv.z) | reinterpret_cast<uintptr_t>(dfp) |
+                      reinterpret_cast<uintptr_t>(sv.fp) | reinterpret_cast<uintptr_t>(sv.argrow) |
+                      reinterpret_cast<uintptr_t>(sv.stats + sv.stats_off[L]) | reinterpret_cast<uintptr_t>(coef)) & 15) == 0;
+  bool dense_done = false;
+  if (cfg->batch_norm && sv.zc_sum && !no_dense_fusion && D % 4 == 0 && al16 && N > 0 && S > 0) {
+    const float* stats_d = sv.stats + sv.stats_off[L];
+    int32_t ch = 0;
+    RET_IF(dcgc_dense_bn_sums(dfp, 2 * D, sv.fp, 2 * D, sv.argrow, t->mol_ptr, S, D, DCGC_ACT_TANH, sv.zc_sum, sv.zc_arg,
+                              stats_d, sv.part, &ch, st));
+    RET_IF(bn_backward(L, sv.z, D, ch, false, true));
+    RET_IF(dcgc_gather_bwd_apply(dfp, 2 * D, sv.fp, 2 * D, sv.argrow, t->membership, N, D, DCGC_ACT_TANH, sv.z, D, stats_d,
+                                 stats_d + D, coef, dA, D, st));
+    dense_done = true;
+  }
+  int32_t fused_gather = -1;
+  DcgcBnFin fin_gather{};
+  if (dense_done) {
+  } else if (cfg->batch_norm && N > 0 && D % 4 == 0 &&
+      ((reinterpret_cast<uintptr_t>(dA) | reinterpret_cast<uintptr_t>(sv.z) | reinterpret_cast<uintptr_t>(dfp) |
+        reinterpret_cast<uintptr_t>(sv.fp) | reinterpret_cast<uintptr_t>(sv.argrow)) & 15) == 0)
+  {
+    fin_gather = bwd_fin(L, D);
+    RET_IF(dcgc_gather_bwd_stats(dfp, 2 * D, sv.fp, 2 * D, sv.argrow, t->membership, N, D, DCGC_ACT_TANH, dA, D, sv.z, D,
+                                 part_chunks(N), sv.part, &fused_gather, fin_gather.kind ? &fin_gather : nullptr, st));
+  }
+  else
+    RET_IF(dcgc_gather_bwd(dfp, 2 * D, sv.fp, 2 * D, sv.argrow, t->membership, N, D, DCGC_ACT_TANH, dA, D, st));
+
   // ---- dense layer backward
-  RET_IF(bn_backward(L, sv.z, D, fused_gather, fin_gather.kind != 0));
+  if (!dense_done) RET_IF(bn_backward(L, sv.z, D, fused_gather, fin_gather.kind != 0));
   RET_IF(dcgc_linear_wgrad(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], dA, D, D, N, grads + lo.dense_w,
                            grads + lo.dense_b, wg, wg_bytes, st));
   RET_IF(slice_done(0));            // head, dense layer and its BatchNorm
