@@ -9,7 +9,7 @@
 //     (every bf16 value is exactly representable in the tf32 container the tile is stored in), the 2e-2 mode.
 //     Half the shared-memory tiles and a third of the MMAs of TF32X3; native 2-byte kind::f16 tiles would halve
 //     the tile bytes again and are the next step.
-// Kernels: tc_gemm_kernel_v3 (forward / dgrad / linear), tc_wgrad_kernel (weight gradient), tc_prep_image.
+// Kernels: tc_gemm_kernel_v5 / v4 (forward / dgrad / linear), tc_wgrad_kernel_v3 / v2 (weight gradient), tc_prep_image.
 #include <stdlib.h>
 
 #include <map>
@@ -27,8 +27,6 @@ constexpr int TC_BN = 128;        // columns per tile (UMMA N)
 constexpr int TC_BK = 32;         // fp32 elements per K chunk = one 128-byte swizzle row
 constexpr int TC_UK = 8;          // tf32 UMMA K
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;          // 16 KB
-constexpr int TC_PRODUCER_WARPS = 8;
-constexpr int TC_GROUP_THREADS = 128;                     // one producer group
 
 struct TcArgs {
   const float* a1; int64_t ld_a1; int k1;
@@ -99,21 +97,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
-// MN-major operand tile (the contiguous dimension of the data is M or N, not K).  For 32-bit (tf32) operands
-// the only layout the tensor core accepts is SWIZZLE_128B_BASE32B (CUTLASS: "for mn-major tf32 operands,
-// SW128_32B is the only available smem layout"): swizzle atoms of 4 K-rows x 128 bytes (32 fp32 along MN) in
-// which the 32-byte chunk index is XORed with the row index (Swizzle<2,5,2>); atoms repeat along MN every
-// LBO = 512 bytes and along K (groups of 4 rows) every SBO = 2048 bytes, i.e. a [32 K x 128 MN] chunk is laid
-// out as [K group of 4][MN atom][4 rows x 128 B]; one K = 8 MMA reads two K groups.
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (32ull << 16) | (128ull << 32) | (1ull << 46) | (1ull << 61);
-}
 // kind::tf32 instruction descriptor: D=f32, A=B=tf32, both K-major, N=128, M=128
 constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                                 ((uint32_t)(TC_BM >> 4) << 24);
-
-// same, both operands MN-major (bits 15 / 16): the tensor core transposes, the producers do not have to
-constexpr uint32_t kIdescTf32MN = kIdescTf32 | (1u << 15) | (1u << 16);
 
 __device__ __forceinline__ float tf32_hi(float x) {
   uint32_t r;
@@ -144,20 +130,6 @@ __device__ __forceinline__ uint32_t swz(int r, int c) {
   return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
 }
 
-__device__ __forceinline__ float4 ld4_masked(const float* p, int valid, bool vec) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (valid >= 4 && vec) return __ldg(reinterpret_cast<const float4*>(p));
-  if (valid > 0) v.x = __ldg(p);
-  if (valid > 1) v.y = __ldg(p + 1);
-  if (valid > 2) v.z = __ldg(p + 2);
-  if (valid > 3) v.w = __ldg(p + 3);
-  return v;
-}
-__device__ __forceinline__ float tc_act(float v, int act) {
-  if (act == DCGC_ACT_RELU) return v > 0.f ? v : 0.f;
-  if (act == DCGC_ACT_TANH) return tanhf(v);
-  return v;
-}
 
 __device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -173,38 +145,6 @@ __device__ __forceinline__ void tile_of(const TcArgs& p, int t, int& row0, int& 
 }
 
 
-// A [32 rows x 32 cols] accumulator block arrives from TMEM as (lane = row, v[0..31] = columns).  Storing it
-// directly makes every STG.128 touch 32 different 128-byte lines with 16 bytes each (ncu: 32 half-filled
-// sectors per request, 53 us of a 124 us GEMM).  Transposing through a padded per-warp staging tile gives
-// stores where 8 consecutive lanes cover one full 128-byte line.
-constexpr int EPI_LD = 36;                              // floats per staged row (conflict-free for 128-bit access)
-constexpr int EPI_WARP_FLOATS = 32 * EPI_LD;
-constexpr int EPI_BYTES = 4 * EPI_WARP_FLOATS * 4;      // four epilogue warps
-template <typename F>
-__device__ __forceinline__ void warp_transpose_store(float* stg, int lane, const uint32_t (&v)[32], F&& f,
-                                                     long long* ts = nullptr) {
-#pragma unroll
-  for (int i = 0; i < 32; i += 4)
-    *reinterpret_cast<float4*>(stg + lane * EPI_LD + i) =
-        make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-  __syncwarp();
-  if (ts) *ts = clock64();
-#pragma unroll
-  for (int i2 = 0; i2 < 8; ++i2) {
-    const int rr = i2 * 4 + (lane >> 3), cc = 4 * (lane & 7);
-    f(rr, cc, *reinterpret_cast<const float4*>(stg + rr * EPI_LD + cc));
-  }
-  __syncwarp();
-}
-
-constexpr int V3_THREADS = 14 * 32;
-// NT = 3: 3 stages x (A hi, A lo, B hi, B lo); NT = 1: 6 stages x (A, B); 192 KB either way
-template <int NT> struct V3Cfg {
-  static constexpr int kStages = NT == 3 ? 3 : 6;
-  static constexpr int kATiles = NT == 3 ? 2 : 1;
-  static constexpr int kStageBytes = 2 * kATiles * TC_TILE_BYTES;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + EPI_BYTES;
-};
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -267,297 +207,6 @@ struct TcArgs3 {
                   // 128 no weight-image kernel — results are wrong, timing only
 };
 
-template <int NT>
-__global__ void __launch_bounds__(V3_THREADS, 1) tc_gemm_kernel_v3(const TcArgs3 q) {
-  const TcArgs& p = q.a;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  constexpr int S = V3Cfg<NT>::kStages;
-  constexpr int V3_STAGE_BYTES = V3Cfg<NT>::kStageBytes;
-  constexpr int kATiles = V3Cfg<NT>::kATiles;               // A tiles per stage; the B tiles follow them
-  const uint32_t bar_base = base + S * V3_STAGE_BYTES;
-  // barriers: full[s] +8s, empty[s] +48+8s, tmem_full[a] +96+8a, tmem_empty[a] +112+8a, tmem slot +128
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + S * V3_STAGE_BYTES + 128);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int P = gridDim.x, pid = blockIdx.x;
-  const int n0 = blockIdx.y * TC_BN;
-  const int N = p.n1 + p.n2;
-  const int chunks1 = (p.k1 + TC_BK - 1) / TC_BK, chunks2 = (p.k2 + TC_BK - 1) / TC_BK;
-  const int total = chunks1 + chunks2;
-  const int my_tiles = pid < q.n_row_tiles ? (q.n_row_tiles - pid + P - 1) / P : 0;
-  const int n_cc = my_tiles * total;
-  const bool dbg_on = q.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && n_cc <= 1024;
-  if (dbg_on && tid == 0) q.dbg[5000] = clock64();
-
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(bar_base + 8 * s, 4 + 1);        // 4 producer warps of one group + the B loader
-      mbar_init(bar_base + 48 + 8 * s, 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(bar_base + 96 + 8 * a, 1);
-      mbar_init(bar_base + 112 + 8 * a, 128);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 12) tmem_alloc(bar_base + 128, 2 * TC_BN);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp >= 4 && warp < 12) {
-    // ===================== A producers =====================
-    const int ptid = tid - 128, group = ptid >> 7, gt = ptid & 127;
-    int c_it = -1, row0 = 0, rows = 0, gg = 0;
-    auto issue = [&](float4 (&r)[8], int cc) {
-      if (cc >= n_cc) return;
-      const int it = cc / total, ch = cc - it * total;
-      if (it != c_it) { tile_of(p, pid + it * P, row0, rows, gg); c_it = it; }
-      const float* src; int64_t ld; int ksrc, kbase; bool vec;
-      if (ch < chunks1) { src = p.a1; ld = p.ld_a1; ksrc = p.k1; kbase = ch * TC_BK; vec = p.a1_vec; }
-      else { src = p.a2; ld = p.ld_a2; ksrc = p.k2; kbase = (ch - chunks1) * TC_BK; vec = p.a2_vec; }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int f = gt + u * TC_GROUP_THREADS, r_ = f >> 3, k = kbase + 4 * (f & 7);
-        r[u] = (r_ < rows && !(q.knockout & 4)) ? ld4_masked(src + (int64_t)(row0 + r_) * ld + k, ksrc - k, vec)
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto commit = [&](const float4 (&r)[8], int cc) {
-      const int s = cc % S, use = cc / S;
-      mbar_wait(bar_base + 48 + 8 * s, (use & 1) ^ 1);
-      uint8_t* st = sm + s * V3_STAGE_BYTES;
-      if (!(q.knockout & 16)) {
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int f = gt + u * TC_GROUP_THREADS;
-          const uint32_t o = swz(f >> 3, f & 7);
-          if (NT == 3) {
-            float4 hi, lo;
-            split4(r[u], hi, lo);
-            *reinterpret_cast<float4*>(st + o) = hi;
-            *reinterpret_cast<float4*>(st + TC_TILE_BYTES + o) = lo;
-          } else {
-            *reinterpret_cast<float4*>(st + o) = round4_bf16(r[u]);
-          }
-        }
-      }
-      if (!(q.knockout & 64)) fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_base + 8 * s);
-      if (dbg_on && gt == 0) q.dbg[(group ? 1024 : 0) + (cc >> 1)] = clock64();
-    };
-    float4 ra[8], rb[8];
-    issue(ra, group);
-    for (int cc = group; cc < n_cc; cc += 4) {
-      issue(rb, cc + 2);
-      commit(ra, cc);
-      issue(ra, cc + 4);
-      if (cc + 2 < n_cc) commit(rb, cc + 2);
-    }
-  } else if (warp == 13) {
-    // ===================== B loader: one bulk copy per chunk =====================
-    if (lane == 0) {
-      int cc = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        int row0, rows, g;
-        tile_of(p, pid + it * P, row0, rows, g);
-        constexpr int kBFloats = kATiles * TC_BM * TC_BK;          // floats of one chunk of B (hi [+ lo])
-        constexpr uint32_t kBBytes = kATiles * TC_TILE_BYTES;
-        const float* src = q.img + ((int64_t)g * q.n_tiles_n + blockIdx.y) * total * kBFloats;
-        for (int ch = 0; ch < total; ++ch, ++cc) {
-          const int s = cc % S, use = cc / S;
-          mbar_wait(bar_base + 48 + 8 * s, (use & 1) ^ 1);
-          if (q.knockout & 8) { mbar_arrive(bar_base + 8 * s); continue; }
-          mbar_arrive_expect_tx(bar_base + 8 * s, kBBytes);
-          bulk_g2s(base + s * V3_STAGE_BYTES + kBBytes, src + (int64_t)ch * kBFloats, kBBytes, bar_base + 8 * s);
-          if (dbg_on) q.dbg[2048 + cc] = clock64();
-        }
-      }
-    }
-  } else if (warp == 12) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      int cc = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const int acc = it & 1;
-        mbar_wait(bar_base + 112 + 8 * acc, ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
-        tc_fence_after();
-        const uint32_t d = tmem + acc * TC_BN;
-        for (int ch = 0; ch < total; ++ch, ++cc) {
-          const int s = cc % S;
-          mbar_wait(bar_base + 8 * s, (cc / S) & 1);
-          tc_fence_after();
-          if (dbg_on) q.dbg[3072 + cc] = clock64();
-          const uint32_t sa = base + s * V3_STAGE_BYTES;
-          if (!(q.knockout & 2)) {
-#pragma unroll
-            for (int k = 0; k < TC_BK / TC_UK; ++k) {
-              const uint32_t ko = k * TC_UK * 4;
-              if (NT == 3) {
-                const uint64_t ahi = make_desc(sa + ko), alo = make_desc(sa + TC_TILE_BYTES + ko);
-                const uint64_t bhi = make_desc(sa + 2 * TC_TILE_BYTES + ko), blo = make_desc(sa + 3 * TC_TILE_BYTES + ko);
-                umma_tf32(d, alo, bhi, kIdescTf32, (ch | k) != 0);
-                umma_tf32(d, ahi, blo, kIdescTf32, 1);
-                umma_tf32(d, ahi, bhi, kIdescTf32, 1);
-              } else {
-                umma_tf32(d, make_desc(sa + ko), make_desc(sa + TC_TILE_BYTES + ko), kIdescTf32, (ch | k) != 0);
-              }
-            }
-          }
-          umma_commit(bar_base + 48 + 8 * s);
-        }
-        umma_commit(bar_base + 96 + 8 * acc);
-      }
-    }
-  } else {
-    // ===================== epilogue (warps 0-3) =====================
-    float* stg = reinterpret_cast<float*>(sm + S * V3_STAGE_BYTES + 256) + warp * EPI_WARP_FLOATS;
-    // fused BatchNorm statistics: this lane's column sums over the rows it stores (16 columns: 4 per 32-column
-    // block), fp32 over at most a few dozen rows, float64 from the cross-lane reduction on
-    // (four separate register sets, selected by a branch: one array indexed by the run-time block number
-    // was demoted to local memory by the compiler)
-    float su0[4] = {0.f, 0.f, 0.f, 0.f}, su1[4] = {0.f, 0.f, 0.f, 0.f}, su2[4] = {0.f, 0.f, 0.f, 0.f},
-          su3[4] = {0.f, 0.f, 0.f, 0.f};
-    float sq0[4] = {0.f, 0.f, 0.f, 0.f}, sq1[4] = {0.f, 0.f, 0.f, 0.f}, sq2[4] = {0.f, 0.f, 0.f, 0.f},
-          sq3[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int it = 0; it < my_tiles; ++it) {
-      int row0, rows, g;
-      tile_of(p, pid + it * P, row0, rows, g);
-      if (q.knockout & 1) rows = 0;
-      const int acc = it & 1;
-      if (total > 0) {
-        mbar_wait(bar_base + 96 + 8 * acc, (it >> 1) & 1);
-        tc_fence_after();
-      }
-      if (dbg_on && tid == 0) q.dbg[4096 + 2 * it] = clock64();
-      const float* bias = p.bias ? p.bias + (int64_t)g * p.bias_group_stride : nullptr;
-#pragma unroll 1   // (fully unrolled, the 32 copies of the store body overflowed the instruction cache: 2x slower)
-      for (int cb = 0; cb < TC_BN; cb += 32) {
-        uint32_t v[32];
-        float ts[4] = {0.f, 0.f, 0.f, 0.f}, tq[4] = {0.f, 0.f, 0.f, 0.f};
-        const bool dbg_cb = dbg_on && tid == 0 && it == 2;
-        if (dbg_cb) q.dbg[5100 + (cb >> 5) * 4 + 0] = clock64();
-        if (total > 0 && !(q.knockout & 32)) {
-          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + acc * TC_BN + cb, v);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
-        }
-        if (dbg_cb) q.dbg[5100 + (cb >> 5) * 4 + 1] = clock64();
-        const int c = n0 + cb + 4 * (lane & 7);       // the 4 columns this lane stores
-        float bv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (bias) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (c + e < N) bv[e] = __ldg(bias + c + e);
-        }
-        // Fast path (decided once per 32-column block, warp-uniform): the whole block lands in one output
-        // with 16-byte aligned rows and the activation is none / ReLU.  The general lambda below (column
-        // split, scalar tails, tanh) compiled to ~240 instructions per stored float4 and made the EPILOGUE the
-        // critical path of the kernel (timeline: 15 k cycles per tile against 9 k for the main loop).
-        const int cblk = n0 + cb;
-        const bool fast1 = p.c1_vec && cblk + 32 <= p.n1;
-        const bool fast2 = !fast1 && p.c2_vec && cblk >= p.n1 && cblk + 32 <= N && ((cblk - p.n1) & 3) == 0;
-        long long* tsp = dbg_cb ? q.dbg + 5100 + (cb >> 5) * 4 + 2 : nullptr;
-        if ((fast1 || fast2) && p.act != DCGC_ACT_TANH) {
-          const int64_t ld = fast1 ? p.ld_c1 : p.ld_c2;
-          float* dst = (fast1 ? p.c1 + c : p.c2 + (c - p.n1)) + (int64_t)(row0 + warp * 32) * ld;
-          const int nrows = rows - warp * 32;
-          const bool relu = p.act == DCGC_ACT_RELU;
-          warp_transpose_store(stg, lane, v, [&](int rr, int, float4 t) {
-            if (rr >= nrows) return;
-            t.x += bv[0]; t.y += bv[1]; t.z += bv[2]; t.w += bv[3];
-            if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
-            ts[0] += t.x; ts[1] += t.y; ts[2] += t.z; ts[3] += t.w;
-            tq[0] = fmaf(t.x, t.x, tq[0]); tq[1] = fmaf(t.y, t.y, tq[1]);
-            tq[2] = fmaf(t.z, t.z, tq[2]); tq[3] = fmaf(t.w, t.w, tq[3]);
-            *reinterpret_cast<float4*>(dst + (int64_t)rr * ld) = t;
-          }, tsp);
-        } else {
-        warp_transpose_store(stg, lane, v, [&](int rr, int, float4 t) {
-          const int row = warp * 32 + rr;
-          if (row >= rows || c >= N) return;
-          const int64_t grow = row0 + row;
-          const float o[4] = {tc_act(t.x + bv[0], p.act), tc_act(t.y + bv[1], p.act), tc_act(t.z + bv[2], p.act),
-                              tc_act(t.w + bv[3], p.act)};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { ts[e] += o[e]; tq[e] = fmaf(o[e], o[e], tq[e]); }
-          if (c + 3 < p.n1 && p.c1_vec) {
-            *reinterpret_cast<float4*>(p.c1 + grow * p.ld_c1 + c) = make_float4(o[0], o[1], o[2], o[3]);
-          } else if (c >= p.n1 && c + 3 < N && p.c2_vec && ((c - p.n1) & 3) == 0) {
-            *reinterpret_cast<float4*>(p.c2 + grow * p.ld_c2 + (c - p.n1)) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int cc2 = c + e;
-              if (cc2 < p.n1) { if (p.c1) p.c1[grow * p.ld_c1 + cc2] = o[e]; }
-              else if (cc2 < N) { if (p.c2) p.c2[grow * p.ld_c2 + (cc2 - p.n1)] = o[e]; }
-            }
-          }
-        }, tsp);
-        }
-        if (dbg_cb) q.dbg[5100 + (cb >> 5) * 4 + 3] = clock64();
-        // fold this block's sums into the statically indexed accumulators (cb is a run-time value here)
-#define DCGC_FOLD(SU, SQ)                                  \
-  {                                                        \
-    _Pragma("unroll") for (int e = 0; e < 4; ++e) {        \
-      SU[e] += ts[e];                                      \
-      SQ[e] += tq[e];                                      \
-    }                                                      \
-  }
-        if (cb == 0) DCGC_FOLD(su0, sq0)
-        else if (cb == 32) DCGC_FOLD(su1, sq1)
-        else if (cb == 64) DCGC_FOLD(su2, sq2)
-        else DCGC_FOLD(su3, sq3)
-#undef DCGC_FOLD
-      }
-      tc_fence_before();
-      mbar_arrive(bar_base + 112 + 8 * acc);
-      if (dbg_on && tid == 0) q.dbg[4096 + 2 * it + 1] = clock64();
-    }
-    if (p.stats) {
-      // lanes l, l+8, l+16, l+24 hold the same columns (different rows): fixed-order butterfly, then the four
-      // epilogue warps are combined in warp order through shared memory (deterministic)
-      double* shd = reinterpret_cast<double*>(sm + S * V3_STAGE_BYTES + 256);   // [4 warps][2][128]
-      named_bar_sync(2, 128);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float* su = (i >> 2) == 0 ? su0 : ((i >> 2) == 1 ? su1 : ((i >> 2) == 2 ? su2 : su3));
-        const float* sq = (i >> 2) == 0 ? sq0 : ((i >> 2) == 1 ? sq1 : ((i >> 2) == 2 ? sq2 : sq3));
-        double a = (double)su[i & 3], b = (double)sq[i & 3];
-        a += __shfl_xor_sync(0xffffffffu, a, 8);  b += __shfl_xor_sync(0xffffffffu, b, 8);
-        a += __shfl_xor_sync(0xffffffffu, a, 16); b += __shfl_xor_sync(0xffffffffu, b, 16);
-        if (lane < 8) {
-          const int col = (i >> 2) * 32 + 4 * lane + (i & 3);
-          shd[(warp * 2 + 0) * TC_BN + col] = a;
-          shd[(warp * 2 + 1) * TC_BN + col] = b;
-        }
-      }
-      named_bar_sync(2, 128);
-      const int col = warp * 32 + lane;
-      if (n0 + col < N) {
-#pragma unroll
-        for (int qn = 0; qn < 2; ++qn) {
-          double t = 0.0;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) t += shd[(w * 2 + qn) * TC_BN + col];
-          p.stats[((int64_t)pid * 2 + qn) * N + n0 + col] = t;
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 12) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 2 * TC_BN);
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // tc_gemm_kernel_v4: the TS form — the A operand lives in TENSOR MEMORY, never in shared memory.
 //
@@ -598,14 +247,6 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
@@ -795,8 +436,6 @@ __global__ void __launch_bounds__(V4_THREADS, 1) tc_gemm_kernel_v4(const TcArgs3
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int P = gridDim.x, pid = blockIdx.x;
-  const int n0 = blockIdx.y * TC_BN;
-  const int N = p.n1 + p.n2;
   const int chunks1 = (p.k1 + TC_BK - 1) / TC_BK, chunks2 = (p.k2 + TC_BK - 1) / TC_BK;
   const int total = chunks1 + chunks2;
   const int my_tiles = pid < q.n_row_tiles ? (q.n_row_tiles - pid + P - 1) / P : 0;
@@ -1232,257 +871,6 @@ tc_gemm_kernel_v5(const TcArgs3 q, const __grid_constant__ CUtensorMap map1, con
 }
 
 // ------------------------------------------------------------------------------------------
-// wgrad on tensor cores: dW[g] = [a1|a2]_g^T . grad_g, a contraction over the ROWS (atoms) of one
-// degree bucket.  One CTA owns one chunk of rows of one group (fixed split => deterministic) and
-// MT 128-row tiles of dW x one 128-column tile:
-//   * 8 producer warps: lane = atom row of a 32-row K chunk, warp w = 16 consecutive feature
-//     columns; LDG.128 of [a1|a2] and grad (two register sets: the loads of chunk c+1 are in flight
-//     while chunk c is split into tf32 hi/lo and TRANSPOSED into the K-major SWIZZLE_128B tiles
-//     with conflict-free 4-byte stores (all lanes of a store hit one 128-byte smem row);
-//   * warp 8: one lane issues MT x 4 K-steps x 3 tcgen05.mma (lo*hi + hi*lo + hi*hi) per chunk;
-//   * epilogue (warps 0-3): tcgen05.ld the fp32 accumulators, store the partial dW to the
-//     workspace; the column sums of grad (dbias) are accumulated by the producers in registers and
-//     combined with a fixed-order warp shuffle reduction.
-// The partials are summed in chunk order by wgrad_reduce_kernel (gemm_simt.cu).
-// ------------------------------------------------------------------------------------------
-constexpr int WG_THREADS = 9 * 32;
-
-template <int MT, int NT>
-__global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgradArgs p) {
-  constexpr int NL = 4 * (MT + 1);                              // float4 loads per thread per chunk
-  constexpr int TPO = NT == 3 ? 2 : 1;                          // tiles per operand: (hi, lo) or one
-  constexpr int WG_STAGES = NT == 3 ? 2 : 4;
-  constexpr int STAGE_BYTES = TPO * (MT + 1) * TC_TILE_BYTES;   // A tiles x MT, then the G tile(s)
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t bar_base = base + WG_STAGES * STAGE_BYTES;
-  // barriers: full[s] +8s, empty[s] +32+8s, accumulator-ready +64, tmem slot +72
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + WG_STAGES * STAGE_BYTES + 72);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int chunk = blockIdx.x;
-  int g = 0;
-  while (g + 1 < p.n_groups && chunk >= p.chunk_prefix[g + 1]) ++g;
-  const int64_t r_begin = p.group_row0[g] + (int64_t)(chunk - p.chunk_prefix[g]) * p.chunk_rows;
-  const int64_t r_end = min(p.group_row0[g + 1], r_begin + p.chunk_rows);
-  const int mp = blockIdx.y / p.tiles_n, nt = blockIdx.y - mp * p.tiles_n;
-  const int m0 = mp * MT * TC_BM, n0 = nt * TC_BN;
-  const int Kt = p.k1 + p.k2;
-  const int steps = (int)((r_end - r_begin + TC_BK - 1) / TC_BK);
-  const bool wdbg = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
-  if (wdbg && tid == 0) { p.dbg[5000] = clock64(); p.dbg[5001] = steps; }
-
-  if (tid == 0) {
-    for (int s = 0; s < WG_STAGES; ++s) {
-      mbar_init(bar_base + 8 * s, TC_PRODUCER_WARPS);
-      mbar_init(bar_base + 32 + 8 * s, 1);
-    }
-    mbar_init(bar_base + 64, 1);
-    fence_barrier_init();
-  }
-  if (warp == TC_PRODUCER_WARPS) tmem_alloc(bar_base + 72, MT * TC_BN);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp < TC_PRODUCER_WARPS) {
-    // The contraction runs over the ATOMS, so both operands ([atoms, features] and [atoms, columns], row-major)
-    // have their M / N dimension contiguous: they are stored as MN-major SWIZZLE_128B_BASE32B tiles and the tensor core
-    // does the transposition (instruction-descriptor bits 15/16).  The producers only copy: a warp instruction
-    // covers 4 atoms x 32 features = four coalesced 128-byte row segments, stored as 16-byte chunks of one
-    // 128-byte smem row per atom (conflict-free).  (Two earlier versions transposed in the producers with
-    // 4-byte stores: ~100 STS + address arithmetic per thread and chunk made the producers the critical path,
-    // 4.7 k cycles per 32-atom chunk against 1.2 k for the MMAs: scripts/wgrad_timeline.py.)
-    // Warp w owns atoms 4w..4w+3 of the chunk; load j of a tile covers features 32j..32j+31.
-    float bsum[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) bsum[i] = 0.f;
-    const int la = lane >> 3, lc = lane & 7;
-    const int k = 4 * warp + la;                  // atom inside the 32-atom chunk = K index
-    // byte offset of this lane's 16 bytes inside the chunk: [K group k>>2][MN atom j][row k&3][32-byte chunk ^ row]
-    const uint32_t k_off = (uint32_t)((k >> 2) * 2048 + (k & 3) * 128 + (((lc >> 1) ^ (k & 3)) << 5) + (lc & 1) * 16);
-
-    auto gload = [&](float4 (&r)[NL], int c) {
-      const int64_t row = r_begin + (int64_t)c * TC_BK + k;
-      const bool live = row < r_end;
-#pragma unroll
-      for (int t = 0; t < MT; ++t) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int m = m0 + t * TC_BM + 32 * j + 4 * lc;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live && m < Kt) {
-            if (m + 3 < p.k1) {
-              v = ld4_masked(p.a1 + row * p.ld_a1 + m, 4, p.a1_vec);
-            } else if (m >= p.k1) {
-              const int f2 = m - p.k1;
-              v = ld4_masked(p.a2 + row * p.ld_a2 + f2, p.k2 - f2, p.a2_vec && (f2 & 3) == 0);
-            } else {   // the float4 straddles the a1 | a2 boundary
-              float e[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const int fe = m + q;
-                e[q] = fe < p.k1 ? __ldg(p.a1 + row * p.ld_a1 + fe)
-                                 : (fe < Kt ? __ldg(p.a2 + row * p.ld_a2 + (fe - p.k1)) : 0.f);
-              }
-              v = make_float4(e[0], e[1], e[2], e[3]);
-            }
-          }
-          r[4 * t + j] = v;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = n0 + 32 * j + 4 * lc;
-        r[4 * MT + j] = live ? ld4_masked(p.g + row * p.ld_g + n, p.n - n, p.g_vec)
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    auto sstore = [&](const float4 (&r)[NL], int c) {
-      const int s = c % WG_STAGES, use = c / WG_STAGES;
-      mbar_wait(bar_base + 32 + 8 * s, (use & 1) ^ 1);           // the MMAs that read this stage retired
-      uint8_t* st = sm + s * STAGE_BYTES;
-#pragma unroll
-      for (int t = 0; t <= MT; ++t) {
-        uint8_t* hi_t = st + TPO * t * TC_TILE_BYTES + k_off;
-        uint8_t* lo_t = hi_t + TC_TILE_BYTES;
-        const bool want_lo = !(p.a_exact && t < MT);          // exact A operand: its lo tiles are identically zero
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (NT == 3) {
-            float4 hi, lo;
-            split4(r[4 * t + j], hi, lo);
-            *reinterpret_cast<float4*>(hi_t + j * 512) = hi;
-            if (want_lo) *reinterpret_cast<float4*>(lo_t + j * 512) = lo;
-          } else {
-            *reinterpret_cast<float4*>(hi_t + j * 512) = round4_bf16(r[4 * t + j]);
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        bsum[4 * j + 0] += r[4 * MT + j].x; bsum[4 * j + 1] += r[4 * MT + j].y;
-        bsum[4 * j + 2] += r[4 * MT + j].z; bsum[4 * j + 3] += r[4 * MT + j].w;
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_base + 8 * s);
-      if (wdbg && tid == 0 && c < 1000) p.dbg[c] = clock64();
-    };
-
-    float4 ra[NL], rb[NL];
-    if (steps > 0) gload(ra, 0);
-    for (int c = 0; c < steps; c += 2) {
-      if (c + 1 < steps) gload(rb, c + 1);
-      sstore(ra, c);
-      if (c + 2 < steps) gload(ra, c + 2);
-      if (c + 1 < steps) sstore(rb, c + 1);
-    }
-    // dbias partial: bsum[4j+e] = this lane's sum of column 32j + 4 lc + e over its atom of every chunk;
-    // combine the 4 atom lanes (fixed butterfly), then the 8 warps in warp order through shared memory
-    if (mp == 0) {
-      float* sb = reinterpret_cast<float*>(sm + WG_STAGES * STAGE_BYTES + 256);   // [8 warps][128]: the epilogue staging area
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float v = bsum[i];
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        if (la == 0) sb[warp * TC_BN + 32 * (i >> 2) + 4 * lc + (i & 3)] = v;
-      }
-      named_bar_sync(1, TC_PRODUCER_WARPS * 32);
-      if (tid < TC_BN) {
-        float v = 0.f;
-#pragma unroll
-        for (int w = 0; w < TC_PRODUCER_WARPS; ++w) v += sb[w * TC_BN + tid];
-        const int n = n0 + tid;
-        if (n < p.n) p.wsb[(int64_t)chunk * p.n + n] = v;
-      }
-      named_bar_sync(1, TC_PRODUCER_WARPS * 32);   // the staging area is reused by the epilogue warps
-    }
-  } else if (lane == 0) {
-    for (int c = 0; c < steps; ++c) {
-      const int s = c % WG_STAGES;
-      mbar_wait(bar_base + 8 * s, (c / WG_STAGES) & 1);
-      tc_fence_after();
-      if (wdbg && c < 1000) p.dbg[3072 + c] = clock64();
-      const uint32_t sa = base + s * STAGE_BYTES;
-      const uint32_t sg_hi = sa + TPO * MT * TC_TILE_BYTES, sg_lo = sg_hi + TC_TILE_BYTES;
-#pragma unroll
-      for (int t = 0; t < MT; ++t) {
-        const uint32_t a_hi = sa + TPO * t * TC_TILE_BYTES, a_lo = a_hi + TC_TILE_BYTES;
-#pragma unroll
-        for (int k = 0; k < TC_BK / TC_UK; ++k) {
-          const uint32_t ko = k * 4096;                         // K rows 8k..8k+7 = two K groups of 4
-          const uint64_t ahi = make_desc_mn(a_hi + ko), alo = make_desc_mn(a_lo + ko);
-          const uint64_t ghi = make_desc_mn(sg_hi + ko), glo = make_desc_mn(sg_lo + ko);
-          if (NT == 3) {
-            if (!p.a_exact) {
-              umma_tf32(tmem + t * TC_BN, alo, ghi, kIdescTf32MN, (c | k) != 0);
-              umma_tf32(tmem + t * TC_BN, ahi, glo, kIdescTf32MN, 1);
-            } else {
-              umma_tf32(tmem + t * TC_BN, ahi, glo, kIdescTf32MN, (c | k) != 0);
-            }
-            umma_tf32(tmem + t * TC_BN, ahi, ghi, kIdescTf32MN, 1);
-          } else {
-            umma_tf32(tmem + t * TC_BN, ahi, ghi, kIdescTf32MN, (c | k) != 0);
-          }
-        }
-      }
-      umma_commit(bar_base + 32 + 8 * s);
-    }
-    umma_commit(bar_base + 64);
-  }
-
-  if (warp < 4) {
-    if (wdbg && tid == 0) p.dbg[4096] = clock64();
-    if (steps > 0) {
-      mbar_wait(bar_base + 64, 0);
-      tc_fence_after();
-    }
-    if (wdbg && tid == 0) p.dbg[4097] = clock64();
-    const bool n_vec = (p.n & 3) == 0 && (reinterpret_cast<uintptr_t>(p.ws) & 15) == 0;
-    float* stg = reinterpret_cast<float*>(sm + WG_STAGES * STAGE_BYTES + 256) + warp * EPI_WARP_FLOATS;
-#pragma unroll 1
-    for (int t = 0; t < MT; ++t) {
-      const int mbase = m0 + t * TC_BM + warp * 32;
-#pragma unroll 1
-      for (int cb = 0; cb < TC_BN; cb += 32) {
-        uint32_t v[32];
-        if (steps > 0) {
-          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + t * TC_BN + cb, v);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0u;
-        }
-        const int c = n0 + cb + 4 * (lane & 7);
-        warp_transpose_store(stg, lane, v, [&](int rr, int, float4 o) {
-          const int m = mbase + rr;
-          if (m >= Kt || c >= p.n) return;
-          float* dst = p.ws + ((int64_t)chunk * Kt + m) * p.n + c;
-          if (c + 3 < p.n && n_vec) {
-            *reinterpret_cast<float4*>(dst) = o;
-          } else {
-            const float e[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (c + q < p.n) dst[q] = e[q];
-          }
-        });
-      }
-    }
-  }
-  if (wdbg && tid == 0) p.dbg[4098] = clock64();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == TC_PRODUCER_WARPS) {
-    tc_fence_after();
-    tmem_dealloc(tmem, MT * TC_BN);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // tc_wgrad_kernel_v2: the weight gradient with the operand roles SWAPPED and the MMAs 256 columns wide.
 //
 // Why (scripts/mma_rate.py, profiles/r5d_mma_rate.md): one tcgen05.mma with N = 128 occupies the tensor pipe for
@@ -1507,6 +895,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) tc_wgrad_kernel(const DcgcWgrad
 constexpr int WG2_THREADS = 13 * 32;
 constexpr int WG2_B_STAGES = 3;
 constexpr int WG2_G_STAGES = 4;
+// MN-major operand tile (the contiguous dimension of the data is M or N, not K).  For 32-bit (tf32) operands
+// the only layout the tensor core accepts is SWIZZLE_128B_BASE32B (CUTLASS: "for mn-major tf32 operands,
+// SW128_32B is the only available smem layout"): swizzle atoms of 4 K-rows x 128 bytes (32 fp32 along MN) in
+// which the 32-byte chunk index is XORed with the row index (Swizzle<2,5,2>); atoms repeat along MN every
+// LBO = 512 bytes and along K (groups of 4 rows) every SBO = 2048 bytes, i.e. a [32 K x 128 MN] chunk is laid
+// out as [K group of 4][MN atom][4 rows x 128 B]; one K = 8 MMA reads two K groups.
 __device__ __forceinline__ uint64_t make_desc_mn_nb(uint32_t saddr, int nb) {
   // MN atoms (32 fp32) 512 bytes apart, K groups (4 atoms) nb * 2048 bytes apart
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (32ull << 16) | ((uint64_t)(nb * 128) << 32) | (1ull << 46) | (1ull << 61);
@@ -2157,10 +1551,6 @@ long long* g_timeline = nullptr;   // debugging aid, see dcgcdbg_tc_timeline
 int ensure_smem_attr() {
   static bool done = false;   // per process; the attribute is per function per device context
   if (!done) {
-    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        V3Cfg<3>::kSmemBytes));
-    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        V3Cfg<1>::kSmemBytes));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v4<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         V4Cfg<3>::kSmemBytes));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2177,10 +1567,6 @@ int ensure_smem_attr() {
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v2<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v2<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel_v2<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_wgrad_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int dev = 0;
     DCGC_CUDA_CALL(cudaGetDevice(&dev));
     DCGC_CUDA_CALL(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -2319,15 +1705,8 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
     p3.stats = stats;
     if (stats_chunks) *stats_chunks = ctas;
     dim3 grid((unsigned)ctas, (unsigned)n_tiles_n);
-    // DCGC_TC_V3=1: the previous kernel (both operands in shared memory), kept for A/B measurements
-    static const bool use_v3 = [] { const char* e = getenv("DCGC_TC_V3"); return e && e[0] == '1'; }();
     static const bool use_v4 = [] { const char* e = getenv("DCGC_TC_V4"); return e && e[0] == '1'; }();
-    if (use_v3) {
-      q3.a_exact = 0;
-      if (q3.bnfin.kind != 0) { dcgc_set_error("DCGC_TC_V3: the last-CTA BatchNorm finalize needs the v4 / v5 kernels"); return DCGC_ERR_INVALID; }
-      if (nt == 3) tc_gemm_kernel_v3<3><<<grid, V3_THREADS, V3Cfg<3>::kSmemBytes, st>>>(q3);
-      else tc_gemm_kernel_v3<1><<<grid, V3_THREADS, V3Cfg<1>::kSmemBytes, st>>>(q3);
-    } else if (use_v4 || !p3.a1_vec || (a2 && !p3.a2_vec) || n_rows >= (1ll << 31)) {
+    if (use_v4 || !p3.a1_vec || (a2 && !p3.a2_vec) || n_rows >= (1ll << 31)) {
       // register-fed producers: operands whose rows are not 16-byte aligned (no tensor map), or DCGC_TC_V4=1
       if (nt == 3) tc_gemm_kernel_v4<3><<<grid, V4_THREADS, V4Cfg<3>::kSmemBytes, st>>>(q3);
       else tc_gemm_kernel_v4<1><<<grid, V4_THREADS, V4Cfg<1>::kSmemBytes, st>>>(q3);
@@ -2377,11 +1756,9 @@ int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p_in, int chunks, cudaStre
   const int m_pairs = (Kt + mt * TC_BM - 1) / (mt * TC_BM);
   dim3 grid((unsigned)chunks, (unsigned)(m_pairs * p.tiles_n));
   // NT = 3: 2 stages x (hi, lo) x (mt + 1) tiles; NT = 1: 4 stages x (mt + 1) tiles — the same bytes
-  // DCGC_WGRAD_V1=1: the first kernel (features as M, N = 128), kept for A/B measurements
-  static const bool use_v1 = [] { const char* e = getenv("DCGC_WGRAD_V1"); return e && e[0] == '1'; }();
   // v3 (TMA-fed) where its layout conditions hold; DCGC_WGRAD_V2=1 forces the register-fed kernel (A/B measurements)
   static const bool use_v2 = [] { const char* e = getenv("DCGC_WGRAD_V2"); return e && e[0] == '1'; }();
-  const bool v3_ok = !use_v1 && !use_v2 && p.a1_vec && (p.k2 == 0 || p.a2_vec) && p.g_vec && (p.k1 & 3) == 0 &&
+  const bool v3_ok = !use_v2 && p.a1_vec && (p.k2 == 0 || p.a2_vec) && p.g_vec && (p.k1 & 3) == 0 &&
                      (p.k2 & 3) == 0 && p.k1 <= 128 && p.k2 <= 128 && m_pairs == 1 && p.group_row0[p.n_groups] < (1ll << 31);
   if (v3_ok) {
     const int64_t rows_total = p.group_row0[p.n_groups];
@@ -2403,7 +1780,7 @@ int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p_in, int chunks, cudaStre
     DCGC_CUDA_LAUNCH_CHECK("tc_wgrad_kernel_v3");
     return DCGC_OK;
   }
-  if (!use_v1) {
+  {
     const int smem2 = WG2_B_STAGES * (nt == 3 ? 2 : 1) * mt * TC_TILE_BYTES + 1024 + 256;
     if (nt == 3) {
       if (mt == 2) tc_wgrad_kernel_v2<2, 3><<<grid, WG2_THREADS, smem2, st>>>(p);
@@ -2415,16 +1792,6 @@ int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p_in, int chunks, cudaStre
     DCGC_CUDA_LAUNCH_CHECK("tc_wgrad_kernel_v2");
     return DCGC_OK;
   }
-  const int smem = 4 * (mt + 1) * TC_TILE_BYTES + 1024 + 256 + EPI_BYTES;
-  if (nt == 3) {
-    if (mt == 2) tc_wgrad_kernel<2, 3><<<grid, WG_THREADS, smem, st>>>(p);
-    else tc_wgrad_kernel<1, 3><<<grid, WG_THREADS, smem, st>>>(p);
-  } else {
-    if (mt == 2) tc_wgrad_kernel<2, 1><<<grid, WG_THREADS, smem, st>>>(p);
-    else tc_wgrad_kernel<1, 1><<<grid, WG_THREADS, smem, st>>>(p);
-  }
-  DCGC_CUDA_LAUNCH_CHECK("tc_wgrad_kernel");
-  return DCGC_OK;
 }
 
 // Debugging aid (not part of the ABI in include/dcgc.h): subsequent tensor-core GEMM launches make CTA (0,0)

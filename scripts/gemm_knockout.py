@@ -1,4 +1,4 @@
-"""Timing-only knockout study of the tcgen05 GEMM (tc_gemm_kernel_v3): which stage bounds it?
+"""Timing-only knockout study of the tcgen05 GEMM (the register-fed tcgen05 GEMM, tc_gemm_kernel_v4 with DCGC_TC_V4=1; written for its predecessor v3): which stage bounds it?
 Each mask runs in its own process (DCGC_TC_KNOCKOUT is read once).  Results under a non-zero mask
 are numerically wrong by construction; only the durations mean anything.
 
