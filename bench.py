@@ -489,8 +489,12 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "global_batch": world * B, "atoms_per_batch": n_atoms_mean,
                    "parallelism": "dp%d" % world, "gemm_mode": args.gemm_mode,
                    "arithmetic": "fp32 storage and accumulation everywhere; tf32x3 = every GEMM product as three tcgen05 "
-                                 "kind::tf32 MMAs (hi*hi + hi*lo + lo*hi), error ~2^-21, inside the 1e-5 parity bar "
-                                 "(tests/test_gpu_engine_fp64.py pins this exact configuration to float64); fp32 = SIMT FFMA",
+                                 "MMAs over 11-bit operand halves (hi*hi + hi*lo + lo*hi), error ~2^-21, inside the 1e-5 "
+                                 "parity bar (tests/test_gpu_engine_fp64.py pins this exact configuration to float64): "
+                                 "kind::tf32 halves in the backward GEMMs, kind::f16 halves (same significand, K 16 per "
+                                 "instruction) in the forward GEMMs, whose operands are activations inside fp16's range "
+                                 "(sticky overflow flag checked after the run; DCGC_FWD_F16X3=0 = tf32 halves everywhere); "
+                                 "fp32 = SIMT FFMA",
                    "optimizer": "Adam (in step)", "host_workers": host_workers,
                    "value_is": "kernel-only: device-resident batches, no layout build / H2D in the timed region; the "
                                "like-for-like number against the CPU arm is e2e",
@@ -509,6 +513,9 @@ def run_ours(args):
                            "rows": kernels}
     for k_, v_ in sub_records.items():
         line[k_] = v_
+    # the forward GEMMs ran with fp16 operand halves: say whether any operand left fp16's range (0 = none did)
+    from deepchem_b200 import _lib as _dl
+    line["config"]["f16_overflow_flag"] = int(_dl.lib().dcgc_tc_f16_overflow())
     print(json.dumps(line), flush=True)
 
 
@@ -708,14 +715,17 @@ def kernel_table(rep, n_steps, topos, B):
         "dcgc_gather_sum": sum(2 * act(w_) + E * 4 for w_ in fp) + sum(3 * act(w_) + E * 4 for w_ in fp[1:]),
         "dcgc_pool_fwd": sum(2 * act(c) + E * 4 + N * c for c in LAYERS),
         "dcgc_pool_bwd": sum(3 * act(c) + 2 * E * 4 + N * c for c in LAYERS),
-        "dcgc_gather_fwd": act(D) + N * 4 + 2 * B * D * 4,
-        "dcgc_gather_bwd": act(D) + N * 4 + 2 * B * D * 4,
+        # GraphGather forward: reads z, writes the fingerprint, the arg-max rows and (training) the two per-molecule
+        # centred sums; backward: reads z and the per-molecule tensors, writes G = relu'(z) * BatchNorm-backward(dA)
+        # directly (the dense layer's apply pass is inside this kernel since r6a)
+        "dcgc_gather_fwd": act(D) + N * 4 + 5 * B * D * 4,
+        "dcgc_gather_bwd": 2 * act(D) + N * 4 + 5 * B * D * 4,
         # conv forward GEMMs read [X | S] and write Y; the 4th call of the scope is the dense layer's input gradient
         "dcgc_group_gemm_fwd": sum(2 * act(w_) + act(c) for w_, c in zip(fp, LAYERS)) + act(D) + act(C),
         "dcgc_group_gemm_dgrad": sum(act(c) + 2 * act(w_) for w_, c in zip(fp[1:], LAYERS[1:])),
         "dcgc_group_gemm_wgrad": sum(2 * act(w_) + act(c) for w_, c in zip(fp, LAYERS)) + act(C) + act(D),
         "dcgc_linear_fwd": act(C) + act(D),
-        "bn_relu_bwd_apply": sum(3 * act(c) for c in LAYERS) + 3 * act(D),
+        "bn_relu_bwd_apply": sum(3 * act(c) for c in LAYERS),
     }
     rows = []
     for name, (t_ms, n_calls) in sorted(rep.items(), key=lambda kv: -kv[1][0]):

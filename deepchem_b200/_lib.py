@@ -16,7 +16,7 @@ DCGC_ERR_CUDA = -4
 DCGC_ERR_NOMEM = -5
 
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
-GEMM_FP32, GEMM_BF16, GEMM_TF32X3 = 0, 1, 2
+GEMM_FP32, GEMM_BF16, GEMM_TF32X3, GEMM_F16X3 = 0, 1, 2, 3
 N_DEG = 11
 TILE_ROWS = 128
 
@@ -190,6 +190,7 @@ _SIGNATURES = {
     "dcgc_p2p_open": (c_int32, [_P, POINTER(ctypes.c_void_p)]),
     "dcgc_p2p_close": (c_int32, [_P]),
     "dcgc_p2p_free": (c_int32, [_P]),
+    "dcgc_tc_f16_overflow": (c_int32, []),
     "dcgc_adam_step": (c_int32, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_int64, c_float, _P]),
 }
 

@@ -29,7 +29,9 @@ struct DcgcProfScope {
   cudaStream_t st_;
 };
 // tensor-core modes -> number of MMA terms (0 = not a tensor-core mode)
-static inline int dcgc_tc_terms(int mode) { return mode == DCGC_GEMM_TF32X3 ? 3 : (mode == DCGC_GEMM_BF16 ? 1 : 0); }
+static inline int dcgc_tc_terms(int mode) {
+  return (mode == DCGC_GEMM_TF32X3 || mode == DCGC_GEMM_F16X3) ? 3 : (mode == DCGC_GEMM_BF16 ? 1 : 0);
+}
 #define DCGC_CUDA_LAUNCH_CHECK(what)                                        \
   do {                                                                      \
     g_dcgc_launches.fetch_add(1, std::memory_order_relaxed);                \
@@ -77,6 +79,8 @@ struct DcgcGemmOpts {
   const float* img = nullptr;
   int a_exact = 0;
   const DcgcBnFin* fin = nullptr;   // BatchNorm finalize by the last CTA (only with the fused column statistics)
+  int f16x3 = 0;                    // forward GEMMs: fp16 hi / lo halves instead of tf32 ones (tc_gemm_kernel_v6); img, if
+                                    // given, must then come from dcgc_tc_prep_weights_f16
 };
 int dcgc_gather_bwd_stats(const float* dout, int64_t ld_dout, const float* out, int64_t ld_out, const int32_t* argrow,
                           const int32_t* membership, int64_t n_rows, int32_t width, int32_t act, float* dx,
@@ -107,6 +111,8 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
 // early weight images (gemm_tc.cu): build on any stream, pass to the GEMM in DcgcGemmOpts::img
 int64_t dcgc_tc_image_bytes(int nt, int k1, int k2, int N, int n_groups);
 int dcgc_tc_prep_weights(int nt, const float* w, int n_groups, int trans_w, int k1, int k2, int N, float* img, cudaStream_t st);
+int64_t dcgc_tc_image_bytes_f16(int k1, int k2, int N, int n_groups);
+int dcgc_tc_prep_weights_f16(const float* w, int n_groups, int trans_w, int k1, int k2, int N, float* img, cudaStream_t st);
 // the C-ABI entry points of gemm_simt.cu with explicit options (used by the fused engines)
 int dcgc_group_gemm_fwd_opts(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2, int64_t ld_a2,
                              int32_t k2, const float* w, const float* bias, int32_t n, const int32_t* tiles,

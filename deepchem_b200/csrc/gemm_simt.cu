@@ -393,9 +393,12 @@ static int group_gemm_fwd_impl(int32_t mode, const float* a1, int64_t ld_a1, int
   if (n_rows == 0 || n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(a1 && w && y, "dcgc_group_gemm_fwd: null pointer");
   DcgcProfScope prof_scope("dcgc_group_gemm_fwd", (cudaStream_t)stream);
-  if (dcgc_tc_terms(mode))
+  if (dcgc_tc_terms(mode)) {
+    DcgcGemmOpts o2 = opts ? *opts : DcgcGemmOpts{};
+    if (mode == DCGC_GEMM_F16X3) o2.f16x3 = 1;
     return dcgc_tc_gemm(dcgc_tc_terms(mode), a1, ld_a1, k1, a2, ld_a2, a2 ? k2 : 0, w, tiles ? DCGC_N_DEG : 1, 1, bias, n, 0, tiles, n_tiles,
-                        n_rows, act, y, ld_y, nullptr, 0, (cudaStream_t)stream, stats, stats_chunks, opts);
+                        n_rows, act, y, ld_y, nullptr, 0, (cudaStream_t)stream, stats, stats_chunks, &o2);
+  }
   GemmArgs p{};
   p.a1 = a1; p.ld_a1 = ld_a1; p.k1 = k1;
   p.a2 = a2; p.ld_a2 = ld_a2; p.k2 = a2 ? k2 : 0;
@@ -641,9 +644,12 @@ static int linear_fwd_impl(int32_t mode, const float* x, int64_t ld_x, int32_t k
   if (n_rows == 0 || n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(x && w && y, "dcgc_linear_fwd: null pointer");
   DcgcProfScope prof_scope("dcgc_linear_fwd", (cudaStream_t)stream);
-  if (dcgc_tc_terms(mode))
+  if (dcgc_tc_terms(mode)) {
+    DcgcGemmOpts o2 = opts ? *opts : DcgcGemmOpts{};
+    if (mode == DCGC_GEMM_F16X3) o2.f16x3 = 1;
     return dcgc_tc_gemm(dcgc_tc_terms(mode), x, ld_x, k, nullptr, 0, 0, w, 1, 0, bias, n, 0, nullptr, 0, n_rows, act, y, ld_y, nullptr, 0,
-                        (cudaStream_t)stream, stats, stats_chunks, opts);
+                        (cudaStream_t)stream, stats, stats_chunks, &o2);
+  }
   GemmArgs p{};
   p.a1 = x; p.ld_a1 = ld_x; p.k1 = k;
   p.w = w; p.w_group_stride = 0; p.ld_w = k;

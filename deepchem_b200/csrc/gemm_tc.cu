@@ -17,6 +17,7 @@
 #include <utility>
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.h"
 
@@ -191,6 +192,40 @@ __global__ void __launch_bounds__(256) tc_prep_image(const ImgArgs p) {
     const uint32_t o = (swz(r[u], kl[u] >> 2) >> 2) + (kl[u] & 3);   // float index inside the 16 KB tile
     blk[o] = h;
     if (NT == 3) blk[TC_BM * TC_BK + o] = tf32_lo(v[u], h);
+  }
+}
+
+// Weight image of the fp16x3 forward kernel (tc_gemm_kernel_v6): per (group, n-tile, 64-wide K chunk) a hi tile and a lo
+// tile of [128 rows x 64 halves] = 16 KB each, K-major SWIZZLE_128B (a 128-byte row holds 64 K values instead of the 32
+// of the tf32 image).  hi = fp16(w), lo = fp16(w - hi): w = hi + lo to ~2^-22 (11 + 11 significand bits), or to an
+// absolute 3e-8 where lo falls into fp16's subnormal range.  K is padded per operand to multiples of 64.
+__global__ void __launch_bounds__(256) tc_prep_image_f16(const ImgArgs p) {
+  // one block = an eighth (1024 elements) of one [128 x 64] tile
+  const int g = blockIdx.z, nt = blockIdx.y, ch = blockIdx.x >> 3, part = blockIdx.x & 7;
+  __half* blk = reinterpret_cast<__half*>(p.img) + (((int64_t)g * p.n_tiles + nt) * p.chunks + ch) * (2 * TC_BM * 64);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = part * 1024 + u * 256 + threadIdx.x;
+    int r, kl;
+    if (p.trans) { r = i & (TC_BN - 1); kl = i >> 7; }     // source is n-contiguous
+    else { kl = i & 63; r = i >> 6; }                      // source is k-contiguous
+    const int nn = nt * TC_BN + r, kk = ch * 64 + kl;
+    float v = 0.f;
+    if (nn < p.n) {
+      if (p.trans) {
+        int ks = -1;
+        if (kk < p.k1_pad) { if (kk < p.k1) ks = kk; }
+        else if (kk - p.k1_pad < p.k2) ks = p.k1 + (kk - p.k1_pad);
+        if (ks >= 0) v = __ldg(p.src + g * p.src_group_stride + (int64_t)ks * p.src_ld + nn);
+      } else if (kk < p.k1) {
+        v = __ldg(p.src + g * p.src_group_stride + (int64_t)nn * p.src_ld + kk);
+      }
+    }
+    const __half h = __float2half_rn(v);
+    const __half l = __float2half_rn(v - __half2float(h));
+    const uint32_t o = (swz(r, kl >> 3) >> 1) + (kl & 7);      // half index inside the 16 KB tile
+    blk[o] = h;
+    blk[TC_BM * 64 + o] = l;
   }
 }
 
@@ -648,7 +683,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) tc_gemm_kernel_v4(const TcArgs3
 // producers every ~1 500 cycles, while one chunk of MMAs is 768 cycles of tensor time and the HBM floor of the
 // forward GEMM (16 KB of A + 8 KB of output per chunk and SM at 6.55 TB/s) is ~1 075 cycles.  The GEMM is memory
 // bound, so what it needs is BYTES IN FLIGHT: here one thread issues a tensor-map TMA load per chunk
-// (cp.async.bulk.tensor.2d, SWIZZLE_128B, SASS UTMALDG) into a five-deep ring of raw fp32 tiles — 80 KB in flight per
+// (cp.async.bulk.tensor.2d, SWIZZLE_128B, SASS UTMALDG) into a four-deep ring of raw fp32 tiles — 64 KB in flight per
 // SM without a register — and the converter warps only move a landed tile from shared memory into tensor memory:
 // one row per thread, 8 conflict-free LDS.128 (the swizzle spreads the 8 rows of a quarter-warp over the 8 16-byte
 // chunks), tf32 hi / lo split, tcgen05.st.32x32b.  Rows past the tile (next degree bucket) are loaded and multiplied
@@ -662,7 +697,8 @@ __global__ void __launch_bounds__(V4_THREADS, 1) tc_gemm_kernel_v4(const TcArgs3
 // ring has the same depth and index as the A stages in tensor memory, so ONE tcgen05.commit frees both.
 // ------------------------------------------------------------------------------------------
 constexpr int V5_THREADS = 19 * 32;
-constexpr int V5_A_STAGES = 5;
+constexpr int V5_A_STAGES = 4;     // even, like V5_W_STAGES: see the note at V6_A_STAGES (five stages worked in every test,
+                                   // but only because the TMA loads complete in issue order in practice)
 constexpr int V5_W_STAGES = 4;
 template <int NT> struct V5Cfg {
   static constexpr int kBTiles = NT == 3 ? 2 : 1;
@@ -869,6 +905,219 @@ tc_gemm_kernel_v5(const TcArgs3 q, const __grid_constant__ CUtensorMap map1, con
     tmem_dealloc(tmem, 512);
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// tc_gemm_kernel_v6: the FORWARD GEMMs in fp16x3 — v5 with 2-byte operand halves.
+//
+// Why: a tcgen05.mma of N = 128 can be issued once per ~116 cycles whatever its kind (profiles/r5d_mma_rate.md), and
+// kind::f16 covers K = 16 per instruction where kind::tf32 covers 8.  fp16 has the 11-bit significand of tf32, so the
+// same three-term product (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM) needs HALF the instructions: 48 per
+// 128-row tile at K = 256 instead of 96, which takes the forward GEMM from issue-bound (11.1 k cycles of a 12.5 k tile)
+// to the HBM floor of its tile (8.6 k).  What fp16 lacks is tf32's exponent range: hi overflows above 65 504 and lo
+// loses bits below 6e-5 (absolute error <= 3e-8 per element).  The ACTIVATIONS of the forward pass are in range by
+// construction (atom features and their neighbour sums; BatchNorm outputs, max-pooled), the gradients of the backward
+// pass are not (1e-7 .. 1e-3), so dgrad and the weight gradient stay TF32x3; the converters raise a sticky flag if they
+// ever see |x| > 60 000 (dcgc_tc_f16_overflow) and DCGC_FWD_F16X3=0 switches the mode off.
+// Structure = v5: a K chunk is 64 values (a 128-byte row of halves), the raw fp32 chunk arrives as two 32-float TMA
+// boxes, the converter packs two halves per TMEM column (32 hi + 32 lo columns per stage, as v5), four K = 16 steps.
+// ------------------------------------------------------------------------------------------
+constexpr int V6_A_STAGES = 2;     // 2 x 32 KB of raw fp32 chunks in flight
+constexpr int V6_W_STAGES = 4;     // weight chunks (L2 hits); also the number of A stages in tensor memory
+// Both ring depths must be EVEN: the two converter sets take alternate chunks, so with an even depth a ring slot is always
+// used by the same set, whose waits on it are one phase apart.  With an odd depth a slot alternates between the sets and a
+// set can reach its FIRST wait on a slot (use 1, parity 1) before use 0 has completed — a parity wait on a fresh barrier
+// passes at once — and convert a chunk that has not landed (measured: 3 A stages faulted in the bench, r6d).
+static_assert(V6_A_STAGES % 2 == 0 && V6_W_STAGES % 2 == 0, "ring depths must be even (two converter sets)");
+constexpr int V6_SMEM_BYTES = V6_A_STAGES * 2 * TC_TILE_BYTES + V6_W_STAGES * 2 * TC_TILE_BYTES + 1024 + 256 + 8 * 2 * 64 * 8;
+// kind::f16 instruction descriptor: D = f32, A = B = fp16 (format 0), both K-major, N = 128, M = 128
+constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+__device__ int g_f16_overflow = 0;
+__device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+               ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
+}
+__global__ void __launch_bounds__(V5_THREADS, 1)
+tc_gemm_kernel_v6(const TcArgs3 q, const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2) {
+  const TcArgs& p = q.a;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
+  constexpr int NT = 3;
+  constexpr int SA = V6_A_STAGES, SW = V6_W_STAGES;
+  constexpr int A_STAGE_BYTES = 2 * TC_TILE_BYTES;          // two 32-float sub-tiles = 64 K values per row
+  constexpr int W_STAGE_BYTES = 2 * TC_TILE_BYTES;          // fp16 hi | lo tiles of [128 x 64]
+  constexpr uint32_t A_BYTES = SA * A_STAGE_BYTES;
+  const uint32_t w_base = base + A_BYTES;
+  const uint32_t bar_base = w_base + SW * W_STAGE_BYTES;
+  uint8_t* bar_ptr = sm + A_BYTES + SW * W_STAGE_BYTES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + V5_TMEM_SLOT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int P = gridDim.x, pid = blockIdx.x;
+  const int chunks1 = (p.k1 + 63) / 64, chunks2 = (p.k2 + 63) / 64;        // 64-wide K chunks
+  const int total = chunks1 + chunks2;
+  const int my_tiles = pid < q.n_row_tiles ? (q.n_row_tiles - pid + P - 1) / P : 0;
+  const int n_cc = my_tiles * total;
+  const bool dbg_on = q.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && n_cc <= 1024;
+  if (dbg_on && tid == 0) q.dbg[5000] = clock64();
+
+  if (tid == 0) {
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(bar_base + V5_A_FULL + 8 * s, 1);          // the loader's arrive.expect_tx (+ the TMA bytes)
+      mbar_init(bar_base + V5_A_EMPTY + 8 * s, 4);         // the four converter warps of one set
+    }
+    for (int s = 0; s < SW; ++s) {
+      mbar_init(bar_base + V5_W_FULL + 8 * s, 1);
+      mbar_init(bar_base + V5_T_FULL + 8 * s, 4);
+      mbar_init(bar_base + V5_WT_EMPTY + 8 * s, 1);        // tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_base + V5_ACC_FULL + 8 * a, 1);
+      mbar_init(bar_base + V5_ACC_EMPTY + 8 * a, 8);       // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 17) tmem_alloc(bar_base + V5_TMEM_SLOT, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= 8 && warp < 16) {
+    // ===================== converters: shared memory (raw fp32, SWIZZLE_128B) -> tf32 hi / lo -> tensor memory ======
+    const int pw = warp - 8, set = pw >> 2, qd = pw & 3;
+    const int row = qd * 32 + lane;                                  // this thread's row of the tile = its TMEM lane
+    const uint32_t row_off = (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+    const uint32_t sw7 = (uint32_t)(row & 7);
+    const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
+    for (int cc = set; cc < n_cc; cc += 2) {
+      const int sa = cc % SA, st = cc % SW;
+      mbar_wait(bar_base + V5_A_FULL + 8 * sa, (cc / SA) & 1);               // the tile has landed
+      mbar_wait(bar_base + V5_WT_EMPTY + 8 * st, ((cc / SW) & 1) ^ 1);       // the MMAs that read this TMEM stage retired
+      tc_fence_after();
+      const uint32_t a_col = V4_A_COL0 + (uint32_t)st * 64u;
+      // 64 K values of this row: two sub-tiles x 8 chunks of 16 bytes; fp16 hi / lo pairs packed two per column
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        const uint8_t* tile = sm + sa * A_STAGE_BYTES + sub * TC_TILE_BYTES + row_off;
+        float4 v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(tile + ((((uint32_t)c) ^ sw7) << 4));
+        float amax = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[c].x), fabsf(v[c].y)), fmaxf(fabsf(v[c].z), fabsf(v[c].w))));
+        if (amax > 60000.f) g_f16_overflow = 1;              // sticky: the caller must not trust fp16x3 for this data
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const __half2 h01 = __floats2half2_rn(v[c].x, v[c].y), h23 = __floats2half2_rn(v[c].z, v[c].w);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(v[c].x - f01.x, v[c].y - f01.y);
+          const __half2 l23 = __floats2half2_rn(v[c].z - f23.x, v[c].w - f23.y);
+          hi[2 * c] = *reinterpret_cast<const uint32_t*>(&h01); hi[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h23);
+          lo[2 * c] = *reinterpret_cast<const uint32_t*>(&l01); lo[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&l23);
+        }
+        tmem_st32x16(t_lane + a_col + 16u * sub, hi);
+        if (!q.a_exact) tmem_st32x16(t_lane + a_col + 32u + 16u * sub, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_base + V5_A_EMPTY + 8 * sa);       // the raw tile may be overwritten
+        mbar_arrive(bar_base + V5_T_FULL + 8 * st);        // A (hi, lo) of this chunk is in tensor memory
+      }
+      if (dbg_on && lane == 0 && qd == 0) q.dbg[(set ? 1024 : 0) + (cc >> 1)] = clock64();
+    }
+  } else if (warp == 16) {
+    // ===================== A loader: one tensor-map TMA load per chunk =====================
+    if (lane == 0) {
+      int cc = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        int row0, rows, g;
+        tile_of(p, pid + it * P, row0, rows, g);
+        for (int ch = 0; ch < total; ++ch, ++cc) {
+          const int s = cc % SA;
+          mbar_wait(bar_base + V5_A_EMPTY + 8 * s, ((cc / SA) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_base + V5_A_FULL + 8 * s, (uint32_t)A_STAGE_BYTES);
+          const uint32_t dst = base + s * A_STAGE_BYTES, fb = bar_base + V5_A_FULL + 8 * s;
+          if (ch < chunks1) {
+            tma_load_2d(dst, &map1, ch * 64, row0, fb);
+            tma_load_2d(dst + TC_TILE_BYTES, &map1, ch * 64 + 32, row0, fb);
+          } else {
+            tma_load_2d(dst, &map2, (ch - chunks1) * 64, row0, fb);
+            tma_load_2d(dst + TC_TILE_BYTES, &map2, (ch - chunks1) * 64 + 32, row0, fb);
+          }
+          if (dbg_on) q.dbg[2048 + cc] = clock64();
+        }
+      }
+    }
+  } else if (warp == 18) {
+    // ===================== weight loader: one bulk copy of the ready-made image per chunk =====================
+    if (lane == 0) {
+      int cc = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        int row0, rows, g;
+        tile_of(p, pid + it * P, row0, rows, g);
+        constexpr int kBFloats = W_STAGE_BYTES / 4;                 // (the image is addressed in floats)
+        constexpr uint32_t kBBytes = (uint32_t)W_STAGE_BYTES;
+        const float* src = q.img + ((int64_t)g * q.n_tiles_n + blockIdx.y) * total * kBFloats;
+        for (int ch = 0; ch < total; ++ch, ++cc) {
+          const int s = cc % SW;
+          mbar_wait(bar_base + V5_WT_EMPTY + 8 * s, ((cc / SW) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar_base + V5_W_FULL + 8 * s, kBBytes);
+          bulk_g2s(w_base + s * W_STAGE_BYTES, src + (int64_t)ch * kBFloats, kBBytes, bar_base + V5_W_FULL + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 17) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int cc = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const int acc = it & 1;
+        mbar_wait(bar_base + V5_ACC_EMPTY + 8 * acc, ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t d = tmem + acc * TC_BN;
+        for (int ch = 0; ch < total; ++ch, ++cc) {
+          const int s = cc % SW;
+          const uint32_t par = (cc / SW) & 1;
+          mbar_wait(bar_base + V5_W_FULL + 8 * s, par);
+          mbar_wait(bar_base + V5_T_FULL + 8 * s, par);
+          tc_fence_after();
+          if (dbg_on) q.dbg[3072 + cc] = clock64();
+          const uint32_t sb = w_base + s * W_STAGE_BYTES;
+          const uint32_t a_hi = tmem + V4_A_COL0 + (uint32_t)s * 64u, a_lo = a_hi + 32u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {                        // four K = 16 steps per 64-wide chunk
+            const uint32_t ko = k * 32;                        // 16 halves
+            const uint64_t bhi = make_desc(sb + ko), blo = make_desc(sb + TC_TILE_BYTES + ko);
+            if (!q.a_exact) {
+              umma_f16_ts(d, a_lo + k * 8, bhi, kIdescF16, (ch | k) != 0);
+              umma_f16_ts(d, a_hi + k * 8, blo, kIdescF16, 1);
+            } else {
+              umma_f16_ts(d, a_hi + k * 8, blo, kIdescF16, (ch | k) != 0);
+            }
+            umma_f16_ts(d, a_hi + k * 8, bhi, kIdescF16, 1);
+          }
+          umma_commit(bar_base + V5_WT_EMPTY + 8 * s);
+        }
+        umma_commit(bar_base + V5_ACC_FULL + 8 * acc);
+      }
+    }
+  } else {
+    ts_epilogue(q, tmem, bar_base + V5_ACC_FULL, bar_base + V5_ACC_EMPTY, reinterpret_cast<double*>(bar_ptr + 256), my_tiles,
+                total, dbg_on);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 
 // ------------------------------------------------------------------------------------------
 // tc_wgrad_kernel_v2: the weight gradient with the operand roles SWAPPED and the MMAs 256 columns wide.
@@ -1432,11 +1681,6 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d, uint64_t a, uint64_t b, 
                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
-__device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-               ::"r"(d), "r"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
-}
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int variant, int reps, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1555,6 +1799,7 @@ int ensure_smem_attr() {
                                         V4Cfg<3>::kSmemBytes));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v4<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         V4Cfg<1>::kSmemBytes));
+    DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v6, cudaFuncAttributeMaxDynamicSharedMemorySize, V6_SMEM_BYTES));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v5<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         V5Cfg<3>::kSmemBytes));
     DCGC_CUDA_CALL(cudaFuncSetAttribute(tc_gemm_kernel_v5<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1627,6 +1872,30 @@ ImgShape img_shape(int nt, int k1, int k2, int N, int n_groups) {
   s.bytes = (size_t)n_groups * s.n_tiles_n * (s.chunks > 0 ? s.chunks : 1) * s.b_tiles * TC_TILE_BYTES;
   return s;
 }
+// fp16x3 image (tc_prep_image_f16): K padded per operand to multiples of 64, two 16 KB tiles per chunk
+ImgShape img_shape_f16(int k1, int k2, int N, int n_groups) {
+  ImgShape s;
+  s.k1_pad = (k1 + 63) / 64 * 64;
+  s.k_pad = s.k1_pad + (k2 + 63) / 64 * 64;
+  s.n_tiles_n = (N + TC_BN - 1) / TC_BN;
+  s.chunks = s.k_pad / 64;
+  s.b_tiles = 2;
+  s.bytes = (size_t)n_groups * s.n_tiles_n * (s.chunks > 0 ? s.chunks : 1) * 2 * TC_TILE_BYTES;
+  return s;
+}
+int launch_prep_f16(const float* w, int n_groups, int trans_w, int k1, int k2, int N, float* img, cudaStream_t st) {
+  const ImgShape sh = img_shape_f16(k1, k2, N, n_groups);
+  if (sh.chunks <= 0 || N <= 0) return DCGC_OK;
+  ImgArgs ia{};
+  ia.src = w; ia.img = img; ia.n = N; ia.k1 = k1; ia.k2 = k2; ia.k1_pad = sh.k1_pad; ia.trans = trans_w;
+  ia.n_tiles = sh.n_tiles_n; ia.chunks = sh.chunks;
+  if (trans_w) { ia.src_ld = N; ia.src_group_stride = (int64_t)(k1 + k2) * N; }
+  else { ia.src_ld = k1; ia.src_group_stride = (int64_t)N * k1; }
+  dim3 pgrid((unsigned)sh.chunks * 8, (unsigned)sh.n_tiles_n, (unsigned)n_groups);
+  tc_prep_image_f16<<<pgrid, 256, 0, st>>>(ia);
+  DCGC_CUDA_LAUNCH_CHECK("tc_prep_image_f16");
+  return DCGC_OK;
+}
 int launch_prep(int nt, const float* w, int n_groups, int trans_w, int k1, int k2, int N, float* img, cudaStream_t st) {
   const ImgShape sh = img_shape(nt, k1, k2, N, n_groups);
   if (sh.chunks <= 0 || N <= 0) return DCGC_OK;
@@ -1652,6 +1921,20 @@ int dcgc_tc_prep_weights(int nt, const float* w, int n_groups, int trans_w, int 
   return launch_prep(nt, w, n_groups, trans_w, k1, k2, N, img, st);
 }
 
+int64_t dcgc_tc_image_bytes_f16(int k1, int k2, int N, int n_groups) { return (int64_t)img_shape_f16(k1, k2, N, n_groups).bytes; }
+int dcgc_tc_prep_weights_f16(const float* w, int n_groups, int trans_w, int k1, int k2, int N, float* img, cudaStream_t st) {
+  DCGC_CHECK_ARG(w && img && (reinterpret_cast<uintptr_t>(img) & 127) == 0, "dcgc_tc_prep_weights_f16: bad pointer");
+  int st_ = ensure_smem_attr();
+  if (st_ != DCGC_OK) return st_;
+  return launch_prep_f16(w, n_groups, trans_w, k1, k2, N, img, st);
+}
+// 1 if a converter of the fp16x3 forward kernel has seen |x| > 60 000 since the library was loaded (synchronises)
+extern "C" int dcgc_tc_f16_overflow(void) {
+  int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_f16_overflow, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return v;
+}
+
 // Called by dcgc_group_gemm_fwd / _dgrad / dcgc_linear_* in the tensor-core modes; nt = 3 (DCGC_GEMM_TF32X3) or
 // 1 (DCGC_GEMM_BF16).
 //   trans_w = 1: w is [G][k1+k2][n] (forward);  trans_w = 0: w is [G][n1+n2][k1] (dgrad / nn.Linear forward)
@@ -1672,8 +1955,18 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
     const int n_tiles_n = (N + TC_BN - 1) / TC_BN, chunks = k_pad / TC_BK;
     float* img = const_cast<float*>(ready_img);
     static const int knockout = [] { const char* e = getenv("DCGC_TC_KNOCKOUT"); return e ? atoi(e) : 0; }();
+    static const bool use_v4 = [] { const char* e = getenv("DCGC_TC_V4"); return e && e[0] == '1'; }();
+    const bool tma_ok = !use_v4 && ld_a1 % 4 == 0 && aligned16(a1) && (!a2 || (ld_a2 % 4 == 0 && aligned16(a2))) &&
+                        n_rows < (1ll << 31);
+    // fp16x3 forward kernel (v6): asked for by the caller, TF32x3 mode, TMA-feedable operands
+    const bool f16 = opts && opts->f16x3 && nt == 3 && tma_ok;
     float* own_img = nullptr;
-    if (img == nullptr) {
+    if (img == nullptr && f16) {
+      DCGC_CUDA_CALL(cudaMallocAsync((void**)&own_img, img_shape_f16(k1, a2 ? k2 : 0, N, n_groups).bytes, st));
+      img = own_img;
+      st_ = launch_prep_f16(w, n_groups, trans_w, k1, a2 ? k2 : 0, N, img, st);
+      if (st_ != DCGC_OK) { cudaFreeAsync(own_img, st); return st_; }
+    } else if (img == nullptr) {
       // no image from the caller: a stream-ordered scratch allocation (no hidden buffer, no synchronisation; the
       // driver's pool makes it an O(1) call after the first use) freed in stream order right after the launch
       DCGC_CUDA_CALL(cudaMallocAsync((void**)&own_img, img_shape(nt, k1, a2 ? k2 : 0, N, n_groups).bytes, st));
@@ -1705,8 +1998,14 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
     p3.stats = stats;
     if (stats_chunks) *stats_chunks = ctas;
     dim3 grid((unsigned)ctas, (unsigned)n_tiles_n);
-    static const bool use_v4 = [] { const char* e = getenv("DCGC_TC_V4"); return e && e[0] == '1'; }();
-    if (use_v4 || !p3.a1_vec || (a2 && !p3.a2_vec) || n_rows >= (1ll << 31)) {
+    if (f16) {
+      alignas(64) CUtensorMap m1, m2;
+      st_ = make_a_map(&m1, a1, n_rows, k1, ld_a1, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (st_ == DCGC_OK) st_ = a2 ? make_a_map(&m2, a2, n_rows, k2, ld_a2, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B)
+                                   : make_a_map(&m2, a1, n_rows, k1, ld_a1, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (st_ != DCGC_OK) { if (own_img) cudaFreeAsync(own_img, st); return st_; }
+      tc_gemm_kernel_v6<<<grid, V5_THREADS, V6_SMEM_BYTES, st>>>(q3, m1, m2);
+    } else if (!tma_ok) {
       // register-fed producers: operands whose rows are not 16-byte aligned (no tensor map), or DCGC_TC_V4=1
       if (nt == 3) tc_gemm_kernel_v4<3><<<grid, V4_THREADS, V4Cfg<3>::kSmemBytes, st>>>(q3);
       else tc_gemm_kernel_v4<1><<<grid, V4_THREADS, V4Cfg<1>::kSmemBytes, st>>>(q3);

@@ -845,6 +845,13 @@ int side_stream(SideStream** out) {
   *out = &it->second;
   return DCGC_OK;
 }
+// Forward GEMMs of the TF32x3 mode in fp16x3 (tc_gemm_kernel_v6: half the tensor-core instructions, the same 22-bit
+// products; activations are in fp16's range by construction, gradients are not, so the backward GEMMs stay TF32x3).
+// DCGC_FWD_F16X3=0 keeps the forward pass on tf32 halves.
+bool fwd_f16x3_on(const dcgc_gcmodel_config* cfg) {
+  static const bool on = [] { const char* e = getenv("DCGC_FWD_F16X3"); return !(e && e[0] == '0'); }();
+  return on && cfg->gemm_mode == DCGC_GEMM_TF32X3;
+}
 bool early_images_on() {
   // measured (profiles/r3i_*): forward GEMM scopes 239 -> 210 us, dgrad 141 -> 131 us, step 1.2445 -> 1.2333 ms
   static const bool on = [] { const char* e = getenv("DCGC_EARLY_IMAGES"); return !(e && e[0] == '0'); }();
@@ -1016,7 +1023,8 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
     if (l == 0 && sv.img_fwd_ready) DCGC_CUDA_CALL(cudaStreamWaitEvent(st, sv.img_fwd_ready, 0));
     DcgcGemmOpts go;
     go.img = sv.img_fwd[l];
-    go.a_exact = (l == 0 && cfg->input_exact) ? 1 : 0;      // integer-valued features: [X | S] is exact in tf32
+    go.a_exact = (l == 0 && cfg->input_exact) ? 1 : 0;      // integer-valued features: [X | S] is exact in tf32 / fp16
+    go.f16x3 = fwd_f16x3_on(cfg) ? 1 : 0;
     const DcgcBnFin fin = fuse_stats ? fwd_fin(cfg, lo, l, c, N, params, bn_running, sv) : DcgcBnFin{};
     if (fin.kind) go.fin = &fin;
     RET_IF(dcgc_group_gemm_fwd_opts(cfg->gemm_mode, h, ld, fp, sv.s[l], fp, fp, params + lo.conv_w[l], sv.b11[l], c,
@@ -1041,6 +1049,7 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
     const bool fuse_d = cfg->batch_norm && training && dcgc_tc_terms(cfg->gemm_mode) != 0;
     DcgcGemmOpts go;
     go.img = sv.img_dense;
+    go.f16x3 = fwd_f16x3_on(cfg) ? 1 : 0;
     fin_d = fuse_d ? fwd_fin(cfg, lo, L, D, N, params, bn_running, sv) : DcgcBnFin{};
     if (fin_d.kind) go.fin = &fin_d;
     RET_IF(dcgc_linear_fwd_opts(cfg->gemm_mode, sv.h[L], sv.ld_h[L], lo.f[L], params + lo.dense_w, params + lo.dense_b,
@@ -1237,9 +1246,13 @@ extern "C" int dcgc_gcmodel_train_step_sync(const dcgc_gcmodel_config* cfg, cons
     }
     DCGC_CUDA_CALL(cudaEventRecord(side->e0, st));
     DCGC_CUDA_CALL(cudaStreamWaitEvent(side->s, side->e0, 0));
-    for (int l = 0; l < L; ++l)       // forward: [X | S] . W[g], W stored [G][2 fp][c]
-      RET_IF(dcgc_tc_prep_weights(nt, params + lo.conv_w[l], DCGC_N_DEG, 1, lo.fp[l], lo.fp[l], cfg->widths[l], imf[l], side->s));
-    RET_IF(dcgc_tc_prep_weights(nt, params + lo.dense_w, 1, 0, lo.f[L], 0, D, im_dense, side->s));   // nn.Linear layout
+    const bool f16 = fwd_f16x3_on(cfg);     // (the fp16 images are never larger than the tf32 ones they replace)
+    for (int l = 0; l < L; ++l) {     // forward: [X | S] . W[g], W stored [G][2 fp][c]
+      if (f16) RET_IF(dcgc_tc_prep_weights_f16(params + lo.conv_w[l], DCGC_N_DEG, 1, lo.fp[l], lo.fp[l], cfg->widths[l], imf[l], side->s));
+      else RET_IF(dcgc_tc_prep_weights(nt, params + lo.conv_w[l], DCGC_N_DEG, 1, lo.fp[l], lo.fp[l], cfg->widths[l], imf[l], side->s));
+    }
+    if (f16) RET_IF(dcgc_tc_prep_weights_f16(params + lo.dense_w, 1, 0, lo.f[L], 0, D, im_dense, side->s));
+    else RET_IF(dcgc_tc_prep_weights(nt, params + lo.dense_w, 1, 0, lo.f[L], 0, D, im_dense, side->s));   // nn.Linear layout
     DCGC_CUDA_CALL(cudaEventRecord(side->e1, side->s));
     RET_IF(dcgc_tc_prep_weights(nt, params + lo.dense_w, 1, 1, D, 0, lo.f[L], im_dense_d, side->s)); // dx = g . w
     for (int l = L - 1; l >= 1; --l)  // dgrad: G . W[g]^T, the same W read as [G][2 fp][c] = [n1 + n2][k1]

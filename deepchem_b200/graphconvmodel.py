@@ -570,6 +570,16 @@ class _Prefetcher(object):
                 self.thread.join(timeout=0.05)
 
 
+def _check_f16_range(model):
+    """The fused engine runs its forward GEMMs with fp16 operand halves (DCGC_GEMM_F16X3, csrc/gemm_tc.cu): raise if a
+    forward GEMM has seen an operand outside fp16's range — its results are then wrong, not merely inexact."""
+    if model._engine is None or model.device.type != "cuda":
+        return
+    if _lib_mod.lib().dcgc_tc_f16_overflow() == 1:
+        raise FloatingPointError("an activation above 60 000 reached a forward GEMM that runs with fp16 operand halves; "
+                                 "set DCGC_FWD_F16X3=0 (TF32 halves) for data of this range")
+
+
 class GraphConvModel(object):
     """Graph convolutional model on the B200 path.
 
@@ -915,6 +925,7 @@ class GraphConvModel(object):
         if self.model_dir and checkpoint_interval > 0:
             self.save_checkpoint(max_checkpoints_to_keep)
         logger.info("TIMING: model fitting took %0.3f s" % (time.time() - t0))
+        _check_f16_range(self)
         return state["last"]
 
     def _train_step(self, inputs, labels, weights):
@@ -1097,6 +1108,7 @@ class GraphConvModel(object):
                     final = [h[:o].numpy() for h, o in zip(host, offs)]      # views keep the pinned tensors alive
                 else:
                     final = [torch.cat(c, dim=0).cpu().numpy() for c in chunks]
+                _check_f16_range(self)
                 return final[0] if len(final) == 1 else final
             for batch in generator:
                 inputs, _, _ = self._prepare_batch(batch)

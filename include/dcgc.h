@@ -42,6 +42,10 @@ extern "C" {
 #define DCGC_GEMM_FP32 0 /* SIMT FFMA, fp32 in / fp32 accumulate: the 1e-5 parity mode        */
 #define DCGC_GEMM_BF16 1 /* tcgen05, operands rounded to bf16 / fp32 accumulate: the 2e-2 mode     */
 #define DCGC_GEMM_TF32X3 2 /* tcgen05 kind::tf32 with 3-term split: fp32-grade accuracy       */
+#define DCGC_GEMM_F16X3 3 /* forward entry points (dcgc_group_gemm_fwd*, dcgc_linear_fwd): the same 3-term split with
+                             fp16 halves (kind::f16, K 16 per instruction: half the tensor-core instructions, the same
+                             11 + 11 significand bits) for operands inside fp16's range, |x| < 65 504 — activations,
+                             not gradients; everywhere else it means DCGC_GEMM_TF32X3 */
 
 const char* dcgc_last_error(void);
 int dcgc_version(void);
@@ -523,6 +527,12 @@ int dcgc_lstm_step_bwd(const float* z_dev, int64_t ld_z, const float* c_in_dev, 
 
 /* param_offsets: 4 per conv layer (W, b, gamma, beta), then dense (W, b, gamma, beta), then head
  * (W, b); -1 where batch_norm is off.  bn_offsets: (mean, var) per BN, conv layers then dense. */
+/* The fused engine runs the FORWARD GEMMs of the TF32x3 mode with fp16 operand halves (same 11 + 11 significand bits,
+ * half the tensor-core instructions); fp16 overflows above 65 504.  Returns 1 if a forward GEMM has seen an operand
+ * above 60 000 since the library was loaded (its results are then not to be trusted: set DCGC_FWD_F16X3=0), 0 if not,
+ * -1 on a CUDA error.  Synchronises the device. */
+int dcgc_tc_f16_overflow(void);
+
 int dcgc_gcmodel_layout(const dcgc_gcmodel_config* cfg, int64_t* param_offsets, int64_t* bn_offsets,
                         int64_t* n_params, int64_t* n_bn);
 int64_t dcgc_gcmodel_workspace_bytes(const dcgc_gcmodel_config* cfg, int64_t n_atoms,

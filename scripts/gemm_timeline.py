@@ -11,7 +11,7 @@ x = torch.randn(n, 128, device=dev); s = torch.randn(n, 128, device=dev)
 w = torch.randn(11, 256, 128, device=dev) / 16; b = torch.randn(11, 128, device=dev)
 L = _lib.lib()
 L.dcgcdbg_tc_timeline.argtypes = [ctypes.c_void_p]; L.dcgcdbg_tc_timeline.restype = None
-for mode, name in ((_lib.GEMM_TF32X3, "tf32x3"), (_lib.GEMM_BF16, "bf16")):
+for mode, name in ((_lib.GEMM_TF32X3, "tf32x3"), (_lib.GEMM_F16X3, "f16x3 (64-wide chunks: 4 per tile)"), (_lib.GEMM_BF16, "bf16")):
     for _ in range(3):
         ops.group_gemm_fwd(x, s, w, b, topo, 1, mode)
     buf = torch.zeros(6000, dtype=torch.int64, device=dev)
@@ -21,7 +21,7 @@ for mode, name in ((_lib.GEMM_TF32X3, "tf32x3"), (_lib.GEMM_BF16, "bf16")):
     L.dcgcdbg_tc_timeline(None)
     t = buf.cpu().numpy().astype(np.int64)
     t0 = t[5000]
-    total = 8
+    total = 4 if mode == _lib.GEMM_F16X3 else 8
     tiles = int((t[4096:4096 + 64:2] > 0).sum())
     print("== %s: %d tiles on CTA 0; cycles relative to kernel start (1 cycle = 0.51 ns at 1965 MHz)" % (name, tiles))
     print("tile | mma first chunk seen | mma last chunk seen | prod0 first/last commit | prod1 first/last | B first/last issue | epi start | epi end")

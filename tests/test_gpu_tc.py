@@ -287,3 +287,52 @@ def test_bf16_model_step_within_two_percent():
     oracle, whole gradient within 25 % in norm (per-tensor 2e-2 is out of reach of bf16 operand rounding through
     BatchNorm backward passes: tests/test_gpu_engine_fp64.py)."""
     _engine_vs_float64("bf16", 2e-2, seed=6)
+
+
+@pytest.mark.parametrize("k,c,act", [(128, 128, 1), (76, 128, 0), (64, 64, 1), (128, 256, 0), (75, 100, 2), (40, 128, 1)])
+def test_f16x3_group_gemm_forward(k, c, act):
+    """The forward GEMM with fp16 operand halves (tc_gemm_kernel_v6, DCGC_GEMM_F16X3: what the fused engine runs for
+    its forward pass) against float64: the same 1e-5 bar as the tf32 halves for operands inside fp16's range, K tails
+    that are not multiples of 64 included; and the sticky overflow flag stays clear."""
+    from deepchem_b200 import ops, _lib
+    dev = _cuda()
+    topo = _topo()
+    n = topo.n_atoms
+    g = torch.Generator(device=dev).manual_seed(11)
+    kp = (k + 3) // 4 * 4
+    x = torch.zeros(n, kp, device=dev)
+    s = torch.zeros(n, kp, device=dev)
+    x[:, :k] = torch.randn(n, k, device=dev, generator=g)
+    s[:, :k] = torch.randn(n, k, device=dev, generator=g) * 5.0        # neighbour sums are larger than the features
+    x._dcgc_zero_padded = s._dcgc_zero_padded = True
+    w = torch.randn(11, 2 * kp, c, device=dev, generator=g) / np.sqrt(2 * k)
+    b = torch.randn(11, c, device=dev, generator=g)
+    y16 = ops.group_gemm_fwd(x, s, w, b, topo, act, _lib.GEMM_F16X3)
+    y32 = ops.group_gemm_fwd(x, s, w, b, topo, act, _lib.GEMM_TF32X3)
+    deg = torch.repeat_interleave(torch.arange(11, device=dev), torch.tensor(topo.deg_count, device=dev))
+    a = torch.cat([x, s], 1).double()
+    ref = torch.bmm(a.unsqueeze(1), w.double()[deg]).squeeze(1) + b.double()[deg]
+    ref = torch.relu(ref) if act == 1 else (torch.tanh(ref) if act == 2 else ref)
+    assert _rel(y32, ref) < TOL
+    assert _rel(y16, ref) < TOL, _rel(y16, ref)
+    assert _lib.lib().dcgc_tc_f16_overflow() == 0
+
+
+def test_f16x3_linear_forward_and_small_magnitudes():
+    """nn.Linear layout through the fp16x3 kernel, and operands far below 1 (their lo halves fall into fp16's
+    subnormal range: the absolute error bound, 3e-8 per element, still holds the 1e-5 bar of the output scale)."""
+    from deepchem_b200 import _lib
+    import ctypes
+    dev = _cuda()
+    g = torch.Generator(device=dev).manual_seed(12)
+    for scale in (1.0, 1e-2):
+        x = torch.randn(3000, 128, device=dev, generator=g) * scale
+        x[:, ::7] *= 1e-3                                   # a few very small columns next to ordinary ones
+        w = torch.randn(96, 128, device=dev, generator=g) / 11.0
+        b = torch.randn(96, device=dev, generator=g) * scale
+        y = torch.empty(3000, 96, device=dev)
+        _lib.check(_lib.lib().dcgc_linear_fwd(_lib.GEMM_F16X3, x.data_ptr(), 128, 128, w.data_ptr(), b.data_ptr(), 96,
+                                              3000, 0, y.data_ptr(), 96,
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ref = x.double() @ w.double().t() + b.double()
+        assert _rel(y, ref) < TOL, scale
