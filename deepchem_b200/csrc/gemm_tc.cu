@@ -198,7 +198,14 @@ __global__ void __launch_bounds__(256) tc_prep_image(const ImgArgs p) {
 // Weight image of the fp16x3 forward kernel (tc_gemm_kernel_v6): per (group, n-tile, 64-wide K chunk) a hi tile and a lo
 // tile of [128 rows x 64 halves] = 16 KB each, K-major SWIZZLE_128B (a 128-byte row holds 64 K values instead of the 32
 // of the tf32 image).  hi = fp16(w), lo = fp16(w - hi): w = hi + lo to ~2^-22 (11 + 11 significand bits), or to an
-// absolute 3e-8 where lo falls into fp16's subnormal range.  K is padded per operand to multiples of 64.
+// absolute 3e-8 / kF16Scale where lo falls into fp16's subnormal range.  Both operands are multiplied by kF16Scale
+// (a power of two: exact, undone by the epilogue's 1 / kF16Scale^2) before the split, so that lo stays a normal fp16
+// number down to |x| = 2^-3 / kF16Scale instead of 2^-3 — weights of a 128..300-wide layer sit around 0.05.  The price
+// is range: |x| kF16Scale must stay below fp16's 65504, checked on both operands (g_f16_overflow).  K is padded per
+// operand to multiples of 64.
+constexpr float kF16Scale = 16.f;
+constexpr float kF16Limit = 60000.f / kF16Scale;
+__device__ int g_f16_overflow = 0;
 __global__ void __launch_bounds__(256) tc_prep_image_f16(const ImgArgs p) {
   // one block = an eighth (1024 elements) of one [128 x 64] tile
   const int g = blockIdx.z, nt = blockIdx.y, ch = blockIdx.x >> 3, part = blockIdx.x & 7;
@@ -221,8 +228,9 @@ __global__ void __launch_bounds__(256) tc_prep_image_f16(const ImgArgs p) {
         v = __ldg(p.src + g * p.src_group_stride + (int64_t)nn * p.src_ld + kk);
       }
     }
-    const __half h = __float2half_rn(v);
-    const __half l = __float2half_rn(v - __half2float(h));
+    if (fabsf(v) > kF16Limit) g_f16_overflow = 1;
+    const __half h = __float2half_rn(v * kF16Scale);
+    const __half l = __float2half_rn(fmaf(v, kF16Scale, -__half2float(h)));
     const uint32_t o = (swz(r, kl >> 3) >> 1) + (kl & 7);      // half index inside the 16 KB tile
     blk[o] = h;
     blk[TC_BM * 64 + o] = l;
@@ -236,6 +244,7 @@ struct TcArgs3 {
   long long* dbg;  // optional timeline buffer (dcgcdbg_tc_timeline): CTA (0,0) records clock64() per role and chunk
   int a_exact;    // v4: every A value is exactly representable in tf32 (integer-valued features and their neighbour
                   // sums): the lo(A) tile is identically zero, its stores and the lo(A)*hi(W) MMA are skipped
+  float acc_scale; // the epilogue multiplies the accumulators by this (1, or 1 / kF16Scale^2 in the fp16x3 kernel)
   DcgcBnFin bnfin; // v4 / v5 with column statistics: BatchNorm finalize by the last CTA (kind 0 = off)
   int knockout;   // debugging aid (env DCGC_TC_KNOCKOUT): 1 no output stores, 2 no MMAs, 4 no A loads,
                   // 8 no weight copies, 16 no A shared-memory stores, 32 no TMEM loads, 64 no proxy fence,
@@ -324,6 +333,7 @@ __device__ __forceinline__ void ts_epilogue(const TcArgs3& q, uint32_t tmem, uin
 #pragma unroll
   for (int i = 0; i < 16; ++i) { su[i] = 0.f; sq[i] = 0.f; }
   const int act = p.act;
+  const float acc_scale = q.acc_scale;
   for (int it = 0; it < my_tiles; ++it) {
     int row0, rows, g;
     tile_of(p, pid + it * P, row0, rows, g);
@@ -371,8 +381,8 @@ __device__ __forceinline__ void ts_epilogue(const TcArgs3& q, uint32_t tmem, uin
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
           for (int rr = 0; rr < 2; ++rr) {
-            float ox = __uint_as_float(v[4 * j + 2 * rr]) + bv[j].x;
-            float oy = __uint_as_float(v[4 * j + 2 * rr + 1]) + bv[j].y;
+            float ox = fmaf(__uint_as_float(v[4 * j + 2 * rr]), acc_scale, bv[j].x);      // acc_scale 1: the plain sum
+            float oy = fmaf(__uint_as_float(v[4 * j + 2 * rr + 1]), acc_scale, bv[j].y);
             if (act == DCGC_ACT_RELU) { ox = fmaxf(ox, 0.f); oy = fmaxf(oy, 0.f); }
             else if (act == DCGC_ACT_TANH) { ox = tanhf(ox); oy = tanhf(oy); }
             o[4 * j + 2 * rr] = ox; o[4 * j + 2 * rr + 1] = oy;
@@ -931,7 +941,6 @@ static_assert(V6_A_STAGES % 2 == 0 && V6_W_STAGES % 2 == 0, "ring depths must be
 constexpr int V6_SMEM_BYTES = V6_A_STAGES * 2 * TC_TILE_BYTES + V6_W_STAGES * 2 * TC_TILE_BYTES + 1024 + 256 + 8 * 2 * 64 * 8;
 // kind::f16 instruction descriptor: D = f32, A = B = fp16 (format 0), both K-major, N = 128, M = 128
 constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-__device__ int g_f16_overflow = 0;
 __device__ __forceinline__ void umma_f16_ts(uint32_t d, uint32_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
@@ -1007,14 +1016,15 @@ tc_gemm_kernel_v6(const TcArgs3 q, const __grid_constant__ CUtensorMap map1, con
         float amax = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[c].x), fabsf(v[c].y)), fmaxf(fabsf(v[c].z), fabsf(v[c].w))));
-        if (amax > 60000.f) g_f16_overflow = 1;              // sticky: the caller must not trust fp16x3 for this data
+        if (amax > kF16Limit) g_f16_overflow = 1;            // sticky: the caller must not trust fp16x3 for this data
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const __half2 h01 = __floats2half2_rn(v[c].x, v[c].y), h23 = __floats2half2_rn(v[c].z, v[c].w);
+          const __half2 h01 = __floats2half2_rn(v[c].x * kF16Scale, v[c].y * kF16Scale);
+          const __half2 h23 = __floats2half2_rn(v[c].z * kF16Scale, v[c].w * kF16Scale);
           const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-          const __half2 l01 = __floats2half2_rn(v[c].x - f01.x, v[c].y - f01.y);
-          const __half2 l23 = __floats2half2_rn(v[c].z - f23.x, v[c].w - f23.y);
+          const __half2 l01 = __floats2half2_rn(fmaf(v[c].x, kF16Scale, -f01.x), fmaf(v[c].y, kF16Scale, -f01.y));
+          const __half2 l23 = __floats2half2_rn(fmaf(v[c].z, kF16Scale, -f23.x), fmaf(v[c].w, kF16Scale, -f23.y));
           hi[2 * c] = *reinterpret_cast<const uint32_t*>(&h01); hi[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&h23);
           lo[2 * c] = *reinterpret_cast<const uint32_t*>(&l01); lo[2 * c + 1] = *reinterpret_cast<const uint32_t*>(&l23);
         }
@@ -1989,6 +1999,7 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
     p3.c2_vec = c2 && ld_c2 % 4 == 0 && aligned16(c2);
     q3.img = img; q3.n_row_tiles = (int)row_tiles; q3.n_tiles_n = n_tiles_n;
     q3.knockout = knockout;
+    q3.acc_scale = f16 ? 1.f / (kF16Scale * kF16Scale) : 1.f;
     q3.a_exact = (opts && opts->a_exact && nt == 3) ? 1 : 0;
     if (opts && opts->fin && stats && opts->fin->width <= 256) q3.bnfin = *opts->fin;   // (needs one thread per column)
     q3.dbg = g_timeline;

@@ -576,8 +576,9 @@ def _check_f16_range(model):
     if model._engine is None or model.device.type != "cuda":
         return
     if _lib_mod.lib().dcgc_tc_f16_overflow() == 1:
-        raise FloatingPointError("an activation above 60 000 reached a forward GEMM that runs with fp16 operand halves; "
-                                 "set DCGC_FWD_F16X3=0 (TF32 halves) for data of this range")
+        raise FloatingPointError("an activation or weight above 3750 reached a forward GEMM that runs with fp16 operand "
+                                 "halves (operands are scaled by 16 before the split); set DCGC_FWD_F16X3=0 (TF32 "
+                                 "halves) for data of this range")
 
 
 class GraphConvModel(object):

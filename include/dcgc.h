@@ -528,8 +528,10 @@ int dcgc_lstm_step_bwd(const float* z_dev, int64_t ld_z, const float* c_in_dev, 
 /* param_offsets: 4 per conv layer (W, b, gamma, beta), then dense (W, b, gamma, beta), then head
  * (W, b); -1 where batch_norm is off.  bn_offsets: (mean, var) per BN, conv layers then dense. */
 /* The fused engine runs the FORWARD GEMMs of the TF32x3 mode with fp16 operand halves (same 11 + 11 significand bits,
- * half the tensor-core instructions); fp16 overflows above 65 504.  Returns 1 if a forward GEMM has seen an operand
- * above 60 000 since the library was loaded (its results are then not to be trusted: set DCGC_FWD_F16X3=0), 0 if not,
+ * half the tensor-core instructions).  Both operands are multiplied by 16 before the split (undone exactly in the
+ * epilogue) so that the low halves of values down to 2^-7 stay normal fp16 numbers; fp16 overflows above 65 504, i.e.
+ * for operands above 4094.  Returns 1 if a forward GEMM has seen an activation or weight above 3750 since the library
+ * was loaded (its results are then not to be trusted: set DCGC_FWD_F16X3=0), 0 if not,
  * -1 on a CUDA error.  Synchronises the device. */
 int dcgc_tc_f16_overflow(void);
 

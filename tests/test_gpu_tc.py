@@ -320,7 +320,8 @@ def test_f16x3_group_gemm_forward(k, c, act):
 
 def test_f16x3_linear_forward_and_small_magnitudes():
     """nn.Linear layout through the fp16x3 kernel, and operands far below 1 (their lo halves fall into fp16's
-    subnormal range: the absolute error bound, 3e-8 per element, still holds the 1e-5 bar of the output scale)."""
+    subnormal range below 2^-7: the absolute error bound, 2e-9 per element, still holds the 1e-5 bar of the output
+    scale)."""
     from deepchem_b200 import _lib
     import ctypes
     dev = _cuda()
@@ -336,3 +337,53 @@ def test_f16x3_linear_forward_and_small_magnitudes():
                                               ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
         ref = x.double() @ w.double().t() + b.double()
         assert _rel(y, ref) < TOL, scale
+
+
+@pytest.mark.gpu
+def test_f16x3_is_as_accurate_as_tf32x3_at_layer_scale_weights():
+    """Weights of a 128..300-wide layer sit around 0.05, where an unscaled fp16 low half would be subnormal (absolute
+    error 3e-8 = 6e-7 relative).  With both operands scaled by 16 before the split the fp16x3 product is as close to
+    the float64 product as the tf32x3 one (both 11 + 11 significand bits); and the sticky range flag rises at 3750."""
+    from deepchem_b200 import _lib
+    import ctypes
+    dev = _cuda()
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.randn(4096, 300, device=dev, generator=g).relu() * 0.3
+    xp = torch.zeros(4096, 304, device=dev)
+    xp[:, :300] = x
+    w = (torch.rand(300, 300, device=dev, generator=g) * 2 - 1) / 300 ** 0.5
+    ref = x.double() @ w.double().t()
+    err = {}
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for name, mode in (("f16", _lib.GEMM_F16X3), ("tf32", _lib.GEMM_TF32X3)):
+        y = torch.empty(4096, 300, device=dev)
+        _lib.check(_lib.lib().dcgc_linear_fwd(mode, xp.data_ptr(), 304, 300, w.data_ptr(), None, 300, 4096, 0,
+                                              y.data_ptr(), 300, st))
+        err[name] = float((y.double() - ref).pow(2).mean().sqrt() / ref.pow(2).mean().sqrt())
+    # (both ~1e-6 at K = 300: the tensor core's fp32 accumulation, one truncation per instruction, dominates — and the
+    # fp16 kind issues half as many instructions; measured 1.1e-6 against 2.1e-6)
+    assert err["f16"] < 1.5 * err["tf32"] + 1e-8 and err["f16"] < 3e-6, err
+    assert _lib.lib().dcgc_tc_f16_overflow() == 0
+
+
+@pytest.mark.gpu
+def test_f16x3_range_flag_rises_above_3750():
+    """The flag is sticky for the life of the process, so the out-of-range call runs in its own interpreter."""
+    import subprocess
+    import sys
+    code = (
+        "import ctypes, torch\n"
+        "from deepchem_b200 import _lib\n"
+        "x = torch.ones(256, 128, device='cuda'); w = torch.ones(128, 128, device='cuda') * 0.01\n"
+        "y = torch.empty(256, 128, device='cuda')\n"
+        "st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)\n"
+        "def run(): _lib.check(_lib.lib().dcgc_linear_fwd(_lib.GEMM_F16X3, x.data_ptr(), 128, 128, w.data_ptr(), None,"
+        " 128, 256, 0, y.data_ptr(), 128, st))\n"
+        "run(); assert _lib.lib().dcgc_tc_f16_overflow() == 0\n"
+        "assert abs(float(y[0, 0]) - 1.28) < 1e-5\n"
+        "x[7, 5] = 3800.0; run(); assert _lib.lib().dcgc_tc_f16_overflow() == 1\n"
+        "print('ok')\n")
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
