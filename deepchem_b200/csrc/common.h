@@ -113,6 +113,9 @@ int64_t dcgc_tc_image_bytes(int nt, int k1, int k2, int N, int n_groups);
 int dcgc_tc_prep_weights(int nt, const float* w, int n_groups, int trans_w, int k1, int k2, int N, float* img, cudaStream_t st);
 int64_t dcgc_tc_image_bytes_f16(int k1, int k2, int N, int n_groups);
 int dcgc_tc_prep_weights_f16(const float* w, int n_groups, int trans_w, int k1, int k2, int N, float* img, cudaStream_t st);
+// several images in one launch (arguments as dcgc_tc_prep_weights / _f16 per job; f16 jobs need nt == 3)
+struct DcgcImgJob { const float* w; int n_groups, trans_w, k1, k2, N; float* img; int f16; };
+int dcgc_tc_prep_weights_batch(int nt, const DcgcImgJob* jobs, int n_jobs, cudaStream_t st);
 // the C-ABI entry points of gemm_simt.cu with explicit options (used by the fused engines)
 int dcgc_group_gemm_fwd_opts(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, const float* a2, int64_t ld_a2,
                              int32_t k2, const float* w, const float* bias, int32_t n, const int32_t* tiles,

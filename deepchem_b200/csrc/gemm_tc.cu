@@ -161,10 +161,10 @@ struct ImgArgs {
   int n, k1, k2, k1_pad, trans, src_ld, n_tiles, chunks;
 };
 template <int NT>
-__global__ void __launch_bounds__(256) tc_prep_image(const ImgArgs p) {
+__device__ __forceinline__ void prep_image_body(const ImgArgs& p, int bx, int nt, int g) {
   // one block = a quarter (1024 elements) of one [128 x 32] tile; 4 independent loads per thread
   constexpr int kTiles = NT == 3 ? 2 : 1;   // (hi, lo) or the single bf16-rounded tile
-  const int g = blockIdx.z, nt = blockIdx.y, ch = blockIdx.x >> 2, quarter = blockIdx.x & 3;
+  const int ch = bx >> 2, quarter = bx & 3;
   float* blk = p.img + (((int64_t)g * p.n_tiles + nt) * p.chunks + ch) * (kTiles * TC_BM * TC_BK);
   float v[4];
   int r[4], kl[4];
@@ -194,6 +194,10 @@ __global__ void __launch_bounds__(256) tc_prep_image(const ImgArgs p) {
     if (NT == 3) blk[TC_BM * TC_BK + o] = tf32_lo(v[u], h);
   }
 }
+template <int NT>
+__global__ void __launch_bounds__(256) tc_prep_image(const ImgArgs p) {
+  prep_image_body<NT>(p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
 
 // Weight image of the fp16x3 forward kernel (tc_gemm_kernel_v6): per (group, n-tile, 64-wide K chunk) a hi tile and a lo
 // tile of [128 rows x 64 halves] = 16 KB each, K-major SWIZZLE_128B (a 128-byte row holds 64 K values instead of the 32
@@ -206,9 +210,9 @@ __global__ void __launch_bounds__(256) tc_prep_image(const ImgArgs p) {
 constexpr float kF16Scale = 16.f;
 constexpr float kF16Limit = 60000.f / kF16Scale;
 __device__ int g_f16_overflow = 0;
-__global__ void __launch_bounds__(256) tc_prep_image_f16(const ImgArgs p) {
+__device__ __forceinline__ void prep_image_f16_body(const ImgArgs& p, int bx, int nt, int g) {
   // one block = an eighth (1024 elements) of one [128 x 64] tile
-  const int g = blockIdx.z, nt = blockIdx.y, ch = blockIdx.x >> 3, part = blockIdx.x & 7;
+  const int ch = bx >> 3, part = bx & 7;
   __half* blk = reinterpret_cast<__half*>(p.img) + (((int64_t)g * p.n_tiles + nt) * p.chunks + ch) * (2 * TC_BM * 64);
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
@@ -235,6 +239,30 @@ __global__ void __launch_bounds__(256) tc_prep_image_f16(const ImgArgs p) {
     blk[o] = h;
     blk[TC_BM * 64 + o] = l;
   }
+}
+__global__ void __launch_bounds__(256) tc_prep_image_f16(const ImgArgs p) {
+  prep_image_f16_body(p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Several weight images in ONE launch (the fused engine builds the images of all GEMMs of a step at its start): a
+// linear block index is mapped to (job, x, y, z) through the prefix of the jobs' block counts.
+constexpr int kImgBatchMax = 8;
+struct ImgBatch {
+  ImgArgs job[kImgBatchMax];
+  int first_block[kImgBatchMax + 1];
+  int gx[kImgBatchMax], gy[kImgBatchMax];
+  int f16[kImgBatchMax];
+  int n_jobs;
+};
+template <int NT>
+__global__ void __launch_bounds__(256) tc_prep_image_batch(const __grid_constant__ ImgBatch b) {
+  int j = 0;
+  while (j + 1 < b.n_jobs && (int)blockIdx.x >= b.first_block[j + 1]) ++j;
+  const int lb = (int)blockIdx.x - b.first_block[j];
+  const int bx = lb % b.gx[j], rest = lb / b.gx[j];
+  const int by = rest % b.gy[j], bz = rest / b.gy[j];
+  if (b.f16[j]) prep_image_f16_body(b.job[j], bx, by, bz);
+  else prep_image_body<NT>(b.job[j], bx, by, bz);
 }
 
 struct TcArgs3 {
@@ -1921,6 +1949,38 @@ int launch_prep(int nt, const float* w, int n_groups, int trans_w, int k1, int k
   return DCGC_OK;
 }
 }  // namespace
+
+int dcgc_tc_prep_weights_batch(int nt, const DcgcImgJob* jobs, int n_jobs, cudaStream_t st) {
+  int st_ = ensure_smem_attr();
+  if (st_ != DCGC_OK) return st_;
+  for (int j0 = 0; j0 < n_jobs; j0 += kImgBatchMax) {
+    ImgBatch b{};
+    int blocks = 0;
+    for (int j = j0; j < n_jobs && b.n_jobs < kImgBatchMax; ++j) {
+      const DcgcImgJob& q = jobs[j];
+      DCGC_CHECK_ARG(q.w && q.img && (reinterpret_cast<uintptr_t>(q.img) & 127) == 0, "dcgc_tc_prep_weights_batch: bad pointer");
+      const ImgShape sh = q.f16 ? img_shape_f16(q.k1, q.k2, q.N, q.n_groups) : img_shape(nt, q.k1, q.k2, q.N, q.n_groups);
+      if (sh.chunks <= 0 || q.N <= 0) continue;
+      const int i = b.n_jobs++;
+      ImgArgs& ia = b.job[i];
+      ia.src = q.w; ia.img = q.img; ia.n = q.N; ia.k1 = q.k1; ia.k2 = q.k2; ia.k1_pad = sh.k1_pad; ia.trans = q.trans_w;
+      ia.n_tiles = sh.n_tiles_n; ia.chunks = sh.chunks;
+      if (q.trans_w) { ia.src_ld = q.N; ia.src_group_stride = (int64_t)(q.k1 + q.k2) * q.N; }
+      else { ia.src_ld = q.k1; ia.src_group_stride = (int64_t)q.N * q.k1; }
+      b.f16[i] = q.f16 ? 1 : 0;
+      b.gx[i] = sh.chunks * (q.f16 ? 8 : 4);
+      b.gy[i] = sh.n_tiles_n;
+      b.first_block[i] = blocks;
+      blocks += b.gx[i] * b.gy[i] * q.n_groups;
+    }
+    b.first_block[b.n_jobs] = blocks;
+    if (blocks == 0) continue;
+    if (nt == 3) tc_prep_image_batch<3><<<(unsigned)blocks, 256, 0, st>>>(b);
+    else tc_prep_image_batch<1><<<(unsigned)blocks, 256, 0, st>>>(b);
+    DCGC_CUDA_LAUNCH_CHECK("tc_prep_image_batch");
+  }
+  return DCGC_OK;
+}
 
 // k2 = 0 when the GEMM has no second operand.  Bytes are 1024-aligned sizes (whole 16 KB tiles).
 int64_t dcgc_tc_image_bytes(int nt, int k1, int k2, int N, int n_groups) { return (int64_t)img_shape(nt, k1, k2, N, n_groups).bytes; }

@@ -1247,16 +1247,28 @@ extern "C" int dcgc_gcmodel_train_step_sync(const dcgc_gcmodel_config* cfg, cons
     DCGC_CUDA_CALL(cudaEventRecord(side->e0, st));
     DCGC_CUDA_CALL(cudaStreamWaitEvent(side->s, side->e0, 0));
     const bool f16 = fwd_f16x3_on(cfg);     // (the fp16 images are never larger than the tf32 ones they replace)
-    for (int l = 0; l < L; ++l) {     // forward: [X | S] . W[g], W stored [G][2 fp][c]
-      if (f16) RET_IF(dcgc_tc_prep_weights_f16(params + lo.conv_w[l], DCGC_N_DEG, 1, lo.fp[l], lo.fp[l], cfg->widths[l], imf[l], side->s));
-      else RET_IF(dcgc_tc_prep_weights(nt, params + lo.conv_w[l], DCGC_N_DEG, 1, lo.fp[l], lo.fp[l], cfg->widths[l], imf[l], side->s));
-    }
-    if (f16) RET_IF(dcgc_tc_prep_weights_f16(params + lo.dense_w, 1, 0, lo.f[L], 0, D, im_dense, side->s));
-    else RET_IF(dcgc_tc_prep_weights(nt, params + lo.dense_w, 1, 0, lo.f[L], 0, D, im_dense, side->s));   // nn.Linear layout
-    DCGC_CUDA_CALL(cudaEventRecord(side->e1, side->s));
-    RET_IF(dcgc_tc_prep_weights(nt, params + lo.dense_w, 1, 1, D, 0, lo.f[L], im_dense_d, side->s)); // dx = g . w
+    // ONE launch for all of them (forward images first in block order); DCGC_IMAGE_BATCH=0: one launch per image
+    static const bool batch = [] { const char* e = getenv("DCGC_IMAGE_BATCH"); return !(e && e[0] == '0'); }();
+    DcgcImgJob jobs[2 * DCGC_MODEL_MAX_LAYERS + 2];
+    int nj = 0;
+    for (int l = 0; l < L; ++l)       // forward: [X | S] . W[g], W stored [G][2 fp][c]
+      jobs[nj++] = DcgcImgJob{params + lo.conv_w[l], DCGC_N_DEG, 1, lo.fp[l], lo.fp[l], cfg->widths[l], imf[l], f16 ? 1 : 0};
+    jobs[nj++] = DcgcImgJob{params + lo.dense_w, 1, 0, lo.f[L], 0, D, im_dense, f16 ? 1 : 0};     // nn.Linear layout
+    const int n_fwd = nj;
+    jobs[nj++] = DcgcImgJob{params + lo.dense_w, 1, 1, D, 0, lo.f[L], im_dense_d, 0};             // dx = g . w
     for (int l = L - 1; l >= 1; --l)  // dgrad: G . W[g]^T, the same W read as [G][2 fp][c] = [n1 + n2][k1]
-      RET_IF(dcgc_tc_prep_weights(nt, params + lo.conv_w[l], DCGC_N_DEG, 0, cfg->widths[l], 0, 2 * lo.fp[l], imd[l], side->s));
+      jobs[nj++] = DcgcImgJob{params + lo.conv_w[l], DCGC_N_DEG, 0, cfg->widths[l], 0, 2 * lo.fp[l], imd[l], 0};
+    if (batch) {
+      RET_IF(dcgc_tc_prep_weights_batch(nt, jobs, nj, side->s));
+      DCGC_CUDA_CALL(cudaEventRecord(side->e1, side->s));
+    } else {
+      for (int j = 0; j < nj; ++j) {
+        const DcgcImgJob& q = jobs[j];
+        if (q.f16) RET_IF(dcgc_tc_prep_weights_f16(q.w, q.n_groups, q.trans_w, q.k1, q.k2, q.N, q.img, side->s));
+        else RET_IF(dcgc_tc_prep_weights(nt, q.w, q.n_groups, q.trans_w, q.k1, q.k2, q.N, q.img, side->s));
+        if (j == n_fwd - 1) DCGC_CUDA_CALL(cudaEventRecord(side->e1, side->s));
+      }
+    }
     DCGC_CUDA_CALL(cudaEventRecord(side->e2, side->s));
     for (int l = 0; l < L; ++l) { sv.img_fwd[l] = imf[l]; img_dgrad[l] = imd[l]; }
     sv.img_dense = im_dense;
