@@ -216,6 +216,10 @@ struct Work {
   float *per_elem;                   // [n_mols * n_out]
   float *wo_t, *dwo_t, *dbo;         // W_o^T [fa+H, H], its gradient, bias gradient
   void* wgrad_ws; int64_t wgrad_bytes;
+  // split-weight images of the tensor-core GEMMs (null in DCGC_GEMM_FP32 mode), all built by ONE launch at the start
+  // of the call instead of one launch in front of every GEMM: W_i, W_h, W_o forward, FFN forward; then the dgrad ones
+  float *img_wi, *img_wh, *img_wo, *img_ffn[DCGC_DMPNN_MAX_FFN];
+  float *img_ffn_d[DCGC_DMPNN_MAX_FFN], *img_wo_d, *img_wh_d;
   int64_t total_bytes;
 };
 
@@ -250,7 +254,55 @@ void carve(const dcgc_dmpnn_model_config* c, const Layout& lo, int64_t n_rows, i
   w->wgrad_bytes = wb;
   w->wgrad_ws = base ? base + off : nullptr;
   off += dcgc_align_up(wb, 256);
+  w->img_wi = w->img_wh = w->img_wo = w->img_wo_d = w->img_wh_d = nullptr;
+  for (int i = 0; i < DCGC_DMPNN_MAX_FFN; ++i) w->img_ffn[i] = w->img_ffn_d[i] = nullptr;
+  const int nt = dcgc_tc_terms(c->gemm_mode);
+  if (nt != 0) {
+    const int fa = c->atom_fdim, fi = c->atom_fdim + c->bond_fdim;
+    auto take_img = [&](int k1, int k2, int n) { return take(dcgc_tc_image_bytes(nt, k1, k2, n, 1) / 4); };
+    w->img_wi = take_img(fi, 0, H);
+    w->img_wh = take_img(H, 0, H);
+    w->img_wo = take_img(fa, H, H);
+    for (int i = 0; i < c->ffn_layers; ++i) w->img_ffn[i] = take_img(lo.ffn_in[i], 0, lo.ffn_out[i]);
+    for (int i = 0; i < c->ffn_layers; ++i) w->img_ffn_d[i] = take_img(lo.ffn_out[i], 0, lo.ffn_in[i]);
+    w->img_wo_d = take_img(H, 0, fa + H);
+    w->img_wh_d = take_img(H, 0, H);
+  }
   w->total_bytes = off;
+}
+
+// W_o^T (the two-operand GEMM wants [fa + H, H]) and the weight images of the call, in front of its first GEMM.
+// Job arguments follow the dcgc_tc_gemm calls behind dcgc_linear_fwd / _dgrad and dcgc_group_gemm_fwd / _dgrad
+// (csrc/gemm_simt.cu): forward of nn.Linear weights [n, k] = (trans 0, k, n); dx = g . w = (trans 1, K = n, N = k).
+int build_images(const dcgc_dmpnn_model_config* c, const Layout& lo, const float* params, const Work& w, bool backward,
+                 cudaStream_t st) {
+  const int H = c->hidden, fa = c->atom_fdim, fi = c->atom_fdim + c->bond_fdim;
+  {
+    dim3 grid((unsigned)((fa + H + 31) / 32), (unsigned)((H + 31) / 32));
+    transpose_kernel<<<grid, kT, 0, st>>>(params + lo.w_o, H, fa + H, w.wo_t);
+    DCGC_CUDA_LAUNCH_CHECK("dmpnn transpose W_o");
+  }
+  const int nt = dcgc_tc_terms(c->gemm_mode);
+  if (nt == 0) return DCGC_OK;
+  DcgcImgJob jobs[5 + 2 * DCGC_DMPNN_MAX_FFN];
+  int nj = 0;
+  jobs[nj++] = DcgcImgJob{params + lo.w_i, 1, 0, fi, 0, H, w.img_wi, 0};
+  jobs[nj++] = DcgcImgJob{params + lo.w_h, 1, 0, H, 0, H, w.img_wh, 0};
+  jobs[nj++] = DcgcImgJob{w.wo_t, 1, 1, fa, H, H, w.img_wo, 0};
+  for (int i = 0; i < c->ffn_layers; ++i)
+    jobs[nj++] = DcgcImgJob{params + lo.ffn_w[i], 1, 0, lo.ffn_in[i], 0, lo.ffn_out[i], w.img_ffn[i], 0};
+  if (backward) {
+    for (int i = 0; i < c->ffn_layers; ++i)
+      jobs[nj++] = DcgcImgJob{params + lo.ffn_w[i], 1, 1, lo.ffn_out[i], 0, lo.ffn_in[i], w.img_ffn_d[i], 0};
+    jobs[nj++] = DcgcImgJob{w.wo_t, 1, 0, H, 0, fa + H, w.img_wo_d, 0};
+    jobs[nj++] = DcgcImgJob{params + lo.w_h, 1, 1, H, 0, H, w.img_wh_d, 0};
+  }
+  return dcgc_tc_prep_weights_batch(nt, jobs, nj, st);
+}
+inline DcgcGemmOpts with_img(const float* img) {
+  DcgcGemmOpts o{};
+  o.img = img;
+  return o;
 }
 
 int check_tables(const dcgc_dmpnn_tables* t) {
@@ -272,7 +324,8 @@ int forward_impl(const dcgc_dmpnn_model_config* c, const Layout& lo, const dcgc_
   const int64_t R = t->n_rows, A = t->n_atoms, B = t->n_mols;
   const int64_t r4 = R * H / 4;
   // input = W_i(f_ini)  (layers.py:1622);  message = act(input)  (:1624)
-  RET_IF(dcgc_linear_fwd(mode, fini, ld_fi, fi, params + lo.w_i, nullptr, H, R, DCGC_ACT_NONE, w.r0, H, st));
+  RET_IF(dcgc_linear_fwd_opts(mode, fini, ld_fi, fi, params + lo.w_i, nullptr, H, R, DCGC_ACT_NONE, w.r0, H, nullptr, nullptr,
+                              with_img(w.img_wi), st));
   // message = message[mapping].sum(1), depth - 1 times  (:1627-1629); the first gather reads act(input) on the fly
   float *src = w.r1, *dst = w.r2;
   for (int d = 1; d < c->depth; ++d) {
@@ -283,7 +336,8 @@ int forward_impl(const dcgc_dmpnn_model_config* c, const Layout& lo, const dcgc_
     float* tmp = src; src = dst; dst = tmp;
   }
   // src == msg_final; h_message = act(input + W_h(message))  (:1630-1633, only the last product is live)
-  RET_IF(dcgc_linear_fwd(mode, src, H, H, params + lo.w_h, nullptr, H, R, DCGC_ACT_NONE, dst, H, st));
+  RET_IF(dcgc_linear_fwd_opts(mode, src, H, H, params + lo.w_h, nullptr, H, R, DCGC_ACT_NONE, dst, H, nullptr, nullptr,
+                              with_img(w.img_wh), st));
   if (r4 > 0) {
     add_relu_kernel<<<blocks_for(r4), kT, 0, st>>>(reinterpret_cast<const float4*>(w.r0), reinterpret_cast<const float4*>(dst),
                                                   reinterpret_cast<float4*>(w.r3), r4);
@@ -291,13 +345,8 @@ int forward_impl(const dcgc_dmpnn_model_config* c, const Layout& lo, const dcgc_
   }
   // messages to atoms (:1539), atoms_hidden = act(W_o(cat(atom_features, m2a)))  (:1541-1547)
   RET_IF(dcgc_gather_sum(w.r3, H, t->a2b_ptr, t->a2b_idx, A, H, nullptr, 0, w.a0, H, st));
-  {
-    dim3 grid((unsigned)((fa + H + 31) / 32), (unsigned)((H + 31) / 32));
-    transpose_kernel<<<grid, kT, 0, st>>>(params + lo.w_o, H, fa + H, w.wo_t);
-    DCGC_CUDA_LAUNCH_CHECK("dmpnn transpose W_o");
-  }
-  RET_IF(dcgc_group_gemm_fwd(mode, af, ld_af, fa, w.a0, H, H, w.wo_t, params + lo.b_o, H, nullptr, 0, 128, A,
-                             DCGC_ACT_RELU, w.a1, H, st));
+  RET_IF(dcgc_group_gemm_fwd_opts(mode, af, ld_af, fa, w.a0, H, H, w.wo_t, params + lo.b_o, H, nullptr, 0, 128, A,
+                                  DCGC_ACT_RELU, w.a1, H, nullptr, nullptr, with_img(w.img_wo), st));
   // readout (:1550-1583)
   RET_IF(dcgc_segment_readout_fwd(w.a1, H, t->mol_ptr, B, H, c->aggregation, c->aggregation_norm, w.enc, H, st));
   // feed-forward (layers.py:880-910 with dropout 0)
@@ -307,8 +356,8 @@ int forward_impl(const dcgc_dmpnn_model_config* c, const Layout& lo, const dcgc_
     const bool last = i == c->ffn_layers - 1;
     float* y = last && out ? out : w.x[i];
     const int64_t ld_y = last && out ? ld_out : pad4(lo.ffn_out[i]);
-    RET_IF(dcgc_linear_fwd(mode, x, ld_x, lo.ffn_in[i], params + lo.ffn_w[i], params + lo.ffn_b[i], lo.ffn_out[i], B,
-                           last ? DCGC_ACT_NONE : DCGC_ACT_RELU, y, ld_y, st));
+    RET_IF(dcgc_linear_fwd_opts(mode, x, ld_x, lo.ffn_in[i], params + lo.ffn_w[i], params + lo.ffn_b[i], lo.ffn_out[i], B,
+                                last ? DCGC_ACT_NONE : DCGC_ACT_RELU, y, ld_y, nullptr, nullptr, with_img(w.img_ffn[i]), st));
     x = y; ld_x = ld_y;
   }
   return DCGC_OK;
@@ -354,6 +403,7 @@ extern "C" int dcgc_dmpnn_model_forward(const dcgc_dmpnn_model_config* cfg, cons
   DCGC_CHECK_ARG(workspace_bytes >= w.total_bytes, "dcgc_dmpnn_model_forward: workspace too small (%lld < %lld)",
                  (long long)workspace_bytes, (long long)w.total_bytes);
   cudaStream_t st = (cudaStream_t)stream;
+  RET_IF(build_images(cfg, lo, params, w, false, st));
   RET_IF(forward_impl(cfg, lo, t, atom_feat, ld_af, f_ini, ld_fi, params, w, out, cfg->n_out, st));
   if (encoding_out)
     DCGC_CUDA_CALL(cudaMemcpyAsync(encoding_out, w.enc, (size_t)t->n_mols * cfg->hidden * 4, cudaMemcpyDeviceToDevice, st));
@@ -384,6 +434,7 @@ extern "C" int dcgc_dmpnn_model_train_step(const dcgc_dmpnn_model_config* cfg, c
   const int64_t r4 = R * H / 4, a4 = A * H / 4;
 
   // ---------------- forward (the last linear writes into x[L-1], [B, pad4(T)])
+  RET_IF(build_images(cfg, lo, params, w, true, st));
   RET_IF(forward_impl(cfg, lo, t, atom_feat, ld_af, f_ini, ld_fi, params, w, nullptr, 0, st));
   const int64_t ld_o = pad4(T);
   if (out) DCGC_CUDA_CALL(cudaMemcpy2DAsync(out, (size_t)T * 4, w.x[L - 1], (size_t)ld_o * 4, (size_t)T * 4, (size_t)B,
@@ -431,7 +482,7 @@ extern "C" int dcgc_dmpnn_model_train_step(const dcgc_dmpnn_model_config* cfg, c
     float* dxo = i == 0 ? w.denc : g_next;
     const int64_t ld_dx = i == 0 ? H : pad4(k);
     if (i != 0 && ld_dx != k) DCGC_CUDA_CALL(cudaMemsetAsync(dxo, 0, (size_t)B * ld_dx * 4, st));
-    RET_IF(dcgc_linear_dgrad(mode, g, ld_g, n, params + lo.ffn_w[i], k, B, dxo, ld_dx, st));
+    RET_IF(dcgc_linear_dgrad_opts(mode, g, ld_g, n, params + lo.ffn_w[i], k, B, dxo, ld_dx, with_img(w.img_ffn_d[i]), st));
     if (i != 0) { float* tmp = g; g = g_next; g_next = tmp; }
   }
 
@@ -448,7 +499,8 @@ extern "C" int dcgc_dmpnn_model_train_step(const dcgc_dmpnn_model_config* cfg, c
     DCGC_CUDA_LAUNCH_CHECK("dmpnn transpose dW_o");
   }
   // d(m2a) = g . W_o[:, fa:]  -> a1 (atoms_hidden is not needed any more); atom features need no gradient
-  RET_IF(dcgc_group_gemm_dgrad(mode, w.a2, H, H, w.wo_t, fa, H, nullptr, 0, 128, A, nullptr, 0, w.a1, H, st));
+  RET_IF(dcgc_group_gemm_dgrad_opts(mode, w.a2, H, H, w.wo_t, fa, H, nullptr, 0, 128, A, nullptr, 0, w.a1, H,
+                                    with_img(w.img_wo_d), st));
 
   // ---------------- bonds: transposed gathers, ReLU masks, W_h, W_i
   float* mf = msg_final(w, cfg->depth);   // message after the gathers (input of W_h)
@@ -457,7 +509,7 @@ extern "C" int dcgc_dmpnn_model_train_step(const dcgc_dmpnn_model_config* cfg, c
   RET_IF((fused_gather<false, 1>(w.a1, t->a2b_t_ptr, t->a2b_t_idx, R, H, w.r3, nullptr, mo, st)));
   RET_IF(dcgc_linear_wgrad(mode, mf, H, H, mo, H, H, R, grads + lo.w_h, nullptr, w.wgrad_ws, w.wgrad_bytes, st));
   // d(message) = ds . W_h  -> r3 (h is not needed any more), then depth - 1 transposed gathers r3 -> mf -> r3 ...
-  RET_IF(dcgc_linear_dgrad(mode, mo, H, H, params + lo.w_h, H, R, w.r3, H, st));
+  RET_IF(dcgc_linear_dgrad_opts(mode, mo, H, H, params + lo.w_h, H, R, w.r3, H, with_img(w.img_wh_d), st));
   float *src = w.r3, *dst = mf;
   for (int d = 1; d < cfg->depth; ++d) {
     if (d == cfg->depth - 1)   // the last one lands on message_0 = act(input): d(input) = ds + (input > 0) * it, in place in mo
