@@ -11,6 +11,8 @@
 // FFN with >= 2 linears.  depth >= 2 as in the reference (depth 1 leaves h_message unbound there).
 #include <cuda_runtime.h>
 
+#include <stdlib.h>
+
 #include "common.h"
 
 namespace {
@@ -259,7 +261,9 @@ void carve(const dcgc_dmpnn_model_config* c, const Layout& lo, int64_t n_rows, i
   const int nt = dcgc_tc_terms(c->gemm_mode);
   if (nt != 0) {
     const int fa = c->atom_fdim, fi = c->atom_fdim + c->bond_fdim;
-    auto take_img = [&](int k1, int k2, int n) { return take(dcgc_tc_image_bytes(nt, k1, k2, n, 1) / 4); };
+    auto take_img = [&](int k1, int k2, int n) {
+      return take(max64(dcgc_tc_image_bytes(nt, k1, k2, n, 1), dcgc_tc_image_bytes_f16(k1, k2, n, 1)) / 4);
+    };
     w->img_wi = take_img(fi, 0, H);
     w->img_wh = take_img(H, 0, H);
     w->img_wo = take_img(fa, H, H);
@@ -274,9 +278,17 @@ void carve(const dcgc_dmpnn_model_config* c, const Layout& lo, int64_t n_rows, i
 // W_o^T (the two-operand GEMM wants [fa + H, H]) and the weight images of the call, in front of its first GEMM.
 // Job arguments follow the dcgc_tc_gemm calls behind dcgc_linear_fwd / _dgrad and dcgc_group_gemm_fwd / _dgrad
 // (csrc/gemm_simt.cu): forward of nn.Linear weights [n, k] = (trans 0, k, n); dx = g . w = (trans 1, K = n, N = k).
+// Forward GEMMs of the TF32x3 mode with fp16 operand halves (DCGC_GEMM_F16X3, csrc/gemm_tc.cu tc_gemm_kernel_v6: half
+// the tensor-core instructions for the same 22-bit products; 0/1 features, messages and their sums are far inside
+// the range it needs, and the range flag is checked by DMPNNModel).  DCGC_FWD_F16X3=0 keeps tf32 halves.
+int forward_mode(const dcgc_dmpnn_model_config* c) {
+  static const bool on = [] { const char* e = getenv("DCGC_FWD_F16X3"); return !(e && e[0] == '0'); }();
+  return (on && c->gemm_mode == DCGC_GEMM_TF32X3) ? DCGC_GEMM_F16X3 : c->gemm_mode;
+}
 int build_images(const dcgc_dmpnn_model_config* c, const Layout& lo, const float* params, const Work& w, bool backward,
                  cudaStream_t st) {
   const int H = c->hidden, fa = c->atom_fdim, fi = c->atom_fdim + c->bond_fdim;
+  const int f16 = forward_mode(c) == DCGC_GEMM_F16X3 ? 1 : 0;
   {
     dim3 grid((unsigned)((fa + H + 31) / 32), (unsigned)((H + 31) / 32));
     transpose_kernel<<<grid, kT, 0, st>>>(params + lo.w_o, H, fa + H, w.wo_t);
@@ -286,11 +298,11 @@ int build_images(const dcgc_dmpnn_model_config* c, const Layout& lo, const float
   if (nt == 0) return DCGC_OK;
   DcgcImgJob jobs[5 + 2 * DCGC_DMPNN_MAX_FFN];
   int nj = 0;
-  jobs[nj++] = DcgcImgJob{params + lo.w_i, 1, 0, fi, 0, H, w.img_wi, 0};
-  jobs[nj++] = DcgcImgJob{params + lo.w_h, 1, 0, H, 0, H, w.img_wh, 0};
-  jobs[nj++] = DcgcImgJob{w.wo_t, 1, 1, fa, H, H, w.img_wo, 0};
+  jobs[nj++] = DcgcImgJob{params + lo.w_i, 1, 0, fi, 0, H, w.img_wi, f16};
+  jobs[nj++] = DcgcImgJob{params + lo.w_h, 1, 0, H, 0, H, w.img_wh, f16};
+  jobs[nj++] = DcgcImgJob{w.wo_t, 1, 1, fa, H, H, w.img_wo, f16};
   for (int i = 0; i < c->ffn_layers; ++i)
-    jobs[nj++] = DcgcImgJob{params + lo.ffn_w[i], 1, 0, lo.ffn_in[i], 0, lo.ffn_out[i], w.img_ffn[i], 0};
+    jobs[nj++] = DcgcImgJob{params + lo.ffn_w[i], 1, 0, lo.ffn_in[i], 0, lo.ffn_out[i], w.img_ffn[i], f16};
   if (backward) {
     for (int i = 0; i < c->ffn_layers; ++i)
       jobs[nj++] = DcgcImgJob{params + lo.ffn_w[i], 1, 1, lo.ffn_out[i], 0, lo.ffn_in[i], w.img_ffn_d[i], 0};
@@ -320,7 +332,7 @@ inline float* msg_other(const Work& w, int depth) { return (depth - 1) % 2 == 0 
 int forward_impl(const dcgc_dmpnn_model_config* c, const Layout& lo, const dcgc_dmpnn_tables* t, const float* af,
                  int64_t ld_af, const float* fini, int64_t ld_fi, const float* params, const Work& w, float* out,
                  int64_t ld_out, cudaStream_t st) {
-  const int H = c->hidden, fa = c->atom_fdim, fi = c->atom_fdim + c->bond_fdim, mode = c->gemm_mode;
+  const int H = c->hidden, fa = c->atom_fdim, fi = c->atom_fdim + c->bond_fdim, mode = forward_mode(c);
   const int64_t R = t->n_rows, A = t->n_atoms, B = t->n_mols;
   const int64_t r4 = R * H / 4;
   // input = W_i(f_ini)  (layers.py:1622);  message = act(input)  (:1624)

@@ -201,13 +201,13 @@ def _linear(x, lin, act_code, mode, x2=None, split=None):
         wt = w.t()
         if k != w.shape[1]:                      # zero-padded input view
             wt = torch.cat([wt, wt.new_zeros(k - w.shape[1], w.shape[0])], 0)
-        return ops.GroupLinear2Fn.apply(x, None, wt, lin.bias, act_code, mode)
+        return ops.GroupLinear2Fn.apply(x, None, wt, lin.bias, act_code, mode, ops.forward_gemm_mode(mode))
     k1 = x.shape[1]
     parts = [w[:, :split].t()]
     if k1 != split:
         parts.append(w.new_zeros(k1 - split, w.shape[0]))
     parts.append(w[:, split:].t())
-    return ops.GroupLinear2Fn.apply(x, x2, torch.cat(parts, 0), lin.bias, act_code, mode)
+    return ops.GroupLinear2Fn.apply(x, x2, torch.cat(parts, 0), lin.bias, act_code, mode, ops.forward_gemm_mode(mode))
 
 
 class DMPNNEncoderLayer(nn.Module):
@@ -601,7 +601,15 @@ class DMPNNModel(object):
         if self.model_dir and checkpoint_interval > 0:
             self.save_checkpoint(max_checkpoints_to_keep)
         logger.info("TIMING: model fitting took %0.3f s" % (time.time() - t0))
+        self._check_f16_range()
         return last_avg
+
+    def _check_f16_range(self):
+        """The forward GEMMs run with fp16 operand halves (csrc/dmpnn_model.cu forward_mode): fail loudly if an operand
+        has left the range they need (same check as GraphConvModel's)."""
+        if self.device.type == "cuda":
+            from .graphconvmodel import _check_f16_range
+            _check_f16_range(self, any_path=True)
 
     def _train_step(self, inputs, labels, weights):
         """zero_grad, forward, loss, backward, (gradient all-reduce), Adam step (torch_model.py:435-443)."""
@@ -675,6 +683,7 @@ class DMPNNModel(object):
                 else:
                     o = self.model(inputs)
                 outs.append((o if self.mode == 'regression' else o[0]).detach().cpu().numpy())
+        self._check_f16_range()
         y = np.concatenate(outs, 0) if outs else np.zeros((0, self.n_tasks), np.float32)
         for t in reversed(list(transformers)):              # deepchem.trans.undo_transforms (torch_model.py:625-634)
             if getattr(t, "transform_y", False):

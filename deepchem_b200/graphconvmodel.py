@@ -570,10 +570,11 @@ class _Prefetcher(object):
                 self.thread.join(timeout=0.05)
 
 
-def _check_f16_range(model):
+def _check_f16_range(model, any_path=False):
     """The fused engine runs its forward GEMMs with fp16 operand halves (DCGC_GEMM_F16X3, csrc/gemm_tc.cu): raise if a
-    forward GEMM has seen an operand outside fp16's range — its results are then wrong, not merely inexact."""
-    if model._engine is None or model.device.type != "cuda":
+    forward GEMM has seen an operand outside fp16's range — its results are then wrong, not merely inexact.
+    ``any_path``: the model's per-layer path uses them too (D-MPNN)."""
+    if (model._engine is None and not any_path) or model.device.type != "cuda":
         return
     if _lib_mod.lib().dcgc_tc_f16_overflow() == 1:
         raise FloatingPointError("an activation or weight above 3750 reached a forward GEMM that runs with fp16 operand "

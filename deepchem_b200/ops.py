@@ -483,12 +483,13 @@ class GroupLinear2Fn(torch.autograd.Function):
     W_o(cat(atom_features, messages)) (layers.py:1541) without materialising the concatenation."""
 
     @staticmethod
-    def forward(ctx, a1, a2, w, bias, act, mode):
+    def forward(ctx, a1, a2, w, bias, act, mode, fwd_mode=None):
         _check_dev(a1, "input")
         a1 = _rowmajor(a1)
         a2 = _rowmajor(a2) if a2 is not None else None
         w = w.contiguous()
-        y = group_gemm_fwd(a1, a2, w, bias, None, act, mode)
+        # fwd_mode: arithmetic of the forward product alone (the D-MPNN layers pass fp16x3 where the fused engine does)
+        y = group_gemm_fwd(a1, a2, w, bias, None, act, mode if fwd_mode is None else fwd_mode)
         ctx.act, ctx.mode = act, mode
         ctx.has2 = a2 is not None
         ctx.save_for_backward(a1, a2, w, y if act != ACT_NONE else None)
@@ -511,7 +512,16 @@ class GroupLinear2Fn(torch.autograd.Function):
         need1, need2 = ctx.needs_input_grad[0], ctx.has2 and ctx.needs_input_grad[1]
         if need1 or need2:
             d1, d2 = group_gemm_dgrad(g, w, k1, k2, None, need1, need2, ctx.mode)
-        return d1, d2, dw, (db if ctx.needs_input_grad[3] else None), None, None
+        return d1, d2, dw, (db if ctx.needs_input_grad[3] else None), None, None, None
+
+
+def forward_gemm_mode(mode):
+    """The arithmetic the fused engines use for FORWARD products of the tf32x3 mode: fp16 operand halves
+    (csrc/gemm_tc.cu tc_gemm_kernel_v6) unless DCGC_FWD_F16X3=0 — the rule of csrc/dmpnn_model.cu forward_mode."""
+    import os
+    if mode == _lib.GEMM_TF32X3 and os.environ.get("DCGC_FWD_F16X3", "1")[:1] != "0":
+        return _lib.GEMM_F16X3
+    return mode
 
 
 _READOUT_MODES = {"mean": 0, "sum": 1, "norm": 2}
