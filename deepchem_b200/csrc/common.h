@@ -136,6 +136,28 @@ int dcgc_group_gemm_wgrad_opts(int32_t mode, const float* a1, int64_t ld_a1, int
 #endif
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (sm_90+): every kernel of the library starts with dcgc_griddep_wait() — wait until the
+// kernel in front of it on the stream has completed and its writes are visible (a no-op for a launch without the
+// attribute), then allow the NEXT kernel to be launched — and is launched through dcgc_launch with
+// programmatic stream serialization: the next grid is set up and its CTAs are placed as SMs free up while this one
+// still runs, instead of after it has drained.  Nothing before the wait may touch global memory.  DCGC_PDL=0: plain
+// stream-ordered launches.
+__device__ __forceinline__ void dcgc_griddep_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+bool dcgc_pdl_on();   // profile.cu
+template <typename... KArgs, typename... Args>
+inline void dcgc_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = dcgc_pdl_on() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // (errors surface in DCGC_CUDA_LAUNCH_CHECK)
+}
+
 // mbarrier wait shared by the tcgen05 GEMMs and the molecule-group kernels.  The wait itself is the hardware's
 // (try_wait suspends the thread); the guard around it is WALL-CLOCK based (%globaltimer, 20 s): a protocol bug still
 // traps instead of hanging the GPU, but a context that is preempted, time-sliced (MPS) or replayed by a profiler is

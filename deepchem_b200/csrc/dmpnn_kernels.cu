@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(kT)
 concat_rows_kernel(const float* __restrict__ af, int64_t ld_a, int fa, const float* __restrict__ bf, int64_t ld_b,
                    int fb, const int32_t* __restrict__ bond_src, const int32_t* __restrict__ bond_edge,
                    int64_t n_rows, float* __restrict__ out, int64_t ld_out) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * kT + threadIdx.x;
   const int64_t r = t / ld_out;
   const int c = (int)(t - r * ld_out);
@@ -30,6 +31,7 @@ concat_rows_kernel(const float* __restrict__ af, int64_t ld_a, int fa, const flo
 __global__ void __launch_bounds__(kT)
 readout_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restrict__ mol_ptr, int64_t n_mols,
                    int width, int mode, float norm, float* __restrict__ out, int64_t ld_out) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * kT + threadIdx.x;
   const int64_t m = t / width;
   const int c = (int)(t - m * width);
@@ -46,6 +48,7 @@ readout_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __r
 __global__ void __launch_bounds__(kT)
 readout_bwd_kernel(const float* __restrict__ dout, int64_t ld_dout, const int32_t* __restrict__ mol_ptr,
                    int64_t n_mols, int width, int mode, float norm, float* __restrict__ dx, int64_t ld_dx) {
+  dcgc_griddep_wait();
   // one block row per molecule: blockIdx.x = molecule, threads stride over (atom, column)
   const int64_t m = blockIdx.x;
   const int a0 = __ldg(mol_ptr + m), a1 = __ldg(mol_ptr + m + 1);
@@ -71,7 +74,7 @@ extern "C" int dcgc_dmpnn_concat_rows(const float* af, int64_t ld_a, int32_t fa,
                  "dcgc_dmpnn_concat_rows: null pointer");
   DcgcProfScope prof_scope("dcgc_dmpnn_concat_rows", (cudaStream_t)stream);
   const int64_t work = n_rows * ld_out;
-  concat_rows_kernel<<<(unsigned)((work + kT - 1) / kT), kT, 0, (cudaStream_t)stream>>>(
+  dcgc_launch(concat_rows_kernel, (unsigned)((work + kT - 1) / kT), kT, 0, (cudaStream_t)stream, 
       af, ld_a, fa, bf, ld_b, fb, bond_src, bond_edge, n_rows, out, ld_out);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_dmpnn_concat_rows");
   return DCGC_OK;
@@ -86,7 +89,7 @@ extern "C" int dcgc_segment_readout_fwd(const float* x, int64_t ld_x, const int3
   DCGC_CHECK_ARG(x && mol_ptr && out, "dcgc_segment_readout_fwd: null pointer");
   DcgcProfScope prof_scope("dcgc_segment_readout_fwd", (cudaStream_t)stream);
   const int64_t work = n_mols * width;
-  readout_fwd_kernel<<<(unsigned)((work + kT - 1) / kT), kT, 0, (cudaStream_t)stream>>>(x, ld_x, mol_ptr, n_mols,
+  dcgc_launch(readout_fwd_kernel, (unsigned)((work + kT - 1) / kT), kT, 0, (cudaStream_t)stream, x, ld_x, mol_ptr, n_mols,
                                                                                        width, mode, norm, out, ld_out);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_segment_readout_fwd");
   return DCGC_OK;
@@ -101,7 +104,7 @@ extern "C" int dcgc_segment_readout_bwd(const float* dout, int64_t ld_dout, cons
   if (n_mols == 0 || width == 0 || n_atoms == 0) return DCGC_OK;
   DCGC_CHECK_ARG(dout && mol_ptr && dx, "dcgc_segment_readout_bwd: null pointer");
   DcgcProfScope prof_scope("dcgc_segment_readout_bwd", (cudaStream_t)stream);
-  readout_bwd_kernel<<<(unsigned)n_mols, kT, 0, (cudaStream_t)stream>>>(dout, ld_dout, mol_ptr, n_mols, width, mode,
+  dcgc_launch(readout_bwd_kernel, (unsigned)n_mols, kT, 0, (cudaStream_t)stream, dout, ld_dout, mol_ptr, n_mols, width, mode,
                                                                         norm, dx, ld_dx);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_segment_readout_bwd");
   return DCGC_OK;

@@ -29,6 +29,7 @@ inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kT - 1) / kT); }
 
 // all element-wise kernels work on [rows, width] matrices with width % 4 == 0 and 16-byte aligned rows
 __global__ void __launch_bounds__(kT) relu_copy_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4) {
+  dcgc_griddep_wait();
   const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
   if (i >= n4) return;
   float4 v = x[i];
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(kT) relu_copy_kernel(const float4* __restrict_
 // h = relu(a + b)                                                   (layers.py:1632: act(input + W_h(message)))
 __global__ void __launch_bounds__(kT) add_relu_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                                       float4* __restrict__ y, int64_t n4) {
+  dcgc_griddep_wait();
   const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
   if (i >= n4) return;
   const float4 p = a[i], q = b[i];
@@ -45,6 +47,7 @@ __global__ void __launch_bounds__(kT) add_relu_kernel(const float4* __restrict__
 }
 // g = (y > 0) ? g : 0      (ReLU backward from the saved OUTPUT, in place)
 __global__ void __launch_bounds__(kT) relu_mask_kernel(float4* __restrict__ g, const float4* __restrict__ y, int64_t n4) {
+  dcgc_griddep_wait();
   const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
   if (i >= n4) return;
   float4 v = g[i];
@@ -55,6 +58,7 @@ __global__ void __launch_bounds__(kT) relu_mask_kernel(float4* __restrict__ g, c
 // ds += (inp > 0) ? dm : 0     (gradient of `input`: the residual path + the message path through act(input))
 __global__ void __launch_bounds__(kT) mask_add_kernel(float4* __restrict__ ds, const float4* __restrict__ dm,
                                                       const float4* __restrict__ inp, int64_t n4) {
+  dcgc_griddep_wait();
   const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
   if (i >= n4) return;
   float4 v = ds[i];
@@ -73,6 +77,7 @@ __global__ void __launch_bounds__(kT) fused_gather_kernel(const float* __restric
                                                           const int32_t* __restrict__ idx, int64_t n_rows, int width,
                                                           const float* __restrict__ mask, const float* addend,
                                                           float* out) {
+  dcgc_griddep_wait();
   const int groups = width >> 2;
   const int64_t t = (int64_t)blockIdx.x * kT + threadIdx.x;
   const int64_t row = t / groups;
@@ -122,7 +127,7 @@ int fused_gather(const float* x, const int32_t* row_ptr, const int32_t* idx, int
                  const float* addend, float* out, cudaStream_t st) {
   if (n_rows == 0) return DCGC_OK;
   DcgcProfScope prof_scope("dcgc_gather_sum", st);
-  fused_gather_kernel<RELU_IN, MODE><<<blocks_for(n_rows * (width >> 2)), kT, 0, st>>>(x, row_ptr, idx, n_rows, width, mask,
+  dcgc_launch(fused_gather_kernel<RELU_IN, MODE>, blocks_for(n_rows * (width >> 2)), kT, 0, st, x, row_ptr, idx, n_rows, width, mask,
                                                                                       addend, out);
   DCGC_CUDA_LAUNCH_CHECK("dmpnn fused_gather");
   return DCGC_OK;
@@ -131,6 +136,7 @@ int fused_gather(const float* x, const int32_t* row_ptr, const int32_t* idx, int
 // dst[c, r] = src[r, c]   (nn.Linear weight [n, k] <-> the [k, n] layout of the two-operand GEMM entry points)
 __global__ void __launch_bounds__(kT) transpose_kernel(const float* __restrict__ src, int rows, int cols,
                                                        float* __restrict__ dst) {
+  dcgc_griddep_wait();
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
@@ -148,6 +154,7 @@ __global__ void __launch_bounds__(kT) transpose_kernel(const float* __restrict__
 __global__ void __launch_bounds__(kT) l2_loss_kernel(const float* __restrict__ out, const float* __restrict__ y,
                                                      const float* __restrict__ w, int64_t n, float inv_n,
                                                      float* __restrict__ per_elem, float* __restrict__ dout) {
+  dcgc_griddep_wait();
   const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
   if (i >= n) return;
   const float d = out[i] - y[i], ww = w ? w[i] : 1.f;
@@ -157,6 +164,7 @@ __global__ void __launch_bounds__(kT) l2_loss_kernel(const float* __restrict__ o
 // fixed-order sum of per_elem (float64), one block: deterministic
 __global__ void __launch_bounds__(1024) loss_sum_kernel(const float* __restrict__ per_elem, int64_t n, float inv_n,
                                                         float* __restrict__ loss) {
+  dcgc_griddep_wait();
   __shared__ double sh[1024];
   double acc = 0.0;
   for (int64_t i = threadIdx.x; i < n; i += 1024) acc += (double)per_elem[i];
@@ -291,7 +299,7 @@ int build_images(const dcgc_dmpnn_model_config* c, const Layout& lo, const float
   const int f16 = forward_mode(c) == DCGC_GEMM_F16X3 ? 1 : 0;
   {
     dim3 grid((unsigned)((fa + H + 31) / 32), (unsigned)((H + 31) / 32));
-    transpose_kernel<<<grid, kT, 0, st>>>(params + lo.w_o, H, fa + H, w.wo_t);
+    dcgc_launch(transpose_kernel, grid, kT, 0, st, params + lo.w_o, H, fa + H, w.wo_t);
     DCGC_CUDA_LAUNCH_CHECK("dmpnn transpose W_o");
   }
   const int nt = dcgc_tc_terms(c->gemm_mode);
@@ -351,7 +359,7 @@ int forward_impl(const dcgc_dmpnn_model_config* c, const Layout& lo, const dcgc_
   RET_IF(dcgc_linear_fwd_opts(mode, src, H, H, params + lo.w_h, nullptr, H, R, DCGC_ACT_NONE, dst, H, nullptr, nullptr,
                               with_img(w.img_wh), st));
   if (r4 > 0) {
-    add_relu_kernel<<<blocks_for(r4), kT, 0, st>>>(reinterpret_cast<const float4*>(w.r0), reinterpret_cast<const float4*>(dst),
+    dcgc_launch(add_relu_kernel, blocks_for(r4), kT, 0, st, reinterpret_cast<const float4*>(w.r0), reinterpret_cast<const float4*>(dst),
                                                   reinterpret_cast<float4*>(w.r3), r4);
     DCGC_CUDA_LAUNCH_CHECK("dmpnn add_relu");
   }
@@ -467,9 +475,9 @@ extern "C" int dcgc_dmpnn_model_train_step(const dcgc_dmpnn_model_config* cfg, c
     const float inv_n = 1.0f / (float)n;
     // dout is written densely [B, T] into per_elem's neighbour, then spread to the padded layout if needed
     float* dense_d = ld_o == T ? g : w.denc;      // denc is free until the FFN backward reaches the encoder
-    l2_loss_kernel<<<blocks_for(n), kT, 0, st>>>(o, y, wts, n, inv_n, w.per_elem, dense_d);
+    dcgc_launch(l2_loss_kernel, blocks_for(n), kT, 0, st, o, y, wts, n, inv_n, w.per_elem, dense_d);
     DCGC_CUDA_LAUNCH_CHECK("dmpnn l2_loss");
-    loss_sum_kernel<<<1, 1024, 0, st>>>(w.per_elem, n, inv_n, loss_dev);
+    dcgc_launch(loss_sum_kernel, 1, 1024, 0, st, w.per_elem, n, inv_n, loss_dev);
     DCGC_CUDA_LAUNCH_CHECK("dmpnn loss_sum");
     if (ld_o != T) {
       DCGC_CUDA_CALL(cudaMemsetAsync(g, 0, (size_t)B * ld_o * 4, st));
@@ -486,7 +494,7 @@ extern "C" int dcgc_dmpnn_model_train_step(const dcgc_dmpnn_model_config* cfg, c
     const int64_t ld_x = i == 0 ? H : pad4(lo.ffn_out[i - 1]);
     if (i != L - 1) {     // ReLU of this linear's output
       const int64_t n4 = B * ld_g / 4;
-      relu_mask_kernel<<<blocks_for(n4), kT, 0, st>>>(reinterpret_cast<float4*>(g), reinterpret_cast<const float4*>(w.x[i]), n4);
+      dcgc_launch(relu_mask_kernel, blocks_for(n4), kT, 0, st, reinterpret_cast<float4*>(g), reinterpret_cast<const float4*>(w.x[i]), n4);
       DCGC_CUDA_LAUNCH_CHECK("dmpnn relu_mask ffn");
     }
     RET_IF(dcgc_linear_wgrad(mode, x_in, ld_x, k, g, ld_g, n, B, grads + lo.ffn_w[i], grads + lo.ffn_b[i], w.wgrad_ws,
@@ -500,14 +508,14 @@ extern "C" int dcgc_dmpnn_model_train_step(const dcgc_dmpnn_model_config* cfg, c
 
   // ---------------- readout backward, ReLU of atoms_hidden, W_o
   RET_IF(dcgc_segment_readout_bwd(w.denc, H, t->mol_ptr, B, A, H, cfg->aggregation, cfg->aggregation_norm, w.a2, H, st));
-  relu_mask_kernel<<<blocks_for(a4), kT, 0, st>>>(reinterpret_cast<float4*>(w.a2), reinterpret_cast<const float4*>(w.a1), a4);
+  dcgc_launch(relu_mask_kernel, blocks_for(a4), kT, 0, st, reinterpret_cast<float4*>(w.a2), reinterpret_cast<const float4*>(w.a1), a4);
   DCGC_CUDA_LAUNCH_CHECK("dmpnn relu_mask atoms");
   {
     const int64_t rows[1] = {A};
     RET_IF(dcgc_group_gemm_wgrad(mode, atom_feat, ld_af, fa, w.a0, H, H, w.a2, H, H, rows, 1, w.dwo_t, grads + lo.b_o,
                                  w.wgrad_ws, w.wgrad_bytes, st));
     dim3 grid((unsigned)((H + 31) / 32), (unsigned)((fa + H + 31) / 32));
-    transpose_kernel<<<grid, kT, 0, st>>>(w.dwo_t, fa + H, H, grads + lo.w_o);
+    dcgc_launch(transpose_kernel, grid, kT, 0, st, w.dwo_t, fa + H, H, grads + lo.w_o);
     DCGC_CUDA_LAUNCH_CHECK("dmpnn transpose dW_o");
   }
   // d(m2a) = g . W_o[:, fa:]  -> a1 (atoms_hidden is not needed any more); atom features need no gradient

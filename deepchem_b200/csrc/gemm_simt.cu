@@ -75,6 +75,7 @@ __device__ __forceinline__ void mma_tile(const float (*As)[LDS_A], const float (
 // y = act([a1|a2] . B + bias), B[k][j] = W[g][k][j] (TRANS_B = false) or W[g][j][k] (true)
 template <int BN, bool TRANS_B>
 __global__ void __launch_bounds__(NT, 2) gemm_kernel(const GemmArgs p) {
+  dcgc_griddep_wait();
   constexpr int TN = BN / 16;
   constexpr int B_IT = BN / 64;  // float4 loads of the B tile per thread
   __shared__ __align__(16) float As[2][BK][LDS_A];
@@ -205,6 +206,7 @@ using WgradArgs = DcgcWgradArgs;
 
 template <int BN>
 __global__ void __launch_bounds__(NT, 2) wgrad_kernel(const WgradArgs p) {
+  dcgc_griddep_wait();
   constexpr int TN = BN / 16;
   constexpr int B_IT = BN / 64;
   __shared__ __align__(16) float As[2][BK][LDS_A];
@@ -333,6 +335,7 @@ struct ReduceArgs {
 };
 
 __global__ void __launch_bounds__(NT) wgrad_reduce_kernel(const ReduceArgs p) {
+  dcgc_griddep_wait();
   const int g = blockIdx.y;
   const int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x;
   if (idx >= p.kn + p.n) return;
@@ -417,10 +420,10 @@ static int group_gemm_fwd_impl(int32_t mode, const float* a1, int64_t ld_a1, int
   cudaStream_t st = (cudaStream_t)stream;
   if (n > 64) {
     dim3 grid((unsigned)row_tiles, (unsigned)((n + 127) / 128));
-    gemm_kernel<128, false><<<grid, NT, 0, st>>>(p);
+    dcgc_launch(gemm_kernel<128, false>, grid, NT, 0, st, p);
   } else {
     dim3 grid((unsigned)row_tiles, 1);
-    gemm_kernel<64, false><<<grid, NT, 0, st>>>(p);
+    dcgc_launch(gemm_kernel<64, false>, grid, NT, 0, st, p);
   }
   DCGC_CUDA_LAUNCH_CHECK("dcgc_group_gemm_fwd");
   return DCGC_OK;
@@ -481,10 +484,10 @@ static int group_gemm_dgrad_impl(int32_t mode, const float* g, int64_t ld_g, int
   cudaStream_t st = (cudaStream_t)stream;
   if (N > 64) {
     dim3 grid((unsigned)row_tiles, (unsigned)((N + 127) / 128));
-    gemm_kernel<128, true><<<grid, NT, 0, st>>>(p);
+    dcgc_launch(gemm_kernel<128, true>, grid, NT, 0, st, p);
   } else {
     dim3 grid((unsigned)row_tiles, 1);
-    gemm_kernel<64, true><<<grid, NT, 0, st>>>(p);
+    dcgc_launch(gemm_kernel<64, true>, grid, NT, 0, st, p);
   }
   DCGC_CUDA_LAUNCH_CHECK("dcgc_group_gemm_dgrad");
   return DCGC_OK;
@@ -595,11 +598,11 @@ static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, 
     if (n > 64) {
       p.tiles_n = (n + 127) / 128;
       dim3 grid((unsigned)chunks, (unsigned)(tiles_m * p.tiles_n));
-      wgrad_kernel<128><<<grid, NT, 0, st>>>(p);
+      dcgc_launch(wgrad_kernel<128>, grid, NT, 0, st, p);
     } else {
       p.tiles_n = 1;
       dim3 grid((unsigned)chunks, (unsigned)tiles_m);
-      wgrad_kernel<64><<<grid, NT, 0, st>>>(p);
+      dcgc_launch(wgrad_kernel<64>, grid, NT, 0, st, p);
     }
     DCGC_CUDA_LAUNCH_CHECK("dcgc_group_gemm_wgrad (stage 1)");
   }
@@ -607,7 +610,7 @@ static int wgrad_impl(int32_t mode, const float* a1, int64_t ld_a1, int32_t k1, 
   q.transpose = transpose;
   q.dbias21 = (dbias && n_groups == DCGC_N_DEG) ? dbias21 : nullptr;
   dim3 rgrid((unsigned)((kn + n + NT - 1) / NT), (unsigned)n_groups);
-  wgrad_reduce_kernel<<<rgrid, NT, 0, st>>>(q);
+  dcgc_launch(wgrad_reduce_kernel, rgrid, NT, 0, st, q);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_group_gemm_wgrad (stage 2)");
   return DCGC_OK;
 }
@@ -664,10 +667,10 @@ static int linear_fwd_impl(int32_t mode, const float* x, int64_t ld_x, int32_t k
   cudaStream_t st = (cudaStream_t)stream;
   if (n > 64) {
     dim3 grid((unsigned)row_tiles, (unsigned)((n + 127) / 128));
-    gemm_kernel<128, true><<<grid, NT, 0, st>>>(p);
+    dcgc_launch(gemm_kernel<128, true>, grid, NT, 0, st, p);
   } else {
     dim3 grid((unsigned)row_tiles, 1);
-    gemm_kernel<64, true><<<grid, NT, 0, st>>>(p);
+    dcgc_launch(gemm_kernel<64, true>, grid, NT, 0, st, p);
   }
   DCGC_CUDA_LAUNCH_CHECK("dcgc_linear_fwd");
   return DCGC_OK;

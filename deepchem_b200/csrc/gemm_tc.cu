@@ -196,6 +196,7 @@ __device__ __forceinline__ void prep_image_body(const ImgArgs& p, int bx, int nt
 }
 template <int NT>
 __global__ void __launch_bounds__(256) tc_prep_image(const ImgArgs p) {
+  dcgc_griddep_wait();
   prep_image_body<NT>(p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
@@ -241,6 +242,7 @@ __device__ __forceinline__ void prep_image_f16_body(const ImgArgs& p, int bx, in
   }
 }
 __global__ void __launch_bounds__(256) tc_prep_image_f16(const ImgArgs p) {
+  dcgc_griddep_wait();
   prep_image_f16_body(p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
@@ -256,6 +258,7 @@ struct ImgBatch {
 };
 template <int NT>
 __global__ void __launch_bounds__(256) tc_prep_image_batch(const __grid_constant__ ImgBatch b) {
+  dcgc_griddep_wait();
   int j = 0;
   while (j + 1 < b.n_jobs && (int)blockIdx.x >= b.first_block[j + 1]) ++j;
   const int lb = (int)blockIdx.x - b.first_block[j];
@@ -530,6 +533,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) tc_gemm_kernel_v4(const TcArgs3
   if (warp == 17) tmem_alloc(bar_base + 128, 512);
   tc_fence_before();
   __syncthreads();
+  dcgc_griddep_wait();     // (everything above is set-up in shared / tensor memory: it overlaps the kernel in front)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -805,6 +809,7 @@ tc_gemm_kernel_v5(const TcArgs3 q, const __grid_constant__ CUtensorMap map1, con
   if (warp == 17) tmem_alloc(bar_base + V5_TMEM_SLOT, 512);
   tc_fence_before();
   __syncthreads();
+  dcgc_griddep_wait();     // (everything above is set-up in shared / tensor memory: it overlaps the kernel in front)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -1018,6 +1023,7 @@ tc_gemm_kernel_v6(const TcArgs3 q, const __grid_constant__ CUtensorMap map1, con
   if (warp == 17) tmem_alloc(bar_base + V5_TMEM_SLOT, 512);
   tc_fence_before();
   __syncthreads();
+  dcgc_griddep_wait();     // (everything above is set-up in shared / tensor memory: it overlaps the kernel in front)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -1241,6 +1247,7 @@ __global__ void __launch_bounds__(WG2_THREADS, 1) tc_wgrad_kernel_v2(const DcgcW
   if (warp == 12) tmem_alloc(bar_base + 120, 512);
   tc_fence_before();
   __syncthreads();
+  dcgc_griddep_wait();     // (everything above is set-up in shared / tensor memory: it overlaps the kernel in front)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -1535,6 +1542,7 @@ tc_wgrad_kernel_v3(const DcgcWgradArgs p, const __grid_constant__ CUtensorMap ma
   if (warp == 12) tmem_alloc(bar_base + 136, 512);
   tc_fence_before();
   __syncthreads();
+  dcgc_griddep_wait();     // (everything above is set-up in shared / tensor memory: it overlaps the kernel in front)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -1720,6 +1728,7 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t d, uint64_t a, uint64_t b, 
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int variant, int reps, long long* out) {
+  dcgc_griddep_wait();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -1930,7 +1939,7 @@ int launch_prep_f16(const float* w, int n_groups, int trans_w, int k1, int k2, i
   if (trans_w) { ia.src_ld = N; ia.src_group_stride = (int64_t)(k1 + k2) * N; }
   else { ia.src_ld = k1; ia.src_group_stride = (int64_t)N * k1; }
   dim3 pgrid((unsigned)sh.chunks * 8, (unsigned)sh.n_tiles_n, (unsigned)n_groups);
-  tc_prep_image_f16<<<pgrid, 256, 0, st>>>(ia);
+  dcgc_launch(tc_prep_image_f16, pgrid, 256, 0, st, ia);
   DCGC_CUDA_LAUNCH_CHECK("tc_prep_image_f16");
   return DCGC_OK;
 }
@@ -1943,8 +1952,8 @@ int launch_prep(int nt, const float* w, int n_groups, int trans_w, int k1, int k
   if (trans_w) { ia.src_ld = N; ia.src_group_stride = (int64_t)(k1 + k2) * N; }
   else { ia.src_ld = k1; ia.src_group_stride = (int64_t)N * k1; }
   dim3 pgrid((unsigned)sh.chunks * 4, (unsigned)sh.n_tiles_n, (unsigned)n_groups);
-  if (nt == 3) tc_prep_image<3><<<pgrid, 256, 0, st>>>(ia);
-  else tc_prep_image<1><<<pgrid, 256, 0, st>>>(ia);
+  if (nt == 3) dcgc_launch(tc_prep_image<3>, pgrid, 256, 0, st, ia);
+  else dcgc_launch(tc_prep_image<1>, pgrid, 256, 0, st, ia);
   DCGC_CUDA_LAUNCH_CHECK("tc_prep_image");
   return DCGC_OK;
 }
@@ -1975,8 +1984,8 @@ int dcgc_tc_prep_weights_batch(int nt, const DcgcImgJob* jobs, int n_jobs, cudaS
     }
     b.first_block[b.n_jobs] = blocks;
     if (blocks == 0) continue;
-    if (nt == 3) tc_prep_image_batch<3><<<(unsigned)blocks, 256, 0, st>>>(b);
-    else tc_prep_image_batch<1><<<(unsigned)blocks, 256, 0, st>>>(b);
+    if (nt == 3) dcgc_launch(tc_prep_image_batch<3>, (unsigned)blocks, 256, 0, st, b);
+    else dcgc_launch(tc_prep_image_batch<1>, (unsigned)blocks, 256, 0, st, b);
     DCGC_CUDA_LAUNCH_CHECK("tc_prep_image_batch");
   }
   return DCGC_OK;
@@ -2075,19 +2084,19 @@ int dcgc_tc_gemm(int nt, const float* a1, int64_t ld_a1, int k1, const float* a2
       if (st_ == DCGC_OK) st_ = a2 ? make_a_map(&m2, a2, n_rows, k2, ld_a2, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B)
                                    : make_a_map(&m2, a1, n_rows, k1, ld_a1, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
       if (st_ != DCGC_OK) { if (own_img) cudaFreeAsync(own_img, st); return st_; }
-      tc_gemm_kernel_v6<<<grid, V5_THREADS, V6_SMEM_BYTES, st>>>(q3, m1, m2);
+      dcgc_launch(tc_gemm_kernel_v6, grid, V5_THREADS, V6_SMEM_BYTES, st, q3, m1, m2);
     } else if (!tma_ok) {
       // register-fed producers: operands whose rows are not 16-byte aligned (no tensor map), or DCGC_TC_V4=1
-      if (nt == 3) tc_gemm_kernel_v4<3><<<grid, V4_THREADS, V4Cfg<3>::kSmemBytes, st>>>(q3);
-      else tc_gemm_kernel_v4<1><<<grid, V4_THREADS, V4Cfg<1>::kSmemBytes, st>>>(q3);
+      if (nt == 3) dcgc_launch(tc_gemm_kernel_v4<3>, grid, V4_THREADS, V4Cfg<3>::kSmemBytes, st, q3);
+      else dcgc_launch(tc_gemm_kernel_v4<1>, grid, V4_THREADS, V4Cfg<1>::kSmemBytes, st, q3);
     } else {
       alignas(64) CUtensorMap m1, m2;
       st_ = make_a_map(&m1, a1, n_rows, k1, ld_a1, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
       if (st_ == DCGC_OK) st_ = a2 ? make_a_map(&m2, a2, n_rows, k2, ld_a2, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B)
                                    : make_a_map(&m2, a1, n_rows, k1, ld_a1, TC_BK, TC_BM, CU_TENSOR_MAP_SWIZZLE_128B);
       if (st_ != DCGC_OK) { if (own_img) cudaFreeAsync(own_img, st); return st_; }
-      if (nt == 3) tc_gemm_kernel_v5<3><<<grid, V5_THREADS, V5Cfg<3>::kSmemBytes, st>>>(q3, m1, m2);
-      else tc_gemm_kernel_v5<1><<<grid, V5_THREADS, V5Cfg<1>::kSmemBytes, st>>>(q3, m1, m2);
+      if (nt == 3) dcgc_launch(tc_gemm_kernel_v5<3>, grid, V5_THREADS, V5Cfg<3>::kSmemBytes, st, q3, m1, m2);
+      else dcgc_launch(tc_gemm_kernel_v5<1>, grid, V5_THREADS, V5Cfg<1>::kSmemBytes, st, q3, m1, m2);
     }
     const cudaError_t launch_err = cudaGetLastError();
     if (own_img) cudaFreeAsync(own_img, st);
@@ -2141,11 +2150,11 @@ int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p_in, int chunks, cudaStre
     if (st_ != DCGC_OK) return st_;
     const int smem3 = WG3_B_STAGES * (nt == 3 ? 2 : 1) * mt * TC_TILE_BYTES + WG3_RAW_STAGES * 3 * WG3_RAW_TILE + 1024 + 256;
     if (nt == 3) {
-      if (mt == 2) tc_wgrad_kernel_v3<2, 3><<<grid, WG3_THREADS, smem3, st>>>(p, m1, m2, mg);
-      else tc_wgrad_kernel_v3<1, 3><<<grid, WG3_THREADS, smem3, st>>>(p, m1, m2, mg);
+      if (mt == 2) dcgc_launch(tc_wgrad_kernel_v3<2, 3>, grid, WG3_THREADS, smem3, st, p, m1, m2, mg);
+      else dcgc_launch(tc_wgrad_kernel_v3<1, 3>, grid, WG3_THREADS, smem3, st, p, m1, m2, mg);
     } else {
-      if (mt == 2) tc_wgrad_kernel_v3<2, 1><<<grid, WG3_THREADS, smem3, st>>>(p, m1, m2, mg);
-      else tc_wgrad_kernel_v3<1, 1><<<grid, WG3_THREADS, smem3, st>>>(p, m1, m2, mg);
+      if (mt == 2) dcgc_launch(tc_wgrad_kernel_v3<2, 1>, grid, WG3_THREADS, smem3, st, p, m1, m2, mg);
+      else dcgc_launch(tc_wgrad_kernel_v3<1, 1>, grid, WG3_THREADS, smem3, st, p, m1, m2, mg);
     }
     DCGC_CUDA_LAUNCH_CHECK("tc_wgrad_kernel_v3");
     return DCGC_OK;
@@ -2153,11 +2162,11 @@ int dcgc_tc_wgrad_stage1(int nt, const DcgcWgradArgs& p_in, int chunks, cudaStre
   {
     const int smem2 = WG2_B_STAGES * (nt == 3 ? 2 : 1) * mt * TC_TILE_BYTES + 1024 + 256;
     if (nt == 3) {
-      if (mt == 2) tc_wgrad_kernel_v2<2, 3><<<grid, WG2_THREADS, smem2, st>>>(p);
-      else tc_wgrad_kernel_v2<1, 3><<<grid, WG2_THREADS, smem2, st>>>(p);
+      if (mt == 2) dcgc_launch(tc_wgrad_kernel_v2<2, 3>, grid, WG2_THREADS, smem2, st, p);
+      else dcgc_launch(tc_wgrad_kernel_v2<1, 3>, grid, WG2_THREADS, smem2, st, p);
     } else {
-      if (mt == 2) tc_wgrad_kernel_v2<2, 1><<<grid, WG2_THREADS, smem2, st>>>(p);
-      else tc_wgrad_kernel_v2<1, 1><<<grid, WG2_THREADS, smem2, st>>>(p);
+      if (mt == 2) dcgc_launch(tc_wgrad_kernel_v2<2, 1>, grid, WG2_THREADS, smem2, st, p);
+      else dcgc_launch(tc_wgrad_kernel_v2<1, 1>, grid, WG2_THREADS, smem2, st, p);
     }
     DCGC_CUDA_LAUNCH_CHECK("tc_wgrad_kernel_v2");
     return DCGC_OK;
@@ -2176,12 +2185,12 @@ extern "C" int dcgcdbg_mma_rate(int variant, int reps, int ctas, long long* out_
   const int smem = 196608 + 1024 + 64;
   if (variant & 32) {          // CTA pairs: `ctas` pairs, one int64 per pair
     DCGC_CUDA_CALL(cudaFuncSetAttribute(mma_rate2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mma_rate2_kernel<<<2 * ctas, 128, smem, (cudaStream_t)stream>>>(variant, reps, out_dev);
+    dcgc_launch(mma_rate2_kernel, 2 * ctas, 128, smem, (cudaStream_t)stream, variant, reps, out_dev);
     DCGC_CUDA_LAUNCH_CHECK("mma_rate2_kernel");
     return DCGC_OK;
   }
   DCGC_CUDA_CALL(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  mma_rate_kernel<<<ctas, 128, smem, (cudaStream_t)stream>>>(variant, reps, out_dev);
+  dcgc_launch(mma_rate_kernel, ctas, 128, smem, (cudaStream_t)stream, variant, reps, out_dev);
   DCGC_CUDA_LAUNCH_CHECK("mma_rate_kernel");
   return DCGC_OK;
 }

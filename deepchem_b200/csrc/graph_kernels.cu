@@ -46,6 +46,7 @@ inline unsigned grid_for(int64_t work) { return (unsigned)((work + kThreads - 1)
 __global__ void __launch_bounds__(kThreads)
 permute_rows_kernel(const float* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ perm,
                     int64_t n_rows, int n_feat, float* __restrict__ dst, int64_t ld_dst) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t row = t / ld_dst;
   const int c = (int)(t - row * ld_dst);
@@ -58,6 +59,7 @@ permute_rows_kernel(const float* __restrict__ src, int64_t ld_src, const int32_t
 __global__ void __launch_bounds__(kThreads)
 permute_rows_i8_kernel(const int8_t* __restrict__ src, int64_t ld_src, const int32_t* __restrict__ perm,
                        int64_t n_rows, int n_feat, float* __restrict__ dst, int64_t ld_dst) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int groups = (int)(ld_dst >> 2);
   const int64_t row = t / groups;
@@ -88,6 +90,7 @@ __global__ void __launch_bounds__(kThreads)
 gather_sum_kernel(const float* __restrict__ x, int64_t ld_x, const int32_t* __restrict__ row_ptr,
                   const DegBuckets bk, const int32_t* __restrict__ idx, int64_t n_rows, int groups, int width,
                   const float* addend, int64_t ld_add, float* out, int64_t ld_out) {
+  dcgc_griddep_wait();
   using V = Vec<VEC>;
   const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t row = t / groups;
@@ -154,6 +157,7 @@ pool_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restri
                 const float* __restrict__ shift, const int32_t* __restrict__ row_ptr,
                 const int32_t* __restrict__ col_idx, int64_t n_rows, int groups, int width,
                 float* __restrict__ out, int64_t ld_out, uint8_t* __restrict__ arg, int64_t ld_arg) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t row = t / groups;
   const int c = (int)(t - row * groups) * VEC;
@@ -235,6 +239,7 @@ pool_bwd_kernel(const float* __restrict__ dy, int64_t ld_dy, const uint8_t* __re
                 int64_t ld_arg, const float* __restrict__ scale, const int32_t* __restrict__ t_row_ptr,
                 const int32_t* __restrict__ t_src, const int32_t* __restrict__ t_slot, int64_t n_rows,
                 int groups, int width, float* __restrict__ dx, int64_t ld_dx) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t row = t / groups;
   const int c = (int)(t - row * groups) * VEC;
@@ -298,6 +303,7 @@ gather_fwd_kernel(const float* __restrict__ x, int64_t ld_x, const float* __rest
                   const int32_t* __restrict__ mol_atoms, int64_t n_seg, int groups, int width, int act,
                   float* __restrict__ out, int64_t ld_out, int32_t* __restrict__ argrow,
                   const float* __restrict__ mean, float* __restrict__ zc_sum, float* __restrict__ zc_arg) {
+  dcgc_griddep_wait();
   // zc_sum / zc_arg (training with BatchNorm folded in, optional): per molecule the sum over its rows of the RAW input
   // centred on the batch mean, and the centred raw value of the row that attains the max — what the BatchNorm backward
   // of the layer in front needs to form its column sums at MOLECULE level (dense_bn_sums_kernel, model.cu)
@@ -369,6 +375,7 @@ __global__ void __launch_bounds__(kThreads)
 gather_bwd_kernel(const float* __restrict__ dout, int64_t ld_dout, const float* __restrict__ out,
                   int64_t ld_out, const int32_t* __restrict__ argrow, const int32_t* __restrict__ membership,
                   int64_t n_rows, int groups, int width, int act, float* __restrict__ dx, int64_t ld_dx) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t row = t / groups;
   const int c = (int)(t - row * groups) * VEC;
@@ -392,6 +399,7 @@ __global__ void __launch_bounds__(kThreads)
 gather_bwd_vec_kernel(const float* __restrict__ dout, int64_t ld_dout, const float* __restrict__ out,
                       int64_t ld_out, const int32_t* __restrict__ argrow, const int32_t* __restrict__ membership,
                       int64_t n_rows, int groups, int width, int act, float* __restrict__ dx, int64_t ld_dx) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   const int64_t row = t / groups;
   const int c = (int)(t - row * groups) * 4;
@@ -422,6 +430,7 @@ gather_bwd_apply_kernel(const float* __restrict__ dout, int64_t ld_dout, const f
                         int width, int act, const float* __restrict__ z, int64_t ld_z, const float* __restrict__ mean,
                         const float* __restrict__ invstd, const float* __restrict__ coef, float* __restrict__ g,
                         int64_t ld_g, int64_t rows_per_chunk) {
+  dcgc_griddep_wait();
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.y * 128 + 4 * cx;
   if (c >= width) return;
@@ -475,6 +484,7 @@ dense_bn_sums_kernel(const float* __restrict__ dout, int64_t ld_dout, const floa
                      const int32_t* __restrict__ argrow, const int32_t* __restrict__ mol_ptr, int64_t n_seg, int width,
                      int act, const float* __restrict__ zc_sum, const float* __restrict__ zc_arg,
                      const float* __restrict__ mean, double* __restrict__ part) {
+  dcgc_griddep_wait();
   const int cx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int c = blockIdx.y * 32 + cx;
   const int64_t m0 = (int64_t)blockIdx.x * kDbsMols, m1 = min(n_seg, m0 + kDbsMols);
@@ -529,6 +539,7 @@ gather_bwd_stats_kernel(const float* __restrict__ dout, int64_t ld_dout, const f
                         const int32_t* __restrict__ argrow, const int32_t* __restrict__ membership, int64_t n_rows,
                         int width, int act, float* __restrict__ dx, int64_t ld_dx, const float* __restrict__ z,
                         int64_t ld_z, int64_t rows_per_chunk, double* __restrict__ part, const DcgcBnFin bnfin) {
+  dcgc_griddep_wait();
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.y * 128 + 4 * cx;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
@@ -624,7 +635,7 @@ extern "C" int dcgc_permute_rows(const float* src, int64_t ld_src, const int32_t
                  "dcgc_permute_rows: bad sizes");
   if (n_rows == 0 || ld_dst == 0) return DCGC_OK;
   DCGC_CHECK_ARG(src && perm && dst, "dcgc_permute_rows: null pointer");
-  permute_rows_kernel<<<grid_for(n_rows * ld_dst), kThreads, 0, (cudaStream_t)stream>>>(
+  dcgc_launch(permute_rows_kernel, grid_for(n_rows * ld_dst), kThreads, 0, (cudaStream_t)stream, 
       src, ld_src, perm, n_rows, n_feat, dst, ld_dst);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_permute_rows");
   return DCGC_OK;
@@ -636,7 +647,7 @@ extern "C" int dcgc_permute_rows_i8(const int8_t* src, int64_t ld_src, const int
   if (n_rows == 0 || ld_dst == 0) return DCGC_OK;
   DCGC_CHECK_ARG(src && perm && dst, "dcgc_permute_rows_i8: null pointer");
   DCGC_CHECK_ARG(ld_dst % 4 == 0 && aligned16(dst), "dcgc_permute_rows_i8: dst rows must be 16-byte aligned");
-  permute_rows_i8_kernel<<<grid_for(n_rows * (ld_dst / 4)), kThreads, 0, (cudaStream_t)stream>>>(
+  dcgc_launch(permute_rows_i8_kernel, grid_for(n_rows * (ld_dst / 4)), kThreads, 0, (cudaStream_t)stream, 
       src, ld_src, perm, n_rows, n_feat, dst, ld_dst);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_permute_rows_i8");
   return DCGC_OK;
@@ -669,7 +680,7 @@ static int gather_sum_impl(const float* x, int64_t ld_x, const int32_t* row_ptr,
   const int groups = v4 ? width / 4 : width;
   const unsigned grid = grid_for(n_rows_out * groups);
 #define DCGC_GS_LAUNCH(V, B) \
-  gather_sum_kernel<V, B><<<grid, kThreads, 0, st>>>(x, ld_x, row_ptr, bk, idx, n_rows_out, groups, width, addend, ld_add, out, ld_out)
+  dcgc_launch(gather_sum_kernel<V, B>, grid, kThreads, 0, st, x, ld_x, row_ptr, bk, idx, n_rows_out, groups, width, addend, ld_add, out, ld_out)
   if (v4) { if (deg_count) DCGC_GS_LAUNCH(4, true); else DCGC_GS_LAUNCH(4, false); }
   else { if (deg_count) DCGC_GS_LAUNCH(1, true); else DCGC_GS_LAUNCH(1, false); }
 #undef DCGC_GS_LAUNCH
@@ -708,7 +719,7 @@ extern "C" int dcgc_pool_fwd(const float* x, int64_t ld_x, const float* scale, c
   const unsigned grid = grid_for(n_rows * groups);
   cudaStream_t st = (cudaStream_t)stream;
 #define DCGC_POOL_LAUNCH(V, A, R)                                                              \
-  pool_fwd_kernel<V, A, R><<<grid, kThreads, 0, st>>>(x, ld_x, scale, shift, row_ptr, col_idx, \
+  dcgc_launch(pool_fwd_kernel<V, A, R>, grid, kThreads, 0, st, x, ld_x, scale, shift, row_ptr, col_idx, \
                                                       n_rows, groups, width, out, ld_out, arg, ld_arg)
   if (v4) {
     if (scale) { if (arg) DCGC_POOL_LAUNCH(4, true, true); else DCGC_POOL_LAUNCH(4, true, false); }
@@ -737,7 +748,7 @@ extern "C" int dcgc_pool_bwd(const float* dy, int64_t ld_dy, const uint8_t* arg,
   const unsigned grid = grid_for(n_rows * groups);
   cudaStream_t st = (cudaStream_t)stream;
 #define DCGC_POOLB_LAUNCH(V, A)                                                                   \
-  pool_bwd_kernel<V, A><<<grid, kThreads, 0, st>>>(dy, ld_dy, arg, ld_arg, scale, t_row_ptr, t_src, \
+  dcgc_launch(pool_bwd_kernel<V, A>, grid, kThreads, 0, st, dy, ld_dy, arg, ld_arg, scale, t_row_ptr, t_src, \
                                                    t_slot, n_rows, groups, width, dx, ld_dx)
   if (v4) { if (scale) DCGC_POOLB_LAUNCH(4, true); else DCGC_POOLB_LAUNCH(4, false); }
   else { if (scale) DCGC_POOLB_LAUNCH(1, true); else DCGC_POOLB_LAUNCH(1, false); }
@@ -774,7 +785,7 @@ int dcgc_gather_fwd_train(const float* x, int64_t ld_x, const float* scale, cons
   const unsigned grid = grid_for(n_segments * groups);
   cudaStream_t st = (cudaStream_t)stream;
 #define DCGC_GATHER_LAUNCH(V, R)                                                                    \
-  gather_fwd_kernel<V, R><<<grid, kThreads, 0, st>>>(x, ld_x, scale, shift, mol_ptr, mol_atoms,      \
+  dcgc_launch(gather_fwd_kernel<V, R>, grid, kThreads, 0, st, x, ld_x, scale, shift, mol_ptr, mol_atoms,      \
                                                      n_segments, groups, width, act, out, ld_out, argrow, mean,  \
                                                      zc_sum, zc_arg)
   if (v4) { if (argrow) DCGC_GATHER_LAUNCH(4, true); else DCGC_GATHER_LAUNCH(4, false); }
@@ -797,10 +808,10 @@ extern "C" int dcgc_gather_bwd(const float* dout, int64_t ld_dout, const float* 
   const bool v4 = width % 4 == 0 && ld_dout % 4 == 0 && ld_out % 4 == 0 && ld_dx % 4 == 0 && aligned16(dout) &&
                   aligned16(out) && aligned16(dx) && aligned16(argrow);
   if (v4)
-    gather_bwd_vec_kernel<<<grid_for(n_rows * groups), kThreads, 0, (cudaStream_t)stream>>>(
+    dcgc_launch(gather_bwd_vec_kernel, grid_for(n_rows * groups), kThreads, 0, (cudaStream_t)stream, 
         dout, ld_dout, out, ld_out, argrow, membership, n_rows, groups, width, act, dx, ld_dx);
   else
-    gather_bwd_kernel<4><<<grid_for(n_rows * groups), kThreads, 0, (cudaStream_t)stream>>>(
+    dcgc_launch(gather_bwd_kernel<4>, grid_for(n_rows * groups), kThreads, 0, (cudaStream_t)stream, 
         dout, ld_dout, out, ld_out, argrow, membership, n_rows, groups, width, act, dx, ld_dx);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_gather_bwd");
   return DCGC_OK;
@@ -826,7 +837,7 @@ int dcgc_gather_bwd_stats(const float* dout, int64_t ld_dout, const float* out, 
   rows = (rows + kGbRowLanes - 1) / kGbRowLanes * kGbRowLanes;
   chunks = (n_rows + rows - 1) / rows;
   dim3 grid((unsigned)chunks, (unsigned)((width + 127) / 128));
-  gather_bwd_stats_kernel<<<grid, 32 * kGbRowLanes, 0, (cudaStream_t)stream>>>(
+  dcgc_launch(gather_bwd_stats_kernel, grid, 32 * kGbRowLanes, 0, (cudaStream_t)stream, 
       dout, ld_dout, out, ld_out, argrow, membership, n_rows, width, act, dx, ld_dx, z, ld_z, rows, part,
       fin ? *fin : DcgcBnFin{});
   DCGC_CUDA_LAUNCH_CHECK("dcgc_gather_bwd_stats");
@@ -845,7 +856,7 @@ int dcgc_dense_bn_sums(const float* dout, int64_t ld_dout, const float* out, int
   DcgcProfScope prof_scope("bn_stats_bwd", (cudaStream_t)stream);
   const int64_t chunks = (n_segments + kDbsMols - 1) / kDbsMols;
   dim3 grid((unsigned)chunks, (unsigned)((width + 31) / 32));
-  dense_bn_sums_kernel<<<grid, 32 * kDbsLanes, 0, (cudaStream_t)stream>>>(dout, ld_dout, out, ld_out, argrow, mol_ptr, n_segments, width,
+  dcgc_launch(dense_bn_sums_kernel, grid, 32 * kDbsLanes, 0, (cudaStream_t)stream, dout, ld_dout, out, ld_out, argrow, mol_ptr, n_segments, width,
                                                              act, zc_sum, zc_arg, mean, part);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_dense_bn_sums");
   *n_chunks_out = (int32_t)chunks;
@@ -869,7 +880,7 @@ int dcgc_gather_bwd_apply(const float* dout, int64_t ld_dout, const float* out, 
   rows = (rows + kGbRowLanes - 1) / kGbRowLanes * kGbRowLanes;
   chunks = (n_rows + rows - 1) / rows;
   dim3 grid((unsigned)chunks, (unsigned)((width + 127) / 128));
-  gather_bwd_apply_kernel<<<grid, 32 * kGbRowLanes, 0, (cudaStream_t)stream>>>(
+  dcgc_launch(gather_bwd_apply_kernel, grid, 32 * kGbRowLanes, 0, (cudaStream_t)stream, 
       dout, ld_dout, out, ld_out, argrow, membership, n_rows, width, act, z, ld_z, mean, invstd, coef, g, ld_g, rows);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_gather_bwd_apply");
   return DCGC_OK;

@@ -55,6 +55,7 @@ inline int part_chunks(int64_t n) {
 __global__ void __launch_bounds__(32 * kMomLanes, 2)
 col_moments_partial(const float* __restrict__ a, int64_t ld_a, const float* __restrict__ b, int64_t ld_b,
                     int64_t n_rows, int width, int64_t rows_per_chunk, double* __restrict__ part) {
+  dcgc_griddep_wait();
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.y * 128 + 4 * cx;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_chunk;
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(32 * kFinCols) bn_fwd_finalize(const double* _
                                 float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
                                 float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                 float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  dcgc_griddep_wait();
   double s, ss;
   int c;
   if (!reduce_partials(part, n_chunks, width, s, ss, c)) return;
@@ -167,6 +169,7 @@ __global__ void __launch_bounds__(32 * kFinCols) bn_fwd_finalize(const double* _
 __global__ void bn_eval_fold(const float* __restrict__ gamma, const float* __restrict__ beta,
                              const float* __restrict__ running_mean, const float* __restrict__ running_var,
                              float eps, int width, float* __restrict__ scale_out, float* __restrict__ shift_out) {
+  dcgc_griddep_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= width) return;
   const float invstd = 1.f / sqrtf(running_var[c] + eps);
@@ -181,6 +184,7 @@ __global__ void __launch_bounds__(32 * kFinCols) bn_bwd_finalize(const double* _
                                 const float* __restrict__ mean, const float* __restrict__ invstd,
                                 const float* __restrict__ scale, float* __restrict__ dgamma,
                                 float* __restrict__ dbeta, float* __restrict__ coef /* [3, width] */) {
+  dcgc_griddep_wait();
   double sda, sday;
   int c;
   if (!reduce_partials(part, n_chunks, width, sda, sday, c)) return;
@@ -201,6 +205,7 @@ __global__ void __launch_bounds__(kT)
 bn_relu_bwd_apply(const float* da, int64_t ld_da, const float* __restrict__ y, int64_t ld_y,
                   const float* __restrict__ mean, const float* __restrict__ invstd,
                   const float* __restrict__ coef, int64_t n_rows, int width, int relu, float* g, int64_t ld_g) {
+  dcgc_griddep_wait();
   const int groups = width >> 2;
   const int rows_per_block = (kT / groups) * kApplyRows;      // kT is a multiple of groups or groups > kT
   const int tg = threadIdx.x % groups, tr = threadIdx.x / groups;
@@ -243,6 +248,7 @@ bn_relu_bwd_apply(const float* da, int64_t ld_da, const float* __restrict__ y, i
 __global__ void __launch_bounds__(kT)
 relu_bwd_apply(const float* da, int64_t ld_da, const float* __restrict__ y, int64_t ld_y, int64_t n_rows,
                int width, float* g, int64_t ld_g) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * kT + threadIdx.x;
   const int groups = width >> 2;
   const int64_t row = t / groups;
@@ -276,6 +282,7 @@ bn_sync_kernel(const SyncArgs sy, const double* __restrict__ part, int n_chunks,
                float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_io,
                float* __restrict__ invstd_io, float* __restrict__ scale_io, float* __restrict__ shift_out,
                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+  dcgc_griddep_wait();
   const int t = threadIdx.x;
   const int slot = (int)(sy.seq & 1ull);
   const size_t row = 2 * (size_t)sy.cap + 2;
@@ -395,6 +402,7 @@ bn_sync_kernel(const SyncArgs sy, const double* __restrict__ part, int n_chunks,
 struct BiasPackAll { const float* b21[DCGC_MODEL_MAX_LAYERS]; float* b11[DCGC_MODEL_MAX_LAYERS]; int c[DCGC_MODEL_MAX_LAYERS]; };
 // every conv layer of the model in one launch (blockIdx.y = layer)
 __global__ void conv_bias_pack_all(const BiasPackAll a) {
+  dcgc_griddep_wait();
   const int l = blockIdx.y, c_out = a.c[l];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= DCGC_N_DEG * c_out) return;
@@ -408,6 +416,7 @@ __global__ void conv_bias_pack_all(const BiasPackAll a) {
 __global__ void __launch_bounds__(kT)
 head_fwd(const float* __restrict__ fp, int64_t ld_fp, const float* __restrict__ wh, const float* __restrict__ bh,
          int64_t n_rows, int k, int n_out, float* __restrict__ out) {
+  dcgc_griddep_wait();
   const int64_t warp = ((int64_t)blockIdx.x * kT + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n_rows * n_out) return;
@@ -426,6 +435,7 @@ head_fwd(const float* __restrict__ fp, int64_t ld_fp, const float* __restrict__ 
 __global__ void __launch_bounds__(kT)
 loss_fwd_bwd(const float* __restrict__ out, const float* __restrict__ y, const float* __restrict__ w,
              int64_t n_elems, int n_classes, int mode, float* __restrict__ per_elem, float* __restrict__ dout) {
+  dcgc_griddep_wait();
   const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
   if (i >= n_elems) return;
   const float wi = w ? w[i] : 1.f;
@@ -454,6 +464,7 @@ loss_fwd_bwd(const float* __restrict__ out, const float* __restrict__ y, const f
 
 __global__ void __launch_bounds__(1024) loss_reduce(const float* __restrict__ per_elem, int64_t n_elems,
                                                     float* __restrict__ loss) {
+  dcgc_griddep_wait();
   __shared__ double sh[1024];
   double s = 0.0;
   for (int64_t i = threadIdx.x; i < n_elems; i += 1024) s += per_elem[i];
@@ -468,6 +479,7 @@ __global__ void __launch_bounds__(1024) loss_reduce(const float* __restrict__ pe
 
 __global__ void softmax_rows(const float* __restrict__ logits, int64_t n_rows, int n_classes,
                              float* __restrict__ probs) {
+  dcgc_griddep_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows) return;
   const float* lg = logits + i * n_classes;
@@ -483,6 +495,7 @@ constexpr int kHeadChunk = 128;
 __global__ void __launch_bounds__(kT)
 head_bwd_partial(const float* __restrict__ dout, const float* __restrict__ fp, int64_t ld_fp, int64_t n_rows,
                  int k, int n_out, float* __restrict__ part /* [chunks, n_out, k+1] */) {
+  dcgc_griddep_wait();
   const int t = blockIdx.y;
   const int64_t b0 = (int64_t)blockIdx.x * kHeadChunk, b1 = min(n_rows, b0 + kHeadChunk);
   for (int j = threadIdx.x; j <= k; j += kT) {
@@ -497,6 +510,7 @@ head_bwd_partial(const float* __restrict__ dout, const float* __restrict__ fp, i
 }
 __global__ void head_bwd_final(const float* __restrict__ part, int n_chunks, int k, int n_out,
                                float* __restrict__ dwh, float* __restrict__ dbh) {
+  dcgc_griddep_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)n_out * (k + 1)) return;
   const int t = (int)(i / (k + 1)), j = (int)(i - (int64_t)t * (k + 1));
@@ -509,6 +523,7 @@ __global__ void head_bwd_final(const float* __restrict__ part, int n_chunks, int
 __global__ void __launch_bounds__(kT)
 head_bwd_input(const float* __restrict__ dout, const float* __restrict__ wh, int64_t n_rows, int64_t n_seg, int k,
                int n_out, float* __restrict__ dfp) {
+  dcgc_griddep_wait();
   const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
   if (i >= n_seg * k) return;
   const int64_t b = i / k;
@@ -533,6 +548,7 @@ head_fused_kernel(const float* __restrict__ fp, int64_t ld_fp, const float* __re
                   const float* __restrict__ y, const float* __restrict__ w, int64_t n_samples, int64_t n_seg, int k,
                   int n_out, int n_classes, int mode, int64_t n_elems, float* __restrict__ out, float* __restrict__ dfp,
                   float* __restrict__ part /* [blocks][n_out][k + 1] */, double* __restrict__ loss_part /* [blocks] */) {
+  dcgc_griddep_wait();
   extern __shared__ float hsm[];
   const int kp = k + 1;
   float* fp_s = hsm;                          // [32][k + 1]
@@ -662,6 +678,7 @@ head_fused_kernel(const float* __restrict__ fp, int64_t ld_fp, const float* __re
 __global__ void __launch_bounds__(kT)
 head_fused_final(const float* __restrict__ part, const double* __restrict__ loss_part, int n_blocks, int k, int n_out,
                  int64_t n_elems, float* __restrict__ dwh, float* __restrict__ dbh, float* __restrict__ loss) {
+  dcgc_griddep_wait();
   const int64_t i = ((int64_t)blockIdx.x * kT + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t n_el = (int64_t)n_out * (k + 1);
@@ -690,6 +707,7 @@ head_fused_final(const float* __restrict__ part, const double* __restrict__ loss
 __global__ void __launch_bounds__(kT)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             int64_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+  dcgc_griddep_wait();
   const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
   if (i >= n) return;
   const float gi = g[i] * grad_scale;
@@ -705,6 +723,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 __global__ void __launch_bounds__(kT)
 adam_kernel_vec(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
                 int64_t n4, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt, float grad_scale) {
+  dcgc_griddep_wait();
   const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
   if (i >= n4) return;
   const float4 gv = g[i];
@@ -937,25 +956,25 @@ int bn_forward(const dcgc_gcmodel_config* cfg, const Layout& lo, int idx, const 
       chunks = n > 0 ? sv.n_chunks : 0;
       if (n > 0) {
         dim3 grid((unsigned)sv.n_chunks, (unsigned)((width + 127) / 128));
-        col_moments_partial<<<grid, 32 * kMomLanes, 0, st>>>(y, ld_y, y, ld_y, n, width, mom_rows(n, sv.n_chunks),
+        dcgc_launch(col_moments_partial, grid, 32 * kMomLanes, 0, st, y, ld_y, y, ld_y, n, width, mom_rows(n, sv.n_chunks),
                                                              sv.part);
         DCGC_CUDA_LAUNCH_CHECK("col_moments_partial");
       }
     }
     if (sv.sync) {
       // statistics over the rows of every rank: exchange through the peer mailboxes inside the finalize kernel
-      bn_sync_kernel<1><<<1, 512, 0, st>>>(sync_args(sv.sync, sv.sync->seq0 + (unsigned long long)idx), sv.part, chunks,
+      dcgc_launch(bn_sync_kernel<1>, 1, 512, 0, st, sync_args(sv.sync, sv.sync->seq0 + (unsigned long long)idx), sv.part, chunks,
                                            width, (long long)n, gamma, beta, cfg->bn_eps, cfg->bn_momentum, rm, rv, mean,
                                            invstd, scale, shift, nullptr, nullptr, nullptr);
       DCGC_CUDA_LAUNCH_CHECK("bn_sync_kernel (forward)");
       return DCGC_OK;
     }
-    bn_fwd_finalize<<<(width + kFinCols - 1) / kFinCols, 32 * kFinCols, 0, st>>>(sv.part, chunks, width, n, gamma, beta, cfg->bn_eps,
+    dcgc_launch(bn_fwd_finalize, (width + kFinCols - 1) / kFinCols, 32 * kFinCols, 0, st, sv.part, chunks, width, n, gamma, beta, cfg->bn_eps,
                                                        cfg->bn_momentum, rm, rv, mean, invstd, scale, shift);
     DCGC_CUDA_LAUNCH_CHECK("bn_fwd_finalize");
   } else {
     DCGC_CHECK_ARG(rm && rv, "dcgc_gcmodel: eval-mode BatchNorm needs the running statistics");
-    bn_eval_fold<<<(width + 127) / 128, 128, 0, st>>>(gamma, beta, rm, rv, cfg->bn_eps, width, scale, shift);
+    dcgc_launch(bn_eval_fold, (width + 127) / 128, 128, 0, st, gamma, beta, rm, rv, cfg->bn_eps, width, scale, shift);
     DCGC_CUDA_LAUNCH_CHECK("bn_eval_fold");
   }
   return DCGC_OK;
@@ -1007,7 +1026,7 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
       cmax = cmax > cfg->widths[l] ? cmax : cfg->widths[l];
     }
     dim3 grid(blocks_for(DCGC_N_DEG * cmax), (unsigned)L);
-    conv_bias_pack_all<<<grid, kT, 0, st>>>(bp);
+    dcgc_launch(conv_bias_pack_all, grid, kT, 0, st, bp);
     DCGC_CUDA_LAUNCH_CHECK("conv_bias_pack_all");
   }
   for (int l = 0; l < L; ++l) {
@@ -1065,7 +1084,7 @@ int forward_impl(const dcgc_gcmodel_config* cfg, const Layout& lo, const dcgc_to
   RET_IF(dcgc_gather_fwd_train(sv.z, D, scale, shift, t->mol_ptr, t->mol_atoms, S, D, DCGC_ACT_TANH, sv.fp, 2 * D,
                                sv.argrow, sv.zc_sum ? sv.stats + sv.stats_off[L] : nullptr, sv.zc_sum, sv.zc_arg, st));
   if (n_samples > 0 && !skip_head) {
-    head_fwd<<<blocks_for(n_samples * cfg->n_out * 32), kT, 0, st>>>(sv.fp, 2 * D, params + lo.head_w,
+    dcgc_launch(head_fwd, blocks_for(n_samples * cfg->n_out * 32), kT, 0, st, sv.fp, 2 * D, params + lo.head_w,
                                                                     params + lo.head_b, n_samples, 2 * D, cfg->n_out,
                                                                     sv.out);
     DCGC_CUDA_LAUNCH_CHECK("head_fwd");
@@ -1157,7 +1176,7 @@ extern "C" int dcgc_gcmodel_forward(const dcgc_gcmodel_config* cfg, const dcgc_t
     DCGC_CUDA_CALL(cudaMemcpyAsync(out, sv.out, (size_t)n_samples * cfg->n_out * 4, cudaMemcpyDeviceToDevice, st));
   if (probs && n_samples > 0 && cfg->mode == 1) {
     const int64_t rows = n_samples * (cfg->n_out / cfg->n_classes);
-    softmax_rows<<<blocks_for(rows), kT, 0, st>>>(sv.out, rows, cfg->n_classes, probs);
+    dcgc_launch(softmax_rows, blocks_for(rows), kT, 0, st, sv.out, rows, cfg->n_classes, probs);
     DCGC_CUDA_LAUNCH_CHECK("softmax_rows");
   }
   return DCGC_OK;
@@ -1330,12 +1349,12 @@ extern "C" int dcgc_gcmodel_train_step_sync(const dcgc_gcmodel_config* cfg, cons
       attr_done = true;
     }
     if (head_blocks > 0) {
-      head_fused_kernel<<<head_blocks, kT, head_fused_smem(cfg), st>>>(
+      dcgc_launch(head_fused_kernel, head_blocks, kT, head_fused_smem(cfg), st, 
           sv.fp, 2 * D, params + lo.head_w, params + lo.head_b, y, w, n_samples, S, 2 * D, T,
           cfg->mode == 1 ? cfg->n_classes : 1, cfg->mode, n_elems, sv.out, dfp, head_part, loss_part);
       DCGC_CUDA_LAUNCH_CHECK("head_fused_kernel");
     }
-    head_fused_final<<<blocks_for(((int64_t)T * (2 * D + 1) + 1) * 32), kT, 0, st>>>(head_part, loss_part, head_blocks, 2 * D, T,
+    dcgc_launch(head_fused_final, blocks_for(((int64_t)T * (2 * D + 1) + 1) * 32), kT, 0, st, head_part, loss_part, head_blocks, 2 * D, T,
                                                                           n_elems, grads + lo.head_w,
                                                                           grads + lo.head_b, loss_dev);
     DCGC_CUDA_LAUNCH_CHECK("head_fused_final");
@@ -1343,24 +1362,24 @@ extern "C" int dcgc_gcmodel_train_step_sync(const dcgc_gcmodel_config* cfg, cons
       DCGC_CUDA_CALL(cudaMemcpyAsync(out, sv.out, (size_t)n_samples * T * 4, cudaMemcpyDeviceToDevice, st));
   } else {
   if (n_elems > 0) {
-    loss_fwd_bwd<<<blocks_for(n_elems), kT, 0, st>>>(sv.out, y, w, n_elems, cfg->mode == 1 ? cfg->n_classes : 1,
+    dcgc_launch(loss_fwd_bwd, blocks_for(n_elems), kT, 0, st, sv.out, y, w, n_elems, cfg->mode == 1 ? cfg->n_classes : 1,
                                                      cfg->mode, per_elem, dout);
     DCGC_CUDA_LAUNCH_CHECK("loss_fwd_bwd");
   }
-  loss_reduce<<<1, 1024, 0, st>>>(per_elem, n_elems, loss_dev);
+  dcgc_launch(loss_reduce, 1, 1024, 0, st, per_elem, n_elems, loss_dev);
   DCGC_CUDA_LAUNCH_CHECK("loss_reduce");
   if (out && n_samples > 0)
     DCGC_CUDA_CALL(cudaMemcpyAsync(out, sv.out, (size_t)n_samples * T * 4, cudaMemcpyDeviceToDevice, st));
   if (head_chunks > 0) {
     dim3 grid((unsigned)head_chunks, (unsigned)T);
-    head_bwd_partial<<<grid, kT, 0, st>>>(dout, sv.fp, 2 * D, n_samples, 2 * D, T, head_part);
+    dcgc_launch(head_bwd_partial, grid, kT, 0, st, dout, sv.fp, 2 * D, n_samples, 2 * D, T, head_part);
     DCGC_CUDA_LAUNCH_CHECK("head_bwd_partial");
   }
-  head_bwd_final<<<blocks_for((int64_t)T * (2 * D + 1)), kT, 0, st>>>(head_part, head_chunks, 2 * D, T,
+  dcgc_launch(head_bwd_final, blocks_for((int64_t)T * (2 * D + 1)), kT, 0, st, head_part, head_chunks, 2 * D, T,
                                                                       grads + lo.head_w, grads + lo.head_b);
   DCGC_CUDA_LAUNCH_CHECK("head_bwd_final");
   if (S > 0) {
-    head_bwd_input<<<blocks_for(S * 2 * D), kT, 0, st>>>(dout, params + lo.head_w, n_samples, S, 2 * D, T, dfp);
+    dcgc_launch(head_bwd_input, blocks_for(S * 2 * D), kT, 0, st, dout, params + lo.head_w, n_samples, S, 2 * D, T, dfp);
     DCGC_CUDA_LAUNCH_CHECK("head_bwd_input");
   }
   }
@@ -1386,20 +1405,20 @@ extern "C" int dcgc_gcmodel_train_step_sync(const dcgc_gcmodel_config* cfg, cons
       DcgcProfScope prof_scope("bn_stats_bwd", st);
       if (N > 0 && fused_chunks < 0) {
         dim3 grid((unsigned)sv.n_chunks, (unsigned)((width + 127) / 128));
-        col_moments_partial<<<grid, 32 * kMomLanes, 0, st>>>(dA, width, yv, width, N, width,
+        dcgc_launch(col_moments_partial, grid, 32 * kMomLanes, 0, st, dA, width, yv, width, N, width,
                                                              mom_rows(N, sv.n_chunks), sv.part);
         DCGC_CUDA_LAUNCH_CHECK("col_moments_partial (bwd)");
       }
       if (sv.sync) {
         const int chunks = fused_chunks >= 0 ? fused_chunks : (N > 0 ? sv.n_chunks : 0);
         float* stats_w = sv.stats + sv.stats_off[idx];
-        bn_sync_kernel<2><<<1, 512, 0, st>>>(
+        dcgc_launch(bn_sync_kernel<2>, 1, 512, 0, st, 
             sync_args(sv.sync, sv.sync->seq0 + (unsigned long long)(L + 1 + (L - idx))), sv.part, chunks, width,
             (long long)N, nullptr, nullptr, 0.f, 0.f, nullptr, nullptr, stats_w, stats_w + width, stats_w + 2 * width,
             nullptr, grads + lo.bn_g[idx], grads + lo.bn_b[idx], coef);
         DCGC_CUDA_LAUNCH_CHECK("bn_sync_kernel (backward)");
       } else if (!(finalized && fused_chunks >= 0)) {
-        bn_bwd_finalize<<<(width + kFinCols - 1) / kFinCols, 32 * kFinCols, 0, st>>>(sv.part, fused_chunks >= 0 ? fused_chunks : (N > 0 ? sv.n_chunks : 0), width, N, stats,
+        dcgc_launch(bn_bwd_finalize, (width + kFinCols - 1) / kFinCols, 32 * kFinCols, 0, st, sv.part, fused_chunks >= 0 ? fused_chunks : (N > 0 ? sv.n_chunks : 0), width, N, stats,
                                                              stats + width, stats + 2 * width, grads + lo.bn_g[idx],
                                                              grads + lo.bn_b[idx], coef);
         DCGC_CUDA_LAUNCH_CHECK("bn_bwd_finalize");
@@ -1411,12 +1430,12 @@ extern "C" int dcgc_gcmodel_train_step_sync(const dcgc_gcmodel_config* cfg, cons
         const int groups = width / 4;
         DCGC_CHECK_ARG(groups <= kT, "dcgc_gcmodel: layer width above %d is not supported by bn_relu_bwd_apply", 4 * kT);
         const int64_t rows_per_block = (int64_t)(kT / groups) * kApplyRows;
-        bn_relu_bwd_apply<<<(unsigned)((N + rows_per_block - 1) / rows_per_block), kT, 0, st>>>(
+        dcgc_launch(bn_relu_bwd_apply, (unsigned)((N + rows_per_block - 1) / rows_per_block), kT, 0, st, 
             dA, width, yv, width, stats, stats + width, coef, N, width, 1, dA, width);
         DCGC_CUDA_LAUNCH_CHECK("bn_relu_bwd_apply");
       }
     } else if (N > 0) {
-      relu_bwd_apply<<<blocks_for(N * (width / 4)), kT, 0, st>>>(dA, width, yv, width, N, width, dA, width);
+      dcgc_launch(relu_bwd_apply, blocks_for(N * (width / 4)), kT, 0, st, dA, width, yv, width, N, width, dA, width);
       DCGC_CUDA_LAUNCH_CHECK("relu_bwd_apply");
     }
     return DCGC_OK;
@@ -1522,11 +1541,11 @@ extern "C" int dcgc_adam_step(float* params, const float* grads, float* exp_avg,
   const int64_t n4 = ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) |
                        reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15) == 0 ? n / 4 : 0;
   if (n4 > 0)
-    adam_kernel_vec<<<blocks_for(n4), kT, 0, (cudaStream_t)stream>>>(
+    dcgc_launch(adam_kernel_vec, blocks_for(n4), kT, 0, (cudaStream_t)stream, 
         reinterpret_cast<float4*>(params), reinterpret_cast<const float4*>(grads), reinterpret_cast<float4*>(exp_avg),
         reinterpret_cast<float4*>(exp_avg_sq), n4, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
   if (n - 4 * n4 > 0)      // the tail (or everything, for unaligned slabs): identical arithmetic per element
-    adam_kernel<<<blocks_for(n - 4 * n4), kT, 0, (cudaStream_t)stream>>>(params + 4 * n4, grads + 4 * n4, exp_avg + 4 * n4,
+    dcgc_launch(adam_kernel, blocks_for(n - 4 * n4), kT, 0, (cudaStream_t)stream, params + 4 * n4, grads + 4 * n4, exp_avg + 4 * n4,
                                                                        exp_avg_sq + 4 * n4, n - 4 * n4, lr, beta1, beta2,
                                                                        eps, (float)bc1, (float)sqrt(bc2), grad_scale);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_adam_step");

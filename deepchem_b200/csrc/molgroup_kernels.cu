@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256)
 mg_prepare_kernel(const MgBuckets bk, const int32_t* __restrict__ groups, int n_groups,
                   const int32_t* __restrict__ col_idx, const int32_t* __restrict__ t_src,
                   const int32_t* __restrict__ t_slot, int n_rows, uint4* __restrict__ rec_f, uint4* __restrict__ rec_b) {
+  dcgc_griddep_wait();
   const int r = blockIdx.x * 256 + threadIdx.x;
   if (r >= n_rows) return;
   int d = 0, r0 = bk.row0[0], e0 = bk.e0[0];
@@ -430,6 +431,7 @@ mg_kernel(const MgGeom geo, const int32_t* __restrict__ groups, int n_groups, co
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  dcgc_griddep_wait();     // (everything above is set-up in shared / tensor memory: it overlaps the kernel in front)
   const int warp = threadIdx.x >> 5;
   if (warp >= kConsumerWarps) {
     const int s = warp - kConsumerWarps;
@@ -550,7 +552,7 @@ int mg_launch(const dcgc_topology* t, const MgGeom& geo, const void* recs, const
   src.p[0] = reinterpret_cast<const char*>(recs);
   src.p[1] = reinterpret_cast<const char*>(rows);
   src.p[2] = reinterpret_cast<const char*>(args);
-  mg_kernel<Op><<<grid, 32 * (kMaxStages + kConsumerWarps), smem, st>>>(geo, t->groups, t->n_groups, src, cgroups, op,
+  dcgc_launch(mg_kernel<Op>, grid, 32 * (kMaxStages + kConsumerWarps), smem, st, geo, t->groups, t->n_groups, src, cgroups, op,
                                                                         g_mg_timeline, g_mg_dbg_mode);
   DCGC_CUDA_LAUNCH_CHECK(what);
   return DCGC_OK;
@@ -579,7 +581,7 @@ extern "C" int dcgc_mg_prepare(const dcgc_topology* t, void* records, void* stre
   if (st0 != DCGC_OK) return st0;
   uint4* rec_f = reinterpret_cast<uint4*>(records);
   uint4* rec_b = t->symmetric ? reinterpret_cast<uint4*>(reinterpret_cast<char*>(records) + t->n_atoms * kRecF) : nullptr;
-  mg_prepare_kernel<<<(unsigned)((t->n_atoms + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  dcgc_launch(mg_prepare_kernel, (unsigned)((t->n_atoms + 255) / 256), 256, 0, (cudaStream_t)stream, 
       bk, t->groups, t->n_groups, t->col_idx, t->t_src, t->t_slot, (int)t->n_atoms, rec_f, rec_b);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_mg_prepare");
   return DCGC_OK;

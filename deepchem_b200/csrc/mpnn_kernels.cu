@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(kT)
 pair_contract_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ pf, int64_t ld_pf,
                      const int32_t* __restrict__ pair_ptr, const int32_t* __restrict__ pair_id,
                      const int32_t* __restrict__ pair_src, int n_pf, int h, float* __restrict__ z, int64_t ld_z) {
+  dcgc_griddep_wait();
   const int i = blockIdx.x;
   const int q0 = __ldg(pair_ptr + i), q1 = __ldg(pair_ptr + i + 1);
   for (int b = threadIdx.x; b < h; b += kT) {
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256)
 gru_gates_kernel(const float* __restrict__ g, int64_t ld_g, const float* __restrict__ bz, const float* __restrict__ br,
                  const float* __restrict__ hprev, int64_t ld_h, int64_t n, int h, float* __restrict__ z, int64_t ld_z,
                  float* __restrict__ hr, int64_t ld_hr) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t r_ = t / h;
   const int c = (int)(t - r_ * h);
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(256)
 gru_out_kernel(const float* __restrict__ g, int64_t ld_g, const float* __restrict__ u, int64_t ld_u,
                const float* __restrict__ bh, const float* __restrict__ z, int64_t ld_z, const float* __restrict__ x,
                int64_t ld_x, int64_t n, int h, float* __restrict__ out, int64_t ld_out) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t r_ = t / h;
   const int c = (int)(t - r_ * h);
@@ -84,6 +87,7 @@ __global__ void __launch_bounds__(kT)
 setgather_attend_kernel(const float* __restrict__ x, int64_t ld_x, const float* __restrict__ q, int64_t ld_q,
                         const int32_t* __restrict__ mol_ptr, const int32_t* __restrict__ mol_atoms, int h,
                         float* __restrict__ qstar, int64_t ld_qs) {
+  dcgc_griddep_wait();
   extern __shared__ float e_sh[];
   __shared__ float red[2];
   const int g = blockIdx.x;
@@ -130,6 +134,7 @@ setgather_attend_kernel(const float* __restrict__ x, int64_t ld_x, const float* 
 __global__ void __launch_bounds__(256)
 lstm_step_kernel(const float* __restrict__ zg, int64_t ld_z, const float* __restrict__ c_in, int64_t n, int h,
                  float* __restrict__ h_out, float* __restrict__ c_out) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t r_ = t / h;
   const int c = (int)(t - r_ * h);
@@ -152,6 +157,7 @@ __global__ void __launch_bounds__(kT)
 pair_contract_bwd_x_kernel(const float* __restrict__ dz, int64_t ld_z, const float* __restrict__ pf, int64_t ld_pf,
                            const int32_t* __restrict__ src_ptr, const int32_t* __restrict__ src_pair,
                            const int32_t* __restrict__ pair_dst, int n_pf, int h, float* __restrict__ dx, int64_t ld_dx) {
+  dcgc_griddep_wait();
   const int j = blockIdx.x;
   const int q0 = __ldg(src_ptr + j), q1 = __ldg(src_ptr + j + 1);
   for (int b = threadIdx.x; b < h; b += kT) {
@@ -180,6 +186,7 @@ gru_out_bwd_kernel(const float* __restrict__ dout, int64_t ld_do, const float* _
                    const float* __restrict__ u, int64_t ld_u, const float* __restrict__ bh, const float* __restrict__ z,
                    int64_t ld_z, const float* __restrict__ x, int64_t ld_x, int64_t n, int h, float* __restrict__ dzg,
                    int64_t ld_dz, float* __restrict__ dx, int64_t ld_dx, float* __restrict__ dpre, int64_t ld_dp) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t r_ = t / h;
   const int c = (int)(t - r_ * h);
@@ -200,6 +207,7 @@ gru_gates_bwd_kernel(const float* __restrict__ dzg, int64_t ld_dz, const float* 
                      const float* __restrict__ bz, const float* __restrict__ br, const float* __restrict__ hprev,
                      int64_t ld_h, int64_t n, int h, float* __restrict__ dg, int64_t ld_dg, float* __restrict__ dh,
                      int64_t ld_dh) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t r_ = t / h;
   const int c = (int)(t - r_ * h);
@@ -223,6 +231,7 @@ setgather_attend_bwd_kernel(const float* __restrict__ x, int64_t ld_x, const flo
                             const float* __restrict__ dqs, int64_t ld_dqs, const int32_t* __restrict__ mol_ptr,
                             const int32_t* __restrict__ mol_atoms, int h, int max_atoms, float* __restrict__ dx,
                             int64_t ld_dx, float* __restrict__ dq, int64_t ld_dq) {
+  dcgc_griddep_wait();
   extern __shared__ float sh[];
   float* a_sh = sh;
   float* de_sh = sh + max_atoms;
@@ -280,6 +289,7 @@ __global__ void __launch_bounds__(256)
 lstm_step_bwd_kernel(const float* __restrict__ zg, int64_t ld_z, const float* __restrict__ c_in,
                      const float* __restrict__ dh, const float* __restrict__ dc_out, int64_t n, int h,
                      float* __restrict__ dz, int64_t ld_dz, float* __restrict__ dc_in) {
+  dcgc_griddep_wait();
   const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
   const int64_t r_ = t / h;
   const int c = (int)(t - r_ * h);
@@ -315,11 +325,11 @@ extern "C" int dcgc_pair_contract_fwd(const float* x, int64_t ld_x, const float*
   cudaStream_t st = (cudaStream_t)stream;
   DcgcProfScope prof_scope("dcgc_pair_contract_fwd", st);
   if (n_pf <= 8)
-    pair_contract_kernel<8><<<(unsigned)n_dst, kT, 0, st>>>(x, ld_x, pf, ld_pf, pair_ptr, pair_id, pair_src, n_pf, h, z, ld_z);
+    dcgc_launch(pair_contract_kernel<8>, (unsigned)n_dst, kT, 0, st, x, ld_x, pf, ld_pf, pair_ptr, pair_id, pair_src, n_pf, h, z, ld_z);
   else if (n_pf <= 16)
-    pair_contract_kernel<16><<<(unsigned)n_dst, kT, 0, st>>>(x, ld_x, pf, ld_pf, pair_ptr, pair_id, pair_src, n_pf, h, z, ld_z);
+    dcgc_launch(pair_contract_kernel<16>, (unsigned)n_dst, kT, 0, st, x, ld_x, pf, ld_pf, pair_ptr, pair_id, pair_src, n_pf, h, z, ld_z);
   else
-    pair_contract_kernel<32><<<(unsigned)n_dst, kT, 0, st>>>(x, ld_x, pf, ld_pf, pair_ptr, pair_id, pair_src, n_pf, h, z, ld_z);
+    dcgc_launch(pair_contract_kernel<32>, (unsigned)n_dst, kT, 0, st, x, ld_x, pf, ld_pf, pair_ptr, pair_id, pair_src, n_pf, h, z, ld_z);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_pair_contract_fwd");
   return DCGC_OK;
 }
@@ -331,7 +341,7 @@ extern "C" int dcgc_gru_gates_fwd(const float* g, int64_t ld_g, const float* bz,
                  "dcgc_gru_gates_fwd: bad sizes");
   if (n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(g && bz && br && hprev && z && hr, "dcgc_gru_gates_fwd: null pointer");
-  gru_gates_kernel<<<blocks_for(n * h, 256), 256, 0, (cudaStream_t)stream>>>(g, ld_g, bz, br, hprev, ld_h, n, h, z, ld_z,
+  dcgc_launch(gru_gates_kernel, blocks_for(n * h, 256), 256, 0, (cudaStream_t)stream, g, ld_g, bz, br, hprev, ld_h, n, h, z, ld_z,
                                                                              hr, ld_hr);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_gru_gates_fwd");
   return DCGC_OK;
@@ -344,7 +354,7 @@ extern "C" int dcgc_gru_out_fwd(const float* g, int64_t ld_g, const float* u, in
                  "dcgc_gru_out_fwd: bad sizes");
   if (n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(g && u && bh && z && x && out, "dcgc_gru_out_fwd: null pointer");
-  gru_out_kernel<<<blocks_for(n * h, 256), 256, 0, (cudaStream_t)stream>>>(g, ld_g, u, ld_u, bh, z, ld_z, x, ld_x, n, h,
+  dcgc_launch(gru_out_kernel, blocks_for(n * h, 256), 256, 0, (cudaStream_t)stream, g, ld_g, u, ld_u, bh, z, ld_z, x, ld_x, n, h,
                                                                            out, ld_out);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_gru_out_fwd");
   return DCGC_OK;
@@ -358,7 +368,7 @@ extern "C" int dcgc_setgather_attend_fwd(const float* x, int64_t ld_x, const flo
   DCGC_CHECK_ARG(max_atoms <= 12000, "dcgc_setgather_attend_fwd: molecules of more than 12000 atoms are not supported");
   if (n_mols == 0) return DCGC_OK;
   DCGC_CHECK_ARG(q && mol_ptr && qstar && (max_atoms == 0 || (x && mol_atoms)), "dcgc_setgather_attend_fwd: null pointer");
-  setgather_attend_kernel<<<(unsigned)n_mols, kT, (size_t)(max_atoms > 0 ? max_atoms : 1) * 4, (cudaStream_t)stream>>>(
+  dcgc_launch(setgather_attend_kernel, (unsigned)n_mols, kT, (size_t)(max_atoms > 0 ? max_atoms : 1) * 4, (cudaStream_t)stream, 
       x, ld_x, q, ld_q, mol_ptr, mol_atoms, h, qstar, ld_qs);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_setgather_attend_fwd");
   return DCGC_OK;
@@ -369,7 +379,7 @@ extern "C" int dcgc_lstm_step_fwd(const float* zg, int64_t ld_z, const float* c_
   DCGC_CHECK_ARG(n >= 0 && h > 0 && ld_z >= 4 * (int64_t)h, "dcgc_lstm_step_fwd: bad sizes");
   if (n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(zg && c_in && h_out && c_out, "dcgc_lstm_step_fwd: null pointer");
-  lstm_step_kernel<<<blocks_for(n * h, 256), 256, 0, (cudaStream_t)stream>>>(zg, ld_z, c_in, n, h, h_out, c_out);
+  dcgc_launch(lstm_step_kernel, blocks_for(n * h, 256), 256, 0, (cudaStream_t)stream, zg, ld_z, c_in, n, h, h_out, c_out);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_lstm_step_fwd");
   return DCGC_OK;
 }
@@ -386,11 +396,11 @@ extern "C" int dcgc_pair_contract_bwd_x(const float* dz, int64_t ld_z, const flo
   cudaStream_t st = (cudaStream_t)stream;
   DcgcProfScope prof_scope("dcgc_pair_contract_bwd_x", st);
   if (n_pf <= 8)
-    pair_contract_bwd_x_kernel<8><<<(unsigned)n_src, kT, 0, st>>>(dz, ld_z, pf, ld_pf, src_ptr, src_pair, pair_dst, n_pf, h, dx, ld_dx);
+    dcgc_launch(pair_contract_bwd_x_kernel<8>, (unsigned)n_src, kT, 0, st, dz, ld_z, pf, ld_pf, src_ptr, src_pair, pair_dst, n_pf, h, dx, ld_dx);
   else if (n_pf <= 16)
-    pair_contract_bwd_x_kernel<16><<<(unsigned)n_src, kT, 0, st>>>(dz, ld_z, pf, ld_pf, src_ptr, src_pair, pair_dst, n_pf, h, dx, ld_dx);
+    dcgc_launch(pair_contract_bwd_x_kernel<16>, (unsigned)n_src, kT, 0, st, dz, ld_z, pf, ld_pf, src_ptr, src_pair, pair_dst, n_pf, h, dx, ld_dx);
   else
-    pair_contract_bwd_x_kernel<32><<<(unsigned)n_src, kT, 0, st>>>(dz, ld_z, pf, ld_pf, src_ptr, src_pair, pair_dst, n_pf, h, dx, ld_dx);
+    dcgc_launch(pair_contract_bwd_x_kernel<32>, (unsigned)n_src, kT, 0, st, dz, ld_z, pf, ld_pf, src_ptr, src_pair, pair_dst, n_pf, h, dx, ld_dx);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_pair_contract_bwd_x");
   return DCGC_OK;
 }
@@ -403,7 +413,7 @@ extern "C" int dcgc_gru_out_bwd(const float* dout, int64_t ld_do, const float* g
                      ld_dz >= h && ld_dx >= h && ld_dp >= h, "dcgc_gru_out_bwd: bad sizes");
   if (n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(dout && g && u && bh && z && x && dzg && dx && dpre, "dcgc_gru_out_bwd: null pointer");
-  gru_out_bwd_kernel<<<blocks_for(n * h, 256), 256, 0, (cudaStream_t)stream>>>(dout, ld_do, g, ld_g, u, ld_u, bh, z, ld_z,
+  dcgc_launch(gru_out_bwd_kernel, blocks_for(n * h, 256), 256, 0, (cudaStream_t)stream, dout, ld_do, g, ld_g, u, ld_u, bh, z, ld_z,
                                                                                x, ld_x, n, h, dzg, ld_dz, dx, ld_dx, dpre,
                                                                                ld_dp);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_gru_out_bwd");
@@ -418,7 +428,7 @@ extern "C" int dcgc_gru_gates_bwd(const float* dzg, int64_t ld_dz, const float* 
                      ld_dg >= 3 * (int64_t)h && ld_dh >= h, "dcgc_gru_gates_bwd: bad sizes");
   if (n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(dzg && dhr && dpre && g && bz && br && hprev && dg && dh, "dcgc_gru_gates_bwd: null pointer");
-  gru_gates_bwd_kernel<<<blocks_for(n * h, 256), 256, 0, (cudaStream_t)stream>>>(dzg, ld_dz, dhr, ld_dhr, dpre, ld_dp, g,
+  dcgc_launch(gru_gates_bwd_kernel, blocks_for(n * h, 256), 256, 0, (cudaStream_t)stream, dzg, ld_dz, dhr, ld_dhr, dpre, ld_dp, g,
                                                                                  ld_g, bz, br, hprev, ld_h, n, h, dg,
                                                                                  ld_dg, dh, ld_dh);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_gru_gates_bwd");
@@ -436,7 +446,7 @@ extern "C" int dcgc_setgather_attend_bwd(const float* x, int64_t ld_x, const flo
   DCGC_CHECK_ARG(q && dqs && mol_ptr && dq && (max_atoms == 0 || (x && mol_atoms && dx)),
                  "dcgc_setgather_attend_bwd: null pointer");
   const int ma = max_atoms > 0 ? max_atoms : 1;
-  setgather_attend_bwd_kernel<<<(unsigned)n_mols, kT, (size_t)ma * 8, (cudaStream_t)stream>>>(
+  dcgc_launch(setgather_attend_bwd_kernel, (unsigned)n_mols, kT, (size_t)ma * 8, (cudaStream_t)stream, 
       x, ld_x, q, ld_q, dqs, ld_dqs, mol_ptr, mol_atoms, h, ma, dx, ld_dx, dq, ld_dq);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_setgather_attend_bwd");
   return DCGC_OK;
@@ -447,7 +457,7 @@ extern "C" int dcgc_lstm_step_bwd(const float* zg, int64_t ld_z, const float* c_
   DCGC_CHECK_ARG(n >= 0 && h > 0 && ld_z >= 4 * (int64_t)h && ld_dz >= 4 * (int64_t)h, "dcgc_lstm_step_bwd: bad sizes");
   if (n == 0) return DCGC_OK;
   DCGC_CHECK_ARG(zg && c_in && dz && dc_in, "dcgc_lstm_step_bwd: null pointer");
-  lstm_step_bwd_kernel<<<blocks_for(n * h, 256), 256, 0, (cudaStream_t)stream>>>(zg, ld_z, c_in, dh, dc_out, n, h, dz,
+  dcgc_launch(lstm_step_bwd_kernel, blocks_for(n * h, 256), 256, 0, (cudaStream_t)stream, zg, ld_z, c_in, dh, dc_out, n, h, dz,
                                                                                  ld_dz, dc_in);
   DCGC_CUDA_LAUNCH_CHECK("dcgc_lstm_step_bwd");
   return DCGC_OK;

@@ -1,5 +1,6 @@
 // Launch accounting and per-entry-point CUDA-event timing (bench.py: gpu_launches and the live
 // roofline measurement).  Events are recorded on the stream the kernel is launched on.
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -9,6 +10,11 @@
 #include "common.h"
 
 std::atomic<long long> g_dcgc_launches{0};
+
+bool dcgc_pdl_on() {
+  static const bool on = [] { const char* e = getenv("DCGC_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 
 namespace {
 std::mutex g_mu;
