@@ -186,6 +186,25 @@ __device__ __forceinline__ void prep_image_body(const ImgArgs& p, int bx, int nt
       }
     }
   }
+  if (p.trans) {
+    // (block-uniform) n-contiguous source: consecutive threads hold consecutive ROWS of the tile, 128 bytes apart —
+    // through shared memory, so that a thread stores one 32-byte sector of a row (chunks 2 q, 2 q + 1; the swizzle
+    // keeps the pair together) instead of 4 bytes of it
+    __shared__ __align__(16) float sh[kTiles][TC_BM][8 + 4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float h = term_hi<NT>(v[u]);
+      sh[0][r[u]][kl[u] & 7] = h;
+      if (NT == 3) sh[kTiles - 1][r[u]][kl[u] & 7] = tf32_lo(v[u], h);
+    }
+    __syncthreads();
+    const int row = threadIdx.x >> 1, c = threadIdx.x & 1;
+#pragma unroll
+    for (int t = 0; t < kTiles; ++t)
+      *reinterpret_cast<float4*>(reinterpret_cast<char*>(blk + t * TC_BM * TC_BK) + swz(row, 2 * quarter + c)) =
+          *reinterpret_cast<const float4*>(&sh[t][row][4 * c]);
+    return;
+  }
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const float h = term_hi<NT>(v[u]);
@@ -212,16 +231,20 @@ constexpr float kF16Scale = 16.f;
 constexpr float kF16Limit = 60000.f / kF16Scale;
 __device__ int g_f16_overflow = 0;
 __device__ __forceinline__ void prep_image_f16_body(const ImgArgs& p, int bx, int nt, int g) {
-  // one block = an eighth (1024 elements) of one [128 x 64] tile
-  const int ch = bx >> 3, part = bx & 7;
-  __half* blk = reinterpret_cast<__half*>(p.img) + (((int64_t)g * p.n_tiles + nt) * p.chunks + ch) * (2 * TC_BM * 64);
+  // one block = a quarter (128 rows x 16 K values) of one [128 x 64] tile.  Loads follow the source's contiguous
+  // dimension; the halves go through shared memory so that every thread then stores one whole 32-byte sector of a
+  // tile row (the first version stored single halves 128 bytes apart: 2 useful bytes per sector, 23 us for the seven
+  // images of a step, profiles/r6k_launches.md)
+  __shared__ __align__(16) __half sh[2][TC_BM][16 + 8];
+  const int ch = bx >> 2, part = bx & 3;
+  char* blk = reinterpret_cast<char*>(p.img) + (((int64_t)g * p.n_tiles + nt) * p.chunks + ch) * (int64_t)(2 * TC_BM * 64 * 2);
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int i = part * 1024 + u * 256 + threadIdx.x;
-    int r, kl;
-    if (p.trans) { r = i & (TC_BN - 1); kl = i >> 7; }     // source is n-contiguous
-    else { kl = i & 63; r = i >> 6; }                      // source is k-contiguous
-    const int nn = nt * TC_BN + r, kk = ch * 64 + kl;
+  for (int u = 0; u < 8; ++u) {
+    const int i = u * 256 + threadIdx.x;
+    int r, kq;
+    if (p.trans) { r = i & (TC_BN - 1); kq = i >> 7; }     // source is n-contiguous
+    else { kq = i & 15; r = i >> 4; }                      // source is k-contiguous
+    const int nn = nt * TC_BN + r, kk = ch * 64 + part * 16 + kq;
     float v = 0.f;
     if (nn < p.n) {
       if (p.trans) {
@@ -235,11 +258,17 @@ __device__ __forceinline__ void prep_image_f16_body(const ImgArgs& p, int bx, in
     }
     if (fabsf(v) > kF16Limit) g_f16_overflow = 1;
     const __half h = __float2half_rn(v * kF16Scale);
-    const __half l = __float2half_rn(fmaf(v, kF16Scale, -__half2float(h)));
-    const uint32_t o = (swz(r, kl >> 3) >> 1) + (kl & 7);      // half index inside the 16 KB tile
-    blk[o] = h;
-    blk[TC_BM * 64 + o] = l;
+    sh[0][r][kq] = h;
+    sh[1][r][kq] = __float2half_rn(fmaf(v, kF16Scale, -__half2float(h)));
   }
+  __syncthreads();
+  // thread -> (row, hi | lo): the two 16-byte chunks 2 part, 2 part + 1 of the row; the 128B swizzle XORs both with
+  // (row & 7), which keeps them inside one 32-byte sector
+  const int r = threadIdx.x >> 1, hl = threadIdx.x & 1;
+  char* tile = blk + hl * (TC_BM * 64 * 2);
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    *reinterpret_cast<uint4*>(tile + swz(r, 2 * part + c)) = *reinterpret_cast<const uint4*>(&sh[hl][r][8 * c]);
 }
 __global__ void __launch_bounds__(256) tc_prep_image_f16(const ImgArgs p) {
   dcgc_griddep_wait();
@@ -1938,7 +1967,7 @@ int launch_prep_f16(const float* w, int n_groups, int trans_w, int k1, int k2, i
   ia.n_tiles = sh.n_tiles_n; ia.chunks = sh.chunks;
   if (trans_w) { ia.src_ld = N; ia.src_group_stride = (int64_t)(k1 + k2) * N; }
   else { ia.src_ld = k1; ia.src_group_stride = (int64_t)N * k1; }
-  dim3 pgrid((unsigned)sh.chunks * 8, (unsigned)sh.n_tiles_n, (unsigned)n_groups);
+  dim3 pgrid((unsigned)sh.chunks * 4, (unsigned)sh.n_tiles_n, (unsigned)n_groups);
   dcgc_launch(tc_prep_image_f16, pgrid, 256, 0, st, ia);
   DCGC_CUDA_LAUNCH_CHECK("tc_prep_image_f16");
   return DCGC_OK;
@@ -1977,7 +2006,7 @@ int dcgc_tc_prep_weights_batch(int nt, const DcgcImgJob* jobs, int n_jobs, cudaS
       if (q.trans_w) { ia.src_ld = q.N; ia.src_group_stride = (int64_t)(q.k1 + q.k2) * q.N; }
       else { ia.src_ld = q.k1; ia.src_group_stride = (int64_t)q.N * q.k1; }
       b.f16[i] = q.f16 ? 1 : 0;
-      b.gx[i] = sh.chunks * (q.f16 ? 8 : 4);
+      b.gx[i] = sh.chunks * 4;
       b.gy[i] = sh.n_tiles_n;
       b.first_block[i] = blocks;
       blocks += b.gx[i] * b.gy[i] * q.n_groups;
