@@ -661,6 +661,8 @@ class GraphConvModel(object):
         # the chunked int8 upload, so it stays an experiment switch.
         self._fwd_events = None
         self._last_fwd_event = None
+        self._bn_steps_pending = 0
+        self.model.register_state_dict_pre_hook(self._flush_bn_counters)
         if self.device.type == "cuda" and os.environ.get("DCGC_H2D_PHASE", "none") == "bwd":
             self._fwd_events = []
             with torch.cuda.device(self.device):
@@ -927,6 +929,7 @@ class GraphConvModel(object):
         if self.model_dir and checkpoint_interval > 0:
             self.save_checkpoint(max_checkpoints_to_keep)
         logger.info("TIMING: model fitting took %0.3f s" % (time.time() - t0))
+        self._flush_bn_counters()
         _check_f16_range(self)
         return state["last"]
 
@@ -967,21 +970,24 @@ class GraphConvModel(object):
         if self._dp:
             from .parallel import world_size
             dp = world_size() > 1
-        # Per-slice exchange beside the backward pass, or ONE all-reduce after the step?  Measured (profiles/r5v_dp8.md):
-        # 2 GPUs 1.2151 against 1.2246 ms/step for the overlapped form, 8 GPUs 1.128 against 1.110 — NCCL's CTAs take
-        # SMs away from the persistent one-CTA-per-SM kernels of the backward pass (their displaced CTAs run as a tail),
-        # and four asynchronous calls per step cost the Python thread more than one.  Default: overlap on 2 ranks,
-        # one all-reduce above; DCGC_NO_OVERLAP=1 / DCGC_OVERLAP=1 force either.
+        # Per-slice exchange beside the backward pass, or ONE all-reduce after the step?  Measured: device-timed steps of
+        # 1.2151 against 1.2246 ms at 2 GPUs for the overlapped form and 1.128 against 1.110 at 8 (profiles/r5v_dp8.md:
+        # NCCL's CTAs take SMs away from the persistent one-CTA-per-SM kernels of the backward pass), but END TO END the
+        # four asynchronous collective calls cost the launching thread 0.62 ms per step against 0.15 for one call
+        # (scripts/e2e_trace_dp.py, 2 GPUs: 1.190 against 1.048 ms per step).  Default: one all-reduce;
+        # DCGC_OVERLAP=1 selects the per-slice form.
         if os.environ.get("DCGC_NO_OVERLAP", "0") == "1":
             overlap = False
         elif os.environ.get("DCGC_OVERLAP", "0") == "1":
             overlap = dp
         else:
-            from .parallel import world_size as _ws_
-            overlap = dp and _ws_() <= 2
+            overlap = False
         gev = self._dp_events() if overlap else None
+        tr = self._pipe_trace
+        t_0 = time.perf_counter() if tr is not None else 0.0
         loss = eng.train_step(topo, inputs[0], labels[0].contiguous(), w.contiguous() if w is not None else None,
                               int(inputs[3]), forward_event=fe, grad_events=gev)
+        t_1 = time.perf_counter() if tr is not None else 0.0
         if fe is not None:
             self._last_fwd_event = fe
         scale = 1.0
@@ -1007,10 +1013,26 @@ class GraphConvModel(object):
             for wk in works:
                 wk.wait()                    # stream-level: the training stream waits, the host does not
             scale = 1.0 / world_size()
+        t_2 = time.perf_counter() if tr is not None else 0.0
         eng.adam_step(scale)
+        t_3 = time.perf_counter() if tr is not None else 0.0
         if eng.cfg.batch_norm:
-            torch._foreach_add_([bn.num_batches_tracked for bn in self.model.batch_norms], 1)
+            # BatchNorm1d.num_batches_tracked: counted on the host, added to the buffers when somebody can see them
+            # (state_dict / the end of fit_generator) — a launch and 50 us of the launching thread per step otherwise
+            self._bn_steps_pending += 1
+        if tr is not None:
+            t_4 = time.perf_counter()
+            tr["step_c_call"] += t_1 - t_0
+            tr["step_allreduce"] += t_2 - t_1
+            tr["step_adam"] += t_3 - t_2
+            tr["step_bn_counters"] += t_4 - t_3
         return loss
+
+    def _flush_bn_counters(self, *unused):
+        n = self._bn_steps_pending
+        if n:
+            self._bn_steps_pending = 0
+            torch._foreach_add_([bn.num_batches_tracked for bn in self.model.batch_norms], n)
 
     def _dp_events(self):
         """Events of the gradient slices (one set per step in flight) and the communication stream, made on first use."""
@@ -1056,6 +1078,7 @@ class GraphConvModel(object):
             self.batch_size = bs
         loss = self._train_step(*self._prepare_batch(batch))
         self._global_step += 1
+        self._flush_bn_counters()
         return float(loss)
 
     # ------------------------------------------------------------------ inference
@@ -1222,6 +1245,7 @@ class GraphConvModel(object):
                 raise ValueError('No checkpoint found')
             checkpoint = cps[0]
         data = torch.load(checkpoint, map_location=self.device)
+        self._bn_steps_pending = 0                      # (the loaded counters replace whatever was pending)
         self.model.load_state_dict(data['model_state_dict'])
         opt = data['optimizer_state_dict']
         if self._engine is not None:
