@@ -6,8 +6,9 @@ bench.py::make_pool), B = 4096 — and the Tox21-shaped 12-task classification c
 against `oracle/graphconv_torch.py` evaluated in float64 and float32 on the host:
 
   * outputs and loss within 1e-5 (relative to the tensor scale),
-  * every gradient tensor, anchored on float64 with no flat slack (helpers.py): rms error and max error each
-    <= max(1e-5, 3 x the fp32 oracle's),
+  * every gradient tensor, anchored on float64 with no flat slack (helpers.py): rms error
+    <= max(1e-5, 3 x the fp32 oracle's), max error <= max(1e-5, 6 x the fp32 oracle's) (the oracle's own error depends
+    on the host it runs on, helpers.py),
   * the bf16-GEMM mode: outputs and loss within the north star's 2e-2.  Its GRADIENTS are not within 2e-2 per
     tensor and no kernel can make them: rounding every GEMM operand to bfloat16 perturbs the activations by ~1e-2,
     and the BatchNorm backward passes (differences of large sums) amplify that to 0.1 - 0.19 of a tensor's scale
