@@ -146,6 +146,9 @@ __device__ __forceinline__ void dcgc_griddep_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// the wait alone: for a kernel that itself WAITS FOR ANOTHER STREAM OR DEVICE (bn_sync_kernel) — the grid behind it must
+// not be placed on the SMs while it spins, or two ranks emulated on one device could starve each other
+__device__ __forceinline__ void dcgc_griddep_wait_only() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 bool dcgc_pdl_on();   // profile.cu
 template <typename... KArgs, typename... Args>
 inline void dcgc_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

@@ -282,7 +282,7 @@ bn_sync_kernel(const SyncArgs sy, const double* __restrict__ part, int n_chunks,
                float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_io,
                float* __restrict__ invstd_io, float* __restrict__ scale_io, float* __restrict__ shift_out,
                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
-  dcgc_griddep_wait();
+  dcgc_griddep_wait_only();     // (no early launch of the kernel behind this one: it waits for its peers below)
   const int t = threadIdx.x;
   const int slot = (int)(sy.seq & 1ull);
   const size_t row = 2 * (size_t)sy.cap + 2;
