@@ -28,14 +28,6 @@ constexpr int kT = 256;
 inline unsigned blocks_for(int64_t n) { return (unsigned)((n + kT - 1) / kT); }
 
 // all element-wise kernels work on [rows, width] matrices with width % 4 == 0 and 16-byte aligned rows
-__global__ void __launch_bounds__(kT) relu_copy_kernel(const float4* __restrict__ x, float4* __restrict__ y, int64_t n4) {
-  dcgc_griddep_wait();
-  const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
-  if (i >= n4) return;
-  float4 v = x[i];
-  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-  y[i] = v;
-}
 // h = relu(a + b)                                                   (layers.py:1632: act(input + W_h(message)))
 __global__ void __launch_bounds__(kT) add_relu_kernel(const float4* __restrict__ a, const float4* __restrict__ b,
                                                       float4* __restrict__ y, int64_t n4) {
@@ -54,17 +46,6 @@ __global__ void __launch_bounds__(kT) relu_mask_kernel(float4* __restrict__ g, c
   const float4 t = y[i];
   v.x = t.x > 0.f ? v.x : 0.f; v.y = t.y > 0.f ? v.y : 0.f; v.z = t.z > 0.f ? v.z : 0.f; v.w = t.w > 0.f ? v.w : 0.f;
   g[i] = v;
-}
-// ds += (inp > 0) ? dm : 0     (gradient of `input`: the residual path + the message path through act(input))
-__global__ void __launch_bounds__(kT) mask_add_kernel(float4* __restrict__ ds, const float4* __restrict__ dm,
-                                                      const float4* __restrict__ inp, int64_t n4) {
-  dcgc_griddep_wait();
-  const int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x;
-  if (i >= n4) return;
-  float4 v = ds[i];
-  const float4 m = dm[i], t = inp[i];
-  v.x += t.x > 0.f ? m.x : 0.f; v.y += t.y > 0.f ? m.y : 0.f; v.z += t.z > 0.f ? m.z : 0.f; v.w += t.w > 0.f ? m.w : 0.f;
-  ds[i] = v;
 }
 // CSR gather-sum with the element-wise neighbours of the D-MPNN step folded in (one thread per 16-byte column group
 // of one output row, entries summed in index order exactly as dcgc_gather_sum does):
@@ -451,7 +432,7 @@ extern "C" int dcgc_dmpnn_model_train_step(const dcgc_dmpnn_model_config* cfg, c
   const int H = cfg->hidden, fa = cfg->atom_fdim, fi = cfg->atom_fdim + cfg->bond_fdim, mode = cfg->gemm_mode;
   const int L = cfg->ffn_layers, T = cfg->n_out;
   const int64_t R = t->n_rows, A = t->n_atoms, B = t->n_mols;
-  const int64_t r4 = R * H / 4, a4 = A * H / 4;
+  const int64_t a4 = A * H / 4;
 
   // ---------------- forward (the last linear writes into x[L-1], [B, pad4(T)])
   RET_IF(build_images(cfg, lo, params, w, true, st));

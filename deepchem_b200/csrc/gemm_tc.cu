@@ -1014,7 +1014,6 @@ tc_gemm_kernel_v6(const TcArgs3 q, const __grid_constant__ CUtensorMap map1, con
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
-  constexpr int NT = 3;
   constexpr int SA = V6_A_STAGES, SW = V6_W_STAGES;
   constexpr int A_STAGE_BYTES = 2 * TC_TILE_BYTES;          // two 32-float sub-tiles = 64 K values per row
   constexpr int W_STAGE_BYTES = 2 * TC_TILE_BYTES;          // fp16 hi | lo tiles of [128 x 64]

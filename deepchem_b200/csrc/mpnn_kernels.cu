@@ -235,7 +235,6 @@ setgather_attend_bwd_kernel(const float* __restrict__ x, int64_t ld_x, const flo
   extern __shared__ float sh[];
   float* a_sh = sh;
   float* de_sh = sh + max_atoms;
-  __shared__ float red[2];
   const int g = blockIdx.x;
   const int t0 = __ldg(mol_ptr + g), t1 = __ldg(mol_ptr + g + 1);
   const int n = t1 - t0;
