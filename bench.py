@@ -516,6 +516,8 @@ def run_ours(args):
     # the forward GEMMs ran with fp16 operand halves: say whether any operand left fp16's range (0 = none did)
     from deepchem_b200 import _lib as _dl
     line["config"]["f16_overflow_flag"] = int(_dl.lib().dcgc_tc_f16_overflow())
+    line["config"]["kernel_launches"] = ("programmatic dependent launch between the kernels of a step (DCGC_PDL=%s)"
+                                         % os.environ.get("DCGC_PDL", "1"))
     print(json.dumps(line), flush=True)
 
 
