@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "deepchem_b200", "libdcgc.so")
 WANT = ("UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "STTM", "UTCBAR", "UTCCP", "SYNCS", "LDGSTS", "REDUX",
-        "ATOM", "RED.")
+        "ATOM", "RED.", "ACQBULK", "PREEXIT")
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 fn, counts = None, collections.OrderedDict()
 for line in out.splitlines():
@@ -21,7 +21,7 @@ for line in out.splitlines():
         continue
     if fn is None:
         continue
-    m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]+)", line)
+    m = re.search(r"/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]+)", line)
     if not m:
         continue
     op = m.group(1)
@@ -33,7 +33,8 @@ dem = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, t
 print("# SASS of `deepchem_b200/libdcgc.so` (sm_100a): tensor-core / tensor-memory / TMA instructions per kernel\n")
 print("`python scripts/sass_summary.py` (cuobjdump -sass, counted per kernel; kernels without any of them are omitted). "
       "UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG = cp.async.bulk.tensor (tensor-map TMA load), "
-      "UBLKCP = cp.async.bulk, UTCBAR = tcgen05.commit, SYNCS = mbarrier operations; ATOM / RED = atomics (none on float data).\n")
+      "UBLKCP = cp.async.bulk, UTCBAR = tcgen05.commit, SYNCS = mbarrier operations; ATOM / RED = atomics (none on float data); ACQBULK / PREEXIT = griddepcontrol.wait / "
+      "launch_dependents (programmatic dependent launch: every kernel has both).\n")
 print("| kernel | instructions |")
 print("|---|---|")
 for n, d in zip(names, dem):
